@@ -1,0 +1,218 @@
+/*
+ * mmdyn_b200 — C ABI of the B200-native (sm_100a) kernels behind the cnn-vae / cnn-mvae
+ * training + inference step of SAIC-MONTREAL/multimodal-dynamics.
+ *
+ * The reference has no FFI of its own (it is 100 % Python calling torch ops), so
+ * every entry point below cites the torch call site in the reference that it replaces
+ * (paths relative to the reference root, mmdyn/pytorch/...).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all data pointers are DEVICE pointers unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - no allocation, no synchronisation, no ownership transfer inside any call;
+ *   - return 0 on success, <0 on error (mmdyn_last_error() gives the message); never throws;
+ *   - "op" tensors are IEEE fp16 (10-bit mantissa, = TF32 operand precision) in NHWC layout,
+ *     accumulators / statistics / losses / optimizer state are fp32.
+ */
+#ifndef MMDYN_B200_H_
+#define MMDYN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMDYN_MAX_TAPS 16
+#define MMDYN_MAX_PHASES 4
+
+/* --- library ------------------------------------------------------------------------------- */
+const char* mmdyn_last_error(void);
+int mmdyn_version(void);
+/* number of kernels launched by this library in this process since load (bench gpu_launches) */
+long long mmdyn_launch_count(void);
+/* one-time per device: raises the dynamic shared memory limits of the tcgen05 kernels */
+int mmdyn_init(int device);
+
+/* --- implicit-GEMM convolution / transposed convolution / linear (tcgen05 + TMEM + TMA) ------
+ * replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward and their input-gradients:
+ *   models/vae.py:198-216 (encoder convs, fc, heads), :263-277 (decoder upsample + deconvs),
+ *   and the autograd backward of the same (problems/problems.py:153 loss.backward()).
+ *
+ *   out[row(m), n] = sum_{tap t, channel c} A[gather(m, t), c] * W[phase][n][t*Cin + c] (+ bias[n])
+ *
+ * rows m enumerate a "virtual grid" (image, yv, xv); tap t reads input pixel
+ * (yv*s_in + dy[t], xv*s_in + dx[t]) (zero outside the image); the result goes to output pixel
+ * (yv*s_out + off_y[phase], xv*s_out + off_x[phase]).  This one form covers stride-2 convs,
+ * sub-pixel phases of stride-2 transposed convs, stride-1 k4 (5<->8) layers, linears (one tap)
+ * and all of their dgrads.
+ */
+typedef struct mmdyn_igemm_desc {
+  const void* A;        /* fp16 NHWC gathered operand                                        */
+  const void* W;        /* fp16 packed weights [n_phases*N][ntaps*Cin], K contiguous (TMA)    */
+  void* out;            /* see out_mode                                                        */
+  const float* bias;    /* [N] or NULL                                                         */
+  int32_t n_img;        /* images (rows of the virtual grid = n_img*P)                         */
+  int32_t P;            /* virtual pixels per image = OYv*OXv                                  */
+  int32_t OXv;          /* virtual grid width                                                  */
+  int32_t IH, IW;       /* input spatial size                                                  */
+  int32_t a_pix_stride; /* elements between consecutive input pixels (>= Cin)                  */
+  int32_t Cin;          /* channels per tap (multiple of 8); ntaps*Cin multiple of 64          */
+  int32_t s_in;         /* input stride                                                        */
+  int32_t ntaps;
+  int32_t n_phases;
+  int8_t tap_dy[MMDYN_MAX_PHASES][MMDYN_MAX_TAPS];
+  int8_t tap_dx[MMDYN_MAX_PHASES][MMDYN_MAX_TAPS];
+  int32_t N;            /* output channels (multiple of block_n)                               */
+  int32_t block_n;      /* 16, 32, 64, 128 or 256                                              */
+  int32_t ksplit;       /* >1: split K across CTAs, out_mode must be 2 (atomic fp32)           */
+  int32_t row_mode;     /* 0: tile = 128 consecutive rows (image-major);
+                           1: tile = one virtual pixel x 128 images, invalid taps skipped      */
+  int32_t out_mode;     /* 0: fp16 rows, 1: fp32 rows, 2: fp32 rows atomicAdd,
+                           3: fp32 NCHW planes from merged 2x2 sub-pixel phases (N = 16, 12 used) */
+  int32_t OH, OW;       /* output spatial size                                                 */
+  int32_t s_out;
+  int32_t off_y[MMDYN_MAX_PHASES], off_x[MMDYN_MAX_PHASES];
+  int32_t ldc;          /* elements between consecutive output pixels                          */
+} mmdyn_igemm_desc;
+int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream);
+
+/* --- weight gradient (tcgen05, both operands MN-major) ---------------------------------------
+ * replaces the weight-gradient half of autograd for the same layers (problems/problems.py:153).
+ *   dW[n][t*Cg + c] += scale * sum_m Nat[m][n] * G[gather(m, t), c]
+ * `Nat` is read in natural row order (rows = virtual grid), `G` is gathered with the taps.
+ */
+typedef struct mmdyn_wgrad_desc {
+  const void* G;        /* fp16 NHWC gathered operand, Cg channels per tap                     */
+  const void* Nat;      /* fp16 [n_img*P][nat_stride] natural-order operand                    */
+  float* dW;            /* fp32 [Cn][ntaps*Cg], accumulated with atomics (caller zeroes)       */
+  int32_t n_img, P, OXv, IH, IW;
+  int32_t g_pix_stride; /* elements between consecutive pixels of G                            */
+  int32_t Cg;           /* channels per tap of G (multiple of 8), ntaps*Cg multiple of 128     */
+  int32_t s_in, ntaps;
+  int8_t tap_dy[MMDYN_MAX_TAPS];
+  int8_t tap_dx[MMDYN_MAX_TAPS];
+  int32_t Cn;           /* channels of Nat used (16, 32, or multiple of 64; <=256 per launch)  */
+  int32_t nat_stride;   /* elements between consecutive rows of Nat                            */
+  int32_t ldw;          /* row pitch of dW in elements (>= ntaps*Cg)                           */
+  int32_t row_splits;   /* CTAs along the reduction                                            */
+  float scale;
+} mmdyn_wgrad_desc;
+int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream);
+
+/* --- first encoder layer: Conv2d(3,32,4,2,1) on the fp32 NCHW input ---------------------------
+ * replaces vae.py:198 forward and its weight gradient (the input needs no gradient).
+ * W is the fp16 packed [32][64] matrix (K order (ci,kh,kw), 48 used).  out: fp16 NHWC (B,32,32,32).
+ */
+int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, int n_img, void* stream);
+int mmdyn_conv1_wgrad(const float* x_nchw, const void* dRaw, float* dW /*[32][48]*/, int n_img,
+                      float scale, int row_splits, void* stream);
+
+/* --- grouped BatchNorm2d (training statistics) + Swish ----------------------------------------
+ * replaces nn.BatchNorm2d + Swish, vae.py:201-208, 269-276, 331-334, forward and backward.
+ * Tensors are [G groups][rows_per_group][C] fp16 (NHWC flattened); every group (= one
+ * sub-sampled MVAE pass, problems.py:478-529) has its own batch statistics.
+ */
+int mmdyn_bn_stats(const void* x, float* sums /*[G][C][2] zeroed*/, int G, int rows_per_group,
+                   int C, void* stream);
+/* mean/invstd -> scale/shift (a = gamma*invstd, b = beta - mean*a); running stats updated once
+ * per group in group order with `momentum`, unbiased variance (torch semantics). */
+int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* ab /*[G][C][2]*/,
+                      float* mean_invstd /*[G][C][2]*/, float* running_mean, float* running_var,
+                      int G, int rows_per_group, int C, float eps, float momentum, void* stream);
+/* y = swish(a*x + b); ab == NULL means identity affine (plain Swish) */
+int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_per_group, int C,
+                       void* stream);
+/* dU = dY * swish'(a*x+b) written over dY; sums2[g][c] = {sum dU, sum dU*xhat} (zeroed by caller).
+ * ab == NULL: identity affine, no sums (dU is then already the gradient w.r.t. x). */
+int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const float* mean_invstd, void* dY,
+                              float* sums2, int G, int rows_per_group, int C, void* stream);
+/* dX = a*(dU - mean(dU) - xhat*mean(dU*xhat)) in place over dU; dgamma += sum dU*xhat,
+ * dbeta += sum dU (summed over groups, times grad_unscale) */
+int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
+                       void* dU, float* dgamma, float* dbeta, int G, int rows_per_group, int C,
+                       float grad_unscale, void* stream);
+
+/* --- fc tail: bias + Swish + Dropout mask (vae.py:210-214) ------------------------------------
+ * raw [B][C] fp32 (igemm output incl. bias); for each of n_masks masks (fp32, values 0 or 1/(1-p),
+ * or NULL = no dropout) writes h[m][B][C] fp16 = swish(raw) * mask_m.  Backward: dRaw (fp16) =
+ * swish'(raw) * sum_m mask_m * dH[m]. */
+int mmdyn_swish_dropout_fwd(const float* raw, const float* const* masks, void* h, int n_masks,
+                            int B, int C, void* stream);
+int mmdyn_swish_dropout_bwd(const float* raw, const float* const* masks, const float* dH,
+                            void* dRaw, int n_masks, int B, int C, void* stream);
+
+/* --- ProductOfExperts + reparametrisation + KL (vae.py:52-61, 139-157, 311-328; problems.py:406,429)
+ * experts: up to 3 (mu_e, logvar_e) pairs [B][D] fp32 with row stride `ld`; the prior expert
+ * N(0, I) is implicit when use_prior != 0 (MVAE); with use_prior == 0 and one expert this is the
+ * plain VAE posterior (vae.py:84-85).  Outputs: mu, logvar (posterior), z = eps*exp(0.5 logvar)+mu
+ * (fp32 [B][D]) and zh / zh2 (optional fp16 copies of z: the operand rows of up to two decoders); kl_sum += -0.5*sum(1+lv-mu^2-e^lv).
+ */
+int mmdyn_poe_fwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
+                  int ld, const float* eps, float* mu, float* lv, float* z, void* zh, void* zh2,
+                  float* kl_sum, int B, int D, void* stream);
+/* backward: dmu_e/dlv_e[e] (+)= grads through z and KL (kl_coef = kl_weight * grad scale);
+ * dz[0..2]: up to three (nullable) fp32 [B][D] gradients w.r.t. z, one per decoder, summed here;
+ * accumulate != 0 adds into dmu_e/dlv_e (row stride ld_out) */
+int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
+                  int ld, const float* eps, const float* const* dz, float kl_coef, float* const* dmu_e,
+                  float* const* dlv_e, int ld_out, int accumulate, int B, int D, void* stream);
+
+/* --- reconstruction losses (problems.py:409-413, 431-449, 499-503, 535) -----------------------
+ * BCE-with-logits, reduction 'sum' into loss_sum[0]; dlogits (fp16 NHWC, 8 channels per pixel,
+ * 3 used) = gscale*(sigmoid(x) - t)*m.  mask (optional, NCHW fp32) multiplies logits and targets
+ * as the reference does.  logits/target: NCHW fp32 (n,3,H,W). */
+int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
+                     void* dlogits_nhwc8, float gscale, int n, int HW, void* stream);
+/* MSE 'sum' * multiplier for the pose vectors: loss_sum += mult*sum (r-t)^2; dr = gscale*2*mult*(r-t) */
+int mmdyn_mse(const float* recon, const float* target, float* loss_sum, float* drecon, float mult,
+              float gscale, int n, void* stream);
+
+/* --- fp32 linear layers of the pose MLP expert (vae.py:14-19, 118-123, 219-222, 282-283) -------
+ * y = act(x W^T + b), W [N][K] row-major (torch layout), act: 0 identity, 1 ReLU. */
+int mmdyn_linear_f32_fwd(const float* x, const float* W, const float* b, float* y, int M, int N,
+                         int K, int ldx, int ldy, int act, void* stream);
+/* dx (=|+=) (dy * act'(y)) W ; dW += scale * (dy*act')^T x ; db += scale * colsum(dy*act').
+ * dy_act (scratch, [M][N]) receives dy*act'(y); any of dx / dW / db may be NULL;
+ * dx_accumulate != 0 adds into dx (several decoders feed the same latent). */
+int mmdyn_linear_f32_bwd(const float* x, const float* W, const float* y, const float* dy,
+                         float* dy_act, float* dx, float* dW, float* db, int M, int N, int K,
+                         int ldx, int ldy, int lddx, int act, int dx_accumulate, float scale,
+                         void* stream);
+
+/* --- misc reductions / packing ----------------------------------------------------------------
+ * column sums of an fp32 [M][N] matrix (bias gradients): out[n] += scale*sum_m x[m][n] */
+int mmdyn_colsum_f32(const float* x, float* out, int M, int N, int ld, float scale, void* stream);
+/* same for an fp16 matrix (N multiple of 8, 16-byte aligned rows) */
+int mmdyn_colsum_f16(const void* x, float* out, int M, int N, int ld, float scale, void* stream);
+/* gather-pack fp32 parameters into an fp16 operand matrix: dst[i] = idx[i] < 0 ? 0 : src[idx[i]] */
+int mmdyn_pack_f16(const float* src, const int32_t* idx, void* dst, long long n, void* stream);
+/* fp32 gather (packed bias copies): dst[i] = idx[i] < 0 ? 0 : src[idx[i]] */
+int mmdyn_gather_f32(const float* src, const int32_t* idx, float* dst, long long n, void* stream);
+/* scatter-add a packed fp32 gradient back to parameter layout: dst[idx[i]] += src[i] (idx>=0);
+ * each parameter element appears at most once in idx */
+int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float* dst, long long n,
+                         void* stream);
+int mmdyn_f32_to_f16(const float* src, void* dst, long long n, void* stream);
+
+/* --- fused Adam over a flat fp32 arena (problems.py:138,155; torch.optim.Adam defaults) --------
+ * p, g, m, v: [n] fp32.  step_count is the 1-based step AFTER this update (bias correction).
+ * g is multiplied by gscale first (e.g. 1/world_size after a sum-allreduce). */
+int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step_count,
+                    float gscale, void* stream);
+/* SGD with momentum (problems.py:132-136): buf = mom*buf + (g + wd*p); p -= lr*buf */
+int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n, float lr, float momentum,
+                   float weight_decay, int first_step, float gscale, void* stream);
+
+/* --- deterministic device RNG (Philox4x32-10) for eps / dropout masks --------------------------
+ * replaces torch.randn (vae.py:58) and nn.Dropout's mask (vae.py:213) on the fast path */
+int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset, void* stream);
+int mmdyn_fill_dropout_mask(float* out, long long n, float p_drop, uint64_t seed, uint64_t offset,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDYN_B200_H_ */

@@ -1,0 +1,927 @@
+// HBM-bound kernels of the cnn-vae / cnn-mvae step: grouped BatchNorm statistics, BN+Swish
+// forward/backward, fc tail (Swish + Dropout), ProductOfExperts + reparametrisation + KL,
+// BCE / MSE reconstruction losses, weight packing, fused Adam / SGD, Philox RNG.
+//
+// All of them are coalesced, 16-byte vectorised where the layout allows, reduce with warp
+// shuffles -> shared memory -> one atomic per block and channel, and keep fp32 math throughout
+// (fp16 is a storage format for activations only).
+//
+// Reference semantics: mmdyn/pytorch/models/vae.py:52-61, 201-214, 269-276, 311-334 and
+// mmdyn/pytorch/problems/problems.py:130-138, 401-458.
+#include "common.cuh"
+#include "../../include/mmdyn_b200.h"
+
+#include <atomic>
+
+namespace mmdyn {
+extern std::atomic<long long> g_launch_count;
+
+namespace {
+
+#define LAUNCHED()                                            \
+  do {                                                        \
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);   \
+    MMDYN_CHECK_CUDA(cudaGetLastError());                     \
+  } while (0)
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+constexpr int RED_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm statistics: per (group, channel) sum and sum of squares over rows.
+// grid = (chunks, G); thread -> (8-channel vector, row lane); block partials -> atomics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS)
+bn_stats_kernel(const __half* __restrict__ x, float* __restrict__ sums, int rows_per_group, int C,
+                int rows_per_chunk) {
+  extern __shared__ float red[];  // [row_lanes][C][2]
+  const int vpr = C >> 3;
+  const int row_lanes = RED_THREADS / vpr;
+  const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+  const int g = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(rows_per_group, r_begin + rows_per_chunk);
+  const __half* xg = x + static_cast<long long>(g) * rows_per_group * C;
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.0f;
+  if (rl < row_lanes) {
+    for (int r = r_begin + rl; r < r_end; r += row_lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(xg + static_cast<long long>(r) * C + vec * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        ss[i] = fmaf(f[i], f[i], ss[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[(rl * C + vec * 8 + i) * 2] = s[i];
+      red[(rl * C + vec * 8 + i) * 2 + 1] = ss[i];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * 2; idx += RED_THREADS) {
+    float a = 0.0f;
+    for (int l = 0; l < row_lanes; ++l) a += red[l * C * 2 + idx];
+    atomicAdd(sums + static_cast<long long>(g) * C * 2 + idx, a);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ ab,
+                                   float* __restrict__ mean_invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int G, int n, int C, float eps,
+                                   float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv_n = 1.0f / static_cast<float>(n);
+  const float unbias = n > 1 ? static_cast<float>(n) / static_cast<float>(n - 1) : 1.0f;
+  float rm = running_mean ? running_mean[c] : 0.0f;
+  float rv = running_var ? running_var[c] : 0.0f;
+  const float ga = gamma[c], be = beta[c];
+  for (int g = 0; g < G; ++g) {
+    const float s = sums[(g * C + c) * 2], ss = sums[(g * C + c) * 2 + 1];
+    const float mean = s * inv_n;
+    const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
+    const float invstd = rsqrtf(var + eps);
+    const float a = ga * invstd;
+    ab[(g * C + c) * 2] = a;
+    ab[(g * C + c) * 2 + 1] = be - mean * a;
+    mean_invstd[(g * C + c) * 2] = mean;
+    mean_invstd[(g * C + c) * 2 + 1] = invstd;
+    rm = (1.0f - momentum) * rm + momentum * mean;
+    rv = (1.0f - momentum) * rv + momentum * var * unbias;
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+// y = swish(a*x + b), 8 channels per thread
+__global__ void __launch_bounds__(256)
+bn_swish_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
+                    long long n_vec, int rows_per_group, int C) {
+  const int vpr = C >> 3;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = v / vpr;
+    const int c0 = static_cast<int>(v - row * vpr) * 8;
+    float f[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[v], f);
+    if (ab) {
+      const int g = static_cast<int>(row / rows_per_group);
+      const float4* p = reinterpret_cast<const float4*>(ab + (static_cast<long long>(g) * C + c0) * 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = __ldg(p + q);
+        f[2 * q] = swishf_(fmaf(t.x, f[2 * q], t.y));
+        f[2 * q + 1] = swishf_(fmaf(t.z, f[2 * q + 1], t.w));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = swishf_(f[i]);
+    }
+    reinterpret_cast<uint4*>(y)[v] = pack8(f);
+  }
+}
+
+// dU = dY * swish'(a*x+b) in place; sums2[g][c] = {sum dU, sum dU * xhat}
+__global__ void __launch_bounds__(RED_THREADS)
+bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
+                           const float* __restrict__ mean_invstd, __half* __restrict__ dY,
+                           float* __restrict__ sums2, int rows_per_group, int C, int rows_per_chunk) {
+  extern __shared__ float red[];
+  const int vpr = C >> 3;
+  const int row_lanes = RED_THREADS / vpr;
+  const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+  const int g = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(rows_per_group, r_begin + rows_per_chunk);
+  const long long gbase = static_cast<long long>(g) * rows_per_group * C;
+  float a[8], b[8], mean[8], invstd[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = vec * 8 + i;
+    a[i] = ab[(g * C + c) * 2];
+    b[i] = ab[(g * C + c) * 2 + 1];
+    mean[i] = mean_invstd[(g * C + c) * 2];
+    invstd[i] = mean_invstd[(g * C + c) * 2 + 1];
+    s1[i] = s2[i] = 0.0f;
+  }
+  if (rl < row_lanes) {
+    for (int r = r_begin + rl; r < r_end; r += row_lanes) {
+      const long long off = gbase + static_cast<long long>(r) * C + vec * 8;
+      float fx[8], fd[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + off), fx);
+      unpack8(*reinterpret_cast<const uint4*>(dY + off), fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(a[i], fx[i], b[i]);
+        const float du = fd[i] * swish_gradf_(u);
+        fd[i] = du;
+        s1[i] += du;
+        s2[i] = fmaf(du, (fx[i] - mean[i]) * invstd[i], s2[i]);
+      }
+      *reinterpret_cast<uint4*>(dY + off) = pack8(fd);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[(rl * C + vec * 8 + i) * 2] = s1[i];
+      red[(rl * C + vec * 8 + i) * 2 + 1] = s2[i];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * 2; idx += RED_THREADS) {
+    float acc = 0.0f;
+    for (int l = 0; l < row_lanes; ++l) acc += red[l * C * 2 + idx];
+    atomicAdd(sums2 + static_cast<long long>(g) * C * 2 + idx, acc);
+  }
+}
+
+// plain Swish backward in place: dX = dY * swish'(x)
+__global__ void __launch_bounds__(256)
+swish_bwd_kernel(const __half* __restrict__ x, __half* __restrict__ dY, long long n_vec) {
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float fx[8], fd[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[v], fx);
+    unpack8(reinterpret_cast<const uint4*>(dY)[v], fd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fd[i] *= swish_gradf_(fx[i]);
+    reinterpret_cast<uint4*>(dY)[v] = pack8(fd);
+  }
+}
+
+// dX = a * (dU - mean(dU) - xhat * mean(dU * xhat)) in place
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
+                    const float* __restrict__ mean_invstd, const float* __restrict__ sums2,
+                    __half* __restrict__ dU, long long n_vec, int rows_per_group, int C) {
+  const int vpr = C >> 3;
+  const float inv_n = 1.0f / static_cast<float>(rows_per_group);
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = v / vpr;
+    const int c0 = static_cast<int>(v - row * vpr) * 8;
+    const int g = static_cast<int>(row / rows_per_group);
+    float fx[8], fd[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[v], fx);
+    unpack8(reinterpret_cast<const uint4*>(dU)[v], fd);
+    const long long pb = (static_cast<long long>(g) * C + c0) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = __ldg(ab + pb + 2 * i);
+      const float mean = __ldg(mean_invstd + pb + 2 * i), invstd = __ldg(mean_invstd + pb + 2 * i + 1);
+      const float m1 = __ldg(sums2 + pb + 2 * i) * inv_n, m2 = __ldg(sums2 + pb + 2 * i + 1) * inv_n;
+      const float xhat = (fx[i] - mean) * invstd;
+      fd[i] = a * (fd[i] - m1 - xhat * m2);
+    }
+    reinterpret_cast<uint4*>(dU)[v] = pack8(fd);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const float* __restrict__ sums2, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int G, int C, float unscale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int g = 0; g < G; ++g) {
+    s1 += sums2[(g * C + c) * 2];
+    s2 += sums2[(g * C + c) * 2 + 1];
+  }
+  dgamma[c] += unscale * s2;
+  dbeta[c] += unscale * s1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fc tail
+// ---------------------------------------------------------------------------------------------
+struct MaskPtrs {
+  const float* p[8];
+};
+
+__global__ void __launch_bounds__(256)
+swish_dropout_fwd_kernel(const float* __restrict__ raw, MaskPtrs masks, __half* __restrict__ h,
+                         int n_masks, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float s = swishf_(raw[i]);
+    for (int m = 0; m < n_masks; ++m) {
+      const float k = masks.p[m] ? masks.p[m][i] : 1.0f;
+      h[static_cast<long long>(m) * n + i] = __float2half_rn(s * k);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swish_dropout_bwd_kernel(const float* __restrict__ raw, MaskPtrs masks, const float* __restrict__ dH,
+                         __half* __restrict__ dRaw, int n_masks, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.0f;
+    for (int m = 0; m < n_masks; ++m) {
+      const float k = masks.p[m] ? masks.p[m][i] : 1.0f;
+      acc = fmaf(k, dH[static_cast<long long>(m) * n + i], acc);
+    }
+    dRaw[i] = __float2half_rn(acc * swish_gradf_(raw[i]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ProductOfExperts + reparametrisation + KL
+// ---------------------------------------------------------------------------------------------
+struct ExpertPtrs {
+  const float* mu[3];
+  const float* lv[3];
+  float* dmu[3];
+  float* dlv[3];
+  const float* dz[3];
+};
+constexpr float POE_EPS = 1e-8f;
+
+__global__ void __launch_bounds__(256)
+poe_fwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
+               float* __restrict__ mu_o, float* __restrict__ lv_o, float* __restrict__ z_o,
+               __half* __restrict__ zh_o, __half* __restrict__ zh2_o, float* __restrict__ kl_sum, int B, int D) {
+  const long long n = static_cast<long long>(B) * D;
+  float kl = 0.0f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / D), col = static_cast<int>(i - static_cast<long long>(row) * D);
+    const long long ei = static_cast<long long>(row) * ld + col;
+    float mu, lv;
+    if (!use_prior && n_experts == 1) {
+      mu = ex.mu[0][ei];
+      lv = ex.lv[0][ei];
+    } else {
+      // vae.py:311-318 — eps is added twice on the way in and once on the way out
+      float st = 0.0f, sm = 0.0f;
+      if (use_prior) {
+        const float t0 = 1.0f / ((1.0f + POE_EPS) + POE_EPS);
+        st = t0;  // mu_0 = 0
+      }
+      for (int e = 0; e < n_experts; ++e) {
+        const float var = expf(ex.lv[e][ei]) + POE_EPS;
+        const float t = 1.0f / (var + POE_EPS);
+        st += t;
+        sm = fmaf(ex.mu[e][ei], t, sm);
+      }
+      mu = sm / st;
+      lv = logf(1.0f / st + POE_EPS);
+    }
+    const float std = expf(0.5f * lv);
+    const float z = fmaf(eps[i], std, mu);
+    mu_o[i] = mu;
+    lv_o[i] = lv;
+    z_o[i] = z;
+    if (zh_o) zh_o[i] = __float2half_rn(z);
+    if (zh2_o) zh2_o[i] = __float2half_rn(z);
+    kl += 1.0f + lv - mu * mu - expf(lv);
+  }
+  kl = warp_sum(kl);
+  __shared__ float wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += wsum[w];
+    atomicAdd(kl_sum, -0.5f * t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
+               float kl_coef, int ld_out, int accumulate, int B, int D) {
+  const long long n = static_cast<long long>(B) * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / D), col = static_cast<int>(i - static_cast<long long>(row) * D);
+    const long long ei = static_cast<long long>(row) * ld + col;
+    const long long oi = static_cast<long long>(row) * ld_out + col;
+    float g = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (ex.dz[q]) g += ex.dz[q][i];
+    if (!use_prior && n_experts == 1) {
+      const float mu = ex.mu[0][ei], lv = ex.lv[0][ei];
+      const float dmu = g + kl_coef * mu;
+      const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f);
+      if (accumulate) {
+        ex.dmu[0][oi] += dmu;
+        ex.dlv[0][oi] += dlv;
+      } else {
+        ex.dmu[0][oi] = dmu;
+        ex.dlv[0][oi] = dlv;
+      }
+      continue;
+    }
+    float st = 0.0f, sm = 0.0f, t_e[3], elv[3];
+    if (use_prior) st = 1.0f / ((1.0f + POE_EPS) + POE_EPS);
+    for (int e = 0; e < n_experts; ++e) {
+      elv[e] = expf(ex.lv[e][ei]);
+      t_e[e] = 1.0f / ((elv[e] + POE_EPS) + POE_EPS);
+      st += t_e[e];
+      sm = fmaf(ex.mu[e][ei], t_e[e], sm);
+    }
+    const float mu = sm / st;
+    const float pvar = 1.0f / st;
+    const float lv = logf(pvar + POE_EPS);
+    const float dmu = g + kl_coef * mu;
+    const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f);
+    const float dpvar = dlv / (pvar + POE_EPS);
+    const float dsm = dmu / st;
+    const float dst = -dpvar * pvar * pvar - dmu * mu / st;
+    for (int e = 0; e < n_experts; ++e) {
+      const float dmu_e = dsm * t_e[e];
+      const float dt = fmaf(dsm, ex.mu[e][ei], dst);
+      const float dlv_e = -dt * t_e[e] * t_e[e] * elv[e];
+      if (accumulate) {
+        ex.dmu[e][oi] += dmu_e;
+        ex.dlv[e][oi] += dlv_e;
+      } else {
+        ex.dmu[e][oi] = dmu_e;
+        ex.dlv[e][oi] = dlv_e;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// losses
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v) {
+  __shared__ float wsum[8];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += wsum[w];
+  return t;  // valid on thread 0
+}
+
+// one thread per pixel: reads the 3 planes (coalesced), writes one 16-byte NHWC8 gradient
+__global__ void __launch_bounds__(256)
+bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                  const float* __restrict__ mask, float* __restrict__ loss_sum,
+                  __half* __restrict__ dlogits, float gscale, long long n_pix, int HW) {
+  float acc = 0.0f;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long img = p / HW;
+    const int hw = static_cast<int>(p - img * HW);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long idx = (img * 3 + c) * HW + hw;
+      float x = logits[idx], t = target[idx], m = 1.0f;
+      if (mask) {
+        m = mask[idx];
+        x *= m;
+        t *= m;
+      }
+      // max(x,0) - x*t + log(1 + exp(-|x|))  (torch's stable form)
+      acc += fmaxf(x, 0.0f) - x * t + log1pf(expf(-fabsf(x)));
+      g[c] = gscale * (1.0f / (1.0f + expf(-x)) - t) * m;
+    }
+    if (dlogits) reinterpret_cast<uint4*>(dlogits)[p] = pack8(g);
+  }
+  const float t = block_sum_256(acc);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, t);
+}
+
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ recon, const float* __restrict__ target, float* __restrict__ loss_sum,
+           float* __restrict__ drecon, float mult, float gscale, long long n) {
+  float acc = 0.0f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = recon[i] - target[i];
+    acc = fmaf(d, d, acc);
+    if (drecon) drecon[i] = gscale * 2.0f * mult * d;
+  }
+  const float t = block_sum_256(acc);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, mult * t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums, packing, casts
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ld, float scale,
+              int rows_per_cta) {
+  // thread -> column (coalesced across the row), loop over the CTA's rows
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc = 0.0f;
+  for (int r = r0; r < r1; ++r) acc += x[static_cast<long long>(r) * ld + n];
+  atomicAdd(out + n, scale * acc);
+}
+
+// fp16 [M][N] column sums: block = 32 8-channel vectors x 8 row lanes
+__global__ void __launch_bounds__(256)
+colsum_f16_kernel(const __half* __restrict__ x, float* __restrict__ out, int M, int N, int ld, float scale,
+                  int rows_per_cta) {
+  __shared__ float red[8][256 + 1];
+  const int vl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + vl) * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld + c0), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl][vl * 8 + i] = s[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float a = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a += red[l][threadIdx.x];
+    atomicAdd(out + c, scale * a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_f16_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, __half* __restrict__ dst,
+                long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int32_t j = idx[i];
+    dst[i] = __float2half_rn(j < 0 ? 0.0f : src[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
+                  long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int32_t j = idx[i];
+    dst[i] = j < 0 ? 0.0f : src[j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
+                  long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int32_t j = idx[i];
+    if (j >= 0) dst[j] += src[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimizers (flat arena, float4 vectorised; 28 B / parameter for Adam)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+            float bc1, float bc2_sqrt, float gscale) {
+  const long long n4 = n >> 2;
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float gr = ga[q] * gscale;
+      if (wd != 0.0f) gr = fmaf(wd, pa[q], gr);
+      ma[q] = fmaf(b1, ma[q], (1.0f - b1) * gr);       // torch: m.lerp_(g, 1-b1)
+      va[q] = fmaf(b2, va[q], (1.0f - b2) * gr * gr);  // v.mul_(b2).addcmul_(g, g, 1-b2)
+      const float denom = sqrtf(va[q]) / bc2_sqrt + eps;
+      pa[q] -= step * (ma[q] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (n not a multiple of 4)
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    float gr = g[i] * gscale;
+    if (wd != 0.0f) gr = fmaf(wd, p[i], gr);
+    const float mm = fmaf(b1, m[i], (1.0f - b1) * gr);
+    const float vv = fmaf(b2, v[i], (1.0f - b2) * gr * gr);
+    m[i] = mm;
+    v[i] = vv;
+    p[i] -= step * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+           float lr, float momentum, float wd, int first_step, float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gr = fmaf(wd, p[i], g[i] * gscale);
+    const float b = first_step ? gr : fmaf(momentum, buf[i], gr);
+    buf[i] = b;
+    p[i] -= lr * b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (one 128-bit block -> 4 uniforms)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
+  return (static_cast<float>(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256)
+fill_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset) {
+  const long long n4 = (n + 3) >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint64_t c = offset + static_cast<uint64_t>(i);
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0x6e6f726du, 0),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    float o[4];
+    const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+    sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+    o[0] = r0 * c0; o[1] = r0 * s0; o[2] = r1 * c1; o[3] = r1 * s1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (4 * i + q < n) out[4 * i + q] = o[q];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_dropout_kernel(float* __restrict__ out, long long n, float p_drop, float keep_scale, uint64_t seed,
+                    uint64_t offset) {
+  const long long n4 = (n + 3) >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint64_t c = offset + static_cast<uint64_t>(i);
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0x64726f70u, 0),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (4 * i + q < n) out[4 * i + q] = (u01(w[q]) > p_drop) ? keep_scale : 0.0f;
+  }
+}
+
+inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 8) {
+  long long b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+inline int chunking(int rows_per_group, int G, int C, int* rows_per_chunk) {
+  // enough CTAs to cover the machine, at least 64 rows per lane pass
+  const int row_lanes = RED_THREADS / (C >> 3);
+  int chunks = (148 * 4 + G - 1) / G;
+  const int max_chunks = (rows_per_group + row_lanes * 4 - 1) / (row_lanes * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  *rows_per_chunk = (rows_per_group + chunks - 1) / chunks;
+  return (rows_per_group + *rows_per_chunk - 1) / *rows_per_chunk;
+}
+
+}  // namespace
+}  // namespace mmdyn
+
+using namespace mmdyn;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (RED_THREADS % (C >> 3)) == 0; }
+
+extern "C" int mmdyn_bn_stats(const void* x, float* sums, int G, int rows_per_group, int C, void* stream) {
+  MMDYN_REQUIRE(x && sums && G > 0 && rows_per_group > 0 && bn_c_ok(C), "bn_stats: bad arguments (C=%d)", C);
+  int rpc;
+  const int chunks = chunking(rows_per_group, G, C, &rpc);
+  const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
+  bn_stats_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
+      reinterpret_cast<const __half*>(x), sums, rows_per_group, C, rpc);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* ab,
+                                 float* mean_invstd, float* running_mean, float* running_var, int G,
+                                 int rows_per_group, int C, float eps, float momentum, void* stream) {
+  MMDYN_REQUIRE(sums && gamma && beta && ab && mean_invstd && G > 0 && C > 0, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, gamma, beta, ab, mean_invstd, running_mean,
+                                                               running_var, G, rows_per_group, C, eps, momentum);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_per_group, int C,
+                                  void* stream) {
+  MMDYN_REQUIRE(x && y && G > 0 && rows_per_group > 0 && C % 8 == 0, "bn_swish_fwd: bad arguments");
+  const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
+  bn_swish_fwd_kernel<<<grid_for(n_vec), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
+                                                               reinterpret_cast<__half*>(y), n_vec,
+                                                               rows_per_group, C);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const float* mean_invstd, void* dY,
+                                         float* sums2, int G, int rows_per_group, int C, void* stream) {
+  MMDYN_REQUIRE(x && dY && G > 0 && rows_per_group > 0 && C % 8 == 0, "bn_swish_bwd_reduce: bad arguments");
+  if (!ab) {
+    const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
+    swish_bwd_kernel<<<grid_for(n_vec), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x),
+                                                              reinterpret_cast<__half*>(dY), n_vec);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
+  MMDYN_REQUIRE(mean_invstd && sums2 && bn_c_ok(C), "bn_swish_bwd_reduce: bad arguments (C=%d)", C);
+  int rpc;
+  const int chunks = chunking(rows_per_group, G, C, &rpc);
+  const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
+  bn_swish_bwd_reduce_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
+      reinterpret_cast<const __half*>(x), ab, mean_invstd, reinterpret_cast<__half*>(dY), sums2,
+      rows_per_group, C, rpc);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
+                                  void* dU, float* dgamma, float* dbeta, int G, int rows_per_group, int C,
+                                  float grad_unscale, void* stream) {
+  MMDYN_REQUIRE(x && ab && mean_invstd && sums2 && dU && G > 0 && C % 8 == 0, "bn_bwd_apply: bad arguments");
+  const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
+  bn_bwd_apply_kernel<<<grid_for(n_vec), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
+                                                               mean_invstd, sums2, reinterpret_cast<__half*>(dU),
+                                                               n_vec, rows_per_group, C);
+  LAUNCHED();
+  if (dgamma && dbeta) {
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums2, dgamma, dbeta, G, C, grad_unscale);
+    LAUNCHED();
+  }
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_swish_dropout_fwd(const float* raw, const float* const* masks, void* h, int n_masks,
+                                       int B, int C, void* stream) {
+  MMDYN_REQUIRE(raw && h && n_masks >= 1 && n_masks <= 8, "swish_dropout_fwd: bad arguments");
+  MaskPtrs mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = (masks && i < n_masks) ? masks[i] : nullptr;
+  const long long n = static_cast<long long>(B) * C;
+  swish_dropout_fwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(raw, mp, reinterpret_cast<__half*>(h), n_masks, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_swish_dropout_bwd(const float* raw, const float* const* masks, const float* dH, void* dRaw,
+                                       int n_masks, int B, int C, void* stream) {
+  MMDYN_REQUIRE(raw && dH && dRaw && n_masks >= 1 && n_masks <= 8, "swish_dropout_bwd: bad arguments");
+  MaskPtrs mp;
+  for (int i = 0; i < 8; ++i) mp.p[i] = (masks && i < n_masks) ? masks[i] : nullptr;
+  const long long n = static_cast<long long>(B) * C;
+  swish_dropout_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(raw, mp, dH, reinterpret_cast<__half*>(dRaw),
+                                                                n_masks, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_poe_fwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
+                             int ld, const float* eps, float* mu, float* lv, float* z, void* zh, void* zh2,
+                             float* kl_sum, int B, int D, void* stream) {
+  MMDYN_REQUIRE(n_experts >= 0 && n_experts <= 3 && (n_experts > 0 || use_prior), "poe_fwd: n_experts=%d", n_experts);
+  MMDYN_REQUIRE(eps && mu && lv && z && kl_sum && B > 0 && D > 0, "poe_fwd: null pointer");
+  ExpertPtrs ex = {};
+  for (int e = 0; e < n_experts; ++e) {
+    MMDYN_REQUIRE(mu_e[e] && lv_e[e], "poe_fwd: null expert %d", e);
+    ex.mu[e] = mu_e[e];
+    ex.lv[e] = lv_e[e];
+  }
+  const long long n = static_cast<long long>(B) * D;
+  poe_fwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(ex, n_experts, use_prior, ld, eps, mu, lv, z,
+                                                      reinterpret_cast<__half*>(zh), reinterpret_cast<__half*>(zh2),
+                                                      kl_sum, B, D);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
+                             int ld, const float* eps, const float* const* dz, float kl_coef, float* const* dmu_e,
+                             float* const* dlv_e, int ld_out, int accumulate, int B, int D, void* stream) {
+  MMDYN_REQUIRE(n_experts >= 0 && n_experts <= 3, "poe_bwd: n_experts=%d", n_experts);
+  if (n_experts == 0) return MMDYN_OK;
+  MMDYN_REQUIRE(eps && B > 0 && D > 0, "poe_bwd: null pointer");
+  ExpertPtrs ex = {};
+  for (int e = 0; e < n_experts; ++e) {
+    MMDYN_REQUIRE(mu_e[e] && lv_e[e] && dmu_e[e] && dlv_e[e], "poe_bwd: null expert %d", e);
+    ex.mu[e] = mu_e[e];
+    ex.lv[e] = lv_e[e];
+    ex.dmu[e] = dmu_e[e];
+    ex.dlv[e] = dlv_e[e];
+  }
+  for (int q = 0; q < 3; ++q) ex.dz[q] = dz ? dz[q] : nullptr;
+  const long long n = static_cast<long long>(B) * D;
+  poe_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(ex, n_experts, use_prior, ld, eps, kl_coef, ld_out,
+                                                      accumulate, B, D);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
+                                void* dlogits_nhwc8, float gscale, int n, int HW, void* stream) {
+  MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && HW > 0, "bce_logits: bad arguments");
+  const long long n_pix = static_cast<long long>(n) * HW;
+  bce_logits_kernel<<<grid_for(n_pix), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum,
+                                                             reinterpret_cast<__half*>(dlogits_nhwc8), gscale,
+                                                             n_pix, HW);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_mse(const float* recon, const float* target, float* loss_sum, float* drecon, float mult,
+                         float gscale, int n, void* stream) {
+  MMDYN_REQUIRE(recon && target && loss_sum && n > 0, "mse: bad arguments");
+  mse_kernel<<<grid_for(n, 256, 64), 256, 0, ST(stream)>>>(recon, target, loss_sum, drecon, mult, gscale, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_colsum_f32(const float* x, float* out, int M, int N, int ld, float scale, void* stream) {
+  MMDYN_REQUIRE(x && out && M > 0 && N > 0, "colsum: bad arguments");
+  int row_ctas = (148 * 2) / ((N + 255) / 256);
+  if (row_ctas < 1) row_ctas = 1;
+  int rpc = (M + row_ctas - 1) / row_ctas;
+  if (rpc < 16) rpc = 16;
+  const int gy = (M + rpc - 1) / rpc;
+  colsum_kernel<<<dim3((N + 255) / 256, gy), 256, 0, ST(stream)>>>(x, out, M, N, ld, scale, rpc);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_colsum_f16(const void* x, float* out, int M, int N, int ld, float scale, void* stream) {
+  MMDYN_REQUIRE(x && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum_f16: bad arguments");
+  const int gx = (N + 255) / 256;
+  int row_ctas = (148 * 2) / gx;
+  if (row_ctas < 1) row_ctas = 1;
+  int rpc = (M + row_ctas - 1) / row_ctas;
+  if (rpc < 32) rpc = 32;
+  const int gy = (M + rpc - 1) / rpc;
+  colsum_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), out, M, N, ld, scale,
+                                                          rpc);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_pack_f16(const float* src, const int32_t* idx, void* dst, long long n, void* stream) {
+  MMDYN_REQUIRE(src && idx && dst && n > 0, "pack_f16: bad arguments");
+  pack_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, reinterpret_cast<__half*>(dst), n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_gather_f32(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
+  MMDYN_REQUIRE(src && idx && dst && n > 0, "gather_f32: bad arguments");
+  gather_f32_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
+  MMDYN_REQUIRE(src && idx && dst && n > 0, "unpack_add: bad arguments");
+  unpack_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_f32_to_f16(const float* src, void* dst, long long n, void* stream) {
+  MMDYN_REQUIRE(src && dst && n > 0, "f32_to_f16: bad arguments");
+  f32_to_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, reinterpret_cast<__half*>(dst), n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, int step_count, float gscale,
+                               void* stream) {
+  MMDYN_REQUIRE(p && g && m && v && n > 0 && step_count >= 1, "adam_flat: bad arguments");
+  MMDYN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+                "adam_flat: arenas must be 16-byte aligned");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step_count);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step_count);
+  adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                        static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+                                                        gscale);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n, float lr, float momentum,
+                              float weight_decay, int first_step, float gscale, void* stream) {
+  MMDYN_REQUIRE(p && g && buf && n > 0, "sgd_flat: bad arguments");
+  sgd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, first_step, gscale);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset, void* stream) {
+  MMDYN_REQUIRE(out && n > 0, "fill_normal: bad arguments");
+  fill_normal_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, seed, offset);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_fill_dropout_mask(float* out, long long n, float p_drop, uint64_t seed, uint64_t offset,
+                                       void* stream) {
+  MMDYN_REQUIRE(out && n > 0 && p_drop >= 0.0f && p_drop < 1.0f, "fill_dropout_mask: bad arguments");
+  fill_dropout_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, p_drop, 1.0f / (1.0f - p_drop), seed,
+                                                                      offset);
+  LAUNCHED();
+  return MMDYN_OK;
+}

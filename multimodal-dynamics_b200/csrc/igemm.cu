@@ -1,0 +1,767 @@
+// Implicit-GEMM convolution / transposed convolution / linear kernels for sm_100a.
+//
+//   igemm_kernel  : out[row, n] = sum_k A_gather[row, k] * W[n, k]        (fwd + dgrad form)
+//   wgrad_kernel  : dW[n, k]   += sum_row Nat[row, n] * G_gather[row, k]  (weight gradients)
+//   conv1_*       : the Cin = 3 first encoder layer on the fp32 NCHW input
+//
+// Mapping to the hardware (B200):
+//   * accumulators live in TMEM (tcgen05.alloc, 128 lanes x BLOCK_N fp32 columns);
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N, K = 16)
+//     on UMMA shared-memory descriptors (128B swizzle; K-major for igemm, MN-major for wgrad);
+//   * the weight operand arrives by TMA (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier tx);
+//   * the gathered activation operand is an im2col gather done with 16-byte cp.async (LDGSTS,
+//     zero fill for padding) straight into the swizzled UMMA layout by four producer warps,
+//     published to the async proxy with fence.proxy.async + mbarrier arrive;
+//   * a STAGES-deep smem ring decouples {gather, TMA} from the MMA issuer; tcgen05.commit frees
+//     ring slots and finally signals the epilogue, which reads TMEM with tcgen05.ld.
+//
+// Reference semantics: nn.Conv2d / nn.ConvTranspose2d / nn.Linear in
+// mmdyn/pytorch/models/vae.py:198-216, 263-277 and their autograd (problems.py:153).
+#include "common.cuh"
+#include "../../include/mmdyn_b200.h"
+
+#include <atomic>
+
+namespace mmdyn {
+
+std::atomic<long long> g_launch_count{0};
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_PRODUCER_THREADS = 128;
+constexpr int CTA_THREADS = 192;  // 4 producer/epilogue warps + MMA warp + TMA warp
+constexpr int A_STAGE_BYTES = TILE_M * 128;
+
+struct __align__(16) RowInfo {
+  int32_t a_off;    // element offset of (img, iy0, ix0, 0) in A
+  int32_t out_off;  // element offset of the output pixel, -1: row out of range
+  int32_t iy0, ix0;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int STAGES = (BLOCK_N == 128) ? 3 : 4;
+  static constexpr int LAG = STAGES - 2;  // cp.async groups kept in flight per producer thread
+  static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// igemm: forward / dgrad form
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(CTA_THREADS)
+igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmW) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ RowInfo rows[TILE_M];
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;
+  const int phase = blockIdx.z / d.ksplit;
+  const int split = blockIdx.z - phase * d.ksplit;
+
+  // ---- tile geometry -----------------------------------------------------------------------
+  int row0, tile_pix = 0;
+  if (d.row_mode == 0) {
+    row0 = blockIdx.x * TILE_M;
+  } else {
+    const int img_blocks = (d.n_img + TILE_M - 1) / TILE_M;
+    tile_pix = blockIdx.x / img_blocks;
+    row0 = (blockIdx.x - tile_pix * img_blocks) * TILE_M;
+  }
+  if (threadIdx.x < TILE_M) {
+    const int r = threadIdx.x;
+    int img, p;
+    bool valid;
+    if (d.row_mode == 0) {
+      const int m = row0 + r;
+      valid = m < d.n_img * d.P;
+      img = m / d.P;
+      p = m - img * d.P;
+    } else {
+      img = row0 + r;
+      valid = img < d.n_img;
+      p = tile_pix;
+    }
+    const int yv = p / d.OXv, xv = p - yv * d.OXv;
+    RowInfo ri;
+    ri.iy0 = valid ? yv * d.s_in : -(1 << 20);
+    ri.ix0 = xv * d.s_in;
+    ri.a_off = valid ? ((img * d.IH + yv * d.s_in) * d.IW + xv * d.s_in) * d.a_pix_stride : 0;
+    if (d.out_mode == 3) {
+      ri.out_off = valid ? ((img * 3 * d.OH) + 2 * yv) * d.OW + 2 * xv : -1;
+    } else {
+      const int oy = yv * d.s_out + d.off_y[phase], ox = xv * d.s_out + d.off_x[phase];
+      ri.out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
+    }
+    rows[r] = ri;
+  }
+
+  // ---- barriers + TMEM ---------------------------------------------------------------------
+  if (threadIdx.x == NUM_PRODUCER_THREADS) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), NUM_PRODUCER_THREADS + 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // ---- k-block range of this CTA -----------------------------------------------------------
+  const int kb_total = (d.ntaps * d.Cin) >> 6;
+  const int kb_per = (kb_total + d.ksplit - 1) / d.ksplit;
+  const int kb_begin = split * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  // row_mode 1: all rows of the tile share the virtual pixel, so out-of-image taps are skipped
+  const int tyv = tile_pix / d.OXv, txv = tile_pix - tyv * d.OXv;
+  auto kb_live = [&](int kb) -> bool {
+    if (d.row_mode == 0) return true;
+    const int tap = (kb << 6) / d.Cin;
+    const int iy = tyv * d.s_in + d.tap_dy[phase][tap];
+    const int ix = txv * d.s_in + d.tap_dx[phase][tap];
+    return (unsigned)iy < (unsigned)d.IH && (unsigned)ix < (unsigned)d.IW;
+  };
+
+  int n_issued = 0;
+  if (warp < 4) {
+    // ======================= A producers: im2col gather with cp.async =======================
+    const __half* A = reinterpret_cast<const __half*>(d.A);
+    const int j = threadIdx.x & 7;      // 16-byte chunk inside the 128-byte k-block row
+    const int rsub = threadIdx.x >> 3;  // rows rsub + 16*i
+    const uint32_t sw = static_cast<uint32_t>((j ^ (rsub & 7)) << 4);
+    int it = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      if (!kb_live(kb)) continue;
+      const int s = it % C::STAGES;
+      mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+      const int k = (kb << 6) + (j << 3);
+      const int tap = k / d.Cin;
+      const int c = k - tap * d.Cin;
+      const int dy = d.tap_dy[phase][tap], dx = d.tap_dx[phase][tap];
+      const int tap_off = (dy * d.IW + dx) * d.a_pix_stride + c;
+      const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        const RowInfo ri = rows[r];
+        const bool v = (unsigned)(ri.iy0 + dy) < (unsigned)d.IH &&
+                       (unsigned)(ri.ix0 + dx) < (unsigned)d.IW;
+        const __half* src = v ? (A + (ri.a_off + tap_off)) : A;
+        cp_async16(a_stage + r * 128 + sw, src, v);
+      }
+      cp_async_commit();
+      if (it >= C::LAG) {
+        cp_async_wait<C::LAG>();
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&full_bar[(it - C::LAG) % C::STAGES]));
+      }
+      ++it;
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int q = (it > C::LAG ? it - C::LAG : 0); q < it; ++q)
+      mbar_arrive(smem_u32(&full_bar[q % C::STAGES]));
+    n_issued = it;
+  } else if (warp == 5) {
+    // ======================= B producer: TMA loads of the packed weights =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        if (!kb_live(kb)) continue;
+        const int s = it % C::STAGES;
+        mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_arrive_expect_tx(bar, C::B_STAGE_BYTES);
+        tma_load_2d(smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES, &tmW, bar, kb << 6,
+                    phase * d.N + n_tile * BLOCK_N);
+        ++it;
+      }
+    }
+  } else {
+    // ======================= MMA issuer ======================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 0, 0, 0, 0);
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        if (!kb_live(kb)) continue;
+        const int s = it % C::STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
+        const uint64_t adesc = make_smem_desc(a_base, 16, 1024, LAYOUT_SW128);
+        const uint64_t bdesc = make_smem_desc(a_base + A_STAGE_BYTES, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // 4 x (K = 16) per 64-wide k-block: +32 B per step
+          umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (it | kk) != 0);
+        umma_commit(smem_u32(&empty_bar[s]));
+        ++it;
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  }
+
+  // ======================= epilogue: TMEM -> registers -> global ============================
+  if (warp < 4) {
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    const int r = threadIdx.x;
+    const RowInfo ri = rows[r];
+    const int n_base = n_tile * BLOCK_N;
+    const bool add_bias = d.bias != nullptr && split == 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (ri.out_off < 0) continue;
+      float f[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) f[q] = n_issued > 0 ? __uint_as_float(v[q]) : 0.0f;
+      if (add_bias) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
+      }
+      if (d.out_mode == 0) {
+        __half* o = reinterpret_cast<__half*>(d.out) + ri.out_off + n_base + c0;
+        uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]),
+                              pack_h2(f[6], f[7]));
+        uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
+                              pack_h2(f[14], f[15]));
+        reinterpret_cast<uint4*>(o)[0] = u0;
+        reinterpret_cast<uint4*>(o)[1] = u1;
+      } else if (d.out_mode == 1) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + ri.out_off +
+                                              n_base + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      } else if (d.out_mode == 2) {
+        float* o = reinterpret_cast<float*>(d.out) + ri.out_off + n_base + c0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
+      } else {
+        // merged 2x2 sub-pixel phases -> fp32 NCHW planes; n = (ph*2 + pw)*3 + c
+        float* o = reinterpret_cast<float*>(d.out) + ri.out_off;
+        const int plane = d.OH * d.OW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph)
+            *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
+                make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[n][k] += scale * sum_rows Nat[row][n] * G_gather[row][k]
+//   D tile = [128 k-columns (M)] x [CN channels (N)], reduction over rows in steps of 64.
+//   Both operands sit in smem as rows-of-channels (the layout they have in HBM), which is the
+//   MN-major UMMA canonical layout: no transposes anywhere.
+// ---------------------------------------------------------------------------------------------
+template <int CN>
+__global__ void __launch_bounds__(CTA_THREADS)
+wgrad_kernel(const __grid_constant__ mmdyn_wgrad_desc d) {
+  using C = Cfg<CN>;
+  constexpr int STEP_ROWS = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kcol0 = blockIdx.y * 128;
+  const int n0 = blockIdx.z * CN;
+
+  if (threadIdx.x == NUM_PRODUCER_THREADS) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), NUM_PRODUCER_THREADS);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int M = d.n_img * d.P;
+  const int steps_total = (M + STEP_ROWS - 1) / STEP_ROWS;
+  const int steps_per = (steps_total + d.row_splits - 1) / d.row_splits;
+  const int step_begin = blockIdx.x * steps_per;
+  const int step_end = min(steps_total, step_begin + steps_per);
+  const int n_steps = max(0, step_end - step_begin);
+
+  if (warp < 4) {
+    const __half* G = reinterpret_cast<const __half*>(d.G);
+    const __half* Nat = reinterpret_cast<const __half*>(d.Nat);
+    const int j = threadIdx.x & 7;
+    const int rsub = threadIdx.x >> 3;
+    const uint32_t sw = static_cast<uint32_t>((j ^ (rsub & 7)) << 4);
+    // (tap, channel) of this thread's chunk in each of the two 64-wide k-column blocks
+    int tap_off[2], tdy[2], tdx[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int k = kcol0 + b * 64 + j * 8;
+      const int tap = k / d.Cg;
+      const int c = k - tap * d.Cg;
+      tdy[b] = d.tap_dy[tap];
+      tdx[b] = d.tap_dx[tap];
+      tap_off[b] = (tdy[b] * d.IW + tdx[b]) * d.g_pix_stride + c;
+    }
+    for (int it = 0; it < n_steps; ++it) {
+      const int s = it % C::STAGES;
+      mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+      const int m_base = (step_begin + it) * STEP_ROWS;
+      const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+      const uint32_t b_stage = a_stage + A_STAGE_BYTES;
+      // gathered operand: 2 blocks x [64 rows x 128 B]
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rsub + 16 * i;
+        const int m = m_base + r;
+        const bool rv = m < M;
+        const int img = m / d.P;
+        const int p = m - img * d.P;
+        const int yv = p / d.OXv, xv = p - yv * d.OXv;
+        const int iy0 = yv * d.s_in, ix0 = xv * d.s_in;
+        const int a_off = ((img * d.IH + iy0) * d.IW + ix0) * d.g_pix_stride;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const bool v = rv && (unsigned)(iy0 + tdy[b]) < (unsigned)d.IH &&
+                         (unsigned)(ix0 + tdx[b]) < (unsigned)d.IW;
+          const __half* src = v ? (G + (a_off + tap_off[b])) : G;
+          cp_async16(a_stage + b * 8192 + r * 128 + sw, src, v);
+        }
+      }
+      // natural operand: [64 rows x CN channels]
+      constexpr int CHUNKS_PER_ROW = CN / 8;
+#pragma unroll
+      for (int q = 0; q < (STEP_ROWS * CHUNKS_PER_ROW + 127) / 128; ++q) {
+        const int idx = q * 128 + threadIdx.x;
+        if (idx < STEP_ROWS * CHUNKS_PER_ROW) {
+          const int row = idx / CHUNKS_PER_ROW;
+          const int cj = idx - row * CHUNKS_PER_ROW;
+          const int m = m_base + row;
+          const bool v = m < M;
+          const __half* src = v ? (Nat + (static_cast<long long>(m) * d.nat_stride + n0 + cj * 8)) : Nat;
+          uint32_t off;
+          if (CN >= 64) {
+            off = (cj >> 3) * 8192 + row * 128 + (((cj & 7) ^ (row & 7)) << 4);
+          } else if (CN == 32) {
+            off = swz<2>(row * 64 + cj * 16);
+          } else {
+            off = swz<1>(row * 32 + cj * 16);
+          }
+          cp_async16(b_stage + off, src, v);
+        }
+      }
+      cp_async_commit();
+      if (it >= C::LAG) {
+        cp_async_wait<C::LAG>();
+        fence_proxy_async_smem();
+        mbar_arrive(smem_u32(&full_bar[(it - C::LAG) % C::STAGES]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int q = (n_steps > C::LAG ? n_steps - C::LAG : 0); q < n_steps; ++q)
+      mbar_arrive(smem_u32(&full_bar[q % C::STAGES]));
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, CN, 0, 0, 1, 1);
+      constexpr uint32_t b_layout = CN >= 64 ? LAYOUT_SW128 : (CN == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
+      constexpr uint32_t b_sbo = CN >= 64 ? 1024 : (CN == 32 ? 512 : 256);  // 8 rows of the tile
+      for (int it = 0; it < n_steps; ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
+        const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // 16 reduction rows per MMA
+          const uint64_t adesc = make_smem_desc(a_base + kk * 2048, 8192, 1024, LAYOUT_SW128);
+          const uint64_t bdesc = make_smem_desc(b_base + kk * 2 * b_sbo, 8192, b_sbo, b_layout);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (it | kk) != 0);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  }
+
+  if (warp < 4 && n_steps > 0) {
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    float* o = d.dW + static_cast<long long>(n0) * d.ldw + kcol0 + threadIdx.x;
+#pragma unroll 1
+    for (int c0 = 0; c0 < CN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        atomicAdd(o + static_cast<long long>(c0 + q) * d.ldw, d.scale * __uint_as_float(v[q]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1: Conv2d(3, 32, k4, s2, p1) on the fp32 NCHW input, 64x64 -> 32x32, fp16 NHWC out.
+//   One tile = 4 output rows x 32 columns of one image (128 GEMM rows), K = 48 (+16 zero pad),
+//   N = 32: a single 64-wide k-block, so no ring: gather -> 4 MMAs -> epilogue.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __half* __restrict__ out,
+                 int n_img) {
+  __shared__ __align__(1024) uint8_t a_tile[TILE_M * 128];
+  __shared__ __align__(1024) uint8_t b_tile[32 * 128];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const int r = threadIdx.x;
+  const int tile = blockIdx.x;  // n_img * 8 tiles
+  const int img = tile >> 3;
+  const int oy = ((tile & 7) << 2) + (r >> 5);
+  const int ox = r & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&accum_bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_base_s), 32);
+    tmem_relinquish();
+  }
+  // weights: 32 rows x 128 B -> swizzled K-major tile (256 16-byte chunks, 2 per thread)
+  for (int idx = threadIdx.x; idx < 256; idx += 128) {
+    const int n = idx >> 3, cj = idx & 7;
+    const uint4 w = reinterpret_cast<const uint4*>(Wp)[idx];
+    *reinterpret_cast<uint4*>(b_tile + n * 128 + ((cj ^ (n & 7)) << 4)) = w;
+  }
+  // patch gather: k = (ci, kh, kw); chunk cj holds (ci = cj/2, kh = 2*(cj&1) + {0,1}, kw = 0..3)
+  const float* xi = x + static_cast<long long>(img) * 3 * 64 * 64;
+#pragma unroll
+  for (int cj = 0; cj < 8; ++cj) {
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = 0.0f;
+    if (cj < 6) {
+      const int ci = cj >> 1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int iy = 2 * oy - 1 + 2 * (cj & 1) + h;
+        if ((unsigned)iy < 64u) {
+          const float* row = xi + (ci * 64 + iy) * 64;
+#pragma unroll
+          for (int kw = 0; kw < 4; ++kw) {
+            const int ix = 2 * ox - 1 + kw;
+            if ((unsigned)ix < 64u) f[h * 4 + kw] = __ldg(row + ix);
+          }
+        }
+      }
+    }
+    const uint4 u = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]),
+                               pack_h2(f[6], f[7]));
+    *reinterpret_cast<uint4*>(a_tile + r * 128 + ((cj ^ (r & 7)) << 4)) = u;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = make_idesc_f16(128, 32, 0, 0, 0, 0);
+    const uint64_t adesc = make_smem_desc(smem_u32(a_tile), 16, 1024, LAYOUT_SW128);
+    const uint64_t bdesc = make_smem_desc(smem_u32(b_tile), 16, 1024, LAYOUT_SW128);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+    umma_commit(smem_u32(&accum_bar));
+  }
+  mbar_wait(smem_u32(&accum_bar), 0);
+  tc_fence_after();
+  __half* o = out + ((static_cast<long long>(img) * 32 + oy) * 32 + ox) * 32;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
+    reinterpret_cast<uint4*>(o + c0)[0] = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]),
+                                                     pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+    reinterpret_cast<uint4*>(o + c0)[1] = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]),
+                                                     pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+// conv1 weight gradient on CUDA cores: dW[co][k] += scale * sum_pix dRaw[pix][co] * patch[pix][k].
+// 1536 outputs, HBM-bound (reads the fp32 input once and the fp16 dRaw once); 256 threads, each
+// owns 6 (co, k) outputs; pixels are staged through smem 64 at a time.
+__global__ void __launch_bounds__(256)
+conv1_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dRaw, float* __restrict__ dW,
+                   int n_img, float scale, int pix_per_cta) {
+  constexpr int PIX = 64;
+  __shared__ float patch[PIX][49];
+  __shared__ float dy[PIX][33];
+  const int t = threadIdx.x;
+  const long long total_pix = static_cast<long long>(n_img) * 1024;
+  const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_cta;
+  const long long p_end = min(total_pix, p_begin + pix_per_cta);
+  // outputs owned: co = t & 31, k = (t >> 5) * 6 + q, q < 6  (8 groups x 6 = 48)
+  const int co = t & 31, kg = (t >> 5) * 6;
+  float acc[6] = {0, 0, 0, 0, 0, 0};
+  for (long long p0 = p_begin; p0 < p_end; p0 += PIX) {
+    // stage patches: 64 pixels x 48 taps
+    for (int idx = t; idx < PIX * 48; idx += 256) {
+      const int pp = idx / 48, k = idx - pp * 48;
+      const long long pix = p0 + pp;
+      float v = 0.0f;
+      if (pix < p_end) {
+        const int img = static_cast<int>(pix >> 10);
+        const int oy = static_cast<int>(pix >> 5) & 31, ox = static_cast<int>(pix) & 31;
+        const int ci = k >> 4, kh = (k >> 2) & 3, kw = k & 3;
+        const int iy = 2 * oy - 1 + kh, ix = 2 * ox - 1 + kw;
+        if ((unsigned)iy < 64u && (unsigned)ix < 64u)
+          v = __ldg(x + ((static_cast<long long>(img) * 3 + ci) * 64 + iy) * 64 + ix);
+      }
+      patch[pp][k] = v;
+    }
+    for (int idx = t; idx < PIX * 32; idx += 256) {
+      const int pp = idx >> 5, c = idx & 31;
+      const long long pix = p0 + pp;
+      dy[pp][c] = pix < p_end ? __half2float(dRaw[pix * 32 + c]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < PIX; ++pp) {
+      const float g = dy[pp][co];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[q] = fmaf(g, patch[pp][kg + q], acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) atomicAdd(dW + co * 48 + kg + q, scale * acc[q]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+template <int BLOCK_N>
+int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, dim3 grid, cudaStream_t st) {
+  igemm_kernel<BLOCK_N><<<grid, CTA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tm);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+template <int CN>
+int launch_wgrad(const mmdyn_wgrad_desc* d, dim3 grid, cudaStream_t st) {
+  wgrad_kernel<CN><<<grid, CTA_THREADS, Cfg<CN>::SMEM_BYTES, st>>>(*d);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+}  // namespace
+
+int igemm_init() {
+#define SET_SMEM(K, BYTES) \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES))
+  SET_SMEM(igemm_kernel<16>, Cfg<16>::SMEM_BYTES);
+  SET_SMEM(igemm_kernel<32>, Cfg<32>::SMEM_BYTES);
+  SET_SMEM(igemm_kernel<64>, Cfg<64>::SMEM_BYTES);
+  SET_SMEM(igemm_kernel<128>, Cfg<128>::SMEM_BYTES);
+  SET_SMEM(igemm_kernel<256>, Cfg<256>::SMEM_BYTES);
+  SET_SMEM(wgrad_kernel<16>, Cfg<16>::SMEM_BYTES);
+  SET_SMEM(wgrad_kernel<32>, Cfg<32>::SMEM_BYTES);
+  SET_SMEM(wgrad_kernel<64>, Cfg<64>::SMEM_BYTES);
+  SET_SMEM(wgrad_kernel<128>, Cfg<128>::SMEM_BYTES);
+  SET_SMEM(wgrad_kernel<256>, Cfg<256>::SMEM_BYTES);
+#undef SET_SMEM
+  return MMDYN_OK;
+}
+
+}  // namespace mmdyn
+
+using namespace mmdyn;
+
+extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
+  MMDYN_REQUIRE(d && d->A && d->W && d->out, "igemm: null pointer");
+  MMDYN_REQUIRE(d->Cin > 0 && d->Cin % 8 == 0, "igemm: Cin=%d must be a positive multiple of 8", d->Cin);
+  MMDYN_REQUIRE(d->ntaps >= 1 && d->ntaps <= MMDYN_MAX_TAPS, "igemm: ntaps=%d", d->ntaps);
+  MMDYN_REQUIRE((d->ntaps * d->Cin) % 64 == 0, "igemm: ntaps*Cin=%d must be a multiple of 64",
+                d->ntaps * d->Cin);
+  MMDYN_REQUIRE(d->n_phases >= 1 && d->n_phases <= MMDYN_MAX_PHASES, "igemm: n_phases=%d", d->n_phases);
+  MMDYN_REQUIRE(d->block_n == 16 || d->block_n == 32 || d->block_n == 64 || d->block_n == 128 ||
+                    d->block_n == 256,
+                "igemm: block_n=%d", d->block_n);
+  MMDYN_REQUIRE(d->N > 0 && d->N % d->block_n == 0, "igemm: N=%d not a multiple of block_n=%d", d->N,
+                d->block_n);
+  MMDYN_REQUIRE(d->ksplit >= 1 && (d->ksplit == 1 || d->out_mode == 2),
+                "igemm: ksplit=%d needs out_mode 2", d->ksplit);
+  MMDYN_REQUIRE(d->out_mode >= 0 && d->out_mode <= 3, "igemm: out_mode=%d", d->out_mode);
+  MMDYN_REQUIRE(d->out_mode != 3 || (d->block_n == 16 && d->N == 16), "igemm: out_mode 3 needs N=16");
+  MMDYN_REQUIRE(d->row_mode == 0 || (d->row_mode == 1 && d->ksplit == 1 && d->Cin % 64 == 0),
+                "igemm: row_mode=%d (row_mode 1 needs ksplit 1 and Cin %% 64 == 0)", d->row_mode);
+  MMDYN_REQUIRE(d->n_img > 0 && d->P > 0 && d->OXv > 0, "igemm: empty problem");
+  MMDYN_REQUIRE((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->W) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && d->a_pix_stride % 8 == 0,
+                "igemm: operands must be 16-byte aligned");
+  const long long rows = static_cast<long long>(d->n_img) * d->P;
+  MMDYN_REQUIRE(rows * d->ldc < (1LL << 31) &&
+                    static_cast<long long>(d->n_img) * d->IH * d->IW * d->a_pix_stride < (1LL << 31),
+                "igemm: tensor too large for 32-bit offsets");
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_last_error("igemm: cuTensorMapEncodeTiled driver entry point not available");
+    return MMDYN_ERR_CUDA;
+  }
+  const int ktot = d->ntaps * d->Cin;
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(d->n_phases) * d->N};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ktot) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(d->block_n)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->W), gdim, gstr, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_last_error("igemm: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(cr));
+    return MMDYN_ERR_CUDA;
+  }
+  dim3 grid;
+  if (d->row_mode == 0)
+    grid.x = static_cast<unsigned>((rows + TILE_M - 1) / TILE_M);
+  else
+    grid.x = static_cast<unsigned>(d->P) * ((d->n_img + TILE_M - 1) / TILE_M);
+  grid.y = d->N / d->block_n;
+  grid.z = d->n_phases * d->ksplit;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (d->block_n) {
+    case 16: return launch_igemm<16>(d, tm, grid, st);
+    case 32: return launch_igemm<32>(d, tm, grid, st);
+    case 64: return launch_igemm<64>(d, tm, grid, st);
+    case 128: return launch_igemm<128>(d, tm, grid, st);
+    default: return launch_igemm<256>(d, tm, grid, st);
+  }
+}
+
+extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
+  MMDYN_REQUIRE(d && d->G && d->Nat && d->dW, "wgrad: null pointer");
+  MMDYN_REQUIRE(d->Cg > 0 && d->Cg % 8 == 0 && (d->ntaps * d->Cg) % 128 == 0,
+                "wgrad: Cg=%d ntaps=%d (ntaps*Cg must be a multiple of 128)", d->Cg, d->ntaps);
+  MMDYN_REQUIRE(d->ntaps >= 1 && d->ntaps <= MMDYN_MAX_TAPS, "wgrad: ntaps=%d", d->ntaps);
+  const int cn_tile = d->Cn >= 256 ? 256 : d->Cn;
+  MMDYN_REQUIRE(cn_tile == 16 || cn_tile == 32 || cn_tile == 64 || cn_tile == 128 || cn_tile == 256,
+                "wgrad: Cn=%d unsupported", d->Cn);
+  MMDYN_REQUIRE(d->Cn % cn_tile == 0, "wgrad: Cn=%d not a multiple of %d", d->Cn, cn_tile);
+  MMDYN_REQUIRE(d->row_splits >= 1, "wgrad: row_splits=%d", d->row_splits);
+  MMDYN_REQUIRE((reinterpret_cast<uintptr_t>(d->G) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->Nat) & 15) == 0 &&
+                    d->g_pix_stride % 8 == 0 && d->nat_stride % 8 == 0,
+                "wgrad: operands must be 16-byte aligned");
+  MMDYN_REQUIRE(static_cast<long long>(d->n_img) * d->IH * d->IW * d->g_pix_stride < (1LL << 31),
+                "wgrad: tensor too large for 32-bit offsets");
+  dim3 grid(d->row_splits, (d->ntaps * d->Cg) / 128, d->Cn / cn_tile);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (cn_tile) {
+    case 16: return launch_wgrad<16>(d, grid, st);
+    case 32: return launch_wgrad<32>(d, grid, st);
+    case 64: return launch_wgrad<64>(d, grid, st);
+    case 128: return launch_wgrad<128>(d, grid, st);
+    default: return launch_wgrad<256>(d, grid, st);
+  }
+}
+
+extern "C" int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, int n_img, void* stream) {
+  MMDYN_REQUIRE(x_nchw && Wp && out && n_img > 0, "conv1_fwd: bad arguments");
+  conv1_fwd_kernel<<<n_img * 8, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, reinterpret_cast<const __half*>(Wp), reinterpret_cast<__half*>(out), n_img);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_conv1_wgrad(const float* x_nchw, const void* dRaw, float* dW, int n_img, float scale,
+                                 int row_splits, void* stream) {
+  MMDYN_REQUIRE(x_nchw && dRaw && dW && n_img > 0 && row_splits > 0, "conv1_wgrad: bad arguments");
+  const long long total = static_cast<long long>(n_img) * 1024;
+  long long per = (total + row_splits - 1) / row_splits;
+  per = (per + 63) / 64 * 64;
+  const int grid = static_cast<int>((total + per - 1) / per);
+  conv1_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, reinterpret_cast<const __half*>(dRaw), dW, n_img, scale, static_cast<int>(per));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}

@@ -1,0 +1,184 @@
+"""Thin torch-tensor front end over the C ABI (lib.py): extracts device pointers / the current
+CUDA stream and fills the descriptor structs.  No math happens here and nothing falls back to
+PyTorch: every function launches one or two kernels of libmmdyn_b200.so or raises."""
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .lib import IgemmDesc, WgradDesc, MAX_PHASES, MAX_TAPS, check
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "mmdyn_b200 kernels need CUDA tensors (there is no CPU path)"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _L():
+    return _lib.init(torch.cuda.current_device())
+
+
+def _ptr_array(tensors, n):
+    arr = (C.c_void_p * n)()
+    for i in range(n):
+        arr[i] = tensors[i].data_ptr() if (i < len(tensors) and tensors[i] is not None) else None
+    return arr
+
+
+def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None, a_pix_stride=None):
+    d = IgemmDesc()
+    d.A, d.W, d.out = A.data_ptr(), Wp.data_ptr(), out.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.n_img, d.P, d.OXv, d.IH, d.IW = n_img, geom.P, geom.OXv, geom.IH, geom.IW
+    d.a_pix_stride = geom.a_pix_stride if a_pix_stride is None else a_pix_stride
+    d.Cin, d.s_in, d.ntaps, d.n_phases = geom.Cin, geom.s_in, geom.ntaps, geom.n_phases
+    for p in range(geom.n_phases):
+        for t in range(geom.ntaps):
+            d.tap_dy[p][t] = geom.tap_dy[p][t]
+            d.tap_dx[p][t] = geom.tap_dx[p][t]
+        d.off_y[p], d.off_x[p] = geom.off_y[p], geom.off_x[p]
+    d.N, d.block_n, d.ksplit, d.row_mode = geom.N, geom.block_n, ksplit, geom.row_mode
+    d.out_mode = geom.out_mode if out_mode is None else out_mode
+    d.OH, d.OW, d.s_out = geom.OH, geom.OW, geom.s_out
+    d.ldc = geom.ldc if ldc is None else ldc
+    check(_L().mmdyn_igemm(C.byref(d), _stream()), "mmdyn_igemm")
+
+
+def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride=None, g_pix_stride=None):
+    d = WgradDesc()
+    d.G, d.Nat, d.dW = G.data_ptr(), Nat.data_ptr(), dW.data_ptr()
+    d.n_img, d.P, d.OXv, d.IH, d.IW = n_img, geom.P, geom.OXv, geom.IH, geom.IW
+    d.g_pix_stride = geom.g_pix_stride if g_pix_stride is None else g_pix_stride
+    d.Cg, d.s_in, d.ntaps = geom.Cg, geom.s_in, geom.ntaps
+    for t in range(geom.ntaps):
+        d.tap_dy[t], d.tap_dx[t] = geom.tap_dy[t], geom.tap_dx[t]
+    d.Cn = geom.Cn
+    d.nat_stride = geom.nat_stride if nat_stride is None else nat_stride
+    d.ldw = geom.K if ldw is None else ldw
+    d.row_splits, d.scale = row_splits, scale
+    check(_L().mmdyn_wgrad(C.byref(d), _stream()), "mmdyn_wgrad")
+
+
+def conv1_fwd(x, Wp, out, n_img):
+    check(_L().mmdyn_conv1_fwd(_ptr(x), _ptr(Wp), _ptr(out), n_img, _stream()), "conv1_fwd")
+
+
+def conv1_wgrad(x, dRaw, dW, n_img, scale, row_splits):
+    check(_L().mmdyn_conv1_wgrad(_ptr(x), _ptr(dRaw), _ptr(dW), n_img, scale, row_splits, _stream()), "conv1_wgrad")
+
+
+def bn_stats(x, sums, G, rows, Cch):
+    check(_L().mmdyn_bn_stats(_ptr(x), _ptr(sums), G, rows, Cch, _stream()), "bn_stats")
+
+
+def bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows, Cch, eps, momentum):
+    check(_L().mmdyn_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(ab), _ptr(mean_invstd),
+                                 _ptr(running_mean), _ptr(running_var), G, rows, Cch, eps, momentum, _stream()),
+          "bn_finalize")
+
+
+def bn_swish_fwd(x, ab, y, G, rows, Cch):
+    check(_L().mmdyn_bn_swish_fwd(_ptr(x), _ptr(ab), _ptr(y), G, rows, Cch, _stream()), "bn_swish_fwd")
+
+
+def bn_swish_bwd_reduce(x, ab, mean_invstd, dY, sums2, G, rows, Cch):
+    check(_L().mmdyn_bn_swish_bwd_reduce(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(dY), _ptr(sums2), G, rows,
+                                         Cch, _stream()), "bn_swish_bwd_reduce")
+
+
+def bn_bwd_apply(x, ab, mean_invstd, sums2, dU, dgamma, dbeta, G, rows, Cch, unscale):
+    check(_L().mmdyn_bn_bwd_apply(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(sums2), _ptr(dU), _ptr(dgamma),
+                                  _ptr(dbeta), G, rows, Cch, unscale, _stream()), "bn_bwd_apply")
+
+
+def swish_dropout_fwd(raw, masks, h, B, Cch):
+    n = len(masks)
+    check(_L().mmdyn_swish_dropout_fwd(_ptr(raw), _ptr_array(masks, n), _ptr(h), n, B, Cch, _stream()),
+          "swish_dropout_fwd")
+
+
+def swish_dropout_bwd(raw, masks, dH, dRaw, B, Cch):
+    n = len(masks)
+    check(_L().mmdyn_swish_dropout_bwd(_ptr(raw), _ptr_array(masks, n), _ptr(dH), _ptr(dRaw), n, B, Cch,
+                                       _stream()), "swish_dropout_bwd")
+
+
+def poe_fwd(mu_e, lv_e, use_prior, ld, eps, mu, lv, z, zh, zh2, kl_sum, B, D):
+    n = len(mu_e)
+    check(_L().mmdyn_poe_fwd(_ptr_array(mu_e, 3), _ptr_array(lv_e, 3), n, int(use_prior), ld, _ptr(eps), _ptr(mu),
+                             _ptr(lv), _ptr(z), _ptr(zh), _ptr(zh2), _ptr(kl_sum), B, D, _stream()), "poe_fwd")
+
+
+def poe_bwd(mu_e, lv_e, use_prior, ld, eps, dzs, kl_coef, dmu_e, dlv_e, ld_out, accumulate, B, D):
+    n = len(mu_e)
+    check(_L().mmdyn_poe_bwd(_ptr_array(mu_e, 3), _ptr_array(lv_e, 3), n, int(use_prior), ld, _ptr(eps),
+                             _ptr_array(dzs, 3), kl_coef, _ptr_array(dmu_e, 3), _ptr_array(dlv_e, 3), ld_out,
+                             int(accumulate), B, D, _stream()), "poe_bwd")
+
+
+def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, HW):
+    check(_L().mmdyn_bce_logits(_ptr(logits), _ptr(target), _ptr(mask), _ptr(loss_sum), _ptr(dlogits), gscale, n,
+                                HW, _stream()), "bce_logits")
+
+
+def mse(recon, target, loss_sum, drecon, mult, gscale, n):
+    check(_L().mmdyn_mse(_ptr(recon), _ptr(target), _ptr(loss_sum), _ptr(drecon), mult, gscale, n, _stream()), "mse")
+
+
+def linear_f32_fwd(x, W, b, y, M, N, K, ldx, ldy, act):
+    check(_L().mmdyn_linear_f32_fwd(_ptr(x), _ptr(W), _ptr(b), _ptr(y), M, N, K, ldx, ldy, act, _stream()),
+          "linear_f32_fwd")
+
+
+def linear_f32_bwd(x, W, y, dy, dy_act, dx, dW, db, M, N, K, ldx, ldy, lddx, act, dx_accumulate, scale):
+    check(_L().mmdyn_linear_f32_bwd(_ptr(x), _ptr(W), _ptr(y), _ptr(dy), _ptr(dy_act), _ptr(dx), _ptr(dW), _ptr(db),
+                                    M, N, K, ldx, ldy, lddx, act, int(dx_accumulate), scale, _stream()),
+          "linear_f32_bwd")
+
+
+def colsum_f32(x, out, M, N, ld, scale):
+    check(_L().mmdyn_colsum_f32(_ptr(x), _ptr(out), M, N, ld, scale, _stream()), "colsum_f32")
+
+
+def colsum_f16(x, out, M, N, ld, scale):
+    check(_L().mmdyn_colsum_f16(_ptr(x), _ptr(out), M, N, ld, scale, _stream()), "colsum_f16")
+
+
+def pack_f16(src, idx, dst):
+    check(_L().mmdyn_pack_f16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "pack_f16")
+
+
+def gather_f32(src, idx, dst):
+    check(_L().mmdyn_gather_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_f32")
+
+
+def unpack_add_f32(src, idx, dst):
+    check(_L().mmdyn_unpack_add_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "unpack_add_f32")
+
+
+def f32_to_f16(src, dst, n):
+    check(_L().mmdyn_f32_to_f16(_ptr(src), _ptr(dst), n, _stream()), "f32_to_f16")
+
+
+def adam_flat(p, g, m, v, n, lr, b1, b2, eps, wd, step, gscale=1.0):
+    check(_L().mmdyn_adam_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, step, gscale, _stream()),
+          "adam_flat")
+
+
+def sgd_flat(p, g, buf, n, lr, momentum, wd, first_step, gscale=1.0):
+    check(_L().mmdyn_sgd_flat(_ptr(p), _ptr(g), _ptr(buf), n, lr, momentum, wd, int(first_step), gscale, _stream()),
+          "sgd_flat")
+
+
+def fill_normal(out, n, seed, offset):
+    check(_L().mmdyn_fill_normal(_ptr(out), n, seed, offset, _stream()), "fill_normal")
+
+
+def fill_dropout_mask(out, n, p_drop, seed, offset):
+    check(_L().mmdyn_fill_dropout_mask(_ptr(out), n, p_drop, seed, offset, _stream()), "fill_dropout_mask")

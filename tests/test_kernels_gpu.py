@@ -1,0 +1,478 @@
+"""Kernel-level parity on a real B200: every C-ABI entry point against a torch fp64/fp32 CPU
+reference of the same op, on the layer shapes of the reference model (vae.py:197-216, 263-279).
+
+Tolerances: the tcgen05 kernels take fp16 operands (10-bit mantissa, TF32-equivalent) and
+accumulate in fp32.  References are computed in fp64 from the *same fp16-rounded operands*, so
+the only differences are accumulation order and the output rounding: rel 1e-3 of the output
+scale for fp16 outputs, 1e-5 for fp32 outputs."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from mmdyn_b200 import plan  # noqa: E402
+
+
+def _ops():
+    from mmdyn_b200 import ops
+    return ops
+
+
+DEV = "cuda"
+
+
+def nhwc16(x):
+    return x.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+
+
+def packed(w, idx):
+    ops = _ops()
+    flat = w.reshape(-1).float().to(DEV)
+    Wp = torch.empty(idx.shape, dtype=torch.float16, device=DEV)
+    ops.pack_f16(flat, torch.from_numpy(idx).to(DEV), Wp)
+    return Wp
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def r16(x):
+    return x.half().double()
+
+
+def run_fwd(geom, idx, w, A, n, out_dtype=torch.float16, bias=None, ksplit=1, out_mode=None):
+    ops = _ops()
+    if geom.out_mode == 3:
+        out = torch.zeros(n, 3, geom.OH, geom.OW, dtype=torch.float32, device=DEV)
+    else:
+        out = torch.zeros(n, geom.OH, geom.OW, geom.ldc, dtype=out_dtype, device=DEV)
+    ops.igemm(geom, A, packed(w, idx), out, n, bias=bias, ksplit=ksplit, out_mode=out_mode)
+    torch.cuda.synchronize()
+    return out
+
+
+def conv_case(lp, w, x, stride, pad, transposed, n):
+    op = F.conv_transpose2d if transposed else F.conv2d
+    xr = r16(x).requires_grad_(True)
+    wr = r16(w).requires_grad_(True)
+    y = op(xr, wr, stride=stride, padding=pad)
+    dy = torch.randn_like(y).half().double()
+    y.backward(dy)
+    return xr, wr, y.detach(), dy
+
+
+def check_conv_layer(lp, w, x, stride, pad, transposed, grad_pad=None):
+    ops = _ops()
+    n = x.shape[0]
+    xr, wr, y, dy = conv_case(lp, w, x, stride, pad, transposed, n)
+    # forward
+    out = run_fwd(lp.fwd, lp.idx_fwd, w, nhwc16(x), n)
+    if lp.fwd.out_mode == 3:
+        assert rel_err(out, y) < 1e-5 * 50, rel_err(out, y)
+    else:
+        assert rel_err(out.permute(0, 3, 1, 2)[:, :y.shape[1]], y) < 1e-3
+    # dgrad
+    dyn = dy.float()
+    if grad_pad:
+        dyn = torch.cat([dyn, torch.zeros(n, grad_pad - dyn.shape[1], *dyn.shape[2:])], 1)
+    dA = nhwc16(dyn)
+    dx = run_fwd(lp.dgrad, lp.idx_dgrad, w, dA, n)
+    assert rel_err(dx.permute(0, 3, 1, 2)[:, :x.shape[1]], xr.grad) < 1e-3
+    # wgrad
+    if transposed:
+        G, Nat = dA, nhwc16(x)
+    else:
+        G, Nat = nhwc16(x), dA
+    dWp = torch.zeros(lp.wgrad.Cn, lp.wgrad.K, dtype=torch.float32, device=DEV)
+    ops.wgrad(lp.wgrad, G, Nat, dWp, n, scale=0.5, row_splits=plan.choose_row_splits(lp.wgrad, n))
+    dW = torch.zeros(w.numel(), dtype=torch.float32, device=DEV)
+    ops.unpack_add_f32(dWp, torch.from_numpy(lp.idx_wgrad).to(DEV), dW)
+    torch.cuda.synchronize()
+    assert rel_err(dW, 0.5 * wr.grad.reshape(-1)) < 2e-5
+
+
+def test_library_loads_and_inits():
+    from mmdyn_b200 import lib
+    l = lib.init(0)
+    assert l.mmdyn_version() >= 100
+
+
+@pytest.mark.parametrize("n", [3, 40])
+def test_conv2_s2(n):
+    torch.manual_seed(1)
+    w = torch.randn(64, 32, 4, 4) * 0.05
+    x = torch.randn(n, 32, 32, 32)
+    check_conv_layer(plan.conv_s2_plan("c2", 0, 32, 64, 32), w, x, 2, 1, False)
+
+
+def test_conv3_s2():
+    torch.manual_seed(2)
+    w = torch.randn(128, 64, 4, 4) * 0.05
+    x = torch.randn(5, 64, 16, 16)
+    check_conv_layer(plan.conv_s2_plan("c3", 0, 64, 128, 16), w, x, 2, 1, False)
+
+
+@pytest.mark.parametrize("n", [7, 130])
+def test_conv4_k4s1p0(n):
+    torch.manual_seed(3)
+    w = torch.randn(256, 128, 4, 4) * 0.03
+    x = torch.randn(n, 128, 8, 8)
+    check_conv_layer(plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), w, x, 1, 0, False)
+
+
+@pytest.mark.parametrize("n", [7, 130])
+def test_deconv1_k4s1p0(n):
+    torch.manual_seed(4)
+    w = torch.randn(256, 128, 4, 4) * 0.03
+    x = torch.randn(n, 256, 5, 5)
+    check_conv_layer(plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), w, x, 1, 0, True)
+
+
+def test_deconv2_s2():
+    torch.manual_seed(5)
+    w = torch.randn(128, 64, 4, 4) * 0.05
+    x = torch.randn(5, 128, 8, 8)
+    check_conv_layer(plan.deconv_s2_plan("d2", 0, 128, 64, 8), w, x, 2, 1, True)
+
+
+def test_deconv3_s2():
+    torch.manual_seed(6)
+    w = torch.randn(64, 32, 4, 4) * 0.05
+    x = torch.randn(3, 64, 16, 16)
+    check_conv_layer(plan.deconv_s2_plan("d3", 0, 64, 32, 16), w, x, 2, 1, True)
+
+
+def test_deconv4_out():
+    torch.manual_seed(7)
+    w = torch.randn(32, 3, 4, 4) * 0.1
+    x = torch.randn(3, 32, 32, 32)
+    check_conv_layer(plan.deconv_out_plan("d4", 0, 32, 3, 32), w, x, 2, 1, True, grad_pad=8)
+
+
+@pytest.mark.parametrize("M", [5, 128, 300])
+def test_linear_fc_splitk_and_heads(M):
+    ops = _ops()
+    torch.manual_seed(8)
+    K, N = 6400, 512
+    w = torch.randn(N, K) * 0.01
+    b = torch.randn(N)
+    x = torch.randn(M, K)
+    flat = torch.cat([w.reshape(-1), b])
+    lp = plan.linear_plan("fc", [0], [N * K], K, [N])
+    A = x.half().to(DEV)
+    ref = F.linear(r16(x), r16(w), b.double())
+    for ks in (1, plan.choose_ksplit(lp.fwd, M)):
+        out = torch.zeros(M, N, dtype=torch.float32, device=DEV)
+        bias = flat.to(DEV)[torch.from_numpy(lp.bias_idx).to(DEV).long()].contiguous()
+        ops.igemm(lp.fwd, A, packed(flat, lp.idx_fwd), out, M, bias=bias, ksplit=ks, out_mode=2 if ks > 1 else 1)
+        torch.cuda.synchronize()
+        assert rel_err(out, ref) < 2e-5, (ks, rel_err(out, ref))
+    # dgrad: dx = dy W
+    dy = torch.randn(M, N)
+    dx = torch.zeros(M, K, dtype=torch.float16, device=DEV)
+    ops.igemm(lp.dgrad, dy.half().to(DEV), packed(flat, lp.idx_dgrad), dx, M)
+    torch.cuda.synchronize()
+    assert rel_err(dx, r16(dy) @ r16(w)) < 1e-3
+    # wgrad: dW = dy^T x
+    dW = torch.zeros(N, K, dtype=torch.float32, device=DEV)
+    ops.wgrad(lp.wgrad, A, dy.half().to(DEV), dW, M, scale=1.0, row_splits=plan.choose_row_splits(lp.wgrad, M))
+    torch.cuda.synchronize()
+    assert rel_err(dW, r16(dy).t() @ r16(x)) < 2e-5
+
+
+def test_upsample_linear_permuted_out():
+    ops = _ops()
+    torch.manual_seed(9)
+    K, N, M = 256, 6400, 200
+    w = torch.randn(N, K) * 0.05
+    b = torch.randn(N)
+    flat = torch.cat([w.reshape(-1), b])
+    perm = plan.nhwc_perm(256, 5, 5)
+    lp = plan.linear_plan("up", [0], [N * K], K, [N], n_perm=perm)
+    z = torch.randn(M, K)
+    out = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    bias = flat.to(DEV)[torch.from_numpy(lp.bias_idx).to(DEV).long()].contiguous()
+    ops.igemm(lp.fwd, z.half().to(DEV), packed(flat, lp.idx_fwd), out, M, bias=bias)
+    torch.cuda.synchronize()
+    ref = F.linear(r16(z), r16(w), b.double()).reshape(M, 256, 5, 5).permute(0, 2, 3, 1).reshape(M, -1)
+    assert rel_err(out, ref) < 1e-3
+
+
+def test_conv1_fwd_and_wgrad():
+    ops = _ops()
+    torch.manual_seed(10)
+    n = 5
+    w = torch.randn(32, 3, 4, 4) * 0.2
+    x = torch.rand(n, 3, 64, 64)
+    lp = plan.conv1_plan("c1", 0)
+    out = torch.zeros(n, 32, 32, 32, dtype=torch.float16, device=DEV)
+    ops.conv1_fwd(x.to(DEV), packed(w, lp.idx_fwd), out, n)
+    torch.cuda.synchronize()
+    xr = r16(x)
+    wr = r16(w).requires_grad_(True)
+    y = F.conv2d(xr, wr, stride=2, padding=1)
+    assert rel_err(out.permute(0, 3, 1, 2), y) < 1e-3
+    dy = torch.randn_like(y).half().double()
+    y.backward(dy)
+    dW = torch.zeros(32 * 48, dtype=torch.float32, device=DEV)
+    ops.conv1_wgrad(x.to(DEV), nhwc16(dy.float()), dW, n, 0.25, 64)
+    torch.cuda.synchronize()
+    # the wgrad kernel reads the fp32 input directly (no fp16 rounding of x)
+    wr2 = w.double().requires_grad_(True)
+    F.conv2d(x.double(), wr2, stride=2, padding=1).backward(dy)
+    assert rel_err(dW, 0.25 * wr2.grad.reshape(-1)) < 2e-5
+
+
+@pytest.mark.parametrize("C,rows,G", [(64, 16 * 16 * 6, 1), (32, 32 * 32 * 3, 4), (256, 25 * 5, 3), (128, 64 * 9, 2)])
+def test_grouped_bn_swish_fwd_bwd(C, rows, G):
+    ops = _ops()
+    torch.manual_seed(11)
+    x = (torch.randn(G, rows, C) * 2 + 0.5).half()
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+    rm, rv = torch.zeros(C), torch.ones(C)
+    dy = torch.randn(G, rows, C).half()
+    # reference: per-group training-mode BN + swish in fp64
+    xr = x.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    ys = []
+    for g in range(G):
+        xg = xr[g].t().reshape(1, C, rows)
+        yg = F.batch_norm(xg, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
+        ys.append((yg * torch.sigmoid(yg)).reshape(C, rows).t())
+    y = torch.stack(ys)
+    y.backward(dy.double())
+    # device
+    xd = x.to(DEV)
+    sums = torch.zeros(G, C, 2, device=DEV)
+    ab = torch.empty(G, C, 2, device=DEV)
+    mi = torch.empty(G, C, 2, device=DEV)
+    rmd, rvd = rm.to(DEV), rv.to(DEV)
+    ops.bn_stats(xd, sums, G, rows, C)
+    ops.bn_finalize(sums, gamma.to(DEV), beta.to(DEV), ab, mi, rmd, rvd, G, rows, C, 1e-5, 0.1)
+    yd = torch.empty_like(xd)
+    ops.bn_swish_fwd(xd, ab, yd, G, rows, C)
+    torch.cuda.synchronize()
+    assert rel_err(yd, y) < 1e-3
+    assert rel_err(rmd, rm_ref) < 1e-5 and rel_err(rvd, rv_ref) < 1e-5
+    dyd = dy.to(DEV).clone()
+    sums2 = torch.zeros(G, C, 2, device=DEV)
+    dgam, dbet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ops.bn_swish_bwd_reduce(xd, ab, mi, dyd, sums2, G, rows, C)
+    ops.bn_bwd_apply(xd, ab, mi, sums2, dyd, dgam, dbet, G, rows, C, 0.5)
+    torch.cuda.synchronize()
+    assert rel_err(dyd, xr.grad) < 3e-3
+    assert rel_err(dgam, 0.5 * gr.grad) < 2e-3 and rel_err(dbet, 0.5 * br.grad) < 2e-3
+
+
+def test_plain_swish_fwd_bwd():
+    ops = _ops()
+    torch.manual_seed(12)
+    x = torch.randn(3, 100, 64).half()
+    dy = torch.randn(3, 100, 64).half()
+    xr = x.double().requires_grad_(True)
+    y = xr * torch.sigmoid(xr)
+    y.backward(dy.double())
+    xd, dyd = x.to(DEV), dy.to(DEV).clone()
+    yd = torch.empty_like(xd)
+    ops.bn_swish_fwd(xd, None, yd, 3, 100, 64)
+    ops.bn_swish_bwd_reduce(xd, None, None, dyd, None, 3, 100, 64)
+    torch.cuda.synchronize()
+    assert rel_err(yd, y) < 1e-3 and rel_err(dyd, xr.grad) < 1e-3
+
+
+def test_swish_dropout_fwd_bwd():
+    ops = _ops()
+    torch.manual_seed(13)
+    B, C = 37, 512
+    raw = torch.randn(B, C)
+    masks = [torch.empty(B, C).bernoulli_(0.9) / 0.9 for _ in range(3)] + [None]
+    rr = raw.double().requires_grad_(True)
+    s = rr * torch.sigmoid(rr)
+    hs = torch.stack([s * (m.double() if m is not None else 1.0) for m in masks])
+    dH = torch.randn(4, B, C)
+    hs.backward(dH.double())
+    md = [m.to(DEV) if m is not None else None for m in masks]
+    h = torch.empty(4, B, C, dtype=torch.float16, device=DEV)
+    ops.swish_dropout_fwd(raw.to(DEV), md, h, B, C)
+    dRaw = torch.empty(B, C, dtype=torch.float16, device=DEV)
+    ops.swish_dropout_bwd(raw.to(DEV), md, dH.to(DEV), dRaw, B, C)
+    torch.cuda.synchronize()
+    assert rel_err(h, hs) < 1e-3 and rel_err(dRaw, rr.grad) < 1e-3
+
+
+def _poe_ref(mus, lvs, use_prior, eps_n):
+    """vae.py:311-318 + :52-61 + problems.py:429 in fp64."""
+    if not use_prior and len(mus) == 1:
+        mu, lv = mus[0], lvs[0]
+    else:
+        mu_s = torch.stack(([torch.zeros_like(mus[0])] if use_prior else []) + list(mus))
+        lv_s = torch.stack(([torch.zeros_like(lvs[0])] if use_prior else []) + list(lvs))
+        e = 1e-8
+        var = torch.exp(lv_s) + e
+        T = 1.0 / (var + e)
+        mu = torch.sum(mu_s * T, 0) / torch.sum(T, 0)
+        pvar = 1.0 / torch.sum(T, 0)
+        lv = torch.log(pvar + e)
+    z = eps_n * torch.exp(0.5 * lv) + mu
+    kl = -0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp())
+    return mu, lv, z, kl
+
+
+@pytest.mark.parametrize("n_exp,use_prior", [(1, False), (1, True), (2, True), (3, True)])
+def test_poe_reparam_kl_fwd_bwd(n_exp, use_prior):
+    ops = _ops()
+    torch.manual_seed(14)
+    B, D = 33, 256
+    heads = [torch.randn(B, 2 * D) * 0.7 for _ in range(n_exp)]  # [mu | logvar], ld = 512
+    eps_n = torch.randn(B, D)
+    hr = [h.double().requires_grad_(True) for h in heads]
+    mu, lv, z, kl = _poe_ref([h[:, :D] for h in hr], [h[:, D:] for h in hr], use_prior, eps_n.double())
+    dz = [torch.randn(B, D), None, torch.randn(B, D)]
+    klw = 0.37
+    (klw * kl + (z * (dz[0] + dz[2]).double()).sum()).backward()
+    hd = [h.to(DEV) for h in heads]
+    mu_d, lv_d, z_d = (torch.empty(B, D, device=DEV) for _ in range(3))
+    zh = torch.empty(B, D, dtype=torch.float16, device=DEV)
+    kls = torch.zeros(1, device=DEV)
+    ops.poe_fwd([h[:, :D] for h in hd], [h[:, D:] for h in hd], use_prior, 2 * D, eps_n.to(DEV), mu_d, lv_d, z_d, zh,
+                None, kls, B, D)
+    gd = [torch.zeros(B, 2 * D, device=DEV) for _ in range(n_exp)]
+    ops.poe_bwd([h[:, :D] for h in hd], [h[:, D:] for h in hd], use_prior, 2 * D, eps_n.to(DEV),
+                [d.to(DEV) if d is not None else None for d in dz], klw, [g[:, :D] for g in gd],
+                [g[:, D:] for g in gd], 2 * D, False, B, D)
+    torch.cuda.synchronize()
+    assert rel_err(mu_d, mu) < 1e-5 and rel_err(lv_d, lv) < 1e-5 and rel_err(z_d, z) < 1e-5
+    assert abs(kls.item() - kl.item()) / abs(kl.item()) < 1e-5
+    assert rel_err(zh, z) < 1e-3
+    for g, h in zip(gd, hr):
+        assert rel_err(g, h.grad) < 1e-5
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_bce_logits_and_mse(use_mask):
+    ops = _ops()
+    torch.manual_seed(15)
+    n, HW = 5, 64 * 64
+    x = torch.randn(n, 3, 64, 64) * 3
+    t = torch.rand(n, 3, 64, 64)
+    m = (torch.rand(n, 3, 64, 64) > 0.5).float() if use_mask else None
+    xr = x.double().requires_grad_(True)
+    if use_mask:
+        loss = F.binary_cross_entropy_with_logits(xr * m.double(), t.double() * m.double(), reduction="sum")
+    else:
+        loss = F.binary_cross_entropy_with_logits(xr, t.double(), reduction="sum")
+    loss.backward()
+    ls = torch.zeros(1, device=DEV)
+    dl = torch.empty(n, 64, 64, 8, dtype=torch.float16, device=DEV)
+    ops.bce_logits(x.to(DEV), t.to(DEV), m.to(DEV) if use_mask else None, ls, dl, 2.0, n, HW)
+    torch.cuda.synchronize()
+    assert abs(ls.item() - loss.item()) / loss.item() < 1e-5
+    assert rel_err(dl[..., :3].permute(0, 3, 1, 2), 2.0 * xr.grad) < 1e-3
+    assert dl[..., 3:].abs().max().item() == 0
+    # pose MSE * multiplier
+    r, tt = torch.randn(n, 7), torch.rand(n, 7)
+    rr = r.double().requires_grad_(True)
+    l2 = 1000 * F.mse_loss(rr, tt.double(), reduction="sum")
+    l2.backward()
+    ls2 = torch.zeros(1, device=DEV)
+    dr = torch.empty(n, 7, device=DEV)
+    ops.mse(r.to(DEV), tt.to(DEV), ls2, dr, 1000.0, 0.5, n * 7)
+    torch.cuda.synchronize()
+    assert abs(ls2.item() - l2.item()) / l2.item() < 1e-5 and rel_err(dr, 0.5 * rr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,act", [(50, 512, 7, 1), (130, 512, 512, 0), (64, 7, 512, 0), (33, 512, 256, 1)])
+def test_linear_f32(M, N, K, act):
+    ops = _ops()
+    torch.manual_seed(16)
+    x, w, b = torch.randn(M, K), torch.randn(N, K) * 0.05, torch.randn(N)
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    y = F.linear(xr, wr, br)
+    if act:
+        y = F.relu(y)
+    dy = torch.randn(M, N)
+    y.backward(dy.double())
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    yd = torch.empty(M, N, device=DEV)
+    ops.linear_f32_fwd(xd, wd, bd, yd, M, N, K, K, N, act)
+    dya, dx = torch.empty(M, N, device=DEV), torch.empty(M, K, device=DEV)
+    dW, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    ops.linear_f32_bwd(xd, wd, yd, dy.to(DEV), dya, dx, dW, db, M, N, K, K, N, K, act, False, 0.5)
+    torch.cuda.synchronize()
+    assert rel_err(yd, y) < 1e-5 and rel_err(dx, xr.grad) < 1e-5
+    assert rel_err(dW, 0.5 * wr.grad) < 1e-5 and rel_err(db, 0.5 * br.grad) < 1e-5
+
+
+def test_colsum_pack_gather():
+    ops = _ops()
+    torch.manual_seed(17)
+    x = torch.randn(300, 6400).half()
+    out = torch.zeros(6400, device=DEV)
+    ops.colsum_f16(x.to(DEV), out, 300, 6400, 6400, 0.5)
+    xf = torch.randn(77, 512)
+    out2 = torch.zeros(512, device=DEV)
+    ops.colsum_f32(xf.to(DEV), out2, 77, 512, 512, 2.0)
+    src = torch.randn(1000)
+    idx = torch.randint(-1, 1000, (333,), dtype=torch.int32)
+    g = torch.empty(333, device=DEV)
+    ops.gather_f32(src.to(DEV), idx.to(DEV), g)
+    torch.cuda.synchronize()
+    assert rel_err(out, 0.5 * x.double().sum(0)) < 1e-5
+    assert rel_err(out2, 2.0 * xf.double().sum(0)) < 1e-5
+    ref = torch.where(idx >= 0, src[idx.clamp(min=0).long()], torch.zeros(()))
+    assert torch.equal(g.cpu(), ref)
+
+
+def test_adam_and_sgd_flat_match_torch():
+    ops = _ops()
+    torch.manual_seed(18)
+    n = 100003
+    p0 = torch.randn(n)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=1e-3)
+    pd = p0.to(DEV).clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        g = torch.randn(n) * (10.0 ** (step - 2))
+        pt.grad = g.clone()
+        opt.step()
+        ops.adam_flat(pd, g.to(DEV), m, v, n, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
+    torch.cuda.synchronize()
+    assert (pd.cpu() - pt.detach()).abs().max().item() < 2e-6
+    ps = p0.clone().requires_grad_(True)
+    sgd = torch.optim.SGD([ps], lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    pd2, buf = p0.to(DEV).clone(), torch.zeros(n, device=DEV)
+    for step in range(3):
+        g = torch.randn(n)
+        ps.grad = g.clone()
+        sgd.step()
+        ops.sgd_flat(pd2, g.to(DEV), buf, n, 1e-3, 0.9, 5e-4, step == 0)
+    torch.cuda.synchronize()
+    assert (pd2.cpu() - ps.detach()).abs().max().item() < 2e-6
+
+
+def test_philox_rng_statistics():
+    ops = _ops()
+    n = 1 << 20
+    a = torch.empty(n, device=DEV)
+    ops.fill_normal(a, n, 1234, 0)
+    b = torch.empty(n, device=DEV)
+    ops.fill_normal(b, n, 1234, 0)
+    c = torch.empty(n, device=DEV)
+    ops.fill_normal(c, n, 1234, n)
+    mk = torch.empty(n, device=DEV)
+    ops.fill_dropout_mask(mk, n, 0.1, 99, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1) < 5e-3
+    assert abs(a.pow(4).mean().item() - 3) < 0.1
+    keep = (mk > 0).float().mean().item()
+    assert abs(keep - 0.9) < 2e-3
+    assert torch.all((mk == 0) | ((mk - 1 / 0.9).abs() < 1e-6))

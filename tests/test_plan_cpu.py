@@ -1,0 +1,118 @@
+"""Host planning logic (tap tables, sub-pixel phases, weight pack maps) against torch conv ops."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mmdyn_b200 import plan
+from tests import emul
+
+torch.manual_seed(0)
+torch.set_default_dtype(torch.float64)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().double().numpy()
+
+
+def check_layer(lp, w, x, y_ref, dy, stride, pad, transposed, cin_pad=None):
+    n = x.shape[0]
+    flat = w.detach().double().reshape(-1).numpy()
+    # forward
+    if lp.fwd is not None:
+        out = emul.igemm(lp.fwd, nhwc(x), emul.pack(flat, lp.idx_fwd), n)
+        if lp.fwd.out_mode == 3:
+            np.testing.assert_allclose(out, y_ref.double().numpy(), atol=1e-9)
+        else:
+            np.testing.assert_allclose(out[..., :y_ref.shape[1]], nhwc(y_ref), atol=1e-9)
+    # reference grads
+    xr = x.clone().double().requires_grad_(True)
+    wr = w.clone().double().requires_grad_(True)
+    op = F.conv_transpose2d if transposed else F.conv2d
+    yr = op(xr, wr, stride=stride, padding=pad)
+    yr.backward(dy.double())
+    dyn = nhwc(dy)
+    if cin_pad:
+        dyn = np.concatenate([dyn, np.zeros(dyn.shape[:-1] + (cin_pad - dyn.shape[-1],))], -1)
+    dx = emul.igemm(lp.dgrad, dyn, emul.pack(flat, lp.idx_dgrad), n)
+    np.testing.assert_allclose(dx[..., :x.shape[1]], nhwc(xr.grad), atol=1e-9)
+    # weight gradient
+    if transposed:
+        G, Nat = dyn, nhwc(x).reshape(n, -1, x.shape[1])
+    else:
+        G, Nat = nhwc(x), dyn.reshape(n, -1, dyn.shape[-1])
+    dWp = emul.wgrad(lp.wgrad, G, Nat, n)
+    dW = emul.unpack_add(dWp, lp.idx_wgrad, flat.size)
+    np.testing.assert_allclose(dW, wr.grad.reshape(-1).numpy(), atol=1e-8)
+
+
+@pytest.mark.parametrize("Cin,Cout,H", [(32, 64, 8), (64, 128, 4)])
+def test_conv_s2(Cin, Cout, H):
+    w = torch.randn(Cout, Cin, 4, 4)
+    x = torch.randn(2, Cin, H, H)
+    y = F.conv2d(x, w, stride=2, padding=1)
+    check_layer(plan.conv_s2_plan("c", 0, Cin, Cout, H), w, x, y, torch.randn_like(y), 2, 1, False)
+
+
+def test_conv_k4s1p0():
+    w = torch.randn(256, 128, 4, 4)
+    x = torch.randn(2, 128, 8, 8)
+    y = F.conv2d(x, w)
+    check_layer(plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), w, x, y, torch.randn_like(y), 1, 0, False)
+
+
+def test_deconv_k4s1p0():
+    w = torch.randn(256, 128, 4, 4)
+    x = torch.randn(2, 256, 5, 5)
+    y = F.conv_transpose2d(x, w)
+    check_layer(plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), w, x, y, torch.randn_like(y), 1, 0, True)
+
+
+@pytest.mark.parametrize("Cin,Cout,H", [(128, 64, 4), (64, 32, 8)])
+def test_deconv_s2(Cin, Cout, H):
+    w = torch.randn(Cin, Cout, 4, 4)
+    x = torch.randn(2, Cin, H, H)
+    y = F.conv_transpose2d(x, w, stride=2, padding=1)
+    check_layer(plan.deconv_s2_plan("d", 0, Cin, Cout, H), w, x, y, torch.randn_like(y), 2, 1, True)
+
+
+def test_deconv_out():
+    w = torch.randn(32, 3, 4, 4)
+    x = torch.randn(2, 32, 8, 8)
+    y = F.conv_transpose2d(x, w, stride=2, padding=1)
+    check_layer(plan.deconv_out_plan("d4", 0, 32, 3, 8), w, x, y, torch.randn_like(y), 2, 1, True, cin_pad=8)
+
+
+def test_linear_permuted_and_concat():
+    K, N1, N2 = 128, 64, 64
+    w1, w2 = torch.randn(N1, K), torch.randn(N2, K)
+    b1, b2 = torch.randn(N1), torch.randn(N2)
+    flat = torch.cat([w1.reshape(-1), b1, w2.reshape(-1), b2]).double().numpy()
+    offs = [0, N1 * K, N1 * K + N1, N1 * K + N1 + N2 * K]
+    kperm = np.random.RandomState(0).permutation(K)
+    lp = plan.linear_plan("heads", [offs[0], offs[2]], [offs[1], offs[3]], K, [N1, N2], k_perm=kperm)
+    x = torch.randn(5, K)
+    xp = x[:, kperm].double().numpy().reshape(5, 1, 1, K)
+    out = emul.igemm(lp.fwd, xp, emul.pack(flat, lp.idx_fwd), 5, bias=flat[lp.bias_idx])
+    ref = torch.cat([F.linear(x, w1, b1), F.linear(x, w2, b2)], 1).double().numpy()
+    np.testing.assert_allclose(out.reshape(5, -1), ref, atol=1e-9)
+    dy = torch.randn(5, N1 + N2).double().numpy()
+    dx = emul.igemm(lp.dgrad, dy.reshape(5, 1, 1, -1), emul.pack(flat, lp.idx_dgrad), 5).reshape(5, K)
+    dx_ref = dy @ torch.cat([w1, w2], 0).double().numpy()
+    np.testing.assert_allclose(dx, dx_ref[:, kperm], atol=1e-9)
+
+
+def test_nhwc_perm_matches_flatten():
+    x = torch.randn(2, 256, 5, 5)
+    perm = plan.nhwc_perm(256, 5, 5)
+    a = x.permute(0, 2, 3, 1).reshape(2, -1)
+    b = x.reshape(2, -1)[:, perm]
+    assert torch.equal(a, b)
+
+
+def test_heuristics():
+    lp = plan.linear_plan("fc", [0], [6400 * 512], 6400, [512])
+    assert plan.choose_ksplit(lp.fwd, 128) > 1
+    assert plan.choose_ksplit(lp.fwd, 128 * 200) == 1
+    c2 = plan.conv_s2_plan("c2", 0, 32, 64, 32)
+    assert plan.choose_row_splits(c2.wgrad, 128) >= 1
