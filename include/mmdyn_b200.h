@@ -116,11 +116,13 @@ int mmdyn_conv1_wgrad(const float* x_nchw, const void* dRaw, float* dW /*[32][48
  */
 int mmdyn_bn_stats(const void* x, float* sums /*[G][C][2] zeroed*/, int G, int rows_per_group,
                    int C, void* stream);
-/* mean/invstd -> scale/shift (a = gamma*invstd, b = beta - mean*a); running stats updated once
- * per group in group order with `momentum`, unbiased variance (torch semantics). */
+/* mean/invstd -> scale/shift (a = gamma*invstd, b = beta - mean*a); running stats updated
+ * `stat_repeat` times per group, in group order, with `momentum` and the unbiased variance (torch
+ * semantics; stat_repeat > 1 replays the update for passes that share one trunk evaluation). */
 int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* ab /*[G][C][2]*/,
                       float* mean_invstd /*[G][C][2]*/, float* running_mean, float* running_var,
-                      int G, int rows_per_group, int C, float eps, float momentum, void* stream);
+                      int G, int rows_per_group, int C, float eps, float momentum, int stat_repeat,
+                      void* stream);
 /* y = swish(a*x + b); ab == NULL means identity affine (plain Swish) */
 int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_per_group, int C,
                        void* stream);
@@ -144,7 +146,7 @@ int mmdyn_swish_dropout_bwd(const float* raw, const float* const* masks, const f
                             void* dRaw, int n_masks, int B, int C, void* stream);
 
 /* --- ProductOfExperts + reparametrisation + KL (vae.py:52-61, 139-157, 311-328; problems.py:406,429)
- * experts: up to 3 (mu_e, logvar_e) pairs [B][D] fp32 with row stride `ld`; the prior expert
+ * experts: up to 4 (mu_e, logvar_e) pairs [B][D] fp32 with row stride `ld`; the prior expert
  * N(0, I) is implicit when use_prior != 0 (MVAE); with use_prior == 0 and one expert this is the
  * plain VAE posterior (vae.py:84-85).  Outputs: mu, logvar (posterior), z = eps*exp(0.5 logvar)+mu
  * (fp32 [B][D]) and zh / zh2 (optional fp16 copies of z: the operand rows of up to two decoders); kl_sum += -0.5*sum(1+lv-mu^2-e^lv).
@@ -152,12 +154,15 @@ int mmdyn_swish_dropout_bwd(const float* raw, const float* const* masks, const f
 int mmdyn_poe_fwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
                   int ld, const float* eps, float* mu, float* lv, float* z, void* zh, void* zh2,
                   float* kl_sum, int B, int D, void* stream);
-/* backward: dmu_e/dlv_e[e] (+)= grads through z and KL (kl_coef = kl_weight * grad scale);
- * dz[0..2]: up to three (nullable) fp32 [B][D] gradients w.r.t. z, one per decoder, summed here;
+/* backward: dmu_e/dlv_e[e] (+)= grads through z, KL and (optionally) direct upstream gradients of
+ * the posterior.  kl_coef = kl_weight * grad scale; dz[0..2]: up to three (nullable) fp32 [B][D]
+ * gradients w.r.t. z, one per decoder, summed here; dmu_in / dlv_in (nullable, [B][D]) are added
+ * to dL/dmu and dL/dlogvar (loss terms computed outside the library on the posterior);
  * accumulate != 0 adds into dmu_e/dlv_e (row stride ld_out) */
 int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
-                  int ld, const float* eps, const float* const* dz, float kl_coef, float* const* dmu_e,
-                  float* const* dlv_e, int ld_out, int accumulate, int B, int D, void* stream);
+                  int ld, const float* eps, const float* const* dz, const float* dmu_in,
+                  const float* dlv_in, float kl_coef, float* const* dmu_e, float* const* dlv_e,
+                  int ld_out, int accumulate, int B, int D, void* stream);
 
 /* --- reconstruction losses (problems.py:409-413, 431-449, 499-503, 535) -----------------------
  * BCE-with-logits, reduction 'sum' into loss_sum[0]; dlogits (fp16 NHWC, 8 channels per pixel,
@@ -194,7 +199,14 @@ int mmdyn_gather_f32(const float* src, const int32_t* idx, float* dst, long long
  * each parameter element appears at most once in idx */
 int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float* dst, long long n,
                          void* stream);
-int mmdyn_f32_to_f16(const float* src, void* dst, long long n, void* stream);
+/* dst = fp16(scale * src) */
+int mmdyn_f32_to_f16(const float* src, void* dst, long long n, float scale, void* stream);
+/* x *= s in place */
+int mmdyn_scale_f32(float* x, long long n, float s, void* stream);
+/* fp32 NCHW (n,3,H,W) logit gradients -> fp16 NHWC8 (3 used) times scale: the layout the decoder
+ * backward reads (used when the loss is computed outside the library, e.g. by torch autograd) */
+int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int HW,
+                          void* stream);
 
 /* --- fused Adam over a flat fp32 arena (problems.py:138,155; torch.optim.Adam defaults) --------
  * p, g, m, v: [n] fp32.  step_count is the 1-based step AFTER this update (bias correction).
@@ -208,9 +220,13 @@ int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n, float lr, 
 
 /* --- deterministic device RNG (Philox4x32-10) for eps / dropout masks --------------------------
  * replaces torch.randn (vae.py:58) and nn.Dropout's mask (vae.py:213) on the fast path */
-int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset, void* stream);
+/* the Philox counter of element block i is (*ctr_dev if ctr_dev else 0) + offset + i; keeping the
+ * running counter in device memory lets a captured CUDA graph draw fresh numbers at every replay */
+int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset,
+                      const uint64_t* ctr_dev, void* stream);
 int mmdyn_fill_dropout_mask(float* out, long long n, float p_drop, uint64_t seed, uint64_t offset,
-                            void* stream);
+                            const uint64_t* ctr_dev, void* stream);
+int mmdyn_rng_advance(uint64_t* ctr_dev, uint64_t inc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -89,7 +89,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    const float* __restrict__ beta, float* __restrict__ ab,
                                    float* __restrict__ mean_invstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int G, int n, int C, float eps,
-                                   float momentum) {
+                                   float momentum, int stat_repeat) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float inv_n = 1.0f / static_cast<float>(n);
@@ -107,8 +107,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
     ab[(g * C + c) * 2 + 1] = be - mean * a;
     mean_invstd[(g * C + c) * 2] = mean;
     mean_invstd[(g * C + c) * 2 + 1] = invstd;
-    rm = (1.0f - momentum) * rm + momentum * mean;
-    rv = (1.0f - momentum) * rv + momentum * var * unbias;
+    for (int q = 0; q < stat_repeat; ++q) {
+      rm = (1.0f - momentum) * rm + momentum * mean;
+      rv = (1.0f - momentum) * rv + momentum * var * unbias;
+    }
   }
   if (running_mean) running_mean[c] = rm;
   if (running_var) running_var[c] = rv;
@@ -287,11 +289,12 @@ swish_dropout_bwd_kernel(const float* __restrict__ raw, MaskPtrs masks, const fl
 // ---------------------------------------------------------------------------------------------
 // ProductOfExperts + reparametrisation + KL
 // ---------------------------------------------------------------------------------------------
+constexpr int MAX_EXPERTS = 4;
 struct ExpertPtrs {
-  const float* mu[3];
-  const float* lv[3];
-  float* dmu[3];
-  float* dlv[3];
+  const float* mu[MAX_EXPERTS];
+  const float* lv[MAX_EXPERTS];
+  float* dmu[MAX_EXPERTS];
+  float* dlv[MAX_EXPERTS];
   const float* dz[3];
 };
 constexpr float POE_EPS = 1e-8f;
@@ -348,7 +351,8 @@ poe_fwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
 
 __global__ void __launch_bounds__(256)
 poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
-               float kl_coef, int ld_out, int accumulate, int B, int D) {
+               const float* __restrict__ dmu_in, const float* __restrict__ dlv_in, float kl_coef, int ld_out,
+               int accumulate, int B, int D) {
   const long long n = static_cast<long long>(B) * D;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -361,8 +365,9 @@ poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
       if (ex.dz[q]) g += ex.dz[q][i];
     if (!use_prior && n_experts == 1) {
       const float mu = ex.mu[0][ei], lv = ex.lv[0][ei];
-      const float dmu = g + kl_coef * mu;
-      const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f);
+      const float dmu = g + kl_coef * mu + (dmu_in ? dmu_in[i] : 0.0f);
+      const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f) +
+                        (dlv_in ? dlv_in[i] : 0.0f);
       if (accumulate) {
         ex.dmu[0][oi] += dmu;
         ex.dlv[0][oi] += dlv;
@@ -372,7 +377,7 @@ poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
       }
       continue;
     }
-    float st = 0.0f, sm = 0.0f, t_e[3], elv[3];
+    float st = 0.0f, sm = 0.0f, t_e[MAX_EXPERTS], elv[MAX_EXPERTS];
     if (use_prior) st = 1.0f / ((1.0f + POE_EPS) + POE_EPS);
     for (int e = 0; e < n_experts; ++e) {
       elv[e] = expf(ex.lv[e][ei]);
@@ -383,8 +388,9 @@ poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
     const float mu = sm / st;
     const float pvar = 1.0f / st;
     const float lv = logf(pvar + POE_EPS);
-    const float dmu = g + kl_coef * mu;
-    const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f);
+    const float dmu = g + kl_coef * mu + (dmu_in ? dmu_in[i] : 0.0f);
+    const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f) +
+                      (dlv_in ? dlv_in[i] : 0.0f);
     const float dpvar = dlv / (pvar + POE_EPS);
     const float dsm = dmu / st;
     const float dst = -dpvar * pvar * pvar - dmu * mu / st;
@@ -536,10 +542,31 @@ unpack_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx
 }
 
 __global__ void __launch_bounds__(256)
-f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, float scale) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    dst[i] = __float2half_rn(src[i]);
+    dst[i] = __float2half_rn(scale * src[i]);
+}
+
+__global__ void __launch_bounds__(256)
+scale_f32_kernel(float* __restrict__ x, long long n, float s) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    x[i] *= s;
+}
+
+__global__ void __launch_bounds__(256)
+logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, float scale, long long n_pix,
+                       int HW) {
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long img = p / HW;
+    const int hw = static_cast<int>(p - img * HW);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = scale * dl[(img * 3 + c) * HW + hw];
+    reinterpret_cast<uint4*>(out)[p] = pack8(g);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -619,7 +646,9 @@ __device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
 }
 
 __global__ void __launch_bounds__(256)
-fill_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset) {
+fill_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset,
+                   const uint64_t* __restrict__ ctr) {
+  if (ctr) offset += *ctr;
   const long long n4 = (n + 3) >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -640,7 +669,8 @@ fill_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t
 
 __global__ void __launch_bounds__(256)
 fill_dropout_kernel(float* __restrict__ out, long long n, float p_drop, float keep_scale, uint64_t seed,
-                    uint64_t offset) {
+                    uint64_t offset, const uint64_t* __restrict__ ctr) {
+  if (ctr) offset += *ctr;
   const long long n4 = (n + 3) >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -653,6 +683,8 @@ fill_dropout_kernel(float* __restrict__ out, long long n, float p_drop, float ke
       if (4 * i + q < n) out[4 * i + q] = (u01(w[q]) > p_drop) ? keep_scale : 0.0f;
   }
 }
+
+__global__ void rng_advance_kernel(uint64_t* ctr, uint64_t inc) { *ctr += inc; }
 
 inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 8) {
   long long b = (n + threads - 1) / threads;
@@ -693,10 +725,12 @@ extern "C" int mmdyn_bn_stats(const void* x, float* sums, int G, int rows_per_gr
 
 extern "C" int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* ab,
                                  float* mean_invstd, float* running_mean, float* running_var, int G,
-                                 int rows_per_group, int C, float eps, float momentum, void* stream) {
+                                 int rows_per_group, int C, float eps, float momentum, int stat_repeat,
+                                 void* stream) {
   MMDYN_REQUIRE(sums && gamma && beta && ab && mean_invstd && G > 0 && C > 0, "bn_finalize: bad arguments");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, gamma, beta, ab, mean_invstd, running_mean,
-                                                               running_var, G, rows_per_group, C, eps, momentum);
+                                                               running_var, G, rows_per_group, C, eps, momentum,
+                                                               stat_repeat);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -775,7 +809,7 @@ extern "C" int mmdyn_swish_dropout_bwd(const float* raw, const float* const* mas
 extern "C" int mmdyn_poe_fwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
                              int ld, const float* eps, float* mu, float* lv, float* z, void* zh, void* zh2,
                              float* kl_sum, int B, int D, void* stream) {
-  MMDYN_REQUIRE(n_experts >= 0 && n_experts <= 3 && (n_experts > 0 || use_prior), "poe_fwd: n_experts=%d", n_experts);
+  MMDYN_REQUIRE(n_experts >= 0 && n_experts <= MAX_EXPERTS && (n_experts > 0 || use_prior), "poe_fwd: n_experts=%d", n_experts);
   MMDYN_REQUIRE(eps && mu && lv && z && kl_sum && B > 0 && D > 0, "poe_fwd: null pointer");
   ExpertPtrs ex = {};
   for (int e = 0; e < n_experts; ++e) {
@@ -792,9 +826,10 @@ extern "C" int mmdyn_poe_fwd(const float* const* mu_e, const float* const* lv_e,
 }
 
 extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_experts, int use_prior,
-                             int ld, const float* eps, const float* const* dz, float kl_coef, float* const* dmu_e,
+                             int ld, const float* eps, const float* const* dz, const float* dmu_in,
+                             const float* dlv_in, float kl_coef, float* const* dmu_e,
                              float* const* dlv_e, int ld_out, int accumulate, int B, int D, void* stream) {
-  MMDYN_REQUIRE(n_experts >= 0 && n_experts <= 3, "poe_bwd: n_experts=%d", n_experts);
+  MMDYN_REQUIRE(n_experts >= 0 && n_experts <= MAX_EXPERTS, "poe_bwd: n_experts=%d", n_experts);
   if (n_experts == 0) return MMDYN_OK;
   MMDYN_REQUIRE(eps && B > 0 && D > 0, "poe_bwd: null pointer");
   ExpertPtrs ex = {};
@@ -807,8 +842,8 @@ extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e,
   }
   for (int q = 0; q < 3; ++q) ex.dz[q] = dz ? dz[q] : nullptr;
   const long long n = static_cast<long long>(B) * D;
-  poe_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(ex, n_experts, use_prior, ld, eps, kl_coef, ld_out,
-                                                      accumulate, B, D);
+  poe_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(ex, n_experts, use_prior, ld, eps, dmu_in, dlv_in, kl_coef,
+                                                      ld_out, accumulate, B, D);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -879,9 +914,26 @@ extern "C" int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float*
   return MMDYN_OK;
 }
 
-extern "C" int mmdyn_f32_to_f16(const float* src, void* dst, long long n, void* stream) {
+extern "C" int mmdyn_f32_to_f16(const float* src, void* dst, long long n, float scale, void* stream) {
   MMDYN_REQUIRE(src && dst && n > 0, "f32_to_f16: bad arguments");
-  f32_to_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, reinterpret_cast<__half*>(dst), n);
+  f32_to_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, reinterpret_cast<__half*>(dst), n, scale);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_scale_f32(float* x, long long n, float s, void* stream) {
+  MMDYN_REQUIRE(x && n > 0, "scale_f32: bad arguments");
+  scale_f32_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(x, n, s);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int HW,
+                                     void* stream) {
+  MMDYN_REQUIRE(dlogits_nchw && out_nhwc8 && n > 0 && HW > 0, "logit_grad_pack: bad arguments");
+  const long long n_pix = static_cast<long long>(n) * HW;
+  logit_grad_pack_kernel<<<grid_for(n_pix), 256, 0, ST(stream)>>>(dlogits_nchw, reinterpret_cast<__half*>(out_nhwc8),
+                                                                  scale, n_pix, HW);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -910,18 +962,26 @@ extern "C" int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n,
   return MMDYN_OK;
 }
 
-extern "C" int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int mmdyn_rng_advance(uint64_t* ctr_dev, uint64_t inc, void* stream) {
+  MMDYN_REQUIRE(ctr_dev, "rng_advance: null counter");
+  rng_advance_kernel<<<1, 1, 0, ST(stream)>>>(ctr_dev, inc);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset, const uint64_t* ctr_dev,
+                                 void* stream) {
   MMDYN_REQUIRE(out && n > 0, "fill_normal: bad arguments");
-  fill_normal_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, seed, offset);
+  fill_normal_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, seed, offset, ctr_dev);
   LAUNCHED();
   return MMDYN_OK;
 }
 
 extern "C" int mmdyn_fill_dropout_mask(float* out, long long n, float p_drop, uint64_t seed, uint64_t offset,
-                                       void* stream) {
+                                       const uint64_t* ctr_dev, void* stream) {
   MMDYN_REQUIRE(out && n > 0 && p_drop >= 0.0f && p_drop < 1.0f, "fill_dropout_mask: bad arguments");
   fill_dropout_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, p_drop, 1.0f / (1.0f - p_drop), seed,
-                                                                      offset);
+                                                                      offset, ctr_dev);
   LAUNCHED();
   return MMDYN_OK;
 }

@@ -1,0 +1,776 @@
+"""Execution engine of the cnn-vae / cnn-mvae step on top of the C-ABI kernels (ops.py).
+
+Pieces
+  ParamArena   one flat fp32 parameter arena + one flat gradient arena; every nn.Parameter of the
+               model becomes a view (so torch optimizers / state_dict / .to() plumbing keep
+               working, and the fused Adam and the gradient all-reduce see one buffer).
+  PackedLayer  fp16 K-contiguous operand copies of the weights (forward and dgrad packing),
+               refreshed by one gather kernel per layer whenever the arena changes.
+  EncoderExec / DecoderExec / PoseExec
+               forward + hand-written backward of the three network kinds of the reference
+               (vae.py:179-301), batched over "groups" (= sub-sampled passes) with per-group
+               BatchNorm statistics.
+  StepEngine   the whole training / evaluation step of Reconstruction._evaluate_mvae and
+               SeqModeling._evaluate_model (problems.py:473-546, 683-716): image-encoder trunks run
+               ONCE and are shared by the passes that use them (only the Dropout mask differs),
+               the loss-bearing decoder invocations of all passes run as one group-batched launch
+               sequence, PoE/reparam/KL, losses, full backward into the gradient arena.
+
+Gradients are carried through the fp16 backward tensors multiplied by `grad_scale` (default: the
+batch size, which makes dlogits = sigmoid(x) - t exactly) and un-scaled in fp32 where they are
+reduced into parameter gradients.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import ops, plan
+
+F16, F32 = torch.float16, torch.float32
+LATENT_HEADS = 512  # [mu | logvar] of a 256-d latent
+
+
+# ---------------------------------------------------------------------------------------------
+# allocation helpers
+# ---------------------------------------------------------------------------------------------
+class FreshAlloc:
+    """New tensors on every call (module-level API: activations are owned by the autograd ctx)."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __call__(self, key, shape, dtype, zero=False):
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+
+
+class Workspace:
+    """Persistent named buffers (fused step: stable addresses, CUDA-graph friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def __call__(self, key, shape, dtype, zero=False):
+        shape = tuple(int(s) for s in shape)
+        t = self.bufs.get(key)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter arena
+# ---------------------------------------------------------------------------------------------
+class ParamArena:
+    ALIGN = 4  # floats (16 bytes)
+
+    def __init__(self, module):
+        self.module = module
+        named = list(module.named_parameters())
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.offset, self.numel = {}, {}
+        off = 0
+        for n, p in named:
+            self.offset[n] = off
+            self.numel[n] = p.numel()
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.total = off
+        self.flat = None
+        self.grad = None
+        self.manual_version = 0
+
+    def _is_bound(self, device):
+        if self.flat is None or self.flat.device != device:
+            return False
+        base = self.flat.data_ptr()
+        for n, p in zip(self.names, self.params):
+            if p.data_ptr() != base + 4 * self.offset[n] or not p.is_contiguous():
+                return False
+        return True
+
+    def ensure(self, device=None):
+        """Make every parameter a view of the flat arena on `device` (idempotent)."""
+        device = torch.device(device) if device is not None else self.params[0].device
+        if device.type != "cuda":
+            raise RuntimeError("mmdyn_b200 has no CPU path: move the model to a CUDA device (B200)")
+        if self._is_bound(device):
+            return False
+        flat = torch.zeros(self.total, dtype=F32, device=device)
+        with torch.no_grad():
+            for n, p in zip(self.names, self.params):
+                o, k = self.offset[n], self.numel[n]
+                flat[o:o + k].copy_(p.data.reshape(-1))
+                p.data = flat[o:o + k].view(p.shape)
+        self.flat = flat
+        self.grad = torch.zeros(self.total, dtype=F32, device=device)
+        for p in self.params:
+            p.grad = None
+        self.manual_version += 1
+        return True
+
+    def view(self, name, of=None):
+        o, k = self.offset[name], self.numel[name]
+        return (self.flat if of is None else of)[o:o + k]
+
+    def attach_grads(self):
+        """p.grad := view of the gradient arena (zeroed where it was None, like a fresh backward)."""
+        base = self.grad.data_ptr()
+        missing = [i for i, p in enumerate(self.params)
+                   if p.grad is None or p.grad.data_ptr() != base + 4 * self.offset[self.names[i]]]
+        if not missing:
+            return
+        if len(missing) == len(self.params):
+            self.grad.zero_()
+        for i in missing:
+            n, p = self.names[i], self.params[i]
+            g = self.view(n, self.grad)
+            if len(missing) != len(self.params):
+                g.zero_()
+            p.grad = g.view(p.shape)
+
+    def token(self):
+        return (id(self.flat), self.flat._version, self.manual_version)
+
+    def bump(self):
+        self.manual_version += 1
+
+
+def get_arena(module, device=None):
+    arena = module.__dict__.get("_mmdyn_arena")
+    if arena is None:
+        arena = ParamArena(module)
+        module.__dict__["_mmdyn_arena"] = arena
+    arena.ensure(device)
+    return arena
+
+
+# ---------------------------------------------------------------------------------------------
+# packed layers
+# ---------------------------------------------------------------------------------------------
+class PackedLayer:
+    def __init__(self, lp, device, cache):
+        self.lp = lp
+        self.device = device
+
+        def up(a):
+            if a is None:
+                return None
+            t = cache.get(id(a))
+            if t is None:
+                t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+                cache[id(a)] = t
+            return t
+        self.idx_fwd, self.idx_dgrad = up(lp.idx_fwd), up(lp.idx_dgrad)
+        self.idx_wgrad, self.bias_idx = up(lp.idx_wgrad), up(lp.bias_idx)
+        self.Wf = torch.empty(lp.idx_fwd.shape, dtype=F16, device=device) if lp.idx_fwd is not None else None
+        self.Wd = torch.empty(lp.idx_dgrad.shape, dtype=F16, device=device) if lp.idx_dgrad is not None else None
+        self.bias = torch.empty(lp.bias_idx.shape, dtype=F32, device=device) if lp.bias_idx is not None else None
+
+    def refresh(self, flat):
+        if self.Wf is not None:
+            ops.pack_f16(flat, self.idx_fwd, self.Wf)
+        if self.Wd is not None:
+            ops.pack_f16(flat, self.idx_dgrad, self.Wd)
+        if self.bias is not None:
+            ops.gather_f32(flat, self.bias_idx, self.bias)
+
+
+class _NetBase:
+    def __init__(self, arena, prefix, device):
+        self.arena, self.prefix, self.device = arena, prefix, device
+        self.layers = []
+        self._cache = {}
+        self._token = None
+
+    def _pl(self, lp):
+        pl = PackedLayer(lp, self.device, self._cache)
+        self.layers.append(pl)
+        return pl
+
+    def _full(self, name):
+        return self.prefix + "." + name if self.prefix else name
+
+    def off(self, name):
+        return self.arena.offset[self._full(name)]
+
+    def pview(self, name, grad=False):
+        return self.arena.view(self._full(name), self.arena.grad if grad else None)
+
+    def buf(self, name):
+        return self.arena.module.get_buffer(self._full(name))
+
+    def refresh(self):
+        tok = self.arena.token()
+        if tok != self._token:
+            for pl in self.layers:
+                pl.refresh(self.arena.flat)
+            self._token = tok
+
+
+def _gemm(pl_geom, A, W, out, n_img, bias, f32_out, alloc_zero=None):
+    """igemm with an automatic split-K decision for fp32 outputs."""
+    ks = plan.choose_ksplit(pl_geom, n_img) if f32_out else 1
+    if ks > 1:
+        out.zero_()
+        ops.igemm(pl_geom, A, W, out, n_img, bias=bias, ksplit=ks, out_mode=2)
+    else:
+        ops.igemm(pl_geom, A, W, out, n_img, bias=bias, out_mode=1 if f32_out else None)
+
+
+def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale):
+    wg = pl.lp.wgrad
+    dWp = alloc(key, (wg.Cn, wg.K), F32, zero=True)
+    ops.wgrad(wg, G, Nat, dWp, n_img, scale=scale, row_splits=plan.choose_row_splits(wg, n_img))
+    ops.unpack_add_f32(dWp, pl.idx_wgrad, arena.grad)
+
+
+class _BN:
+    """Grouped training-mode BatchNorm2d + Swish around a raw conv output."""
+
+    def __init__(self, net, idx_name, C):
+        self.net, self.name, self.C = net, idx_name, C
+
+    def forward(self, raw, act, G, rows, alloc, key, track, repeat=1):
+        net, C = self.net, self.C
+        sums = alloc(key + ".sums", (G, C, 2), F32, zero=True)
+        ab = alloc(key + ".ab", (G, C, 2), F32)
+        mi = alloc(key + ".mi", (G, C, 2), F32)
+        ops.bn_stats(raw, sums, G, rows, C)
+        rm = net.buf(self.name + ".running_mean") if track else None
+        rv = net.buf(self.name + ".running_var") if track else None
+        ops.bn_finalize(sums, net.pview(self.name + ".weight"), net.pview(self.name + ".bias"), ab, mi, rm, rv,
+                        G, rows, C, 1e-5, 0.1, repeat)
+        if track:
+            net.buf(self.name + ".num_batches_tracked").add_(G * repeat)
+        ops.bn_swish_fwd(raw, ab, act, G, rows, C)
+        return ab, mi
+
+    def backward(self, raw, ab, mi, dAct, G, rows, alloc, key, unscale):
+        net, C = self.net, self.C
+        sums2 = alloc(key + ".sums2", (G, C, 2), F32, zero=True)
+        ops.bn_swish_bwd_reduce(raw, ab, mi, dAct, sums2, G, rows, C)
+        ops.bn_bwd_apply(raw, ab, mi, sums2, dAct, net.pview(self.name + ".weight", True),
+                         net.pview(self.name + ".bias", True), G, rows, C, unscale)
+        return dAct  # now dRaw
+
+
+# ---------------------------------------------------------------------------------------------
+# image encoder (vae.py:197-216, 224-242)
+# ---------------------------------------------------------------------------------------------
+class EncoderExec(_NetBase):
+    def __init__(self, arena, prefix, device):
+        super().__init__(arena, prefix, device)
+        self.c1 = self._pl(plan.conv1_plan("conv1", self.off("conv_net.0.weight")))
+        self.c2 = self._pl(plan.conv_s2_plan("conv2", self.off("conv_net.2.weight"), 32, 64, 32))
+        self.c3 = self._pl(plan.conv_s2_plan("conv3", self.off("conv_net.5.weight"), 64, 128, 16))
+        self.c4 = self._pl(plan.conv_k4s1p0_plan("conv4", self.off("conv_net.8.weight"), 128, 256, 8))
+        self.fc = self._pl(plan.linear_plan("fc", [self.off("fc_net.0.weight")], [self.off("fc_net.0.bias")],
+                                            6400, [512], k_perm=plan.nhwc_perm(256, 5, 5)))
+        self.heads = self._pl(plan.linear_plan(
+            "heads", [self.off("linear_means.weight"), self.off("linear_log_var.weight")],
+            [self.off("linear_means.bias"), self.off("linear_log_var.bias")], 512, [256, 256]))
+        self.bn2, self.bn3, self.bn4 = _BN(self, "conv_net.3", 64), _BN(self, "conv_net.6", 128), _BN(self, "conv_net.9", 256)
+
+    def forward(self, x, masks, alloc, key, track=True):
+        """x: (B,3,64,64) fp32 NCHW; masks: list of (B,512) fp32 dropout masks or None entries (one per
+        pass sharing this trunk evaluation; BN running statistics are updated once per mask, as the
+        reference's repeated forward passes would).  Returns a record whose 'heads' entry is
+        (len(masks)*B, 512) fp32 = [mu | logvar] per mask."""
+        self.refresh()
+        B, nm = x.shape[0], len(masks)
+        r = {"x": x, "B": B, "masks": masks}
+        raw1 = alloc(key + ".raw1", (B, 32, 32, 32), F16)
+        ops.conv1_fwd(x, self.c1.Wf, raw1, B)
+        act1 = alloc(key + ".act1", (B, 32, 32, 32), F16)
+        ops.bn_swish_fwd(raw1, None, act1, 1, B * 1024, 32)
+        raw2 = alloc(key + ".raw2", (B, 16, 16, 64), F16)
+        ops.igemm(self.c2.lp.fwd, act1, self.c2.Wf, raw2, B)
+        act2 = alloc(key + ".act2", (B, 16, 16, 64), F16)
+        r["bn2"] = self.bn2.forward(raw2, act2, 1, B * 256, alloc, key + ".bn2", track, nm)
+        raw3 = alloc(key + ".raw3", (B, 8, 8, 128), F16)
+        ops.igemm(self.c3.lp.fwd, act2, self.c3.Wf, raw3, B)
+        act3 = alloc(key + ".act3", (B, 8, 8, 128), F16)
+        r["bn3"] = self.bn3.forward(raw3, act3, 1, B * 64, alloc, key + ".bn3", track, nm)
+        raw4 = alloc(key + ".raw4", (B, 5, 5, 256), F16)
+        ops.igemm(self.c4.lp.fwd, act3, self.c4.Wf, raw4, B)
+        act4 = alloc(key + ".act4", (B, 5, 5, 256), F16)
+        r["bn4"] = self.bn4.forward(raw4, act4, 1, B * 25, alloc, key + ".bn4", track, nm)
+        fc_raw = alloc(key + ".fc_raw", (B, 512), F32)
+        _gemm(self.fc.lp.fwd, act4, self.fc.Wf, fc_raw, B, self.fc.bias, True)
+        h = alloc(key + ".h", (nm, B, 512), F16)
+        ops.swish_dropout_fwd(fc_raw, masks, h, B, 512)
+        heads = alloc(key + ".heads", (nm * B, LATENT_HEADS), F32)
+        _gemm(self.heads.lp.fwd, h, self.heads.Wf, heads, nm * B, self.heads.bias, True)
+        r.update(raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3, raw4=raw4, act4=act4,
+                 fc_raw=fc_raw, h=h, heads=heads)
+        return r
+
+    def backward(self, r, d_heads, alloc, key, unscale, in_scale=1.0):
+        """d_heads: (n_masks*B, 512) fp32 gradient; in_scale * d_heads is what flows through the
+        fp16 backward (times grad_scale), unscale * in_scale brings parameter gradients back.
+        Accumulates parameter gradients into the arena."""
+        arena, B, nm = self.arena, r["B"], len(r["masks"])
+        rows = nm * B
+        dh16 = alloc(key + ".dheads16", (rows, 512), F16)
+        ops.f32_to_f16(d_heads, dh16, rows * 512, in_scale)
+        db = alloc(key + ".db512", (512,), F32, zero=True)
+        ops.colsum_f32(d_heads, db, rows, 512, 512, unscale * in_scale)
+        ops.unpack_add_f32(db, self.heads.bias_idx, arena.grad)
+        _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale)
+        dH = alloc(key + ".dH", (rows, 512), F32)
+        _gemm(self.heads.lp.dgrad, dh16, self.heads.Wd, dH, rows, None, True)
+        dfc = alloc(key + ".dfc16", (B, 512), F16)
+        ops.swish_dropout_bwd(r["fc_raw"], r["masks"], dH, dfc, B, 512)
+        ops.colsum_f16(dfc, self.pview("fc_net.0.bias", True), B, 512, 512, unscale)
+        _wgrad_into(self.fc, r["act4"], dfc, B, arena, alloc, key + ".dW_fc", unscale)
+        d4 = alloc(key + ".d4", (B, 5, 5, 256), F16)
+        ops.igemm(self.fc.lp.dgrad, dfc, self.fc.Wd, d4, B)
+        self.bn4.backward(r["raw4"], r["bn4"][0], r["bn4"][1], d4, 1, B * 25, alloc, key + ".bn4", unscale)
+        _wgrad_into(self.c4, r["act3"], d4, B, arena, alloc, key + ".dW_c4", unscale)
+        d3 = alloc(key + ".d3", (B, 8, 8, 128), F16)
+        ops.igemm(self.c4.lp.dgrad, d4, self.c4.Wd, d3, B)
+        self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], d3, 1, B * 64, alloc, key + ".bn3", unscale)
+        _wgrad_into(self.c3, r["act2"], d3, B, arena, alloc, key + ".dW_c3", unscale)
+        d2 = alloc(key + ".d2", (B, 16, 16, 64), F16)
+        ops.igemm(self.c3.lp.dgrad, d3, self.c3.Wd, d2, B)
+        self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], d2, 1, B * 256, alloc, key + ".bn2", unscale)
+        _wgrad_into(self.c2, r["act1"], d2, B, arena, alloc, key + ".dW_c2", unscale)
+        d1 = alloc(key + ".d1", (B, 32, 32, 32), F16)
+        ops.igemm(self.c2.lp.dgrad, d2, self.c2.Wd, d1, B)
+        ops.bn_swish_bwd_reduce(r["raw1"], None, None, d1, None, 1, B * 1024, 32)
+        ops.conv1_wgrad(r["x"], d1, self.pview("conv_net.0.weight", True), B, unscale, 296)
+
+
+# ---------------------------------------------------------------------------------------------
+# image decoder (vae.py:263-279, 293-296)
+# ---------------------------------------------------------------------------------------------
+class DecoderExec(_NetBase):
+    def __init__(self, arena, prefix, device):
+        super().__init__(arena, prefix, device)
+        self.up = self._pl(plan.linear_plan("up", [self.off("upsample.0.weight")], [self.off("upsample.0.bias")],
+                                            256, [6400], n_perm=plan.nhwc_perm(256, 5, 5)))
+        self.d1 = self._pl(plan.deconv_k4s1p0_plan("deconv1", self.off("hallucinate.0.weight"), 256, 128, 5))
+        self.d2 = self._pl(plan.deconv_s2_plan("deconv2", self.off("hallucinate.3.weight"), 128, 64, 8))
+        self.d3 = self._pl(plan.deconv_s2_plan("deconv3", self.off("hallucinate.6.weight"), 64, 32, 16))
+        self.d4 = self._pl(plan.deconv_out_plan("deconv4", self.off("hallucinate.9.weight"), 32, 3, 32))
+        self.bn1, self.bn2, self.bn3 = _BN(self, "hallucinate.1", 128), _BN(self, "hallucinate.4", 64), _BN(self, "hallucinate.7", 32)
+
+    def forward(self, zh, G, B, alloc, key, track=True):
+        """zh: (G*B, 256) fp16 latent rows, group-major.  Returns record with fp32 NCHW logits."""
+        self.refresh()
+        R = G * B
+        r = {"zh": zh, "G": G, "B": B}
+        raw0 = alloc(key + ".raw0", (R, 5, 5, 256), F16)
+        ops.igemm(self.up.lp.fwd, zh, self.up.Wf, raw0, R, bias=self.up.bias)
+        act0 = alloc(key + ".act0", (R, 5, 5, 256), F16)
+        ops.bn_swish_fwd(raw0, None, act0, 1, R * 25, 256)
+        raw1 = alloc(key + ".raw1", (R, 8, 8, 128), F16)
+        ops.igemm(self.d1.lp.fwd, act0, self.d1.Wf, raw1, R)
+        act1 = alloc(key + ".act1", (R, 8, 8, 128), F16)
+        r["bn1"] = self.bn1.forward(raw1, act1, G, B * 64, alloc, key + ".bn1", track)
+        raw2 = alloc(key + ".raw2", (R, 16, 16, 64), F16)
+        ops.igemm(self.d2.lp.fwd, act1, self.d2.Wf, raw2, R)
+        act2 = alloc(key + ".act2", (R, 16, 16, 64), F16)
+        r["bn2"] = self.bn2.forward(raw2, act2, G, B * 256, alloc, key + ".bn2", track)
+        raw3 = alloc(key + ".raw3", (R, 32, 32, 32), F16)
+        ops.igemm(self.d3.lp.fwd, act2, self.d3.Wf, raw3, R)
+        act3 = alloc(key + ".act3", (R, 32, 32, 32), F16)
+        r["bn3"] = self.bn3.forward(raw3, act3, G, B * 1024, alloc, key + ".bn3", track)
+        logits = alloc(key + ".logits", (R, 3, 64, 64), F32)
+        ops.igemm(self.d4.lp.fwd, act3, self.d4.Wf, logits, R)
+        r.update(raw0=raw0, act0=act0, raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3,
+                 logits=logits)
+        return r
+
+    def backward(self, r, dl8, alloc, key, unscale):
+        """dl8: (G*B, 64, 64, 8) fp16 logit gradients (3 channels used, times grad_scale).
+        Returns dz (G*B, 256) fp32 (times grad_scale)."""
+        arena, G, B = self.arena, r["G"], r["B"]
+        R = G * B
+        _wgrad_into(self.d4, dl8, r["act3"], R, arena, alloc, key + ".dW_d4", unscale)
+        g3 = alloc(key + ".g3", (R, 32, 32, 32), F16)
+        ops.igemm(self.d4.lp.dgrad, dl8, self.d4.Wd, g3, R)
+        self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], g3, G, B * 1024, alloc, key + ".bn3", unscale)
+        _wgrad_into(self.d3, g3, r["act2"], R, arena, alloc, key + ".dW_d3", unscale)
+        g2 = alloc(key + ".g2", (R, 16, 16, 64), F16)
+        ops.igemm(self.d3.lp.dgrad, g3, self.d3.Wd, g2, R)
+        self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], g2, G, B * 256, alloc, key + ".bn2", unscale)
+        _wgrad_into(self.d2, g2, r["act1"], R, arena, alloc, key + ".dW_d2", unscale)
+        g1 = alloc(key + ".g1", (R, 8, 8, 128), F16)
+        ops.igemm(self.d2.lp.dgrad, g2, self.d2.Wd, g1, R)
+        self.bn1.backward(r["raw1"], r["bn1"][0], r["bn1"][1], g1, G, B * 64, alloc, key + ".bn1", unscale)
+        _wgrad_into(self.d1, g1, r["act0"], R, arena, alloc, key + ".dW_d1", unscale)
+        g0 = alloc(key + ".g0", (R, 5, 5, 256), F16)
+        ops.igemm(self.d1.lp.dgrad, g1, self.d1.Wd, g0, R)
+        ops.bn_swish_bwd_reduce(r["raw0"], None, None, g0, None, 1, R * 25, 256)
+        dbp = alloc(key + ".db_up", (6400,), F32, zero=True)
+        ops.colsum_f16(g0, dbp, R, 6400, 6400, unscale)
+        ops.unpack_add_f32(dbp, self.up.bias_idx, arena.grad)
+        _wgrad_into(self.up, r["zh"], g0, R, arena, alloc, key + ".dW_up", unscale)
+        dz = alloc(key + ".dz", (R, 256), F32)
+        _gemm(self.up.lp.dgrad, g0, self.up.Wd, dz, R, None, True)
+        return dz
+
+
+# ---------------------------------------------------------------------------------------------
+# pose MLP expert, fp32 (vae.py:118-123, 219-222, 282-283)
+# ---------------------------------------------------------------------------------------------
+class PoseExec:
+    def __init__(self, arena, device):
+        self.arena, self.device = arena, device
+
+    def p(self, name, grad=False):
+        return self.arena.view(name, self.arena.grad if grad else None)
+
+    def enc_forward(self, pose, alloc, key):
+        B = pose.shape[0]
+        h1 = alloc(key + ".h1", (B, 512), F32)
+        ops.linear_f32_fwd(pose, self.p("pose_encoder.fc_net.0.weight"), self.p("pose_encoder.fc_net.0.bias"), h1,
+                           B, 512, 7, 7, 512, 1)
+        h2 = alloc(key + ".h2", (B, 512), F32)
+        ops.linear_f32_fwd(h1, self.p("pose_encoder.fc_net.2.weight"), self.p("pose_encoder.fc_net.2.bias"), h2,
+                           B, 512, 512, 512, 512, 0)
+        heads = alloc(key + ".heads", (B, LATENT_HEADS), F32)
+        ops.linear_f32_fwd(h2, self.p("pose_encoder.linear_means.weight"), self.p("pose_encoder.linear_means.bias"),
+                           heads, B, 256, 512, 512, 512, 0)
+        ops.linear_f32_fwd(h2, self.p("pose_encoder.linear_log_var.weight"),
+                           self.p("pose_encoder.linear_log_var.bias"), heads[:, 256:], B, 256, 512, 512, 512, 0)
+        return {"pose": pose, "h1": h1, "h2": h2, "heads": heads, "B": B}
+
+    def enc_backward(self, r, d_heads, alloc, key, unscale):
+        B = r["B"]
+        scr = alloc(key + ".scr", (B, 512), F32)
+        dh2 = alloc(key + ".dh2", (B, 512), F32)
+        for i, nm in enumerate(("linear_means", "linear_log_var")):
+            ops.linear_f32_bwd(r["h2"], self.p(f"pose_encoder.{nm}.weight"), r["heads"][:, 256 * i:],
+                               d_heads[:, 256 * i:], scr, dh2, self.p(f"pose_encoder.{nm}.weight", True),
+                               self.p(f"pose_encoder.{nm}.bias", True), B, 256, 512, 512, 512, 512, 0, i == 1, unscale)
+        dh1 = alloc(key + ".dh1", (B, 512), F32)
+        ops.linear_f32_bwd(r["h1"], self.p("pose_encoder.fc_net.2.weight"), r["h2"], dh2, scr, dh1,
+                           self.p("pose_encoder.fc_net.2.weight", True), self.p("pose_encoder.fc_net.2.bias", True),
+                           B, 512, 512, 512, 512, 512, 0, False, unscale)
+        ops.linear_f32_bwd(r["pose"], self.p("pose_encoder.fc_net.0.weight"), r["h1"], dh1, scr, None,
+                           self.p("pose_encoder.fc_net.0.weight", True), self.p("pose_encoder.fc_net.0.bias", True),
+                           B, 512, 7, 7, 512, 7, 1, False, unscale)
+
+    def dec_forward(self, z, alloc, key):
+        R = z.shape[0]
+        a1 = alloc(key + ".a1", (R, 512), F32)
+        ops.linear_f32_fwd(z, self.p("pose_decoder.deconv_net.0.weight"), self.p("pose_decoder.deconv_net.0.bias"),
+                           a1, R, 512, 256, 256, 512, 1)
+        a2 = alloc(key + ".a2", (R, 512), F32)
+        ops.linear_f32_fwd(a1, self.p("pose_decoder.deconv_net.2.weight"), self.p("pose_decoder.deconv_net.2.bias"),
+                           a2, R, 512, 512, 512, 512, 1)
+        rec = alloc(key + ".rec", (R, 7), F32)
+        ops.linear_f32_fwd(a2, self.p("pose_decoder.deconv_net.4.weight"), self.p("pose_decoder.deconv_net.4.bias"),
+                           rec, R, 7, 512, 512, 7, 0)
+        return {"z": z, "a1": a1, "a2": a2, "rec": rec, "R": R}
+
+    def dec_backward(self, r, d_rec, alloc, key, unscale):
+        R = r["R"]
+        scr = alloc(key + ".scr", (R, 512), F32)
+        da2 = alloc(key + ".da2", (R, 512), F32)
+        ops.linear_f32_bwd(r["a2"], self.p("pose_decoder.deconv_net.4.weight"), r["rec"], d_rec, scr, da2,
+                           self.p("pose_decoder.deconv_net.4.weight", True),
+                           self.p("pose_decoder.deconv_net.4.bias", True), R, 7, 512, 512, 7, 512, 0, False, unscale)
+        da1 = alloc(key + ".da1", (R, 512), F32)
+        ops.linear_f32_bwd(r["a1"], self.p("pose_decoder.deconv_net.2.weight"), r["a2"], da2, scr, da1,
+                           self.p("pose_decoder.deconv_net.2.weight", True),
+                           self.p("pose_decoder.deconv_net.2.bias", True), R, 512, 512, 512, 512, 512, 1, False, unscale)
+        dz = alloc(key + ".dz", (R, 256), F32)
+        ops.linear_f32_bwd(r["z"], self.p("pose_decoder.deconv_net.0.weight"), r["a1"], da1, scr, dz,
+                           self.p("pose_decoder.deconv_net.0.weight", True),
+                           self.p("pose_decoder.deconv_net.0.bias", True), R, 512, 256, 256, 512, 256, 1, False, unscale)
+        return dz
+
+
+def get_execs(module, device):
+    """Build (once per module and device) the executors of every sub-network present."""
+    arena = get_arena(module, device)
+    ex = module.__dict__.get("_mmdyn_execs")
+    if ex is None or ex["device"] != arena.flat.device or ex["flat_id"] != id(arena.flat):
+        dev = arena.flat.device
+        ex = {"device": dev, "flat_id": id(arena.flat), "enc": {}, "dec": {}, "pose": None}
+        names = set(n.split(".")[0] for n in arena.names)
+        for n in sorted(names):
+            if n.endswith("encoder") and n != "pose_encoder":
+                ex["enc"][n] = EncoderExec(arena, n, dev)
+            elif n.endswith("decoder") and n != "pose_decoder":
+                ex["dec"][n] = DecoderExec(arena, n, dev)
+        if "pose_encoder" in names:
+            ex["pose"] = PoseExec(arena, dev)
+        module.__dict__["_mmdyn_execs"] = ex
+    return arena, ex
+
+
+# ---------------------------------------------------------------------------------------------
+# fused training / evaluation step
+# ---------------------------------------------------------------------------------------------
+class _StepLossFn(torch.autograd.Function):
+    """Connects the fused step to torch autograd: loss.backward() (problems.py:153) runs the
+    hand-written backward of the whole step into the gradient arena."""
+
+    @staticmethod
+    def forward(ctx, anchor, loss_value, eng, token):
+        ctx.eng, ctx.token = eng, token
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctx.eng._backward(ctx.token, grad_out)
+        return None, None, None, None
+
+
+class StepEngine:
+    """One object per model: evaluate() is Reconstruction._evaluate_mvae / the VAE branch of
+    SeqModeling._evaluate_model (problems.py:473-546, 702-716) as one fused launch sequence.
+
+    kind 'vae'  : one pass {x}; posterior = encoder output (no prior expert).
+    kind 'mvae' : passes {v,t} {v} {t} and, with use_pose, {v,t,p} {v,p} {t,p} {p}; the image
+                  encoder trunks are evaluated once and shared; decoders run group-batched over
+                  the passes that carry their loss.
+    exact_running_stats: also run the decoder invocations whose outputs the reference discards
+                  (vae.py:160-161) so BatchNorm running statistics match it bit-for-bit in count.
+    """
+
+    IMG = 3 * 64 * 64
+
+    def __init__(self, model, kind, use_pose=False, pose_multiplier=1000.0, noise_src=None,
+                 exact_running_stats=False, grad_scale=None):
+        self.model, self.kind, self.use_pose = model, kind, bool(use_pose)
+        self.pose_multiplier = float(pose_multiplier)
+        self.noise_src = noise_src
+        self.exact = bool(exact_running_stats)
+        self.grad_scale = grad_scale
+        if kind == "vae":
+            self.mods = {"x": ("encoder", "decoder")}
+            self.passes = [("x",)]
+            self.use_prior = False
+        else:
+            self.mods = {"v": ("visual_encoder", "visual_decoder"), "t": ("tactile_encoder", "tactile_decoder")}
+            self.passes = [("v", "t"), ("v",), ("t",)]
+            if self.use_pose:
+                self.passes += [("v", "t", "p"), ("v", "p"), ("t", "p"), ("p",)]
+            self.use_prior = True
+        self.ws = None
+        self._token = 0
+        self._state = None
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _noise(self):
+        if self.noise_src is not None:
+            return self.noise_src
+        src = getattr(self.model, "noise", None)
+        if src is not None:
+            return src
+        from . import noise
+        return noise.get_default()
+
+    def _setup(self, device):
+        arena, ex = get_execs(self.model, device)
+        if self.ws is None or self.ws.device != arena.flat.device:
+            self.ws = Workspace(arena.flat.device)
+        return arena, ex
+
+    def evaluate(self, x, targets, kl_weight, loss_mask=None, want_outputs=True):
+        """x / targets: tensor (vae) or list [visual, tactile(, pose)] (mvae), fp32, on the GPU.
+        Returns (outputs, loss) like the reference; loss.backward() then fills the parameter
+        gradients.  Under torch.no_grad() only the forward runs (Problem._test_epoch)."""
+        if self.kind == "vae":
+            xs, ts = {"x": x}, {"x": targets}
+        else:
+            xs = {"v": x[0], "t": x[1]}
+            ts = {"v": targets[0], "t": targets[1]}
+            if self.use_pose:
+                xs["p"], ts["p"] = x[2], targets[2]
+        first = next(iter(xs.values()))
+        if not first.is_cuda:
+            raise RuntimeError("mmdyn_b200 has no CPU path: inputs must be CUDA tensors")
+        if not self.model.training:
+            raise NotImplementedError("eval-mode BatchNorm/Dropout is not part of the reference path "
+                                      "(the reference keeps model.train() even for validation: problems.py:174)")
+        arena, ex = self._setup(first.device)
+        ws, B, D = self.ws, first.shape[0], 256
+        for k in xs:
+            xs[k] = xs[k].contiguous().float()
+            ts[k] = ts[k].contiguous().float()
+        need_grad = torch.is_grad_enabled()
+        gs = float(self.grad_scale) if self.grad_scale else float(B)
+        npass = len(self.passes)
+        src = self._noise()
+
+        # groups: which passes each decoder runs (loss-bearing ones, or all with exact stats)
+        img_mods = [m for m in self.mods]
+        enc_passes = {m: [i for i, p in enumerate(self.passes) if m in p] for m in img_mods}
+        dec_groups = {m: (list(range(npass)) if self.exact else enc_passes[m]) for m in img_mods}
+        pose_passes = [i for i, p in enumerate(self.passes) if "p" in p]
+
+        # noise in the reference's consumption order: per pass visual mask, tactile mask, eps
+        masks = {m: [None] * len(enc_passes[m]) for m in img_mods}
+        eps = ws("eps", (npass, B, D), F32)
+        mbuf = {m: ws("mask_" + m, (len(enc_passes[m]), B, 512), F32) for m in img_mods}
+        train_mode = self.model.training
+        for i, p in enumerate(self.passes):
+            for m in img_mods:
+                if m in p and train_mode:
+                    j = enc_passes[m].index(i)
+                    masks[m][j] = src.dropout_mask(B, first.device, out=mbuf[m][j])
+            src.normal(B, D, first.device, out=eps[i])
+
+        # encoders (once per modality)
+        enc_rec = {m: ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True) for m in img_mods}
+        pose_rec = ex["pose"].enc_forward(xs["p"], ws, "penc") if self.use_pose else None
+
+        # PoE + reparam + KL per pass
+        scal = ws("scal", (64,), F32, zero=True)
+        mu_all, lv_all = ws("mu", (npass, B, D), F32), ws("lv", (npass, B, D), F32)
+        zscr = ws("z_scratch", (B, D), F32)
+        zdec = {m: ws("z_" + m, (len(dec_groups[m]) * B, D), F16) for m in img_mods}
+        zpose = ws("z_p", (max(1, len(pose_passes)) * B, D), F32) if self.use_pose else None
+
+        def experts(i):
+            out = []
+            for m in img_mods:
+                if m in self.passes[i]:
+                    j = enc_passes[m].index(i)
+                    out.append(enc_rec[m]["heads"][j * B:(j + 1) * B])
+            if "p" in self.passes[i]:
+                out.append(pose_rec["heads"])
+            return out
+
+        for i, p in enumerate(self.passes):
+            hs = experts(i)
+            zh = []
+            for m in img_mods:
+                if i in dec_groups[m]:
+                    g = dec_groups[m].index(i)
+                    zh.append(zdec[m][g * B:(g + 1) * B])
+            zf = zpose[pose_passes.index(i) * B:(pose_passes.index(i) + 1) * B] if "p" in p else zscr
+            ops.poe_fwd([h[:, :D] for h in hs], [h[:, D:] for h in hs], self.use_prior, 2 * D, eps[i], mu_all[i],
+                        lv_all[i], zf, zh[0] if len(zh) > 0 else None, zh[1] if len(zh) > 1 else None,
+                        scal[i:i + 1], B, D)
+
+        # decoders, group-batched
+        dec_rec = {m: ex["dec"][self.mods[m][1]].forward(zdec[m], len(dec_groups[m]), B, ws, "dec_" + m, True)
+                   for m in img_mods}
+        pdec_rec = ex["pose"].dec_forward(zpose, ws, "pdec") if self.use_pose else None
+
+        # losses (+ logit gradients when training)
+        slot = {}
+        nslot = 8
+        dl8 = {}
+        for m in img_mods:
+            G = len(dec_groups[m])
+            dl8[m] = ws("dl8_" + m, (G * B, 64, 64, 8), F16, zero=self.exact) if need_grad else None
+            for i in enc_passes[m]:
+                g = dec_groups[m].index(i)
+                slot[(m, i)] = nslot
+                lg = dec_rec[m]["logits"][g * B:(g + 1) * B]
+                ops.bce_logits(lg, ts[m], loss_mask, scal[nslot:nslot + 1],
+                               dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64 * 64)
+                nslot += 1
+        d_prec = None
+        if self.use_pose:
+            d_prec = ws("d_prec", (len(pose_passes) * B, 7), F32) if need_grad else None
+            for g, i in enumerate(pose_passes):
+                slot[("p", i)] = nslot
+                ops.mse(pdec_rec["rec"][g * B:(g + 1) * B], ts["p"], scal[nslot:nslot + 1],
+                        d_prec[g * B:(g + 1) * B] if need_grad else None, self.pose_multiplier, gs / B, B * 7)
+                nslot += 1
+        klw = float(kl_weight)
+        loss_value = (scal[8:nslot].sum() + klw * scal[:npass].sum()) / B
+
+        self._token += 1
+        self._state = dict(token=self._token, arena=arena, ex=ex, B=B, gs=gs, klw=klw, enc_rec=enc_rec,
+                           pose_rec=pose_rec, dec_rec=dec_rec, pdec_rec=pdec_rec, dl8=dl8, d_prec=d_prec,
+                           enc_passes=enc_passes, dec_groups=dec_groups, pose_passes=pose_passes, eps=eps,
+                           experts=experts, img_mods=img_mods) if need_grad else None
+        loss = _StepLossFn.apply(arena.params[0], loss_value, self, self._token) if need_grad else loss_value
+
+        outputs = None
+        if want_outputs:
+            outputs = self._outputs(dec_rec, pdec_rec, mu_all, lv_all, scal, slot, ts, loss_mask, B,
+                                    dec_groups, pose_passes)
+        return outputs, loss
+
+    def _outputs(self, dec_rec, pdec_rec, mu_all, lv_all, scal, slot, ts, loss_mask, B, dec_groups, pose_passes):
+        """The reference's `outputs` dict (problems.py:537-544, 714-715), including its name-rebinding
+        quirks: recon_x = reconstructions of the joint pass, means/log_var = posterior of the LAST pass.
+        perf_measure values are 0-dim device tensors (no host sync inside the step)."""
+        n_el = float(B * self.IMG)
+        if self.kind == "vae":
+            lg = dec_rec["x"]["logits"]
+            if loss_mask is None:
+                meas = scal[slot[("x", 0)]] / n_el
+            else:
+                tmp = self.ws("metric_tmp", (4,), F32, zero=True)
+                ops.bce_logits(lg, ts["x"], None, tmp[0:1], None, 0.0, B, 64 * 64)
+                meas = tmp[0] / n_el
+            return {"recon_x": lg.clone(), "means": mu_all[0].clone(), "log_var": lv_all[0].clone(),
+                    "perf_measure": {"x": meas}}
+        joint = 3 if self.use_pose else 0
+        rec = []
+        for m in ("v", "t"):
+            g = dec_groups[m].index(joint)
+            rec.append(dec_rec[m]["logits"][g * B:(g + 1) * B].clone())
+        perf = {}
+        for m, name, uni in (("v", "visual", 1), ("t", "tactile", 2)):
+            if loss_mask is None:
+                perf[name] = scal[slot[(m, uni)]] / n_el
+            else:
+                tmp = self.ws("metric_tmp_" + m, (4,), F32, zero=True)
+                g = dec_groups[m].index(uni)
+                ops.bce_logits(dec_rec[m]["logits"][g * B:(g + 1) * B], ts[m], None, tmp[0:1], None, 0.0, B, 64 * 64)
+                perf[name] = tmp[0] / n_el
+        if self.use_pose:
+            g = pose_passes.index(joint)
+            rec.append(pdec_rec["rec"][g * B:(g + 1) * B].clone())
+            perf["pose"] = scal[slot[("p", 6)]] / (self.pose_multiplier * B * 7)
+        last = len(self.passes) - 1
+        return {"recon_x": rec, "means": mu_all[last].clone(), "log_var": lv_all[last].clone(), "perf_measure": perf}
+
+    def _backward(self, token, grad_out=None):
+        st = self._state
+        if st is None or st["token"] != token:
+            raise RuntimeError("mmdyn_b200: backward() called for a step whose buffers were overwritten by a "
+                               "later evaluate(); call loss.backward() before evaluating the next batch")
+        if os.environ.get("MMDYN_CHECK_GRAD_OUT") and grad_out is not None:
+            assert abs(float(grad_out) - 1.0) < 1e-6, "the fused backward assumes d(loss) = 1"
+        arena, ex, ws, B, gs = st["arena"], st["ex"], self.ws, st["B"], st["gs"]
+        arena.attach_grads()
+        unscale = 1.0 / gs
+        D = 256
+        img_mods = st["img_mods"]
+        dz = {m: ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale)
+              for m in img_mods}
+        dzp = ex["pose"].dec_backward(st["pdec_rec"], st["d_prec"], ws, "pdec", unscale) if self.use_pose else None
+        dh = {m: ws("dheads_" + m, (len(st["enc_passes"][m]) * B, 512), F32, zero=True) for m in img_mods}
+        dhp = ws("dheads_p", (B, 512), F32, zero=True) if self.use_pose else None
+        for i, p in enumerate(self.passes):
+            hs = st["experts"](i)
+            outs, dzs = [], []
+            for m in img_mods:
+                if m in p:
+                    j = st["enc_passes"][m].index(i)
+                    outs.append(dh[m][j * B:(j + 1) * B])
+                    g = st["dec_groups"][m].index(i)
+                    dzs.append(dz[m][g * B:(g + 1) * B])
+            if "p" in p:
+                outs.append(dhp)
+                g = st["pose_passes"].index(i)
+                dzs.append(dzp[g * B:(g + 1) * B])
+            ops.poe_bwd([h[:, :D] for h in hs], [h[:, D:] for h in hs], self.use_prior, 2 * D, st["eps"][i], dzs,
+                        st["klw"] * gs / B, [o[:, :D] for o in outs], [o[:, D:] for o in outs], 2 * D, True, B, D)
+        for m in img_mods:
+            ex["enc"][self.mods[m][0]].backward(st["enc_rec"][m], dh[m], ws, "enc_" + m, unscale)
+        if self.use_pose:
+            ex["pose"].enc_backward(st["pose_rec"], dhp, ws, "penc", unscale)
+        self._state = None

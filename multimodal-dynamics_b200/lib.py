@@ -60,14 +60,14 @@ SIGNATURES = {
     "mmdyn_conv1_fwd": ([_P, _P, _P, _I, _P], _I),
     "mmdyn_conv1_wgrad": ([_P, _P, _P, _I, _F, _I, _P], _I),
     "mmdyn_bn_stats": ([_P, _P, _I, _I, _I, _P], _I),
-    "mmdyn_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P], _I),
+    "mmdyn_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
     "mmdyn_bn_swish_fwd": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_swish_bwd_reduce": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_bwd_apply": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P], _I),
     "mmdyn_swish_dropout_fwd": ([_P, C.POINTER(_P), _P, _I, _I, _I, _P], _I),
     "mmdyn_swish_dropout_bwd": ([_P, C.POINTER(_P), _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_poe_fwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
-    "mmdyn_poe_bwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, C.POINTER(_P), _F, C.POINTER(_P), C.POINTER(_P),
+    "mmdyn_poe_bwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, C.POINTER(_P), _P, _P, _F, C.POINTER(_P), C.POINTER(_P),
                        _I, _I, _I, _I, _P], _I),
     "mmdyn_bce_logits": ([_P, _P, _P, _P, _P, _F, _I, _I, _P], _I),
     "mmdyn_mse": ([_P, _P, _P, _P, _F, _F, _I, _P], _I),
@@ -78,11 +78,14 @@ SIGNATURES = {
     "mmdyn_pack_f16": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_gather_f32": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_unpack_add_f32": ([_P, _P, _P, _LL, _P], _I),
-    "mmdyn_f32_to_f16": ([_P, _P, _LL, _P], _I),
+    "mmdyn_f32_to_f16": ([_P, _P, _LL, _F, _P], _I),
+    "mmdyn_scale_f32": ([_P, _LL, _F, _P], _I),
+    "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _P], _I),
     "mmdyn_adam_flat": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P], _I),
     "mmdyn_sgd_flat": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),
-    "mmdyn_fill_normal": ([_P, _LL, _U64, _U64, _P], _I),
-    "mmdyn_fill_dropout_mask": ([_P, _LL, _F, _U64, _U64, _P], _I),
+    "mmdyn_fill_normal": ([_P, _LL, _U64, _U64, _P, _P], _I),
+    "mmdyn_fill_dropout_mask": ([_P, _LL, _F, _U64, _U64, _P, _P], _I),
+    "mmdyn_rng_advance": ([_P, _U64, _P], _I),
 }
 
 _lib = None

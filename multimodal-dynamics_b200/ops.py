@@ -77,9 +77,11 @@ def bn_stats(x, sums, G, rows, Cch):
     check(_L().mmdyn_bn_stats(_ptr(x), _ptr(sums), G, rows, Cch, _stream()), "bn_stats")
 
 
-def bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows, Cch, eps, momentum):
+def bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows, Cch, eps, momentum,
+                stat_repeat=1):
     check(_L().mmdyn_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(ab), _ptr(mean_invstd),
-                                 _ptr(running_mean), _ptr(running_var), G, rows, Cch, eps, momentum, _stream()),
+                                 _ptr(running_mean), _ptr(running_var), G, rows, Cch, eps, momentum, stat_repeat,
+                                 _stream()),
           "bn_finalize")
 
 
@@ -111,14 +113,16 @@ def swish_dropout_bwd(raw, masks, dH, dRaw, B, Cch):
 
 def poe_fwd(mu_e, lv_e, use_prior, ld, eps, mu, lv, z, zh, zh2, kl_sum, B, D):
     n = len(mu_e)
-    check(_L().mmdyn_poe_fwd(_ptr_array(mu_e, 3), _ptr_array(lv_e, 3), n, int(use_prior), ld, _ptr(eps), _ptr(mu),
+    check(_L().mmdyn_poe_fwd(_ptr_array(mu_e, 4), _ptr_array(lv_e, 4), n, int(use_prior), ld, _ptr(eps), _ptr(mu),
                              _ptr(lv), _ptr(z), _ptr(zh), _ptr(zh2), _ptr(kl_sum), B, D, _stream()), "poe_fwd")
 
 
-def poe_bwd(mu_e, lv_e, use_prior, ld, eps, dzs, kl_coef, dmu_e, dlv_e, ld_out, accumulate, B, D):
+def poe_bwd(mu_e, lv_e, use_prior, ld, eps, dzs, kl_coef, dmu_e, dlv_e, ld_out, accumulate, B, D,
+            dmu_in=None, dlv_in=None):
     n = len(mu_e)
-    check(_L().mmdyn_poe_bwd(_ptr_array(mu_e, 3), _ptr_array(lv_e, 3), n, int(use_prior), ld, _ptr(eps),
-                             _ptr_array(dzs, 3), kl_coef, _ptr_array(dmu_e, 3), _ptr_array(dlv_e, 3), ld_out,
+    check(_L().mmdyn_poe_bwd(_ptr_array(mu_e, 4), _ptr_array(lv_e, 4), n, int(use_prior), ld, _ptr(eps),
+                             _ptr_array(dzs, 3), _ptr(dmu_in), _ptr(dlv_in), kl_coef, _ptr_array(dmu_e, 4),
+                             _ptr_array(dlv_e, 4), ld_out,
                              int(accumulate), B, D, _stream()), "poe_bwd")
 
 
@@ -162,8 +166,16 @@ def unpack_add_f32(src, idx, dst):
     check(_L().mmdyn_unpack_add_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "unpack_add_f32")
 
 
-def f32_to_f16(src, dst, n):
-    check(_L().mmdyn_f32_to_f16(_ptr(src), _ptr(dst), n, _stream()), "f32_to_f16")
+def f32_to_f16(src, dst, n, scale=1.0):
+    check(_L().mmdyn_f32_to_f16(_ptr(src), _ptr(dst), n, scale, _stream()), "f32_to_f16")
+
+
+def scale_f32(x, n, s):
+    check(_L().mmdyn_scale_f32(_ptr(x), n, s, _stream()), "scale_f32")
+
+
+def logit_grad_pack(dl, out, scale, n, HW):
+    check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, HW, _stream()), "logit_grad_pack")
 
 
 def adam_flat(p, g, m, v, n, lr, b1, b2, eps, wd, step, gscale=1.0):
@@ -176,9 +188,13 @@ def sgd_flat(p, g, buf, n, lr, momentum, wd, first_step, gscale=1.0):
           "sgd_flat")
 
 
-def fill_normal(out, n, seed, offset):
-    check(_L().mmdyn_fill_normal(_ptr(out), n, seed, offset, _stream()), "fill_normal")
+def fill_normal(out, n, seed, offset, ctr=None):
+    check(_L().mmdyn_fill_normal(_ptr(out), n, seed, offset, _ptr(ctr), _stream()), "fill_normal")
 
 
-def fill_dropout_mask(out, n, p_drop, seed, offset):
-    check(_L().mmdyn_fill_dropout_mask(_ptr(out), n, p_drop, seed, offset, _stream()), "fill_dropout_mask")
+def fill_dropout_mask(out, n, p_drop, seed, offset, ctr=None):
+    check(_L().mmdyn_fill_dropout_mask(_ptr(out), n, p_drop, seed, offset, _ptr(ctr), _stream()), "fill_dropout_mask")
+
+
+def rng_advance(ctr, inc):
+    check(_L().mmdyn_rng_advance(_ptr(ctr), inc, _stream()), "rng_advance")

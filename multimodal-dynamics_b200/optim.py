@@ -1,0 +1,69 @@
+"""Fused optimizers over the flat parameter arena (one kernel launch per step).
+
+FusedAdam / FusedSGD are torch.optim.Optimizer subclasses so that `Problem.set_optimizer`
+(problems.py:130-138) and user code keep their shape; the update itself is `mmdyn_adam_flat` /
+`mmdyn_sgd_flat`: a single float4-vectorised pass over parameters, gradients and moments
+(28 B/parameter for Adam) instead of torch's multi-tensor foreach sequence."""
+import torch
+
+from . import engine, ops
+
+
+class _FlatOptimizer(torch.optim.Optimizer):
+    def __init__(self, model, defaults):
+        self.model = model
+        params = list(model.parameters())
+        super().__init__(params, defaults)
+        self._step = 0
+        self._bufs = None
+        self.grad_prescale = 1.0  # e.g. 1/world_size after a sum all-reduce
+
+    def _arena(self):
+        arena = engine.get_arena(self.model)
+        if self._bufs is None or self._bufs[0].device != arena.flat.device or self._bufs[0].numel() != arena.total:
+            self._bufs = tuple(torch.zeros_like(arena.flat) for _ in range(self._n_bufs))
+            self._step = 0
+        return arena
+
+    def zero_grad(self, set_to_none=True):
+        """Keeps p.grad as views of the gradient arena and clears it with one memset."""
+        arena = self._arena()
+        arena.attach_grads()
+        arena.grad.zero_()
+
+
+class FusedAdam(_FlatOptimizer):
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) semantics (problems.py:138)."""
+    _n_bufs = 2
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(model, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        arena = self._arena()
+        arena.attach_grads()
+        g = self.param_groups[0]
+        self._step += 1
+        m, v = self._bufs
+        ops.adam_flat(arena.flat, arena.grad, m, v, arena.total, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                      g["weight_decay"], self._step, self.grad_prescale)
+        arena.bump()
+
+
+class FusedSGD(_FlatOptimizer):
+    """torch.optim.SGD(lr, momentum=0.9, weight_decay=5e-4) semantics (problems.py:132-136)."""
+    _n_bufs = 1
+
+    def __init__(self, model, lr=1e-3, momentum=0.9, weight_decay=5e-4):
+        super().__init__(model, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        arena = self._arena()
+        arena.attach_grads()
+        g = self.param_groups[0]
+        self._step += 1
+        ops.sgd_flat(arena.flat, arena.grad, self._bufs[0], arena.total, g["lr"], g["momentum"], g["weight_decay"],
+                     self._step == 1, self.grad_prescale)
+        arena.bump()

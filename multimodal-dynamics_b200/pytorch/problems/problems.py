@@ -1,0 +1,449 @@
+"""Problem layer — B200-native mirror of `mmdyn/pytorch/problems/problems.py`.
+
+Same classes (`Problem` > `Reconstruction` > `SeqModeling` > `DynModeling`), constructor
+(`Problem(args, log_dir=None, load_dataset=None)`), public methods (`train`, `parse_input`,
+`_evaluate_model(x, targets, reduction, reduce) -> (outputs, loss)`, `_anneal_KL`, properties) and
+on-disk artefacts (run dirs, tensorboard scalars, best-loss checkpoints with the reference's
+state_dict keys) — but `_evaluate_model` / `_evaluate_mvae` hand the whole sub-sampled step to
+`mmdyn_b200.engine.StepEngine` (one fused launch sequence: shared encoder trunks, group-batched
+decoders, fused PoE/KL/losses and a hand-written backward), and `set_optimizer` installs the
+single-kernel `FusedAdam` / `FusedSGD` over the flat parameter arena.
+
+Differences that are deliberate and documented in DESIGN.md:
+  * perf_measure values stay on the device (0-dim tensors) so the step has no host sync; they
+    are converted with float() only where the reference logs them per epoch;
+  * `--problem-type regression` and `--conditional` are outside the accelerated path;
+  * dyn_modeling batches are sequence-collated (the reference crashes there).
+"""
+import math
+import os
+from collections import defaultdict
+from datetime import datetime
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from mmdyn_b200 import engine, optim as fused_optim
+from mmdyn_b200.pytorch import config
+from mmdyn_b200.pytorch.models.models import setup_model
+from mmdyn_b200.pytorch.utils.datasets import dataset_setup
+from mmdyn_b200.pytorch.utils.training import progress_bar, save_pkl
+
+
+def _f(v):
+    return float(v) if not isinstance(v, (int, float)) else v
+
+
+class Problem:
+    def __init__(self, problem_args, log_dir=None, load_dataset=None):
+        self._model = self._log_dir = self._checkpoint_dir = self._tensorboard_dir = self._plot_dir = None
+        self._condition_dim = self._classes = self._criterion = self._optimizer = self._writer = None
+        self.train_dataset = self.test_dataset = self.train_loader = self.test_loader = None
+        self._best_acc, self._best_loss = 0, np.inf
+        self._load_dataset = load_dataset
+        self._logger_dict = defaultdict(list)
+        self._logger_histogram = defaultdict(list)
+        self._img_logger_dict = defaultdict()
+        self._fig_logger_dict = defaultdict()
+        self.parameters = vars(problem_args) if not isinstance(problem_args, dict) else dict(problem_args)
+        self._cross_modal = self.parameters['input_type'] == 'visuotactile'
+        self._kl_weight = self.parameters['kl_weight']
+        self._pose_multiplier = self.parameters['pose_multiplier']
+        self._conditional = self.parameters['conditional']
+        self._categorical_conditions = None
+        self._seq_length = None
+        self._engine = None
+        if self.parameters.get('no_cuda') or not torch.cuda.is_available():
+            raise RuntimeError("mmdyn_b200 runs on a CUDA device (B200) only; --no-cuda / CPU execution is the "
+                               "reference's own path")
+        self._device = torch.device('cuda', torch.cuda.current_device())
+        assert (self.parameters['input_type'] in config.INPUT_TYPES), "Input type is not implemented"
+        if log_dir:
+            self.load_dir(log_dir)
+            self._load_problem()
+        else:
+            self.set_dir()
+            self._set_problem()
+
+    # -- construction ---------------------------------------------------------------------------
+    def _set_problem(self):
+        self.set_dataset()
+        self.set_model()
+        self.set_criterion()
+        self.set_optimizer()
+
+    def _load_problem(self):
+        if self._load_dataset:
+            self.set_dataset()
+            self.set_model()
+
+    def set_model(self):
+        raise NotImplementedError
+
+    def _set_condition_dim(self):
+        raise NotImplementedError
+
+    def load_dir(self, log_dir):
+        self._log_dir = log_dir
+        self._checkpoint_dir = log_dir + '/checkpoint/'
+        self._tensorboard_dir = log_dir + '/tensorboard/'
+        self._plot_dir = log_dir + '/plot/'
+
+    def set_dir(self):
+        stamp = datetime.now().strftime("_%Y_%m_%d_%H_%M_%S")
+        self.load_dir('./logs/' + self.parameters['save_name'] + stamp)
+        for d in (self._log_dir, self._checkpoint_dir, self._tensorboard_dir, self._plot_dir):
+            Path(d).mkdir(parents=True, exist_ok=True)
+
+    def parse_input(self, data, target):
+        it = self.parameters['input_type']
+        if not isinstance(data, list):
+            model_input = data.to(self._device)
+        elif it == 'visuotactile':
+            model_input = [data[0].to(self._device), data[1].to(self._device)]
+        else:
+            model_input = data[{'visual': 0, 'tactile': 1}[it]].to(self._device)
+        return model_input, target.to(self._device)
+
+    def set_dataset(self):
+        self._input_size = (64, 64)
+        self._n_channels = 3
+        self.dataset_dict = dataset_setup(self.parameters['dataset_path'], self.parameters['problem_type'],
+                                          input_size=self._input_size, batchsize=self.parameters['batchsize'],
+                                          shuffle=True)
+        d = self.dataset_dict
+        self.train_dataset, self.test_dataset = d['train_dataset'], d['test_dataset']
+        self.train_loader, self.test_loader = d['train_loader'], d['test_loader']
+        self._seq_length = d['seq_length']
+        if 'classes' in d:
+            self._classes = d['classes']
+
+    def set_criterion(self):
+        raise NotImplementedError
+
+    def set_optimizer(self):
+        """problems.py:130-138 with the fused single-kernel updates."""
+        name = self.parameters['optimizer']
+        assert (name in config.OPTIMIZERS), "loss name not implemented in Problem"
+        if name == 'SGD':
+            self._optimizer = fused_optim.FusedSGD(self._model, lr=self.parameters['lr'], momentum=0.9,
+                                                   weight_decay=5e-4)
+        else:
+            self._optimizer = fused_optim.FusedAdam(self._model, lr=self.parameters['lr'])
+
+    def _evaluate_model(self, inputs, targets, **kwargs):
+        raise NotImplementedError
+
+    # -- epochs (problems.py:143-216) -----------------------------------------------------------------
+    def _train_epoch(self, epoch):
+        print('Epoch: %d' % epoch)
+        self._model.train()
+        train_loss = torch.zeros((), device=self._device)
+        inputs = outputs = targets = []
+        perf_measure = {'visual': 0, 'tactile': 0, 'pose': 0}
+        n = len(self.train_loader)
+        for batch_idx, (data_input, data_target) in enumerate(self.train_loader):
+            inputs, targets = self.parse_input(data_input, data_target)
+            self._optimizer.zero_grad()
+            outputs, loss = self._evaluate_model(inputs, targets)
+            loss.backward()
+            self._optimizer.step()
+            train_loss += loss.detach()
+            for k, v in outputs.get('perf_measure', {}).items():
+                perf_measure[k] = perf_measure[k] + v
+            if self._writer is not None and (batch_idx % 50 == 0 or batch_idx == n - 1):
+                self._writer.add_scalar('Loss/train_step', loss.item(), epoch * n + batch_idx)
+                progress_bar(batch_idx + 1, n, 'Loss %.3f' % loss.item())
+        self._log_train_info(inputs, outputs, targets, _f(train_loss), epoch, perf_measure=perf_measure)
+        return perf_measure
+
+    def _test_epoch(self, epoch):
+        self._model.train()  # sic: the reference validates with batch statistics and dropout on (:174)
+        validation_loss = torch.zeros((), device=self._device)
+        inputs = outputs = targets = []
+        perf_measure = {'visual': 0, 'tactile': 0, 'pose': 0}
+        with torch.no_grad():
+            for batch_idx, (data_input, data_target) in enumerate(self.test_loader):
+                inputs, targets = self.parse_input(data_input, data_target)
+                outputs, loss = self._evaluate_model(inputs, targets)
+                validation_loss += loss
+                for k, v in outputs.get('perf_measure', {}).items():
+                    perf_measure[k] = perf_measure[k] + v
+            self._log_test_info(inputs, outputs, targets, _f(validation_loss), epoch, perf_measure=perf_measure)
+        return perf_measure
+
+    def train(self, save=True):
+        from torch.utils.tensorboard import SummaryWriter
+        perf_measure = 0
+        self._writer = SummaryWriter(self._tensorboard_dir)
+        for epoch in range(self.parameters['num_epochs']):
+            self._anneal_KL(epoch)
+            self._train_epoch(epoch)
+            perf_measure = self._test_epoch(epoch)
+            self._sample(n=50)
+            for key in self._logger_dict:
+                self._writer.add_scalar(key, self._logger_dict[key][epoch], epoch)
+            for key in self._logger_histogram:
+                self._writer.add_histogram(key, self._logger_histogram[key], global_step=epoch)
+            self._write_images(epoch)
+        hp = {k: v for k, v in self.parameters.items() if isinstance(v, (int, float, str, bool))}
+        self._writer.add_hparams(hp, {k: _f(v) for k, v in perf_measure.items()})
+        if save:
+            save_pkl(dict(self._logger_dict), os.path.join(self._log_dir, 'results.pkl'))
+
+    def _anneal_KL(self, epoch):
+        """problems.py:212-216: linear warm-up over `annealing_epochs`, overriding --kl-weight."""
+        ae = self.parameters['annealing_epochs']
+        self._kl_weight = (epoch + 1) / ae if epoch < ae else 1
+
+    def _sample(self, n=50):
+        raise NotImplementedError
+
+    def _log_train_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
+        raise NotImplementedError
+
+    def _log_test_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
+        raise NotImplementedError
+
+    def _write_images(self, epoch, n_images=100):
+        raise NotImplementedError
+
+    log_dir = property(lambda self: self._log_dir)
+    model = property(lambda self: self._model)
+    checkpoint_dir = property(lambda self: self._checkpoint_dir)
+    plot_dir = property(lambda self: self._plot_dir)
+    dataset = property(lambda self: self.test_dataset)
+    num_epochs = property(lambda self: self.parameters['num_epochs'])
+    input_type = property(lambda self: self.parameters['input_type'])
+    condition_dim = property(lambda self: self._condition_dim)
+
+
+class Regression(Problem):
+    """Pose-regression baseline (problems.py:263-359): not part of the accelerated path."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("--problem-type regression is outside the B200 hot path (SURVEY.md §8f); "
+                                  "use the reference for it")
+
+
+class Reconstruction(Problem):
+    def set_model(self):
+        self._set_condition_dim()
+        name = self.parameters['model_name']
+        kw = dict(condition_dim=self._condition_dim, input_dim=int(np.prod(np.array(self._input_size))),
+                  architecture=name.split('-')[0], conditional=self._conditional,
+                  categorical_conditions=self._categorical_conditions,
+                  latent_size=self.parameters.get('latent_size', 256))
+        if 'mvae' in name:
+            kw['use_pose'] = self.parameters['use_pose']
+        self._model = setup_model(name, cross_modal=self._cross_modal, **kw)
+        self._model.to(self._device)
+        self._engine = None
+
+    def _set_condition_dim(self):
+        self._categorical_conditions = True
+        self._condition_dim = int(np.max(np.array(self.train_dataset.targets))) + 1
+
+    def set_criterion(self):
+        self._criterion = self._mvae_elbo_loss if 'mvae' in self.parameters['model_name'] else self._elbo_loss
+
+    # The two ELBO entry points of the reference (problems.py:401-458) exist for callers that hold
+    # reconstructions already; inside this package the loss is fused into the step (StepEngine).
+    def _elbo_loss(self, recon_x, x, means, log_var, loss_mask=None, reduce=None, reduction='sum'):
+        raise NotImplementedError("the ELBO is computed inside the fused step: use _evaluate_model()")
+
+    def _mvae_elbo_loss(self, recon_x, x, means, log_var, loss_mask=None, reduce=None, reduction='sum'):
+        raise NotImplementedError("the ELBO is computed inside the fused step: use _evaluate_model()")
+
+    def _get_engine(self):
+        kind = 'mvae' if ('mvae' in self.parameters['model_name'] and self._cross_modal) else 'vae'
+        if self._engine is None or self._engine.model is not self._model:
+            self._engine = engine.StepEngine(self._model, kind, use_pose=self.parameters.get('use_pose', False),
+                                             pose_multiplier=self._pose_multiplier)
+        self._engine.pose_multiplier = float(self._pose_multiplier)
+        return self._engine
+
+    def _evaluate_model(self, x, targets, **kwargs):
+        if 'mvae' in self.parameters['model_name']:
+            return self._evaluate_mvae(x=x, targets=x)
+        if self._conditional:
+            raise NotImplementedError("--conditional is outside the accelerated path")
+        outputs, loss = self._get_engine().evaluate(x, x, self._kl_weight)
+        outputs.pop('perf_measure', None)
+        return outputs, loss
+
+    def _evaluate_mvae(self, x, targets, loss_mask=None, reduce=None, reduction='sum', condition=None):
+        """problems.py:473-546 as one fused step (3 passes, or 7 with --use-pose)."""
+        assert isinstance(x, list) and isinstance(targets, list)
+        if reduce is not None or reduction != 'sum':
+            raise NotImplementedError("per-sample ELBO scoring (reduce != None) is a 'next' row (SURVEY.md §8f)")
+        if condition is not None:
+            raise NotImplementedError("--conditional is outside the accelerated path")
+        return self._get_engine().evaluate(x, targets, self._kl_weight, loss_mask=loss_mask)
+
+    def _sample(self, n=50):
+        with torch.no_grad():
+            if self._conditional:
+                raise NotImplementedError("--conditional is outside the accelerated path")
+            self._img_logger_dict['Samples/latent_space'] = self.apply_sigmoid(self._model.inference(n=n))
+
+    def _log_train_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
+        n = len(self.train_loader)
+        self._logger_dict['Loss/train_epoch'].append(loss / n)
+        self._logger_dict['KL_annealing/train_epoch'].append(self._kl_weight)
+        self._img_logger_dict['Input_img/train'] = inputs
+        self._img_logger_dict['Output_img/train'] = self.apply_sigmoid(outputs['recon_x'])
+        for k, v in (perf_measure or {}).items():
+            self._logger_dict['Perf_measure_train/' + k].append(_f(v) / n)
+
+    def _log_test_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
+        n = len(self.test_loader)
+        self._logger_dict['Loss/validation_epoch'].append(loss / n)
+        self._img_logger_dict['Input_img/validation'] = inputs
+        self._img_logger_dict['Output_img/validation'] = self.apply_sigmoid(outputs['recon_x'])
+        for k, v in (perf_measure or {}).items():
+            self._logger_dict['Perf_measure_validation/' + k].append(_f(v) / n)
+        self._save_if_best(loss, epoch)
+
+    def _save_if_best(self, loss, epoch):
+        """Best-validation checkpoint with the reference's keys (problems.py:580-586)."""
+        if loss < self._best_loss:
+            state = {'model': self._model.state_dict(), 'loss': loss, 'epoch': epoch}
+            torch.save(state, self._checkpoint_dir + '/epoch_' + str(epoch) + '.ckpt')
+            self._best_loss = loss
+
+    def _write_images(self, epoch, n_images=120):
+        import torchvision
+        L, bs = self._seq_length, self.parameters['batchsize']
+        sv = 'sv' in self.parameters['dataset_path']
+        nrow = L if (L and L > 1 and not sv) else int(math.sqrt(bs))
+        if 'modeling' in self.parameters['problem_type'] and not sv:
+            n_images = min(bs * (L or 1), n_images)
+        else:
+            n_images = min(bs, n_images)
+        for key, v in self._img_logger_dict.items():
+            if isinstance(v, (list, tuple)):
+                img = torch.cat((v[0][:n_images], v[1][:n_images]), dim=0)
+            else:
+                img = v[:n_images]
+            self._writer.add_image(key, torchvision.utils.make_grid(img, nrow=nrow), global_step=epoch)
+
+    def apply_sigmoid(self, img):
+        """Sigmoid for visualisation only (problems.py:616-626); host-side display path."""
+        with torch.no_grad():
+            if isinstance(img, (list, tuple)):
+                return [torch.sigmoid(t) for t in img]
+            return torch.sigmoid(img)
+
+
+class SeqModeling(Reconstruction, Problem):
+    def parse_input(self, data, target):
+        """First frame of every sequence -> resting-state target (problems.py:634-673).  Row selection
+        `[::L]` happens on the host tensors exactly as in the reference, then the batch is shipped."""
+        L, dev, it = self._seq_length, self._device, self.parameters['input_type']
+        model_input = target_output = None
+        if not isinstance(data, list):
+            model_input, target_output = data.to(dev), target.to(dev)
+        elif len(data) == 1:
+            model_input, target_output = data[0].to(dev), target[0].to(dev)
+        elif it in ('visual', 'tactile'):
+            k = 0 if it == 'visual' else 1
+            model_input, target_output = data[k][::L].to(dev), target[k][::L].to(dev)
+        elif it == 'visuotactile':
+            model_input = [data[0][::L].to(dev), data[1][::L].to(dev)]
+            target_output = [target[0][::L].to(dev), target[1][::L].to(dev)]
+        pose = avail = tpose = mask = shock = None
+        if isinstance(data, list) and len(data) > 2:
+            pose, avail = [data[2][::L].to(dev)], data[3][::L].to(dev)
+            tpose, mask = [target[2][::L].to(dev)], target[3][::L].to(dev)
+            shock = data[4][::L].to(dev) if len(data) > 4 else None
+        return ({'model_input': model_input, 'input_object_pose': pose, 'input_available_modals': avail,
+                 'shock': shock},
+                {'target_output': target_output, 'target_object_pose': tpose, 'loss_mask': mask})
+
+    def _set_condition_dim(self):
+        self._categorical_conditions = False
+        try:
+            self._condition_dim = len(self.train_dataset.data[0][0][4])
+        except Exception:
+            self._condition_dim = 0
+
+    def _evaluate_model(self, x, targets, reduction='sum', reduce=None, **kwargs):
+        """problems.py:683-716."""
+        loss_mask = targets['loss_mask'] if self.parameters['mask_loss'] else None
+        x.setdefault('shock', None)
+        if self._conditional:
+            raise NotImplementedError("--conditional is outside the accelerated path")
+        if 'mvae' in self.parameters['model_name']:
+            if self.parameters['use_pose']:
+                if loss_mask is not None:
+                    raise ValueError("--mask-loss with --use-pose cannot broadcast a (B,3,64,64) mask over (B,7) "
+                                     "poses; the reference fails here too (problems.py:446)")
+                return self._evaluate_mvae(x=x['model_input'] + x['input_object_pose'],
+                                           targets=targets['target_output'] + targets['target_object_pose'],
+                                           loss_mask=loss_mask, reduce=reduce, reduction=reduction)
+            return self._evaluate_mvae(x=x['model_input'], targets=targets['target_output'], loss_mask=loss_mask,
+                                       reduce=reduce, reduction=reduction)
+        if reduce is not None or reduction != 'sum':
+            raise NotImplementedError("per-sample ELBO scoring (reduce != None) is a 'next' row (SURVEY.md §8f)")
+        outputs, loss = self._get_engine().evaluate(x['model_input'], targets['target_output'], self._kl_weight,
+                                                    loss_mask=loss_mask)
+        outputs['perf_measure'] = {self.parameters['input_type']: outputs['perf_measure']['x']}
+        return outputs, loss
+
+    def _log_train_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None, log_pose=False):
+        n = len(self.train_loader)
+        self._logger_dict['Loss/train_epoch'].append(loss / n)
+        self._logger_dict['KL_annealing/train_epoch'].append(self._kl_weight)
+        self._img_logger_dict['Input_img/train'] = inputs['model_input']
+        self._img_logger_dict['Output_img/train'] = self.apply_sigmoid(outputs['recon_x'])
+        self._img_logger_dict['Target_img/train'] = targets['target_output']
+        for k, v in (perf_measure or {}).items():
+            self._logger_dict['Perf_measure_train/' + k].append(_f(v) / n)
+
+    def _log_test_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None, log_pose=False):
+        n = len(self.test_loader)
+        self._logger_dict['Loss/validation_epoch'].append(loss / n)
+        self._img_logger_dict['Input_img/validation'] = inputs['model_input']
+        self._img_logger_dict['Output_img/validation'] = self.apply_sigmoid(outputs['recon_x'])
+        self._img_logger_dict['Target_img/validation'] = targets['target_output']
+        for k, v in (perf_measure or {}).items():
+            self._logger_dict['Perf_measure_validation/' + k].append(_f(v) / n)
+        self._save_if_best(loss, epoch)
+
+    def _write_images(self, epoch, n_images=120):
+        # recon_x of an MVAE+pose step carries the pose vector as third entry: images only
+        for k, v in list(self._img_logger_dict.items()):
+            if isinstance(v, (list, tuple)):
+                self._img_logger_dict[k] = [t for t in v if t.dim() == 4]
+        super()._write_images(epoch, n_images)
+
+
+class DynModeling(SeqModeling):
+    def parse_input(self, data, target):
+        """One-step dynamics targets (problems.py:765-803): roll(-1) along the frame axis with every
+        last-of-sequence row replaced by the resting-state target; the pose target is the bare roll
+        (no end-of-sequence fix-up, :798) — reproduced as is."""
+        dev, it = self._device, self.parameters['input_type']
+        model_input = target_output = None
+        if not isinstance(data, list):
+            model_input = data.to(dev)
+        else:
+            L = self._seq_length
+
+            def shifted(k):
+                t = torch.roll(data[k], -1, dims=0).to(dev)
+                t[L - 1::L] = target[k][L - 1::L].to(dev)
+                return t
+            if it in ('visual', 'tactile'):
+                k = 0 if it == 'visual' else 1
+                model_input, target_output = data[k].to(dev), shifted(k)
+            elif it == 'visuotactile':
+                model_input = [data[0].to(dev), data[1].to(dev)]
+                target_output = [shifted(0), shifted(1)]
+        shock = data[4].to(dev) if len(data) > 4 else None
+        return ({'model_input': model_input, 'input_object_pose': [data[2].to(dev)],
+                 'input_available_modals': data[3].to(dev), 'shock': shock},
+                {'target_output': target_output, 'target_object_pose': [torch.roll(data[2], -1, dims=0).to(dev)],
+                 'loss_mask': target[3].to(dev)})

@@ -1,0 +1,241 @@
+"""End-to-end parity of the B200 path against the oracle (CPU fp32 restatement of the reference,
+pinned to the live reference by tests/golden/) on identical weights, inputs and noise.
+
+Stated tolerances (north_star): conv-path tensors (fp16 operands = TF32-equivalent mantissa,
+fp32 accumulate) rel 1e-3 per layer; fp32 PoE/KL 1e-5 given identical inputs (kernel test);
+end-to-end quantities are compared with the norm-wise relative error  ||a-b|| / ||b||  and the
+thresholds written next to each assert.  Masks / index work is bit-exact.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mmdyn_oracle as orc  # noqa: E402
+
+DEV = "cuda"
+KW = dict(condition_dim=0, input_dim=4096, architecture="cnn", conditional=False, categorical_conditions=False,
+          latent_size=256)
+
+
+def nrel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+def make(model_name, use_pose=False, seed=0):
+    from mmdyn_b200.pytorch.models.models import setup_model
+    torch.manual_seed(seed)
+    kw = dict(KW)
+    if "mvae" in model_name:
+        kw["use_pose"] = use_pose
+    m = setup_model(model_name, cross_modal="mvae" in model_name, **kw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    return m.to(DEV), sd
+
+
+def batch(B, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g)
+    return dict(v=r(B, 3, 64, 64), t=r(B, 3, 64, 64), p=r(B, 7), tv=r(B, 3, 64, 64), tt=r(B, 3, 64, 64), tp=r(B, 7))
+
+
+def oracle_noises(passes, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [orc.draw_pass_noise(B, hv, ht, generator=g) for (hv, ht, hp) in passes]
+
+
+@pytest.mark.parametrize("use_pose", [False, True])
+def test_mvae_fused_step_matches_oracle(use_pose):
+    from mmdyn_b200 import engine, noise, optim
+    B = 8
+    model, sd = make("cnn-mvae", use_pose)
+    d = batch(B)
+    passes = orc.MVAE_PASSES_POSE if use_pose else orc.MVAE_PASSES_NOPOSE
+    klw, pm = 0.02, 1000.0
+    # ---- oracle: forward, backward, one Adam step ----
+    pkeys = [k for k, _ in model.named_parameters()]
+    x_o = [d["v"], d["t"]] + ([d["p"]] if use_pose else [])
+    t_o = [d["tv"], d["tt"]] + ([d["tp"]] if use_pose else [])
+    acts = {}
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    out_o, loss_o, per_pass = orc.evaluate_mvae(sd_o, x_o, t_o, klw, pm, use_pose, oracle_noises(passes, B, 7),
+                                                acts=acts)
+    loss_o.backward()
+    grads_o = {k: sd_o[k].grad.clone() for k in pkeys}
+    # ---- B200 path ----
+    eng = engine.StepEngine(model, "mvae", use_pose=use_pose, pose_multiplier=pm,
+                            noise_src=noise.HostNoise(torch.Generator().manual_seed(7)), exact_running_stats=True)
+    opt = optim.FusedAdam(model, lr=1e-3)
+    opt.zero_grad()
+    x_d = [t.to(DEV) for t in x_o]
+    t_d = [t.to(DEV) for t in t_o]
+    out_d, loss_d = eng.evaluate(x_d, t_d, klw)
+    torch.cuda.synchronize()
+    # per-layer activations of the shared visual trunk and of the visual decoder (joint pass)
+    rec = eng._state["enc_rec"]["v"]
+    a0 = acts[0]
+    errs = {
+        "enc.conv1": nrel(nchw(rec["raw1"]), a0["visual_encoder.conv1"]),
+        "enc.conv2": nrel(nchw(rec["raw2"]), a0["visual_encoder.conv2"]),
+        "enc.act2": nrel(nchw(rec["act2"]), a0["visual_encoder.act2"]),
+        "enc.conv3": nrel(nchw(rec["raw3"]), a0["visual_encoder.conv3"]),
+        "enc.conv4": nrel(nchw(rec["raw4"]), a0["visual_encoder.conv4"]),
+        "enc.act4": nrel(nchw(rec["act4"]), a0["visual_encoder.act4"]),
+    }
+    dr = eng._state["dec_rec"]["v"]
+    errs.update({
+        "dec.up": nrel(nchw(dr["act0"][:B]), a0["visual_decoder.up"]),
+        "dec.deconv1": nrel(nchw(dr["raw1"][:B]), a0["visual_decoder.deconv1"]),
+        "dec.deconv2": nrel(nchw(dr["raw2"][:B]), a0["visual_decoder.deconv2"]),
+        "dec.deconv3": nrel(nchw(dr["raw3"][:B]), a0["visual_decoder.deconv3"]),
+        "dec.logits": nrel(dr["logits"][:B], a0["visual_decoder.logits"]),
+    })
+    mu_d, lv_d = eng.ws.bufs["mu"], eng.ws.bufs["lv"]
+    for i, pp in enumerate(per_pass):
+        errs[f"mu[{i}]"] = nrel(mu_d[i], pp["mu"])
+        errs[f"lv[{i}]"] = nrel(lv_d[i], pp["lv"])
+    errs["loss"] = abs(loss_d.item() - loss_o.item()) / abs(loss_o.item())
+    print("\n".join(f"{k:14s} {v:.3e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        # chained activations compound the per-layer 1e-3 budget over depth (isolated layers are
+        # held to 1e-3 in test_layers_in_isolation); the scalar loss averages the noise out
+        tol = 1e-4 if k == "loss" else 3e-3
+        assert v < tol, (k, v, tol)
+    # outputs dict: reference bindings (recon_x of the joint pass, posterior of the last pass)
+    for a, b in zip(out_d["recon_x"], out_o["recon_x"]):
+        assert nrel(a, b) < 2e-3
+    assert nrel(out_d["means"], out_o["means"]) < 2e-3 and nrel(out_d["log_var"], out_o["log_var"]) < 2e-3
+    for k, v in out_o["perf_measure"].items():
+        assert abs(float(out_d["perf_measure"][k]) - v) / abs(v) < 1e-3, k
+    # BatchNorm running statistics and counters (exact_running_stats=True replays every pass)
+    sdd = model.state_dict()
+    for k in sd_o:
+        if k.endswith("num_batches_tracked"):
+            assert int(sdd[k]) == int(sd_o[k]), k
+        elif "running_" in k:
+            assert nrel(sdd[k], sd_o[k]) < 2e-3, (k, nrel(sdd[k], sd_o[k]))
+    # ---- backward ----
+    loss_d.backward()
+    torch.cuda.synchronize()
+    gerr = {k: nrel(p.grad, grads_o[k]) for k, p in model.named_parameters()}
+    worst = sorted(gerr.items(), key=lambda kv: -kv[1])[:8]
+    print("worst gradient errors:\n" + "\n".join(f"{k:50s} {v:.3e}" for k, v in worst))
+    # fp16 activations/gradients through 10 layers: norm-wise 1e-2 per tensor, 3e-3 on the whole arena.
+    # With the pose expert the ReLU MLP decoder sits behind z: a 1e-3 perturbation of z (fp16 image
+    # trunks) flips a few ReLU units of the 8-row batch and moves dz of that pass by ~2 % (measured:
+    # the pose kernels themselves reproduce torch to 4e-7 on identical inputs), so the bound is 5e-2.
+    tol_t, tol_all = (5e-2, 2e-2) if use_pose else (1e-2, 3e-3)
+    for k, v in gerr.items():
+        assert v < tol_t, (k, v)
+    flat_o = torch.cat([grads_o[k].reshape(-1) for k in pkeys])
+    flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    assert nrel(flat_d, flat_o) < tol_all, nrel(flat_d, flat_o)
+    # ---- one Adam step (problems.py:155) ----
+    # (a) in situ: the fused update applied to the B200 gradients equals the oracle's Adam applied to
+    #     the SAME gradients to fp32 round-off (1e-6 abs on parameters of scale 1e-2..1);
+    # (b) against the oracle's own step: step 1 of Adam is lr*g/(|g|+eps) ~ lr*sign(g), so entries
+    #     whose gradient is below the fp16 noise floor may flip sign; bound the relative L2 distance of
+    #     the parameter DELTAS (0.15) instead of an element-wise tolerance.
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    g_dev = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        def oracle_adam(grads):
+            st = {"step": 0, "m": [torch.zeros_like(sd[k]) for k in pkeys], "v": [torch.zeros_like(sd[k]) for k in pkeys]}
+            params = [sd[k].clone() for k in pkeys]
+            orc.adam_step(params, [grads[k] for k in pkeys], st, lr=1e-3)
+            return params
+        same_g = oracle_adam(g_dev)
+        own_g = oracle_adam(grads_o)
+    num = den = 0.0
+    for (k, p), ps, po in zip(model.named_parameters(), same_g, own_g):
+        assert (p.detach().cpu() - ps).abs().max().item() < 1e-6, k
+        dd, do = (p.detach().cpu() - before[k].cpu()).double(), (po - sd[k]).double()
+        num += (dd - do).pow(2).sum().item()
+        den += do.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 0.15, (num / den) ** 0.5
+
+
+def test_vae_fused_step_and_module_api_match_oracle():
+    from mmdyn_b200 import engine, noise
+    B = 8
+    model, sd = make("cnn-vae")
+    d = batch(B, seed=3)
+    klw = 0.02
+    pkeys = [k for k, _ in model.named_parameters()]
+    g = torch.Generator().manual_seed(11)
+    mask, _, eps = orc.draw_pass_noise(B, True, False, generator=g)
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    out_o, loss_o = orc.evaluate_vae(sd_o, d["t"], d["tt"], klw, (mask, eps), track=True, input_type="tactile")
+    loss_o.backward()
+    # fused step
+    eng = engine.StepEngine(model, "vae", noise_src=noise.HostNoise(torch.Generator().manual_seed(11)))
+    out_d, loss_d = eng.evaluate(d["t"].to(DEV), d["tt"].to(DEV), klw)
+    loss_d.backward()
+    torch.cuda.synchronize()
+    assert abs(loss_d.item() - loss_o.item()) / loss_o.item() < 1e-4
+    assert nrel(out_d["recon_x"], out_o["recon_x"]) < 2e-3
+    assert nrel(out_d["means"], out_o["means"]) < 2e-3 and nrel(out_d["log_var"], out_o["log_var"]) < 2e-3
+    assert abs(float(out_d["perf_measure"]["x"]) - out_o["perf_measure"]["tactile"]) / out_o["perf_measure"]["tactile"] < 1e-3
+    g1 = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    for k in pkeys:
+        assert nrel(g1[k], sd_o[k].grad) < 1e-2, (k, nrel(g1[k], sd_o[k].grad))
+    # module-level API (model(x) + torch loss + autograd) on a fresh copy of the same weights
+    model2, _ = make("cnn-vae")
+    model2.noise = noise.HostNoise(torch.Generator().manual_seed(11))
+    recon, mu, lv = model2(d["t"].to(DEV))
+    kld = -0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp())
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(recon, d["tt"].to(DEV), reduction="sum")
+    loss2 = (bce + klw * kld) / B
+    loss2.backward()
+    torch.cuda.synchronize()
+    assert abs(loss2.item() - loss_o.item()) / loss_o.item() < 1e-4
+    assert nrel(mu, out_o["means"]) < 2e-3
+    for k, p in model2.named_parameters():
+        assert nrel(p.grad, sd_o[k].grad) < 1e-2, (k, nrel(p.grad, sd_o[k].grad))
+
+
+def test_mvae_module_api_forward_and_inference():
+    from mmdyn_b200 import noise
+    B = 4
+    model, sd = make("cnn-mvae", True, seed=2)
+    model.noise = noise.HostNoise(torch.Generator().manual_seed(5))
+    d = batch(B, seed=9)
+    g = torch.Generator().manual_seed(5)
+    nz = orc.draw_pass_noise(B, True, False, generator=g)
+    sd_o = copy.deepcopy(sd)
+    v_o, t_o, p_o, mu_o, lv_o = orc.mvae_forward(sd_o, d["v"], None, d["p"], nz, True)
+    v, t, p, mu, lv = model([d["v"].to(DEV), None], pose=d["p"].to(DEV))
+    torch.cuda.synchronize()
+    assert nrel(mu, mu_o) < 2e-3 and nrel(lv, lv_o) < 2e-3
+    assert nrel(v, v_o) < 2e-3 and nrel(t, t_o) < 2e-3 and nrel(p, p_o) < 2e-3
+    vi, ti = model.inference(n=6)
+    assert vi.shape == (6, 3, 64, 64) and ti.shape == (6, 3, 64, 64) and torch.isfinite(vi).all()
+    # state_dict round trip keeps the reference's 106 keys and survives a re-load
+    keys = list(model.state_dict().keys())
+    assert len(keys) == 106 and keys[0] == "visual_encoder.conv_net.0.weight"
+    model.load_state_dict({k: v_.to(DEV) for k, v_ in sd.items()})
+    v2, *_ = model([d["v"].to(DEV), None], pose=d["p"].to(DEV))
+    assert torch.isfinite(v2).all()
+
+
+def test_product_of_experts_module_matches_reference_formula():
+    from mmdyn_b200.pytorch.models.vae import ProductOfExperts
+    torch.manual_seed(0)
+    mu, lv = torch.randn(4, 9, 256), torch.randn(4, 9, 256) * 0.5
+    mu[0].zero_(), lv[0].zero_()
+    m_o, l_o = orc.product_of_experts(mu.double(), lv.double())
+    m_d, l_d = ProductOfExperts()(mu.to(DEV), lv.to(DEV))
+    assert nrel(m_d, m_o) < 1e-5 and nrel(l_d, l_o) < 1e-5
