@@ -214,6 +214,11 @@ int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scal
 int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step_count,
                     float gscale, void* stream);
+/* same update with the step count read from device memory (*step_dev, already incremented for
+ * this update): lets a captured CUDA graph replay the optimizer with correct bias correction */
+int mmdyn_adam_flat_devstep(float* p, const float* g, float* m, float* v, long long n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay,
+                            const uint64_t* step_dev, float gscale, void* stream);
 /* SGD with momentum (problems.py:132-136): buf = mom*buf + (g + wd*p); p -= lr*buf */
 int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n, float lr, float momentum,
                    float weight_decay, int first_step, float gscale, void* stream);

@@ -575,7 +575,12 @@ logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, f
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-            float bc1, float bc2_sqrt, float gscale) {
+            float bc1, float bc2_sqrt, float gscale, const uint64_t* __restrict__ step_dev) {
+  if (step_dev) {  // bias corrections from the device-resident step counter
+    const double t = static_cast<double>(*step_dev);
+    bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), t));
+    bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(b2), t)));
+  }
   const long long n4 = n >> 2;
   const float step = lr / bc1;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
@@ -949,7 +954,20 @@ extern "C" int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, lon
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step_count);
   adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                         static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
-                                                        gscale);
+                                                        gscale, nullptr);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_adam_flat_devstep(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                       float beta1, float beta2, float eps, float weight_decay,
+                                       const uint64_t* step_dev, float gscale, void* stream) {
+  MMDYN_REQUIRE(p && g && m && v && n > 0 && step_dev, "adam_flat_devstep: bad arguments");
+  MMDYN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+                "adam_flat_devstep: arenas must be 16-byte aligned");
+  adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f,
+                                                        1.0f, gscale, step_dev);
   LAUNCHED();
   return MMDYN_OK;
 }

@@ -215,20 +215,23 @@ class _NetBase:
             self._token = tok
 
 
-def _gemm(pl_geom, A, W, out, n_img, bias, f32_out, alloc_zero=None):
-    """igemm with an automatic split-K decision for fp32 outputs."""
-    ks = plan.choose_ksplit(pl_geom, n_img) if f32_out else 1
+def _ig(pl, which, A, out, n_img, bias=None, f32_out=False):
+    """One implicit-GEMM launch of layer `pl` ('fwd' or 'dgrad'); fp32 outputs may split K."""
+    geom, W = (pl.lp.fwd, pl.Wf) if which == "fwd" else (pl.lp.dgrad, pl.Wd)
+    kw = dict(tag=f"{pl.lp.name}.{which}", macs_per_img=pl.lp.extra.get("macs"))
+    ks = plan.choose_ksplit(geom, n_img) if f32_out else 1
     if ks > 1:
         out.zero_()
-        ops.igemm(pl_geom, A, W, out, n_img, bias=bias, ksplit=ks, out_mode=2)
+        ops.igemm(geom, A, W, out, n_img, bias=bias, ksplit=ks, out_mode=2, **kw)
     else:
-        ops.igemm(pl_geom, A, W, out, n_img, bias=bias, out_mode=1 if f32_out else None)
+        ops.igemm(geom, A, W, out, n_img, bias=bias, out_mode=1 if f32_out else None, **kw)
 
 
 def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale):
     wg = pl.lp.wgrad
     dWp = alloc(key, (wg.Cn, wg.K), F32, zero=True)
-    ops.wgrad(wg, G, Nat, dWp, n_img, scale=scale, row_splits=plan.choose_row_splits(wg, n_img))
+    ops.wgrad(wg, G, Nat, dWp, n_img, scale=scale, row_splits=plan.choose_row_splits(wg, n_img),
+              tag=f"{pl.lp.name}.wgrad", macs_per_img=pl.lp.extra.get("macs"))
     ops.unpack_add_f32(dWp, pl.idx_wgrad, arena.grad)
 
 
@@ -292,23 +295,23 @@ class EncoderExec(_NetBase):
         act1 = alloc(key + ".act1", (B, 32, 32, 32), F16)
         ops.bn_swish_fwd(raw1, None, act1, 1, B * 1024, 32)
         raw2 = alloc(key + ".raw2", (B, 16, 16, 64), F16)
-        ops.igemm(self.c2.lp.fwd, act1, self.c2.Wf, raw2, B)
+        _ig(self.c2, "fwd", act1, raw2, B)
         act2 = alloc(key + ".act2", (B, 16, 16, 64), F16)
         r["bn2"] = self.bn2.forward(raw2, act2, 1, B * 256, alloc, key + ".bn2", track, nm)
         raw3 = alloc(key + ".raw3", (B, 8, 8, 128), F16)
-        ops.igemm(self.c3.lp.fwd, act2, self.c3.Wf, raw3, B)
+        _ig(self.c3, "fwd", act2, raw3, B)
         act3 = alloc(key + ".act3", (B, 8, 8, 128), F16)
         r["bn3"] = self.bn3.forward(raw3, act3, 1, B * 64, alloc, key + ".bn3", track, nm)
         raw4 = alloc(key + ".raw4", (B, 5, 5, 256), F16)
-        ops.igemm(self.c4.lp.fwd, act3, self.c4.Wf, raw4, B)
+        _ig(self.c4, "fwd", act3, raw4, B)
         act4 = alloc(key + ".act4", (B, 5, 5, 256), F16)
         r["bn4"] = self.bn4.forward(raw4, act4, 1, B * 25, alloc, key + ".bn4", track, nm)
         fc_raw = alloc(key + ".fc_raw", (B, 512), F32)
-        _gemm(self.fc.lp.fwd, act4, self.fc.Wf, fc_raw, B, self.fc.bias, True)
+        _ig(self.fc, "fwd", act4, fc_raw, B, self.fc.bias, True)
         h = alloc(key + ".h", (nm, B, 512), F16)
         ops.swish_dropout_fwd(fc_raw, masks, h, B, 512)
         heads = alloc(key + ".heads", (nm * B, LATENT_HEADS), F32)
-        _gemm(self.heads.lp.fwd, h, self.heads.Wf, heads, nm * B, self.heads.bias, True)
+        _ig(self.heads, "fwd", h, heads, nm * B, self.heads.bias, True)
         r.update(raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3, raw4=raw4, act4=act4,
                  fc_raw=fc_raw, h=h, heads=heads)
         return r
@@ -326,25 +329,25 @@ class EncoderExec(_NetBase):
         ops.unpack_add_f32(db, self.heads.bias_idx, arena.grad)
         _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale)
         dH = alloc(key + ".dH", (rows, 512), F32)
-        _gemm(self.heads.lp.dgrad, dh16, self.heads.Wd, dH, rows, None, True)
+        _ig(self.heads, "dgrad", dh16, dH, rows, None, True)
         dfc = alloc(key + ".dfc16", (B, 512), F16)
         ops.swish_dropout_bwd(r["fc_raw"], r["masks"], dH, dfc, B, 512)
         ops.colsum_f16(dfc, self.pview("fc_net.0.bias", True), B, 512, 512, unscale)
         _wgrad_into(self.fc, r["act4"], dfc, B, arena, alloc, key + ".dW_fc", unscale)
         d4 = alloc(key + ".d4", (B, 5, 5, 256), F16)
-        ops.igemm(self.fc.lp.dgrad, dfc, self.fc.Wd, d4, B)
+        _ig(self.fc, "dgrad", dfc, d4, B)
         self.bn4.backward(r["raw4"], r["bn4"][0], r["bn4"][1], d4, 1, B * 25, alloc, key + ".bn4", unscale)
         _wgrad_into(self.c4, r["act3"], d4, B, arena, alloc, key + ".dW_c4", unscale)
         d3 = alloc(key + ".d3", (B, 8, 8, 128), F16)
-        ops.igemm(self.c4.lp.dgrad, d4, self.c4.Wd, d3, B)
+        _ig(self.c4, "dgrad", d4, d3, B)
         self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], d3, 1, B * 64, alloc, key + ".bn3", unscale)
         _wgrad_into(self.c3, r["act2"], d3, B, arena, alloc, key + ".dW_c3", unscale)
         d2 = alloc(key + ".d2", (B, 16, 16, 64), F16)
-        ops.igemm(self.c3.lp.dgrad, d3, self.c3.Wd, d2, B)
+        _ig(self.c3, "dgrad", d3, d2, B)
         self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], d2, 1, B * 256, alloc, key + ".bn2", unscale)
         _wgrad_into(self.c2, r["act1"], d2, B, arena, alloc, key + ".dW_c2", unscale)
         d1 = alloc(key + ".d1", (B, 32, 32, 32), F16)
-        ops.igemm(self.c2.lp.dgrad, d2, self.c2.Wd, d1, B)
+        _ig(self.c2, "dgrad", d2, d1, B)
         ops.bn_swish_bwd_reduce(r["raw1"], None, None, d1, None, 1, B * 1024, 32)
         ops.conv1_wgrad(r["x"], d1, self.pview("conv_net.0.weight", True), B, unscale, 296)
 
@@ -369,23 +372,23 @@ class DecoderExec(_NetBase):
         R = G * B
         r = {"zh": zh, "G": G, "B": B}
         raw0 = alloc(key + ".raw0", (R, 5, 5, 256), F16)
-        ops.igemm(self.up.lp.fwd, zh, self.up.Wf, raw0, R, bias=self.up.bias)
+        _ig(self.up, "fwd", zh, raw0, R, self.up.bias)
         act0 = alloc(key + ".act0", (R, 5, 5, 256), F16)
         ops.bn_swish_fwd(raw0, None, act0, 1, R * 25, 256)
         raw1 = alloc(key + ".raw1", (R, 8, 8, 128), F16)
-        ops.igemm(self.d1.lp.fwd, act0, self.d1.Wf, raw1, R)
+        _ig(self.d1, "fwd", act0, raw1, R)
         act1 = alloc(key + ".act1", (R, 8, 8, 128), F16)
         r["bn1"] = self.bn1.forward(raw1, act1, G, B * 64, alloc, key + ".bn1", track)
         raw2 = alloc(key + ".raw2", (R, 16, 16, 64), F16)
-        ops.igemm(self.d2.lp.fwd, act1, self.d2.Wf, raw2, R)
+        _ig(self.d2, "fwd", act1, raw2, R)
         act2 = alloc(key + ".act2", (R, 16, 16, 64), F16)
         r["bn2"] = self.bn2.forward(raw2, act2, G, B * 256, alloc, key + ".bn2", track)
         raw3 = alloc(key + ".raw3", (R, 32, 32, 32), F16)
-        ops.igemm(self.d3.lp.fwd, act2, self.d3.Wf, raw3, R)
+        _ig(self.d3, "fwd", act2, raw3, R)
         act3 = alloc(key + ".act3", (R, 32, 32, 32), F16)
         r["bn3"] = self.bn3.forward(raw3, act3, G, B * 1024, alloc, key + ".bn3", track)
         logits = alloc(key + ".logits", (R, 3, 64, 64), F32)
-        ops.igemm(self.d4.lp.fwd, act3, self.d4.Wf, logits, R)
+        _ig(self.d4, "fwd", act3, logits, R)
         r.update(raw0=raw0, act0=act0, raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3,
                  logits=logits)
         return r
@@ -397,26 +400,26 @@ class DecoderExec(_NetBase):
         R = G * B
         _wgrad_into(self.d4, dl8, r["act3"], R, arena, alloc, key + ".dW_d4", unscale)
         g3 = alloc(key + ".g3", (R, 32, 32, 32), F16)
-        ops.igemm(self.d4.lp.dgrad, dl8, self.d4.Wd, g3, R)
+        _ig(self.d4, "dgrad", dl8, g3, R)
         self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], g3, G, B * 1024, alloc, key + ".bn3", unscale)
         _wgrad_into(self.d3, g3, r["act2"], R, arena, alloc, key + ".dW_d3", unscale)
         g2 = alloc(key + ".g2", (R, 16, 16, 64), F16)
-        ops.igemm(self.d3.lp.dgrad, g3, self.d3.Wd, g2, R)
+        _ig(self.d3, "dgrad", g3, g2, R)
         self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], g2, G, B * 256, alloc, key + ".bn2", unscale)
         _wgrad_into(self.d2, g2, r["act1"], R, arena, alloc, key + ".dW_d2", unscale)
         g1 = alloc(key + ".g1", (R, 8, 8, 128), F16)
-        ops.igemm(self.d2.lp.dgrad, g2, self.d2.Wd, g1, R)
+        _ig(self.d2, "dgrad", g2, g1, R)
         self.bn1.backward(r["raw1"], r["bn1"][0], r["bn1"][1], g1, G, B * 64, alloc, key + ".bn1", unscale)
         _wgrad_into(self.d1, g1, r["act0"], R, arena, alloc, key + ".dW_d1", unscale)
         g0 = alloc(key + ".g0", (R, 5, 5, 256), F16)
-        ops.igemm(self.d1.lp.dgrad, g1, self.d1.Wd, g0, R)
+        _ig(self.d1, "dgrad", g1, g0, R)
         ops.bn_swish_bwd_reduce(r["raw0"], None, None, g0, None, 1, R * 25, 256)
         dbp = alloc(key + ".db_up", (6400,), F32, zero=True)
         ops.colsum_f16(g0, dbp, R, 6400, 6400, unscale)
         ops.unpack_add_f32(dbp, self.up.bias_idx, arena.grad)
         _wgrad_into(self.up, r["zh"], g0, R, arena, alloc, key + ".dW_up", unscale)
         dz = alloc(key + ".dz", (R, 256), F32)
-        _gemm(self.up.lp.dgrad, g0, self.up.Wd, dz, R, None, True)
+        _ig(self.up, "dgrad", g0, dz, R, None, True)
         return dz
 
 
@@ -563,6 +566,8 @@ class StepEngine:
         self.ws = None
         self._token = 0
         self._state = None
+        self.always_refresh = False   # set while capturing a CUDA graph: the packing kernels must be in it
+        self.bucket_hook = None       # callable(prefixes) fired when those sub-networks' gradients are final
 
     # -- helpers ------------------------------------------------------------------------------
     def _noise(self):
@@ -580,10 +585,12 @@ class StepEngine:
             self.ws = Workspace(arena.flat.device)
         return arena, ex
 
-    def evaluate(self, x, targets, kl_weight, loss_mask=None, want_outputs=True):
+    def evaluate(self, x, targets, kl_weight, loss_mask=None, want_outputs=True, need_grad=None, autograd=True):
         """x / targets: tensor (vae) or list [visual, tactile(, pose)] (mvae), fp32, on the GPU.
         Returns (outputs, loss) like the reference; loss.backward() then fills the parameter
-        gradients.  Under torch.no_grad() only the forward runs (Problem._test_epoch)."""
+        gradients.  Under torch.no_grad() only the forward runs (Problem._test_epoch).
+        need_grad / autograd=False: keep the backward state without an autograd node, for callers
+        that invoke backward() themselves (CUDA-graph capture of the whole step)."""
         if self.kind == "vae":
             xs, ts = {"x": x}, {"x": targets}
         else:
@@ -602,7 +609,11 @@ class StepEngine:
         for k in xs:
             xs[k] = xs[k].contiguous().float()
             ts[k] = ts[k].contiguous().float()
-        need_grad = torch.is_grad_enabled()
+        need_grad = torch.is_grad_enabled() if need_grad is None else bool(need_grad)
+        if self.always_refresh:
+            for grp in (ex["enc"], ex["dec"]):
+                for net in grp.values():
+                    net._token = None
         gs = float(self.grad_scale) if self.grad_scale else float(B)
         npass = len(self.passes)
         src = self._noise()
@@ -693,7 +704,8 @@ class StepEngine:
                            pose_rec=pose_rec, dec_rec=dec_rec, pdec_rec=pdec_rec, dl8=dl8, d_prec=d_prec,
                            enc_passes=enc_passes, dec_groups=dec_groups, pose_passes=pose_passes, eps=eps,
                            experts=experts, img_mods=img_mods) if need_grad else None
-        loss = _StepLossFn.apply(arena.params[0], loss_value, self, self._token) if need_grad else loss_value
+        loss = _StepLossFn.apply(arena.params[0], loss_value, self, self._token) if (need_grad and autograd) \
+            else loss_value
 
         outputs = None
         if want_outputs:
@@ -737,6 +749,12 @@ class StepEngine:
         last = len(self.passes) - 1
         return {"recon_x": rec, "means": mu_all[last].clone(), "log_var": lv_all[last].clone(), "perf_measure": perf}
 
+    def backward(self):
+        """Run the fused backward of the last evaluate(need_grad=True) (no autograd involved)."""
+        if self._state is None:
+            raise RuntimeError("mmdyn_b200: no pending step to differentiate")
+        self._backward(self._state["token"])
+
     def _backward(self, token, grad_out=None):
         st = self._state
         if st is None or st["token"] != token:
@@ -749,8 +767,11 @@ class StepEngine:
         unscale = 1.0 / gs
         D = 256
         img_mods = st["img_mods"]
-        dz = {m: ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale)
-              for m in img_mods}
+        hook = self.bucket_hook or (lambda prefixes: None)
+        dz = {}
+        for m in img_mods:
+            dz[m] = ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale)
+            hook([self.mods[m][1]])
         dzp = ex["pose"].dec_backward(st["pdec_rec"], st["d_prec"], ws, "pdec", unscale) if self.use_pose else None
         dh = {m: ws("dheads_" + m, (len(st["enc_passes"][m]) * B, 512), F32, zero=True) for m in img_mods}
         dhp = ws("dheads_p", (B, 512), F32, zero=True) if self.use_pose else None
@@ -771,6 +792,71 @@ class StepEngine:
                         st["klw"] * gs / B, [o[:, :D] for o in outs], [o[:, D:] for o in outs], 2 * D, True, B, D)
         for m in img_mods:
             ex["enc"][self.mods[m][0]].backward(st["enc_rec"][m], dh[m], ws, "enc_" + m, unscale)
+            hook([self.mods[m][0]])
         if self.use_pose:
             ex["pose"].enc_backward(st["pose_rec"], dhp, ws, "penc", unscale)
+            hook(["pose_encoder", "pose_decoder"])
         self._state = None
+
+
+class GraphedTrainStep:
+    """zero_grad + fused forward + fused backward (+ optimizer) captured once in a CUDA graph and
+    replayed per batch: the ~300 kernel launches of a cnn-mvae+pose step cost one graph launch.
+
+    Inputs are copied into static device buffers (`load`), results are static tensors overwritten
+    by every replay.  The noise source must be a DeviceNoise (device-resident Philox counter) and
+    the optimizer a FusedAdam / FusedSGD (device-resident step counter), so that replays advance.
+    With `grad_sync` (data parallel) the graph ends after the backward; the caller all-reduces the
+    gradient arena and then calls `apply()`, a second graph holding the optimizer update."""
+
+    def __init__(self, step_engine, optimizer, example_x, example_t, kl_weight, loss_mask=None, split_optimizer=False,
+                 warmup=2):
+        self.eng, self.opt, self.klw = step_engine, optimizer, float(kl_weight)
+        self.split = split_optimizer
+        lst = isinstance(example_x, (list, tuple))
+        self.x = [t.clone() for t in example_x] if lst else example_x.clone()
+        self.t = [t.clone() for t in example_t] if lst else example_t.clone()
+        self.mask = loss_mask.clone() if loss_mask is not None else None
+        eng = self.eng
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body(True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        eng.always_refresh = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs, self.loss = self._body(not self.split)
+        self.graph_opt = None
+        if self.split:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self.opt.step()
+        eng.always_refresh = False
+
+    def _body(self, with_opt):
+        self.opt.zero_grad()
+        outputs, loss = self.eng.evaluate(self.x, self.t, self.klw, loss_mask=self.mask, need_grad=True, autograd=False)
+        self.eng.backward()
+        if with_opt:
+            self.opt.step()
+        return outputs, loss
+
+    def load(self, x, t, non_blocking=True):
+        if isinstance(self.x, list):
+            for d, s_ in zip(self.x, x):
+                d.copy_(s_, non_blocking=non_blocking)
+            for d, s_ in zip(self.t, t):
+                d.copy_(s_, non_blocking=non_blocking)
+        else:
+            self.x.copy_(x, non_blocking=non_blocking)
+            self.t.copy_(t, non_blocking=non_blocking)
+
+    def run(self):
+        self.graph.replay()
+        return self.outputs, self.loss
+
+    def apply(self):
+        self.graph_opt.replay()

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mmdyn_scale_f32": ([_P, _LL, _F, _P], _I),
     "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _P], _I),
     "mmdyn_adam_flat": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P], _I),
+    "mmdyn_adam_flat_devstep": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _F, _P], _I),
     "mmdyn_sgd_flat": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),
     "mmdyn_fill_normal": ([_P, _LL, _U64, _U64, _P, _P], _I),
     "mmdyn_fill_dropout_mask": ([_P, _LL, _F, _U64, _U64, _P, _P], _I),

@@ -31,7 +31,58 @@ def _ptr_array(tensors, n):
     return arr
 
 
-def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None, a_pix_stride=None):
+# ---------------------------------------------------------------------------------------------
+# optional per-launch timing with CUDA events on the launching stream (bench.py roofline pass);
+# off by default: the timed steps of the benchmark run without it
+# ---------------------------------------------------------------------------------------------
+_prof = None
+
+
+def start_profile():
+    global _prof
+    _prof = []
+
+
+def stop_profile():
+    """-> {tag: dict(count, ms, flops, bytes)} (synchronises)."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for tag, e0, e1, alg in rec or []:
+        d = out.setdefault(tag, dict(count=0, ms=0.0, flops=0.0, bytes=0.0))
+        d["count"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        if alg is not None:
+            d["flops"] += alg[0]
+            d["bytes"] += alg[1]
+    return out
+
+
+class _Timed:
+    __slots__ = ("tag", "alg", "e0")
+
+    def __init__(self, tag, alg=None):
+        self.tag, self.alg = tag, alg
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.tag, self.e0, e1, self.alg() if callable(self.alg) else self.alg))
+
+
+def _esz(t):
+    return t.element_size()
+
+
+def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None, a_pix_stride=None, tag="igemm",
+          macs_per_img=None):
     d = IgemmDesc()
     d.A, d.W, d.out = A.data_ptr(), Wp.data_ptr(), out.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
@@ -47,10 +98,19 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     d.out_mode = geom.out_mode if out_mode is None else out_mode
     d.OH, d.OW, d.s_out = geom.OH, geom.OW, geom.s_out
     d.ldc = geom.ldc if ldc is None else ldc
-    check(_L().mmdyn_igemm(C.byref(d), _stream()), "mmdyn_igemm")
+
+    def alg():
+        # algorithmic work: true MACs of the layer (no padding / phase-union waste) and one read of
+        # each operand + one write of the output
+        macs = (macs_per_img if macs_per_img is not None else geom.P * geom.n_phases * geom.N * geom.K) * n_img
+        nbytes = n_img * geom.IH * geom.IW * geom.Cin * 2 + Wp.numel() * 2 + out.numel() * _esz(out)
+        return 2.0 * macs, float(nbytes)
+    with _Timed(tag, alg):
+        check(_L().mmdyn_igemm(C.byref(d), _stream()), "mmdyn_igemm")
 
 
-def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride=None, g_pix_stride=None):
+def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride=None, g_pix_stride=None,
+          tag="wgrad", macs_per_img=None):
     d = WgradDesc()
     d.G, d.Nat, d.dW = G.data_ptr(), Nat.data_ptr(), dW.data_ptr()
     d.n_img, d.P, d.OXv, d.IH, d.IW = n_img, geom.P, geom.OXv, geom.IH, geom.IW
@@ -62,139 +122,179 @@ def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride
     d.nat_stride = geom.nat_stride if nat_stride is None else nat_stride
     d.ldw = geom.K if ldw is None else ldw
     d.row_splits, d.scale = row_splits, scale
-    check(_L().mmdyn_wgrad(C.byref(d), _stream()), "mmdyn_wgrad")
+
+    def alg():
+        macs = (macs_per_img if macs_per_img is not None else geom.P * geom.Cn * geom.K) * n_img
+        nbytes = n_img * geom.IH * geom.IW * geom.Cg * 2 + n_img * geom.P * geom.Cn * 2 + dW.numel() * 4
+        return 2.0 * macs, float(nbytes)
+    with _Timed(tag, alg):
+        check(_L().mmdyn_wgrad(C.byref(d), _stream()), "mmdyn_wgrad")
 
 
 def conv1_fwd(x, Wp, out, n_img):
-    check(_L().mmdyn_conv1_fwd(_ptr(x), _ptr(Wp), _ptr(out), n_img, _stream()), "conv1_fwd")
+    with _Timed("conv1_fwd", lambda: (2.0 * n_img * 1024 * 32 * 48, n_img * (3 * 64 * 64 * 4 + 1024 * 32 * 2.0))):
+        check(_L().mmdyn_conv1_fwd(_ptr(x), _ptr(Wp), _ptr(out), n_img, _stream()), "conv1_fwd")
 
 
 def conv1_wgrad(x, dRaw, dW, n_img, scale, row_splits):
-    check(_L().mmdyn_conv1_wgrad(_ptr(x), _ptr(dRaw), _ptr(dW), n_img, scale, row_splits, _stream()), "conv1_wgrad")
+    with _Timed("conv1_wgrad", lambda: (2.0 * n_img * 1024 * 32 * 48, n_img * (3 * 64 * 64 * 4 + 1024 * 32 * 2.0))):
+        check(_L().mmdyn_conv1_wgrad(_ptr(x), _ptr(dRaw), _ptr(dW), n_img, scale, row_splits, _stream()), "conv1_wgrad")
 
 
 def bn_stats(x, sums, G, rows, Cch):
-    check(_L().mmdyn_bn_stats(_ptr(x), _ptr(sums), G, rows, Cch, _stream()), "bn_stats")
+    with _Timed("bn_stats", lambda: (0.0, G * rows * Cch * 2.0)):
+        check(_L().mmdyn_bn_stats(_ptr(x), _ptr(sums), G, rows, Cch, _stream()), "bn_stats")
 
 
 def bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows, Cch, eps, momentum,
                 stat_repeat=1):
-    check(_L().mmdyn_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(ab), _ptr(mean_invstd),
-                                 _ptr(running_mean), _ptr(running_var), G, rows, Cch, eps, momentum, stat_repeat,
-                                 _stream()),
-          "bn_finalize")
+    with _Timed("bn_finalize", None):
+        check(_L().mmdyn_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(ab), _ptr(mean_invstd),
+                                     _ptr(running_mean), _ptr(running_var), G, rows, Cch, eps, momentum, stat_repeat,
+                                     _stream()),
+              "bn_finalize")
 
 
 def bn_swish_fwd(x, ab, y, G, rows, Cch):
-    check(_L().mmdyn_bn_swish_fwd(_ptr(x), _ptr(ab), _ptr(y), G, rows, Cch, _stream()), "bn_swish_fwd")
+    with _Timed("bn_swish_fwd", lambda: (0.0, G * rows * Cch * 4.0)):
+        check(_L().mmdyn_bn_swish_fwd(_ptr(x), _ptr(ab), _ptr(y), G, rows, Cch, _stream()), "bn_swish_fwd")
 
 
 def bn_swish_bwd_reduce(x, ab, mean_invstd, dY, sums2, G, rows, Cch):
-    check(_L().mmdyn_bn_swish_bwd_reduce(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(dY), _ptr(sums2), G, rows,
-                                         Cch, _stream()), "bn_swish_bwd_reduce")
+    with _Timed("bn_swish_bwd_reduce", lambda: (0.0, G * rows * Cch * 6.0)):
+        check(_L().mmdyn_bn_swish_bwd_reduce(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(dY), _ptr(sums2), G, rows,
+                                             Cch, _stream()), "bn_swish_bwd_reduce")
 
 
 def bn_bwd_apply(x, ab, mean_invstd, sums2, dU, dgamma, dbeta, G, rows, Cch, unscale):
-    check(_L().mmdyn_bn_bwd_apply(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(sums2), _ptr(dU), _ptr(dgamma),
-                                  _ptr(dbeta), G, rows, Cch, unscale, _stream()), "bn_bwd_apply")
+    with _Timed("bn_bwd_apply", lambda: (0.0, G * rows * Cch * 6.0)):
+        check(_L().mmdyn_bn_bwd_apply(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(sums2), _ptr(dU), _ptr(dgamma),
+                                      _ptr(dbeta), G, rows, Cch, unscale, _stream()), "bn_bwd_apply")
 
 
 def swish_dropout_fwd(raw, masks, h, B, Cch):
     n = len(masks)
-    check(_L().mmdyn_swish_dropout_fwd(_ptr(raw), _ptr_array(masks, n), _ptr(h), n, B, Cch, _stream()),
-          "swish_dropout_fwd")
+    with _Timed("swish_dropout_fwd", None):
+        check(_L().mmdyn_swish_dropout_fwd(_ptr(raw), _ptr_array(masks, n), _ptr(h), n, B, Cch, _stream()),
+              "swish_dropout_fwd")
 
 
 def swish_dropout_bwd(raw, masks, dH, dRaw, B, Cch):
     n = len(masks)
-    check(_L().mmdyn_swish_dropout_bwd(_ptr(raw), _ptr_array(masks, n), _ptr(dH), _ptr(dRaw), n, B, Cch,
-                                       _stream()), "swish_dropout_bwd")
+    with _Timed("swish_dropout_bwd", None):
+        check(_L().mmdyn_swish_dropout_bwd(_ptr(raw), _ptr_array(masks, n), _ptr(dH), _ptr(dRaw), n, B, Cch,
+                                           _stream()), "swish_dropout_bwd")
 
 
 def poe_fwd(mu_e, lv_e, use_prior, ld, eps, mu, lv, z, zh, zh2, kl_sum, B, D):
     n = len(mu_e)
-    check(_L().mmdyn_poe_fwd(_ptr_array(mu_e, 4), _ptr_array(lv_e, 4), n, int(use_prior), ld, _ptr(eps), _ptr(mu),
-                             _ptr(lv), _ptr(z), _ptr(zh), _ptr(zh2), _ptr(kl_sum), B, D, _stream()), "poe_fwd")
+    with _Timed("poe_fwd", None):
+        check(_L().mmdyn_poe_fwd(_ptr_array(mu_e, 4), _ptr_array(lv_e, 4), n, int(use_prior), ld, _ptr(eps), _ptr(mu),
+                                 _ptr(lv), _ptr(z), _ptr(zh), _ptr(zh2), _ptr(kl_sum), B, D, _stream()), "poe_fwd")
 
 
 def poe_bwd(mu_e, lv_e, use_prior, ld, eps, dzs, kl_coef, dmu_e, dlv_e, ld_out, accumulate, B, D,
             dmu_in=None, dlv_in=None):
     n = len(mu_e)
-    check(_L().mmdyn_poe_bwd(_ptr_array(mu_e, 4), _ptr_array(lv_e, 4), n, int(use_prior), ld, _ptr(eps),
-                             _ptr_array(dzs, 3), _ptr(dmu_in), _ptr(dlv_in), kl_coef, _ptr_array(dmu_e, 4),
-                             _ptr_array(dlv_e, 4), ld_out,
-                             int(accumulate), B, D, _stream()), "poe_bwd")
+    with _Timed("poe_bwd", None):
+        check(_L().mmdyn_poe_bwd(_ptr_array(mu_e, 4), _ptr_array(lv_e, 4), n, int(use_prior), ld, _ptr(eps),
+                                 _ptr_array(dzs, 3), _ptr(dmu_in), _ptr(dlv_in), kl_coef, _ptr_array(dmu_e, 4),
+                                 _ptr_array(dlv_e, 4), ld_out,
+                                 int(accumulate), B, D, _stream()), "poe_bwd")
 
 
 def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, HW):
-    check(_L().mmdyn_bce_logits(_ptr(logits), _ptr(target), _ptr(mask), _ptr(loss_sum), _ptr(dlogits), gscale, n,
-                                HW, _stream()), "bce_logits")
+    with _Timed("bce_logits", lambda: (0.0, n * HW * (3 * 8.0 + (16.0 if dlogits is not None else 0.0)))):
+        check(_L().mmdyn_bce_logits(_ptr(logits), _ptr(target), _ptr(mask), _ptr(loss_sum), _ptr(dlogits), gscale, n,
+                                    HW, _stream()), "bce_logits")
 
 
 def mse(recon, target, loss_sum, drecon, mult, gscale, n):
-    check(_L().mmdyn_mse(_ptr(recon), _ptr(target), _ptr(loss_sum), _ptr(drecon), mult, gscale, n, _stream()), "mse")
+    with _Timed("mse", None):
+        check(_L().mmdyn_mse(_ptr(recon), _ptr(target), _ptr(loss_sum), _ptr(drecon), mult, gscale, n, _stream()), "mse")
 
 
 def linear_f32_fwd(x, W, b, y, M, N, K, ldx, ldy, act):
-    check(_L().mmdyn_linear_f32_fwd(_ptr(x), _ptr(W), _ptr(b), _ptr(y), M, N, K, ldx, ldy, act, _stream()),
-          "linear_f32_fwd")
+    with _Timed("linear_f32_fwd", None):
+        check(_L().mmdyn_linear_f32_fwd(_ptr(x), _ptr(W), _ptr(b), _ptr(y), M, N, K, ldx, ldy, act, _stream()),
+              "linear_f32_fwd")
 
 
 def linear_f32_bwd(x, W, y, dy, dy_act, dx, dW, db, M, N, K, ldx, ldy, lddx, act, dx_accumulate, scale):
-    check(_L().mmdyn_linear_f32_bwd(_ptr(x), _ptr(W), _ptr(y), _ptr(dy), _ptr(dy_act), _ptr(dx), _ptr(dW), _ptr(db),
-                                    M, N, K, ldx, ldy, lddx, act, int(dx_accumulate), scale, _stream()),
-          "linear_f32_bwd")
+    with _Timed("linear_f32_bwd", None):
+        check(_L().mmdyn_linear_f32_bwd(_ptr(x), _ptr(W), _ptr(y), _ptr(dy), _ptr(dy_act), _ptr(dx), _ptr(dW), _ptr(db),
+                                        M, N, K, ldx, ldy, lddx, act, int(dx_accumulate), scale, _stream()),
+              "linear_f32_bwd")
 
 
 def colsum_f32(x, out, M, N, ld, scale):
-    check(_L().mmdyn_colsum_f32(_ptr(x), _ptr(out), M, N, ld, scale, _stream()), "colsum_f32")
+    with _Timed("colsum_f32", None):
+        check(_L().mmdyn_colsum_f32(_ptr(x), _ptr(out), M, N, ld, scale, _stream()), "colsum_f32")
 
 
 def colsum_f16(x, out, M, N, ld, scale):
-    check(_L().mmdyn_colsum_f16(_ptr(x), _ptr(out), M, N, ld, scale, _stream()), "colsum_f16")
+    with _Timed("colsum_f16", None):
+        check(_L().mmdyn_colsum_f16(_ptr(x), _ptr(out), M, N, ld, scale, _stream()), "colsum_f16")
 
 
 def pack_f16(src, idx, dst):
-    check(_L().mmdyn_pack_f16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "pack_f16")
+    with _Timed("pack_f16", lambda: (0.0, idx.numel() * 10.0)):
+        check(_L().mmdyn_pack_f16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "pack_f16")
 
 
 def gather_f32(src, idx, dst):
-    check(_L().mmdyn_gather_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_f32")
+    with _Timed("gather_f32", None):
+        check(_L().mmdyn_gather_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_f32")
 
 
 def unpack_add_f32(src, idx, dst):
-    check(_L().mmdyn_unpack_add_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "unpack_add_f32")
+    with _Timed("unpack_add_f32", lambda: (0.0, idx.numel() * 16.0)):
+        check(_L().mmdyn_unpack_add_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "unpack_add_f32")
 
 
 def f32_to_f16(src, dst, n, scale=1.0):
-    check(_L().mmdyn_f32_to_f16(_ptr(src), _ptr(dst), n, scale, _stream()), "f32_to_f16")
+    with _Timed("f32_to_f16", None):
+        check(_L().mmdyn_f32_to_f16(_ptr(src), _ptr(dst), n, scale, _stream()), "f32_to_f16")
 
 
 def scale_f32(x, n, s):
-    check(_L().mmdyn_scale_f32(_ptr(x), n, s, _stream()), "scale_f32")
+    with _Timed("scale_f32", None):
+        check(_L().mmdyn_scale_f32(_ptr(x), n, s, _stream()), "scale_f32")
 
 
 def logit_grad_pack(dl, out, scale, n, HW):
-    check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, HW, _stream()), "logit_grad_pack")
+    with _Timed("logit_grad_pack", None):
+        check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, HW, _stream()), "logit_grad_pack")
 
 
 def adam_flat(p, g, m, v, n, lr, b1, b2, eps, wd, step, gscale=1.0):
-    check(_L().mmdyn_adam_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, step, gscale, _stream()),
-          "adam_flat")
+    with _Timed("adam_flat", lambda: (0.0, n * 28.0)):
+        check(_L().mmdyn_adam_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, step, gscale, _stream()),
+              "adam_flat")
+
+
+def adam_flat_devstep(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, gscale=1.0):
+    with _Timed("adam_flat", lambda: (0.0, n * 28.0)):
+        check(_L().mmdyn_adam_flat_devstep(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, _ptr(step_dev),
+                                           gscale, _stream()), "adam_flat_devstep")
 
 
 def sgd_flat(p, g, buf, n, lr, momentum, wd, first_step, gscale=1.0):
-    check(_L().mmdyn_sgd_flat(_ptr(p), _ptr(g), _ptr(buf), n, lr, momentum, wd, int(first_step), gscale, _stream()),
-          "sgd_flat")
+    with _Timed("sgd_flat", None):
+        check(_L().mmdyn_sgd_flat(_ptr(p), _ptr(g), _ptr(buf), n, lr, momentum, wd, int(first_step), gscale, _stream()),
+              "sgd_flat")
 
 
 def fill_normal(out, n, seed, offset, ctr=None):
-    check(_L().mmdyn_fill_normal(_ptr(out), n, seed, offset, _ptr(ctr), _stream()), "fill_normal")
+    with _Timed("fill_normal", None):
+        check(_L().mmdyn_fill_normal(_ptr(out), n, seed, offset, _ptr(ctr), _stream()), "fill_normal")
 
 
 def fill_dropout_mask(out, n, p_drop, seed, offset, ctr=None):
-    check(_L().mmdyn_fill_dropout_mask(_ptr(out), n, p_drop, seed, offset, _ptr(ctr), _stream()), "fill_dropout_mask")
+    with _Timed("fill_dropout_mask", None):
+        check(_L().mmdyn_fill_dropout_mask(_ptr(out), n, p_drop, seed, offset, _ptr(ctr), _stream()), "fill_dropout_mask")
 
 
 def rng_advance(ctr, inc):
-    check(_L().mmdyn_rng_advance(_ptr(ctr), inc, _stream()), "rng_advance")
+    with _Timed("rng_advance", None):
+        check(_L().mmdyn_rng_advance(_ptr(ctr), inc, _stream()), "rng_advance")

@@ -23,6 +23,8 @@ class _FlatOptimizer(torch.optim.Optimizer):
         if self._bufs is None or self._bufs[0].device != arena.flat.device or self._bufs[0].numel() != arena.total:
             self._bufs = tuple(torch.zeros_like(arena.flat) for _ in range(self._n_bufs))
             self._step = 0
+            # the step count also lives on the device so that a captured CUDA graph advances it
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=arena.flat.device)
         return arena
 
     def zero_grad(self, set_to_none=True):
@@ -46,8 +48,9 @@ class FusedAdam(_FlatOptimizer):
         g = self.param_groups[0]
         self._step += 1
         m, v = self._bufs
-        ops.adam_flat(arena.flat, arena.grad, m, v, arena.total, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
-                      g["weight_decay"], self._step, self.grad_prescale)
+        ops.rng_advance(self._step_dev, 1)
+        ops.adam_flat_devstep(arena.flat, arena.grad, m, v, arena.total, g["lr"], g["betas"][0], g["betas"][1],
+                              g["eps"], g["weight_decay"], self._step_dev, self.grad_prescale)
         arena.bump()
 
 
@@ -64,6 +67,7 @@ class FusedSGD(_FlatOptimizer):
         arena.attach_grads()
         g = self.param_groups[0]
         self._step += 1
+        # the momentum buffer starts at zero, so momentum*buf + g == g on step 1 (torch's first-step rule)
         ops.sgd_flat(arena.flat, arena.grad, self._bufs[0], arena.total, g["lr"], g["momentum"], g["weight_decay"],
-                     self._step == 1, self.grad_prescale)
+                     False, self.grad_prescale)
         arena.bump()

@@ -163,7 +163,7 @@ def conv_s2_plan(name, w_off, Cin, Cout, H):
             ci_, co_ = np.meshgrid(np.arange(Cin), np.arange(Cout), indexing="ij")
             idx_dg[p * Cin:(p + 1) * Cin, t_ * Cout:(t_ + 1) * Cout] = widx(co_, ci_, kh, kw)
     wg = WgradGeom(P=Ho * Ho, OXv=Ho, IH=H, IW=H, Cg=Cin, s_in=2, tap_dy=dy, tap_dx=dx, Cn=Cout)
-    return LayerPlan(name, "conv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd)
+    return LayerPlan(name, "conv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd, extra={"macs": Ho * Ho * Cout * Cin * 16})
 
 
 def conv_k4s1p0_plan(name, w_off, Cin, Cout, H):
@@ -185,7 +185,7 @@ def conv_k4s1p0_plan(name, w_off, Cin, Cout, H):
     ci_, t_, co_ = np.meshgrid(np.arange(Cin), np.arange(16), np.arange(Cout), indexing="ij")
     idx_dg = widx(co_, ci_, t_ // 4, t_ % 4).reshape(Cin, 16 * Cout).astype(np.int32)
     wg = WgradGeom(P=Ho * Ho, OXv=Ho, IH=H, IW=H, Cg=Cin, s_in=1, tap_dy=dy, tap_dx=dx, Cn=Cout)
-    return LayerPlan(name, "conv_s1", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd)
+    return LayerPlan(name, "conv_s1", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd, extra={"macs": Ho * Ho * Cout * Cin * 16})
 
 
 def deconv_k4s1p0_plan(name, w_off, Cin, Cout, H):
@@ -208,7 +208,7 @@ def deconv_k4s1p0_plan(name, w_off, Cin, Cout, H):
     idx_dg = widx(ci_, co_, t_ // 4, t_ % 4).reshape(Cin, 16 * Cout).astype(np.int32)
     # wgrad: natural operand = layer input (rows = 5x5 input pixels), gathered = dOut
     wg = WgradGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cg=Cout, s_in=1, tap_dy=dy, tap_dx=dx, Cn=Cin)
-    return LayerPlan(name, "deconv_s1", fwd, idx_fwd, dg, idx_dg, wg, idx_dg)
+    return LayerPlan(name, "deconv_s1", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
 
 
 def deconv_s2_plan(name, w_off, Cin, Cout, H):
@@ -232,7 +232,7 @@ def deconv_s2_plan(name, w_off, Cin, Cout, H):
     ci_, t_, co_ = np.meshgrid(np.arange(Cin), np.arange(16), np.arange(Cout), indexing="ij")
     idx_dg = widx(ci_, co_, t_ // 4, t_ % 4).reshape(Cin, 16 * Cout).astype(np.int32)
     wg = WgradGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cg=Cout, s_in=2, tap_dy=dy, tap_dx=dx, Cn=Cin)
-    return LayerPlan(name, "deconv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_dg)
+    return LayerPlan(name, "deconv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
 
 
 def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
@@ -269,7 +269,7 @@ def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
         for co in range(Cout):
             idx_dg[:, t_ * CP + co] = widx(np.arange(Cin), co, t_ // 4, t_ % 4)
     wg = WgradGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cg=CP, s_in=2, tap_dy=dy, tap_dx=dx, Cn=Cin)
-    return LayerPlan(name, "deconv_out", fwd, idx_fwd, dg, idx_dg, wg, idx_dg)
+    return LayerPlan(name, "deconv_out", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
 
 
 def linear_plan(name, w_offs, b_offs, K, Ns, k_perm=None, n_perm=None):
@@ -290,7 +290,7 @@ def linear_plan(name, w_offs, b_offs, K, Ns, k_perm=None, n_perm=None):
                   s_out=1, off_y=[0], off_x=[0], ldc=K)
     idx_dg = np.ascontiguousarray(idx_fwd.T)                   # [K][N]
     wg = WgradGeom(P=1, OXv=1, IH=1, IW=1, Cg=K, s_in=1, tap_dy=[0], tap_dx=[0], Cn=N)
-    return LayerPlan(name, "linear", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd, bias_idx=bias_idx)
+    return LayerPlan(name, "linear", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd, bias_idx=bias_idx, extra={"macs": K * N})
 
 
 def conv1_plan(name, w_off):
@@ -298,7 +298,7 @@ def conv1_plan(name, w_off):
     k = ci*16 + kh*4 + kw (the torch layout), 48 used."""
     idx = np.full((32, 64), -1, np.int32)
     idx[:, :48] = w_off + np.arange(32)[:, None] * 48 + np.arange(48)[None, :]
-    return LayerPlan(name, "conv1", None, idx, None, None, None, None)
+    return LayerPlan(name, "conv1", None, idx, None, None, None, None, extra={"macs": 1024 * 32 * 48})
 
 
 def nhwc_perm(C, H, W):
