@@ -171,9 +171,16 @@ def run_b200(args):
     host_batches = [synth_batch(B, 10 + 3 * rank + i, pin=True) for i in range(3)]
 
     arena = engine.get_arena(model, dev)
+    from mmdyn_b200 import parallel
+    # eager path: bucketed all-reduce launched from the backward as sub-networks finish (overlap);
+    # graphed path: one all-reduce of the flat arena between the backward graph and the Adam graph
+    bucketed = parallel.attach(eng, opt, arena, overlap=True) if (world > 1 and args.no_graph) else None
 
     def sync_grads():
-        if world > 1:
+        if bucketed is not None:
+            bucketed.finish()
+            bucketed.begin()
+        elif world > 1:
             dist.all_reduce(arena.grad)
 
     # one eager step: builds workspaces, counts this library's launches per step

@@ -1,0 +1,97 @@
+"""Data parallelism for the fused step: one process per GPU, gradients summed with NCCL all-reduce
+over NVLink 5 / NVSwitch (torch.distributed is the plumbing; the reference has no distributed code
+at all — SURVEY.md §5 — so the semantics are defined here and in DESIGN.md §multi-GPU):
+
+  * every rank holds an identical replica and a disjoint shard of the step batch (by rows; by whole
+    sequences for dyn_modeling so the roll/fix-up of DynModeling.parse_input stays local);
+  * BatchNorm statistics are per rank (local batch), like torch DDP without SyncBN;
+  * the flat gradient arena is cut into contiguous buckets, one per sub-network (decoders first:
+    their gradients are final first in the fused backward), each all-reduced (SUM) on a side stream as
+    soon as the backward reports it ready, overlapping the remaining encoder backward;
+  * the fused Adam multiplies by 1/world_size (`grad_prescale`) — sum then scale = average.
+
+Parity definition: N ranks == the oracle run independently on each shard with identical weights,
+gradients averaged, one Adam step.
+"""
+import torch
+import torch.distributed as dist
+
+
+def bucket_ranges(names, offsets, numels, total):
+    """Contiguous [start, end) ranges of the flat arena per top-level sub-network, in arena order.
+    -> dict prefix -> (start, end).  Padding between parameters stays inside its bucket."""
+    order, first = [], {}
+    for n in names:
+        p = n.split(".")[0]
+        if p not in first:
+            first[p] = offsets[n]
+            order.append(p)
+    out = {}
+    for i, p in enumerate(order):
+        end = first[order[i + 1]] if i + 1 < len(order) else total
+        out[p] = (first[p], end)
+    return out
+
+
+def shard_rows(n_rows, world, rank, seq_length=1):
+    """Row range of this rank: whole sequences only, remainder spread over the first ranks."""
+    assert n_rows % seq_length == 0
+    n_seq = n_rows // seq_length
+    base, rem = divmod(n_seq, world)
+    start = rank * base + min(rank, rem)
+    stop = start + base + (1 if rank < rem else 0)
+    return start * seq_length, stop * seq_length
+
+
+class GradSync:
+    """Bucketed, overlapped all-reduce of a flat gradient tensor.  Works on any device / backend
+    (the CPU + gloo combination is what the host-logic tests use)."""
+
+    def __init__(self, flat_grad, ranges, group=None, overlap=True):
+        self.flat, self.ranges, self.group = flat_grad, dict(ranges), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.overlap = overlap and flat_grad.is_cuda
+        self.stream = torch.cuda.Stream() if self.overlap else None
+        self.pending = []
+        self.done = set()
+
+    def begin(self):
+        self.pending, self.done = [], set()
+
+    def ready(self, prefixes):
+        """Gradients of these sub-networks are final: launch their all-reduce."""
+        if self.world == 1:
+            return
+        for p in prefixes:
+            if p in self.done or p not in self.ranges:
+                continue
+            self.done.add(p)
+            a, b = self.ranges[p]
+            chunk = self.flat[a:b]
+            if self.overlap:
+                self.stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    dist.all_reduce(chunk, group=self.group)
+            else:
+                self.pending.append(dist.all_reduce(chunk, group=self.group, async_op=True))
+
+    def finish(self):
+        """Reduce whatever was not reported and make the result visible to the compute stream."""
+        if self.world == 1:
+            return
+        self.ready([p for p in self.ranges if p not in self.done])
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+
+def attach(step_engine, optimizer, arena, group=None, overlap=True):
+    """Wire a StepEngine + fused optimizer for data parallel training; returns the GradSync.
+    Usage per step: sync.begin(); loss.backward() (fires bucket hooks); sync.finish(); optimizer.step()."""
+    ranges = bucket_ranges(arena.names, arena.offset, arena.numel, arena.total)
+    sync = GradSync(arena.grad, ranges, group, overlap)
+    step_engine.bucket_hook = sync.ready
+    optimizer.grad_prescale = 1.0 / sync.world
+    return sync

@@ -7,8 +7,15 @@ import torch.nn.functional as F
 from mmdyn_b200 import plan
 from tests import emul
 
-torch.manual_seed(0)
-torch.set_default_dtype(torch.float64)
+
+
+@pytest.fixture(autouse=True)
+def _fp64_default():
+    torch.manual_seed(0)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
 
 
 def nhwc(x):
