@@ -55,75 +55,71 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// igemm: forward / dgrad form
+// igemm: forward / dgrad form — persistent, warp-specialised
+//   warps 0-3  A producers (im2col gather, cp.async)      warp 4  MMA issuer (+ TMEM owner)
+//   warp  5    B producer (TMA)                           warps 6-9 epilogue (TMEM -> global)
+// Every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and its phases run
+// across tile boundaries, and the accumulator is double-buffered in TMEM, so the epilogue of tile
+// i overlaps the loads and MMAs of tile i+1 and the per-CTA set-up (barriers, TMEM allocation)
+// is paid once instead of once per 128 output rows (these layers have K as small as 128).
 // ---------------------------------------------------------------------------------------------
+constexpr int IGEMM_THREADS = 320;
+constexpr int EPI_WARP0 = 6;
+
+struct TileCoord {
+  int row0, tile_pix, n_tile, phase, split;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const mmdyn_igemm_desc& d, int tile, int m_tiles, int n_tiles) {
+  TileCoord t;
+  const int m = tile % m_tiles;
+  int rest = tile / m_tiles;
+  t.n_tile = rest % n_tiles;
+  rest /= n_tiles;
+  t.phase = rest / d.ksplit;
+  t.split = rest - t.phase * d.ksplit;
+  if (d.row_mode == 0) {
+    t.row0 = m * TILE_M;
+    t.tile_pix = 0;
+  } else {
+    const int img_blocks = (d.n_img + TILE_M - 1) / TILE_M;
+    t.tile_pix = m / img_blocks;
+    t.row0 = (m - t.tile_pix * img_blocks) * TILE_M;
+  }
+  return t;
+}
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(CTA_THREADS)
-igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmW) {
+__global__ void __launch_bounds__(IGEMM_THREADS)
+igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmW, int m_tiles,
+             int n_tiles, int total_tiles) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ RowInfo rows[TILE_M];
+  __shared__ RowInfo rows[2][TILE_M];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.y;
-  const int phase = blockIdx.z / d.ksplit;
-  const int split = blockIdx.z - phase * d.ksplit;
 
-  // ---- tile geometry -----------------------------------------------------------------------
-  int row0, tile_pix = 0;
-  if (d.row_mode == 0) {
-    row0 = blockIdx.x * TILE_M;
-  } else {
-    const int img_blocks = (d.n_img + TILE_M - 1) / TILE_M;
-    tile_pix = blockIdx.x / img_blocks;
-    row0 = (blockIdx.x - tile_pix * img_blocks) * TILE_M;
-  }
-  if (threadIdx.x < TILE_M) {
-    const int r = threadIdx.x;
-    int img, p;
-    bool valid;
-    if (d.row_mode == 0) {
-      const int m = row0 + r;
-      valid = m < d.n_img * d.P;
-      img = m / d.P;
-      p = m - img * d.P;
-    } else {
-      img = row0 + r;
-      valid = img < d.n_img;
-      p = tile_pix;
-    }
-    const int yv = p / d.OXv, xv = p - yv * d.OXv;
-    RowInfo ri;
-    ri.iy0 = valid ? yv * d.s_in : -(1 << 20);
-    ri.ix0 = xv * d.s_in;
-    ri.a_off = valid ? ((img * d.IH + yv * d.s_in) * d.IW + xv * d.s_in) * d.a_pix_stride : 0;
-    if (d.out_mode == 3) {
-      ri.out_off = valid ? ((img * 3 * d.OH) + 2 * yv) * d.OW + 2 * xv : -1;
-    } else {
-      const int oy = yv * d.s_out + d.off_y[phase], ox = xv * d.s_out + d.off_x[phase];
-      ri.out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
-    }
-    rows[r] = ri;
-  }
-
-  // ---- barriers + TMEM ---------------------------------------------------------------------
-  if (threadIdx.x == NUM_PRODUCER_THREADS) {
+  if (threadIdx.x == 4 * 32) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), NUM_PRODUCER_THREADS + 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&accum_bar), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), NUM_PRODUCER_THREADS);
+    }
     mbar_fence_init();
     tma_prefetch_desc(&tmW);
   }
   if (warp == 4) {
-    tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -131,155 +127,224 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  // ---- k-block range of this CTA -----------------------------------------------------------
   const int kb_total = (d.ntaps * d.Cin) >> 6;
   const int kb_per = (kb_total + d.ksplit - 1) / d.ksplit;
-  const int kb_begin = split * kb_per;
-  const int kb_end = min(kb_total, kb_begin + kb_per);
-  // row_mode 1: all rows of the tile share the virtual pixel, so out-of-image taps are skipped
-  const int tyv = tile_pix / d.OXv, txv = tile_pix - tyv * d.OXv;
-  auto kb_live = [&](int kb) -> bool {
+  // row_mode 1: all rows of a tile share the virtual pixel, so out-of-image taps are skipped
+  auto kb_live = [&](const TileCoord& t, int kb) -> bool {
     if (d.row_mode == 0) return true;
+    const int tyv = t.tile_pix / d.OXv, txv = t.tile_pix - tyv * d.OXv;
     const int tap = (kb << 6) / d.Cin;
-    const int iy = tyv * d.s_in + d.tap_dy[phase][tap];
-    const int ix = txv * d.s_in + d.tap_dx[phase][tap];
+    const int iy = tyv * d.s_in + d.tap_dy[t.phase][tap];
+    const int ix = txv * d.s_in + d.tap_dx[t.phase][tap];
     return (unsigned)iy < (unsigned)d.IH && (unsigned)ix < (unsigned)d.IW;
   };
 
-  int n_issued = 0;
   if (warp < 4) {
     // ======================= A producers: im2col gather with cp.async =======================
     const __half* A = reinterpret_cast<const __half*>(d.A);
     const int j = threadIdx.x & 7;      // 16-byte chunk inside the 128-byte k-block row
     const int rsub = threadIdx.x >> 3;  // rows rsub + 16*i
     const uint32_t sw = static_cast<uint32_t>((j ^ (rsub & 7)) << 4);
-    int it = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      if (!kb_live(kb)) continue;
-      const int s = it % C::STAGES;
-      mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
-      const int k = (kb << 6) + (j << 3);
-      const int tap = k / d.Cin;
-      const int c = k - tap * d.Cin;
-      const int dy = d.tap_dy[phase][tap], dx = d.tap_dx[phase][tap];
-      const int tap_off = (dy * d.IW + dx) * d.a_pix_stride + c;
-      const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+    int it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord t = decode_tile(d, tile, m_tiles, n_tiles);
+      {
+        const int r = threadIdx.x;
+        int img, p;
+        bool valid;
+        if (d.row_mode == 0) {
+          const int m = t.row0 + r;
+          valid = m < d.n_img * d.P;
+          img = m / d.P;
+          p = m - img * d.P;
+        } else {
+          img = t.row0 + r;
+          valid = img < d.n_img;
+          p = t.tile_pix;
+        }
+        const int yv = p / d.OXv, xv = p - yv * d.OXv;
+        RowInfo ri;
+        ri.iy0 = valid ? yv * d.s_in : -(1 << 20);
+        ri.ix0 = xv * d.s_in;
+        ri.a_off = valid ? ((img * d.IH + yv * d.s_in) * d.IW + xv * d.s_in) * d.a_pix_stride : 0;
+        ri.out_off = 0;
+        rows[tl & 1][r] = ri;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const RowInfo* rw = rows[tl & 1];
+      const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        if (!kb_live(t, kb)) continue;
+        const int s = it % C::STAGES;
+        mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+        const int k = (kb << 6) + (j << 3);
+        const int tap = k / d.Cin;
+        const int c = k - tap * d.Cin;
+        const int dy = d.tap_dy[t.phase][tap], dx = d.tap_dx[t.phase][tap];
+        const int tap_off = (dy * d.IW + dx) * d.a_pix_stride + c;
+        const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = rsub + 16 * i;
-        const RowInfo ri = rows[r];
-        const bool v = (unsigned)(ri.iy0 + dy) < (unsigned)d.IH &&
-                       (unsigned)(ri.ix0 + dx) < (unsigned)d.IW;
-        const __half* src = v ? (A + (ri.a_off + tap_off)) : A;
-        cp_async16(a_stage + r * 128 + sw, src, v);
+        for (int i = 0; i < 8; ++i) {
+          const int r = rsub + 16 * i;
+          const RowInfo ri = rw[r];
+          const bool v = (unsigned)(ri.iy0 + dy) < (unsigned)d.IH && (unsigned)(ri.ix0 + dx) < (unsigned)d.IW;
+          const __half* src = v ? (A + (ri.a_off + tap_off)) : A;
+          cp_async16(a_stage + r * 128 + sw, src, v);
+        }
+        cp_async_commit();
+        if (it >= C::LAG) {
+          // the generic->async proxy fence is issued once by the consumer after it acquires the
+          // stage (see the MMA issuer): a per-thread fence here drains every in-flight cp.async
+          cp_async_wait<C::LAG>();
+          mbar_arrive(smem_u32(&full_bar[(it - C::LAG) % C::STAGES]));
+        }
+        ++it;
       }
-      cp_async_commit();
-      if (it >= C::LAG) {
-        cp_async_wait<C::LAG>();
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&full_bar[(it - C::LAG) % C::STAGES]));
-      }
-      ++it;
     }
     cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int q = (it > C::LAG ? it - C::LAG : 0); q < it; ++q)
-      mbar_arrive(smem_u32(&full_bar[q % C::STAGES]));
-    n_issued = it;
+    for (int q = (it > C::LAG ? it - C::LAG : 0); q < it; ++q) mbar_arrive(smem_u32(&full_bar[q % C::STAGES]));
   } else if (warp == 5) {
     // ======================= B producer: TMA loads of the packed weights =====================
     if (lane == 0) {
       int it = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        if (!kb_live(kb)) continue;
-        const int s = it % C::STAGES;
-        mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
-        const uint32_t bar = smem_u32(&full_bar[s]);
-        mbar_arrive_expect_tx(bar, C::B_STAGE_BYTES);
-        tma_load_2d(smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES, &tmW, bar, kb << 6,
-                    phase * d.N + n_tile * BLOCK_N);
-        ++it;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(d, tile, m_tiles, n_tiles);
+        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!kb_live(t, kb)) continue;
+          const int s = it % C::STAGES;
+          mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_arrive_expect_tx(bar, C::B_STAGE_BYTES);
+          tma_load_2d(smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES, &tmW, bar, kb << 6,
+                      t.phase * d.N + t.n_tile * BLOCK_N);
+          ++it;
+        }
       }
     }
-  } else {
+  } else if (warp == 4) {
     // ======================= MMA issuer ======================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 0, 0, 0, 0);
-      int it = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        if (!kb_live(kb)) continue;
-        const int s = it % C::STAGES;
-        mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord t = decode_tile(d, tile, m_tiles, n_tiles);
+        const int acc = tl & 1;
+        mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
-        const uint64_t adesc = make_smem_desc(a_base, 16, 1024, LAYOUT_SW128);
-        const uint64_t bdesc = make_smem_desc(a_base + A_STAGE_BYTES, 16, 1024, LAYOUT_SW128);
+        const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS;
+        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+        int first = 1;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!kb_live(t, kb)) continue;
+          const int s = it % C::STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+          fence_proxy_async_smem();  // producers' cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
+          tc_fence_after();
+          const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(a_base, 16, 1024, LAYOUT_SW128);
+          const uint64_t bdesc = make_smem_desc(a_base + A_STAGE_BYTES, 16, 1024, LAYOUT_SW128);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // 4 x (K = 16) per 64-wide k-block: +32 B per step
-          umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc, (it | kk) != 0);
-        umma_commit(smem_u32(&empty_bar[s]));
-        ++it;
+          for (int kk = 0; kk < 4; ++kk)  // 4 x (K = 16) per 64-wide k-block: +32 B per step
+            umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+          first = 0;
+          umma_commit(smem_u32(&empty_bar[s]));
+          ++it;
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
       }
-      umma_commit(smem_u32(&accum_bar));
     }
-  }
-
-  // ======================= epilogue: TMEM -> registers -> global ============================
-  if (warp < 4) {
-    mbar_wait(smem_u32(&accum_bar), 0);
-    tc_fence_after();
-    const int r = threadIdx.x;
-    const RowInfo ri = rows[r];
-    const int n_base = n_tile * BLOCK_N;
-    const bool add_bias = d.bias != nullptr && split == 0;
+  } else {
+    // ======================= epilogue: TMEM -> registers -> global ============================
+    const int q4 = warp & 3;               // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;          // tile row owned by this thread
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord t = decode_tile(d, tile, m_tiles, n_tiles);
+      int out_off;
+      {
+        int img, p;
+        bool valid;
+        if (d.row_mode == 0) {
+          const int m = t.row0 + r;
+          valid = m < d.n_img * d.P;
+          img = m / d.P;
+          p = m - img * d.P;
+        } else {
+          img = t.row0 + r;
+          valid = img < d.n_img;
+          p = t.tile_pix;
+        }
+        const int yv = p / d.OXv, xv = p - yv * d.OXv;
+        if (d.out_mode == 3) {
+          out_off = valid ? ((img * 3 * d.OH) + 2 * yv) * d.OW + 2 * xv : -1;
+        } else {
+          const int oy = yv * d.s_out + d.off_y[t.phase], ox = xv * d.s_out + d.off_x[t.phase];
+          out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
+        }
+      }
+      int n_live = 0;
+      {
+        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+        if (d.row_mode == 0) n_live = kb_end - kb_begin;
+        else
+          for (int kb = kb_begin; kb < kb_end; ++kb) n_live += kb_live(t, kb) ? 1 : 0;
+      }
+      const int acc = tl & 1;
+      mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS + (static_cast<uint32_t>(q4 * 32) << 16);
+      const int n_base = t.n_tile * BLOCK_N;
+      const bool add_bias = d.bias != nullptr && t.split == 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (ri.out_off < 0) continue;
-      float f[16];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_d + c0, v);
+        tmem_ld_wait();
+        if (out_off < 0) continue;
+        float f[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) f[q] = n_issued > 0 ? __uint_as_float(v[q]) : 0.0f;
-      if (add_bias) {
+        for (int q = 0; q < 16; ++q) f[q] = n_live > 0 ? __uint_as_float(v[q]) : 0.0f;
+        if (add_bias) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
+          for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
+        }
+        if (d.out_mode == 0) {
+          __half* o = reinterpret_cast<__half*>(d.out) + out_off + n_base + c0;
+          uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
+                                pack_h2(f[14], f[15]));
+          reinterpret_cast<uint4*>(o)[0] = u0;
+          reinterpret_cast<uint4*>(o)[1] = u1;
+        } else if (d.out_mode == 1) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + out_off + n_base + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else if (d.out_mode == 2) {
+          float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
+        } else {
+          // merged 2x2 sub-pixel phases -> fp32 NCHW planes; n = (ph*2 + pw)*3 + c
+          float* o = reinterpret_cast<float*>(d.out) + out_off;
+          const int plane = d.OH * d.OW;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph)
+              *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
+                  make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
+        }
       }
-      if (d.out_mode == 0) {
-        __half* o = reinterpret_cast<__half*>(d.out) + ri.out_off + n_base + c0;
-        uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]),
-                              pack_h2(f[6], f[7]));
-        uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
-                              pack_h2(f[14], f[15]));
-        reinterpret_cast<uint4*>(o)[0] = u0;
-        reinterpret_cast<uint4*>(o)[1] = u1;
-      } else if (d.out_mode == 1) {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + ri.out_off +
-                                              n_base + c0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-      } else if (d.out_mode == 2) {
-        float* o = reinterpret_cast<float*>(d.out) + ri.out_off + n_base + c0;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
-      } else {
-        // merged 2x2 sub-pixel phases -> fp32 NCHW planes; n = (ph*2 + pw)*3 + c
-        float* o = reinterpret_cast<float*>(d.out) + ri.out_off;
-        const int plane = d.OH * d.OW;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int ph = 0; ph < 2; ++ph)
-            *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
-                make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
-      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[acc]));  // accumulator stage free for tile tl + 2
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
   }
 }
 
@@ -616,9 +681,16 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int g_sm_count = 148;
+int g_igemm_occ[5] = {1, 1, 1, 1, 1};  // resident CTAs per SM of igemm_kernel<16,32,64,128,256>
+
 template <int BLOCK_N>
-int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, dim3 grid, cudaStream_t st) {
-  igemm_kernel<BLOCK_N><<<grid, CTA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tm);
+int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, int m_tiles, int n_tiles, int total_tiles,
+                 int occ, cudaStream_t st) {
+  int grid = g_sm_count * occ;
+  if (grid > total_tiles) grid = total_tiles;
+  igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tm, m_tiles, n_tiles,
+                                                                                 total_tiles);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -648,6 +720,22 @@ int igemm_init() {
   SET_SMEM(wgrad_kernel<128>, Cfg<128>::SMEM_BYTES);
   SET_SMEM(wgrad_kernel<256>, Cfg<256>::SMEM_BYTES);
 #undef SET_SMEM
+  int dev = 0;
+  MMDYN_CHECK_CUDA(cudaGetDevice(&dev));
+  MMDYN_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+#define OCC(I, K, BYTES)                                                                                \
+  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_igemm_occ[I], K, IGEMM_THREADS, BYTES)); \
+  if (g_igemm_occ[I] < 1) g_igemm_occ[I] = 1
+  OCC(0, igemm_kernel<16>, Cfg<16>::SMEM_BYTES);
+  OCC(1, igemm_kernel<32>, Cfg<32>::SMEM_BYTES);
+  OCC(2, igemm_kernel<64>, Cfg<64>::SMEM_BYTES);
+  OCC(3, igemm_kernel<128>, Cfg<128>::SMEM_BYTES);
+  OCC(4, igemm_kernel<256>, Cfg<256>::SMEM_BYTES);
+#undef OCC
+  // TMEM: 512 columns per SM, two accumulator stages per CTA
+  const int cols[5] = {64, 64, 128, 256, 512};
+  for (int i = 0; i < 5; ++i)
+    if (g_igemm_occ[i] * cols[i] > 512) g_igemm_occ[i] = 512 / cols[i];
   return MMDYN_OK;
 }
 
@@ -700,20 +788,22 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     set_last_error("igemm: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(cr));
     return MMDYN_ERR_CUDA;
   }
-  dim3 grid;
+  long long m_tiles_ll;
   if (d->row_mode == 0)
-    grid.x = static_cast<unsigned>((rows + TILE_M - 1) / TILE_M);
+    m_tiles_ll = (rows + TILE_M - 1) / TILE_M;
   else
-    grid.x = static_cast<unsigned>(d->P) * ((d->n_img + TILE_M - 1) / TILE_M);
-  grid.y = d->N / d->block_n;
-  grid.z = d->n_phases * d->ksplit;
+    m_tiles_ll = static_cast<long long>(d->P) * ((d->n_img + TILE_M - 1) / TILE_M);
+  const int n_tiles = d->N / d->block_n;
+  const long long total_ll = m_tiles_ll * n_tiles * d->n_phases * d->ksplit;
+  MMDYN_REQUIRE(total_ll < (1LL << 31), "igemm: too many tiles");
+  const int m_tiles = static_cast<int>(m_tiles_ll), total = static_cast<int>(total_ll);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d->block_n) {
-    case 16: return launch_igemm<16>(d, tm, grid, st);
-    case 32: return launch_igemm<32>(d, tm, grid, st);
-    case 64: return launch_igemm<64>(d, tm, grid, st);
-    case 128: return launch_igemm<128>(d, tm, grid, st);
-    default: return launch_igemm<256>(d, tm, grid, st);
+    case 16: return launch_igemm<16>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[0], st);
+    case 32: return launch_igemm<32>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[1], st);
+    case 64: return launch_igemm<64>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[2], st);
+    case 128: return launch_igemm<128>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[3], st);
+    default: return launch_igemm<256>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[4], st);
   }
 }
 
