@@ -21,6 +21,7 @@
 #include "../../include/mmdyn_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace mmdyn {
 
@@ -343,6 +344,277 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// igemm, TMA-fed: the activation operand is fetched by the TMA unit as well — one 4-D tiled box
+// (channels, x, y, image) per filter tap, element strides for stride-2 gathers, hardware zero
+// fill for the padding halo and for partial tiles — so no LSU instruction touches the operands.
+//   warp 0  TMA producer (A boxes + weight box per 64-wide k-block, one mbarrier expect_tx)
+//   warp 1  MMA issuer (tcgen05.mma, accumulators double-buffered in TMEM)
+//   warps 2-5 epilogue (tcgen05.ld -> registers -> global)
+// A tile is 128 GEMM rows = a box of bw x bh virtual pixels x bn images (bw*bh*bn = 128), or, for
+// the 5x5 / single-pixel layers, one virtual pixel x 128 images ("pixel-major").
+// A_MODE: 0 = Cin % 64 == 0 (one 128B-swizzled box per k-block), 1 = Cin == 32 (two 64B-swizzled
+// boxes = two taps), 2 = Cin == 8 (eight un-swizzled 16-byte boxes = eight taps).
+// ---------------------------------------------------------------------------------------------
+constexpr int TMA_THREADS = 192;
+
+struct TileGeom {
+  int lbw, lbh;        // log2 of the box width / height in virtual pixels (image-box mode)
+  int bn;              // images per tile
+  int pixel_major;     // 1: tile = one virtual pixel x 128 images
+  int tiles_y;         // image-box mode: OYv / bh
+  int img_blocks;      // ceil(n_img / bn)
+  int m_tiles, n_tiles, total_tiles;
+};
+
+struct TileCoord2 {
+  int img0, y0, x0, n_tile, phase, split;
+};
+
+__device__ __forceinline__ TileCoord2 decode_tile2(const mmdyn_igemm_desc& d, const TileGeom& g, int tile) {
+  TileCoord2 t;
+  const int m = tile % g.m_tiles;
+  int rest = tile / g.m_tiles;
+  t.n_tile = rest % g.n_tiles;
+  rest /= g.n_tiles;
+  t.phase = rest / d.ksplit;
+  t.split = rest - t.phase * d.ksplit;
+  if (g.pixel_major) {
+    const int pix = m / g.img_blocks;
+    t.img0 = (m - pix * g.img_blocks) * TILE_M;
+    t.y0 = pix / d.OXv;
+    t.x0 = pix - t.y0 * d.OXv;
+  } else {
+    const int ib = m / g.tiles_y;
+    t.img0 = ib * g.bn;
+    t.y0 = (m - ib * g.tiles_y) << g.lbh;
+    t.x0 = 0;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int BLOCK_N, int A_MODE>
+__global__ void __launch_bounds__(TMA_THREADS)
+igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmW, const TileGeom g) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 128);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int kb_total = (d.ntaps * d.Cin) >> 6;
+  const int kb_per = (kb_total + d.ksplit - 1) / d.ksplit;
+  // pixel-major tiles share the virtual pixel: a k-block whose tap(s) fall outside the image is skipped
+  auto kb_live = [&](const TileCoord2& t, int kb) -> bool {
+    if (!g.pixel_major || A_MODE != 0) return true;
+    const int tap = (kb << 6) / d.Cin;
+    const int iy = t.y0 * d.s_in + d.tap_dy[t.phase][tap];
+    const int ix = t.x0 * d.s_in + d.tap_dx[t.phase][tap];
+    return (unsigned)iy < (unsigned)d.IH && (unsigned)ix < (unsigned)d.IW;
+  };
+
+  if (warp == 0) {
+    // ======================= TMA producer =====================================================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord2 t = decode_tile2(d, g, tile);
+        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+        const int wx = t.x0 * d.s_in, wy = t.y0 * d.s_in;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!kb_live(t, kb)) continue;
+          const int s = it % C::STAGES;
+          mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+          mbar_arrive_expect_tx(bar, A_STAGE_BYTES + C::B_STAGE_BYTES);
+          if (A_MODE == 0) {
+            const int k = kb << 6;
+            const int tap = k / d.Cin, c0 = k - tap * d.Cin;
+            tma_load_4d(a_stage, &tmA, bar, c0, wx + d.tap_dx[t.phase][tap], wy + d.tap_dy[t.phase][tap], t.img0);
+          } else if (A_MODE == 1) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int tap = 2 * kb + b;
+              tma_load_4d(a_stage + b * 8192, &tmA, bar, 0, wx + d.tap_dx[t.phase][tap],
+                          wy + d.tap_dy[t.phase][tap], t.img0);
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              const int tap = 8 * kb + b;
+              tma_load_4d(a_stage + b * 2048, &tmA, bar, 0, wx + d.tap_dx[t.phase][tap],
+                          wy + d.tap_dy[t.phase][tap], t.img0);
+            }
+          }
+          tma_load_2d(a_stage + A_STAGE_BYTES, &tmW, bar, kb << 6, t.phase * d.N + t.n_tile * BLOCK_N);
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer ======================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 0, 0, 0, 0);
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord2 t = decode_tile2(d, g, tile);
+        const int acc = tl & 1;
+        mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS;
+        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+        int first = 1;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!kb_live(t, kb)) continue;
+          const int s = it % C::STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
+          const uint64_t bdesc = make_smem_desc(a_base + A_STAGE_BYTES, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16) per 64-wide k-block
+            uint64_t adesc;
+            if (A_MODE == 0) adesc = make_smem_desc(a_base + 32 * kk, 16, 1024, LAYOUT_SW128);
+            else if (A_MODE == 1) adesc = make_smem_desc(a_base + (kk >> 1) * 8192 + (kk & 1) * 32, 16, 512, LAYOUT_SW64);
+            else adesc = make_smem_desc(a_base + kk * 4096, 2048, 128, 0);
+            umma_f16(tmem_d, adesc, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+          }
+          first = 0;
+          umma_commit(smem_u32(&empty_bar[s]));
+          ++it;
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
+      }
+    }
+  } else {
+    // ======================= epilogue: TMEM -> registers -> global ============================
+    const int q4 = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;  // tile row owned by this thread
+    int x_l, y_l, n_l;
+    if (g.pixel_major) {
+      x_l = 0; y_l = 0; n_l = r;
+    } else {
+      x_l = r & ((1 << g.lbw) - 1);
+      y_l = (r >> g.lbw) & ((1 << g.lbh) - 1);
+      n_l = r >> (g.lbw + g.lbh);
+    }
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord2 t = decode_tile2(d, g, tile);
+      const int img = t.img0 + n_l, yv = t.y0 + y_l, xv = t.x0 + x_l;
+      const bool valid = img < d.n_img;
+      int out_off;
+      if (d.out_mode == 3) {
+        out_off = valid ? ((img * 3 * d.OH) + 2 * yv) * d.OW + 2 * xv : -1;
+      } else {
+        const int oy = yv * d.s_out + d.off_y[t.phase], ox = xv * d.s_out + d.off_x[t.phase];
+        out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
+      }
+      int n_live = 0;
+      {
+        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
+        if (!g.pixel_major || A_MODE != 0) n_live = kb_end - kb_begin;
+        else
+          for (int kb = kb_begin; kb < kb_end; ++kb) n_live += kb_live(t, kb) ? 1 : 0;
+      }
+      const int acc = tl & 1;
+      mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS + (static_cast<uint32_t>(q4 * 32) << 16);
+      const int n_base = t.n_tile * BLOCK_N;
+      const bool add_bias = d.bias != nullptr && t.split == 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_d + c0, v);
+        tmem_ld_wait();
+        if (out_off < 0) continue;
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) f[q] = n_live > 0 ? __uint_as_float(v[q]) : 0.0f;
+        if (add_bias) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
+        }
+        if (d.out_mode == 0) {
+          __half* o = reinterpret_cast<__half*>(d.out) + out_off + n_base + c0;
+          uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
+                                pack_h2(f[14], f[15]));
+          reinterpret_cast<uint4*>(o)[0] = u0;
+          reinterpret_cast<uint4*>(o)[1] = u1;
+        } else if (d.out_mode == 1) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + out_off + n_base + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else if (d.out_mode == 2) {
+          float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
+        } else {
+          // merged 2x2 sub-pixel phases -> fp32 NCHW planes; n = (ph*2 + pw)*3 + c
+          float* o = reinterpret_cast<float*>(d.out) + out_off;
+          const int plane = d.OH * d.OW;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph)
+              *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
+                  make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[acc]));  // accumulator stage free for tile tl + 2
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
   }
@@ -683,6 +955,32 @@ EncodeTiledFn get_encode_fn() {
 
 int g_sm_count = 148;
 int g_igemm_occ[5] = {1, 1, 1, 1, 1};  // resident CTAs per SM of igemm_kernel<16,32,64,128,256>
+int g_tma_occ[5] = {1, 1, 1, 1, 1};    // same for igemm_tma_kernel
+
+template <int BLOCK_N, int A_MODE>
+int launch_igemm_tma(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW, const TileGeom& g,
+                     int occ, cudaStream_t st) {
+  int grid = g_sm_count * occ;
+  if (grid > g.total_tiles) grid = g.total_tiles;
+  igemm_tma_kernel<BLOCK_N, A_MODE><<<grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_amode(int a_mode, const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                   const TileGeom& g, int occ, cudaStream_t st) {
+  if (a_mode == 0) return launch_igemm_tma<BLOCK_N, 0>(d, tmA, tmW, g, occ, st);
+  if (a_mode == 1) return launch_igemm_tma<BLOCK_N, 1>(d, tmA, tmW, g, occ, st);
+  return launch_igemm_tma<BLOCK_N, 2>(d, tmA, tmW, g, occ, st);
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
 
 template <int BLOCK_N>
 int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, int m_tiles, int n_tiles, int total_tiles,
@@ -732,10 +1030,28 @@ int igemm_init() {
   OCC(3, igemm_kernel<128>, Cfg<128>::SMEM_BYTES);
   OCC(4, igemm_kernel<256>, Cfg<256>::SMEM_BYTES);
 #undef OCC
+#define SET_TMA(I, BN)                                                                                        \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        Cfg<BN>::SMEM_BYTES));                                               \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        Cfg<BN>::SMEM_BYTES));                                               \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        Cfg<BN>::SMEM_BYTES));                                               \
+  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0>,      \
+                                                                TMA_THREADS, Cfg<BN>::SMEM_BYTES));          \
+  if (g_tma_occ[I] < 1) g_tma_occ[I] = 1
+  SET_TMA(0, 16);
+  SET_TMA(1, 32);
+  SET_TMA(2, 64);
+  SET_TMA(3, 128);
+  SET_TMA(4, 256);
+#undef SET_TMA
   // TMEM: 512 columns per SM, two accumulator stages per CTA
   const int cols[5] = {64, 64, 128, 256, 512};
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 5; ++i) {
     if (g_igemm_occ[i] * cols[i] > 512) g_igemm_occ[i] = 512 / cols[i];
+    if (g_tma_occ[i] * cols[i] > 512) g_tma_occ[i] = 512 / cols[i];
+  }
   return MMDYN_OK;
 }
 
@@ -788,16 +1104,83 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     set_last_error("igemm: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(cr));
     return MMDYN_ERR_CUDA;
   }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_tiles = d->N / d->block_n;
+  const int occ_idx = d->block_n == 16 ? 0 : d->block_n == 32 ? 1 : d->block_n == 64 ? 2 : d->block_n == 128 ? 3 : 4;
+
+  // ---- TMA-fed path: tile = box of bw x bh virtual pixels x bn images, or pixel-major -------------
+  const int a_mode = (d->Cin % 64 == 0) ? 0 : (d->Cin == 32 ? 1 : (d->Cin == 8 ? 2 : -1));
+  static const bool legacy = getenv("MMDYN_IGEMM_LEGACY") != nullptr;
+  if (a_mode >= 0 && !legacy && (a_mode != 1 || d->ntaps % 2 == 0) && (a_mode != 2 || d->ntaps % 8 == 0)) {
+    TileGeom g = {};
+    const int OYv = d->P / d->OXv;
+    const int bw = d->OXv;
+    bool box_ok = d->row_mode == 0 && bw <= TILE_M && (TILE_M % bw) == 0 && d->P > 1;
+    int bh = 1, bn = TILE_M;
+    if (box_ok) {
+      bh = TILE_M / bw < OYv ? TILE_M / bw : OYv;
+      box_ok = (OYv % bh) == 0 && (bh & (bh - 1)) == 0 && (TILE_M % (bw * bh)) == 0;
+      bn = TILE_M / (bw * bh);
+    }
+    // pixel-major tiles need every k-block to belong to one tap when taps can be skipped
+    g.pixel_major = box_ok ? 0 : 1;
+    if (g.pixel_major) {
+      bh = 1;
+      bn = TILE_M;
+    }
+    g.lbw = g.pixel_major ? 0 : ilog2(bw);
+    g.lbh = g.pixel_major ? 0 : ilog2(bh);
+    g.bn = bn;
+    g.tiles_y = g.pixel_major ? 1 : OYv / bh;
+    g.img_blocks = (d->n_img + bn - 1) / bn;
+    const long long m_tiles_ll = g.pixel_major ? static_cast<long long>(d->P) * g.img_blocks
+                                               : static_cast<long long>(g.img_blocks) * g.tiles_y;
+    const long long total_ll = m_tiles_ll * n_tiles * d->n_phases * d->ksplit;
+    MMDYN_REQUIRE(total_ll < (1LL << 31), "igemm: too many tiles");
+    g.m_tiles = static_cast<int>(m_tiles_ll);
+    g.n_tiles = n_tiles;
+    g.total_tiles = static_cast<int>(total_ll);
+
+    CUtensorMap tmA;
+    const int kc = a_mode == 0 ? 64 : (a_mode == 1 ? 32 : 8);
+    const int es = g.pixel_major ? 1 : d->s_in;
+    const cuuint64_t adim[4] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(d->IW),
+                                static_cast<cuuint64_t>(d->IH), static_cast<cuuint64_t>(d->n_img)};
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->a_pix_stride) * 2;
+    const cuuint64_t astr[3] = {pix_b, pix_b * d->IW, pix_b * d->IW * d->IH};
+    const cuuint32_t abox[4] = {static_cast<cuuint32_t>(kc),
+                                static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * es),
+                                static_cast<cuuint32_t>(g.pixel_major ? 1 : bh * es), static_cast<cuuint32_t>(bn)};
+    const cuuint32_t aes[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
+    const CUtensorMapSwizzle asw = a_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                               : (a_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    const CUresult ar = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), adim, astr, abox, aes,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, asw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ar != CUDA_SUCCESS) {
+      set_last_error("igemm: cuTensorMapEncodeTiled(A) failed with CUresult %d (Cin=%d IW=%d IH=%d box=%u,%u,%u,%u es=%d)",
+                     static_cast<int>(ar), d->Cin, d->IW, d->IH, abox[0], abox[1], abox[2], abox[3], es);
+      return MMDYN_ERR_CUDA;
+    }
+    const int occ = g_tma_occ[occ_idx];
+    switch (d->block_n) {
+      case 16: return dispatch_amode<16>(a_mode, d, tmA, tm, g, occ, st);
+      case 32: return dispatch_amode<32>(a_mode, d, tmA, tm, g, occ, st);
+      case 64: return dispatch_amode<64>(a_mode, d, tmA, tm, g, occ, st);
+      case 128: return dispatch_amode<128>(a_mode, d, tmA, tm, g, occ, st);
+      default: return dispatch_amode<256>(a_mode, d, tmA, tm, g, occ, st);
+    }
+  }
+
+  // ---- cp.async gather path (any geometry) -------------------------------------------------------
   long long m_tiles_ll;
   if (d->row_mode == 0)
     m_tiles_ll = (rows + TILE_M - 1) / TILE_M;
   else
     m_tiles_ll = static_cast<long long>(d->P) * ((d->n_img + TILE_M - 1) / TILE_M);
-  const int n_tiles = d->N / d->block_n;
   const long long total_ll = m_tiles_ll * n_tiles * d->n_phases * d->ksplit;
   MMDYN_REQUIRE(total_ll < (1LL << 31), "igemm: too many tiles");
   const int m_tiles = static_cast<int>(m_tiles_ll), total = static_cast<int>(total_ll);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d->block_n) {
     case 16: return launch_igemm<16>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[0], st);
     case 32: return launch_igemm<32>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[1], st);
