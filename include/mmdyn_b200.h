@@ -131,10 +131,10 @@ int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_
 int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const float* mean_invstd, void* dY,
                               float* sums2, int G, int rows_per_group, int C, void* stream);
 /* dX = a*(dU - mean(dU) - xhat*mean(dU*xhat)) in place over dU; dgamma += sum dU*xhat,
- * dbeta += sum dU (summed over groups, times grad_unscale) */
+ * dbeta += sum dU (summed over groups, times grad_unscale); coef_scratch: [G][C][4] floats */
 int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
-                       void* dU, float* dgamma, float* dbeta, int G, int rows_per_group, int C,
-                       float grad_unscale, void* stream);
+                       void* dU, float* dgamma, float* dbeta, float* coef_scratch, int G,
+                       int rows_per_group, int C, float grad_unscale, void* stream);
 
 /* --- fc tail: bias + Swish + Dropout mask (vae.py:210-214) ------------------------------------
  * raw [B][C] fp32 (igemm output incl. bias); for each of n_masks masks (fp32, values 0 or 1/(1-p),

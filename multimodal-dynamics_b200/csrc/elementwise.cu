@@ -116,31 +116,81 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
   if (running_var) running_var[c] = rv;
 }
 
-// y = swish(a*x + b), 8 channels per thread
+// y = swish(a*x + b), 8 channels per 16-byte vector, 4 vectors in flight per thread
+constexpr int EW_UNROLL = 4;
+
 __global__ void __launch_bounds__(256)
 bn_swish_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
                     long long n_vec, int rows_per_group, int C) {
   const int vpr = C >> 3;
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = v / vpr;
-    const int c0 = static_cast<int>(v - row * vpr) * 8;
-    float f[8];
-    unpack8(reinterpret_cast<const uint4*>(x)[v], f);
-    if (ab) {
-      const int g = static_cast<int>(row / rows_per_group);
-      const float4* p = reinterpret_cast<const float4*>(ab + (static_cast<long long>(g) * C + c0) * 2);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < n_vec;
+       v0 += stride * EW_UNROLL) {
+    uint4 in[EW_UNROLL];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = __ldg(p + q);
-        f[2 * q] = swishf_(fmaf(t.x, f[2 * q], t.y));
-        f[2 * q + 1] = swishf_(fmaf(t.z, f[2 * q + 1], t.w));
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = swishf_(f[i]);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < n_vec) in[u] = __ldcs(reinterpret_cast<const uint4*>(x) + v);
     }
-    reinterpret_cast<uint4*>(y)[v] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long v = v0 + u * stride;
+      if (v >= n_vec) continue;
+      float f[8];
+      unpack8(in[u], f);
+      if (ab) {
+        const long long row = v / vpr;
+        const int c0 = static_cast<int>(v - row * vpr) * 8;
+        const int g = static_cast<int>(row / rows_per_group);
+        const float4* p = reinterpret_cast<const float4*>(ab + (static_cast<long long>(g) * C + c0) * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = __ldg(p + q);
+          f[2 * q] = swishf_(fmaf(t.x, f[2 * q], t.y));
+          f[2 * q + 1] = swishf_(fmaf(t.z, f[2 * q + 1], t.w));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = swishf_(f[i]);
+      }
+      reinterpret_cast<uint4*>(y)[v] = pack8(f);
+    }
+  }
+}
+
+// Same op with the thread -> channel mapping fixed (thread owns one 8-channel vector and walks
+// rows), so the per-channel scale/shift live in registers: grid = (chunks, G).
+__global__ void __launch_bounds__(RED_THREADS)
+bn_swish_fwd_rows_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
+                         int rows_per_group, int C, int rows_per_chunk) {
+  const int vpr = C >> 3;
+  const int row_lanes = RED_THREADS / vpr;
+  const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+  const int g = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(rows_per_group, r_begin + rows_per_chunk);
+  const long long gbase = static_cast<long long>(g) * rows_per_group * C + vec * 8;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = ab[(g * C + vec * 8 + i) * 2];
+    b[i] = ab[(g * C + vec * 8 + i) * 2 + 1];
+  }
+  for (int r = r_begin + rl; r < r_end; r += EW_UNROLL * row_lanes) {
+    uint4 in[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u)
+      if (r + u * row_lanes < r_end)
+        in[u] = __ldcs(reinterpret_cast<const uint4*>(x + gbase + static_cast<long long>(r + u * row_lanes) * C));
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      if (r + u * row_lanes >= r_end) continue;
+      float f[8];
+      unpack8(in[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = swishf_(fmaf(a[i], f[i], b[i]));
+      *reinterpret_cast<uint4*>(y + gbase + static_cast<long long>(r + u * row_lanes) * C) = pack8(f);
+    }
   }
 }
 
@@ -168,11 +218,20 @@ bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict
     s1[i] = s2[i] = 0.0f;
   }
   if (rl < row_lanes) {
-    for (int r = r_begin + rl; r < r_end; r += row_lanes) {
+    for (int r = r_begin + rl; r < r_end; r += 2 * row_lanes) {
+      const int r2 = r + row_lanes;
+      const bool has2 = r2 < r_end;
       const long long off = gbase + static_cast<long long>(r) * C + vec * 8;
+      const long long off2 = gbase + static_cast<long long>(r2) * C + vec * 8;
+      uint4 ux = __ldcs(reinterpret_cast<const uint4*>(x + off)), ud = *reinterpret_cast<const uint4*>(dY + off);
+      uint4 ux2 = ux, ud2 = ud;
+      if (has2) {
+        ux2 = __ldcs(reinterpret_cast<const uint4*>(x + off2));
+        ud2 = *reinterpret_cast<const uint4*>(dY + off2);
+      }
       float fx[8], fd[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + off), fx);
-      unpack8(*reinterpret_cast<const uint4*>(dY + off), fd);
+      unpack8(ux, fx);
+      unpack8(ud, fd);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float u = fmaf(a[i], fx[i], b[i]);
@@ -182,6 +241,19 @@ bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict
         s2[i] = fmaf(du, (fx[i] - mean[i]) * invstd[i], s2[i]);
       }
       *reinterpret_cast<uint4*>(dY + off) = pack8(fd);
+      if (has2) {
+        unpack8(ux2, fx);
+        unpack8(ud2, fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float u = fmaf(a[i], fx[i], b[i]);
+          const float du = fd[i] * swish_gradf_(u);
+          fd[i] = du;
+          s1[i] += du;
+          s2[i] = fmaf(du, (fx[i] - mean[i]) * invstd[i], s2[i]);
+        }
+        *reinterpret_cast<uint4*>(dY + off2) = pack8(fd);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -211,31 +283,60 @@ swish_bwd_kernel(const __half* __restrict__ x, __half* __restrict__ dY, long lon
   }
 }
 
-// dX = a * (dU - mean(dU) - xhat * mean(dU * xhat)) in place
-__global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
-                    const float* __restrict__ mean_invstd, const float* __restrict__ sums2,
-                    __half* __restrict__ dU, long long n_vec, int rows_per_group, int C) {
+// dX = a * (dU - mean(dU) - xhat * mean(dU * xhat)) in place, rewritten per channel as
+// dX = A*dU + B*x + K with A = a, B = -a*m2*invstd, K = a*(m2*invstd*mean - m1): the coefficients
+// come from a tiny kernel, the streaming kernel then needs 3 vector loads per 8 channels.
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ ab, const float* __restrict__ mean_invstd,
+                                   const float* __restrict__ sums2, float* __restrict__ coef, int GC,
+                                   float inv_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= GC) return;
+  const float a = ab[2 * i], mean = mean_invstd[2 * i], invstd = mean_invstd[2 * i + 1];
+  const float m1 = sums2[2 * i] * inv_n, m2 = sums2[2 * i + 1] * inv_n;
+  coef[4 * i] = a;
+  coef[4 * i + 1] = -a * m2 * invstd;
+  coef[4 * i + 2] = a * (m2 * invstd * mean - m1);
+  coef[4 * i + 3] = 0.0f;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ coef, __half* __restrict__ dU,
+                    int rows_per_group, int C, int rows_per_chunk) {
   const int vpr = C >> 3;
-  const float inv_n = 1.0f / static_cast<float>(rows_per_group);
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = v / vpr;
-    const int c0 = static_cast<int>(v - row * vpr) * 8;
-    const int g = static_cast<int>(row / rows_per_group);
-    float fx[8], fd[8];
-    unpack8(reinterpret_cast<const uint4*>(x)[v], fx);
-    unpack8(reinterpret_cast<const uint4*>(dU)[v], fd);
-    const long long pb = (static_cast<long long>(g) * C + c0) * 2;
+  const int row_lanes = RED_THREADS / vpr;
+  const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+  const int g = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(rows_per_group, r_begin + rows_per_chunk);
+  const long long gbase = static_cast<long long>(g) * rows_per_group * C + vec * 8;
+  float ka[8], kb[8], kc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float a = __ldg(ab + pb + 2 * i);
-      const float mean = __ldg(mean_invstd + pb + 2 * i), invstd = __ldg(mean_invstd + pb + 2 * i + 1);
-      const float m1 = __ldg(sums2 + pb + 2 * i) * inv_n, m2 = __ldg(sums2 + pb + 2 * i + 1) * inv_n;
-      const float xhat = (fx[i] - mean) * invstd;
-      fd[i] = a * (fd[i] - m1 - xhat * m2);
+  for (int i = 0; i < 8; ++i) {
+    const float4 k = *reinterpret_cast<const float4*>(coef + (static_cast<long long>(g) * C + vec * 8 + i) * 4);
+    ka[i] = k.x;
+    kb[i] = k.y;
+    kc[i] = k.z;
+  }
+  constexpr int U = 2;
+  for (int r = r_begin + rl; r < r_end; r += U * row_lanes) {
+    uint4 ix[U], id[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (r + u * row_lanes < r_end) {
+        const long long off = gbase + static_cast<long long>(r + u * row_lanes) * C;
+        ix[u] = __ldcs(reinterpret_cast<const uint4*>(x + off));
+        id[u] = *reinterpret_cast<const uint4*>(dU + off);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u * row_lanes >= r_end) continue;
+      float fx[8], fd[8];
+      unpack8(ix[u], fx);
+      unpack8(id[u], fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) fd[i] = fmaf(ka[i], fd[i], fmaf(kb[i], fx[i], kc[i]));
+      *reinterpret_cast<uint4*>(dU + gbase + static_cast<long long>(r + u * row_lanes) * C) = pack8(fd);
     }
-    reinterpret_cast<uint4*>(dU)[v] = pack8(fd);
   }
 }
 
@@ -423,31 +524,46 @@ __device__ __forceinline__ float block_sum_256(float v) {
   return t;  // valid on thread 0
 }
 
-// one thread per pixel: reads the 3 planes (coalesced), writes one 16-byte NHWC8 gradient
+// one thread per 4 consecutive pixels: float4 loads from each of the 3 planes (coalesced), four
+// 16-byte NHWC8 gradient stores
 __global__ void __launch_bounds__(256)
 bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                   const float* __restrict__ mask, float* __restrict__ loss_sum,
                   __half* __restrict__ dlogits, float gscale, long long n_pix, int HW) {
   float acc = 0.0f;
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pix;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long n_quad = n_pix >> 2;  // HW is a multiple of 4 (checked by the launcher)
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quad;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = q << 2;
     const long long img = p / HW;
     const int hw = static_cast<int>(p - img * HW);
-    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float g[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[k][c] = 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const long long idx = (img * 3 + c) * HW + hw;
-      float x = logits[idx], t = target[idx], m = 1.0f;
-      if (mask) {
-        m = mask[idx];
-        x *= m;
-        t *= m;
+      const float4 xv = __ldcs(reinterpret_cast<const float4*>(logits + idx));
+      const float4 tv = __ldg(reinterpret_cast<const float4*>(target + idx));
+      float4 mv = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (mask) mv = __ldg(reinterpret_cast<const float4*>(mask + idx));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {tv.x, tv.y, tv.z, tv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float m = ms[k], x = xs[k] * m, t = ts[k] * m;
+        // max(x,0) - x*t + log(1 + exp(-|x|))  (torch's stable form)
+        const float e = __expf(-fabsf(x));
+        acc += fmaxf(x, 0.0f) - x * t + log1pf(e);
+        const float sig = x >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+        g[k][c] = gscale * (sig - t) * m;
       }
-      // max(x,0) - x*t + log(1 + exp(-|x|))  (torch's stable form)
-      acc += fmaxf(x, 0.0f) - x * t + log1pf(expf(-fabsf(x)));
-      g[c] = gscale * (1.0f / (1.0f + expf(-x)) - t) * m;
     }
-    if (dlogits) reinterpret_cast<uint4*>(dlogits)[p] = pack8(g);
+    if (dlogits) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(dlogits)[p + k] = pack8(g[k]);
+    }
   }
   const float t = block_sum_256(acc);
   if (threadIdx.x == 0) atomicAdd(loss_sum, t);
@@ -715,7 +831,7 @@ inline int chunking(int rows_per_group, int G, int C, int* rows_per_chunk) {
 using namespace mmdyn;
 #define ST(s) static_cast<cudaStream_t>(s)
 
-static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (RED_THREADS % (C >> 3)) == 0; }
+static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C >> 3) <= RED_THREADS && (RED_THREADS % (C >> 3)) == 0; }
 
 extern "C" int mmdyn_bn_stats(const void* x, float* sums, int G, int rows_per_group, int C, void* stream) {
   MMDYN_REQUIRE(x && sums && G > 0 && rows_per_group > 0 && bn_c_ok(C), "bn_stats: bad arguments (C=%d)", C);
@@ -744,7 +860,15 @@ extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G
                                   void* stream) {
   MMDYN_REQUIRE(x && y && G > 0 && rows_per_group > 0 && C % 8 == 0, "bn_swish_fwd: bad arguments");
   const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
-  bn_swish_fwd_kernel<<<grid_for(n_vec), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
+  if (ab && bn_c_ok(C)) {
+    int rpc;
+    const int chunks = chunking(rows_per_group, G, C, &rpc);
+    bn_swish_fwd_rows_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
+        reinterpret_cast<const __half*>(x), ab, reinterpret_cast<__half*>(y), rows_per_group, C, rpc);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
+  bn_swish_fwd_kernel<<<grid_for(n_vec / EW_UNROLL + 1), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
                                                                reinterpret_cast<__half*>(y), n_vec,
                                                                rows_per_group, C);
   LAUNCHED();
@@ -773,13 +897,20 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
 }
 
 extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
-                                  void* dU, float* dgamma, float* dbeta, int G, int rows_per_group, int C,
-                                  float grad_unscale, void* stream) {
+                                  void* dU, float* dgamma, float* dbeta, float* coef_scratch, int G,
+                                  int rows_per_group, int C, float grad_unscale, void* stream) {
   MMDYN_REQUIRE(x && ab && mean_invstd && sums2 && dU && G > 0 && C % 8 == 0, "bn_bwd_apply: bad arguments");
+  MMDYN_REQUIRE(coef_scratch, "bn_bwd_apply: coef_scratch ([G][C][4] floats) is required");
   const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
-  bn_bwd_apply_kernel<<<grid_for(n_vec), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
-                                                               mean_invstd, sums2, reinterpret_cast<__half*>(dU),
-                                                               n_vec, rows_per_group, C);
+  bn_bwd_coef_kernel<<<(G * C + 127) / 128, 128, 0, ST(stream)>>>(ab, mean_invstd, sums2, coef_scratch, G * C,
+                                                                   1.0f / static_cast<float>(rows_per_group));
+  LAUNCHED();
+  MMDYN_REQUIRE(bn_c_ok(C), "bn_bwd_apply: C=%d unsupported", C);
+  (void)n_vec;
+  int rpc;
+  const int chunks = chunking(rows_per_group, G, C, &rpc);
+  bn_bwd_apply_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
+      reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
   LAUNCHED();
   if (dgamma && dbeta) {
     bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums2, dgamma, dbeta, G, C, grad_unscale);
@@ -855,9 +986,9 @@ extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e,
 
 extern "C" int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
                                 void* dlogits_nhwc8, float gscale, int n, int HW, void* stream) {
-  MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && HW > 0, "bce_logits: bad arguments");
+  MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && HW > 0 && HW % 4 == 0, "bce_logits: bad arguments");
   const long long n_pix = static_cast<long long>(n) * HW;
-  bce_logits_kernel<<<grid_for(n_pix), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum,
+  bce_logits_kernel<<<grid_for(n_pix >> 2), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum,
                                                              reinterpret_cast<__half*>(dlogits_nhwc8), gscale,
                                                              n_pix, HW);
   LAUNCHED();

@@ -170,17 +170,76 @@ class PackedLayer:
             return t
         self.idx_fwd, self.idx_dgrad = up(lp.idx_fwd), up(lp.idx_dgrad)
         self.idx_wgrad, self.bias_idx = up(lp.idx_wgrad), up(lp.bias_idx)
-        self.Wf = torch.empty(lp.idx_fwd.shape, dtype=F16, device=device) if lp.idx_fwd is not None else None
-        self.Wd = torch.empty(lp.idx_dgrad.shape, dtype=F16, device=device) if lp.idx_dgrad is not None else None
-        self.bias = torch.empty(lp.bias_idx.shape, dtype=F32, device=device) if lp.bias_idx is not None else None
+        self.Wf = self.Wd = self.bias = None  # views into the ModelPacker arenas
 
-    def refresh(self, flat):
-        if self.Wf is not None:
-            ops.pack_f16(flat, self.idx_fwd, self.Wf)
-        if self.Wd is not None:
-            ops.pack_f16(flat, self.idx_dgrad, self.Wd)
-        if self.bias is not None:
-            ops.gather_f32(flat, self.bias_idx, self.bias)
+
+class ModelPacker:
+    """All fp16 operand copies (and permuted fp32 biases) of a model live in two arenas that are
+    rebuilt by ONE gather kernel each when the parameter arena changes; layers hold views."""
+
+    def __init__(self, nets, device):
+        layers = [pl for net in nets for pl in net.layers]
+        idx_parts, self.slots = [], []
+        off = 0
+        for pl in layers:
+            for attr, idx in (("Wf", pl.idx_fwd), ("Wd", pl.idx_dgrad)):
+                if idx is not None:
+                    idx_parts.append(idx.reshape(-1))
+                    self.slots.append((pl, attr, off, tuple(idx.shape)))
+                    off += idx.numel()
+        self.idx = torch.cat(idx_parts) if idx_parts else None
+        self.W = torch.empty(off, dtype=F16, device=device)
+        for pl, attr, o, shape in self.slots:
+            setattr(pl, attr, self.W[o:o + shape[0] * shape[1]].view(shape))
+        b_parts, boff = [], 0
+        for pl in layers:
+            if pl.bias_idx is not None:
+                b_parts.append((pl, boff, pl.bias_idx.numel()))
+                boff += pl.bias_idx.numel()
+        self.bias_idx = torch.cat([pl.bias_idx for pl, _, _ in b_parts]) if b_parts else None
+        self.bias = torch.empty(boff, dtype=F32, device=device)
+        for pl, o, k in b_parts:
+            pl.bias = self.bias[o:o + k]
+        self.token = None
+
+    def refresh(self, arena, force=False):
+        tok = arena.token()
+        if force or tok != self.token:
+            if self.idx is not None:
+                ops.pack_f16(arena.flat, self.idx, self.W)
+            if self.bias_idx is not None:
+                ops.gather_f32(arena.flat, self.bias_idx, self.bias)
+            self.token = tok
+
+
+class GradPack:
+    """Packed fp32 weight-gradient segments of one sub-network: zeroed by one memset, filled by the
+    wgrad launches, scattered into the gradient arena by ONE unpack kernel."""
+
+    def __init__(self, net, device):
+        self.seg, parts, off = {}, [], 0
+        for pl in net.layers:
+            if pl.lp.wgrad is not None:
+                n = pl.lp.wgrad.Cn * pl.lp.wgrad.K
+                self.seg[id(pl)] = (off, (pl.lp.wgrad.Cn, pl.lp.wgrad.K))
+                parts.append(pl.idx_wgrad.reshape(-1))
+                off += n
+        for name, idx in getattr(net, "extra_wgrads", {}).items():
+            self.seg[name] = (off, tuple(idx.shape))
+            parts.append(idx.reshape(-1))
+            off += idx.numel()
+        self.idx = torch.cat(parts)
+        self.buf = torch.zeros(off, dtype=F32, device=device)
+
+    def begin(self):
+        self.buf.zero_()
+
+    def view(self, key):
+        o, shape = self.seg[key]
+        return self.buf[o:o + shape[0] * shape[1]].view(shape)
+
+    def flush(self, arena):
+        ops.unpack_add_f32(self.buf, self.idx, arena.grad)
 
 
 class _NetBase:
@@ -189,6 +248,7 @@ class _NetBase:
         self.layers = []
         self._cache = {}
         self._token = None
+        self.packer = None
 
     def _pl(self, lp):
         pl = PackedLayer(lp, self.device, self._cache)
@@ -208,11 +268,7 @@ class _NetBase:
         return self.arena.module.get_buffer(self._full(name))
 
     def refresh(self):
-        tok = self.arena.token()
-        if tok != self._token:
-            for pl in self.layers:
-                pl.refresh(self.arena.flat)
-            self._token = tok
+        self.packer.refresh(self.arena)
 
 
 def _ig(pl, which, A, out, n_img, bias=None, f32_out=False):
@@ -227,12 +283,15 @@ def _ig(pl, which, A, out, n_img, bias=None, f32_out=False):
         ops.igemm(geom, A, W, out, n_img, bias=bias, out_mode=1 if f32_out else None, **kw)
 
 
-def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale):
+def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale, gp=None):
+    """Weight gradient of layer `pl` into the arena: through the sub-network's GradPack (fused step:
+    one memset + one scatter per sub-network) or a private scratch + scatter (module-level API)."""
     wg = pl.lp.wgrad
-    dWp = alloc(key, (wg.Cn, wg.K), F32, zero=True)
+    dWp = gp.view(id(pl)) if gp is not None else alloc(key, (wg.Cn, wg.K), F32, zero=True)
     ops.wgrad(wg, G, Nat, dWp, n_img, scale=scale, row_splits=plan.choose_row_splits(wg, n_img),
               tag=f"{pl.lp.name}.wgrad", macs_per_img=pl.lp.extra.get("macs"))
-    ops.unpack_add_f32(dWp, pl.idx_wgrad, arena.grad)
+    if gp is None:
+        ops.unpack_add_f32(dWp, pl.idx_wgrad, arena.grad)
 
 
 class _BN:
@@ -260,8 +319,9 @@ class _BN:
         net, C = self.net, self.C
         sums2 = alloc(key + ".sums2", (G, C, 2), F32, zero=True)
         ops.bn_swish_bwd_reduce(raw, ab, mi, dAct, sums2, G, rows, C)
+        coef = alloc(key + ".coef", (G, C, 4), F32)
         ops.bn_bwd_apply(raw, ab, mi, sums2, dAct, net.pview(self.name + ".weight", True),
-                         net.pview(self.name + ".bias", True), G, rows, C, unscale)
+                         net.pview(self.name + ".bias", True), coef, G, rows, C, unscale)
         return dAct  # now dRaw
 
 
@@ -281,6 +341,9 @@ class EncoderExec(_NetBase):
             "heads", [self.off("linear_means.weight"), self.off("linear_log_var.weight")],
             [self.off("linear_means.bias"), self.off("linear_log_var.bias")], 512, [256, 256]))
         self.bn2, self.bn3, self.bn4 = _BN(self, "conv_net.3", 64), _BN(self, "conv_net.6", 128), _BN(self, "conv_net.9", 256)
+        self.c1_wg, c1_idx = plan.conv1_wgrad_plan(self.off("conv_net.0.weight"))
+        self.c1_idx = torch.from_numpy(c1_idx).to(device)
+        self.extra_wgrads = {"conv1": self.c1_idx}
 
     def forward(self, x, masks, alloc, key, track=True):
         """x: (B,3,64,64) fp32 NCHW; masks: list of (B,512) fp32 dropout masks or None entries (one per
@@ -316,7 +379,7 @@ class EncoderExec(_NetBase):
                  fc_raw=fc_raw, h=h, heads=heads)
         return r
 
-    def backward(self, r, d_heads, alloc, key, unscale, in_scale=1.0):
+    def backward(self, r, d_heads, alloc, key, unscale, in_scale=1.0, gp=None):
         """d_heads: (n_masks*B, 512) fp32 gradient; in_scale * d_heads is what flows through the
         fp16 backward (times grad_scale), unscale * in_scale brings parameter gradients back.
         Accumulates parameter gradients into the arena."""
@@ -327,29 +390,36 @@ class EncoderExec(_NetBase):
         db = alloc(key + ".db512", (512,), F32, zero=True)
         ops.colsum_f32(d_heads, db, rows, 512, 512, unscale * in_scale)
         ops.unpack_add_f32(db, self.heads.bias_idx, arena.grad)
-        _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale)
+        _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale, gp)
         dH = alloc(key + ".dH", (rows, 512), F32)
         _ig(self.heads, "dgrad", dh16, dH, rows, None, True)
         dfc = alloc(key + ".dfc16", (B, 512), F16)
         ops.swish_dropout_bwd(r["fc_raw"], r["masks"], dH, dfc, B, 512)
         ops.colsum_f16(dfc, self.pview("fc_net.0.bias", True), B, 512, 512, unscale)
-        _wgrad_into(self.fc, r["act4"], dfc, B, arena, alloc, key + ".dW_fc", unscale)
+        _wgrad_into(self.fc, r["act4"], dfc, B, arena, alloc, key + ".dW_fc", unscale, gp)
         d4 = alloc(key + ".d4", (B, 5, 5, 256), F16)
         _ig(self.fc, "dgrad", dfc, d4, B)
         self.bn4.backward(r["raw4"], r["bn4"][0], r["bn4"][1], d4, 1, B * 25, alloc, key + ".bn4", unscale)
-        _wgrad_into(self.c4, r["act3"], d4, B, arena, alloc, key + ".dW_c4", unscale)
+        _wgrad_into(self.c4, r["act3"], d4, B, arena, alloc, key + ".dW_c4", unscale, gp)
         d3 = alloc(key + ".d3", (B, 8, 8, 128), F16)
         _ig(self.c4, "dgrad", d4, d3, B)
         self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], d3, 1, B * 64, alloc, key + ".bn3", unscale)
-        _wgrad_into(self.c3, r["act2"], d3, B, arena, alloc, key + ".dW_c3", unscale)
+        _wgrad_into(self.c3, r["act2"], d3, B, arena, alloc, key + ".dW_c3", unscale, gp)
         d2 = alloc(key + ".d2", (B, 16, 16, 64), F16)
         _ig(self.c3, "dgrad", d3, d2, B)
         self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], d2, 1, B * 256, alloc, key + ".bn2", unscale)
-        _wgrad_into(self.c2, r["act1"], d2, B, arena, alloc, key + ".dW_c2", unscale)
+        _wgrad_into(self.c2, r["act1"], d2, B, arena, alloc, key + ".dW_c2", unscale, gp)
         d1 = alloc(key + ".d1", (B, 32, 32, 32), F16)
         _ig(self.c2, "dgrad", d2, d1, B)
         ops.bn_swish_bwd_reduce(r["raw1"], None, None, d1, None, 1, B * 1024, 32)
-        ops.conv1_wgrad(r["x"], d1, self.pview("conv_net.0.weight", True), B, unscale, 296)
+        # conv1 weight gradient on the tensor cores: x -> NHWC fp16 with 8 channels per pixel
+        x8 = alloc(key + ".x8", (B, 64, 64, 8), F16)
+        ops.logit_grad_pack(r["x"], x8, 1.0, B, 64 * 64)
+        dW1 = gp.view("conv1") if gp is not None else alloc(key + ".dW_c1", (32, 128), F32, zero=True)
+        ops.wgrad(self.c1_wg, x8, d1, dW1, B, scale=unscale, row_splits=plan.choose_row_splits(self.c1_wg, B),
+                  tag="conv1.wgrad", macs_per_img=1024 * 32 * 48)
+        if gp is None:
+            ops.unpack_add_f32(dW1, self.c1_idx, arena.grad)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -393,31 +463,31 @@ class DecoderExec(_NetBase):
                  logits=logits)
         return r
 
-    def backward(self, r, dl8, alloc, key, unscale):
+    def backward(self, r, dl8, alloc, key, unscale, gp=None):
         """dl8: (G*B, 64, 64, 8) fp16 logit gradients (3 channels used, times grad_scale).
         Returns dz (G*B, 256) fp32 (times grad_scale)."""
         arena, G, B = self.arena, r["G"], r["B"]
         R = G * B
-        _wgrad_into(self.d4, dl8, r["act3"], R, arena, alloc, key + ".dW_d4", unscale)
+        _wgrad_into(self.d4, dl8, r["act3"], R, arena, alloc, key + ".dW_d4", unscale, gp)
         g3 = alloc(key + ".g3", (R, 32, 32, 32), F16)
         _ig(self.d4, "dgrad", dl8, g3, R)
         self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], g3, G, B * 1024, alloc, key + ".bn3", unscale)
-        _wgrad_into(self.d3, g3, r["act2"], R, arena, alloc, key + ".dW_d3", unscale)
+        _wgrad_into(self.d3, g3, r["act2"], R, arena, alloc, key + ".dW_d3", unscale, gp)
         g2 = alloc(key + ".g2", (R, 16, 16, 64), F16)
         _ig(self.d3, "dgrad", g3, g2, R)
         self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], g2, G, B * 256, alloc, key + ".bn2", unscale)
-        _wgrad_into(self.d2, g2, r["act1"], R, arena, alloc, key + ".dW_d2", unscale)
+        _wgrad_into(self.d2, g2, r["act1"], R, arena, alloc, key + ".dW_d2", unscale, gp)
         g1 = alloc(key + ".g1", (R, 8, 8, 128), F16)
         _ig(self.d2, "dgrad", g2, g1, R)
         self.bn1.backward(r["raw1"], r["bn1"][0], r["bn1"][1], g1, G, B * 64, alloc, key + ".bn1", unscale)
-        _wgrad_into(self.d1, g1, r["act0"], R, arena, alloc, key + ".dW_d1", unscale)
+        _wgrad_into(self.d1, g1, r["act0"], R, arena, alloc, key + ".dW_d1", unscale, gp)
         g0 = alloc(key + ".g0", (R, 5, 5, 256), F16)
         _ig(self.d1, "dgrad", g1, g0, R)
         ops.bn_swish_bwd_reduce(r["raw0"], None, None, g0, None, 1, R * 25, 256)
         dbp = alloc(key + ".db_up", (6400,), F32, zero=True)
         ops.colsum_f16(g0, dbp, R, 6400, 6400, unscale)
         ops.unpack_add_f32(dbp, self.up.bias_idx, arena.grad)
-        _wgrad_into(self.up, r["zh"], g0, R, arena, alloc, key + ".dW_up", unscale)
+        _wgrad_into(self.up, r["zh"], g0, R, arena, alloc, key + ".dW_up", unscale, gp)
         dz = alloc(key + ".dz", (R, 256), F32)
         _ig(self.up, "dgrad", g0, dz, R, None, True)
         return dz
@@ -510,6 +580,11 @@ def get_execs(module, device):
                 ex["dec"][n] = DecoderExec(arena, n, dev)
         if "pose_encoder" in names:
             ex["pose"] = PoseExec(arena, dev)
+        nets = list(ex["enc"].values()) + list(ex["dec"].values())
+        ex["packer"] = ModelPacker(nets, dev)
+        for net in nets:
+            net.packer = ex["packer"]
+        ex["gradpack"] = {net.prefix: GradPack(net, dev) for net in nets}
         module.__dict__["_mmdyn_execs"] = ex
     return arena, ex
 
@@ -611,9 +686,7 @@ class StepEngine:
             ts[k] = ts[k].contiguous().float()
         need_grad = torch.is_grad_enabled() if need_grad is None else bool(need_grad)
         if self.always_refresh:
-            for grp in (ex["enc"], ex["dec"]):
-                for net in grp.values():
-                    net._token = None
+            ex["packer"].token = None
         gs = float(self.grad_scale) if self.grad_scale else float(B)
         npass = len(self.passes)
         src = self._noise()
@@ -628,13 +701,18 @@ class StepEngine:
         masks = {m: [None] * len(enc_passes[m]) for m in img_mods}
         eps = ws("eps", (npass, B, D), F32)
         mbuf = {m: ws("mask_" + m, (len(enc_passes[m]), B, 512), F32) for m in img_mods}
-        train_mode = self.model.training
-        for i, p in enumerate(self.passes):
+        if hasattr(src, "fill_step"):
+            # device RNG: no ordering constraint between draws -> one launch per buffer
+            src.fill_step([mbuf[m] for m in img_mods], eps)
             for m in img_mods:
-                if m in p and train_mode:
-                    j = enc_passes[m].index(i)
-                    masks[m][j] = src.dropout_mask(B, first.device, out=mbuf[m][j])
-            src.normal(B, D, first.device, out=eps[i])
+                masks[m] = [mbuf[m][j] for j in range(len(enc_passes[m]))]
+        else:
+            for i, p in enumerate(self.passes):
+                for m in img_mods:
+                    if m in p:
+                        j = enc_passes[m].index(i)
+                        masks[m][j] = src.dropout_mask(B, first.device, out=mbuf[m][j])
+                src.normal(B, D, first.device, out=eps[i])
 
         # encoders (once per modality)
         enc_rec = {m: ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True) for m in img_mods}
@@ -769,8 +847,12 @@ class StepEngine:
         img_mods = st["img_mods"]
         hook = self.bucket_hook or (lambda prefixes: None)
         dz = {}
+        gps = ex["gradpack"]
         for m in img_mods:
-            dz[m] = ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale)
+            gp = gps[self.mods[m][1]]
+            gp.begin()
+            dz[m] = ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale, gp)
+            gp.flush(arena)
             hook([self.mods[m][1]])
         dzp = ex["pose"].dec_backward(st["pdec_rec"], st["d_prec"], ws, "pdec", unscale) if self.use_pose else None
         dh = {m: ws("dheads_" + m, (len(st["enc_passes"][m]) * B, 512), F32, zero=True) for m in img_mods}
@@ -791,7 +873,10 @@ class StepEngine:
             ops.poe_bwd([h[:, :D] for h in hs], [h[:, D:] for h in hs], self.use_prior, 2 * D, st["eps"][i], dzs,
                         st["klw"] * gs / B, [o[:, :D] for o in outs], [o[:, D:] for o in outs], 2 * D, True, B, D)
         for m in img_mods:
-            ex["enc"][self.mods[m][0]].backward(st["enc_rec"][m], dh[m], ws, "enc_" + m, unscale)
+            gp = gps[self.mods[m][0]]
+            gp.begin()
+            ex["enc"][self.mods[m][0]].backward(st["enc_rec"][m], dh[m], ws, "enc_" + m, unscale, 1.0, gp)
+            gp.flush(arena)
             hook([self.mods[m][0]])
         if self.use_pose:
             ex["pose"].enc_backward(st["pose_rec"], dhp, ws, "penc", unscale)

@@ -60,6 +60,18 @@ class DeviceNoise:
         return out
 
 
+    def fill_step(self, mask_bufs, eps):
+        """All dropout masks and reparametrisation noise of one step: one launch per buffer."""
+        ctr = self._counter(eps.device)
+        off = 0
+        for mb in mask_bufs:
+            ops.fill_dropout_mask(mb, mb.numel(), DROPOUT_P, self.seed, off, ctr)
+            off += (mb.numel() + 3) // 4
+        ops.fill_normal(eps, eps.numel(), self.seed, off, ctr)
+        off += (eps.numel() + 3) // 4
+        ops.rng_advance(ctr, off)
+
+
 _default = HostNoise()
 
 

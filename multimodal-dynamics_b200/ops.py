@@ -166,10 +166,10 @@ def bn_swish_bwd_reduce(x, ab, mean_invstd, dY, sums2, G, rows, Cch):
                                              Cch, _stream()), "bn_swish_bwd_reduce")
 
 
-def bn_bwd_apply(x, ab, mean_invstd, sums2, dU, dgamma, dbeta, G, rows, Cch, unscale):
+def bn_bwd_apply(x, ab, mean_invstd, sums2, dU, dgamma, dbeta, coef, G, rows, Cch, unscale):
     with _Timed("bn_bwd_apply", lambda: (0.0, G * rows * Cch * 6.0)):
         check(_L().mmdyn_bn_bwd_apply(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(sums2), _ptr(dU), _ptr(dgamma),
-                                      _ptr(dbeta), G, rows, Cch, unscale, _stream()), "bn_bwd_apply")
+                                      _ptr(dbeta), _ptr(coef), G, rows, Cch, unscale, _stream()), "bn_bwd_apply")
 
 
 def swish_dropout_fwd(raw, masks, h, B, Cch):

@@ -301,6 +301,19 @@ def conv1_plan(name, w_off):
     return LayerPlan(name, "conv1", None, idx, None, None, None, None, extra={"macs": 1024 * 32 * 48})
 
 
+def conv1_wgrad_plan(w_off):
+    """Weight gradient of the first conv through the generic tensor-core wgrad kernel: the fp32 NCHW
+    input is repacked once per backward into NHWC fp16 with 8 channels per pixel (3 used), so
+    dW[co][t*8 + c] = sum_pix dRaw[pix][co] * x8[gather(pix, t)][c] with the 16 taps of k4/s2/p1."""
+    dy, dx = _conv_taps(4, 1)
+    wg = WgradGeom(P=32 * 32, OXv=32, IH=64, IW=64, Cg=8, s_in=2, tap_dy=dy, tap_dx=dx, Cn=32)
+    idx = np.full((32, 16 * 8), -1, np.int32)
+    for t_ in range(16):
+        for c in range(3):
+            idx[:, t_ * 8 + c] = w_off + (np.arange(32) * 3 + c) * 16 + t_
+    return wg, idx
+
+
 def nhwc_perm(C, H, W):
     """perm[k'] = torch flat index (c*H*W + h*W + w) of NHWC flat index k' = (h*W + w)*C + c."""
     hw, c = np.meshgrid(np.arange(H * W), np.arange(C), indexing="ij")

@@ -265,7 +265,8 @@ def test_grouped_bn_swish_fwd_bwd(C, rows, G):
     sums2 = torch.zeros(G, C, 2, device=DEV)
     dgam, dbet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     ops.bn_swish_bwd_reduce(xd, ab, mi, dyd, sums2, G, rows, C)
-    ops.bn_bwd_apply(xd, ab, mi, sums2, dyd, dgam, dbet, G, rows, C, 0.5)
+    coef = torch.empty(G, C, 4, device=DEV)
+    ops.bn_bwd_apply(xd, ab, mi, sums2, dyd, dgam, dbet, coef, G, rows, C, 0.5)
     torch.cuda.synchronize()
     assert rel_err(dyd, xr.grad) < 3e-3
     assert rel_err(dgam, 0.5 * gr.grad) < 2e-3 and rel_err(dbet, 0.5 * br.grad) < 2e-3
