@@ -70,7 +70,9 @@ typedef struct mmdyn_igemm_desc {
   int32_t row_mode;     /* 0: tile = 128 consecutive rows (image-major);
                            1: tile = one virtual pixel x 128 images, invalid taps skipped      */
   int32_t out_mode;     /* 0: fp16 rows, 1: fp32 rows, 2: fp32 rows atomicAdd,
-                           3: fp32 NCHW planes from merged 2x2 sub-pixel phases (N = 16, 12 used) */
+                           3: fp32 NCHW planes from merged 2x2 sub-pixel phases (N = 16, 12 used),
+                           4: fp16 NHWC from merged 2x2 sub-pixel phases: n = (ph*2+pw)*ldc + c goes
+                              to pixel (2*yv+ph, 2*xv+pw), channel c (ldc = channels, multiple of 16) */
   int32_t OH, OW;       /* output spatial size                                                 */
   int32_t s_out;
   int32_t off_y[MMDYN_MAX_PHASES], off_x[MMDYN_MAX_PHASES];

@@ -310,7 +310,15 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
         }
-        if (d.out_mode == 0) {
+        if (d.out_mode == 4) {
+          // merged sub-pixel phases, NHWC fp16: this 16-column chunk belongs to one phase
+          const int n = n_base + c0, phs = n / d.ldc, co0 = n - phs * d.ldc;
+          __half* o = reinterpret_cast<__half*>(d.out) + out_off + ((phs >> 1) * d.OW + (phs & 1)) * d.ldc + co0;
+          reinterpret_cast<uint4*>(o)[0] =
+              make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]),
+                                                      pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+        } else if (d.out_mode == 0) {
           __half* o = reinterpret_cast<__half*>(d.out) + out_off + n_base + c0;
           uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
           uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
@@ -581,7 +589,15 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
         }
-        if (d.out_mode == 0) {
+        if (d.out_mode == 4) {
+          // merged sub-pixel phases, NHWC fp16: this 16-column chunk belongs to one phase
+          const int n = n_base + c0, phs = n / d.ldc, co0 = n - phs * d.ldc;
+          __half* o = reinterpret_cast<__half*>(d.out) + out_off + ((phs >> 1) * d.OW + (phs & 1)) * d.ldc + co0;
+          reinterpret_cast<uint4*>(o)[0] =
+              make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]),
+                                                      pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+        } else if (d.out_mode == 0) {
           __half* o = reinterpret_cast<__half*>(d.out) + out_off + n_base + c0;
           uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
           uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
@@ -1073,7 +1089,9 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
                 d->block_n);
   MMDYN_REQUIRE(d->ksplit >= 1 && (d->ksplit == 1 || d->out_mode == 2),
                 "igemm: ksplit=%d needs out_mode 2", d->ksplit);
-  MMDYN_REQUIRE(d->out_mode >= 0 && d->out_mode <= 3, "igemm: out_mode=%d", d->out_mode);
+  MMDYN_REQUIRE(d->out_mode >= 0 && d->out_mode <= 4, "igemm: out_mode=%d", d->out_mode);
+  MMDYN_REQUIRE(d->out_mode != 4 || (d->ldc % 16 == 0 && d->N == 4 * d->ldc && d->s_out == 2 && d->n_phases == 1),
+                "igemm: out_mode 4 needs N = 4*ldc, ldc %% 16 == 0, s_out = 2");
   MMDYN_REQUIRE(d->out_mode != 3 || (d->block_n == 16 && d->N == 16), "igemm: out_mode 3 needs N=16");
   MMDYN_REQUIRE(d->row_mode == 0 || (d->row_mode == 1 && d->ksplit == 1 && d->Cin % 64 == 0),
                 "igemm: row_mode=%d (row_mode 1 needs ksplit 1 and Cin %% 64 == 0)", d->row_mode);

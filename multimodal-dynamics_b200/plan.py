@@ -20,6 +20,7 @@ from typing import List, Optional
 import numpy as np
 
 MAX_TAPS = 16
+MERGE_PHASES = True  # run the 4 sub-pixel phases of stride-2 (de)convs as one GEMM (see _merged_geom)
 
 
 @dataclass
@@ -140,6 +141,31 @@ def _phase_taps():
     return tdy, tdx, tk
 
 
+# merged sub-pixel phases: union of the 4 phases' taps (3x3 input offsets); phase parity ->
+# {input offset: kernel index}
+KOF = {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}}
+TAPS3 = [(a, b) for a in (-1, 0, 1) for b in (-1, 0, 1)]
+
+
+def _merged_geom(Hv, Cg, Cn_out, widx_fn):
+    """One GEMM for all 4 sub-pixel phases of a k4/s2/p1 transposed conv (or of the dgrad of a k4/s2/p1
+    conv): rows = the Hv x Hv low-resolution grid, K = 9 taps x Cg gathered channels, N = 4 x Cn_out
+    (n = (ph*2+pw)*Cn_out + c), out_mode 4 scatters the 2x2 output pixels.  9 operand boxes per 128
+    rows instead of 16 — these layers are operand-feed bound, the extra (zero-weight) MACs are free."""
+    geom = GemmGeom(P=Hv * Hv, OXv=Hv, IH=Hv, IW=Hv, Cin=Cg, s_in=1, tap_dy=[[t[0] for t in TAPS3]],
+                    tap_dx=[[t[1] for t in TAPS3]], N=4 * Cn_out, OH=2 * Hv, OW=2 * Hv, s_out=2, off_y=[0],
+                    off_x=[0], ldc=Cn_out, out_mode=4)
+    idx = np.full((4 * Cn_out, 9 * Cg), -1, np.int32)
+    for ph in (0, 1):
+        for pw in (0, 1):
+            for t_, (a, b) in enumerate(TAPS3):
+                if a in KOF[ph] and b in KOF[pw]:
+                    n_, g_ = np.meshgrid(np.arange(Cn_out), np.arange(Cg), indexing="ij")
+                    r0 = (ph * 2 + pw) * Cn_out
+                    idx[r0:r0 + Cn_out, t_ * Cg:(t_ + 1) * Cg] = widx_fn(n_, g_, KOF[ph][a], KOF[pw][b])
+    return geom, idx
+
+
 def conv_s2_plan(name, w_off, Cin, Cout, H):
     """nn.Conv2d(Cin, Cout, 4, 2, 1, bias=False) on HxH (vae.py:200,203). weight [Cout][Cin][4][4]."""
     Ho = H // 2
@@ -162,6 +188,8 @@ def conv_s2_plan(name, w_off, Cin, Cout, H):
         for t_, (kh, kw) in enumerate(tk[p]):
             ci_, co_ = np.meshgrid(np.arange(Cin), np.arange(Cout), indexing="ij")
             idx_dg[p * Cin:(p + 1) * Cin, t_ * Cout:(t_ + 1) * Cout] = widx(co_, ci_, kh, kw)
+    if MERGE_PHASES and (9 * Cout) % 64 == 0 and 4 * Cin <= 256 and Cin % 16 == 0:
+        dg, idx_dg = _merged_geom(Ho, Cout, Cin, lambda ci_, co_, kh, kw: widx(co_, ci_, kh, kw))
     wg = WgradGeom(P=Ho * Ho, OXv=Ho, IH=H, IW=H, Cg=Cin, s_in=2, tap_dy=dy, tap_dx=dx, Cn=Cout)
     return LayerPlan(name, "conv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd, extra={"macs": Ho * Ho * Cout * Cin * 16})
 
@@ -226,6 +254,8 @@ def deconv_s2_plan(name, w_off, Cin, Cout, H):
         for t_, (kh, kw) in enumerate(tk[p]):
             co_, ci_ = np.meshgrid(np.arange(Cout), np.arange(Cin), indexing="ij")
             idx_fwd[p * Cout:(p + 1) * Cout, t_ * Cin:(t_ + 1) * Cin] = widx(ci_, co_, kh, kw)
+    if MERGE_PHASES and (9 * Cin) % 64 == 0 and 4 * Cout <= 256 and Cout % 16 == 0:
+        fwd, idx_fwd = _merged_geom(H, Cin, Cout, lambda co_, ci_, kh, kw: widx(ci_, co_, kh, kw))
     dy, dx = _conv_taps(4, 1)
     dg = GemmGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cin=Cout, s_in=2, tap_dy=[dy], tap_dx=[dx], N=Cin,
                   OH=H, OW=H, s_out=1, off_y=[0], off_x=[0], ldc=Cin)

@@ -34,7 +34,12 @@ def igemm(geom, A, Wp, n_img, bias=None):
                         acc += A[:, iy, ix, :g.Cin] @ W[:, t * g.Cin:(t + 1) * g.Cin].T
                 if bias is not None:
                     acc += bias[None, :]
-                if g.out_mode == 3:
+                if g.out_mode == 4:
+                    C = g.ldc
+                    for p2 in range(2):
+                        for q2 in range(2):
+                            out[:, 2 * yv + p2, 2 * xv + q2, :C] = acc[:, (p2 * 2 + q2) * C:(p2 * 2 + q2 + 1) * C]
+                elif g.out_mode == 3:
                     for p2 in range(2):
                         for q2 in range(2):
                             for c in range(3):
