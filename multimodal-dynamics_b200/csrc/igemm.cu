@@ -804,6 +804,158 @@ wgrad_kernel(const __grid_constant__ mmdyn_wgrad_desc d) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// wgrad, TMA-fed: both operands of dW += Nat^T * gather(G) arrive as 4-D TMA boxes of 64 reduction
+// rows (bw x bh virtual pixels x bn images, or one pixel x 64 images); they land in shared memory
+// as rows-of-channels, which IS the MN-major UMMA layout, so nothing is transposed or touched by
+// the LSU.  G_MODE: 0 = Cg % 64 == 0 (2 boxes of 64 k-columns, 128B swizzle), 1 = Cg == 32 (4 taps,
+// 64B swizzle), 2 = Cg == 8 (16 taps, un-swizzled 16-byte rows).
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (fp32 atomics into dW)
+// ---------------------------------------------------------------------------------------------
+struct WgradGeomDev {
+  int lbw, lbh, bn, pixel_major, tiles_y, img_blocks, total_steps;
+};
+
+template <int CN, int G_MODE>
+__global__ void __launch_bounds__(TMA_THREADS)
+wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_constant__ CUtensorMap tmG,
+                 const __grid_constant__ CUtensorMap tmN, const WgradGeomDev g) {
+  using C = Cfg<CN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kcol0 = blockIdx.y * 128;
+  const int n0 = blockIdx.z * CN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmN);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int steps_per = (g.total_steps + d.row_splits - 1) / d.row_splits;
+  const int step_begin = blockIdx.x * steps_per;
+  const int step_end = min(g.total_steps, step_begin + steps_per);
+  const int n_steps = max(0, step_end - step_begin);
+  constexpr int NAT_BYTES = 64 * CN * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_steps; ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+        const int step = step_begin + it;
+        int img0, y0, x0;
+        if (g.pixel_major) {
+          const int pix = step / g.img_blocks;
+          img0 = (step - pix * g.img_blocks) * 64;
+          y0 = pix / d.OXv;
+          x0 = pix - y0 * d.OXv;
+        } else {
+          const int ib = step / g.tiles_y;
+          img0 = ib * g.bn;
+          y0 = (step - ib * g.tiles_y) << g.lbh;
+          x0 = 0;
+        }
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+        const uint32_t b_stage = a_stage + A_STAGE_BYTES;
+        mbar_arrive_expect_tx(bar, A_STAGE_BYTES + NAT_BYTES);
+        const int wx = x0 * d.s_in, wy = y0 * d.s_in;
+        if (G_MODE == 0) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int k = kcol0 + b * 64;
+            const int tap = k / d.Cg, c0 = k - tap * d.Cg;
+            tma_load_4d(a_stage + b * 8192, &tmG, bar, c0, wx + d.tap_dx[tap], wy + d.tap_dy[tap], img0);
+          }
+        } else if (G_MODE == 1) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int tap = (kcol0 >> 5) + b;
+            tma_load_4d(a_stage + b * 4096, &tmG, bar, 0, wx + d.tap_dx[tap], wy + d.tap_dy[tap], img0);
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            const int tap = (kcol0 >> 3) + b;
+            tma_load_4d(a_stage + b * 1024, &tmG, bar, 0, wx + d.tap_dx[tap], wy + d.tap_dy[tap], img0);
+          }
+        }
+        if (CN >= 64) {
+#pragma unroll
+          for (int b = 0; b < CN / 64; ++b) tma_load_4d(b_stage + b * 8192, &tmN, bar, n0 + b * 64, x0, y0, img0);
+        } else {
+          tma_load_4d(b_stage, &tmN, bar, n0, x0, y0, img0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, CN, 0, 0, 1, 1);
+      constexpr uint32_t b_layout = CN >= 64 ? LAYOUT_SW128 : (CN == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
+      constexpr uint32_t b_sbo = CN >= 64 ? 1024 : (CN == 32 ? 512 : 256);  // 8 reduction rows of the tile
+      for (int it = 0; it < n_steps; ++it) {
+        const int s = it % C::STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
+        const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // 16 reduction rows per MMA
+          uint64_t adesc;
+          if (G_MODE == 0) adesc = make_smem_desc(a_base + kk * 2048, 8192, 1024, LAYOUT_SW128);
+          else if (G_MODE == 1) adesc = make_smem_desc(a_base + kk * 1024, 4096, 512, LAYOUT_SW64);
+          else adesc = make_smem_desc(a_base + kk * 256, 128, 1024, 0);
+          const uint64_t bdesc = make_smem_desc(b_base + kk * 2 * b_sbo, 8192, b_sbo, b_layout);
+          umma_f16(tmem_base, adesc, bdesc, idesc, (it | kk) != 0);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  } else if (n_steps > 0) {
+    const int q4 = warp & 3;
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    float* o = d.dW + static_cast<long long>(n0) * d.ldw + kcol0 + q4 * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < CN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        atomicAdd(o + static_cast<long long>(c0 + q) * d.ldw, d.scale * __uint_as_float(v[q]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // conv1: Conv2d(3, 32, k4, s2, p1) on the fp32 NCHW input, 64x64 -> 32x32, fp16 NHWC out.
 //   One tile = 4 output rows x 32 columns of one image (128 GEMM rows), K = 48 (+16 zero pad),
 //   N = 32: a single 64-wide k-block, so no ring: gather -> 4 MMAs -> epilogue.
@@ -992,6 +1144,23 @@ int dispatch_amode(int a_mode, const mmdyn_igemm_desc* d, const CUtensorMap& tmA
   return launch_igemm_tma<BLOCK_N, 2>(d, tmA, tmW, g, occ, st);
 }
 
+template <int CN, int G_MODE>
+int launch_wgrad_tma(const mmdyn_wgrad_desc* d, const CUtensorMap& tmG, const CUtensorMap& tmN,
+                     const WgradGeomDev& g, dim3 grid, cudaStream_t st) {
+  wgrad_tma_kernel<CN, G_MODE><<<grid, TMA_THREADS, Cfg<CN>::SMEM_BYTES, st>>>(*d, tmG, tmN, g);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+template <int CN>
+int dispatch_gmode(int g_mode, const mmdyn_wgrad_desc* d, const CUtensorMap& tmG, const CUtensorMap& tmN,
+                   const WgradGeomDev& g, dim3 grid, cudaStream_t st) {
+  if (g_mode == 0) return launch_wgrad_tma<CN, 0>(d, tmG, tmN, g, grid, st);
+  if (g_mode == 1) return launch_wgrad_tma<CN, 1>(d, tmG, tmN, g, grid, st);
+  return launch_wgrad_tma<CN, 2>(d, tmG, tmN, g, grid, st);
+}
+
 int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -1062,6 +1231,19 @@ int igemm_init() {
   SET_TMA(3, 128);
   SET_TMA(4, 256);
 #undef SET_TMA
+#define SET_WG(CN)                                                                                            \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        Cfg<CN>::SMEM_BYTES));                                               \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        Cfg<CN>::SMEM_BYTES));                                               \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        Cfg<CN>::SMEM_BYTES))
+  SET_WG(16);
+  SET_WG(32);
+  SET_WG(64);
+  SET_WG(128);
+  SET_WG(256);
+#undef SET_WG
   // TMEM: 512 columns per SM, two accumulator stages per CTA
   const int cols[5] = {64, 64, 128, 256, 512};
   for (int i = 0; i < 5; ++i) {
@@ -1225,6 +1407,86 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
                 "wgrad: tensor too large for 32-bit offsets");
   dim3 grid(d->row_splits, (d->ntaps * d->Cg) / 128, d->Cn / cn_tile);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // ---- TMA-fed path ---------------------------------------------------------------------------------
+  const int g_mode = (d->Cg % 64 == 0) ? 0 : (d->Cg == 32 ? 1 : (d->Cg == 8 ? 2 : -1));
+  static const bool legacy = getenv("MMDYN_WGRAD_LEGACY") != nullptr;
+  EncodeTiledFn enc = get_encode_fn();
+  if (g_mode >= 0 && !legacy && enc) {
+    WgradGeomDev g = {};
+    const int OYv = d->P / d->OXv, bw = d->OXv;
+    bool box_ok = d->P > 1 && bw <= 64 && (64 % bw) == 0;
+    int bh = 1, bn = 64;
+    if (box_ok) {
+      bh = 64 / bw < OYv ? 64 / bw : OYv;
+      box_ok = (OYv % bh) == 0 && (bh & (bh - 1)) == 0 && (64 % (bw * bh)) == 0;
+      bn = 64 / (bw * bh);
+    }
+    g.pixel_major = box_ok ? 0 : 1;
+    if (g.pixel_major) {
+      bh = 1;
+      bn = 64;
+    }
+    g.lbw = g.pixel_major ? 0 : ilog2(bw);
+    g.lbh = g.pixel_major ? 0 : ilog2(bh);
+    g.bn = bn;
+    g.tiles_y = g.pixel_major ? 1 : OYv / bh;
+    g.img_blocks = (d->n_img + bn - 1) / bn;
+    const long long steps = g.pixel_major ? static_cast<long long>(d->P) * g.img_blocks
+                                          : static_cast<long long>(g.img_blocks) * g.tiles_y;
+    MMDYN_REQUIRE(steps < (1LL << 31), "wgrad: too many steps");
+    g.total_steps = static_cast<int>(steps);
+    if (static_cast<long long>(grid.x) > steps) grid.x = static_cast<unsigned>(steps);
+
+    const int es = g.pixel_major ? 1 : d->s_in;
+    const int kc = g_mode == 0 ? 64 : (g_mode == 1 ? 32 : 8);
+    CUtensorMap tmG, tmN;
+    {
+      const cuuint64_t dim[4] = {static_cast<cuuint64_t>(d->Cg), static_cast<cuuint64_t>(d->IW),
+                                 static_cast<cuuint64_t>(d->IH), static_cast<cuuint64_t>(d->n_img)};
+      const cuuint64_t pb = static_cast<cuuint64_t>(d->g_pix_stride) * 2;
+      const cuuint64_t str[3] = {pb, pb * d->IW, pb * d->IW * d->IH};
+      const cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * es),
+                                 static_cast<cuuint32_t>(g.pixel_major ? 1 : bh * es), static_cast<cuuint32_t>(bn)};
+      const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
+      const CUtensorMapSwizzle sw = g_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                : (g_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+      const CUresult r = enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->G), dim, str, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_last_error("wgrad: cuTensorMapEncodeTiled(G) failed with CUresult %d", static_cast<int>(r));
+        return MMDYN_ERR_CUDA;
+      }
+    }
+    {
+      const cuuint64_t dim[4] = {static_cast<cuuint64_t>(d->Cn), static_cast<cuuint64_t>(d->OXv),
+                                 static_cast<cuuint64_t>(OYv), static_cast<cuuint64_t>(d->n_img)};
+      const cuuint64_t pb = static_cast<cuuint64_t>(d->nat_stride) * 2;
+      const cuuint64_t str[3] = {pb, pb * d->OXv, pb * d->P};
+      const int cnb = cn_tile >= 64 ? 64 : cn_tile;
+      const cuuint32_t box[4] = {static_cast<cuuint32_t>(cnb), static_cast<cuuint32_t>(g.pixel_major ? 1 : bw),
+                                 static_cast<cuuint32_t>(g.pixel_major ? 1 : bh), static_cast<cuuint32_t>(bn)};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUtensorMapSwizzle sw = cn_tile >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : (cn_tile == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      const CUresult r = enc(&tmN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->Nat), dim, str, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_last_error("wgrad: cuTensorMapEncodeTiled(Nat) failed with CUresult %d", static_cast<int>(r));
+        return MMDYN_ERR_CUDA;
+      }
+    }
+    switch (cn_tile) {
+      case 16: return dispatch_gmode<16>(g_mode, d, tmG, tmN, g, grid, st);
+      case 32: return dispatch_gmode<32>(g_mode, d, tmG, tmN, g, grid, st);
+      case 64: return dispatch_gmode<64>(g_mode, d, tmG, tmN, g, grid, st);
+      case 128: return dispatch_gmode<128>(g_mode, d, tmG, tmN, g, grid, st);
+      default: return dispatch_gmode<256>(g_mode, d, tmG, tmN, g, grid, st);
+    }
+  }
+
   switch (cn_tile) {
     case 16: return launch_wgrad<16>(d, grid, st);
     case 32: return launch_wgrad<32>(d, grid, st);
