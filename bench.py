@@ -214,26 +214,52 @@ def run_b200(args):
         return l
 
     loss_host = torch.zeros(1).pin_memory()
+    # e2e: the host->device copy of step i+1's pinned batch runs on a copy stream into one of two
+    # device staging sets while step i computes; the step then moves staging -> the graph's static
+    # inputs (device-to-device) and reads the loss back.  All of it is inside the timed region.
+    copy_stream = torch.cuda.Stream()
+    staging = [[torch.empty_like(a, device=dev) for a in host_batches[0][0] + host_batches[0][1]] for _ in range(2)]
+    staged_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"primed": False}
+
+    def stage(i):
+        x, t = host_batches[i % 3]
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed_evt[slot])
+            for dst, src in zip(staging[slot], x + t):
+                dst.copy_(src, non_blocking=True)
+            staged_evt[slot].record(copy_stream)
 
     def step_e2e(i):
-        x, t = host_batches[i % 3]
+        if not e2e_state["primed"]:
+            for ev in consumed_evt:
+                ev.record()
+            stage(i)
+            e2e_state["primed"] = True
+        slot = i % 2
+        stage(i + 1)  # prefetch the next batch while this step runs
+        cur = torch.cuda.current_stream()
+        cur.wait_event(staged_evt[slot])
+        xs, ts = staging[slot][:3], staging[slot][3:]
         if gstep is not None:
-            gstep.load(x, t)  # pinned host -> device copies of this step's inputs
+            gstep.load(xs, ts)
+            consumed_evt[slot].record(cur)
             gstep.run()
             if world > 1:
                 sync_grads()
                 gstep.apply()
             l = gstep.loss
         else:
-            xd = [a.to(dev, non_blocking=True) for a in x]
-            td = [a.to(dev, non_blocking=True) for a in t]
             opt.zero_grad()
-            _, l = eng.evaluate(xd, td, klw, need_grad=True, autograd=False, want_outputs=False)
+            _, l = eng.evaluate(xs, ts, klw, need_grad=True, autograd=False, want_outputs=False)
             eng.backward()
+            consumed_evt[slot].record(cur)
             sync_grads()
             opt.step()
         loss_host.copy_(l.reshape(1), non_blocking=True)  # the step's result comes back to the host
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
         return float(loss_host[0])
 
     def timed(fn, n):
@@ -259,7 +285,8 @@ def run_b200(args):
     ms_total = timed(step_resident, K)
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, K)
+    e2e_off = 2
+    ms_e2e = timed(lambda i: step_e2e(i + e2e_off), K)
     sampler.stop_flag = True
     final_loss = float(step_resident(0).item())
     assert final_loss == final_loss and final_loss < 1e9, f"training diverged: loss={final_loss}"

@@ -1409,7 +1409,10 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // ---- TMA-fed path ---------------------------------------------------------------------------------
-  const int g_mode = (d->Cg % 64 == 0) ? 0 : (d->Cg == 32 ? 1 : (d->Cg == 8 ? 2 : -1));
+  // Cg == 8 (16-byte pixels: logit gradients, repacked input) stays on the cp.async gather: sixteen
+  // 1 KB boxes of 16-byte rows per step are slower through TMA than 16-byte LDGSTS (measured)
+  static const bool g8_tma = getenv("MMDYN_WGRAD_G8_TMA") != nullptr;
+  const int g_mode = (d->Cg % 64 == 0) ? 0 : (d->Cg == 32 ? 1 : ((d->Cg == 8 && g8_tma) ? 2 : -1));
   static const bool legacy = getenv("MMDYN_WGRAD_LEGACY") != nullptr;
   EncodeTiledFn enc = get_encode_fn();
   if (g_mode >= 0 && !legacy && enc) {
