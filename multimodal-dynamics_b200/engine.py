@@ -643,6 +643,11 @@ class StepEngine:
         self._state = None
         self.always_refresh = False   # set while capturing a CUDA graph: the packing kernels must be in it
         self.bucket_hook = None       # callable(prefixes) fired when those sub-networks' gradients are final
+        # independent sub-networks (visual / tactile branch, pose MLP) run on separate streams: at
+        # small batch a single branch cannot fill 148 SMs; in a captured graph these become
+        # parallel branches
+        self.concurrent = os.environ.get("MMDYN_SERIAL_BRANCHES") is None
+        self._side = {}
 
     # -- helpers ------------------------------------------------------------------------------
     def _noise(self):
@@ -653,6 +658,32 @@ class StepEngine:
             return src
         from . import noise
         return noise.get_default()
+
+    def _fork(self, branches, main_fn=None):
+        """Run `branches` (dict key -> callable) concurrently on per-key side streams, `main_fn` on the
+        current stream, then join everything back into the current stream."""
+        if not self.concurrent or len(branches) == 0:
+            for fn in branches.values():
+                fn()
+            if main_fn is not None:
+                main_fn()
+            return
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        used = []
+        for k, fn in branches.items():
+            st = self._side.get(k)
+            if st is None:
+                st = self._side[k] = torch.cuda.Stream()
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                fn()
+            used.append(st)
+        if main_fn is not None:
+            main_fn()
+        for st in used:
+            cur.wait_stream(st)
 
     def _setup(self, device):
         arena, ex = get_execs(self.model, device)
@@ -715,8 +746,18 @@ class StepEngine:
                 src.normal(B, D, first.device, out=eps[i])
 
         # encoders (once per modality)
-        enc_rec = {m: ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True) for m in img_mods}
-        pose_rec = ex["pose"].enc_forward(xs["p"], ws, "penc") if self.use_pose else None
+        ex["packer"].refresh(arena)  # before the fork: every branch reads the packed weights
+        enc_rec, pose_box = {}, {}
+
+        def enc_branch(m):
+            def fn():
+                enc_rec[m] = ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True)
+            return fn
+
+        def pose_enc():
+            pose_box["rec"] = ex["pose"].enc_forward(xs["p"], ws, "penc")
+        self._fork({m: enc_branch(m) for m in img_mods}, pose_enc if self.use_pose else None)
+        pose_rec = pose_box.get("rec")
 
         # PoE + reparam + KL per pass
         scal = ws("scal", (64,), F32, zero=True)
@@ -747,33 +788,38 @@ class StepEngine:
                         lv_all[i], zf, zh[0] if len(zh) > 0 else None, zh[1] if len(zh) > 1 else None,
                         scal[i:i + 1], B, D)
 
-        # decoders, group-batched
-        dec_rec = {m: ex["dec"][self.mods[m][1]].forward(zdec[m], len(dec_groups[m]), B, ws, "dec_" + m, True)
-                   for m in img_mods}
-        pdec_rec = ex["pose"].dec_forward(zpose, ws, "pdec") if self.use_pose else None
-
-        # losses (+ logit gradients when training)
-        slot = {}
-        nslot = 8
-        dl8 = {}
+        # decoders, group-batched, + losses (and logit gradients when training): one branch per modality
+        slot, nslot = {}, 8
         for m in img_mods:
-            G = len(dec_groups[m])
-            dl8[m] = ws("dl8_" + m, (G * B, 64, 64, 8), F16, zero=self.exact) if need_grad else None
             for i in enc_passes[m]:
-                g = dec_groups[m].index(i)
                 slot[(m, i)] = nslot
-                lg = dec_rec[m]["logits"][g * B:(g + 1) * B]
-                ops.bce_logits(lg, ts[m], loss_mask, scal[nslot:nslot + 1],
-                               dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64 * 64)
                 nslot += 1
-        d_prec = None
-        if self.use_pose:
-            d_prec = ws("d_prec", (len(pose_passes) * B, 7), F32) if need_grad else None
+        for i in pose_passes:
+            slot[("p", i)] = nslot
+            nslot += 1
+        dec_rec, dl8, pdec_box = {}, {}, {}
+
+        def dec_branch(m):
+            def fn():
+                G = len(dec_groups[m])
+                dec_rec[m] = ex["dec"][self.mods[m][1]].forward(zdec[m], G, B, ws, "dec_" + m, True)
+                dl8[m] = ws("dl8_" + m, (G * B, 64, 64, 8), F16, zero=self.exact) if need_grad else None
+                for i in enc_passes[m]:
+                    g = dec_groups[m].index(i)
+                    k = slot[(m, i)]
+                    ops.bce_logits(dec_rec[m]["logits"][g * B:(g + 1) * B], ts[m], loss_mask, scal[k:k + 1],
+                                   dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64 * 64)
+            return fn
+
+        def pose_dec():
+            pdec_box["rec"] = ex["pose"].dec_forward(zpose, ws, "pdec")
+            pdec_box["d"] = ws("d_prec", (len(pose_passes) * B, 7), F32) if need_grad else None
             for g, i in enumerate(pose_passes):
-                slot[("p", i)] = nslot
-                ops.mse(pdec_rec["rec"][g * B:(g + 1) * B], ts["p"], scal[nslot:nslot + 1],
-                        d_prec[g * B:(g + 1) * B] if need_grad else None, self.pose_multiplier, gs / B, B * 7)
-                nslot += 1
+                k = slot[("p", i)]
+                ops.mse(pdec_box["rec"]["rec"][g * B:(g + 1) * B], ts["p"], scal[k:k + 1],
+                        pdec_box["d"][g * B:(g + 1) * B] if need_grad else None, self.pose_multiplier, gs / B, B * 7)
+        self._fork({m: dec_branch(m) for m in img_mods}, pose_dec if self.use_pose else None)
+        pdec_rec, d_prec = pdec_box.get("rec"), pdec_box.get("d")
         klw = float(kl_weight)
         loss_value = (scal[8:nslot].sum() + klw * scal[:npass].sum()) / B
 
@@ -846,15 +892,22 @@ class StepEngine:
         D = 256
         img_mods = st["img_mods"]
         hook = self.bucket_hook or (lambda prefixes: None)
-        dz = {}
+        dz, dzp_box = {}, {}
         gps = ex["gradpack"]
-        for m in img_mods:
-            gp = gps[self.mods[m][1]]
-            gp.begin()
-            dz[m] = ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale, gp)
-            gp.flush(arena)
-            hook([self.mods[m][1]])
-        dzp = ex["pose"].dec_backward(st["pdec_rec"], st["d_prec"], ws, "pdec", unscale) if self.use_pose else None
+
+        def dec_bwd(m):
+            def fn():
+                gp = gps[self.mods[m][1]]
+                gp.begin()
+                dz[m] = ex["dec"][self.mods[m][1]].backward(st["dec_rec"][m], st["dl8"][m], ws, "dec_" + m, unscale, gp)
+                gp.flush(arena)
+                hook([self.mods[m][1]])
+            return fn
+
+        def pose_dec_bwd():
+            dzp_box["dz"] = ex["pose"].dec_backward(st["pdec_rec"], st["d_prec"], ws, "pdec", unscale)
+        self._fork({m: dec_bwd(m) for m in img_mods}, pose_dec_bwd if self.use_pose else None)
+        dzp = dzp_box.get("dz")
         dh = {m: ws("dheads_" + m, (len(st["enc_passes"][m]) * B, 512), F32, zero=True) for m in img_mods}
         dhp = ws("dheads_p", (B, 512), F32, zero=True) if self.use_pose else None
         for i, p in enumerate(self.passes):
@@ -872,15 +925,19 @@ class StepEngine:
                 dzs.append(dzp[g * B:(g + 1) * B])
             ops.poe_bwd([h[:, :D] for h in hs], [h[:, D:] for h in hs], self.use_prior, 2 * D, st["eps"][i], dzs,
                         st["klw"] * gs / B, [o[:, :D] for o in outs], [o[:, D:] for o in outs], 2 * D, True, B, D)
-        for m in img_mods:
-            gp = gps[self.mods[m][0]]
-            gp.begin()
-            ex["enc"][self.mods[m][0]].backward(st["enc_rec"][m], dh[m], ws, "enc_" + m, unscale, 1.0, gp)
-            gp.flush(arena)
-            hook([self.mods[m][0]])
-        if self.use_pose:
+        def enc_bwd(m):
+            def fn():
+                gp = gps[self.mods[m][0]]
+                gp.begin()
+                ex["enc"][self.mods[m][0]].backward(st["enc_rec"][m], dh[m], ws, "enc_" + m, unscale, 1.0, gp)
+                gp.flush(arena)
+                hook([self.mods[m][0]])
+            return fn
+
+        def pose_enc_bwd():
             ex["pose"].enc_backward(st["pose_rec"], dhp, ws, "penc", unscale)
             hook(["pose_encoder", "pose_decoder"])
+        self._fork({m: enc_bwd(m) for m in img_mods}, pose_enc_bwd if self.use_pose else None)
         self._state = None
 
 
