@@ -298,6 +298,7 @@ def run_b200(args):
     # ---- roofline pass: every launch of this library timed with CUDA events (eager, untimed run) ----
     roof, table = None, []
     if rank == 0:
+        eng.set_concurrent(False)  # serial branches: per-kernel events must not time-share the SMs
         for _ in range(2):
             ops.start_profile()
             opt.zero_grad()

@@ -230,6 +230,7 @@ class GradPack:
             off += idx.numel()
         self.idx = torch.cat(parts)
         self.buf = torch.zeros(off, dtype=F32, device=device)
+        self.wstream = torch.cuda.Stream(device=device) if os.environ.get("MMDYN_SERIAL_BRANCHES") is None else None
 
     def begin(self):
         self.buf.zero_()
@@ -239,6 +240,8 @@ class GradPack:
         return self.buf[o:o + shape[0] * shape[1]].view(shape)
 
     def flush(self, arena):
+        if self.wstream is not None:
+            torch.cuda.current_stream().wait_stream(self.wstream)
         ops.unpack_add_f32(self.buf, self.idx, arena.grad)
 
 
@@ -283,13 +286,32 @@ def _ig(pl, which, A, out, n_img, bias=None, f32_out=False):
         ops.igemm(geom, A, W, out, n_img, bias=bias, out_mode=1 if f32_out else None, **kw)
 
 
+class _on_side:
+    """Launch the enclosed kernels on the GradPack's weight-gradient stream: a layer's wgrad only
+    needs that layer's dRaw, so it overlaps the next layer's dgrad + BatchNorm backward."""
+
+    def __init__(self, gp):
+        self.st = getattr(gp, "wstream", None) if gp is not None else None
+
+    def __enter__(self):
+        if self.st is not None:
+            self.st.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.st)
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.st is not None:
+            self.ctx.__exit__(*a)
+
+
 def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale, gp=None):
     """Weight gradient of layer `pl` into the arena: through the sub-network's GradPack (fused step:
     one memset + one scatter per sub-network) or a private scratch + scatter (module-level API)."""
     wg = pl.lp.wgrad
     dWp = gp.view(id(pl)) if gp is not None else alloc(key, (wg.Cn, wg.K), F32, zero=True)
-    ops.wgrad(wg, G, Nat, dWp, n_img, scale=scale, row_splits=plan.choose_row_splits(wg, n_img),
-              tag=f"{pl.lp.name}.wgrad", macs_per_img=pl.lp.extra.get("macs"))
+    with _on_side(gp):
+        ops.wgrad(wg, G, Nat, dWp, n_img, scale=scale, row_splits=plan.choose_row_splits(wg, n_img),
+                  tag=f"{pl.lp.name}.wgrad", macs_per_img=pl.lp.extra.get("macs"))
     if gp is None:
         ops.unpack_add_f32(dWp, pl.idx_wgrad, arena.grad)
 
@@ -416,8 +438,9 @@ class EncoderExec(_NetBase):
         x8 = alloc(key + ".x8", (B, 64, 64, 8), F16)
         ops.logit_grad_pack(r["x"], x8, 1.0, B, 64 * 64)
         dW1 = gp.view("conv1") if gp is not None else alloc(key + ".dW_c1", (32, 128), F32, zero=True)
-        ops.wgrad(self.c1_wg, x8, d1, dW1, B, scale=unscale, row_splits=plan.choose_row_splits(self.c1_wg, B),
-                  tag="conv1.wgrad", macs_per_img=1024 * 32 * 48)
+        with _on_side(gp):
+            ops.wgrad(self.c1_wg, x8, d1, dW1, B, scale=unscale, row_splits=plan.choose_row_splits(self.c1_wg, B),
+                      tag="conv1.wgrad", macs_per_img=1024 * 32 * 48)
         if gp is None:
             ops.unpack_add_f32(dW1, self.c1_idx, arena.grad)
 
@@ -658,6 +681,17 @@ class StepEngine:
             return src
         from . import noise
         return noise.get_default()
+
+    def set_concurrent(self, flag):
+        """Serialise (False) or parallelise (True) the independent branches — the per-kernel CUDA-event
+        profile of bench.py needs them serial, otherwise kernels time-share the SMs."""
+        self.concurrent = bool(flag)
+        _, ex = get_execs(self.model, None)
+        for gp in ex["gradpack"].values():
+            if flag and gp.wstream is None:
+                gp.wstream = torch.cuda.Stream()
+            elif not flag:
+                gp.wstream = None
 
     def _fork(self, branches, main_fn=None):
         """Run `branches` (dict key -> callable) concurrently on per-key side streams, `main_fn` on the
