@@ -299,6 +299,7 @@ def run_b200(args):
     roof, table = None, []
     if rank == 0:
         eng.set_concurrent(False)  # serial branches: per-kernel events must not time-share the SMs
+        eng.bucket_hook = None     # rank-0-only pass: no collectives
         for _ in range(2):
             ops.start_profile()
             opt.zero_grad()
