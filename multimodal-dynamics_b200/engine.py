@@ -1020,7 +1020,9 @@ class GraphedTrainStep:
             self.opt.step()
         return outputs, loss
 
-    def load(self, x, t, non_blocking=True):
+    def load(self, x, t, non_blocking=True, mask=None):
+        if mask is not None and self.mask is not None:
+            self.mask.copy_(mask, non_blocking=non_blocking)
         if isinstance(self.x, list):
             for d, s_ in zip(self.x, x):
                 d.copy_(s_, non_blocking=non_blocking)

@@ -135,6 +135,10 @@ class Problem:
     def _evaluate_model(self, inputs, targets, **kwargs):
         raise NotImplementedError
 
+    def _graphed_step(self, inputs, targets):
+        """Optional fast path of the training step (see Reconstruction); None = run it eagerly."""
+        return None
+
     # -- epochs (problems.py:143-216) -----------------------------------------------------------------
     def _train_epoch(self, epoch):
         print('Epoch: %d' % epoch)
@@ -145,10 +149,15 @@ class Problem:
         n = len(self.train_loader)
         for batch_idx, (data_input, data_target) in enumerate(self.train_loader):
             inputs, targets = self.parse_input(data_input, data_target)
-            self._optimizer.zero_grad()
-            outputs, loss = self._evaluate_model(inputs, targets)
-            loss.backward()
-            self._optimizer.step()
+            step = self._graphed_step(inputs, targets)
+            if step is not None:
+                # zero_grad + fused forward + fused backward + fused optimizer: one CUDA-graph replay
+                outputs, loss = step
+            else:
+                self._optimizer.zero_grad()
+                outputs, loss = self._evaluate_model(inputs, targets)
+                loss.backward()
+                self._optimizer.step()
             train_loss += loss.detach()
             for k, v in outputs.get('perf_measure', {}).items():
                 perf_measure[k] = perf_measure[k] + v
@@ -255,6 +264,38 @@ class Reconstruction(Problem):
 
     def _mvae_elbo_loss(self, recon_x, x, means, log_var, loss_mask=None, reduce=None, reduction='sum'):
         raise NotImplementedError("the ELBO is computed inside the fused step: use _evaluate_model()")
+
+    use_cuda_graph = True  # replay the whole training step as one CUDA graph when the noise source allows it
+
+    def _step_tensors(self, inputs, targets):
+        """(x, targets, loss_mask, rename) in the form StepEngine.evaluate takes them."""
+        return inputs, inputs, None, None
+
+    def _graphed_step(self, inputs, targets):
+        from mmdyn_b200 import noise as _noise
+        eng = self._get_engine()
+        src = eng._noise()
+        if not self.use_cuda_graph or not isinstance(self._optimizer, (fused_optim.FusedAdam, fused_optim.FusedSGD)):
+            return None
+        if isinstance(src, _noise.HostNoise):
+            if src is not _noise.get_default():
+                return None  # a caller-provided host generator must keep its draw order: eager path
+            eng.noise_src = src = _noise.DeviceNoise(seed=int(torch.initial_seed() % (1 << 31)))
+        x, t, mask, rename = self._step_tensors(inputs, targets)
+        first = x[0] if isinstance(x, (list, tuple)) else x
+        key = (tuple(first.shape), float(self._kl_weight), mask is not None, float(self._pose_multiplier))
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        g = cache.get(key)
+        if g is None:
+            if len(cache) > 4:
+                cache.clear()
+            g = cache[key] = engine.GraphedTrainStep(eng, self._optimizer, x, t, self._kl_weight, loss_mask=mask)
+        g.load(x, t, mask=mask)
+        outputs, loss = g.run()
+        if "x" in outputs.get("perf_measure", {}):
+            outputs = dict(outputs)
+            outputs["perf_measure"] = {rename: outputs["perf_measure"]["x"]} if rename is not None else {}
+        return outputs, loss
 
     def _get_engine(self):
         kind = 'mvae' if ('mvae' in self.parameters['model_name'] and self._cross_modal) else 'vae'
@@ -368,6 +409,20 @@ class SeqModeling(Reconstruction, Problem):
             self._condition_dim = len(self.train_dataset.data[0][0][4])
         except Exception:
             self._condition_dim = 0
+
+    def _step_tensors(self, x, targets):
+        mask = targets['loss_mask'] if self.parameters['mask_loss'] else None
+        if self._conditional:
+            raise NotImplementedError("--conditional is outside the accelerated path")
+        if 'mvae' in self.parameters['model_name']:
+            if self.parameters['use_pose']:
+                if mask is not None:
+                    raise ValueError("--mask-loss with --use-pose cannot broadcast a (B,3,64,64) mask over (B,7) "
+                                     "poses; the reference fails here too (problems.py:446)")
+                return (x['model_input'] + x['input_object_pose'],
+                        targets['target_output'] + targets['target_object_pose'], None, None)
+            return x['model_input'], targets['target_output'], mask, None
+        return x['model_input'], targets['target_output'], mask, self.parameters['input_type']
 
     def _evaluate_model(self, x, targets, reduction='sum', reduce=None, **kwargs):
         """problems.py:683-716."""
