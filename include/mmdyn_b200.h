@@ -128,12 +128,14 @@ int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, 
 /* y = swish(a*x + b); ab == NULL means identity affine (plain Swish) */
 int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_per_group, int C,
                        void* stream);
-/* dU = dY * swish'(a*x+b) written over dY; sums2[g][c] = {sum dU, sum dU*xhat} (zeroed by caller).
- * ab == NULL: identity affine, no sums (dU is then already the gradient w.r.t. x). */
+/* pass 1 of the BN+Swish backward (read-only): with dU = dY * swish'(a*x+b),
+ * sums2[g][c] = {sum dU, sum dU*xhat} (zeroed by caller); dY is left untouched.
+ * ab == NULL: identity affine (plain Swish): dY := dY * swish'(x) in place, no sums. */
 int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const float* mean_invstd, void* dY,
                               float* sums2, int G, int rows_per_group, int C, void* stream);
-/* dX = a*(dU - mean(dU) - xhat*mean(dU*xhat)) in place over dU; dgamma += sum dU*xhat,
- * dbeta += sum dU (summed over groups, times grad_unscale); coef_scratch: [G][C][4] floats */
+/* pass 2: dX = a*(dU - mean(dU) - xhat*mean(dU*xhat)) written over dY (dU recomputed from dY and x);
+ * dgamma += sum dU*xhat, dbeta += sum dU (summed over groups, times grad_unscale);
+ * coef_scratch: [G][C][4] floats */
 int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
                        void* dU, float* dgamma, float* dbeta, float* coef_scratch, int G,
                        int rows_per_group, int C, float grad_unscale, void* stream);

@@ -194,10 +194,12 @@ bn_swish_fwd_rows_kernel(const __half* __restrict__ x, const float* __restrict__
   }
 }
 
-// dU = dY * swish'(a*x+b) in place; sums2[g][c] = {sum dU, sum dU * xhat}
+// BatchNorm+Swish backward, pass 1 of 2 (read-only): with dU = dY * swish'(a*x+b),
+// sums2[g][c] = {sum dU, sum dU * xhat}.  dU is NOT written back — pass 2 (bn_bwd_apply) recomputes it,
+// which trades 2 B/element of HBM writes for a second exp per element.
 __global__ void __launch_bounds__(RED_THREADS)
 bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
-                           const float* __restrict__ mean_invstd, __half* __restrict__ dY,
+                           const float* __restrict__ mean_invstd, const __half* __restrict__ dY,
                            float* __restrict__ sums2, int rows_per_group, int C, int rows_per_chunk) {
   extern __shared__ float red[];
   const int vpr = C >> 3;
@@ -206,60 +208,45 @@ bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict
   const int g = blockIdx.y;
   const int r_begin = blockIdx.x * rows_per_chunk;
   const int r_end = min(rows_per_group, r_begin + rows_per_chunk);
-  const long long gbase = static_cast<long long>(g) * rows_per_group * C;
-  float a[8], b[8], mean[8], invstd[8], s1[8], s2[8];
+  const long long gbase = static_cast<long long>(g) * rows_per_group * C + vec * 8;
+  float a[8], b[8], s1[8], s2[8];  // s2 accumulates sum dU * x; the xhat form follows from the totals
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = vec * 8 + i;
     a[i] = ab[(g * C + c) * 2];
     b[i] = ab[(g * C + c) * 2 + 1];
-    mean[i] = mean_invstd[(g * C + c) * 2];
-    invstd[i] = mean_invstd[(g * C + c) * 2 + 1];
     s1[i] = s2[i] = 0.0f;
   }
-  if (rl < row_lanes) {
-    for (int r = r_begin + rl; r < r_end; r += 2 * row_lanes) {
-      const int r2 = r + row_lanes;
-      const bool has2 = r2 < r_end;
-      const long long off = gbase + static_cast<long long>(r) * C + vec * 8;
-      const long long off2 = gbase + static_cast<long long>(r2) * C + vec * 8;
-      uint4 ux = __ldcs(reinterpret_cast<const uint4*>(x + off)), ud = *reinterpret_cast<const uint4*>(dY + off);
-      uint4 ux2 = ux, ud2 = ud;
-      if (has2) {
-        ux2 = __ldcs(reinterpret_cast<const uint4*>(x + off2));
-        ud2 = *reinterpret_cast<const uint4*>(dY + off2);
+  constexpr int U = 4;
+  for (int r = r_begin + rl; r < r_end; r += U * row_lanes) {
+    uint4 ux[U], ud[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (r + u * row_lanes < r_end) {
+        const long long off = gbase + static_cast<long long>(r + u * row_lanes) * C;
+        ux[u] = __ldg(reinterpret_cast<const uint4*>(x + off));
+        ud[u] = __ldg(reinterpret_cast<const uint4*>(dY + off));
       }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r + u * row_lanes >= r_end) continue;
       float fx[8], fd[8];
-      unpack8(ux, fx);
-      unpack8(ud, fd);
+      unpack8(ux[u], fx);
+      unpack8(ud[u], fd);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float u = fmaf(a[i], fx[i], b[i]);
-        const float du = fd[i] * swish_gradf_(u);
-        fd[i] = du;
+        const float du = fd[i] * swish_gradf_(fmaf(a[i], fx[i], b[i]));
         s1[i] += du;
-        s2[i] = fmaf(du, (fx[i] - mean[i]) * invstd[i], s2[i]);
-      }
-      *reinterpret_cast<uint4*>(dY + off) = pack8(fd);
-      if (has2) {
-        unpack8(ux2, fx);
-        unpack8(ud2, fd);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float u = fmaf(a[i], fx[i], b[i]);
-          const float du = fd[i] * swish_gradf_(u);
-          fd[i] = du;
-          s1[i] += du;
-          s2[i] = fmaf(du, (fx[i] - mean[i]) * invstd[i], s2[i]);
-        }
-        *reinterpret_cast<uint4*>(dY + off2) = pack8(fd);
+        s2[i] = fmaf(du, fx[i], s2[i]);
       }
     }
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red[(rl * C + vec * 8 + i) * 2] = s1[i];
-      red[(rl * C + vec * 8 + i) * 2 + 1] = s2[i];
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int c = vec * 8 + i;
+    const float mean = mean_invstd[(g * C + c) * 2], invstd = mean_invstd[(g * C + c) * 2 + 1];
+    red[(rl * C + c) * 2] = s1[i];
+    red[(rl * C + c) * 2 + 1] = (s2[i] - mean * s1[i]) * invstd;  // sum dU * (x - mean) * invstd
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < C * 2; idx += RED_THREADS) {
@@ -296,7 +283,7 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ ab, const float* __
   coef[4 * i] = a;
   coef[4 * i + 1] = -a * m2 * invstd;
   coef[4 * i + 2] = a * (m2 * invstd * mean - m1);
-  coef[4 * i + 3] = 0.0f;
+  coef[4 * i + 3] = ab[2 * i + 1];  // BatchNorm shift b (dU is recomputed from dY in the apply pass)
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
@@ -309,13 +296,14 @@ bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ coef
   const int r_begin = blockIdx.x * rows_per_chunk;
   const int r_end = min(rows_per_group, r_begin + rows_per_chunk);
   const long long gbase = static_cast<long long>(g) * rows_per_group * C + vec * 8;
-  float ka[8], kb[8], kc[8];
+  float ka[8], kb[8], kc[8], ks[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 k = *reinterpret_cast<const float4*>(coef + (static_cast<long long>(g) * C + vec * 8 + i) * 4);
     ka[i] = k.x;
     kb[i] = k.y;
     kc[i] = k.z;
+    ks[i] = k.w;
   }
   constexpr int U = 2;
   for (int r = r_begin + rl; r < r_end; r += U * row_lanes) {
@@ -334,7 +322,10 @@ bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ coef
       unpack8(ix[u], fx);
       unpack8(id[u], fd);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) fd[i] = fmaf(ka[i], fd[i], fmaf(kb[i], fx[i], kc[i]));
+      for (int i = 0; i < 8; ++i) {
+        const float du = fd[i] * swish_gradf_(fmaf(ka[i], fx[i], ks[i]));  // dU = dY * swish'(a*x + b)
+        fd[i] = fmaf(ka[i], du, fmaf(kb[i], fx[i], kc[i]));
+      }
       *reinterpret_cast<uint4*>(dU + gbase + static_cast<long long>(r + u * row_lanes) * C) = pack8(fd);
     }
   }
@@ -890,7 +881,7 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
   const int chunks = chunking(rows_per_group, G, C, &rpc);
   const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
   bn_swish_bwd_reduce_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
-      reinterpret_cast<const __half*>(x), ab, mean_invstd, reinterpret_cast<__half*>(dY), sums2,
+      reinterpret_cast<const __half*>(x), ab, mean_invstd, reinterpret_cast<const __half*>(dY), sums2,
       rows_per_group, C, rpc);
   LAUNCHED();
   return MMDYN_OK;

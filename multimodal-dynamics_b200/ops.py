@@ -161,7 +161,7 @@ def bn_swish_fwd(x, ab, y, G, rows, Cch):
 
 
 def bn_swish_bwd_reduce(x, ab, mean_invstd, dY, sums2, G, rows, Cch):
-    with _Timed("bn_swish_bwd_reduce", lambda: (0.0, G * rows * Cch * 6.0)):
+    with _Timed("bn_swish_bwd_reduce", lambda: (0.0, G * rows * Cch * (4.0 if ab is not None else 6.0))):
         check(_L().mmdyn_bn_swish_bwd_reduce(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(dY), _ptr(sums2), G, rows,
                                              Cch, _stream()), "bn_swish_bwd_reduce")
 
