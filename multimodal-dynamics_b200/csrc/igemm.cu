@@ -1244,6 +1244,17 @@ int igemm_init() {
   SET_WG(128);
   SET_WG(256);
 #undef SET_WG
+  // cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports these kernels (it returned <= 1 for every
+  // variant on B200 although ncu shows a shared-memory limit of 2-3 CTAs), so the persistent grids
+  // are sized from the resources directly: 228 KB shared memory per SM, 1 KB reserved per CTA.
+  const int smem_dyn[5] = {Cfg<16>::SMEM_BYTES, Cfg<32>::SMEM_BYTES, Cfg<64>::SMEM_BYTES, Cfg<128>::SMEM_BYTES,
+                           Cfg<256>::SMEM_BYTES};
+  for (int i = 0; i < 5; ++i) {
+    const int by_smem_tma = (228 * 1024) / (smem_dyn[i] + 1024 + 256);
+    const int by_smem_cpa = (228 * 1024) / (smem_dyn[i] + 1024 + 4608);
+    g_tma_occ[i] = by_smem_tma < 1 ? 1 : (by_smem_tma > 8 ? 8 : by_smem_tma);
+    g_igemm_occ[i] = by_smem_cpa < 1 ? 1 : (by_smem_cpa > 6 ? 6 : by_smem_cpa);
+  }
   // TMEM: 512 columns per SM, two accumulator stages per CTA
   const int cols[5] = {64, 64, 128, 256, 512};
   for (int i = 0; i < 5; ++i) {
@@ -1388,6 +1399,12 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     case 128: return launch_igemm<128>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[3], st);
     default: return launch_igemm<256>(d, tm, m_tiles, n_tiles, total, g_igemm_occ[4], st);
   }
+}
+
+// diagnostics (not part of the public header): resident-CTA estimates used to size persistent grids
+extern "C" int mmdyn_debug_occ(int which, int idx) {
+  if (idx < 0 || idx > 4) return -1;
+  return which == 0 ? g_igemm_occ[idx] : (which == 1 ? g_tma_occ[idx] : g_sm_count);
 }
 
 extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
