@@ -121,7 +121,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     sample_B = min(args.batch, 128)
-    times = cpu_steps(sample_B, args.steps, min(args.warmup, 2), threads)
+    # ~0.4 s per 128-sample step on 16 cores: cap the timed steps so the arm ends within ~2 minutes
+    times = cpu_steps(sample_B, min(args.steps, 40), min(args.warmup, 2), threads)
     tot = sum(times)
     v = sample_B * len(times) / tot
     sample = f"{len(times)} steps x {sample_B} samples of the same 7-pass cnn-mvae+pose step (fp32, torch CPU ops)"
@@ -365,8 +366,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=int(os.environ.get("MMDYN_BENCH_BATCH", 1024)),
                     help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
