@@ -127,8 +127,8 @@ def run_reference(args):
     v = sample_B * len(times) / tot
     sample = f"{len(times)} steps x {sample_B} samples of the same 7-pass cnn-mvae+pose step (fp32, torch CPU ops)"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.batch),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -331,6 +331,14 @@ def run_b200(args):
             ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
             roof = dict(common, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
                         peak_source=pk["src"])
+        try:  # DRAM traffic of the dominant kernel from the committed ncu capture (same batch only)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tr.get("batch") == B and top_tag in tr:
+                roof["traffic"] = tr[top_tag]["traffic_bytes_largest_launch"]
+                roof["traffic_note"] = ("largest launch of this kernel, ncu --set full; algorithmic bytes of that launch: %d"
+                                        % tr[top_tag]["algorithmic_bytes_largest_launch"])
+        except Exception:
+            pass
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 json.dump({"batch": B, "ms_per_step_events_sum": tot_ms, "kernels": table}, f, indent=1)
