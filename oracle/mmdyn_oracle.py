@@ -98,9 +98,11 @@ def decoder_cnn(sd, p, z, track=True, acts=None):
     h = F.conv_transpose2d(h, sd[p + ".hallucinate.0.weight"], stride=1, padding=0)
     rec("deconv1", h)
     h = swish(_bn_train(h, sd, p + ".hallucinate.1", track))
+    rec("act_d1", h)
     h = F.conv_transpose2d(h, sd[p + ".hallucinate.3.weight"], stride=2, padding=1)
     rec("deconv2", h)
     h = swish(_bn_train(h, sd, p + ".hallucinate.4", track))
+    rec("act_d2", h)
     h = F.conv_transpose2d(h, sd[p + ".hallucinate.6.weight"], stride=2, padding=1)
     rec("deconv3", h)
     h = swish(_bn_train(h, sd, p + ".hallucinate.7", track))
@@ -150,6 +152,8 @@ def vae_forward(sd, x, noise, track=True, acts=None):
     mask, eps = noise
     mu, lv = encoder_cnn(sd, "encoder", x, mask, track, acts)
     z = reparametrize(mu, lv, eps)
+    if acts is not None:
+        acts["z"] = z
     return decoder_cnn(sd, "decoder", z, track, acts), mu, lv
 
 

@@ -239,3 +239,52 @@ def test_product_of_experts_module_matches_reference_formula():
     m_o, l_o = orc.product_of_experts(mu.double(), lv.double())
     m_d, l_d = ProductOfExperts()(mu.to(DEV), lv.to(DEV))
     assert nrel(m_d, m_o) < 1e-5 and nrel(l_d, l_o) < 1e-5
+
+
+def test_layers_in_isolation():
+    """Per-layer parity at the stated 1e-3 (norm-wise): every tensor-core layer of the model is fed the
+    ORACLE's fp32 input activation of that layer (so errors do not compound) with the model's real
+    weights, and compared with the oracle's output of the same layer."""
+    from mmdyn_b200 import engine, ops
+    B = 6
+    model, sd = make("cnn-vae", seed=4)
+    d = batch(B, seed=6)
+    g = torch.Generator().manual_seed(3)
+    _, _, eps = orc.draw_pass_noise(B, False, False, generator=g)
+    acts = {}
+    orc.vae_forward(copy.deepcopy(sd), d["v"], (None, eps), track=False, acts=acts)
+    arena, ex = engine.get_execs(model, torch.device(DEV))
+    enc, dec = ex["enc"]["encoder"], ex["dec"]["decoder"]
+    enc.refresh()
+
+    def nhwc16(t):
+        return t.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+
+    def run(pl, a_in, out_shape, bias=None, dtype=torch.float16):
+        out = torch.zeros(out_shape, dtype=dtype, device=DEV)
+        ops.igemm(pl.lp.fwd, a_in, pl.Wf, out, B, bias=bias, out_mode=1 if dtype == torch.float32 and pl.lp.fwd.out_mode == 0 else None)
+        torch.cuda.synchronize()
+        return out
+
+    errs = {}
+    e = "encoder."
+    raw1 = torch.zeros(B, 32, 32, 32, dtype=torch.float16, device=DEV)
+    ops.conv1_fwd(d["v"].to(DEV), enc.c1.Wf, raw1, B)
+    errs["conv1"] = nrel(nchw(raw1), acts[e + "conv1"])
+    errs["conv2"] = nrel(nchw(run(enc.c2, nhwc16(orc.swish(acts[e + "conv1"])), (B, 16, 16, 64))), acts[e + "conv2"])
+    errs["conv3"] = nrel(nchw(run(enc.c3, nhwc16(acts[e + "act2"]), (B, 8, 8, 128))), acts[e + "conv3"])
+    errs["conv4"] = nrel(nchw(run(enc.c4, nhwc16(acts[e + "act3"]), (B, 5, 5, 256))), acts[e + "conv4"])
+    fc = run(enc.fc, nhwc16(acts[e + "act4"]).reshape(B, 6400), (B, 512), bias=enc.fc.bias, dtype=torch.float32)
+    errs["fc"] = nrel(orc.swish(fc.cpu()), acts[e + "fc"])
+    heads = run(enc.heads, acts[e + "fc"].half().to(DEV), (B, 512), bias=enc.heads.bias, dtype=torch.float32)
+    errs["heads"] = nrel(heads, torch.cat([acts[e + "mu"], acts[e + "lv"]], 1))
+    dd = "decoder."
+    up = run(dec.up, acts["z"].half().to(DEV), (B, 5, 5, 256), bias=dec.up.bias)
+    errs["upsample"] = nrel(orc.swish(nchw(up).float().cpu()), acts[dd + "up"])
+    errs["deconv1"] = nrel(nchw(run(dec.d1, nhwc16(acts[dd + "up"]), (B, 8, 8, 128))), acts[dd + "deconv1"])
+    errs["deconv2"] = nrel(nchw(run(dec.d2, nhwc16(acts[dd + "act_d1"]), (B, 16, 16, 64))), acts[dd + "deconv2"])
+    errs["deconv3"] = nrel(nchw(run(dec.d3, nhwc16(acts[dd + "act_d2"]), (B, 32, 32, 32))), acts[dd + "deconv3"])
+    errs["deconv4"] = nrel(run(dec.d4, nhwc16(acts[dd + "act_d3"]), (B, 3, 64, 64), dtype=torch.float32), acts[dd + "logits"])
+    print("\n".join(f"isolated {k:10s} {v:.3e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < 1e-3, (k, v)
