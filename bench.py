@@ -196,14 +196,33 @@ def run_b200(args):
 
     use_graph = not args.no_graph
     gstep = None
+    dp_mode = "single" if world == 1 else ("eager: bucketed all-reduce overlapped with backward" if args.no_graph else "")
     if use_graph:
-        gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw, split_optimizer=world > 1)
+        if world > 1 and args.nccl_in_graph:
+            # experimental: capture the bucketed NCCL all-reduces inside the step graph.  On this stack
+            # (torch 2.11 / NCCL 2.28.9) the capture HANGS (measured in round 1, 2 GPUs), so the
+            # default for data parallelism is the split scheme below.
+            try:
+                sync_in_graph = parallel.attach(eng, opt, arena, overlap=True)
+                gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw,
+                                                grad_sync=sync_in_graph)
+                dp_mode = "one graph: bucketed all-reduce captured, overlapped with backward"
+            except Exception as e:  # noqa: BLE001 - fall back to the split-graph scheme below
+                if rank == 0:
+                    print(f"[bench] NCCL capture failed ({type(e).__name__}: {e}); using split graphs", file=sys.stderr)
+                eng.bucket_hook = None
+                gstep = None
+        if gstep is None:
+            gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw, split_optimizer=world > 1)
+            if world > 1:
+                dp_mode = "backward graph + flat all-reduce + optimizer graph"
+    in_graph_sync = gstep is not None and gstep.sync is not None
 
     def step_resident(i):
         x, t = dev_batches[i % 3]
         if gstep is not None:
             gstep.run()  # inputs already resident in the graph's static device buffers
-            if world > 1:
+            if world > 1 and not in_graph_sync:
                 sync_grads()
                 gstep.apply()
             return gstep.loss
@@ -248,7 +267,7 @@ def run_b200(args):
             gstep.load(xs, ts)
             consumed_evt[slot].record(cur)
             gstep.run()
-            if world > 1:
+            if world > 1 and not in_graph_sync:
                 sync_grads()
                 gstep.apply()
             l = gstep.loss
@@ -360,7 +379,7 @@ def run_b200(args):
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
-            "cuda_graph": bool(use_graph), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "cuda_graph": bool(use_graph), "data_parallel_mode": dp_mode, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
             "step_tflops": value * FLOP_PER_SAMPLE / 1e12 / world,
             "step_frac_of_tensor_peak": value * FLOP_PER_SAMPLE / 1e12 / world / pk["tf_sust"],
             "final_loss": final_loss, "top_kernels": table[:6],
@@ -380,6 +399,8 @@ def main():
                     help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nccl-in-graph", action="store_true",
+                    help="experimental: capture NCCL inside the step graph (hangs on torch 2.11 / NCCL 2.28.9)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here (JSON)")
     args = ap.parse_args()

@@ -986,9 +986,14 @@ class GraphedTrainStep:
     gradient arena and then calls `apply()`, a second graph holding the optimizer update."""
 
     def __init__(self, step_engine, optimizer, example_x, example_t, kl_weight, loss_mask=None, split_optimizer=False,
-                 warmup=2):
+                 warmup=2, grad_sync=None):
+        """grad_sync: a parallel.GradSync whose bucketed NCCL all-reduces are captured INSIDE the graph
+        (launched from the backward on a side stream, overlapping the encoder backward); the
+        alternative for data parallelism is split_optimizer=True (backward graph, eager all-reduce,
+        optimizer graph)."""
         self.eng, self.opt, self.klw = step_engine, optimizer, float(kl_weight)
         self.split = split_optimizer
+        self.sync = grad_sync
         lst = isinstance(example_x, (list, tuple))
         self.x = [t.clone() for t in example_x] if lst else example_x.clone()
         self.t = [t.clone() for t in example_t] if lst else example_t.clone()
@@ -1014,8 +1019,12 @@ class GraphedTrainStep:
 
     def _body(self, with_opt):
         self.opt.zero_grad()
+        if self.sync is not None:
+            self.sync.begin()
         outputs, loss = self.eng.evaluate(self.x, self.t, self.klw, loss_mask=self.mask, need_grad=True, autograd=False)
         self.eng.backward()
+        if self.sync is not None:
+            self.sync.finish()
         if with_opt:
             self.opt.step()
         return outputs, loss
