@@ -174,6 +174,17 @@ int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_expe
  * as the reference does.  logits/target: NCHW fp32 (n,3,H,W). */
 int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
                      void* dlogits_nhwc8, float gscale, int n, int HW, void* stream);
+/* Same loss for callers outside the fused step (Reconstruction._elbo_loss / _mvae_elbo_loss called
+ * on their own, problems.py:401-458, and the per-sample scoring path reduce=False, :415-417, :451-456):
+ * logits / target / mask are flat fp32 [n][per_sample] in any (identical) layout; loss_sum[0] += total,
+ * per_sample_sum[i] += loss of sample i (nullable), dlogits (nullable, fp32, same layout) =
+ * gscale * (sigmoid(x*m) - t*m) * m. */
+int mmdyn_bce_logits_flat(const float* logits, const float* target, const float* mask, float* loss_sum,
+                          float* per_sample_sum, float* dlogits, float gscale, int n, int per_sample,
+                          void* stream);
+/* row-wise squared error of [n][d] fp32 matrices: row_sum[i] += mult * sum_j (r-t)^2 */
+int mmdyn_mse_rows(const float* recon, const float* target, float* row_sum, float mult, int n, int d,
+                   void* stream);
 /* MSE 'sum' * multiplier for the pose vectors: loss_sum += mult*sum (r-t)^2; dr = gscale*2*mult*(r-t) */
 int mmdyn_mse(const float* recon, const float* target, float* loss_sum, float* drecon, float mult,
               float gscale, int n, void* stream);

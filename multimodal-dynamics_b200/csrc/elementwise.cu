@@ -560,6 +560,39 @@ bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ ta
   if (threadIdx.x == 0) atomicAdd(loss_sum, t);
 }
 
+// generic-layout BCE-with-logits: grid = (chunks, n samples); per-sample and total sums, fp32 gradient
+__global__ void __launch_bounds__(256)
+bce_flat_kernel(const float* __restrict__ logits, const float* __restrict__ target, const float* __restrict__ mask,
+                float* __restrict__ loss_sum, float* __restrict__ per_sample_sum, float* __restrict__ dlogits,
+                float gscale, int per_sample) {
+  const long long base = static_cast<long long>(blockIdx.y) * per_sample;
+  float acc = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
+    float m = mask ? mask[base + i] : 1.0f;
+    const float x = logits[base + i] * m, t = target[base + i] * m;
+    const float e = expf(-fabsf(x));
+    acc += fmaxf(x, 0.0f) - x * t + log1pf(e);
+    if (dlogits) dlogits[base + i] = gscale * ((x >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e)) - t) * m;
+  }
+  const float t = block_sum_256(acc);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_sum, t);
+    if (per_sample_sum) atomicAdd(per_sample_sum + blockIdx.y, t);
+  }
+}
+
+__global__ void mse_rows_kernel(const float* __restrict__ recon, const float* __restrict__ target,
+                                float* __restrict__ row_sum, float mult, int n, int d) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float acc = 0.0f;
+  for (int j = 0; j < d; ++j) {
+    const float df = recon[static_cast<long long>(r) * d + j] - target[static_cast<long long>(r) * d + j];
+    acc = fmaf(df, df, acc);
+  }
+  row_sum[r] += mult * acc;
+}
+
 __global__ void __launch_bounds__(256)
 mse_kernel(const float* __restrict__ recon, const float* __restrict__ target, float* __restrict__ loss_sum,
            float* __restrict__ drecon, float mult, float gscale, long long n) {
@@ -984,6 +1017,28 @@ extern "C" int mmdyn_bce_logits(const float* logits, const float* target, const 
   bce_logits_kernel<<<grid_for(n_pix >> 2), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum,
                                                              reinterpret_cast<__half*>(dlogits_nhwc8), gscale,
                                                              n_pix, HW);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bce_logits_flat(const float* logits, const float* target, const float* mask, float* loss_sum,
+                                     float* per_sample_sum, float* dlogits, float gscale, int n, int per_sample,
+                                     void* stream) {
+  MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && per_sample > 0, "bce_logits_flat: bad arguments");
+  int chunks = (148 * 8 + n - 1) / n;
+  const int max_chunks = (per_sample + 1023) / 1024;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  bce_flat_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum, per_sample_sum, dlogits,
+                                                           gscale, per_sample);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_mse_rows(const float* recon, const float* target, float* row_sum, float mult, int n, int d,
+                              void* stream) {
+  MMDYN_REQUIRE(recon && target && row_sum && n > 0 && d > 0, "mse_rows: bad arguments");
+  mse_rows_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(recon, target, row_sum, mult, n, d);
   LAUNCHED();
   return MMDYN_OK;
 }

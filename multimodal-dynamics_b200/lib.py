@@ -71,6 +71,8 @@ SIGNATURES = {
                        _I, _I, _I, _I, _P], _I),
     "mmdyn_bce_logits": ([_P, _P, _P, _P, _P, _F, _I, _I, _P], _I),
     "mmdyn_mse": ([_P, _P, _P, _P, _F, _F, _I, _P], _I),
+    "mmdyn_bce_logits_flat": ([_P, _P, _P, _P, _P, _P, _F, _I, _I, _P], _I),
+    "mmdyn_mse_rows": ([_P, _P, _P, _F, _I, _I, _P], _I),
     "mmdyn_linear_f32_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "mmdyn_linear_f32_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P], _I),
     "mmdyn_colsum_f32": ([_P, _P, _I, _I, _I, _F, _P], _I),

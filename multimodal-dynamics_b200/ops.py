@@ -209,6 +209,17 @@ def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, HW):
                                     HW, _stream()), "bce_logits")
 
 
+def bce_logits_flat(logits, target, mask, loss_sum, per_sample_sum, dlogits, gscale, n, per_sample):
+    with _Timed("bce_logits_flat", None):
+        check(_L().mmdyn_bce_logits_flat(_ptr(logits), _ptr(target), _ptr(mask), _ptr(loss_sum), _ptr(per_sample_sum),
+                                         _ptr(dlogits), gscale, n, per_sample, _stream()), "bce_logits_flat")
+
+
+def mse_rows(recon, target, row_sum, mult, n, d):
+    with _Timed("mse_rows", None):
+        check(_L().mmdyn_mse_rows(_ptr(recon), _ptr(target), _ptr(row_sum), mult, n, d, _stream()), "mse_rows")
+
+
 def mse(recon, target, loss_sum, drecon, mult, gscale, n):
     with _Timed("mse", None):
         check(_L().mmdyn_mse(_ptr(recon), _ptr(target), _ptr(loss_sum), _ptr(drecon), mult, gscale, n, _stream()), "mse")

@@ -24,7 +24,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from mmdyn_b200 import engine, optim as fused_optim
+from mmdyn_b200 import engine, losses, optim as fused_optim
 from mmdyn_b200.pytorch import config
 from mmdyn_b200.pytorch.models.models import setup_model
 from mmdyn_b200.pytorch.utils.datasets import dataset_setup
@@ -257,13 +257,65 @@ class Reconstruction(Problem):
     def set_criterion(self):
         self._criterion = self._mvae_elbo_loss if 'mvae' in self.parameters['model_name'] else self._elbo_loss
 
-    # The two ELBO entry points of the reference (problems.py:401-458) exist for callers that hold
-    # reconstructions already; inside this package the loss is fused into the step (StepEngine).
     def _elbo_loss(self, recon_x, x, means, log_var, loss_mask=None, reduce=None, reduction='sum'):
-        raise NotImplementedError("the ELBO is computed inside the fused step: use _evaluate_model()")
+        """problems.py:401-419 (VAE / CVAE) for callers that hold a reconstruction already; inside this
+        package the same terms are fused into the step (StepEngine).  reduce=False -> per-sample scores."""
+        if reduction != 'sum' or reduce not in (None, False):
+            raise NotImplementedError("only reduction='sum' (training) and reduce=False (per-sample scoring)")
+        kld = losses.kl_divergence(means, log_var)
+        logits = recon_x.view(x.size())
+        if reduce is False:
+            return losses.bce_with_logits_per_sample(logits, x, loss_mask) + self._kl_weight * kld
+        bce = losses.bce_with_logits_sum(logits, x, loss_mask)
+        return (bce + self._kl_weight * kld) / x.size(0)
 
     def _mvae_elbo_loss(self, recon_x, x, means, log_var, loss_mask=None, reduce=None, reduction='sum'):
-        raise NotImplementedError("the ELBO is computed inside the fused step: use _evaluate_model()")
+        """problems.py:421-458: images -> BCE-with-logits (sum), vectors -> MSE (sum) x pose_multiplier."""
+        assert len(recon_x) == len(x)
+        if reduction != 'sum' or reduce not in (None, False):
+            raise NotImplementedError("only reduction='sum' (training) and reduce=False (per-sample scoring)")
+        kld = losses.kl_divergence(means, log_var)
+        err = 0
+        for r, t in zip(recon_x, x):
+            if r.dim() > 2:
+                r = r.view(t.size())
+                e = losses.bce_with_logits_per_sample(r, t, loss_mask) if reduce is False else \
+                    losses.bce_with_logits_sum(r, t, loss_mask)
+            else:
+                if loss_mask is not None:
+                    raise ValueError("a (B,3,64,64) loss mask cannot broadcast over (B,7) poses; the reference "
+                                     "fails here too (problems.py:446)")
+                e = losses.mse_per_sample(r, t, self._pose_multiplier) if reduce is False else \
+                    self._pose_multiplier * losses.mse_sum(r, t)
+            err = err + e
+        if reduce is False:
+            return err + self._kl_weight * kld
+        return (err + self._kl_weight * kld) / x[0].size(0)
+
+    def _evaluate_mvae_passes(self, x, targets, loss_mask=None, reduce=None, reduction='sum'):
+        """The sub-sampled objective pass by pass through the module-level API, exactly as the reference
+        spells it (problems.py:473-546).  Used for the per-sample scoring variant (reduce=False) and as
+        an independent cross-check of the fused step; training uses the fused StepEngine."""
+        m, up = self._model, self.parameters['use_pose']
+        tv, tt = targets[0], targets[1]
+        vj, tj, _, mu, lv = m([x[0], x[1]])
+        loss = self._mvae_elbo_loss([vj, tj], [tv, tt], mu, lv, loss_mask, reduce, reduction)
+        v1, _, _, mu, lv = m([x[0], None])
+        loss = loss + self._mvae_elbo_loss([v1], [tv], mu, lv, loss_mask, reduce, reduction)
+        _, t1, _, mu, lv = m([None, x[1]])
+        loss = loss + self._mvae_elbo_loss([t1], [tt], mu, lv, loss_mask, reduce, reduction)
+        rec = [vj, tj]
+        if up:
+            vj, tj, pj, mu, lv = m([x[0], x[1]], pose=x[2])
+            loss = loss + self._mvae_elbo_loss([vj, tj, pj], [tv, tt, targets[2]], mu, lv, loss_mask, reduce, reduction)
+            v2, _, p2, mu, lv = m([x[0], None], pose=x[2])
+            loss = loss + self._mvae_elbo_loss([v2, p2], [tv, targets[2]], mu, lv, loss_mask, reduce, reduction)
+            _, t2, p3, mu, lv = m([None, x[1]], pose=x[2])
+            loss = loss + self._mvae_elbo_loss([t2, p3], [tt, targets[2]], mu, lv, loss_mask, reduce, reduction)
+            _, _, p4, mu, lv = m([None, None], pose=x[2])
+            loss = loss + self._mvae_elbo_loss([p4], [targets[2]], mu, lv, loss_mask, reduce, reduction)
+            rec = [vj, tj, pj]
+        return {'recon_x': rec, 'means': mu, 'log_var': lv}, loss
 
     use_cuda_graph = True  # replay the whole training step as one CUDA graph when the noise source allows it
 
@@ -317,10 +369,10 @@ class Reconstruction(Problem):
     def _evaluate_mvae(self, x, targets, loss_mask=None, reduce=None, reduction='sum', condition=None):
         """problems.py:473-546 as one fused step (3 passes, or 7 with --use-pose)."""
         assert isinstance(x, list) and isinstance(targets, list)
-        if reduce is not None or reduction != 'sum':
-            raise NotImplementedError("per-sample ELBO scoring (reduce != None) is a 'next' row (SURVEY.md §8f)")
         if condition is not None:
             raise NotImplementedError("--conditional is outside the accelerated path")
+        if reduce is not None or reduction != 'sum':
+            return self._evaluate_mvae_passes(x, targets, loss_mask, reduce, reduction)
         return self._get_engine().evaluate(x, targets, self._kl_weight, loss_mask=loss_mask)
 
     def _sample(self, n=50):
@@ -441,7 +493,10 @@ class SeqModeling(Reconstruction, Problem):
             return self._evaluate_mvae(x=x['model_input'], targets=targets['target_output'], loss_mask=loss_mask,
                                        reduce=reduce, reduction=reduction)
         if reduce is not None or reduction != 'sum':
-            raise NotImplementedError("per-sample ELBO scoring (reduce != None) is a 'next' row (SURVEY.md §8f)")
+            recon_x, means, log_var = self._model(x['model_input'])
+            loss = self._elbo_loss(recon_x, targets['target_output'], means, log_var, loss_mask=loss_mask,
+                                   reduce=reduce, reduction=reduction)
+            return {'recon_x': recon_x, 'means': means, 'log_var': log_var}, loss
         outputs, loss = self._get_engine().evaluate(x['model_input'], targets['target_output'], self._kl_weight,
                                                     loss_mask=loss_mask)
         outputs['perf_measure'] = {self.parameters['input_type']: outputs['perf_measure']['x']}

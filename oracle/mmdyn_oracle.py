@@ -217,6 +217,23 @@ def mvae_elbo_loss(recons, targets, mu, lv, kl_weight, pose_multiplier, loss_mas
     return (err + kl_weight * kl_divergence(mu, lv)) / B
 
 
+def mvae_elbo_per_sample(recons, targets, mu, lv, kl_weight, pose_multiplier, loss_mask=None):
+    """Reconstruction._mvae_elbo_loss with reduce=False (problems.py:445-456): element-wise losses summed
+    per sample; the KL term stays the batch TOTAL and is added to every sample (reference behaviour)."""
+    err = 0
+    for r, t in zip(recons, targets):
+        if r.dim() > 2:
+            r = r.view(t.size())
+            if loss_mask is not None:
+                e = F.binary_cross_entropy_with_logits(r * loss_mask, t * loss_mask, reduction="none").sum((1, 2, 3))
+            else:
+                e = F.binary_cross_entropy_with_logits(r, t, reduction="none").sum((1, 2, 3))
+        else:
+            e = pose_multiplier * F.mse_loss(r, t, reduction="none").sum(1)
+        err = err + e
+    return err + kl_weight * kl_divergence(mu, lv)
+
+
 MVAE_PASSES_NOPOSE = [(True, True, False), (True, False, False), (False, True, False)]
 MVAE_PASSES_POSE = MVAE_PASSES_NOPOSE + [(True, True, True), (True, False, True), (False, True, True),
                                          (False, False, True)]

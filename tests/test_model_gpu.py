@@ -288,3 +288,100 @@ def test_layers_in_isolation():
     print("\n".join(f"isolated {k:10s} {v:.3e}" for k, v in errs.items()))
     for k, v in errs.items():
         assert v < 1e-3, (k, v)
+
+
+def _dataset_free_problem(model, use_pose, klw=0.02):
+    from mmdyn_b200.pytorch.problems import problems
+    pr = object.__new__(problems.SeqModeling)
+    pr.parameters = {"model_name": "cnn-mvae", "input_type": "visuotactile", "use_pose": use_pose, "mask_loss": False}
+    pr._kl_weight, pr._pose_multiplier, pr._conditional = klw, 1000.0, False
+    pr._model, pr._cross_modal, pr._engine = model, True, None
+    return pr
+
+
+def test_elbo_entry_points_and_pass_loop_match_oracle_and_fused_step():
+    """Reconstruction._mvae_elbo_loss / _elbo_loss called on their own (problems.py:401-458), the
+    pass-by-pass evaluator built on them, the per-sample scoring path (reduce=False) and the fused
+    step all agree with the oracle on the same weights / inputs / noise."""
+    from mmdyn_b200 import noise
+    B, klw = 4, 0.02
+    model, sd = make("cnn-mvae", True, seed=5)
+    d = batch(B, seed=8)
+    x_o, t_o = [d["v"], d["t"], d["p"]], [d["tv"], d["tt"], d["tp"]]
+    x_d, t_d = [a.to(DEV) for a in x_o], [a.to(DEV) for a in t_o]
+    out_o, loss_o, per_pass = orc.evaluate_mvae(copy.deepcopy(sd), x_o, t_o, klw, 1000.0, True,
+                                                oracle_noises(orc.MVAE_PASSES_POSE, B, 21))
+    pr = _dataset_free_problem(model, True, klw)
+    # (a) pass loop through the module-level API + stand-alone loss kernels, with autograd
+    model.noise = noise.HostNoise(torch.Generator().manual_seed(21))
+    out_p, loss_p = pr._evaluate_mvae_passes(x_d, t_d)
+    assert abs(loss_p.item() - loss_o.item()) / loss_o.item() < 1e-4
+    loss_p.backward()
+    g_pass = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    # (b) fused step on the same noise
+    for p in model.parameters():
+        p.grad = None
+    model.noise = noise.HostNoise(torch.Generator().manual_seed(21))
+    out_f, loss_f = pr._evaluate_model({"model_input": x_d[:2], "input_object_pose": [x_d[2]]},
+                                       {"target_output": t_d[:2], "target_object_pose": [t_d[2]], "loss_mask": None})
+    assert abs(loss_f.item() - loss_p.item()) / loss_p.item() < 1e-5
+    loss_f.backward()
+    torch.cuda.synchronize()
+    num = sum((p.grad - g_pass[k]).double().pow(2).sum().item() for k, p in model.named_parameters())
+    den = sum(g_pass[k].double().pow(2).sum().item() for k in g_pass)
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5  # two independent backward implementations
+    # (c) per-sample scoring, reduce=False
+    with torch.no_grad():
+        model.noise = noise.HostNoise(torch.Generator().manual_seed(21))
+        _, score = pr._evaluate_mvae_passes(x_d, t_d, reduce=False)
+    ref = 0
+    for (hv, ht, hp), pp in zip(orc.MVAE_PASSES_POSE, per_pass):
+        recs = ([pp["v_rec"]] if hv else []) + ([pp["t_rec"]] if ht else []) + ([pp["p_rec"]] if hp else [])
+        tgts = ([t_o[0]] if hv else []) + ([t_o[1]] if ht else []) + ([t_o[2]] if hp else [])
+        ref = ref + orc.mvae_elbo_per_sample(recs, tgts, pp["mu"], pp["lv"], klw, 1000.0)
+    assert score.shape == (B,) and nrel(score, ref) < 1e-4
+    # (d) VAE entry point with a loss mask
+    recon, mu, lv = torch.randn(B, 3, 64, 64, device=DEV), torch.randn(B, 256, device=DEV), torch.randn(B, 256, device=DEV) * 0.3
+    mask = (torch.rand(B, 3, 64, 64, device=DEV) > 0.5).float()
+    got = pr._elbo_loss(recon, t_d[0], mu, lv, loss_mask=mask)
+    want = orc.elbo_loss(recon.cpu(), t_o[0], mu.cpu(), lv.cpu(), klw, mask.cpu())
+    assert abs(got.item() - want.item()) / abs(want.item()) < 1e-5
+
+
+def test_data_parallel_semantics_on_one_gpu():
+    """Parity definition of the data-parallel path: N ranks == the oracle run on each
+    shard with identical weights, gradients averaged.  Emulated on one GPU: two shards through the fused
+    step, gradients summed in the arena, `grad_prescale = 1/2` in the fused Adam."""
+    from mmdyn_b200 import engine, noise, optim, parallel
+    B, klw = 8, 0.02
+    model, sd = make("cnn-mvae", False, seed=9)
+    d = batch(B, seed=2)
+    pkeys = [k for k, _ in model.named_parameters()]
+    shards = [parallel.shard_rows(B, 2, r) for r in range(2)]
+    assert shards == [(0, 4), (4, 8)]
+    grads_o = None
+    for r, (a, b) in enumerate(shards):
+        sd_o = copy.deepcopy(sd)
+        for k in pkeys:
+            sd_o[k].requires_grad_(True)
+        _, loss_o, _ = orc.evaluate_mvae(sd_o, [d["v"][a:b], d["t"][a:b]], [d["tv"][a:b], d["tt"][a:b]], klw, 1000.0,
+                                         False, oracle_noises(orc.MVAE_PASSES_NOPOSE, b - a, 30 + r))
+        loss_o.backward()
+        g = [sd_o[k].grad.clone() for k in pkeys]
+        grads_o = g if grads_o is None else [x + y for x, y in zip(grads_o, g)]
+    grads_o = [g / 2 for g in grads_o]
+    opt = optim.FusedAdam(model, lr=1e-3)
+    opt.grad_prescale = 0.5
+    opt.zero_grad()
+    for r, (a, b) in enumerate(shards):
+        eng = engine.StepEngine(model, "mvae", noise_src=noise.HostNoise(torch.Generator().manual_seed(30 + r)))
+        _, loss = eng.evaluate([d["v"][a:b].to(DEV), d["t"][a:b].to(DEV)], [d["tv"][a:b].to(DEV), d["tt"][a:b].to(DEV)], klw)
+        loss.backward()  # accumulates into the gradient arena (the all-reduce SUM of a 2-rank job)
+    torch.cuda.synchronize()
+    flat_d = torch.cat([0.5 * p.grad.reshape(-1) for _, p in model.named_parameters()])
+    flat_o = torch.cat([g.reshape(-1) for g in grads_o])
+    assert nrel(flat_d, flat_o) < 5e-3, nrel(flat_d, flat_o)
+    before = torch.cat([p.detach().reshape(-1).clone() for p in model.parameters()])
+    opt.step()
+    after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert torch.isfinite(after).all() and (after - before).abs().max().item() <= 1.0001e-3  # |lr * m/sqrt(v)| <= lr
