@@ -77,6 +77,11 @@ typedef struct mmdyn_igemm_desc {
   int32_t s_out;
   int32_t off_y[MMDYN_MAX_PHASES], off_x[MMDYN_MAX_PHASES];
   int32_t ldc;          /* elements between consecutive output pixels                          */
+  int32_t a_row_stride; /* elements between input rows; 0 = dense (a_pix_stride*IW)             */
+  int32_t a_img_stride; /* elements between images of A; 0 = dense (row stride * IH).  With
+                           a_pix_stride < Cin the "pixels" overlap: a window of Cin/a_pix_stride
+                           physical pixels is one tap (used by the 3-channel logits layer, whose
+                           4 x-taps of 8 padded channels are one 64-byte window; TMA path only)   */
 } mmdyn_igemm_desc;
 int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream);
 
@@ -100,6 +105,8 @@ typedef struct mmdyn_wgrad_desc {
   int32_t ldw;          /* row pitch of dW in elements (>= ntaps*Cg)                           */
   int32_t row_splits;   /* CTAs along the reduction                                            */
   float scale;
+  int32_t g_row_stride; /* elements between rows / images of G; 0 = dense.  Same overlapping-   */
+  int32_t g_img_stride; /* window convention as mmdyn_igemm_desc (TMA path only)                */
 } mmdyn_wgrad_desc;
 int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream);
 
@@ -171,9 +178,11 @@ int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_expe
 /* --- reconstruction losses (problems.py:409-413, 431-449, 499-503, 535) -----------------------
  * BCE-with-logits, reduction 'sum' into loss_sum[0]; dlogits (fp16 NHWC, 8 channels per pixel,
  * 3 used) = gscale*(sigmoid(x) - t)*m.  mask (optional, NCHW fp32) multiplies logits and targets
- * as the reference does.  logits/target: NCHW fp32 (n,3,H,W). */
+ * as the reference does.  logits/target: NCHW fp32 (n,3,H,W).  pad > 0: dlogits images are
+ * (H+2*pad) x (W+2*pad) with a border that is never written (the caller zeroes it once): the
+ * layout the decoder backward reads as overlapping 4-pixel windows (mmdyn_igemm_desc.a_row_stride). */
 int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
-                     void* dlogits_nhwc8, float gscale, int n, int HW, void* stream);
+                     void* dlogits_nhwc8, float gscale, int n, int H, int W, int pad, void* stream);
 /* Same loss for callers outside the fused step (Reconstruction._elbo_loss / _mvae_elbo_loss called
  * on their own, problems.py:401-458, and the per-sample scoring path reduce=False, :415-417, :451-456):
  * logits / target / mask are flat fp32 [n][per_sample] in any (identical) layout; loss_sum[0] += total,
@@ -220,8 +229,8 @@ int mmdyn_f32_to_f16(const float* src, void* dst, long long n, float scale, void
 int mmdyn_scale_f32(float* x, long long n, float s, void* stream);
 /* fp32 NCHW (n,3,H,W) logit gradients -> fp16 NHWC8 (3 used) times scale: the layout the decoder
  * backward reads (used when the loss is computed outside the library, e.g. by torch autograd) */
-int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int HW,
-                          void* stream);
+int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int H, int W,
+                          int pad, void* stream);
 
 /* --- fused Adam over a flat fp32 arena (problems.py:138,155; torch.optim.Adam defaults) --------
  * p, g, m, v: [n] fp32.  step_count is the 1-based step AFTER this update (bias correction).

@@ -520,9 +520,10 @@ __device__ __forceinline__ float block_sum_256(float v) {
 __global__ void __launch_bounds__(256)
 bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                   const float* __restrict__ mask, float* __restrict__ loss_sum,
-                  __half* __restrict__ dlogits, float gscale, long long n_pix, int HW) {
+                  __half* __restrict__ dlogits, float gscale, long long n_pix, int HW, int W, int pad) {
   float acc = 0.0f;
-  const long long n_quad = n_pix >> 2;  // HW is a multiple of 4 (checked by the launcher)
+  const long long n_quad = n_pix >> 2;  // W is a multiple of 4 (checked by the launcher)
+  const int H = HW / W, Wp = W + 2 * pad, Hp = H + 2 * pad;
   for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < n_quad;
        q += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long p = q << 2;
@@ -552,8 +553,11 @@ bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ ta
       }
     }
     if (dlogits) {
+      // pad > 0: the gradient image carries a zero border of `pad` pixels (never written here)
+      const int y = hw / W, x = hw - y * W;
+      const long long o = (img * Hp + y + pad) * Wp + x + pad;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(dlogits)[p + k] = pack8(g[k]);
+      for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(dlogits)[o + k] = pack8(g[k]);
     }
   }
   const float t = block_sum_256(acc);
@@ -697,7 +701,8 @@ scale_f32_kernel(float* __restrict__ x, long long n, float s) {
 
 __global__ void __launch_bounds__(256)
 logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, float scale, long long n_pix,
-                       int HW) {
+                       int HW, int W, int pad) {
+  const int H = HW / W, Wp = W + 2 * pad, Hp = H + 2 * pad;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pix;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long img = p / HW;
@@ -705,7 +710,8 @@ logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, f
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c] = scale * dl[(img * 3 + c) * HW + hw];
-    reinterpret_cast<uint4*>(out)[p] = pack8(g);
+    const int y = hw / W, x = hw - y * W;
+    reinterpret_cast<uint4*>(out)[(img * Hp + y + pad) * Wp + x + pad] = pack8(g);
   }
 }
 
@@ -1011,12 +1017,14 @@ extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e,
 }
 
 extern "C" int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
-                                void* dlogits_nhwc8, float gscale, int n, int HW, void* stream) {
-  MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && HW > 0 && HW % 4 == 0, "bce_logits: bad arguments");
+                                void* dlogits_nhwc8, float gscale, int n, int H, int W, int pad, void* stream) {
+  MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && H > 0 && W > 0 && W % 4 == 0 && pad >= 0,
+                "bce_logits: bad arguments (n=%d H=%d W=%d pad=%d; W must be a multiple of 4)", n, H, W, pad);
+  const int HW = H * W;
   const long long n_pix = static_cast<long long>(n) * HW;
   bce_logits_kernel<<<grid_for(n_pix >> 2), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum,
                                                              reinterpret_cast<__half*>(dlogits_nhwc8), gscale,
-                                                             n_pix, HW);
+                                                             n_pix, HW, W, pad);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1112,12 +1120,13 @@ extern "C" int mmdyn_scale_f32(float* x, long long n, float s, void* stream) {
   return MMDYN_OK;
 }
 
-extern "C" int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int HW,
-                                     void* stream) {
-  MMDYN_REQUIRE(dlogits_nchw && out_nhwc8 && n > 0 && HW > 0, "logit_grad_pack: bad arguments");
+extern "C" int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int H, int W,
+                                     int pad, void* stream) {
+  MMDYN_REQUIRE(dlogits_nchw && out_nhwc8 && n > 0 && H > 0 && W > 0 && pad >= 0, "logit_grad_pack: bad arguments");
+  const int HW = H * W;
   const long long n_pix = static_cast<long long>(n) * HW;
   logit_grad_pack_kernel<<<grid_for(n_pix), 256, 0, ST(stream)>>>(dlogits_nchw, reinterpret_cast<__half*>(out_nhwc8),
-                                                                  scale, n_pix, HW);
+                                                                  scale, n_pix, HW, W, pad);
   LAUNCHED();
   return MMDYN_OK;
 }

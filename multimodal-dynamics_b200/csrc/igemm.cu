@@ -1296,6 +1296,9 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
   MMDYN_REQUIRE(rows * d->ldc < (1LL << 31) &&
                     static_cast<long long>(d->n_img) * d->IH * d->IW * d->a_pix_stride < (1LL << 31),
                 "igemm: tensor too large for 32-bit offsets");
+  const bool custom_strides = d->a_row_stride != 0 || d->a_img_stride != 0 || d->a_pix_stride < d->Cin;
+  MMDYN_REQUIRE(d->a_row_stride % 8 == 0 && d->a_img_stride % 8 == 0 && d->a_row_stride >= 0 && d->a_img_stride >= 0,
+                "igemm: a_row_stride / a_img_stride must be non-negative multiples of 8 elements");
 
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -1358,7 +1361,9 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     const cuuint64_t adim[4] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(d->IW),
                                 static_cast<cuuint64_t>(d->IH), static_cast<cuuint64_t>(d->n_img)};
     const cuuint64_t pix_b = static_cast<cuuint64_t>(d->a_pix_stride) * 2;
-    const cuuint64_t astr[3] = {pix_b, pix_b * d->IW, pix_b * d->IW * d->IH};
+    const cuuint64_t row_b = d->a_row_stride ? static_cast<cuuint64_t>(d->a_row_stride) * 2 : pix_b * d->IW;
+    const cuuint64_t img_b = d->a_img_stride ? static_cast<cuuint64_t>(d->a_img_stride) * 2 : row_b * d->IH;
+    const cuuint64_t astr[3] = {pix_b, row_b, img_b};
     const cuuint32_t abox[4] = {static_cast<cuuint32_t>(kc),
                                 static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * es),
                                 static_cast<cuuint32_t>(g.pixel_major ? 1 : bh * es), static_cast<cuuint32_t>(bn)};
@@ -1383,7 +1388,9 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     }
   }
 
-  // ---- cp.async gather path (any geometry) -------------------------------------------------------
+  // ---- cp.async gather path (any dense geometry) -------------------------------------------------
+  MMDYN_REQUIRE(!custom_strides, "igemm: a_row_stride / a_img_stride / overlapping windows need the TMA path "
+                "(Cin=%d ntaps=%d)", d->Cin, d->ntaps);
   long long m_tiles_ll;
   if (d->row_mode == 0)
     m_tiles_ll = (rows + TILE_M - 1) / TILE_M;
@@ -1422,6 +1429,9 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
                 "wgrad: operands must be 16-byte aligned");
   MMDYN_REQUIRE(static_cast<long long>(d->n_img) * d->IH * d->IW * d->g_pix_stride < (1LL << 31),
                 "wgrad: tensor too large for 32-bit offsets");
+  const bool custom_strides = d->g_row_stride != 0 || d->g_img_stride != 0 || d->g_pix_stride < d->Cg;
+  MMDYN_REQUIRE(d->g_row_stride % 8 == 0 && d->g_img_stride % 8 == 0 && d->g_row_stride >= 0 && d->g_img_stride >= 0,
+                "wgrad: g_row_stride / g_img_stride must be non-negative multiples of 8 elements");
   dim3 grid(d->row_splits, (d->ntaps * d->Cg) / 128, d->Cn / cn_tile);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -1465,7 +1475,9 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
       const cuuint64_t dim[4] = {static_cast<cuuint64_t>(d->Cg), static_cast<cuuint64_t>(d->IW),
                                  static_cast<cuuint64_t>(d->IH), static_cast<cuuint64_t>(d->n_img)};
       const cuuint64_t pb = static_cast<cuuint64_t>(d->g_pix_stride) * 2;
-      const cuuint64_t str[3] = {pb, pb * d->IW, pb * d->IW * d->IH};
+      const cuuint64_t rb = d->g_row_stride ? static_cast<cuuint64_t>(d->g_row_stride) * 2 : pb * d->IW;
+      const cuuint64_t ib = d->g_img_stride ? static_cast<cuuint64_t>(d->g_img_stride) * 2 : rb * d->IH;
+      const cuuint64_t str[3] = {pb, rb, ib};
       const cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * es),
                                  static_cast<cuuint32_t>(g.pixel_major ? 1 : bh * es), static_cast<cuuint32_t>(bn)};
       const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
@@ -1507,6 +1519,8 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
     }
   }
 
+  MMDYN_REQUIRE(!custom_strides, "wgrad: g_row_stride / g_img_stride / overlapping windows need the TMA path "
+                "(Cg=%d ntaps=%d)", d->Cg, d->ntaps);
   switch (cn_tile) {
     case 16: return launch_wgrad<16>(d, grid, st);
     case 32: return launch_wgrad<32>(d, grid, st);

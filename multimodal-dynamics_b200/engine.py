@@ -436,7 +436,7 @@ class EncoderExec(_NetBase):
         ops.bn_swish_bwd_reduce(r["raw1"], None, None, d1, None, 1, B * 1024, 32)
         # conv1 weight gradient on the tensor cores: x -> NHWC fp16 with 8 channels per pixel
         x8 = alloc(key + ".x8", (B, 64, 64, 8), F16)
-        ops.logit_grad_pack(r["x"], x8, 1.0, B, 64 * 64)
+        ops.logit_grad_pack(r["x"], x8, 1.0, B, 64, 64)
         dW1 = gp.view("conv1") if gp is not None else alloc(key + ".dW_c1", (32, 128), F32, zero=True)
         with _on_side(gp):
             ops.wgrad(self.c1_wg, x8, d1, dW1, B, scale=unscale, row_splits=plan.choose_row_splits(self.c1_wg, B),
@@ -487,7 +487,7 @@ class DecoderExec(_NetBase):
         return r
 
     def backward(self, r, dl8, alloc, key, unscale, gp=None):
-        """dl8: (G*B, 64, 64, 8) fp16 logit gradients (3 channels used, times grad_scale).
+        """dl8: (G*B, 66, 66, 8) fp16 logit gradients with a one-pixel ZERO border (3 channels used, times grad_scale).
         Returns dz (G*B, 256) fp32 (times grad_scale)."""
         arena, G, B = self.arena, r["G"], r["B"]
         R = G * B
@@ -837,12 +837,14 @@ class StepEngine:
             def fn():
                 G = len(dec_groups[m])
                 dec_rec[m] = ex["dec"][self.mods[m][1]].forward(zdec[m], G, B, ws, "dec_" + m, True)
-                dl8[m] = ws("dl8_" + m, (G * B, 64, 64, 8), F16, zero=self.exact) if need_grad else None
+                # one-pixel zero border (zeroed at allocation, never written): deconv4's backward reads
+                # the 4 x-taps of a pixel as one 64-byte window (plan.deconv_out_plan)
+                dl8[m] = ws("dl8_" + m, (G * B, 66, 66, 8), F16, zero=self.exact) if need_grad else None
                 for i in enc_passes[m]:
                     g = dec_groups[m].index(i)
                     k = slot[(m, i)]
                     ops.bce_logits(dec_rec[m]["logits"][g * B:(g + 1) * B], ts[m], loss_mask, scal[k:k + 1],
-                                   dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64 * 64)
+                                   dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64, 64, 1)
             return fn
 
         def pose_dec():
@@ -882,7 +884,7 @@ class StepEngine:
                 meas = scal[slot[("x", 0)]] / n_el
             else:
                 tmp = self.ws("metric_tmp", (4,), F32, zero=True)
-                ops.bce_logits(lg, ts["x"], None, tmp[0:1], None, 0.0, B, 64 * 64)
+                ops.bce_logits(lg, ts["x"], None, tmp[0:1], None, 0.0, B, 64, 64)
                 meas = tmp[0] / n_el
             return {"recon_x": lg.clone(), "means": mu_all[0].clone(), "log_var": lv_all[0].clone(),
                     "perf_measure": {"x": meas}}
@@ -898,7 +900,7 @@ class StepEngine:
             else:
                 tmp = self.ws("metric_tmp_" + m, (4,), F32, zero=True)
                 g = dec_groups[m].index(uni)
-                ops.bce_logits(dec_rec[m]["logits"][g * B:(g + 1) * B], ts[m], None, tmp[0:1], None, 0.0, B, 64 * 64)
+                ops.bce_logits(dec_rec[m]["logits"][g * B:(g + 1) * B], ts[m], None, tmp[0:1], None, 0.0, B, 64, 64)
                 perf[name] = tmp[0] / n_el
         if self.use_pose:
             g = pose_passes.index(joint)

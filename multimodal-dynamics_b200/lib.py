@@ -29,6 +29,7 @@ class IgemmDesc(C.Structure):
         ("N", C.c_int32), ("block_n", C.c_int32), ("ksplit", C.c_int32), ("row_mode", C.c_int32),
         ("out_mode", C.c_int32), ("OH", C.c_int32), ("OW", C.c_int32), ("s_out", C.c_int32),
         ("off_y", C.c_int32 * MAX_PHASES), ("off_x", C.c_int32 * MAX_PHASES), ("ldc", C.c_int32),
+        ("a_row_stride", C.c_int32), ("a_img_stride", C.c_int32),
     ]
 
 
@@ -39,7 +40,7 @@ class WgradDesc(C.Structure):
         ("g_pix_stride", C.c_int32), ("Cg", C.c_int32), ("s_in", C.c_int32), ("ntaps", C.c_int32),
         ("tap_dy", C.c_int8 * MAX_TAPS), ("tap_dx", C.c_int8 * MAX_TAPS),
         ("Cn", C.c_int32), ("nat_stride", C.c_int32), ("ldw", C.c_int32), ("row_splits", C.c_int32),
-        ("scale", C.c_float),
+        ("scale", C.c_float), ("g_row_stride", C.c_int32), ("g_img_stride", C.c_int32),
     ]
 
 
@@ -69,7 +70,7 @@ SIGNATURES = {
     "mmdyn_poe_fwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "mmdyn_poe_bwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, C.POINTER(_P), _P, _P, _F, C.POINTER(_P), C.POINTER(_P),
                        _I, _I, _I, _I, _P], _I),
-    "mmdyn_bce_logits": ([_P, _P, _P, _P, _P, _F, _I, _I, _P], _I),
+    "mmdyn_bce_logits": ([_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P], _I),
     "mmdyn_mse": ([_P, _P, _P, _P, _F, _F, _I, _P], _I),
     "mmdyn_bce_logits_flat": ([_P, _P, _P, _P, _P, _P, _F, _I, _I, _P], _I),
     "mmdyn_mse_rows": ([_P, _P, _P, _F, _I, _I, _P], _I),
@@ -82,7 +83,7 @@ SIGNATURES = {
     "mmdyn_unpack_add_f32": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_f32_to_f16": ([_P, _P, _LL, _F, _P], _I),
     "mmdyn_scale_f32": ([_P, _LL, _F, _P], _I),
-    "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _P], _I),
+    "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _I, _I, _P], _I),
     "mmdyn_adam_flat": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P], _I),
     "mmdyn_adam_flat_devstep": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _F, _P], _I),
     "mmdyn_sgd_flat": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),

@@ -98,12 +98,14 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     d.out_mode = geom.out_mode if out_mode is None else out_mode
     d.OH, d.OW, d.s_out = geom.OH, geom.OW, geom.s_out
     d.ldc = geom.ldc if ldc is None else ldc
+    d.a_row_stride, d.a_img_stride = geom.a_row_stride, geom.a_img_stride
 
     def alg():
         # algorithmic work: true MACs of the layer (no padding / phase-union waste) and one read of
         # each operand + one write of the output
         macs = (macs_per_img if macs_per_img is not None else geom.P * geom.n_phases * geom.N * geom.K) * n_img
-        nbytes = n_img * geom.IH * geom.IW * geom.Cin * 2 + Wp.numel() * 2 + out.numel() * _esz(out)
+        a_elems = geom.a_img_stride if geom.a_img_stride else geom.IH * geom.IW * geom.Cin
+        nbytes = n_img * a_elems * 2 + Wp.numel() * 2 + out.numel() * _esz(out)
         return 2.0 * macs, float(nbytes)
     with _Timed(tag, alg):
         check(_L().mmdyn_igemm(C.byref(d), _stream()), "mmdyn_igemm")
@@ -122,10 +124,12 @@ def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride
     d.nat_stride = geom.nat_stride if nat_stride is None else nat_stride
     d.ldw = geom.K if ldw is None else ldw
     d.row_splits, d.scale = row_splits, scale
+    d.g_row_stride, d.g_img_stride = geom.g_row_stride, geom.g_img_stride
 
     def alg():
         macs = (macs_per_img if macs_per_img is not None else geom.P * geom.Cn * geom.K) * n_img
-        nbytes = n_img * geom.IH * geom.IW * geom.Cg * 2 + n_img * geom.P * geom.Cn * 2 + dW.numel() * 4
+        g_elems = geom.g_img_stride if geom.g_img_stride else geom.IH * geom.IW * geom.Cg
+        nbytes = n_img * g_elems * 2 + n_img * geom.P * geom.Cn * 2 + dW.numel() * 4
         return 2.0 * macs, float(nbytes)
     with _Timed(tag, alg):
         check(_L().mmdyn_wgrad(C.byref(d), _stream()), "mmdyn_wgrad")
@@ -203,10 +207,11 @@ def poe_bwd(mu_e, lv_e, use_prior, ld, eps, dzs, kl_coef, dmu_e, dlv_e, ld_out, 
                                  int(accumulate), B, D, _stream()), "poe_bwd")
 
 
-def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, HW):
-    with _Timed("bce_logits", lambda: (0.0, n * HW * (3 * 8.0 + (16.0 if dlogits is not None else 0.0)))):
+def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, H, W, pad=0):
+    """pad: border (pixels) of the NHWC8 gradient images, see include/mmdyn_b200.h"""
+    with _Timed("bce_logits", lambda: (0.0, n * H * W * (3 * 8.0 + (16.0 if dlogits is not None else 0.0)))):
         check(_L().mmdyn_bce_logits(_ptr(logits), _ptr(target), _ptr(mask), _ptr(loss_sum), _ptr(dlogits), gscale, n,
-                                    HW, _stream()), "bce_logits")
+                                    H, W, pad, _stream()), "bce_logits")
 
 
 def bce_logits_flat(logits, target, mask, loss_sum, per_sample_sum, dlogits, gscale, n, per_sample):
@@ -273,9 +278,9 @@ def scale_f32(x, n, s):
         check(_L().mmdyn_scale_f32(_ptr(x), n, s, _stream()), "scale_f32")
 
 
-def logit_grad_pack(dl, out, scale, n, HW):
+def logit_grad_pack(dl, out, scale, n, H, W, pad=0):
     with _Timed("logit_grad_pack", None):
-        check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, HW, _stream()), "logit_grad_pack")
+        check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, H, W, pad, _stream()), "logit_grad_pack")
 
 
 def adam_flat(p, g, m, v, n, lr, b1, b2, eps, wd, step, gscale=1.0):

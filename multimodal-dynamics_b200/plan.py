@@ -43,6 +43,8 @@ class GemmGeom:
     row_mode: int = 0
     out_mode: int = 0
     a_pix_stride: Optional[int] = None
+    a_row_stride: int = 0     # 0 = dense; see include/mmdyn_b200.h (overlapping-window operands)
+    a_img_stride: int = 0
 
     @property
     def ntaps(self):
@@ -81,6 +83,8 @@ class WgradGeom:
     Cn: int
     g_pix_stride: Optional[int] = None
     nat_stride: Optional[int] = None
+    g_row_stride: int = 0
+    g_img_stride: int = 0
 
     @property
     def ntaps(self):
@@ -291,14 +295,22 @@ def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
                 for t_, (a, b) in enumerate(taps[:9]):
                     if a in kof[ph] and b in kof[pw]:
                         idx_fwd[n, t_ * Cin:(t_ + 1) * Cin] = widx(np.arange(Cin), co, kof[ph][a], kof[pw][b])
-    dy, dx = _conv_taps(4, 1)
-    dg = GemmGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cin=CP, s_in=2, tap_dy=[dy], tap_dx=[dx], N=Cin,
-                  OH=H, OW=H, s_out=1, off_y=[0], off_x=[0], ldc=Cin)
+    # Backward operand = dlogits, NHWC with CP = 8 channels per pixel, stored with a one-pixel zero
+    # border: [img][Ho+2][Ho+2][8].  The 4 x-taps of an output pixel (padded columns 2x .. 2x+3) are
+    # 64 contiguous bytes, so they are read as ONE tap of a "window pixel" with 4*CP = 32 channels whose
+    # pitch is a single physical pixel (a_pix_stride = 8 < Cin = 32): 4 operand boxes of 64-byte rows per
+    # tile instead of 16 boxes of 16-byte rows, and no out-of-image taps.  K order (kh, kw, c) is unchanged.
+    Hp = Ho + 2  # window pixel xw covers padded columns xw .. xw+3, so there are Hp - 3 = Ho - 1 of them per row
+    wdy, wdx = [0, 1, 2, 3], [0, 0, 0, 0]
+    dg = GemmGeom(P=H * H, OXv=H, IH=Hp, IW=Ho - 1, Cin=4 * CP, s_in=2, tap_dy=[wdy], tap_dx=[wdx], N=Cin,
+                  OH=H, OW=H, s_out=1, off_y=[0], off_x=[0], ldc=Cin, a_pix_stride=CP, a_row_stride=Hp * CP,
+                  a_img_stride=Hp * Hp * CP)
     idx_dg = np.full((Cin, 16 * CP), -1, np.int32)
     for t_ in range(16):
         for co in range(Cout):
             idx_dg[:, t_ * CP + co] = widx(np.arange(Cin), co, t_ // 4, t_ % 4)
-    wg = WgradGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cg=CP, s_in=2, tap_dy=dy, tap_dx=dx, Cn=Cin)
+    wg = WgradGeom(P=H * H, OXv=H, IH=Hp, IW=Ho - 1, Cg=4 * CP, s_in=2, tap_dy=wdy, tap_dx=wdx, Cn=Cin,
+                   g_pix_stride=CP, g_row_stride=Hp * CP, g_img_stride=Hp * Hp * CP)
     return LayerPlan(name, "deconv_out", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
 
 

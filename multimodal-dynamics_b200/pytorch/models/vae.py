@@ -124,8 +124,8 @@ class _DecoderFn(torch.autograd.Function):
         ex.arena.attach_grads()
         B = rec["B"]
         gs = float(B)
-        dl8 = torch.empty(B, 64, 64, 8, dtype=F16, device=dlogits.device)
-        ops.logit_grad_pack(dlogits.contiguous().float(), dl8, gs, B, 64 * 64)
+        dl8 = torch.zeros(B, 66, 66, 8, dtype=F16, device=dlogits.device)  # zero border: engine.DecoderExec.backward
+        ops.logit_grad_pack(dlogits.contiguous().float(), dl8, gs, B, 64, 64, 1)
         dz = ex.backward(rec, dl8, engine.FreshAlloc(dlogits.device), "dec", 1.0 / gs)
         ops.scale_f32(dz, dz.numel(), 1.0 / gs)
         return dz, None, None, None

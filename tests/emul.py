@@ -6,6 +6,17 @@ conv2d / conv_transpose2d without a GPU, and so GPU failures isolate to kernel m
 import numpy as np
 
 
+def window_view(buf, n_img, IH, IW, C, pix_stride, row_stride, img_stride):
+    """Strided (possibly overlapping) view [n_img, IH, IW, C] of a flat operand buffer, exactly the
+    addressing of the 4-D tensor map built in mmdyn_igemm / mmdyn_wgrad (strides in elements)."""
+    flat = np.ascontiguousarray(buf).reshape(-1)
+    last = (n_img - 1) * img_stride + (IH - 1) * row_stride + (IW - 1) * pix_stride + C
+    assert last <= flat.size, "operand view reads past the end of the buffer"
+    e = flat.itemsize
+    return np.lib.stride_tricks.as_strided(flat, (n_img, IH, IW, C), (img_stride * e, row_stride * e, pix_stride * e, e),
+                                           writeable=False)
+
+
 def pack(flat_params, idx):
     out = np.zeros(idx.shape, np.float64)
     m = idx >= 0
@@ -18,6 +29,9 @@ def igemm(geom, A, Wp, n_img, bias=None):
     (out_mode 0/1) or NCHW [n_img, 3, OH, OW] (out_mode 3)."""
     g = geom
     OYv = g.P // g.OXv
+    if g.a_row_stride or g.a_img_stride or g.a_pix_stride < g.Cin:
+        A = window_view(A, n_img, g.IH, g.IW, g.Cin, g.a_pix_stride, g.a_row_stride or g.a_pix_stride * g.IW,
+                        g.a_img_stride or (g.a_row_stride or g.a_pix_stride * g.IW) * g.IH)
     if g.out_mode == 3:
         out = np.zeros((n_img, 3, g.OH, g.OW))
     else:
@@ -55,6 +69,9 @@ def wgrad(geom, G, Nat, n_img):
     """G: [n_img, IH, IW, g_pix_stride]; Nat: [n_img, P, nat_stride]. Returns dW [Cn, K]."""
     g = geom
     OYv = g.P // g.OXv
+    if g.g_row_stride or g.g_img_stride or g.g_pix_stride < g.Cg:
+        G = window_view(G, n_img, g.IH, g.IW, g.Cg, g.g_pix_stride, g.g_row_stride or g.g_pix_stride * g.IW,
+                        g.g_img_stride or (g.g_row_stride or g.g_pix_stride * g.IW) * g.IH)
     dW = np.zeros((g.Cn, g.K))
     for yv in range(OYv):
         for xv in range(g.OXv):

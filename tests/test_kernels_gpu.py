@@ -67,7 +67,7 @@ def conv_case(lp, w, x, stride, pad, transposed, n):
     return xr, wr, y.detach(), dy
 
 
-def check_conv_layer(lp, w, x, stride, pad, transposed, grad_pad=None):
+def check_conv_layer(lp, w, x, stride, pad, transposed, grad_pad=None, border=0):
     ops = _ops()
     n = x.shape[0]
     xr, wr, y, dy = conv_case(lp, w, x, stride, pad, transposed, n)
@@ -81,6 +81,8 @@ def check_conv_layer(lp, w, x, stride, pad, transposed, grad_pad=None):
     dyn = dy.float()
     if grad_pad:
         dyn = torch.cat([dyn, torch.zeros(n, grad_pad - dyn.shape[1], *dyn.shape[2:])], 1)
+    if border:  # zero border: the overlapping-window operand layout of the logits layer (plan.deconv_out_plan)
+        dyn = F.pad(dyn, (border, border, border, border))
     dA = nhwc16(dyn)
     dx = run_fwd(lp.dgrad, lp.idx_dgrad, w, dA, n)
     assert rel_err(dx.permute(0, 3, 1, 2)[:, :x.shape[1]], xr.grad) < 1e-3
@@ -152,7 +154,7 @@ def test_deconv4_out():
     torch.manual_seed(7)
     w = torch.randn(32, 3, 4, 4) * 0.1
     x = torch.randn(3, 32, 32, 32)
-    check_conv_layer(plan.deconv_out_plan("d4", 0, 32, 3, 32), w, x, 2, 1, True, grad_pad=8)
+    check_conv_layer(plan.deconv_out_plan("d4", 0, 32, 3, 32), w, x, 2, 1, True, grad_pad=8, border=1)
 
 
 @pytest.mark.parametrize("M", [5, 128, 300])
@@ -370,13 +372,25 @@ def test_bce_logits_and_mse(use_mask):
     else:
         loss = F.binary_cross_entropy_with_logits(xr, t.double(), reduction="sum")
     loss.backward()
-    ls = torch.zeros(1, device=DEV)
-    dl = torch.empty(n, 64, 64, 8, dtype=torch.float16, device=DEV)
-    ops.bce_logits(x.to(DEV), t.to(DEV), m.to(DEV) if use_mask else None, ls, dl, 2.0, n, HW)
-    torch.cuda.synchronize()
-    assert abs(ls.item() - loss.item()) / loss.item() < 1e-5
-    assert rel_err(dl[..., :3].permute(0, 3, 1, 2), 2.0 * xr.grad) < 1e-3
-    assert dl[..., 3:].abs().max().item() == 0
+    for pad in (0, 1):
+        ls = torch.zeros(1, device=DEV)
+        dl = torch.full((n, 64 + 2 * pad, 64 + 2 * pad, 8), 7.0, dtype=torch.float16, device=DEV)
+        ops.bce_logits(x.to(DEV), t.to(DEV), m.to(DEV) if use_mask else None, ls, dl, 2.0, n, 64, 64, pad)
+        torch.cuda.synchronize()
+        assert abs(ls.item() - loss.item()) / loss.item() < 1e-5
+        inner = dl[:, pad:pad + 64, pad:pad + 64]
+        assert rel_err(inner[..., :3].permute(0, 3, 1, 2), 2.0 * xr.grad) < 1e-3
+        assert inner[..., 3:].abs().max().item() == 0
+        if pad:  # the border is never written
+            bord = dl.clone()
+            bord[:, pad:pad + 64, pad:pad + 64] = 7.0
+            assert (bord == 7.0).all()
+        # the same gradient through the stand-alone packer (loss computed outside the library)
+        dl2 = torch.full_like(dl, 7.0)
+        ops.logit_grad_pack(xr.grad.float().to(DEV), dl2, 2.0, n, 64, 64, pad)
+        torch.cuda.synchronize()
+        assert rel_err(dl2[:, pad:pad + 64, pad:pad + 64, :3].permute(0, 3, 1, 2), 2.0 * xr.grad) < 1e-3
+        assert (dl2[:, :pad] == 7.0).all() and (dl2[:, :, :pad] == 7.0).all()
     # pose MSE * multiplier
     r, tt = torch.randn(n, 7), torch.rand(n, 7)
     rr = r.double().requires_grad_(True)

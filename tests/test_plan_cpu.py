@@ -22,7 +22,7 @@ def nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous().double().numpy()
 
 
-def check_layer(lp, w, x, y_ref, dy, stride, pad, transposed, cin_pad=None):
+def check_layer(lp, w, x, y_ref, dy, stride, pad, transposed, cin_pad=None, border=0):
     n = x.shape[0]
     flat = w.detach().double().reshape(-1).numpy()
     # forward
@@ -41,6 +41,8 @@ def check_layer(lp, w, x, y_ref, dy, stride, pad, transposed, cin_pad=None):
     dyn = nhwc(dy)
     if cin_pad:
         dyn = np.concatenate([dyn, np.zeros(dyn.shape[:-1] + (cin_pad - dyn.shape[-1],))], -1)
+    if border:  # zero border of `border` pixels around every image (overlapping-window operand layout)
+        dyn = np.pad(dyn, ((0, 0), (border, border), (border, border), (0, 0)))
     dx = emul.igemm(lp.dgrad, dyn, emul.pack(flat, lp.idx_dgrad), n)
     np.testing.assert_allclose(dx[..., :x.shape[1]], nhwc(xr.grad), atol=1e-9)
     # weight gradient
@@ -87,7 +89,7 @@ def test_deconv_out():
     w = torch.randn(32, 3, 4, 4)
     x = torch.randn(2, 32, 8, 8)
     y = F.conv_transpose2d(x, w, stride=2, padding=1)
-    check_layer(plan.deconv_out_plan("d4", 0, 32, 3, 8), w, x, y, torch.randn_like(y), 2, 1, True, cin_pad=8)
+    check_layer(plan.deconv_out_plan("d4", 0, 32, 3, 8), w, x, y, torch.randn_like(y), 2, 1, True, cin_pad=8, border=1)
 
 
 def test_linear_permuted_and_concat():
