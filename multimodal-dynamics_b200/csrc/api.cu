@@ -9,6 +9,7 @@
 namespace mmdyn {
 extern std::atomic<long long> g_launch_count;
 int igemm_init();
+int elementwise_init();
 
 static thread_local char g_err[512] = "";
 
@@ -33,5 +34,7 @@ extern "C" int mmdyn_init(int device) {
                           device, prop.major, prop.minor);
     return MMDYN_ERR_UNSUPPORTED;
   }
-  return mmdyn::igemm_init();
+  const int rc = mmdyn::igemm_init();
+  if (rc != MMDYN_OK) return rc;
+  return mmdyn::elementwise_init();
 }

@@ -118,6 +118,18 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA bulk copy of a contiguous byte range (global -> shared), completion on an mbarrier.
+// dst, src and bytes must be multiples of 16.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :
+      : "r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // TMA tiled loads (weights / plain 2-D operands)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -331,6 +331,245 @@ bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ coef
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-streamed variants of the four BatchNorm streaming kernels.  The register-fed versions above
+// keep at most 2-4 16-byte loads per thread in flight (~35 KB per SM at 76-79 registers), which is
+// about one bandwidth-delay product of HBM3e and left them latency-bound at 0.4-0.6 of the copy peak.
+// Here one thread per CTA streams contiguous 16 KB row blocks into a shared-memory ring with TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx), so 96-128 KB per SM are in flight regardless of the
+// register budget; the 256 threads consume a stage with conflict-free 16-byte shared loads (same
+// thread -> 8-channel-vector mapping as above, so per-channel coefficients stay in registers).
+// ---------------------------------------------------------------------------------------------
+constexpr int BS_STAGE_BYTES = 16384;
+constexpr int BS_ROWS_PER_THREAD = 4;  // rows_per_stage <= 4 * row_lanes for every C (8192/C vs 2048/C)
+
+template <int NIN, int STAGES>
+struct BulkRows {
+  uint32_t smem, bars;
+  const uint8_t* src[NIN];
+  long long total_bytes;
+  int stage_bytes, n_iter;
+  __device__ __forceinline__ void issue(int it) const {
+    const int s = it % STAGES;
+    const long long off = static_cast<long long>(it) * stage_bytes;
+    const long long left = total_bytes - off;
+    const uint32_t bytes = static_cast<uint32_t>(left < stage_bytes ? left : stage_bytes);
+    const uint32_t bar = bars + s * 8;
+    mbar_arrive_expect_tx(bar, NIN * bytes);
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) bulk_load_1d(smem + (s * NIN + i) * BS_STAGE_BYTES, src[i] + off, bytes, bar);
+  }
+};
+
+#define BS_PROLOGUE(NIN, STAGES)                                                                      \
+  extern __shared__ __align__(128) uint8_t bs_smem[];                                                \
+  __shared__ __align__(8) uint64_t bs_bar[STAGES];                                                   \
+  const int vpr = C >> 3;                                                                            \
+  const int row_lanes = RED_THREADS / vpr;                                                           \
+  const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;                                         \
+  const int g = blockIdx.y;                                                                          \
+  const int r_begin = blockIdx.x * rows_per_chunk;                                                   \
+  const int n_rows = min(rows_per_group, r_begin + rows_per_chunk) - r_begin;                        \
+  const int row_bytes = C * 2;                                                                       \
+  const int rps = BS_STAGE_BYTES / row_bytes;                                                        \
+  const long long base = (static_cast<long long>(g) * rows_per_group + r_begin) * C;                 \
+  BulkRows<NIN, STAGES> st;                                                                          \
+  st.smem = smem_u32(bs_smem);                                                                       \
+  st.bars = smem_u32(bs_bar);                                                                        \
+  st.total_bytes = static_cast<long long>(n_rows) * row_bytes;                                       \
+  st.stage_bytes = rps * row_bytes;                                                                  \
+  st.n_iter = (n_rows + rps - 1) / rps
+
+#define BS_START(STAGES)                                                                              \
+  if (threadIdx.x == 0) {                                                                            \
+    for (int s_ = 0; s_ < STAGES; ++s_) mbar_init(st.bars + s_ * 8, 1);                              \
+    mbar_fence_init();                                                                               \
+  }                                                                                                  \
+  __syncthreads();                                                                                   \
+  if (threadIdx.x == 0)                                                                              \
+    for (int it_ = 0; it_ < STAGES && it_ < st.n_iter; ++it_) st.issue(it_)
+
+template <int STAGES>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_stats_bulk_kernel(const __half* __restrict__ x, float* __restrict__ sums, int rows_per_group, int C,
+                     int rows_per_chunk) {
+  BS_PROLOGUE(1, STAGES);
+  st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
+  BS_START(STAGES);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.0f;
+  for (int it = 0; it < st.n_iter; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(st.bars + s * 8, (it / STAGES) & 1);
+    const int nr = min(rps, n_rows - it * rps);
+    const uint8_t* sx = bs_smem + s * BS_STAGE_BYTES + vec * 16;
+#pragma unroll
+    for (int k = 0; k < BS_ROWS_PER_THREAD; ++k) {
+      const int row = rl + k * row_lanes;
+      if (row < nr) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(sx + row * row_bytes), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += f[i];
+          s2[i] = fmaf(f[i], f[i], s2[i]);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + STAGES < st.n_iter) st.issue(it + STAGES);
+  }
+  float* red = reinterpret_cast<float*>(bs_smem);  // ring is idle: every issued stage was consumed
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[(rl * C + vec * 8 + i) * 2] = s1[i];
+    red[(rl * C + vec * 8 + i) * 2 + 1] = s2[i];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * 2; idx += RED_THREADS) {
+    float a = 0.0f;
+    for (int l = 0; l < row_lanes; ++l) a += red[l * C * 2 + idx];
+    atomicAdd(sums + static_cast<long long>(g) * C * 2 + idx, a);
+  }
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_swish_fwd_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
+                         int rows_per_group, int C, int rows_per_chunk) {
+  BS_PROLOGUE(1, STAGES);
+  st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
+  BS_START(STAGES);
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = ab[(g * C + vec * 8 + i) * 2];
+    b[i] = ab[(g * C + vec * 8 + i) * 2 + 1];
+  }
+  for (int it = 0; it < st.n_iter; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(st.bars + s * 8, (it / STAGES) & 1);
+    const int nr = min(rps, n_rows - it * rps);
+    const uint8_t* sx = bs_smem + s * BS_STAGE_BYTES + vec * 16;
+    __half* out = y + base + static_cast<long long>(it) * rps * C + vec * 8;
+#pragma unroll
+    for (int k = 0; k < BS_ROWS_PER_THREAD; ++k) {
+      const int row = rl + k * row_lanes;
+      if (row < nr) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(sx + row * row_bytes), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = swishf_(fmaf(a[i], f[i], b[i]));
+        *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = pack8(f);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + STAGES < st.n_iter) st.issue(it + STAGES);
+  }
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_swish_bwd_reduce_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
+                                const float* __restrict__ mean_invstd, const __half* __restrict__ dY,
+                                float* __restrict__ sums2, int rows_per_group, int C, int rows_per_chunk) {
+  BS_PROLOGUE(2, STAGES);
+  st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
+  st.src[1] = reinterpret_cast<const uint8_t*>(dY + base);
+  BS_START(STAGES);
+  float a[8], b[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = vec * 8 + i;
+    a[i] = ab[(g * C + c) * 2];
+    b[i] = ab[(g * C + c) * 2 + 1];
+    s1[i] = s2[i] = 0.0f;
+  }
+  for (int it = 0; it < st.n_iter; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(st.bars + s * 8, (it / STAGES) & 1);
+    const int nr = min(rps, n_rows - it * rps);
+    const uint8_t* sx = bs_smem + (s * 2) * BS_STAGE_BYTES + vec * 16;
+    const uint8_t* sd = sx + BS_STAGE_BYTES;
+#pragma unroll
+    for (int k = 0; k < BS_ROWS_PER_THREAD; ++k) {
+      const int row = rl + k * row_lanes;
+      if (row < nr) {
+        float fx[8], fd[8];
+        unpack8(*reinterpret_cast<const uint4*>(sx + row * row_bytes), fx);
+        unpack8(*reinterpret_cast<const uint4*>(sd + row * row_bytes), fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float du = fd[i] * swish_gradf_(fmaf(a[i], fx[i], b[i]));
+          s1[i] += du;
+          s2[i] = fmaf(du, fx[i], s2[i]);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + STAGES < st.n_iter) st.issue(it + STAGES);
+  }
+  float* red = reinterpret_cast<float*>(bs_smem);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = vec * 8 + i;
+    const float mean = mean_invstd[(g * C + c) * 2], invstd = mean_invstd[(g * C + c) * 2 + 1];
+    red[(rl * C + c) * 2] = s1[i];
+    red[(rl * C + c) * 2 + 1] = (s2[i] - mean * s1[i]) * invstd;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * 2; idx += RED_THREADS) {
+    float acc = 0.0f;
+    for (int l = 0; l < row_lanes; ++l) acc += red[l * C * 2 + idx];
+    atomicAdd(sums2 + static_cast<long long>(g) * C * 2 + idx, acc);
+  }
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ coef, __half* __restrict__ dU,
+                         int rows_per_group, int C, int rows_per_chunk) {
+  BS_PROLOGUE(2, STAGES);
+  st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
+  st.src[1] = reinterpret_cast<const uint8_t*>(dU + base);
+  BS_START(STAGES);
+  float ka[8], kb[8], kc[8], ks[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 k = *reinterpret_cast<const float4*>(coef + (static_cast<long long>(g) * C + vec * 8 + i) * 4);
+    ka[i] = k.x;
+    kb[i] = k.y;
+    kc[i] = k.z;
+    ks[i] = k.w;
+  }
+  for (int it = 0; it < st.n_iter; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(st.bars + s * 8, (it / STAGES) & 1);
+    const int nr = min(rps, n_rows - it * rps);
+    const uint8_t* sx = bs_smem + (s * 2) * BS_STAGE_BYTES + vec * 16;
+    const uint8_t* sd = sx + BS_STAGE_BYTES;
+    __half* out = dU + base + static_cast<long long>(it) * rps * C + vec * 8;  // in place: rows of this stage only
+#pragma unroll
+    for (int k = 0; k < BS_ROWS_PER_THREAD; ++k) {
+      const int row = rl + k * row_lanes;
+      if (row < nr) {
+        float fx[8], fd[8];
+        unpack8(*reinterpret_cast<const uint4*>(sx + row * row_bytes), fx);
+        unpack8(*reinterpret_cast<const uint4*>(sd + row * row_bytes), fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float du = fd[i] * swish_gradf_(fmaf(ka[i], fx[i], ks[i]));
+          fd[i] = fmaf(ka[i], du, fmaf(kb[i], fx[i], kc[i]));
+        }
+        *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = pack8(fd);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it + STAGES < st.n_iter) st.issue(it + STAGES);
+  }
+}
+
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums2, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int G, int C, float unscale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -844,6 +1083,24 @@ inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 8) {
   return static_cast<int>(b);
 }
 
+// bulk-streamed kernels: one balanced wave (every CTA resident, equal row ranges, whole stages)
+constexpr int BS_STAGES_1IN = 4, BS_STAGES_2IN = 3;
+inline int bulk_chunking(int rows_per_group, int G, int C, int ctas_per_sm, int* rows_per_chunk) {
+  const int rps = BS_STAGE_BYTES / (C * 2);
+  const int stages_total = (rows_per_group + rps - 1) / rps;
+  int chunks = (148 * ctas_per_sm) / G;
+  if (chunks > stages_total) chunks = stages_total;
+  if (chunks < 1) chunks = 1;
+  const int stages_per_chunk = (stages_total + chunks - 1) / chunks;
+  *rows_per_chunk = stages_per_chunk * rps;
+  return (rows_per_group + *rows_per_chunk - 1) / *rows_per_chunk;
+}
+inline bool bulk_ok(int C) { return C >= 8 && C <= 2048 && (2048 % C) == 0; }
+inline bool use_bulk() {
+  static const bool off = getenv("MMDYN_BN_NO_BULK") != nullptr;
+  return !off;
+}
+
 inline int chunking(int rows_per_group, int G, int C, int* rows_per_chunk) {
   // Many more CTAs than one wave (148 SMs x ~3 resident): ncu showed 1.33 waves with the old 4/SM
   // sizing, i.e. a third of the time spent in a one-third-full tail.  16 CTAs per SM keep the tail
@@ -860,6 +1117,19 @@ inline int chunking(int rows_per_group, int G, int C, int* rows_per_chunk) {
 }  // namespace
 }  // namespace mmdyn
 
+namespace mmdyn {
+int elementwise_init() {
+#define SET_SMEM(K, BYTES) \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES))
+  SET_SMEM(bn_stats_bulk_kernel<BS_STAGES_1IN>, BS_STAGES_1IN * BS_STAGE_BYTES);
+  SET_SMEM(bn_swish_fwd_bulk_kernel<BS_STAGES_1IN>, BS_STAGES_1IN * BS_STAGE_BYTES);
+  SET_SMEM(bn_swish_bwd_reduce_bulk_kernel<BS_STAGES_2IN>, 2 * BS_STAGES_2IN * BS_STAGE_BYTES);
+  SET_SMEM(bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>, 2 * BS_STAGES_2IN * BS_STAGE_BYTES);
+#undef SET_SMEM
+  return MMDYN_OK;
+}
+}  // namespace mmdyn
+
 using namespace mmdyn;
 #define ST(s) static_cast<cudaStream_t>(s)
 
@@ -868,6 +1138,13 @@ static bool bn_c_ok(int C) { return C >= 8 && C % 8 == 0 && (C >> 3) <= RED_THRE
 extern "C" int mmdyn_bn_stats(const void* x, float* sums, int G, int rows_per_group, int C, void* stream) {
   MMDYN_REQUIRE(x && sums && G > 0 && rows_per_group > 0 && bn_c_ok(C), "bn_stats: bad arguments (C=%d)", C);
   int rpc;
+  if (use_bulk() && bulk_ok(C)) {
+    const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
+    bn_stats_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES, ST(stream)>>>(
+        reinterpret_cast<const __half*>(x), sums, rows_per_group, C, rpc);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
   const int chunks = chunking(rows_per_group, G, C, &rpc);
   const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
   bn_stats_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
@@ -892,6 +1169,15 @@ extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G
                                   void* stream) {
   MMDYN_REQUIRE(x && y && G > 0 && rows_per_group > 0 && C % 8 == 0, "bn_swish_fwd: bad arguments");
   const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
+  if (ab && use_bulk() && bulk_ok(C)) {
+    int rpc;
+    const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
+    bn_swish_fwd_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
+                                              ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
+                                                            reinterpret_cast<__half*>(y), rows_per_group, C, rpc);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
   if (ab && bn_c_ok(C)) {
     int rpc;
     const int chunks = chunking(rows_per_group, G, C, &rpc);
@@ -919,6 +1205,15 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
   }
   MMDYN_REQUIRE(mean_invstd && sums2 && bn_c_ok(C), "bn_swish_bwd_reduce: bad arguments (C=%d)", C);
   int rpc;
+  if (use_bulk() && bulk_ok(C)) {
+    const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
+    bn_swish_bwd_reduce_bulk_kernel<BS_STAGES_2IN>
+        <<<dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream)>>>(
+            reinterpret_cast<const __half*>(x), ab, mean_invstd, reinterpret_cast<const __half*>(dY), sums2,
+            rows_per_group, C, rpc);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
   const int chunks = chunking(rows_per_group, G, C, &rpc);
   const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
   bn_swish_bwd_reduce_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
@@ -940,9 +1235,16 @@ extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* m
   MMDYN_REQUIRE(bn_c_ok(C), "bn_bwd_apply: C=%d unsupported", C);
   (void)n_vec;
   int rpc;
-  const int chunks = chunking(rows_per_group, G, C, &rpc);
-  bn_bwd_apply_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
-      reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
+  if (use_bulk() && bulk_ok(C)) {
+    const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
+    bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>
+        <<<dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream)>>>(
+            reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
+  } else {
+    const int chunks = chunking(rows_per_group, G, C, &rpc);
+    bn_bwd_apply_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
+        reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
+  }
   LAUNCHED();
   if (dgamma && dbeta) {
     bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums2, dgamma, dbeta, G, C, grad_unscale);

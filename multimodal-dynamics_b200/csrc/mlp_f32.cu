@@ -2,9 +2,9 @@
 // 256->512->512->7 decoder): mmdyn/pytorch/models/vae.py:14-19, 118-123, 219-222, 282-283.
 //
 // The pose branch is ~1 MFLOP/sample and feeds the fp32 ProductOfExperts directly, so it stays in
-// fp32 on the CUDA cores: a 64x64x16 shared-memory tiled SGEMM (4x4 register micro-tile, 256
-// threads), with transposition flags so the same kernel serves y = xW^T, dx = dy W and
-// dW = dy^T x (split along the reduction with atomics).
+// fp32 on the CUDA cores: a {128,64}x64x16 shared-memory tiled SGEMM (8x4 / 4x4 register micro-tile,
+// 256 threads, double-buffered k-tiles, 16-byte global loads), with transposition flags so the same
+// kernel serves y = xW^T, dx = dy W and dW = dy^T x (split along the reduction with atomics).
 #include "common.cuh"
 #include "../../include/mmdyn_b200.h"
 
@@ -14,76 +14,177 @@ namespace mmdyn {
 extern std::atomic<long long> g_launch_count;
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BN = 64, BK = 16;
+
+// one k-tile of an operand -> registers.  T = false: k contiguous in memory (4 consecutive k of one
+// row per float4); T = true: the row (m or n) index is contiguous (4 consecutive rows at one k).
+template <bool T, int RB, int NV>
+__device__ __forceinline__ void load_tile(const float* __restrict__ X, bool vec, int r0, int R, int ld, int k0,
+                                          int k_end, float4 (&regs)[NV]) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = t + i * 256;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!T) {
+      const int r = idx >> 2, kq = (idx & 3) * 4;
+      const int gr = r0 + r, gk = k0 + kq;
+      if (gr < R) {
+        const float* p = X + static_cast<long long>(gr) * ld + gk;
+        if (vec && gk + 3 < k_end) {
+          v = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (gk < k_end) v.x = __ldg(p);
+          if (gk + 1 < k_end) v.y = __ldg(p + 1);
+          if (gk + 2 < k_end) v.z = __ldg(p + 2);
+          if (gk + 3 < k_end) v.w = __ldg(p + 3);
+        }
+      }
+    } else {
+      const int rq = (idx % (RB / 4)) * 4, k = idx / (RB / 4);
+      const int gr = r0 + rq, gk = k0 + k;
+      if (gk < k_end) {
+        const float* p = X + static_cast<long long>(gk) * ld + gr;
+        if (vec && gr + 3 < R) {
+          v = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (gr < R) v.x = __ldg(p);
+          if (gr + 1 < R) v.y = __ldg(p + 1);
+          if (gr + 2 < R) v.z = __ldg(p + 2);
+          if (gr + 3 < R) v.w = __ldg(p + 3);
+        }
+      }
+    }
+    regs[i] = v;
+  }
+}
 
 // C[m][n] (=|+=) scale * sum_k A(m,k) * B(k,n)   (+ bias[n], optional ReLU)
 //   A(m,k) = TA ? A[k*lda + m] : A[m*lda + k];   B(k,n) = TB ? B[n*ldb + k] : B[k*ldb + n]
-template <bool TA, bool TB>
+// BM x 64 x 16 tiles (BM = 128: 8x4 register micro-tile, BM = 64: 4x4), 256 threads, operands staged
+// k-major in double-buffered shared memory: the next k-tile's global loads (16-byte where the
+// operand layout allows) are issued before the FMAs of the current one, one barrier per k-tile.
+template <int BM, bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
              const float* __restrict__ bias, int M, int N, int K, int lda, int ldb, int ldc, int act,
              int atomic_add, float scale, int k_per_split) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  constexpr int TM = BM / 16;          // rows per thread
+  constexpr int A_V4 = BM * BK / 4 / 256;  // float4 loads of A per thread and k-tile
+  constexpr int B_V4 = BN * BK / 4 / 256;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
-  float acc[4][4];
+  const bool a_vec = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  const bool b_vec = (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+  float4 ra[A_V4], rb[B_V4];
+  auto stage = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < A_V4; ++i) {
       const int idx = t + i * 256;
-      int m, k;
-      if (!TA) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.0f;
-      if (gm < M && gk < k_end) v = TA ? A[static_cast<long long>(gk) * lda + gm] : A[static_cast<long long>(gm) * lda + gk];
-      As[k][m] = v;
-      int n, kb;
-      if (TB) { n = idx >> 4; kb = idx & 15; } else { n = idx & 63; kb = idx >> 6; }
-      const int gn = n0 + n, gkb = k0 + kb;
-      float w = 0.0f;
-      if (gn < N && gkb < k_end) w = TB ? B[static_cast<long long>(gn) * ldb + gkb] : B[static_cast<long long>(gkb) * ldb + gn];
-      Bs[kb][n] = w;
+      if (!TA) {
+        const int r = idx >> 2, kq = (idx & 3) * 4;
+        As[buf][kq][r] = ra[i].x; As[buf][kq + 1][r] = ra[i].y; As[buf][kq + 2][r] = ra[i].z; As[buf][kq + 3][r] = ra[i].w;
+      } else {
+        const int rq = (idx % (BM / 4)) * 4, k = idx / (BM / 4);
+        *reinterpret_cast<float4*>(&As[buf][k][rq]) = ra[i];
+      }
     }
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < B_V4; ++i) {
+      const int idx = t + i * 256;
+      if (TB) {
+        const int r = idx >> 2, kq = (idx & 3) * 4;
+        Bs[buf][kq][r] = rb[i].x; Bs[buf][kq + 1][r] = rb[i].y; Bs[buf][kq + 2][r] = rb[i].z; Bs[buf][kq + 3][r] = rb[i].w;
+      } else {
+        const int rq = (idx % (BN / 4)) * 4, k = idx / (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][k][rq]) = rb[i];
+      }
+    }
+  };
+
+  load_tile<TA, BM, A_V4>(A, a_vec, m0, M, lda, k_begin, k_end, ra);
+  load_tile<!TB, BN, B_V4>(B, b_vec, n0, N, ldb, k_begin, k_end, rb);
+  stage(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    const bool more = k0 + BK < k_end;
+    if (more) {
+      load_tile<TA, BM, A_V4>(A, a_vec, m0, M, lda, k0 + BK, k_end, ra);
+      load_tile<!TB, BN, B_V4>(B, b_vec, n0, N, ldb, k0 + BK, k_end, rb);
+    }
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int h = 0; h < TM / 4; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][h * 64 + ty * 4]);
+        av[4 * h] = a.x; av[4 * h + 1] = a.y; av[4 * h + 2] = a.z; av[4 * h + 3] = a.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
+    if (more) {
+      stage(buf ^ 1);  // the other buffer was last read before the previous barrier
+      __syncthreads();
+      buf ^= 1;
+    }
   }
+  const bool c_vec = !atomic_add && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (gm >= M) continue;
+    const int gn = n0 + tx * 4;
+    float* o = C + static_cast<long long>(gm) * ldc + gn;
+    float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = scale * acc[i][j];
-      float* o = C + static_cast<long long>(gm) * ldc + gn;
-      if (atomic_add) {
-        atomicAdd(o, v);
-      } else {
-        if (bias) v += bias[gn];
-        if (act == 1) v = fmaxf(v, 0.0f);
-        *o = v;
+      v[j] = scale * acc[i][j];
+      if (!atomic_add) {
+        if (bias && gn + j < N) v[j] += __ldg(bias + gn + j);
+        if (act == 1) v[j] = fmaxf(v[j], 0.0f);
       }
     }
+    if (c_vec && gn + 3 < N) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (gn + j >= N) continue;
+        if (atomic_add) atomicAdd(o + j, v[j]);
+        else o[j] = v[j];
+      }
+    }
+  }
+}
+
+// 128-row tiles when they still fill the machine, 64-row tiles otherwise
+template <bool TA, bool TB>
+void launch_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                  int ldc, int act, int atomic_add, float scale, int k_per_split, int splits, cudaStream_t st) {
+  const int nb = (N + BN - 1) / BN;
+  if (static_cast<long long>((M + 127) / 128) * nb * splits >= 148) {
+    sgemm_kernel<128, TA, TB><<<dim3(nb, (M + 127) / 128, splits), 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc,
+                                                                                   act, atomic_add, scale, k_per_split);
+  } else {
+    sgemm_kernel<64, TA, TB><<<dim3(nb, (M + 63) / 64, splits), 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc,
+                                                                                 act, atomic_add, scale, k_per_split);
   }
 }
 
@@ -113,8 +214,7 @@ using namespace mmdyn;
 extern "C" int mmdyn_linear_f32_fwd(const float* x, const float* W, const float* b, float* y, int M, int N,
                                     int K, int ldx, int ldy, int act, void* stream) {
   MMDYN_REQUIRE(x && W && y && M > 0 && N > 0 && K > 0, "linear_f32_fwd: bad arguments");
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
-  sgemm_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(x, W, y, b, M, N, K, ldx, K, ldy, act, 0, 1.0f, K);
+  launch_sgemm<false, true>(x, W, y, b, M, N, K, ldx, K, ldy, act, 0, 1.0f, K, 1, ST(stream));
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -132,20 +232,17 @@ extern "C" int mmdyn_linear_f32_bwd(const float* x, const float* W, const float*
     LAUNCHED();
   }
   if (dx) {  // dx[M][K] = dy_act[M][N] * W[N][K]
-    dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM, 1);
-    sgemm_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(dy_act, W, dx, nullptr, M, K, N, N, K, lddx, 0,
-                                                             dx_accumulate ? 1 : 0, 1.0f, N);
+    launch_sgemm<false, false>(dy_act, W, dx, nullptr, M, K, N, N, K, lddx, 0, dx_accumulate ? 1 : 0, 1.0f, N, 1,
+                               ST(stream));
     LAUNCHED();
   }
   if (dW) {  // dW[N][K] += scale * dy_act^T[N][M] * x[M][K]
-    int splits = (148 * 2) / (((K + BN - 1) / BN) * ((N + BM - 1) / BM));
+    int splits = (148 * 2) / (((K + BN - 1) / BN) * ((N + 127) / 128));
     if (splits < 1) splits = 1;
     int kps = (M + splits - 1) / splits;
     kps = (kps + BK - 1) / BK * BK;
     splits = (M + kps - 1) / kps;
-    dim3 grid((K + BN - 1) / BN, (N + BM - 1) / BM, splits);
-    sgemm_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(dy_act, x, dW, nullptr, N, K, M, N, ldx, K, 0, 1,
-                                                            scale, kps);
+    launch_sgemm<true, false>(dy_act, x, dW, nullptr, N, K, M, N, ldx, K, 0, 1, scale, kps, splits, ST(stream));
     LAUNCHED();
   }
   if (db) {

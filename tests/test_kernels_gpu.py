@@ -403,7 +403,8 @@ def test_bce_logits_and_mse(use_mask):
     assert abs(ls2.item() - l2.item()) / l2.item() < 1e-5 and rel_err(dr, 0.5 * rr.grad) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,K,act", [(50, 512, 7, 1), (130, 512, 512, 0), (64, 7, 512, 0), (33, 512, 256, 1)])
+@pytest.mark.parametrize("M,N,K,act", [(50, 512, 7, 1), (130, 512, 512, 0), (64, 7, 512, 0), (33, 512, 256, 1),
+                                        (4100, 512, 512, 1), (2051, 256, 513, 0), (1024, 7, 512, 0), (4096, 512, 7, 1)])
 def test_linear_f32(M, N, K, act):
     ops = _ops()
     torch.manual_seed(16)
