@@ -26,6 +26,7 @@ extern "C" {
 
 #define MMDYN_MAX_TAPS 16
 #define MMDYN_MAX_PHASES 4
+#define MMDYN_MAX_GROUPS 8
 
 /* --- library ------------------------------------------------------------------------------- */
 const char* mmdyn_last_error(void);
@@ -72,7 +73,8 @@ typedef struct mmdyn_igemm_desc {
   int32_t out_mode;     /* 0: fp16 rows, 1: fp32 rows, 2: fp32 rows atomicAdd,
                            3: fp32 NCHW planes from merged 2x2 sub-pixel phases (N = 16, 12 used),
                            4: fp16 NHWC from merged 2x2 sub-pixel phases: n = (ph*2+pw)*ldc + c goes
-                              to pixel (2*yv+ph, 2*xv+pw), channel c (ldc = channels, multiple of 16) */
+                              to pixel (2*yv+ph, 2*xv+pw), channel c (ldc = channels, multiple of 16),
+                           5: as 3 with the BCE loss + logit gradient fused (bce_* fields below)        */
   int32_t OH, OW;       /* output spatial size                                                 */
   int32_t s_out;
   int32_t off_y[MMDYN_MAX_PHASES], off_x[MMDYN_MAX_PHASES];
@@ -82,6 +84,21 @@ typedef struct mmdyn_igemm_desc {
                            a_pix_stride < Cin the "pixels" overlap: a window of Cin/a_pix_stride
                            physical pixels is one tap (used by the 3-channel logits layer, whose
                            4 x-taps of 8 padded channels are one 64-byte window; TMA path only)   */
+  /* out_mode 5 only — the logits layer with the reconstruction loss fused into its epilogue
+   * (vae.py:277 + problems.py:409-413, 431-449): per output pixel BCE-with-logits against
+   * bce_target (and bce_mask), summed into bce_loss[bce_slot[group]], gradient
+   * gscale*(sigmoid(x*m) - t*m)*m written as fp16 NHWC8 with a one-pixel border (see mmdyn_bce_logits,
+   * pad = 1).  group = image / bce_rows_per_group; every group is compared with the same
+   * bce_rows_per_group target images.  The fp32 NCHW logits themselves are only stored for images
+   * in [logit_row_lo, logit_row_hi). */
+  const float* bce_target;
+  const float* bce_mask;       /* optional */
+  void* bce_dlogits;           /* optional (forward-only evaluation) */
+  float* bce_loss;
+  float bce_gscale;
+  int32_t bce_rows_per_group;
+  int32_t bce_slot[MMDYN_MAX_GROUPS]; /* < 0: group carries no loss (its gradient rows are left untouched) */
+  int32_t logit_row_lo, logit_row_hi;
 } mmdyn_igemm_desc;
 int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream);
 

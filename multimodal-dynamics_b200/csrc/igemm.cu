@@ -551,13 +551,22 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       y_l = (r >> g.lbw) & ((1 << g.lbh) - 1);
       n_l = r >> (g.lbw + g.lbh);
     }
+    // out_mode 5: BCE partial sum of this thread for loss slot bce_cur; a tile lies within one image
+    // (checked by the launcher), so slot changes are warp-uniform and rare (<= groups per CTA)
+    float bce_acc = 0.0f;
+    int bce_cur = -1;
+    auto bce_flush = [&]() {
+      const float v = warp_sum(bce_acc);
+      if (lane == 0 && bce_cur >= 0) atomicAdd(d.bce_loss + bce_cur, v);
+      bce_acc = 0.0f;
+    };
     int tl = 0;
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord2 t = decode_tile2(d, g, tile);
       const int img = t.img0 + n_l, yv = t.y0 + y_l, xv = t.x0 + x_l;
       const bool valid = img < d.n_img;
       int out_off;
-      if (d.out_mode == 3) {
+      if (d.out_mode == 3 || d.out_mode == 5) {
         out_off = valid ? ((img * 3 * d.OH) + 2 * yv) * d.OW + 2 * xv : -1;
       } else {
         const int oy = yv * d.s_out + d.off_y[t.phase], ox = xv * d.s_out + d.off_x[t.phase];
@@ -569,6 +578,30 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
         if (!g.pixel_major || A_MODE != 0) n_live = kb_end - kb_begin;
         else
           for (int kb = kb_begin; kb < kb_end; ++kb) n_live += kb_live(t, kb) ? 1 : 0;
+      }
+      // out_mode 5: the targets (and mask) of this thread's 2x2x3 output pixels depend on the tile
+      // coordinates only, so they are requested BEFORE waiting for the accumulator: their latency
+      // hides behind the tile's MMAs instead of serialising the epilogue
+      float2 bce_t[6], bce_m[6];
+      int bce_slot_now = -1;
+      if constexpr (BLOCK_N == 16) {
+        if (d.out_mode == 5 && valid) {
+          const int grp = img / d.bce_rows_per_group;
+          bce_slot_now = d.bce_slot[grp];
+          if (bce_slot_now >= 0) {
+            const int plane = d.OH * d.OW;
+            const int toff = (((img - grp * d.bce_rows_per_group) * 3) * d.OH + 2 * yv) * d.OW + 2 * xv;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int ph = 0; ph < 2; ++ph) {
+                bce_t[c * 2 + ph] = __ldg(reinterpret_cast<const float2*>(d.bce_target + toff + c * plane + ph * d.OW));
+                bce_m[c * 2 + ph] = d.bce_mask ? __ldg(reinterpret_cast<const float2*>(d.bce_mask + toff + c * plane +
+                                                                                       ph * d.OW))
+                                               : make_float2(1.0f, 1.0f);
+              }
+          }
+        }
       }
       const int acc = tl & 1;
       mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
@@ -612,6 +645,60 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
           float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;
 #pragma unroll
           for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
+        } else if (d.out_mode == 5) {
+          if constexpr (BLOCK_N == 16) {
+            const int plane = d.OH * d.OW;
+            if (img >= d.logit_row_lo && img < d.logit_row_hi) {
+              float* o = reinterpret_cast<float*>(d.out) + out_off;
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph)
+                  *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
+                      make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
+            }
+            const int slot = bce_slot_now;
+            if (slot >= 0) {
+              if (slot != bce_cur) {
+                bce_flush();
+                bce_cur = slot;
+              }
+              float gq[4][4];
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph) {
+                  const float2 tv = bce_t[c * 2 + ph], mv = bce_m[c * 2 + ph];
+                  const float ts[2] = {tv.x, tv.y}, ms[2] = {mv.x, mv.y};
+#pragma unroll
+                  for (int pw = 0; pw < 2; ++pw) {
+                    const float m = ms[pw], x = f[(ph * 2 + pw) * 3 + c] * m, tt = ts[pw] * m;
+                    // torch's stable form max(x,0) - x*t + log(1 + exp(-|x|)) on the SFU (ex2, lg2, rcp):
+                    // log(1+e) loses relative accuracy only where the term is < 1e-7 of the O(1) summands,
+                    // and the 4 epilogue warps of a CTA cannot afford ~100 instructions per logit
+                    const float e = __expf(-fabsf(x));
+                    const float r = __fdividef(1.0f, 1.0f + e);
+                    bce_acc += fmaxf(x, 0.0f) - x * tt + __logf(1.0f + e);
+                    const float sig = x >= 0.0f ? r : e * r;
+                    gq[ph * 2 + pw][c] = d.bce_gscale * (sig - tt) * m;
+                  }
+                }
+              if (d.bce_dlogits) {
+                __half* go = reinterpret_cast<__half*>(d.bce_dlogits);
+#pragma unroll
+                for (int ph = 0; ph < 2; ++ph) {
+                  const long long pix =
+                      (static_cast<long long>(img) * (d.OH + 2) + 2 * yv + ph + 1) * (d.OW + 2) + 2 * xv + 1;
+                  uint4* o4 = reinterpret_cast<uint4*>(go + pix * 8);
+#pragma unroll
+                  for (int pw = 0; pw < 2; ++pw) {
+                    const float* q = gq[ph * 2 + pw];
+                    o4[pw] = make_uint4(pack_h2(q[0], q[1]), pack_h2(q[2], 0.0f), 0u, 0u);
+                  }
+                }
+              }
+            }
+          }
         } else {
           // merged 2x2 sub-pixel phases -> fp32 NCHW planes; n = (ph*2 + pw)*3 + c
           float* o = reinterpret_cast<float*>(d.out) + out_off;
@@ -627,6 +714,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[acc]));  // accumulator stage free for tile tl + 2
     }
+    if (d.out_mode == 5) bce_flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -1282,7 +1370,14 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
                 d->block_n);
   MMDYN_REQUIRE(d->ksplit >= 1 && (d->ksplit == 1 || d->out_mode == 2),
                 "igemm: ksplit=%d needs out_mode 2", d->ksplit);
-  MMDYN_REQUIRE(d->out_mode >= 0 && d->out_mode <= 4, "igemm: out_mode=%d", d->out_mode);
+  MMDYN_REQUIRE(d->out_mode >= 0 && d->out_mode <= 5, "igemm: out_mode=%d", d->out_mode);
+  if (d->out_mode == 5) {
+    MMDYN_REQUIRE(d->block_n == 16 && d->N == 16 && d->bce_target && d->bce_loss && d->bce_rows_per_group > 0 &&
+                      d->n_img <= MMDYN_MAX_GROUPS * d->bce_rows_per_group && d->P >= 128 && d->P % 128 == 0 &&
+                      d->ksplit == 1,
+                  "igemm: out_mode 5 needs N=16, bce_target, bce_loss, rows_per_group > 0, <= %d groups, "
+                  "P a multiple of 128", MMDYN_MAX_GROUPS);
+  }
   MMDYN_REQUIRE(d->out_mode != 4 || (d->ldc % 16 == 0 && d->N == 4 * d->ldc && d->s_out == 2 && d->n_phases == 1),
                 "igemm: out_mode 4 needs N = 4*ldc, ldc %% 16 == 0, s_out = 2");
   MMDYN_REQUIRE(d->out_mode != 3 || (d->block_n == 16 && d->N == 16), "igemm: out_mode 3 needs N=16");
@@ -1378,6 +1473,8 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
                      static_cast<int>(ar), d->Cin, d->IW, d->IH, abox[0], abox[1], abox[2], abox[3], es);
       return MMDYN_ERR_CUDA;
     }
+    MMDYN_REQUIRE(d->out_mode != 5 || (g.bn == 1 && !g.pixel_major),
+                  "igemm: out_mode 5 needs tiles that lie within one image (OXv=%d P=%d)", d->OXv, d->P);
     const int occ = g_tma_occ[occ_idx];
     switch (d->block_n) {
       case 16: return dispatch_amode<16>(a_mode, d, tmA, tm, g, occ, st);
@@ -1389,6 +1486,7 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
   }
 
   // ---- cp.async gather path (any dense geometry) -------------------------------------------------
+  MMDYN_REQUIRE(d->out_mode != 5, "igemm: out_mode 5 needs the TMA path");
   MMDYN_REQUIRE(!custom_strides, "igemm: a_row_stride / a_img_stride / overlapping windows need the TMA path "
                 "(Cin=%d ntaps=%d)", d->Cin, d->ntaps);
   long long m_tiles_ll;

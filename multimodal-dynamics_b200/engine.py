@@ -274,10 +274,12 @@ class _NetBase:
         self.packer.refresh(self.arena)
 
 
-def _ig(pl, which, A, out, n_img, bias=None, f32_out=False):
+def _ig(pl, which, A, out, n_img, bias=None, f32_out=False, bce=None):
     """One implicit-GEMM launch of layer `pl` ('fwd' or 'dgrad'); fp32 outputs may split K."""
     geom, W = (pl.lp.fwd, pl.Wf) if which == "fwd" else (pl.lp.dgrad, pl.Wd)
     kw = dict(tag=f"{pl.lp.name}.{which}", macs_per_img=pl.lp.extra.get("macs"))
+    if bce is not None:
+        kw["bce"] = bce
     ks = plan.choose_ksplit(geom, n_img) if f32_out else 1
     if ks > 1:
         out.zero_()
@@ -323,27 +325,41 @@ class _BN:
         self.net, self.name, self.C = net, idx_name, C
 
     def forward(self, raw, act, G, rows, alloc, key, track, repeat=1):
+        st = self.alloc_fwd(G, alloc, key)
+        self.run_fwd(raw, act, G, rows, st, 0, track, repeat)
+        return st[1], st[2]
+
+    def alloc_fwd(self, G, alloc, key):
+        C = self.C
+        return (alloc(key + ".sums", (G, C, 2), F32, zero=True), alloc(key + ".ab", (G, C, 2), F32),
+                alloc(key + ".mi", (G, C, 2), F32))
+
+    def run_fwd(self, raw, act, Gc, rows, st, g0, track, repeat=1):
+        """Groups g0 .. g0+Gc-1: `raw` / `act` hold exactly these groups' rows, `st` = alloc_fwd(...) of all groups."""
         net, C = self.net, self.C
-        sums = alloc(key + ".sums", (G, C, 2), F32, zero=True)
-        ab = alloc(key + ".ab", (G, C, 2), F32)
-        mi = alloc(key + ".mi", (G, C, 2), F32)
-        ops.bn_stats(raw, sums, G, rows, C)
+        sums, ab, mi = (t[g0:g0 + Gc] for t in st)
+        ops.bn_stats(raw, sums, Gc, rows, C)
         rm = net.buf(self.name + ".running_mean") if track else None
         rv = net.buf(self.name + ".running_var") if track else None
         ops.bn_finalize(sums, net.pview(self.name + ".weight"), net.pview(self.name + ".bias"), ab, mi, rm, rv,
-                        G, rows, C, 1e-5, 0.1, repeat)
+                        Gc, rows, C, 1e-5, 0.1, repeat)
         if track:
-            net.buf(self.name + ".num_batches_tracked").add_(G * repeat)
-        ops.bn_swish_fwd(raw, ab, act, G, rows, C)
-        return ab, mi
+            net.buf(self.name + ".num_batches_tracked").add_(Gc * repeat)
+        ops.bn_swish_fwd(raw, ab, act, Gc, rows, C)
 
     def backward(self, raw, ab, mi, dAct, G, rows, alloc, key, unscale):
+        st = self.alloc_bwd(G, alloc, key)
+        return self.run_bwd(raw, ab, mi, dAct, G, rows, st, 0, unscale)
+
+    def alloc_bwd(self, G, alloc, key):
+        return alloc(key + ".sums2", (G, self.C, 2), F32, zero=True), alloc(key + ".coef", (G, self.C, 4), F32)
+
+    def run_bwd(self, raw, ab, mi, dAct, Gc, rows, st, g0, unscale):
         net, C = self.net, self.C
-        sums2 = alloc(key + ".sums2", (G, C, 2), F32, zero=True)
-        ops.bn_swish_bwd_reduce(raw, ab, mi, dAct, sums2, G, rows, C)
-        coef = alloc(key + ".coef", (G, C, 4), F32)
-        ops.bn_bwd_apply(raw, ab, mi, sums2, dAct, net.pview(self.name + ".weight", True),
-                         net.pview(self.name + ".bias", True), coef, G, rows, C, unscale)
+        sums2, coef = st[0][g0:g0 + Gc], st[1][g0:g0 + Gc]
+        ops.bn_swish_bwd_reduce(raw, ab[g0:g0 + Gc], mi[g0:g0 + Gc], dAct, sums2, Gc, rows, C)
+        ops.bn_bwd_apply(raw, ab[g0:g0 + Gc], mi[g0:g0 + Gc], sums2, dAct, net.pview(self.name + ".weight", True),
+                         net.pview(self.name + ".bias", True), coef, Gc, rows, C, unscale)
         return dAct  # now dRaw
 
 
@@ -459,61 +475,102 @@ class DecoderExec(_NetBase):
         self.d4 = self._pl(plan.deconv_out_plan("deconv4", self.off("hallucinate.9.weight"), 32, 3, 32))
         self.bn1, self.bn2, self.bn3 = _BN(self, "hallucinate.1", 128), _BN(self, "hallucinate.4", 64), _BN(self, "hallucinate.7", 32)
 
-    def forward(self, zh, G, B, alloc, key, track=True):
-        """zh: (G*B, 256) fp16 latent rows, group-major.  Returns record with fp32 NCHW logits."""
+    def forward(self, zh, G, B, alloc, key, track=True, fused_loss=None):
+        """zh: (G*B, 256) fp16 latent rows, group-major.  Returns record with fp32 NCHW logits.
+
+        fused_loss: dict(target (B,3,64,64), mask|None, dlogits (G*B,66,66,8)|None, loss (fp32 vector),
+        slots [loss index per group or -1], gscale, logit_groups (g_lo, g_hi)): the BCE reconstruction
+        loss and its logit gradient are computed in the epilogue of the logits layer (problems.py:409-413,
+        431-449); logits are then only written for the groups in logit_groups.
+
+        BatchNorm statistics are per group, so the groups are independent and the layer chain can run
+        on a subset of the groups at a time (MMDYN_GROUP_CHUNK, see _group_chunk: an L2-residency
+        experiment that measured slower than one launch over all groups, which stays the default)."""
         self.refresh()
         R = G * B
         r = {"zh": zh, "G": G, "B": B}
         raw0 = alloc(key + ".raw0", (R, 5, 5, 256), F16)
-        _ig(self.up, "fwd", zh, raw0, R, self.up.bias)
         act0 = alloc(key + ".act0", (R, 5, 5, 256), F16)
-        ops.bn_swish_fwd(raw0, None, act0, 1, R * 25, 256)
         raw1 = alloc(key + ".raw1", (R, 8, 8, 128), F16)
-        _ig(self.d1, "fwd", act0, raw1, R)
         act1 = alloc(key + ".act1", (R, 8, 8, 128), F16)
-        r["bn1"] = self.bn1.forward(raw1, act1, G, B * 64, alloc, key + ".bn1", track)
         raw2 = alloc(key + ".raw2", (R, 16, 16, 64), F16)
-        _ig(self.d2, "fwd", act1, raw2, R)
         act2 = alloc(key + ".act2", (R, 16, 16, 64), F16)
-        r["bn2"] = self.bn2.forward(raw2, act2, G, B * 256, alloc, key + ".bn2", track)
         raw3 = alloc(key + ".raw3", (R, 32, 32, 32), F16)
-        _ig(self.d3, "fwd", act2, raw3, R)
         act3 = alloc(key + ".act3", (R, 32, 32, 32), F16)
-        r["bn3"] = self.bn3.forward(raw3, act3, G, B * 1024, alloc, key + ".bn3", track)
         logits = alloc(key + ".logits", (R, 3, 64, 64), F32)
-        _ig(self.d4, "fwd", act3, logits, R)
+        s1, s2, s3 = (bn.alloc_fwd(G, alloc, key + nm) for bn, nm in ((self.bn1, ".bn1"), (self.bn2, ".bn2"), (self.bn3, ".bn3")))
+        Gc = _group_chunk(G, B)
+        for g0 in range(0, G, Gc):
+            sl, n = slice(g0 * B, (g0 + Gc) * B), Gc * B
+            _ig(self.up, "fwd", zh[sl], raw0[sl], n, self.up.bias)
+            ops.bn_swish_fwd(raw0[sl], None, act0[sl], 1, n * 25, 256)
+            _ig(self.d1, "fwd", act0[sl], raw1[sl], n)
+            self.bn1.run_fwd(raw1[sl], act1[sl], Gc, B * 64, s1, g0, track)
+            _ig(self.d2, "fwd", act1[sl], raw2[sl], n)
+            self.bn2.run_fwd(raw2[sl], act2[sl], Gc, B * 256, s2, g0, track)
+            _ig(self.d3, "fwd", act2[sl], raw3[sl], n)
+            self.bn3.run_fwd(raw3[sl], act3[sl], Gc, B * 1024, s3, g0, track)
+            if fused_loss is not None:
+                fl = fused_loss
+                lo, hi = fl["logit_groups"]
+                bce = dict(target=fl["target"], mask=fl.get("mask"), loss=fl["loss"], gscale=fl["gscale"],
+                           dlogits=fl["dlogits"][sl] if fl.get("dlogits") is not None else None, rows_per_group=B,
+                           slots=fl["slots"][g0:g0 + Gc],
+                           logit_rows=(max(lo - g0, 0) * B, max(min(hi - g0, Gc), 0) * B))
+                _ig(self.d4, "fwd", act3[sl], logits[sl], n, bce=bce)
+            else:
+                _ig(self.d4, "fwd", act3[sl], logits[sl], n)
+            if self.after_group is not None:
+                self.after_group(g0, Gc, logits[sl])
+        r["bn1"], r["bn2"], r["bn3"] = (s1[1], s1[2]), (s2[1], s2[2]), (s3[1], s3[2])
         r.update(raw0=raw0, act0=act0, raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3,
                  logits=logits)
         return r
+
+    after_group = None  # optional callback(g0, Gc, logits_rows) run right after a group chunk's logits (fused losses)
 
     def backward(self, r, dl8, alloc, key, unscale, gp=None):
         """dl8: (G*B, 66, 66, 8) fp16 logit gradients with a one-pixel ZERO border (3 channels used, times grad_scale).
         Returns dz (G*B, 256) fp32 (times grad_scale)."""
         arena, G, B = self.arena, r["G"], r["B"]
         R = G * B
-        _wgrad_into(self.d4, dl8, r["act3"], R, arena, alloc, key + ".dW_d4", unscale, gp)
         g3 = alloc(key + ".g3", (R, 32, 32, 32), F16)
-        _ig(self.d4, "dgrad", dl8, g3, R)
-        self.bn3.backward(r["raw3"], r["bn3"][0], r["bn3"][1], g3, G, B * 1024, alloc, key + ".bn3", unscale)
-        _wgrad_into(self.d3, g3, r["act2"], R, arena, alloc, key + ".dW_d3", unscale, gp)
         g2 = alloc(key + ".g2", (R, 16, 16, 64), F16)
-        _ig(self.d3, "dgrad", g3, g2, R)
-        self.bn2.backward(r["raw2"], r["bn2"][0], r["bn2"][1], g2, G, B * 256, alloc, key + ".bn2", unscale)
-        _wgrad_into(self.d2, g2, r["act1"], R, arena, alloc, key + ".dW_d2", unscale, gp)
         g1 = alloc(key + ".g1", (R, 8, 8, 128), F16)
-        _ig(self.d2, "dgrad", g2, g1, R)
-        self.bn1.backward(r["raw1"], r["bn1"][0], r["bn1"][1], g1, G, B * 64, alloc, key + ".bn1", unscale)
-        _wgrad_into(self.d1, g1, r["act0"], R, arena, alloc, key + ".dW_d1", unscale, gp)
-        g0 = alloc(key + ".g0", (R, 5, 5, 256), F16)
-        _ig(self.d1, "dgrad", g1, g0, R)
-        ops.bn_swish_bwd_reduce(r["raw0"], None, None, g0, None, 1, R * 25, 256)
+        g0_ = alloc(key + ".g0", (R, 5, 5, 256), F16)
+        b1, b2, b3 = (bn.alloc_bwd(G, alloc, key + nm) for bn, nm in ((self.bn1, ".bn1"), (self.bn2, ".bn2"), (self.bn3, ".bn3")))
+        Gc = _group_chunk(G, B)
+        for g0 in range(0, G, Gc):
+            sl, n = slice(g0 * B, (g0 + Gc) * B), Gc * B
+            _wgrad_into(self.d4, dl8[sl], r["act3"][sl], n, arena, alloc, key + ".dW_d4", unscale, gp)
+            _ig(self.d4, "dgrad", dl8[sl], g3[sl], n)
+            self.bn3.run_bwd(r["raw3"][sl], r["bn3"][0], r["bn3"][1], g3[sl], Gc, B * 1024, b3, g0, unscale)
+            _wgrad_into(self.d3, g3[sl], r["act2"][sl], n, arena, alloc, key + ".dW_d3", unscale, gp)
+            _ig(self.d3, "dgrad", g3[sl], g2[sl], n)
+            self.bn2.run_bwd(r["raw2"][sl], r["bn2"][0], r["bn2"][1], g2[sl], Gc, B * 256, b2, g0, unscale)
+            _wgrad_into(self.d2, g2[sl], r["act1"][sl], n, arena, alloc, key + ".dW_d2", unscale, gp)
+            _ig(self.d2, "dgrad", g2[sl], g1[sl], n)
+            self.bn1.run_bwd(r["raw1"][sl], r["bn1"][0], r["bn1"][1], g1[sl], Gc, B * 64, b1, g0, unscale)
+            _wgrad_into(self.d1, g1[sl], r["act0"][sl], n, arena, alloc, key + ".dW_d1", unscale, gp)
+            _ig(self.d1, "dgrad", g1[sl], g0_[sl], n)
+            ops.bn_swish_bwd_reduce(r["raw0"][sl], None, None, g0_[sl], None, 1, n * 25, 256)
         dbp = alloc(key + ".db_up", (6400,), F32, zero=True)
-        ops.colsum_f16(g0, dbp, R, 6400, 6400, unscale)
+        ops.colsum_f16(g0_, dbp, R, 6400, 6400, unscale)
         ops.unpack_add_f32(dbp, self.up.bias_idx, arena.grad)
-        _wgrad_into(self.up, r["zh"], g0, R, arena, alloc, key + ".dW_up", unscale, gp)
+        _wgrad_into(self.up, r["zh"], g0_, R, arena, alloc, key + ".dW_up", unscale, gp)
         dz = alloc(key + ".dz", (R, 256), F32)
-        _ig(self.up, "dgrad", g0, dz, R, None, True)
+        _ig(self.up, "dgrad", g0_, dz, R, None, True)
         return dz
+
+
+def _group_chunk(G, B):
+    """Groups per launch of the decoder chain.  MMDYN_GROUP_CHUNK overrides (0 = all groups in one
+    launch); default: all groups in one launch."""
+    env = os.environ.get("MMDYN_GROUP_CHUNK")
+    if env is not None:
+        v = int(env)
+        return G if v <= 0 else max(1, min(G, v))
+    return G  # measured (round 1, batch 1024): per-group launches are slower — see DESIGN.md, dead ends
 
 
 # ---------------------------------------------------------------------------------------------
@@ -651,6 +708,9 @@ class StepEngine:
         self.noise_src = noise_src
         self.exact = bool(exact_running_stats)
         self.grad_scale = grad_scale
+        # reconstruction BCE + logit gradient in the epilogue of the logits layer (igemm out_mode 5);
+        # MMDYN_NO_FUSED_BCE=1 keeps the separate mmdyn_bce_logits pass (A/B measurements, debugging)
+        self.fuse_bce = os.environ.get("MMDYN_NO_FUSED_BCE") is None
         if kind == "vae":
             self.mods = {"x": ("encoder", "decoder")}
             self.passes = [("x",)]
@@ -836,15 +896,39 @@ class StepEngine:
         def dec_branch(m):
             def fn():
                 G = len(dec_groups[m])
-                dec_rec[m] = ex["dec"][self.mods[m][1]].forward(zdec[m], G, B, ws, "dec_" + m, True)
+                dex = ex["dec"][self.mods[m][1]]
                 # one-pixel zero border (zeroed at allocation, never written): deconv4's backward reads
                 # the 4 x-taps of a pixel as one 64-byte window (plan.deconv_out_plan)
                 dl8[m] = ws("dl8_" + m, (G * B, 66, 66, 8), F16, zero=self.exact) if need_grad else None
-                for i in enc_passes[m]:
-                    g = dec_groups[m].index(i)
-                    k = slot[(m, i)]
-                    ops.bce_logits(dec_rec[m]["logits"][g * B:(g + 1) * B], ts[m], loss_mask, scal[k:k + 1],
-                                   dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64, 64, 1)
+
+                slots = [slot[(m, i)] if i in enc_passes[m] else -1 for i in dec_groups[m]]
+                if self.fuse_bce:
+                    # logits are only materialised where something reads them: the joint pass for
+                    # `outputs`, every group when the (unmasked) metric must be recomputed from them
+                    if not want_outputs:
+                        lg = (0, 0)
+                    elif loss_mask is not None or self.kind == "vae":
+                        lg = (0, G)
+                    else:
+                        jg = dec_groups[m].index(3 if self.use_pose else 0)
+                        lg = (jg, jg + 1)
+                    fl = dict(target=ts[m], mask=loss_mask, dlogits=dl8[m], loss=scal, slots=slots, gscale=gs / B,
+                              logit_groups=lg)
+                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True, fused_loss=fl)
+                    return
+
+                def losses(g0, Gc, lg_rows):  # right after a group chunk's logits, while they are L2-resident
+                    for g in range(g0, g0 + Gc):
+                        if slots[g] < 0:
+                            continue
+                        k = slots[g]
+                        ops.bce_logits(lg_rows[(g - g0) * B:(g - g0 + 1) * B], ts[m], loss_mask, scal[k:k + 1],
+                                       dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64, 64, 1)
+                dex.after_group = losses
+                try:
+                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True)
+                finally:
+                    dex.after_group = None
             return fn
 
         def pose_dec():

@@ -13,6 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 MAX_TAPS = 16
 MAX_PHASES = 4
+MAX_GROUPS = 8
 
 
 class MmdynError(RuntimeError):
@@ -30,6 +31,9 @@ class IgemmDesc(C.Structure):
         ("out_mode", C.c_int32), ("OH", C.c_int32), ("OW", C.c_int32), ("s_out", C.c_int32),
         ("off_y", C.c_int32 * MAX_PHASES), ("off_x", C.c_int32 * MAX_PHASES), ("ldc", C.c_int32),
         ("a_row_stride", C.c_int32), ("a_img_stride", C.c_int32),
+        ("bce_target", C.c_void_p), ("bce_mask", C.c_void_p), ("bce_dlogits", C.c_void_p), ("bce_loss", C.c_void_p),
+        ("bce_gscale", C.c_float), ("bce_rows_per_group", C.c_int32), ("bce_slot", C.c_int32 * MAX_GROUPS),
+        ("logit_row_lo", C.c_int32), ("logit_row_hi", C.c_int32),
     ]
 
 

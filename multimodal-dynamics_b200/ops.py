@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import lib as _lib
-from .lib import IgemmDesc, WgradDesc, MAX_PHASES, MAX_TAPS, check
+from .lib import IgemmDesc, WgradDesc, MAX_GROUPS, MAX_PHASES, MAX_TAPS, check
 
 
 def _ptr(t):
@@ -82,7 +82,9 @@ def _esz(t):
 
 
 def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None, a_pix_stride=None, tag="igemm",
-          macs_per_img=None):
+          macs_per_img=None, bce=None):
+    """bce (out_mode 5, the logits layer with its loss fused): dict(target, mask, dlogits, loss, gscale,
+    rows_per_group, slots=[loss index per group or -1], logit_rows=(lo, hi))."""
     d = IgemmDesc()
     d.A, d.W, d.out = A.data_ptr(), Wp.data_ptr(), out.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
@@ -99,6 +101,14 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     d.OH, d.OW, d.s_out = geom.OH, geom.OW, geom.s_out
     d.ldc = geom.ldc if ldc is None else ldc
     d.a_row_stride, d.a_img_stride = geom.a_row_stride, geom.a_img_stride
+    if bce is not None:
+        d.out_mode = 5
+        d.bce_target, d.bce_mask = bce["target"].data_ptr(), _ptr(bce.get("mask"))
+        d.bce_dlogits, d.bce_loss = _ptr(bce.get("dlogits")), bce["loss"].data_ptr()
+        d.bce_gscale, d.bce_rows_per_group = bce["gscale"], bce["rows_per_group"]
+        for g in range(MAX_GROUPS):
+            d.bce_slot[g] = bce["slots"][g] if g < len(bce["slots"]) else -1
+        d.logit_row_lo, d.logit_row_hi = bce["logit_rows"]
 
     def alg():
         # algorithmic work: true MACs of the layer (no padding / phase-union waste) and one read of

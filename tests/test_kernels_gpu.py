@@ -157,6 +157,50 @@ def test_deconv4_out():
     check_conv_layer(plan.deconv_out_plan("d4", 0, 32, 3, 32), w, x, 2, 1, True, grad_pad=8, border=1)
 
 
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_deconv4_fused_bce_epilogue(use_mask):
+    """igemm out_mode 5: logits layer + BCE-with-logits (sum) + logit gradient in one launch, against
+    torch conv_transpose2d + binary_cross_entropy_with_logits on the same fp16-rounded operands;
+    3 groups of 2 images share the 2 target images, group 1 carries no loss, logits stored for rows 2..3."""
+    ops = _ops()
+    torch.manual_seed(21)
+    lp = plan.deconv_out_plan("d4", 0, 32, 3, 32)
+    w = torch.randn(32, 3, 4, 4) * 0.1
+    x = torch.randn(6, 32, 32, 32)
+    t = torch.rand(2, 3, 64, 64)
+    m = (torch.rand(2, 3, 64, 64) > 0.4).float() if use_mask else None
+    xr = r16(x).requires_grad_(True)
+    y = F.conv_transpose2d(xr, r16(w), stride=2, padding=1)
+    loss_ref = []
+    for g in range(3):
+        yg, tt = y[2 * g:2 * g + 2], t.double()
+        if use_mask:
+            yg, tt = yg * m.double(), tt * m.double()
+        loss_ref.append(F.binary_cross_entropy_with_logits(yg, tt, reduction="sum"))
+    (loss_ref[0] + loss_ref[2]).backward(retain_graph=True)
+    dy_ref = torch.autograd.grad(loss_ref[0] + loss_ref[2], y, retain_graph=True)[0]
+    logits = torch.full((6, 3, 64, 64), -77.0, device=DEV)
+    dl = torch.full((6, 66, 66, 8), 7.0, dtype=torch.float16, device=DEV)
+    loss = torch.zeros(4, device=DEV)
+    bce = dict(target=t.to(DEV), mask=m.to(DEV) if use_mask else None, dlogits=dl, loss=loss, gscale=2.0,
+               rows_per_group=2, slots=[0, -1, 2], logit_rows=(2, 4))
+    ops.igemm(lp.fwd, nhwc16(x), packed(w, lp.idx_fwd), logits, 6, bce=bce)
+    torch.cuda.synchronize()
+    assert rel_err(logits[2:4], y[2:4].detach()) < 5e-4
+    assert (logits[:2] == -77.0).all() and (logits[4:] == -77.0).all()
+    lc = loss.cpu().double()
+    assert abs(lc[0] - loss_ref[0].item()) / loss_ref[0].item() < 1e-5 and lc[1] == 0 and lc[3] == 0
+    assert abs(lc[2] - loss_ref[2].item()) / loss_ref[2].item() < 1e-5
+    inner = dl[:, 1:65, 1:65]
+    for g in (0, 2):
+        assert rel_err(inner[2 * g:2 * g + 2, :, :, :3].permute(0, 3, 1, 2), 2.0 * dy_ref[2 * g:2 * g + 2]) < 1.5e-3
+        assert inner[2 * g:2 * g + 2, :, :, 3:].abs().max().item() == 0
+    assert (dl[2:4] == 7.0).all()                                   # group without a loss: untouched
+    bord = dl.clone()
+    bord[:, 1:65, 1:65] = 7.0
+    assert (bord == 7.0).all()                                      # border never written
+
+
 @pytest.mark.parametrize("M", [5, 128, 300])
 def test_linear_fc_splitk_and_heads(M):
     ops = _ops()
