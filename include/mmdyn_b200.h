@@ -148,7 +148,7 @@ int mmdyn_bn_stats(const void* x, float* sums /*[G][C][2] zeroed*/, int G, int r
 int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* ab /*[G][C][2]*/,
                       float* mean_invstd /*[G][C][2]*/, float* running_mean, float* running_var,
                       int G, int rows_per_group, int C, float eps, float momentum, int stat_repeat,
-                      void* stream);
+                      long long* num_batches_tracked /* nullable int64 counter += G*stat_repeat */, void* stream);
 /* y = swish(a*x + b); ab == NULL means identity affine (plain Swish) */
 int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_per_group, int C,
                        void* stream);
@@ -240,6 +240,9 @@ int mmdyn_gather_f32(const float* src, const int32_t* idx, float* dst, long long
  * each parameter element appears at most once in idx */
 int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float* dst, long long n,
                          void* stream);
+/* dst[k] += src[inv[k]] for inv[k] >= 0, k < n: the same scatter driven by the inverse map (every
+ * arena element has at most one packed source), so the arena is touched with coalesced accesses */
+int mmdyn_gather_add_f32(const float* src, const int32_t* inv, float* dst, long long n, void* stream);
 /* dst = fp16(scale * src) */
 int mmdyn_f32_to_f16(const float* src, void* dst, long long n, float scale, void* stream);
 /* x *= s in place */

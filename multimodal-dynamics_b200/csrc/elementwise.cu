@@ -89,8 +89,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    const float* __restrict__ beta, float* __restrict__ ab,
                                    float* __restrict__ mean_invstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int G, int n, int C, float eps,
-                                   float momentum, int stat_repeat) {
+                                   float momentum, int stat_repeat, long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += static_cast<long long>(G) * stat_repeat;
   if (c >= C) return;
   const float inv_n = 1.0f / static_cast<float>(n);
   const float unbias = n > 1 ? static_cast<float>(n) / static_cast<float>(n - 1) : 1.0f;
@@ -924,6 +925,18 @@ unpack_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx
   }
 }
 
+// dst[k] += src[inv[k]] (inv[k] < 0: nothing): the scatter above turned inside out — coalesced
+// read-modify-write of the gradient arena, gathered reads of the (L2-resident) packed gradients
+__global__ void __launch_bounds__(256)
+gather_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ inv, float* __restrict__ dst,
+                  long long n) {
+  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int32_t i = __ldg(inv + k);
+    if (i >= 0) dst[k] += __ldg(src + i);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, float scale) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -1156,11 +1169,11 @@ extern "C" int mmdyn_bn_stats(const void* x, float* sums, int G, int rows_per_gr
 extern "C" int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, float* ab,
                                  float* mean_invstd, float* running_mean, float* running_var, int G,
                                  int rows_per_group, int C, float eps, float momentum, int stat_repeat,
-                                 void* stream) {
+                                 long long* num_batches_tracked, void* stream) {
   MMDYN_REQUIRE(sums && gamma && beta && ab && mean_invstd && G > 0 && C > 0, "bn_finalize: bad arguments");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, gamma, beta, ab, mean_invstd, running_mean,
                                                                running_var, G, rows_per_group, C, eps, momentum,
-                                                               stat_repeat);
+                                                               stat_repeat, num_batches_tracked);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1404,6 +1417,13 @@ extern "C" int mmdyn_gather_f32(const float* src, const int32_t* idx, float* dst
 extern "C" int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && idx && dst && n > 0, "unpack_add: bad arguments");
   unpack_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_gather_add_f32(const float* src, const int32_t* inv, float* dst, long long n, void* stream) {
+  MMDYN_REQUIRE(src && inv && dst && n > 0, "gather_add: bad arguments");
+  gather_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, inv, dst, n);
   LAUNCHED();
   return MMDYN_OK;
 }

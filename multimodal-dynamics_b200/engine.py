@@ -47,19 +47,48 @@ class FreshAlloc:
 class Workspace:
     """Persistent named buffers (fused step: stable addresses, CUDA-graph friendly)."""
 
+    POOL_BYTES = 8 << 20
+
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self.pools = []      # fp32 chunks holding every zero="step" buffer: ONE memset per chunk and step
+        self.pool_used = 0   # floats used in the last chunk
 
     def __call__(self, key, shape, dtype, zero=False):
+        """zero=True: zeroed on every call.  zero="step": fp32 accumulator that only needs to be zero when
+        the step starts (BatchNorm sums, bias-gradient partials ...) — carved out of a pool that
+        begin_step() clears with a single memset instead of one fill kernel per buffer."""
         shape = tuple(int(s) for s in shape)
         t = self.bufs.get(key)
         if t is None or tuple(t.shape) != shape or t.dtype != dtype:
-            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            if zero == "step" and dtype == F32:
+                t = self._from_pool(shape)
+            else:
+                t = torch.zeros(shape, dtype=dtype, device=self.device)
             self.bufs[key] = t
-        elif zero:
+        elif zero is True:
             t.zero_()
         return t
+
+    def _from_pool(self, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        n_al = (n + 63) // 64 * 64
+        cap = self.POOL_BYTES // 4
+        if n_al > cap:
+            return torch.zeros(shape, dtype=F32, device=self.device)  # too big to pool; caller gets zero=True semantics
+        if not self.pools or self.pool_used + n_al > cap:
+            self.pools.append(torch.zeros(cap, dtype=F32, device=self.device))
+            self.pool_used = 0
+        t = self.pools[-1][self.pool_used:self.pool_used + n].view(shape)
+        self.pool_used += n_al
+        return t
+
+    def begin_step(self):
+        for p in self.pools:
+            p.zero_()
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
@@ -230,6 +259,17 @@ class GradPack:
             off += idx.numel()
         self.idx = torch.cat(parts)
         self.buf = torch.zeros(off, dtype=F32, device=device)
+        # inverse map over the arena range this sub-network's weights occupy: the flush then walks the
+        # arena (coalesced read-modify-write) and gathers from the packed buffer instead of scattering
+        idx_h = self.idx.cpu().numpy()
+        pos = np.nonzero(idx_h >= 0)[0]
+        tgt = idx_h[pos]
+        self.lo, self.inv = 0, None
+        if tgt.size and np.unique(tgt).size == tgt.size:
+            self.lo, hi = int(tgt.min()), int(tgt.max()) + 1
+            inv = np.full(hi - self.lo, -1, np.int32)
+            inv[tgt - self.lo] = pos.astype(np.int32)
+            self.inv = torch.from_numpy(inv).to(device)
         self.wstream = torch.cuda.Stream(device=device) if os.environ.get("MMDYN_SERIAL_BRANCHES") is None else None
 
     def begin(self):
@@ -242,7 +282,10 @@ class GradPack:
     def flush(self, arena):
         if self.wstream is not None:
             torch.cuda.current_stream().wait_stream(self.wstream)
-        ops.unpack_add_f32(self.buf, self.idx, arena.grad)
+        if self.inv is not None:
+            ops.gather_add_f32(self.buf, self.inv, arena.grad[self.lo:self.lo + self.inv.numel()])
+        else:
+            ops.unpack_add_f32(self.buf, self.idx, arena.grad)
 
 
 class _NetBase:
@@ -331,7 +374,7 @@ class _BN:
 
     def alloc_fwd(self, G, alloc, key):
         C = self.C
-        return (alloc(key + ".sums", (G, C, 2), F32, zero=True), alloc(key + ".ab", (G, C, 2), F32),
+        return (alloc(key + ".sums", (G, C, 2), F32, zero="step"), alloc(key + ".ab", (G, C, 2), F32),
                 alloc(key + ".mi", (G, C, 2), F32))
 
     def run_fwd(self, raw, act, Gc, rows, st, g0, track, repeat=1):
@@ -341,10 +384,9 @@ class _BN:
         ops.bn_stats(raw, sums, Gc, rows, C)
         rm = net.buf(self.name + ".running_mean") if track else None
         rv = net.buf(self.name + ".running_var") if track else None
+        nbt = net.buf(self.name + ".num_batches_tracked") if track else None
         ops.bn_finalize(sums, net.pview(self.name + ".weight"), net.pview(self.name + ".bias"), ab, mi, rm, rv,
-                        Gc, rows, C, 1e-5, 0.1, repeat)
-        if track:
-            net.buf(self.name + ".num_batches_tracked").add_(Gc * repeat)
+                        Gc, rows, C, 1e-5, 0.1, repeat, nbt)
         ops.bn_swish_fwd(raw, ab, act, Gc, rows, C)
 
     def backward(self, raw, ab, mi, dAct, G, rows, alloc, key, unscale):
@@ -352,7 +394,7 @@ class _BN:
         return self.run_bwd(raw, ab, mi, dAct, G, rows, st, 0, unscale)
 
     def alloc_bwd(self, G, alloc, key):
-        return alloc(key + ".sums2", (G, self.C, 2), F32, zero=True), alloc(key + ".coef", (G, self.C, 4), F32)
+        return alloc(key + ".sums2", (G, self.C, 2), F32, zero="step"), alloc(key + ".coef", (G, self.C, 4), F32)
 
     def run_bwd(self, raw, ab, mi, dAct, Gc, rows, st, g0, unscale):
         net, C = self.net, self.C
@@ -425,7 +467,7 @@ class EncoderExec(_NetBase):
         rows = nm * B
         dh16 = alloc(key + ".dheads16", (rows, 512), F16)
         ops.f32_to_f16(d_heads, dh16, rows * 512, in_scale)
-        db = alloc(key + ".db512", (512,), F32, zero=True)
+        db = alloc(key + ".db512", (512,), F32, zero="step")
         ops.colsum_f32(d_heads, db, rows, 512, 512, unscale * in_scale)
         ops.unpack_add_f32(db, self.heads.bias_idx, arena.grad)
         _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale, gp)
@@ -554,7 +596,7 @@ class DecoderExec(_NetBase):
             _wgrad_into(self.d1, g1[sl], r["act0"][sl], n, arena, alloc, key + ".dW_d1", unscale, gp)
             _ig(self.d1, "dgrad", g1[sl], g0_[sl], n)
             ops.bn_swish_bwd_reduce(r["raw0"][sl], None, None, g0_[sl], None, 1, n * 25, 256)
-        dbp = alloc(key + ".db_up", (6400,), F32, zero=True)
+        dbp = alloc(key + ".db_up", (6400,), F32, zero="step")
         ops.colsum_f16(g0_, dbp, R, 6400, 6400, unscale)
         ops.unpack_add_f32(dbp, self.up.bias_idx, arena.grad)
         _wgrad_into(self.up, r["zh"], g0_, R, arena, alloc, key + ".dW_up", unscale, gp)
@@ -806,6 +848,7 @@ class StepEngine:
                                       "(the reference keeps model.train() even for validation: problems.py:174)")
         arena, ex = self._setup(first.device)
         ws, B, D = self.ws, first.shape[0], 256
+        ws.begin_step()
         for k in xs:
             xs[k] = xs[k].contiguous().float()
             ts[k] = ts[k].contiguous().float()
@@ -854,7 +897,7 @@ class StepEngine:
         pose_rec = pose_box.get("rec")
 
         # PoE + reparam + KL per pass
-        scal = ws("scal", (64,), F32, zero=True)
+        scal = ws("scal", (64,), F32, zero="step")
         mu_all, lv_all = ws("mu", (npass, B, D), F32), ws("lv", (npass, B, D), F32)
         zscr = ws("z_scratch", (B, D), F32)
         zdec = {m: ws("z_" + m, (len(dec_groups[m]) * B, D), F16) for m in img_mods}

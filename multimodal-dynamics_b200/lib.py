@@ -65,7 +65,7 @@ SIGNATURES = {
     "mmdyn_conv1_fwd": ([_P, _P, _P, _I, _P], _I),
     "mmdyn_conv1_wgrad": ([_P, _P, _P, _I, _F, _I, _P], _I),
     "mmdyn_bn_stats": ([_P, _P, _I, _I, _I, _P], _I),
-    "mmdyn_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
+    "mmdyn_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P], _I),
     "mmdyn_bn_swish_fwd": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_swish_bwd_reduce": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_bwd_apply": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P], _I),
@@ -85,6 +85,7 @@ SIGNATURES = {
     "mmdyn_pack_f16": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_gather_f32": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_unpack_add_f32": ([_P, _P, _P, _LL, _P], _I),
+    "mmdyn_gather_add_f32": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_f32_to_f16": ([_P, _P, _LL, _F, _P], _I),
     "mmdyn_scale_f32": ([_P, _LL, _F, _P], _I),
     "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _I, _I, _P], _I),

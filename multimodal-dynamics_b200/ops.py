@@ -161,11 +161,11 @@ def bn_stats(x, sums, G, rows, Cch):
 
 
 def bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows, Cch, eps, momentum,
-                stat_repeat=1):
+                stat_repeat=1, num_batches_tracked=None):
     with _Timed("bn_finalize", None):
         check(_L().mmdyn_bn_finalize(_ptr(sums), _ptr(gamma), _ptr(beta), _ptr(ab), _ptr(mean_invstd),
                                      _ptr(running_mean), _ptr(running_var), G, rows, Cch, eps, momentum, stat_repeat,
-                                     _stream()),
+                                     _ptr(num_batches_tracked), _stream()),
               "bn_finalize")
 
 
@@ -271,6 +271,12 @@ def pack_f16(src, idx, dst):
 def gather_f32(src, idx, dst):
     with _Timed("gather_f32", None):
         check(_L().mmdyn_gather_f32(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), _stream()), "gather_f32")
+
+
+def gather_add_f32(src, inv, dst):
+    """dst[k] += src[inv[k]] where inv[k] >= 0 (dst: a slice of the gradient arena)."""
+    with _Timed("unpack_add_f32", lambda: (0.0, inv.numel() * 16.0)):
+        check(_L().mmdyn_gather_add_f32(_ptr(src), _ptr(inv), _ptr(dst), inv.numel(), _stream()), "gather_add_f32")
 
 
 def unpack_add_f32(src, idx, dst):

@@ -301,10 +301,12 @@ def test_grouped_bn_swish_fwd_bwd(C, rows, G):
     mi = torch.empty(G, C, 2, device=DEV)
     rmd, rvd = rm.to(DEV), rv.to(DEV)
     ops.bn_stats(xd, sums, G, rows, C)
-    ops.bn_finalize(sums, gamma.to(DEV), beta.to(DEV), ab, mi, rmd, rvd, G, rows, C, 1e-5, 0.1)
+    nbt = torch.full((), 5, dtype=torch.int64, device=DEV)
+    ops.bn_finalize(sums, gamma.to(DEV), beta.to(DEV), ab, mi, rmd, rvd, G, rows, C, 1e-5, 0.1, 1, nbt)
     yd = torch.empty_like(xd)
     ops.bn_swish_fwd(xd, ab, yd, G, rows, C)
     torch.cuda.synchronize()
+    assert nbt.item() == 5 + G  # num_batches_tracked: one BatchNorm invocation per group
     assert rel_err(yd, y) < 1e-3
     assert rel_err(rmd, rm_ref) < 1e-5 and rel_err(rvd, rv_ref) < 1e-5
     dyd = dy.to(DEV).clone()
