@@ -149,6 +149,12 @@ int mmdyn_bn_finalize(const float* sums, const float* gamma, const float* beta, 
                       float* mean_invstd /*[G][C][2]*/, float* running_mean, float* running_var,
                       int G, int rows_per_group, int C, float eps, float momentum, int stat_repeat,
                       long long* num_batches_tracked /* nullable int64 counter += G*stat_repeat */, void* stream);
+/* mmdyn_bn_finalize + mmdyn_bn_swish_fwd in one launch (the streaming kernel derives scale/shift from
+ * `sums` itself, publishes ab / mean_invstd for the backward and updates the running statistics). */
+int mmdyn_bn_finalize_swish_fwd(const void* x, const float* sums, const float* gamma, const float* beta, float* ab,
+                                float* mean_invstd, float* running_mean, float* running_var,
+                                long long* num_batches_tracked, void* y, int G, int rows_per_group, int C, float eps,
+                                float momentum, int stat_repeat, void* stream);
 /* y = swish(a*x + b); ab == NULL means identity affine (plain Swish) */
 int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G, int rows_per_group, int C,
                        void* stream);

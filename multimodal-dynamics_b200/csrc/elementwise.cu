@@ -341,6 +341,27 @@ bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ coef
 // register budget; the 256 threads consume a stage with conflict-free 16-byte shared loads (same
 // thread -> 8-channel-vector mapping as above, so per-channel coefficients stay in registers).
 // ---------------------------------------------------------------------------------------------
+struct BnFinalizeArgs {  // sums == nullptr: scale/shift come precomputed (ab)
+  const float* sums;
+  const float* gamma;
+  const float* beta;
+  float* ab;
+  float* mean_invstd;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float eps, momentum;
+  int stat_repeat;
+};
+struct BnBwdFinalArgs {  // sums2 == nullptr: coefficients come precomputed (coef)
+  const float* ab;
+  const float* mean_invstd;
+  const float* sums2;
+  float* dgamma;
+  float* dbeta;
+  float inv_n, unscale;
+};
+
 constexpr int BS_STAGE_BYTES = 16384;
 constexpr int BS_ROWS_PER_THREAD = 4;  // rows_per_stage <= 4 * row_lanes for every C (8192/C vs 2048/C)
 
@@ -438,15 +459,59 @@ bn_stats_bulk_kernel(const __half* __restrict__ x, float* __restrict__ sums, int
 template <int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_swish_fwd_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
-                         int rows_per_group, int C, int rows_per_chunk) {
+                         int rows_per_group, int C, int rows_per_chunk, BnFinalizeArgs fin) {
   BS_PROLOGUE(1, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
   BS_START(STAGES);
   float a[8], b[8];
+  if (fin.sums) {
+    // bn_finalize folded in: every thread derives scale/shift of its 8 channels from the statistics
+    // (same arithmetic everywhere, so all CTAs agree bit for bit); chunk 0 of each group publishes
+    // ab / mean_invstd for the backward, CTA (0,0) updates the running statistics in group order
+    const float inv_n = 1.0f / static_cast<float>(rows_per_group);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] = ab[(g * C + vec * 8 + i) * 2];
-    b[i] = ab[(g * C + vec * 8 + i) * 2 + 1];
+    for (int i = 0; i < 8; ++i) {
+      const int c = vec * 8 + i;
+      const float sm = fin.sums[(g * C + c) * 2], ss = fin.sums[(g * C + c) * 2 + 1];
+      const float mean = sm * inv_n;
+      const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
+      const float invstd = rsqrtf(var + fin.eps);
+      a[i] = fin.gamma[c] * invstd;
+      b[i] = fin.beta[c] - mean * a[i];
+      if (blockIdx.x == 0 && rl == 0) {
+        fin.ab[(g * C + c) * 2] = a[i];
+        fin.ab[(g * C + c) * 2 + 1] = b[i];
+        fin.mean_invstd[(g * C + c) * 2] = mean;
+        fin.mean_invstd[(g * C + c) * 2 + 1] = invstd;
+      }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (threadIdx.x == 0 && fin.num_batches_tracked)
+        *fin.num_batches_tracked += static_cast<long long>(gridDim.y) * fin.stat_repeat;
+      if (fin.running_mean && fin.running_var) {
+        const float n = static_cast<float>(rows_per_group);
+        const float unbias = rows_per_group > 1 ? n / (n - 1.0f) : 1.0f;
+        for (int c = threadIdx.x; c < C; c += RED_THREADS) {
+          float rm = fin.running_mean[c], rv = fin.running_var[c];
+          for (int gg = 0; gg < static_cast<int>(gridDim.y); ++gg) {
+            const float mean = fin.sums[(gg * C + c) * 2] * inv_n;
+            const float var = fmaxf(fin.sums[(gg * C + c) * 2 + 1] * inv_n - mean * mean, 0.0f);
+            for (int q = 0; q < fin.stat_repeat; ++q) {
+              rm = (1.0f - fin.momentum) * rm + fin.momentum * mean;
+              rv = (1.0f - fin.momentum) * rv + fin.momentum * var * unbias;
+            }
+          }
+          fin.running_mean[c] = rm;
+          fin.running_var[c] = rv;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i] = ab[(g * C + vec * 8 + i) * 2];
+      b[i] = ab[(g * C + vec * 8 + i) * 2 + 1];
+    }
   }
   for (int it = 0; it < st.n_iter; ++it) {
     const int s = it % STAGES;
@@ -530,19 +595,44 @@ bn_swish_bwd_reduce_bulk_kernel(const __half* __restrict__ x, const float* __res
 template <int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ coef, __half* __restrict__ dU,
-                         int rows_per_group, int C, int rows_per_chunk) {
+                         int rows_per_group, int C, int rows_per_chunk, BnBwdFinalArgs fin) {
   BS_PROLOGUE(2, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
   st.src[1] = reinterpret_cast<const uint8_t*>(dU + base);
   BS_START(STAGES);
   float ka[8], kb[8], kc[8], ks[8];
+  if (fin.sums2) {
+    // bn_bwd_coef and bn_param_grad folded in (see bn_bwd_coef_kernel for the algebra)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 k = *reinterpret_cast<const float4*>(coef + (static_cast<long long>(g) * C + vec * 8 + i) * 4);
-    ka[i] = k.x;
-    kb[i] = k.y;
-    kc[i] = k.z;
-    ks[i] = k.w;
+    for (int i = 0; i < 8; ++i) {
+      const int gc = g * C + vec * 8 + i;
+      const float a = fin.ab[2 * gc], mean = fin.mean_invstd[2 * gc], invstd = fin.mean_invstd[2 * gc + 1];
+      const float m1 = fin.sums2[2 * gc] * fin.inv_n, m2 = fin.sums2[2 * gc + 1] * fin.inv_n;
+      ka[i] = a;
+      kb[i] = -a * m2 * invstd;
+      kc[i] = a * (m2 * invstd * mean - m1);
+      ks[i] = fin.ab[2 * gc + 1];
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && fin.dgamma && fin.dbeta) {
+      for (int c = threadIdx.x; c < C; c += RED_THREADS) {
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int gg = 0; gg < static_cast<int>(gridDim.y); ++gg) {
+          s1 += fin.sums2[(gg * C + c) * 2];
+          s2 += fin.sums2[(gg * C + c) * 2 + 1];
+        }
+        fin.dgamma[c] += fin.unscale * s2;
+        fin.dbeta[c] += fin.unscale * s1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 k = *reinterpret_cast<const float4*>(coef + (static_cast<long long>(g) * C + vec * 8 + i) * 4);
+      ka[i] = k.x;
+      kb[i] = k.y;
+      kc[i] = k.z;
+      ks[i] = k.w;
+    }
   }
   for (int it = 0; it < st.n_iter; ++it) {
     const int s = it % STAGES;
@@ -1185,9 +1275,10 @@ extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G
   if (ab && use_bulk() && bulk_ok(C)) {
     int rpc;
     const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
+    BnFinalizeArgs fin = {};
     bn_swish_fwd_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
                                               ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
-                                                            reinterpret_cast<__half*>(y), rows_per_group, C, rpc);
+                                                            reinterpret_cast<__half*>(y), rows_per_group, C, rpc, fin);
     LAUNCHED();
     return MMDYN_OK;
   }
@@ -1204,6 +1295,29 @@ extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G
                                                                rows_per_group, C);
   LAUNCHED();
   return MMDYN_OK;
+}
+
+extern "C" int mmdyn_bn_finalize_swish_fwd(const void* x, const float* sums, const float* gamma, const float* beta,
+                                          float* ab, float* mean_invstd, float* running_mean, float* running_var,
+                                          long long* num_batches_tracked, void* y, int G, int rows_per_group, int C,
+                                          float eps, float momentum, int stat_repeat, void* stream) {
+  MMDYN_REQUIRE(x && sums && gamma && beta && ab && mean_invstd && y && G > 0 && rows_per_group > 0 && C % 8 == 0,
+                "bn_finalize_swish_fwd: bad arguments");
+  if (use_bulk() && bulk_ok(C)) {
+    int rpc;
+    const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
+    BnFinalizeArgs fin = {sums, gamma, beta, ab, mean_invstd, running_mean, running_var, num_batches_tracked,
+                          eps, momentum, stat_repeat};
+    bn_swish_fwd_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
+                                              ST(stream)>>>(reinterpret_cast<const __half*>(x), nullptr,
+                                                            reinterpret_cast<__half*>(y), rows_per_group, C, rpc, fin);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
+  const int rc = mmdyn_bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows_per_group,
+                                   C, eps, momentum, stat_repeat, num_batches_tracked, stream);
+  if (rc != MMDYN_OK) return rc;
+  return mmdyn_bn_swish_fwd(x, ab, y, G, rows_per_group, C, stream);
 }
 
 extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const float* mean_invstd, void* dY,
@@ -1241,23 +1355,24 @@ extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* m
                                   int rows_per_group, int C, float grad_unscale, void* stream) {
   MMDYN_REQUIRE(x && ab && mean_invstd && sums2 && dU && G > 0 && C % 8 == 0, "bn_bwd_apply: bad arguments");
   MMDYN_REQUIRE(coef_scratch, "bn_bwd_apply: coef_scratch ([G][C][4] floats) is required");
-  const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
+  MMDYN_REQUIRE(bn_c_ok(C), "bn_bwd_apply: C=%d unsupported", C);
+  int rpc;
+  if (use_bulk() && bulk_ok(C)) {  // coefficients and parameter gradients are derived inside the streaming kernel
+    const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
+    BnBwdFinalArgs fin = {ab, mean_invstd, sums2, dgamma, dbeta, 1.0f / static_cast<float>(rows_per_group),
+                          grad_unscale};
+    bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>
+        <<<dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream)>>>(
+            reinterpret_cast<const __half*>(x), nullptr, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc, fin);
+    LAUNCHED();
+    return MMDYN_OK;
+  }
   bn_bwd_coef_kernel<<<(G * C + 127) / 128, 128, 0, ST(stream)>>>(ab, mean_invstd, sums2, coef_scratch, G * C,
                                                                    1.0f / static_cast<float>(rows_per_group));
   LAUNCHED();
-  MMDYN_REQUIRE(bn_c_ok(C), "bn_bwd_apply: C=%d unsupported", C);
-  (void)n_vec;
-  int rpc;
-  if (use_bulk() && bulk_ok(C)) {
-    const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
-    bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>
-        <<<dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream)>>>(
-            reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
-  } else {
-    const int chunks = chunking(rows_per_group, G, C, &rpc);
-    bn_bwd_apply_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
-        reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
-  }
+  const int chunks = chunking(rows_per_group, G, C, &rpc);
+  bn_bwd_apply_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
+      reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
   LAUNCHED();
   if (dgamma && dbeta) {
     bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums2, dgamma, dbeta, G, C, grad_unscale);

@@ -385,9 +385,8 @@ class _BN:
         rm = net.buf(self.name + ".running_mean") if track else None
         rv = net.buf(self.name + ".running_var") if track else None
         nbt = net.buf(self.name + ".num_batches_tracked") if track else None
-        ops.bn_finalize(sums, net.pview(self.name + ".weight"), net.pview(self.name + ".bias"), ab, mi, rm, rv,
-                        Gc, rows, C, 1e-5, 0.1, repeat, nbt)
-        ops.bn_swish_fwd(raw, ab, act, Gc, rows, C)
+        ops.bn_finalize_swish_fwd(raw, sums, net.pview(self.name + ".weight"), net.pview(self.name + ".bias"), ab, mi,
+                                  rm, rv, nbt, act, Gc, rows, C, 1e-5, 0.1, repeat)
 
     def backward(self, raw, ab, mi, dAct, G, rows, alloc, key, unscale):
         st = self.alloc_bwd(G, alloc, key)

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mmdyn_conv1_wgrad": ([_P, _P, _P, _I, _F, _I, _P], _I),
     "mmdyn_bn_stats": ([_P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P], _I),
+    "mmdyn_bn_finalize_swish_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
     "mmdyn_bn_swish_fwd": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_swish_bwd_reduce": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_bwd_apply": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P], _I),

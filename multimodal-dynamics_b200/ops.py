@@ -160,6 +160,15 @@ def bn_stats(x, sums, G, rows, Cch):
         check(_L().mmdyn_bn_stats(_ptr(x), _ptr(sums), G, rows, Cch, _stream()), "bn_stats")
 
 
+def bn_finalize_swish_fwd(x, sums, gamma, beta, ab, mean_invstd, running_mean, running_var, num_batches_tracked, y, G,
+                          rows, Cch, eps, momentum, stat_repeat=1):
+    with _Timed("bn_swish_fwd", lambda: (0.0, G * rows * Cch * 4.0)):
+        check(_L().mmdyn_bn_finalize_swish_fwd(_ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(ab), _ptr(mean_invstd),
+                                               _ptr(running_mean), _ptr(running_var), _ptr(num_batches_tracked),
+                                               _ptr(y), G, rows, Cch, eps, momentum, stat_repeat, _stream()),
+              "bn_finalize_swish_fwd")
+
+
 def bn_finalize(sums, gamma, beta, ab, mean_invstd, running_mean, running_var, G, rows, Cch, eps, momentum,
                 stat_repeat=1, num_batches_tracked=None):
     with _Timed("bn_finalize", None):

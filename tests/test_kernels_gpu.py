@@ -308,6 +308,14 @@ def test_grouped_bn_swish_fwd_bwd(C, rows, G):
     torch.cuda.synchronize()
     assert nbt.item() == 5 + G  # num_batches_tracked: one BatchNorm invocation per group
     assert rel_err(yd, y) < 1e-3
+    # the single-launch form (finalize folded into the streaming kernel) must agree bit for bit
+    ab2, mi2, yd2 = torch.empty_like(ab), torch.empty_like(mi), torch.empty_like(yd)
+    rm2, rv2, nbt2 = rm.to(DEV), rv.to(DEV), torch.full((), 5, dtype=torch.int64, device=DEV)
+    ops.bn_finalize_swish_fwd(xd, sums, gamma.to(DEV), beta.to(DEV), ab2, mi2, rm2, rv2, nbt2, yd2, G, rows, C,
+                              1e-5, 0.1, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(ab2, ab) and torch.equal(mi2, mi) and torch.equal(yd2, yd)
+    assert torch.equal(rm2, rmd) and torch.equal(rv2, rvd) and nbt2.item() == 5 + G
     assert rel_err(rmd, rm_ref) < 1e-5 and rel_err(rvd, rv_ref) < 1e-5
     dyd = dy.to(DEV).clone()
     sums2 = torch.zeros(G, C, 2, device=DEV)
