@@ -258,6 +258,22 @@ int mmdyn_scale_f32(float* x, long long n, float s, void* stream);
 int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int H, int W,
                           int pad, void* stream);
 
+/* --- device-side input pipeline --------------------------------------------
+ * replaces transforms.Compose([Resize(input_size), ToTensor()]) per frame (utils/datasets.py:23-31,
+ * 382-392) and the batch assembly of seq_collate_fn (:395-404) for uint8 frames kept in HBM.
+ * Bit-identical to Pillow's Image.resize(BILINEAR) (antialiased triangle filter, 22-bit fixed point,
+ * horizontal then vertical pass, each rounded to uint8) followed by uint8 / 255.
+ *   mmdyn_resize_table_ints : number of int32 entries of the coefficient table for these sizes
+ *   mmdyn_resize_table      : fills the table on the HOST (double precision, as precompute_coeffs +
+ *                             normalize_coeffs_8bpc); the caller copies it to the device once
+ *   mmdyn_frames_u8_to_f32  : out[i] (fp32, 3 x out_h x out_w, planar) = ToTensor(Resize(frames[index[i]]));
+ *                             frames: uint8 [N][in_h][in_w][3]; index: int64 device array or NULL (= i)
+ */
+int mmdyn_resize_table_ints(int in_h, int in_w, int out_h, int out_w);
+int mmdyn_resize_table(int in_h, int in_w, int out_h, int out_w, int32_t* table_host, int n_ints);
+int mmdyn_frames_u8_to_f32(const void* frames_u8, const long long* index, const int32_t* table_dev,
+                           float* out_nchw, int n, int in_h, int in_w, int out_h, int out_w, void* stream);
+
 /* --- fused Adam over a flat fp32 arena (problems.py:138,155; torch.optim.Adam defaults) --------
  * p, g, m, v: [n] fp32.  step_count is the 1-based step AFTER this update (bias correction).
  * g is multiplied by gscale first (e.g. 1/world_size after a sum-allreduce). */

@@ -339,3 +339,28 @@ def fill_dropout_mask(out, n, p_drop, seed, offset, ctr=None):
 def rng_advance(ctr, inc):
     with _Timed("rng_advance", None):
         check(_L().mmdyn_rng_advance(_ptr(ctr), inc, _stream()), "rng_advance")
+
+
+def resize_table(in_h, in_w, out_h, out_w):
+    """Host-side coefficient table of the PIL-exact bilinear resize (int32 CPU tensor; no GPU needed)."""
+    L = _lib.load()  # host-only entry points: no device initialisation
+    n = L.mmdyn_resize_table_ints(in_h, in_w, out_h, out_w)
+    if n <= 0:
+        raise ValueError(f"resize_table: bad sizes {(in_h, in_w, out_h, out_w)}")
+    t = torch.empty(n, dtype=torch.int32)
+    check(L.mmdyn_resize_table(in_h, in_w, out_h, out_w, t.data_ptr(), n), "resize_table")
+    return t
+
+
+def frames_u8_to_f32(frames, index, table_dev, out):
+    """out[i] = ToTensor(Resize(frames[index[i]])): frames uint8 (N,H,W,3), index int64 (n,) or None, out fp32 (n,3,h,w)."""
+    n, _, oh, ow = out.shape
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3 and frames.is_contiguous()
+    assert index is None or (index.dtype == torch.int64 and index.numel() == n)
+    with _Timed("frames_u8_to_f32", lambda: (0.0, n * (frames.shape[1] * frames.shape[2] * 3.0 + 3 * oh * ow * 4.0))):
+        for s in range(0, n, 32768):  # grid.y limit
+            e = min(n, s + 32768)
+            check(_L().mmdyn_frames_u8_to_f32(_ptr(frames), _ptr(index[s:e]) if index is not None else
+                                              (None if s == 0 else _ptr(torch.arange(s, e, device=out.device))),
+                                              _ptr(table_dev), _ptr(out[s:e]), e - s, frames.shape[1], frames.shape[2],
+                                              oh, ow, _stream()), "frames_u8_to_f32")
