@@ -258,6 +258,25 @@ int mmdyn_scale_f32(float* x, long long n, float s, void* stream);
 int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int H, int W,
                           int pad, void* stream);
 
+/* --- CVAE conditioning (vae.py:231-237, 286-291) ---------------------------
+ * torch.cat((x, c), -1) followed by Linear(K0 + cd, N) = Linear on x (tensor cores, weight columns
+ * 0..K0-1) + the rank-cd term c . W[:, K0:]^T, computed here in fp32 with the weight columns
+ * addressed in place (row pitch ldw = K0 + cd).
+ *   linear_f32_acc   : y[M][N] += x[M][K] . W[N][K]^T                 (pitches ldx, ldw, ldy)
+ *   linear_f32_wgrad : dW[N][K] += scale * dy[M][N]^T . x[M][K]       (pitches lddy, ldx, ldw)
+ *   cond_add_f16     : raw[r][n'] (fp16) += sum_j c[r][j] * W[n_idx[n']*ldw + col0 + j]   (decoder upsample,
+ *                      whose fp16 output columns are permuted: n_idx = torch row of packed column n')
+ *   cond_wgrad_f16   : dW[n_idx[n']*ldw + col0 + j] += scale * sum_r g[r][n'] * c[r][j]
+ */
+int mmdyn_linear_f32_acc(const float* x, const float* W, float* y, int M, int N, int K, int ldx, int ldw, int ldy,
+                         void* stream);
+int mmdyn_linear_f32_wgrad(const float* x, const float* dy, float* dW, int M, int N, int K, int ldx, int lddy,
+                           int ldw, float scale, void* stream);
+int mmdyn_cond_add_f16(void* raw, const float* c, const float* W, const int32_t* n_idx, int R, int N, int ldw,
+                       int col0, int cd, void* stream);
+int mmdyn_cond_wgrad_f16(const void* g, const float* c, float* dW, const int32_t* n_idx, int R, int N, int ldw,
+                         int col0, int cd, float scale, void* stream);
+
 /* --- device-side input pipeline --------------------------------------------
  * replaces transforms.Compose([Resize(input_size), ToTensor()]) per frame (utils/datasets.py:23-31,
  * 382-392) and the batch assembly of seq_collate_fn (:395-404) for uint8 frames kept in HBM.

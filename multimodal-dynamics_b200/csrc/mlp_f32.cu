@@ -200,6 +200,77 @@ act_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy, float
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CVAE conditioning (vae.py:231-237, 286-291): torch.cat((x, c), -1) in front of a Linear is the
+// Linear on x plus a rank-`cd` term  c . W[:, K0:K0+cd]^T  (cd = 3 shock-force components).  The big
+// part stays on the tensor cores; these kernels add the small term in fp32 and produce its weight
+// gradient, addressing the weight columns in place (row pitch ldw = K0 + cd) in the arena.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_COND = 8;
+
+// raw[r][n'] (fp16) += sum_j c[r][j] * W[n_idx[n'] * ldw + col0 + j]   (n_idx: arena row of packed column n')
+__global__ void __launch_bounds__(256)
+cond_add_f16_kernel(__half* __restrict__ raw, const float* __restrict__ c, const float* __restrict__ W,
+                    const int32_t* __restrict__ n_idx, int R, int N, int ldw, int col0, int cd) {
+  const int nv = N >> 3;
+  const long long total = static_cast<long long>(R) * nv;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(v / nv), n0 = static_cast<int>(v - static_cast<long long>(r) * nv) * 8;
+    float cv[MAX_COND];
+#pragma unroll
+    for (int j = 0; j < MAX_COND; ++j) cv[j] = j < cd ? __ldg(c + static_cast<long long>(r) * cd + j) : 0.0f;
+    uint4* p = reinterpret_cast<uint4*>(raw + static_cast<long long>(r) * N + n0);
+    uint4 u = *p;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      const float* w0 = W + static_cast<long long>(__ldg(n_idx + n0 + 2 * i)) * ldw + col0;
+      const float* w1 = W + static_cast<long long>(__ldg(n_idx + n0 + 2 * i + 1)) * ldw + col0;
+      for (int j = 0; j < cd; ++j) {
+        f.x = fmaf(cv[j], __ldg(w0 + j), f.x);
+        f.y = fmaf(cv[j], __ldg(w1 + j), f.y);
+      }
+      h[i] = __floats2half2_rn(f.x, f.y);
+    }
+    *p = u;
+  }
+}
+
+// dW[n_idx[n'] * ldw + col0 + j] += scale * sum_r g[r][n'] * c[r][j];  grid = (ceil(N/256), row chunks)
+__global__ void __launch_bounds__(256)
+cond_wgrad_f16_kernel(const __half* __restrict__ g, const float* __restrict__ c, float* __restrict__ dW,
+                      const int32_t* __restrict__ n_idx, int R, int N, int ldw, int col0, int cd, float scale,
+                      int rows_per_cta) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+  __shared__ float cs[64][MAX_COND];
+  float acc[MAX_COND];
+#pragma unroll
+  for (int j = 0; j < MAX_COND; ++j) acc[j] = 0.0f;
+  for (int rb = r0; rb < r1; rb += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * MAX_COND; i += 256) {
+      const int rr = i / MAX_COND, j = i - rr * MAX_COND;
+      cs[rr][j] = (rb + rr < r1 && j < cd) ? c[static_cast<long long>(rb + rr) * cd + j] : 0.0f;
+    }
+    __syncthreads();
+    if (n < N) {
+      const int lim = min(64, r1 - rb);
+      for (int rr = 0; rr < lim; ++rr) {
+        const float gv = __half2float(g[static_cast<long long>(rb + rr) * N + n]);
+#pragma unroll
+        for (int j = 0; j < MAX_COND; ++j) acc[j] = fmaf(gv, cs[rr][j], acc[j]);
+      }
+    }
+  }
+  if (n < N) {
+    float* o = dW + static_cast<long long>(n_idx[n]) * ldw + col0;
+    for (int j = 0; j < cd; ++j) atomicAdd(o + j, scale * acc[j]);
+  }
+}
+
 }  // namespace
 }  // namespace mmdyn
 
@@ -249,5 +320,58 @@ extern "C" int mmdyn_linear_f32_bwd(const float* x, const float* W, const float*
     const int rc = mmdyn_colsum_f32(dy_act, db, M, N, N, scale, stream);
     if (rc != MMDYN_OK) return rc;
   }
+  return MMDYN_OK;
+}
+
+// y[M][N] += x[M][K] . W[N][K]^T with explicit pitches (W may be a column slice of a wider matrix)
+extern "C" int mmdyn_linear_f32_acc(const float* x, const float* W, float* y, int M, int N, int K, int ldx, int ldw,
+                                    int ldy, void* stream) {
+  MMDYN_REQUIRE(x && W && y && M > 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N,
+                "linear_f32_acc: bad arguments");
+  launch_sgemm<false, true>(x, W, y, nullptr, M, N, K, ldx, ldw, ldy, 0, 1, 1.0f, K, 1, ST(stream));
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+// dW[N][K] (pitch ldw) += scale * dy[M][N]^T . x[M][K]
+extern "C" int mmdyn_linear_f32_wgrad(const float* x, const float* dy, float* dW, int M, int N, int K, int ldx,
+                                      int lddy, int ldw, float scale, void* stream) {
+  MMDYN_REQUIRE(x && dy && dW && M > 0 && N > 0 && K > 0 && ldx >= K && lddy >= N && ldw >= K,
+                "linear_f32_wgrad: bad arguments");
+  int splits = (148 * 2) / (((K + BN - 1) / BN) * ((N + 127) / 128));
+  if (splits < 1) splits = 1;
+  int kps = (M + splits - 1) / splits;
+  kps = (kps + BK - 1) / BK * BK;
+  splits = (M + kps - 1) / kps;
+  launch_sgemm<true, false>(dy, x, dW, nullptr, N, K, M, lddy, ldx, ldw, 0, 1, scale, kps, splits, ST(stream));
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_cond_add_f16(void* raw, const float* c, const float* W, const int32_t* n_idx, int R, int N,
+                                  int ldw, int col0, int cd, void* stream) {
+  MMDYN_REQUIRE(raw && c && W && n_idx && R > 0 && N > 0 && N % 8 == 0 && cd >= 1 && cd <= MAX_COND,
+                "cond_add_f16: bad arguments (N=%d must be a multiple of 8, 1 <= cd=%d <= %d)", N, cd, MAX_COND);
+  const long long total = static_cast<long long>(R) * (N >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cond_add_f16_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(reinterpret_cast<__half*>(raw), c, W, n_idx,
+                                                                         R, N, ldw, col0, cd);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_cond_wgrad_f16(const void* g, const float* c, float* dW, const int32_t* n_idx, int R, int N,
+                                    int ldw, int col0, int cd, float scale, void* stream) {
+  MMDYN_REQUIRE(g && c && dW && n_idx && R > 0 && N > 0 && cd >= 1 && cd <= MAX_COND,
+                "cond_wgrad_f16: bad arguments (1 <= cd=%d <= %d)", cd, MAX_COND);
+  const int gx = (N + 255) / 256;
+  int gy = (148 * 4 + gx - 1) / gx;
+  int rpc = (R + gy - 1) / gy;
+  rpc = (rpc + 63) / 64 * 64;
+  gy = (R + rpc - 1) / rpc;
+  cond_wgrad_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(g), c, dW, n_idx, R, N,
+                                                               ldw, col0, cd, scale, rpc);
+  LAUNCHED();
   return MMDYN_OK;
 }

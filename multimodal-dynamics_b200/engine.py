@@ -408,8 +408,11 @@ class _BN:
 # image encoder (vae.py:197-216, 224-242)
 # ---------------------------------------------------------------------------------------------
 class EncoderExec(_NetBase):
-    def __init__(self, arena, prefix, device):
+    def __init__(self, arena, prefix, device, cond_dim=0):
+        """cond_dim > 0: CVAE heads Linear(512 + cond_dim, 256) (vae.py:196, 231-237): the 512 feature
+        columns go through the tensor cores, the condition columns through mmdyn_linear_f32_acc."""
         super().__init__(arena, prefix, device)
+        self.cd = int(cond_dim)
         self.c1 = self._pl(plan.conv1_plan("conv1", self.off("conv_net.0.weight")))
         self.c2 = self._pl(plan.conv_s2_plan("conv2", self.off("conv_net.2.weight"), 32, 64, 32))
         self.c3 = self._pl(plan.conv_s2_plan("conv3", self.off("conv_net.5.weight"), 64, 128, 16))
@@ -418,14 +421,14 @@ class EncoderExec(_NetBase):
                                             6400, [512], k_perm=plan.nhwc_perm(256, 5, 5)))
         self.heads = self._pl(plan.linear_plan(
             "heads", [self.off("linear_means.weight"), self.off("linear_log_var.weight")],
-            [self.off("linear_means.bias"), self.off("linear_log_var.bias")], 512, [256, 256]))
+            [self.off("linear_means.bias"), self.off("linear_log_var.bias")], 512, [256, 256], ld=512 + self.cd))
         self.bn2, self.bn3, self.bn4 = _BN(self, "conv_net.3", 64), _BN(self, "conv_net.6", 128), _BN(self, "conv_net.9", 256)
         self.c1_wg, c1_idx = plan.conv1_wgrad_plan(self.off("conv_net.0.weight"))
         self.c1_idx = torch.from_numpy(c1_idx).to(device)
         self.extra_wgrads = {"conv1": self.c1_idx}
 
-    def forward(self, x, masks, alloc, key, track=True):
-        """x: (B,3,64,64) fp32 NCHW; masks: list of (B,512) fp32 dropout masks or None entries (one per
+    def forward(self, x, masks, alloc, key, track=True, cond=None):
+        """x: (B,3,64,64) fp32 NCHW; cond: (B, cond_dim) fp32 or None; masks: list of (B,512) fp32 dropout masks or None entries (one per
         pass sharing this trunk evaluation; BN running statistics are updated once per mask, as the
         reference's repeated forward passes would).  Returns a record whose 'heads' entry is
         (len(masks)*B, 512) fp32 = [mu | logvar] per mask."""
@@ -454,6 +457,14 @@ class EncoderExec(_NetBase):
         ops.swish_dropout_fwd(fc_raw, masks, h, B, 512)
         heads = alloc(key + ".heads", (nm * B, LATENT_HEADS), F32)
         _ig(self.heads, "fwd", h, heads, nm * B, self.heads.bias, True)
+        if self.cd:
+            if cond is None or tuple(cond.shape) != (B, self.cd):
+                raise ValueError(f"conditional encoder needs a condition of shape ({B}, {self.cd})")
+            for j in range(nm):
+                for half, nm_ in enumerate(("linear_means", "linear_log_var")):
+                    ops.linear_f32_acc(cond, self.pview(nm_ + ".weight")[512:], heads[j * B:(j + 1) * B, 256 * half:],
+                                       B, 256, self.cd, self.cd, 512 + self.cd, LATENT_HEADS)
+            r["cond"] = cond
         r.update(raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3, raw4=raw4, act4=act4,
                  fc_raw=fc_raw, h=h, heads=heads)
         return r
@@ -470,6 +481,12 @@ class EncoderExec(_NetBase):
         ops.colsum_f32(d_heads, db, rows, 512, 512, unscale * in_scale)
         ops.unpack_add_f32(db, self.heads.bias_idx, arena.grad)
         _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale, gp)
+        if self.cd:
+            for j in range(nm):
+                for half, nm_ in enumerate(("linear_means", "linear_log_var")):
+                    ops.linear_f32_wgrad(r["cond"], d_heads[j * B:(j + 1) * B, 256 * half:],
+                                         self.pview(nm_ + ".weight", True)[512:], B, 256, self.cd, self.cd,
+                                         LATENT_HEADS, 512 + self.cd, unscale * in_scale)
         dH = alloc(key + ".dH", (rows, 512), F32)
         _ig(self.heads, "dgrad", dh16, dH, rows, None, True)
         dfc = alloc(key + ".dfc16", (B, 512), F16)
@@ -506,17 +523,21 @@ class EncoderExec(_NetBase):
 # image decoder (vae.py:263-279, 293-296)
 # ---------------------------------------------------------------------------------------------
 class DecoderExec(_NetBase):
-    def __init__(self, arena, prefix, device):
+    def __init__(self, arena, prefix, device, cond_dim=0):
+        """cond_dim > 0: CVAE upsample Linear(256 + cond_dim, 6400) (vae.py:257, 286-291): the latent
+        columns go through the tensor cores, the condition term is added by mmdyn_cond_add_f16."""
         super().__init__(arena, prefix, device)
+        self.cd = int(cond_dim)
         self.up = self._pl(plan.linear_plan("up", [self.off("upsample.0.weight")], [self.off("upsample.0.bias")],
-                                            256, [6400], n_perm=plan.nhwc_perm(256, 5, 5)))
+                                            256, [6400], n_perm=plan.nhwc_perm(256, 5, 5), ld=256 + self.cd))
+        self.up_rows = torch.from_numpy(np.ascontiguousarray(plan.nhwc_perm(256, 5, 5)).astype(np.int32)).to(device)
         self.d1 = self._pl(plan.deconv_k4s1p0_plan("deconv1", self.off("hallucinate.0.weight"), 256, 128, 5))
         self.d2 = self._pl(plan.deconv_s2_plan("deconv2", self.off("hallucinate.3.weight"), 128, 64, 8))
         self.d3 = self._pl(plan.deconv_s2_plan("deconv3", self.off("hallucinate.6.weight"), 64, 32, 16))
         self.d4 = self._pl(plan.deconv_out_plan("deconv4", self.off("hallucinate.9.weight"), 32, 3, 32))
         self.bn1, self.bn2, self.bn3 = _BN(self, "hallucinate.1", 128), _BN(self, "hallucinate.4", 64), _BN(self, "hallucinate.7", 32)
 
-    def forward(self, zh, G, B, alloc, key, track=True, fused_loss=None):
+    def forward(self, zh, G, B, alloc, key, track=True, fused_loss=None, cond=None):
         """zh: (G*B, 256) fp16 latent rows, group-major.  Returns record with fp32 NCHW logits.
 
         fused_loss: dict(target (B,3,64,64), mask|None, dlogits (G*B,66,66,8)|None, loss (fp32 vector),
@@ -541,9 +562,19 @@ class DecoderExec(_NetBase):
         logits = alloc(key + ".logits", (R, 3, 64, 64), F32)
         s1, s2, s3 = (bn.alloc_fwd(G, alloc, key + nm) for bn, nm in ((self.bn1, ".bn1"), (self.bn2, ".bn2"), (self.bn3, ".bn3")))
         Gc = _group_chunk(G, B)
+        cond_rep = None
+        if self.cd:
+            if cond is None or tuple(cond.shape) != (B, self.cd):
+                raise ValueError(f"conditional decoder needs a condition of shape ({B}, {self.cd})")
+            cond_rep = alloc(key + ".cond", (R, self.cd), F32)
+            cond_rep.view(G, B, self.cd).copy_(cond.unsqueeze(0).expand(G, B, self.cd))  # every group sees the same c
+            r["cond_rep"] = cond_rep
         for g0 in range(0, G, Gc):
             sl, n = slice(g0 * B, (g0 + Gc) * B), Gc * B
             _ig(self.up, "fwd", zh[sl], raw0[sl], n, self.up.bias)
+            if self.cd:
+                ops.cond_add_f16(raw0[sl], cond_rep[sl], self.pview("upsample.0.weight"), self.up_rows, n, 6400,
+                                 256 + self.cd, 256, self.cd)
             ops.bn_swish_fwd(raw0[sl], None, act0[sl], 1, n * 25, 256)
             _ig(self.d1, "fwd", act0[sl], raw1[sl], n)
             self.bn1.run_fwd(raw1[sl], act1[sl], Gc, B * 64, s1, g0, track)
@@ -599,6 +630,9 @@ class DecoderExec(_NetBase):
         ops.colsum_f16(g0_, dbp, R, 6400, 6400, unscale)
         ops.unpack_add_f32(dbp, self.up.bias_idx, arena.grad)
         _wgrad_into(self.up, r["zh"], g0_, R, arena, alloc, key + ".dW_up", unscale, gp)
+        if self.cd:
+            ops.cond_wgrad_f16(g0_, r["cond_rep"], self.pview("upsample.0.weight", True), self.up_rows, R, 6400,
+                               256 + self.cd, 256, self.cd, unscale)
         dz = alloc(key + ".dz", (R, 256), F32)
         _ig(self.up, "dgrad", g0_, dz, R, None, True)
         return dz
@@ -694,11 +728,13 @@ def get_execs(module, device):
         dev = arena.flat.device
         ex = {"device": dev, "flat_id": id(arena.flat), "enc": {}, "dec": {}, "pose": None}
         names = set(n.split(".")[0] for n in arena.names)
+        cd = int(getattr(module, "condition_dim", 0) or 0) if getattr(module, "conditional", False) else 0
+        ex["cond_dim"] = cd
         for n in sorted(names):
             if n.endswith("encoder") and n != "pose_encoder":
-                ex["enc"][n] = EncoderExec(arena, n, dev)
+                ex["enc"][n] = EncoderExec(arena, n, dev, cd)
             elif n.endswith("decoder") and n != "pose_decoder":
-                ex["dec"][n] = DecoderExec(arena, n, dev)
+                ex["dec"][n] = DecoderExec(arena, n, dev, cd)
         if "pose_encoder" in names:
             ex["pose"] = PoseExec(arena, dev)
         nets = list(ex["enc"].values()) + list(ex["dec"].values())
@@ -826,7 +862,8 @@ class StepEngine:
             self.ws = Workspace(arena.flat.device)
         return arena, ex
 
-    def evaluate(self, x, targets, kl_weight, loss_mask=None, want_outputs=True, need_grad=None, autograd=True):
+    def evaluate(self, x, targets, kl_weight, loss_mask=None, want_outputs=True, need_grad=None, autograd=True,
+                 condition=None):
         """x / targets: tensor (vae) or list [visual, tactile(, pose)] (mvae), fp32, on the GPU.
         Returns (outputs, loss) like the reference; loss.backward() then fills the parameter
         gradients.  Under torch.no_grad() only the forward runs (Problem._test_epoch).
@@ -848,6 +885,12 @@ class StepEngine:
         arena, ex = self._setup(first.device)
         ws, B, D = self.ws, first.shape[0], 256
         ws.begin_step()
+        cond = None
+        if ex["cond_dim"]:  # CVAE: the condition (shock force) enters every image encoder head and decoder
+            if condition is None:
+                raise ValueError("this model was built with conditional=True: evaluate() needs `condition`")
+            cond = condition.float()
+            cond = (cond.unsqueeze(1) if cond.dim() == 1 else cond).contiguous()
         for k in xs:
             xs[k] = xs[k].contiguous().float()
             ts[k] = ts[k].contiguous().float()
@@ -887,7 +930,7 @@ class StepEngine:
 
         def enc_branch(m):
             def fn():
-                enc_rec[m] = ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True)
+                enc_rec[m] = ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True, cond)
             return fn
 
         def pose_enc():
@@ -956,7 +999,7 @@ class StepEngine:
                         lg = (jg, jg + 1)
                     fl = dict(target=ts[m], mask=loss_mask, dlogits=dl8[m], loss=scal, slots=slots, gscale=gs / B,
                               logit_groups=lg)
-                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True, fused_loss=fl)
+                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True, fused_loss=fl, cond=cond)
                     return
 
                 def losses(g0, Gc, lg_rows):  # right after a group chunk's logits, while they are L2-resident
@@ -968,7 +1011,7 @@ class StepEngine:
                                        dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64, 64, 1)
                 dex.after_group = losses
                 try:
-                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True)
+                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True, cond=cond)
                 finally:
                     dex.after_group = None
             return fn
@@ -1114,7 +1157,7 @@ class GraphedTrainStep:
     gradient arena and then calls `apply()`, a second graph holding the optimizer update."""
 
     def __init__(self, step_engine, optimizer, example_x, example_t, kl_weight, loss_mask=None, split_optimizer=False,
-                 warmup=2, grad_sync=None):
+                 warmup=2, grad_sync=None, condition=None):
         """grad_sync: a parallel.GradSync whose bucketed NCCL all-reduces are captured INSIDE the graph
         (launched from the backward on a side stream, overlapping the encoder backward); the
         alternative for data parallelism is split_optimizer=True (backward graph, eager all-reduce,
@@ -1126,6 +1169,10 @@ class GraphedTrainStep:
         self.x = [t.clone() for t in example_x] if lst else example_x.clone()
         self.t = [t.clone() for t in example_t] if lst else example_t.clone()
         self.mask = loss_mask.clone() if loss_mask is not None else None
+        self.cond = None  # CVAE condition (shock force): a static fp32 (B, cd) buffer the graph reads
+        if condition is not None:
+            c = condition.float()
+            self.cond = (c.unsqueeze(1) if c.dim() == 1 else c).contiguous().clone()
         eng = self.eng
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -1149,7 +1196,8 @@ class GraphedTrainStep:
         self.opt.zero_grad()
         if self.sync is not None:
             self.sync.begin()
-        outputs, loss = self.eng.evaluate(self.x, self.t, self.klw, loss_mask=self.mask, need_grad=True, autograd=False)
+        outputs, loss = self.eng.evaluate(self.x, self.t, self.klw, loss_mask=self.mask, need_grad=True, autograd=False,
+                                          condition=self.cond)
         self.eng.backward()
         if self.sync is not None:
             self.sync.finish()
@@ -1157,9 +1205,13 @@ class GraphedTrainStep:
             self.opt.step()
         return outputs, loss
 
-    def load(self, x, t, non_blocking=True, mask=None):
+    def load(self, x, t, non_blocking=True, mask=None, condition=None):
         if mask is not None and self.mask is not None:
             self.mask.copy_(mask, non_blocking=non_blocking)
+        if self.cond is not None:
+            if condition is None:
+                raise ValueError("this graph was captured for a conditional model: load() needs `condition`")
+            self.cond.copy_(condition.reshape(self.cond.shape), non_blocking=non_blocking)
         if isinstance(self.x, list):
             for d, s_ in zip(self.x, x):
                 d.copy_(s_, non_blocking=non_blocking)

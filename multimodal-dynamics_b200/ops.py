@@ -364,3 +364,26 @@ def frames_u8_to_f32(frames, index, table_dev, out):
                                               (None if s == 0 else _ptr(torch.arange(s, e, device=out.device))),
                                               _ptr(table_dev), _ptr(out[s:e]), e - s, frames.shape[1], frames.shape[2],
                                               oh, ow, _stream()), "frames_u8_to_f32")
+
+
+def linear_f32_acc(x, W, y, M, N, K, ldx, ldw, ldy):
+    with _Timed("cond_linear", None):
+        check(_L().mmdyn_linear_f32_acc(_ptr(x), _ptr(W), _ptr(y), M, N, K, ldx, ldw, ldy, _stream()), "linear_f32_acc")
+
+
+def linear_f32_wgrad(x, dy, dW, M, N, K, ldx, lddy, ldw, scale):
+    with _Timed("cond_linear", None):
+        check(_L().mmdyn_linear_f32_wgrad(_ptr(x), _ptr(dy), _ptr(dW), M, N, K, ldx, lddy, ldw, scale, _stream()),
+              "linear_f32_wgrad")
+
+
+def cond_add_f16(raw, c, W, n_idx, R, N, ldw, col0, cd):
+    with _Timed("cond_linear", None):
+        check(_L().mmdyn_cond_add_f16(_ptr(raw), _ptr(c), _ptr(W), _ptr(n_idx), R, N, ldw, col0, cd, _stream()),
+              "cond_add_f16")
+
+
+def cond_wgrad_f16(g, c, dW, n_idx, R, N, ldw, col0, cd, scale):
+    with _Timed("cond_linear", None):
+        check(_L().mmdyn_cond_wgrad_f16(_ptr(g), _ptr(c), _ptr(dW), _ptr(n_idx), R, N, ldw, col0, cd, scale, _stream()),
+              "cond_wgrad_f16")

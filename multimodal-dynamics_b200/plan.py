@@ -314,15 +314,17 @@ def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
     return LayerPlan(name, "deconv_out", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
 
 
-def linear_plan(name, w_offs, b_offs, K, Ns, k_perm=None, n_perm=None):
+def linear_plan(name, w_offs, b_offs, K, Ns, k_perm=None, n_perm=None, ld=None):
     """One or several nn.Linear(K, N_i) sharing their input, concatenated along N
     (vae.py:211, 215-216, 264).  k_perm[k'] / n_perm[n'] give the torch index of packed index."""
     N = int(sum(Ns))
+    ld = K if ld is None else int(ld)  # row pitch of the torch weights: > K when extra input columns
+    #                                    (the CVAE condition, vae.py:231-237, 286-291) are handled elsewhere
     kp = np.arange(K) if k_perm is None else np.asarray(k_perm)
     rows, bias = [], []
     for w_off, b_off, n_i in zip(w_offs, b_offs, Ns):
         npm = np.arange(n_i) if n_perm is None else np.asarray(n_perm)
-        rows.append(w_off + npm[:, None] * K + kp[None, :])
+        rows.append(w_off + npm[:, None] * ld + kp[None, :])
         bias.append(b_off + npm)
     idx_fwd = np.concatenate(rows, 0).astype(np.int32)        # [N][K]
     bias_idx = np.concatenate(bias, 0).astype(np.int32)

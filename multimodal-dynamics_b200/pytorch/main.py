@@ -39,7 +39,7 @@ def build_parser():
     p.add_argument('--kl-weight', type=float, default=1.0, help='KL weight in the loss of VAE models (default: 1)')
     p.add_argument('--latent-size', type=int, default=256, help='Latent dimension (default: 256)')
     p.add_argument('--annealing-epochs', type=int, default=50, help='Number of epochs to anneal KL for (default: 50)')
-    p.add_argument('--conditional', action='store_true', default=False, help='Conditional VAE (unsupported here)')
+    p.add_argument('--conditional', action='store_true', default=False, help='Conditional VAE: condition the image experts on the shock force (data[4])')
     return p
 
 

@@ -8,8 +8,10 @@ reference); the forward and backward math runs in libmmdyn_b200.so through
 `mmdyn_b200.engine` — there is no PyTorch compute fallback and no CPU path.
 
 Scope: architecture 'cnn' for the image experts, the 'mlp' pose expert of MVAE,
-unconditional models.  `conditional=True` (CVAE shock conditioning, vae.py:231-237, 286-291) and a
-standalone 'mlp' VAE are reference features outside this path and raise NotImplementedError.
+models, with or without CVAE shock conditioning (`conditional=True`, vae.py:231-237, 286-291: the
+condition columns of the two head Linears and of the decoder's upsample Linear are a rank-cd fp32
+term next to the tensor-core GEMM).  A standalone 'mlp' VAE and categorical (one-hot) conditions are
+reference features outside this path and raise NotImplementedError.
 """
 import torch
 import torch.nn as nn
@@ -83,6 +85,23 @@ def _anchor(arena):
     return arena.params[0]
 
 
+def _condition(mod, c, n):
+    """The reference's handling of `c` in Encoder/Decoder.forward (vae.py:231-237, 286-291) for
+    real-valued conditions: (n,) -> (n, 1), float, concatenated after the features."""
+    if not mod.conditional:
+        return None
+    if mod.categorical_conditions:
+        raise NotImplementedError("categorical (one-hot) conditions are not part of the resting-state path "
+                                  "(SeqModeling / DynModeling set categorical_conditions=False: problems.py:677)")
+    if c is None:
+        raise ValueError("conditional=True: a condition tensor is required")
+    _require_cuda(c, "condition")
+    c = c.unsqueeze(1) if c.dim() == 1 else c
+    if tuple(c.shape) != (n, mod.condition_dim):
+        raise ValueError(f"condition has shape {tuple(c.shape)}, expected ({n}, {mod.condition_dim})")
+    return c.float().contiguous()
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"mmdyn_b200: {what} must live on a CUDA device (B200); there is no CPU path")
@@ -93,8 +112,8 @@ def _require_cuda(t, what):
 # ---------------------------------------------------------------------------------------------
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, ex, mask, track):
-        rec = ex.forward(x.contiguous().float(), [mask], engine.FreshAlloc(x.device), "enc", track)
+    def forward(ctx, x, anchor, ex, mask, track, c=None):
+        rec = ex.forward(x.contiguous().float(), [mask], engine.FreshAlloc(x.device), "enc", track, c)
         ctx.ex, ctx.rec = ex, rec
         return rec["heads"]
 
@@ -104,17 +123,17 @@ class _EncoderFn(torch.autograd.Function):
         ex.arena.attach_grads()
         gs = float(rec["B"])
         ex.backward(rec, d_heads.contiguous(), engine.FreshAlloc(d_heads.device), "enc", 1.0 / gs, gs)
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, anchor, ex, track):
+    def forward(ctx, z, anchor, ex, track, c=None):
         B = z.shape[0]
         zf = z.contiguous().float()
         zh = torch.empty(B, z.shape[1], dtype=F16, device=z.device)
         ops.f32_to_f16(zf, zh, zf.numel())
-        rec = ex.forward(zh, 1, B, engine.FreshAlloc(z.device), "dec", track)
+        rec = ex.forward(zh, 1, B, engine.FreshAlloc(z.device), "dec", track, cond=c)
         ctx.ex, ctx.rec = ex, rec
         return rec["logits"]
 
@@ -128,7 +147,7 @@ class _DecoderFn(torch.autograd.Function):
         ops.logit_grad_pack(dlogits.contiguous().float(), dl8, gs, B, 64, 64, 1)
         dz = ex.backward(rec, dl8, engine.FreshAlloc(dlogits.device), "dec", 1.0 / gs)
         ops.scale_f32(dz, dz.numel(), 1.0 / gs)
-        return dz, None, None, None
+        return dz, None, None, None, None
 
 
 class _PoseEncFn(torch.autograd.Function):
@@ -236,8 +255,6 @@ class VAE(Autoencoder):
         super().__init__(**kwargs)
         if kwargs.get('architecture', 'mlp') != 'cnn':
             raise NotImplementedError("mmdyn_b200 accelerates the cnn-vae / cnn-mvae path only")
-        if kwargs.get('conditional', False):
-            raise NotImplementedError("--conditional (CVAE) is outside the accelerated path (SURVEY.md §8f)")
         self.encoder = Encoder(**kwargs)
         self.decoder = Decoder(**kwargs)
         _bind_children(self)
@@ -260,8 +277,6 @@ class MVAE(Autoencoder):
     def __init__(self, use_pose=False, **kwargs):
         super().__init__(**kwargs)
         assert kwargs['architecture'] != 'mlp', "MVAE is not implemented with MLP"
-        if kwargs.get('conditional', False):
-            raise NotImplementedError("--conditional (CVAE) is outside the accelerated path (SURVEY.md §8f)")
         self._use_pose = use_pose
         self.visual_encoder = Encoder(**kwargs)
         self.visual_decoder = Decoder(**kwargs)
@@ -289,9 +304,9 @@ class MVAE(Autoencoder):
         # experts in the reference's order: (implicit) prior, visual, tactile, pose (vae.py:139-154)
         heads = []
         if visual is not None:
-            heads.append(self.visual_encoder._heads(visual))
+            heads.append(self.visual_encoder._heads(visual, condition))
         if tactile is not None:
-            heads.append(self.tactile_encoder._heads(tactile))
+            heads.append(self.tactile_encoder._heads(tactile, condition))
         if pose is not None and self._use_pose:
             heads.append(self.pose_encoder._heads(pose))
         eps = self._noise().normal(batch_size, self.latent_size, dev)
@@ -319,13 +334,15 @@ class Encoder(nn.Module):
         self.categorical_conditions = categorical_conditions
         self.condition_dim = condition_dim
         self.latent_size = latent_size
-        if conditional:
-            raise NotImplementedError("conditional encoders are outside the accelerated path")
+        if conditional and (architecture != 'cnn' or categorical_conditions or not condition_dim
+                            or not 1 <= int(condition_dim) <= 8):
+            raise NotImplementedError("conditional encoders: cnn architecture with 1..8 real-valued condition "
+                                      "components (the shock force, problems.py:676-681) only")
         if architecture == 'cnn':
             if latent_size != 256:
                 raise NotImplementedError("the sm_100a kernels are specialised for latent_size=256 (main.py:49)")
             cnn_features_out = 256 * 5 * 5
-            cnn_features_comp = 512
+            cnn_features_comp = 512 + self.conditional * (self.condition_dim or 0)
             self.conv_net = nn.Sequential(
                 nn.Conv2d(3, 32, 4, 2, 1, bias=False),
                 Swish(),
@@ -354,7 +371,7 @@ class Encoder(nn.Module):
             self.linear_means = nn.Linear(layer_sizes[-1], latent_size)
             self.linear_log_var = nn.Linear(layer_sizes[-1], latent_size)
 
-    def _heads(self, x):
+    def _heads(self, x, c=None):
         _require_cuda(x, "encoder input")
         root, prefix = _root_of(self)
         arena, ex = engine.get_execs(root, x.device)
@@ -364,11 +381,12 @@ class Encoder(nn.Module):
                                           "(the reference never leaves train mode: problems.py:145,174)")
             src = root.noise if getattr(root, "noise", None) is not None else noise.get_default()
             mask = src.dropout_mask(x.size(0), x.device)
-            return _EncoderFn.apply(x, _anchor(arena), ex["enc"][prefix or "encoder"], mask, True)
+            return _EncoderFn.apply(x, _anchor(arena), ex["enc"][prefix or "encoder"], mask, True,
+                                    _condition(self, c, x.size(0)))
         return _PoseEncFn.apply(x, _anchor(arena), ex["pose"])
 
     def forward(self, x, c=None):
-        h = self._heads(x)
+        h = self._heads(x, c)
         return h[:, :self.latent_size], h[:, self.latent_size:]
 
 
@@ -383,13 +401,15 @@ class Decoder(nn.Module):
         self.conditional = conditional
         self.categorical_conditions = categorical_conditions
         self.condition_dim = condition_dim
-        if conditional:
-            raise NotImplementedError("conditional decoders are outside the accelerated path")
+        if conditional and (architecture != 'cnn' or categorical_conditions or not condition_dim
+                            or not 1 <= int(condition_dim) <= 8):
+            raise NotImplementedError("conditional decoders: cnn architecture with 1..8 real-valued condition "
+                                      "components (the shock force, problems.py:676-681) only")
         if architecture == 'cnn':
             if latent_size != 256:
                 raise NotImplementedError("the sm_100a kernels are specialised for latent_size=256 (main.py:49)")
             self.upsample = nn.Sequential(
-                nn.Linear(latent_size, 256 * 5 * 5),
+                nn.Linear(latent_size + self.conditional * (self.condition_dim or 0), 256 * 5 * 5),
                 Swish()
             )
             self.hallucinate = nn.Sequential(
@@ -419,7 +439,8 @@ class Decoder(nn.Module):
             if not self.training:
                 raise NotImplementedError("eval-mode BatchNorm is not part of the reference path "
                                           "(the reference never leaves train mode: problems.py:145,174)")
-            return _DecoderFn.apply(z, _anchor(arena), ex["dec"][prefix or "decoder"], True)
+            return _DecoderFn.apply(z, _anchor(arena), ex["dec"][prefix or "decoder"], True,
+                                    _condition(self, c, z.size(0)))
         return _PoseDecFn.apply(z, _anchor(arena), ex["pose"])
 
 

@@ -12,7 +12,8 @@ single-kernel `FusedAdam` / `FusedSGD` over the flat parameter arena.
 Differences that are deliberate and documented in DESIGN.md:
   * perf_measure values stay on the device (0-dim tensors) so the step has no host sync; they
     are converted with float() only where the reference logs them per epoch;
-  * `--problem-type regression` and `--conditional` are outside the accelerated path;
+  * `--problem-type regression` and class-label (categorical) conditioning are outside the accelerated path;
+    `--conditional` with the shock force of SeqModeling / DynModeling is supported (SURVEY.md §8f row 2);
   * dyn_modeling batches are sequence-collated (the reference crashes there).
 """
 import math
@@ -292,27 +293,28 @@ class Reconstruction(Problem):
             return err + self._kl_weight * kld
         return (err + self._kl_weight * kld) / x[0].size(0)
 
-    def _evaluate_mvae_passes(self, x, targets, loss_mask=None, reduce=None, reduction='sum'):
+    def _evaluate_mvae_passes(self, x, targets, loss_mask=None, reduce=None, reduction='sum', condition=None):
         """The sub-sampled objective pass by pass through the module-level API, exactly as the reference
         spells it (problems.py:473-546).  Used for the per-sample scoring variant (reduce=False) and as
         an independent cross-check of the fused step; training uses the fused StepEngine."""
         m, up = self._model, self.parameters['use_pose']
+        c = dict(condition=condition)
         tv, tt = targets[0], targets[1]
-        vj, tj, _, mu, lv = m([x[0], x[1]])
+        vj, tj, _, mu, lv = m([x[0], x[1]], **c)
         loss = self._mvae_elbo_loss([vj, tj], [tv, tt], mu, lv, loss_mask, reduce, reduction)
-        v1, _, _, mu, lv = m([x[0], None])
+        v1, _, _, mu, lv = m([x[0], None], **c)
         loss = loss + self._mvae_elbo_loss([v1], [tv], mu, lv, loss_mask, reduce, reduction)
-        _, t1, _, mu, lv = m([None, x[1]])
+        _, t1, _, mu, lv = m([None, x[1]], **c)
         loss = loss + self._mvae_elbo_loss([t1], [tt], mu, lv, loss_mask, reduce, reduction)
         rec = [vj, tj]
         if up:
-            vj, tj, pj, mu, lv = m([x[0], x[1]], pose=x[2])
+            vj, tj, pj, mu, lv = m([x[0], x[1]], pose=x[2], **c)
             loss = loss + self._mvae_elbo_loss([vj, tj, pj], [tv, tt, targets[2]], mu, lv, loss_mask, reduce, reduction)
-            v2, _, p2, mu, lv = m([x[0], None], pose=x[2])
+            v2, _, p2, mu, lv = m([x[0], None], pose=x[2], **c)
             loss = loss + self._mvae_elbo_loss([v2, p2], [tv, targets[2]], mu, lv, loss_mask, reduce, reduction)
-            _, t2, p3, mu, lv = m([None, x[1]], pose=x[2])
+            _, t2, p3, mu, lv = m([None, x[1]], pose=x[2], **c)
             loss = loss + self._mvae_elbo_loss([t2, p3], [tt, targets[2]], mu, lv, loss_mask, reduce, reduction)
-            _, _, p4, mu, lv = m([None, None], pose=x[2])
+            _, _, p4, mu, lv = m([None, None], pose=x[2], **c)
             loss = loss + self._mvae_elbo_loss([p4], [targets[2]], mu, lv, loss_mask, reduce, reduction)
             rec = [vj, tj, pj]
         return {'recon_x': rec, 'means': mu, 'log_var': lv}, loss
@@ -323,26 +325,35 @@ class Reconstruction(Problem):
         """(x, targets, loss_mask, rename) in the form StepEngine.evaluate takes them."""
         return inputs, inputs, None, None
 
+    def _step_condition(self, inputs):
+        """The CVAE condition of this batch (None for un-conditional problems)."""
+        if not self._conditional:
+            return None
+        raise NotImplementedError("class-label (categorical) conditioning is outside the accelerated path")
+
     def _graphed_step(self, inputs, targets):
         from mmdyn_b200 import noise as _noise
         eng = self._get_engine()
         src = eng._noise()
         if not self.use_cuda_graph or not isinstance(self._optimizer, (fused_optim.FusedAdam, fused_optim.FusedSGD)):
             return None
+        cond = self._step_condition(inputs)
         if isinstance(src, _noise.HostNoise):
             if src is not _noise.get_default():
                 return None  # a caller-provided host generator must keep its draw order: eager path
             eng.noise_src = src = _noise.DeviceNoise(seed=int(torch.initial_seed() % (1 << 31)))
         x, t, mask, rename = self._step_tensors(inputs, targets)
         first = x[0] if isinstance(x, (list, tuple)) else x
-        key = (tuple(first.shape), float(self._kl_weight), mask is not None, float(self._pose_multiplier))
+        key = (tuple(first.shape), float(self._kl_weight), mask is not None, float(self._pose_multiplier),
+               cond is not None)
         cache = self.__dict__.setdefault("_graph_cache", {})
         g = cache.get(key)
         if g is None:
             if len(cache) > 4:
                 cache.clear()
-            g = cache[key] = engine.GraphedTrainStep(eng, self._optimizer, x, t, self._kl_weight, loss_mask=mask)
-        g.load(x, t, mask=mask)
+            g = cache[key] = engine.GraphedTrainStep(eng, self._optimizer, x, t, self._kl_weight, loss_mask=mask,
+                                                     condition=cond)
+        g.load(x, t, mask=mask, condition=cond)
         outputs, loss = g.run()
         if "x" in outputs.get("perf_measure", {}):
             outputs = dict(outputs)
@@ -361,7 +372,9 @@ class Reconstruction(Problem):
         if 'mvae' in self.parameters['model_name']:
             return self._evaluate_mvae(x=x, targets=x)
         if self._conditional:
-            raise NotImplementedError("--conditional is outside the accelerated path")
+            raise NotImplementedError("class-label (categorical) conditioning of the plain Reconstruction problem "
+                                      "is outside the accelerated path; SeqModeling / DynModeling --conditional "
+                                      "(shock force) is supported")
         outputs, loss = self._get_engine().evaluate(x, x, self._kl_weight)
         outputs.pop('perf_measure', None)
         return outputs, loss
@@ -369,16 +382,20 @@ class Reconstruction(Problem):
     def _evaluate_mvae(self, x, targets, loss_mask=None, reduce=None, reduction='sum', condition=None):
         """problems.py:473-546 as one fused step (3 passes, or 7 with --use-pose)."""
         assert isinstance(x, list) and isinstance(targets, list)
-        if condition is not None:
-            raise NotImplementedError("--conditional is outside the accelerated path")
+        # the reference hands `condition` to every model call; un-conditional encoders / decoders ignore it
+        condition = condition if self._conditional else None
         if reduce is not None or reduction != 'sum':
-            return self._evaluate_mvae_passes(x, targets, loss_mask, reduce, reduction)
-        return self._get_engine().evaluate(x, targets, self._kl_weight, loss_mask=loss_mask)
+            return self._evaluate_mvae_passes(x, targets, loss_mask, reduce, reduction, condition)
+        return self._get_engine().evaluate(x, targets, self._kl_weight, loss_mask=loss_mask, condition=condition)
 
     def _sample(self, n=50):
         with torch.no_grad():
-            if self._conditional:
-                raise NotImplementedError("--conditional is outside the accelerated path")
+            if self._conditional:  # problems.py:550-556
+                if self._categorical_conditions:
+                    raise NotImplementedError("categorical conditions are outside the accelerated path")
+                y = torch.rand((n, self._condition_dim)).to(self._device)
+                self._img_logger_dict['Samples/latent_space'] = self.apply_sigmoid(self._model.inference(n=n, c=y))
+                return
             self._img_logger_dict['Samples/latent_space'] = self.apply_sigmoid(self._model.inference(n=n))
 
     def _log_train_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
@@ -464,8 +481,6 @@ class SeqModeling(Reconstruction, Problem):
 
     def _step_tensors(self, x, targets):
         mask = targets['loss_mask'] if self.parameters['mask_loss'] else None
-        if self._conditional:
-            raise NotImplementedError("--conditional is outside the accelerated path")
         if 'mvae' in self.parameters['model_name']:
             if self.parameters['use_pose']:
                 if mask is not None:
@@ -476,12 +491,17 @@ class SeqModeling(Reconstruction, Problem):
             return x['model_input'], targets['target_output'], mask, None
         return x['model_input'], targets['target_output'], mask, self.parameters['input_type']
 
+    def _step_condition(self, x):
+        cond = x.get('shock') if self._conditional else None
+        if self._conditional and cond is None:
+            raise ValueError("--conditional needs the shock force as the 5th data field (datasets.py: data[4])")
+        return cond
+
     def _evaluate_model(self, x, targets, reduction='sum', reduce=None, **kwargs):
         """problems.py:683-716."""
         loss_mask = targets['loss_mask'] if self.parameters['mask_loss'] else None
         x.setdefault('shock', None)
-        if self._conditional:
-            raise NotImplementedError("--conditional is outside the accelerated path")
+        cond = self._step_condition(x)
         if 'mvae' in self.parameters['model_name']:
             if self.parameters['use_pose']:
                 if loss_mask is not None:
@@ -489,16 +509,17 @@ class SeqModeling(Reconstruction, Problem):
                                      "poses; the reference fails here too (problems.py:446)")
                 return self._evaluate_mvae(x=x['model_input'] + x['input_object_pose'],
                                            targets=targets['target_output'] + targets['target_object_pose'],
-                                           loss_mask=loss_mask, reduce=reduce, reduction=reduction)
+                                           loss_mask=loss_mask, reduce=reduce, reduction=reduction, condition=cond)
             return self._evaluate_mvae(x=x['model_input'], targets=targets['target_output'], loss_mask=loss_mask,
-                                       reduce=reduce, reduction=reduction)
+                                       reduce=reduce, reduction=reduction, condition=cond)
         if reduce is not None or reduction != 'sum':
-            recon_x, means, log_var = self._model(x['model_input'])
+            recon_x, means, log_var = self._model(x['model_input'], cond) if self._conditional \
+                else self._model(x['model_input'])
             loss = self._elbo_loss(recon_x, targets['target_output'], means, log_var, loss_mask=loss_mask,
                                    reduce=reduce, reduction=reduction)
             return {'recon_x': recon_x, 'means': means, 'log_var': log_var}, loss
         outputs, loss = self._get_engine().evaluate(x['model_input'], targets['target_output'], self._kl_weight,
-                                                    loss_mask=loss_mask)
+                                                    loss_mask=loss_mask, condition=cond)
         outputs['perf_measure'] = {self.parameters['input_type']: outputs['perf_measure']['x']}
         return outputs, loss
 

@@ -3,10 +3,10 @@
 The reference's PNG+JSON loader (`mmdyn/pytorch/utils/datasets.py`) is host-side I/O outside the
 accelerated path; this module only (a) delegates to it when the reference
 package is importable and `dataset_path` is a real directory, and (b) provides a synthetic,
-dataset-shaped stand-in (`--dataset-path synthetic[:n_sequences[:seq_length]]`) whose batches obey
+dataset-shaped stand-in (`--dataset-path synthetic[:n_sequences[:seq_length[:shock_dim]]]`) whose batches obey
 the contract of `seq_collate_fn` (datasets.py:395-404): lists of (B*L, ...) tensors
 
-    data   = [visual (B*L,3,64,64), tactile (same), pose (B*L,7), available (B*L,2)]
+    data   = [visual (B*L,3,64,64), tactile (same), pose (B*L,7), available (B*L,2)(, shock (B*L,shock_dim))]
     target = [visual_final, tactile_final, pose_final (B*L,7), seg_mask (B*L,3,64,64)]
 """
 import os
@@ -17,13 +17,16 @@ from torch.utils.data import DataLoader, Dataset
 
 
 class SyntheticVisuoTactileDataset(Dataset):
-    def __init__(self, n_sequences=256, seq_length=50, seed=0):
+    def __init__(self, n_sequences=256, seq_length=50, seed=0, shock_dim=0):
         self.n, self.L = n_sequences, seq_length
         self.seed = seed
         self.seq_length = seq_length
+        self.shock_dim = int(shock_dim)
         # class labels per sequence: Reconstruction._set_condition_dim reads `.targets`
         self.targets = [0] * n_sequences
-        self.data = None
+        # SeqModeling._set_condition_dim reads len(train_dataset.data[0][0][4]) (problems.py:676-681): the
+        # min-max normalised shock force of exp 3 (datasets.py:251-254), one vector per frame
+        self.data = [[[None, None, None, None, np.zeros(self.shock_dim, np.float32)]]] if self.shock_dim else None
 
     def __len__(self):
         return self.n
@@ -37,6 +40,8 @@ class SyntheticVisuoTactileDataset(Dataset):
         avail = torch.ones(L, 2)
         mask = (torch.rand(L, 3, 64, 64, generator=g) > 0.5).float()
         data = [vis, tac, pose, avail]
+        if self.shock_dim:
+            data.append(torch.rand(1, self.shock_dim, generator=g).expand(L, -1).contiguous())  # one shock per sequence
         target = [vis[-1:].expand(L, -1, -1, -1), tac[-1:].expand(L, -1, -1, -1), pose[-1:].expand(L, -1), mask]
         return data, target
 
@@ -160,8 +165,9 @@ def dataset_setup(dataset_path, problem_type, input_size=(64, 64), batchsize=128
         parts = path.split(":")
         n_seq = int(parts[1]) if len(parts) > 1 else 4 * batchsize
         L = int(parts[2]) if len(parts) > 2 else 50
-        train = SyntheticVisuoTactileDataset(n_seq, L, seed=0)
-        test = SyntheticVisuoTactileDataset(max(batchsize, n_seq // 4), L, seed=1)
+        sd = int(parts[3]) if len(parts) > 3 else 0
+        train = SyntheticVisuoTactileDataset(n_seq, L, seed=0, shock_dim=sd)
+        test = SyntheticVisuoTactileDataset(max(batchsize, n_seq // 4), L, seed=1, shock_dim=sd)
         # NB: the reference only seq-collates when 'seq' is in the problem type and therefore crashes
         # for dyn_modeling; both problem types need (B*L, ...) batches.
         kw = dict(batch_size=batchsize, collate_fn=seq_collate_fn, drop_last=True, num_workers=0)

@@ -44,9 +44,19 @@ def _bn_train(x, sd, prefix, track):
     return y
 
 
-def encoder_cnn(sd, p, x, dropout_mask=None, track=True, acts=None):
+def _cat_condition(h, c):
+    """Real-valued condition handling of Encoder / Decoder.forward (vae.py:231-237, 286-291):
+    (n,) -> (n,1), then torch.cat((features, c.float()), -1).  c = None: un-conditional model."""
+    if c is None:
+        return h
+    c = c.unsqueeze(1) if c.dim() == 1 else c
+    return torch.cat((h, c.to(h.dtype)), dim=-1)
+
+
+def encoder_cnn(sd, p, x, dropout_mask=None, track=True, acts=None, c=None):
     """Encoder.forward, architecture 'cnn' (vae.py:197-216, 224-242).  dropout_mask: (B,512) tensor
-    with values 0 or 1/(1-p) (None = no dropout); returns (means, log_vars)."""
+    with values 0 or 1/(1-p) (None = no dropout); c: condition rows for conditional=True models
+    (heads are Linear(512 + condition_dim, 256), vae.py:196); returns (means, log_vars)."""
     def rec(k, v):
         if acts is not None:
             acts[p + "." + k] = v
@@ -70,6 +80,7 @@ def encoder_cnn(sd, p, x, dropout_mask=None, track=True, acts=None):
     rec("fc", h)
     if dropout_mask is not None:
         h = h * dropout_mask
+    h = _cat_condition(h, c)
     mu = F.linear(h, sd[p + ".linear_means.weight"], sd[p + ".linear_means.bias"])
     lv = F.linear(h, sd[p + ".linear_log_var.weight"], sd[p + ".linear_log_var.bias"])
     rec("mu", mu)
@@ -87,11 +98,13 @@ def encoder_mlp(sd, p, x):
     return mu, lv
 
 
-def decoder_cnn(sd, p, z, track=True, acts=None):
-    """Decoder.forward, architecture 'cnn' (vae.py:263-279, 293-296): returns LOGITS (no sigmoid)."""
+def decoder_cnn(sd, p, z, track=True, acts=None, c=None):
+    """Decoder.forward, architecture 'cnn' (vae.py:263-279, 286-296): returns LOGITS (no sigmoid).
+    c: condition rows for conditional=True models (upsample is Linear(256 + condition_dim, 6400), :257)."""
     def rec(k, v):
         if acts is not None:
             acts[p + "." + k] = v
+    z = _cat_condition(z, c)
     h = swish(F.linear(z, sd[p + ".upsample.0.weight"], sd[p + ".upsample.0.bias"]))
     h = h.view(-1, 256, 5, 5)
     rec("up", h)
@@ -147,29 +160,31 @@ def draw_pass_noise(B, has_visual, has_tactile, latent=256, generator=None, dtyp
     return mv, mt, eps
 
 
-def vae_forward(sd, x, noise, track=True, acts=None):
-    """VAE.forward (vae.py:81-88): noise = (dropout_mask, eps)."""
+def vae_forward(sd, x, noise, track=True, acts=None, c=None):
+    """VAE.forward (vae.py:81-88): noise = (dropout_mask, eps); c = condition (CVAE) or None."""
     mask, eps = noise
-    mu, lv = encoder_cnn(sd, "encoder", x, mask, track, acts)
+    mu, lv = encoder_cnn(sd, "encoder", x, mask, track, acts, c)
     z = reparametrize(mu, lv, eps)
     if acts is not None:
         acts["z"] = z
-    return decoder_cnn(sd, "decoder", z, track, acts), mu, lv
+    return decoder_cnn(sd, "decoder", z, track, acts, c), mu, lv
 
 
-def mvae_forward(sd, visual, tactile, pose, noise, use_pose, track=True, acts=None):
+def mvae_forward(sd, visual, tactile, pose, noise, use_pose, track=True, acts=None, c=None):
     """MVAE.forward (vae.py:126-165).  Expert order prior, visual, tactile, pose; both image
-    decoders always run (:160-161); the pose decoder runs iff use_pose (:163)."""
+    decoders always run (:160-161); the pose decoder runs iff use_pose (:163).  c: condition of a
+    conditional=True model — used by the image encoders / decoders; the pose expert is built
+    un-conditional (vae.py:118-123) and ignores it."""
     mv, mt, eps = noise
     B = (visual if visual is not None else tactile if tactile is not None else pose).size(0)
     ref = next(iter(sd.values()))
     mus = [torch.zeros(B, eps.size(1), dtype=ref.dtype)]   # prior_expert, vae.py:321-328
     lvs = [torch.zeros(B, eps.size(1), dtype=ref.dtype)]
     if visual is not None:
-        m, l = encoder_cnn(sd, "visual_encoder", visual, mv, track, acts)
+        m, l = encoder_cnn(sd, "visual_encoder", visual, mv, track, acts, c)
         mus.append(m), lvs.append(l)
     if tactile is not None:
-        m, l = encoder_cnn(sd, "tactile_encoder", tactile, mt, track, acts)
+        m, l = encoder_cnn(sd, "tactile_encoder", tactile, mt, track, acts, c)
         mus.append(m), lvs.append(l)
     if pose is not None and use_pose:
         m, l = encoder_mlp(sd, "pose_encoder", pose)
@@ -178,8 +193,8 @@ def mvae_forward(sd, visual, tactile, pose, noise, use_pose, track=True, acts=No
     z = reparametrize(mu, lv, eps)
     if acts is not None:
         acts["z"] = z
-    v_rec = decoder_cnn(sd, "visual_decoder", z, track, acts)
-    t_rec = decoder_cnn(sd, "tactile_decoder", z, track, acts)
+    v_rec = decoder_cnn(sd, "visual_decoder", z, track, acts, c)
+    t_rec = decoder_cnn(sd, "tactile_decoder", z, track, acts, c)
     p_rec = decoder_mlp(sd, "pose_decoder", z) if use_pose else None
     return v_rec, t_rec, p_rec, mu, lv
 
@@ -240,7 +255,7 @@ MVAE_PASSES_POSE = MVAE_PASSES_NOPOSE + [(True, True, True), (True, False, True)
 
 
 def evaluate_mvae(sd, x, targets, kl_weight, pose_multiplier, use_pose, noises, loss_mask=None, track=True,
-                  acts=None):
+                  acts=None, condition=None):
     """Reconstruction._evaluate_mvae (problems.py:473-546): sub-sampled training objective, the sum
     of 3 (or 7 with pose) ELBOs.  x = [visual, tactile(, pose)], targets likewise; noises = one
     (mask_v, mask_t, eps) triple per pass in pass order.  Returns (outputs, loss, per_pass) with the
@@ -253,7 +268,7 @@ def evaluate_mvae(sd, x, targets, kl_weight, pose_multiplier, use_pose, noises, 
     for i, ((hv, ht, hp), noise) in enumerate(zip(passes, noises)):
         a = {} if acts is not None else None
         v_rec, t_rec, p_rec, mu, lv = mvae_forward(sd, x[0] if hv else None, x[1] if ht else None,
-                                                   x[2] if hp else None, noise, use_pose, track, a)
+                                                   x[2] if hp else None, noise, use_pose, track, a, condition)
         if acts is not None:
             acts[i] = a
         recs, tgts = [], []
@@ -280,9 +295,10 @@ def evaluate_mvae(sd, x, targets, kl_weight, pose_multiplier, use_pose, noises, 
     return outputs, loss, per_pass
 
 
-def evaluate_vae(sd, x, target, kl_weight, noise, loss_mask=None, track=True, acts=None, input_type="visual"):
-    """SeqModeling._evaluate_model, plain VAE branch (problems.py:702-716)."""
-    recon, mu, lv = vae_forward(sd, x, noise, track, acts)
+def evaluate_vae(sd, x, target, kl_weight, noise, loss_mask=None, track=True, acts=None, input_type="visual",
+                 condition=None):
+    """SeqModeling._evaluate_model, plain VAE / CVAE branch (problems.py:702-716)."""
+    recon, mu, lv = vae_forward(sd, x, noise, track, acts, condition)
     loss = elbo_loss(recon, target, mu, lv, kl_weight, loss_mask)
     with torch.no_grad():
         m = F.binary_cross_entropy_with_logits(recon.view(target.size()), target, reduction="mean").item()
@@ -354,17 +370,18 @@ def adam_step(params, grads, state, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
 
 
 def train_step(sd, param_keys, problem, batch, kl_weight, pose_multiplier, noises, adam_state, lr=1e-3,
-               loss_mask=None):
+               loss_mask=None, condition=None):
     """One iteration of Problem._train_epoch's body (problems.py:150-155): zero_grad, evaluate,
     backward, Adam.  `problem` is 'vae' or 'mvae' / 'mvae+pose'.  Returns (outputs, loss, grads)."""
     params = [sd[k].requires_grad_(True) for k in param_keys]
     for p in params:
         p.grad = None
     if problem == "vae":
-        outputs, loss = evaluate_vae(sd, batch["x"], batch["target"], kl_weight, noises[0], loss_mask)
+        outputs, loss = evaluate_vae(sd, batch["x"], batch["target"], kl_weight, noises[0], loss_mask,
+                                     condition=condition)
     else:
         outputs, loss, _ = evaluate_mvae(sd, batch["x"], batch["targets"], kl_weight, pose_multiplier,
-                                         problem == "mvae+pose", noises, loss_mask)
+                                         problem == "mvae+pose", noises, loss_mask, condition=condition)
     loss.backward()
     grads = [p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p) for p in params]
     with torch.no_grad():

@@ -44,14 +44,15 @@ def summary(t):
             "head": t[:8].float().clone(), "numel": t.numel()}
 
 
-def make_problem(problems, setup_model, cls, model_name, input_type, use_pose, seed, kl_weight, mask_loss=False):
+def make_problem(problems, setup_model, cls, model_name, input_type, use_pose, seed, kl_weight, mask_loss=False,
+                 cond_dim=0):
     pr = object.__new__(cls)
     pr.parameters = {"model_name": model_name, "input_type": input_type, "use_pose": use_pose,
                      "mask_loss": mask_loss, "problem_type": "seq_modeling"}
-    pr._kl_weight, pr._pose_multiplier, pr._conditional = kl_weight, 1000.0, False
+    pr._kl_weight, pr._pose_multiplier, pr._conditional = kl_weight, 1000.0, cond_dim > 0
     pr._device = torch.device("cpu")
     torch.manual_seed(seed)
-    kw = dict(condition_dim=0, input_dim=4096, architecture="cnn", conditional=False,
+    kw = dict(condition_dim=cond_dim, input_dim=4096, architecture="cnn", conditional=cond_dim > 0,
               categorical_conditions=False, latent_size=256)
     if "mvae" in model_name:
         kw["use_pose"] = use_pose
@@ -63,8 +64,10 @@ def make_problem(problems, setup_model, cls, model_name, input_type, use_pose, s
 def batch(B, seed):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=g)
-    return dict(v=r(B, 3, 64, 64), t=r(B, 3, 64, 64), p=r(B, 7), tv=r(B, 3, 64, 64), tt=r(B, 3, 64, 64), tp=r(B, 7),
-                mask=(r(B, 3, 64, 64) > 0.5).float())
+    d = dict(v=r(B, 3, 64, 64), t=r(B, 3, 64, 64), p=r(B, 7), tv=r(B, 3, 64, 64), tt=r(B, 3, 64, 64), tp=r(B, 7),
+             mask=(r(B, 3, 64, 64) > 0.5).float())
+    d["c"] = 2 * r(B, 3) - 1  # shock force (drawn last, so the fields above are what they always were)
+    return d
 
 
 def run_step(pr, x, targets, noise_seed):
@@ -80,9 +83,10 @@ def run_step(pr, x, targets, noise_seed):
     return outputs, loss.detach(), names, grads
 
 
-def golden_case(problems, setup_model, name, model_name, input_type, use_pose, B, mask_loss=False):
+def golden_case(problems, setup_model, name, model_name, input_type, use_pose, B, mask_loss=False, cond_dim=0):
+    """cond_dim > 0: --conditional (CVAE), the shock force d["c"] is the condition (problems.py:683-703)."""
     pr = make_problem(problems, setup_model, problems.SeqModeling, model_name, input_type, use_pose, seed=0,
-                      kl_weight=1.0 / 50, mask_loss=mask_loss)
+                      kl_weight=1.0 / 50, mask_loss=mask_loss, cond_dim=cond_dim)
     d = batch(B, seed=1)
     if input_type == "visuotactile":
         x = {"model_input": [d["v"], d["t"]], "input_object_pose": [d["p"]], "shock": None}
@@ -91,12 +95,15 @@ def golden_case(problems, setup_model, name, model_name, input_type, use_pose, B
         k = "v" if input_type == "visual" else "t"
         x = {"model_input": d[k], "input_object_pose": None, "shock": None}
         t = {"target_output": d["t" + k], "target_object_pose": None, "loss_mask": d["mask"]}
+    if cond_dim:
+        assert cond_dim == d["c"].shape[1]
+        x["shock"] = d["c"]
     w0 = {n: summary(p) for n, p in pr._model.state_dict().items() if p.is_floating_point()}
     outputs, loss, names, grads = run_step(pr, x, t, noise_seed=123)
     rec = outputs["recon_x"]
     rec = rec if isinstance(rec, (list, tuple)) else [rec]
     g = {"case": name, "model_name": model_name, "input_type": input_type, "use_pose": use_pose, "B": B,
-         "mask_loss": mask_loss, "weights_seed": 0, "data_seed": 1, "noise_seed": 123, "kl_weight": 1.0 / 50,
+         "mask_loss": mask_loss, "cond_dim": cond_dim, "weights_seed": 0, "data_seed": 1, "noise_seed": 123, "kl_weight": 1.0 / 50,
          "loss": loss.item(), "means": outputs["means"].detach().clone(), "log_var": outputs["log_var"].detach().clone(),
          "perf_measure": dict(outputs["perf_measure"]),
          "recon_x": [summary(r) for r in rec], "recon_head": [r.detach().reshape(-1)[:64].clone() for r in rec],
@@ -144,10 +151,16 @@ def golden_anneal(problems):
 
 if __name__ == "__main__":
     problems, setup_model = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "conditional":  # only the CVAE fixtures
+        golden_case(problems, setup_model, "cvae_visual_b4", "cnn-vae", "visual", False, 4, cond_dim=3)
+        golden_case(problems, setup_model, "cmvae_pose_b3", "cnn-mvae", "visuotactile", True, 3, cond_dim=3)
+        sys.exit(0)
     golden_case(problems, setup_model, "vae_visual_b4", "cnn-vae", "visual", False, 4)
     golden_case(problems, setup_model, "vae_tactile_masked_b4", "cnn-vae", "tactile", False, 4, mask_loss=True)
     golden_case(problems, setup_model, "mvae_b4", "cnn-mvae", "visuotactile", False, 4)
     golden_case(problems, setup_model, "mvae_pose_b4", "cnn-mvae", "visuotactile", True, 4)
     golden_case(problems, setup_model, "mvae_masked_b3", "cnn-mvae", "visuotactile", False, 3, mask_loss=True)
+    golden_case(problems, setup_model, "cvae_visual_b4", "cnn-vae", "visual", False, 4, cond_dim=3)
+    golden_case(problems, setup_model, "cmvae_pose_b3", "cnn-mvae", "visuotactile", True, 3, cond_dim=3)
     golden_parse_input(problems)
     golden_anneal(problems)

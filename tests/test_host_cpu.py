@@ -47,9 +47,15 @@ def test_no_cpu_fallback():
         m(torch.rand(2, 3, 64, 64))
     with pytest.raises(RuntimeError, match="no CPU path"):
         engine.get_arena(m)
-    with pytest.raises(NotImplementedError):
-        setup_model("cnn-vae", condition_dim=3, input_dim=4096, architecture="cnn", conditional=True,
-                    categorical_conditions=False, latent_size=256)
+    # CVAE shock conditioning is part of the path: same parameter shapes as the reference
+    cm = setup_model("cnn-vae", condition_dim=3, input_dim=4096, architecture="cnn", conditional=True,
+                     categorical_conditions=False, latent_size=256)
+    sd = cm.state_dict()
+    assert tuple(sd["encoder.linear_means.weight"].shape) == (256, 515)
+    assert tuple(sd["decoder.upsample.0.weight"].shape) == (6400, 259)
+    with pytest.raises(NotImplementedError):  # class-label (one-hot) conditions are not
+        setup_model("cnn-vae", condition_dim=10, input_dim=4096, architecture="cnn", conditional=True,
+                    categorical_conditions=True, latent_size=256)
 
 
 def test_product_path_never_imports_oracle():

@@ -388,3 +388,113 @@ def test_data_parallel_semantics_on_one_gpu():
     opt.step()
     after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     assert torch.isfinite(after).all() and (after - before).abs().max().item() <= 1.0001e-3  # |lr * m/sqrt(v)| <= lr
+
+
+# ---------------------------------------------------------------------------------------------
+# CVAE shock conditioning (vae.py:196, 231-237, 257, 286-291)
+# ---------------------------------------------------------------------------------------------
+def make_cond(model_name, use_pose=False, seed=0, cd=3):
+    from mmdyn_b200.pytorch.models.models import setup_model
+    torch.manual_seed(seed)
+    kw = dict(KW, condition_dim=cd, conditional=True)
+    if "mvae" in model_name:
+        kw["use_pose"] = use_pose
+    m = setup_model(model_name, cross_modal="mvae" in model_name, **kw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    return m.to(DEV), sd
+
+
+def test_cvae_fused_step_and_module_api_match_oracle():
+    """cnn-vae --conditional: heads Linear(515,256) and upsample Linear(259,6400); the condition columns
+    are a rank-3 fp32 term next to the tensor-core GEMM.  Loss, posterior, reconstruction and every
+    parameter gradient (the condition columns of the three weights checked on their own)."""
+    from mmdyn_b200 import engine, noise
+    B, klw = 8, 0.02
+    model, sd = make_cond("cnn-vae")
+    assert tuple(sd["encoder.linear_means.weight"].shape) == (256, 515)
+    assert tuple(sd["decoder.upsample.0.weight"].shape) == (6400, 259)
+    d = batch(B, seed=3)
+    c = 2 * torch.rand(B, 3, generator=torch.Generator().manual_seed(17)) - 1
+    pkeys = [k for k, _ in model.named_parameters()]
+    mask, _, eps = orc.draw_pass_noise(B, True, False, generator=torch.Generator().manual_seed(11))
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    out_o, loss_o = orc.evaluate_vae(sd_o, d["v"], d["tv"], klw, (mask, eps), track=True, input_type="visual",
+                                     condition=c)
+    loss_o.backward()
+    # the condition must matter, otherwise this test proves nothing
+    _, loss_nc = orc.evaluate_vae(copy.deepcopy(sd), d["v"], d["tv"], klw, (mask, eps), track=False,
+                                  input_type="visual", condition=torch.zeros_like(c))
+    assert abs(loss_nc.item() - loss_o.item()) / loss_o.item() > 1e-5
+    eng = engine.StepEngine(model, "vae", noise_src=noise.HostNoise(torch.Generator().manual_seed(11)))
+    with pytest.raises(ValueError, match="condition"):
+        eng.evaluate(d["v"].to(DEV), d["tv"].to(DEV), klw)
+    eng = engine.StepEngine(model, "vae", noise_src=noise.HostNoise(torch.Generator().manual_seed(11)))
+    out_d, loss_d = eng.evaluate(d["v"].to(DEV), d["tv"].to(DEV), klw, condition=c.to(DEV))
+    loss_d.backward()
+    torch.cuda.synchronize()
+    assert abs(loss_d.item() - loss_o.item()) / loss_o.item() < 1e-4
+    assert nrel(out_d["recon_x"], out_o["recon_x"]) < 2e-3
+    assert nrel(out_d["means"], out_o["means"]) < 2e-3 and nrel(out_d["log_var"], out_o["log_var"]) < 2e-3
+    for k, p in model.named_parameters():
+        assert nrel(p.grad, sd_o[k].grad) < 1e-2, (k, nrel(p.grad, sd_o[k].grad))
+    for k, col0 in (("encoder.linear_means.weight", 512), ("encoder.linear_log_var.weight", 512),
+                    ("decoder.upsample.0.weight", 256)):
+        e = nrel(dict(model.named_parameters())[k].grad[:, col0:], sd_o[k].grad[:, col0:])
+        print(f"condition columns of {k}: {e:.3e}")
+        assert e < 1e-2, (k, e)
+    # module-level API: model(x, c) + torch loss + autograd on a fresh copy of the same weights
+    model2, _ = make_cond("cnn-vae")
+    model2.noise = noise.HostNoise(torch.Generator().manual_seed(11))
+    recon, mu, lv = model2(d["v"].to(DEV), c.to(DEV))
+    kld = -0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp())
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(recon, d["tv"].to(DEV), reduction="sum")
+    loss2 = (bce + klw * kld) / B
+    loss2.backward()
+    torch.cuda.synchronize()
+    assert abs(loss2.item() - loss_o.item()) / loss_o.item() < 1e-4
+    for k, p in model2.named_parameters():
+        assert nrel(p.grad, sd_o[k].grad) < 1e-2, (k, nrel(p.grad, sd_o[k].grad))
+    with pytest.raises(ValueError):
+        model2(d["v"].to(DEV), c[:, :2].to(DEV))
+    s = model2.inference(n=5, c=torch.rand(5, 3, device=DEV))
+    assert s.shape == (5, 3, 64, 64) and torch.isfinite(s).all()
+
+
+def test_cmvae_pose_fused_step_matches_oracle():
+    """cnn-mvae --use-pose --conditional: 7 sub-sampled passes, every image encoder head / decoder sees
+    the shock force, the pose expert does not (vae.py:118-123)."""
+    from mmdyn_b200 import engine, noise
+    B, klw, pm = 6, 0.02, 1000.0
+    model, sd = make_cond("cnn-mvae", True, seed=1)
+    d = batch(B, seed=4)
+    c = 2 * torch.rand(B, 3, generator=torch.Generator().manual_seed(23)) - 1
+    pkeys = [k for k, _ in model.named_parameters()]
+    x_o, t_o = [d["v"], d["t"], d["p"]], [d["tv"], d["tt"], d["tp"]]
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    out_o, loss_o, per_pass = orc.evaluate_mvae(sd_o, x_o, t_o, klw, pm, True,
+                                                oracle_noises(orc.MVAE_PASSES_POSE, B, 7), condition=c)
+    loss_o.backward()
+    eng = engine.StepEngine(model, "mvae", use_pose=True, pose_multiplier=pm,
+                            noise_src=noise.HostNoise(torch.Generator().manual_seed(7)), exact_running_stats=True)
+    out_d, loss_d = eng.evaluate([t.to(DEV) for t in x_o], [t.to(DEV) for t in t_o], klw, condition=c.to(DEV))
+    torch.cuda.synchronize()
+    assert abs(loss_d.item() - loss_o.item()) / loss_o.item() < 1e-4
+    mu_d, lv_d = eng.ws.bufs["mu"], eng.ws.bufs["lv"]
+    for i, pp in enumerate(per_pass):
+        assert nrel(mu_d[i], pp["mu"]) < 3e-3 and nrel(lv_d[i], pp["lv"]) < 3e-3, i
+    for a, b in zip(out_d["recon_x"], out_o["recon_x"]):
+        assert nrel(a, b) < 2e-3
+    loss_d.backward()
+    torch.cuda.synchronize()
+    gerr = {k: nrel(p.grad, sd_o[k].grad) for k, p in model.named_parameters()}
+    worst = sorted(gerr.items(), key=lambda kv: -kv[1])[:5]
+    print("worst gradient errors:\n" + "\n".join(f"{k:50s} {v:.3e}" for k, v in worst))
+    for k, v in gerr.items():
+        assert v < 5e-2, (k, v)  # same bound as the un-conditional pose case (ReLU flips behind z)
+    flat_o = torch.cat([sd_o[k].grad.reshape(-1) for k in pkeys])
+    flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    assert nrel(flat_d, flat_o) < 2e-2

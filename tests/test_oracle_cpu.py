@@ -34,8 +34,10 @@ def check_summary(mine, gold, rtol, what):
 def batch(B, seed):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.rand(*s, generator=g)
-    return dict(v=r(B, 3, 64, 64), t=r(B, 3, 64, 64), p=r(B, 7), tv=r(B, 3, 64, 64), tt=r(B, 3, 64, 64), tp=r(B, 7),
-                mask=(r(B, 3, 64, 64) > 0.5).float())
+    d = dict(v=r(B, 3, 64, 64), t=r(B, 3, 64, 64), p=r(B, 7), tv=r(B, 3, 64, 64), tt=r(B, 3, 64, 64), tp=r(B, 7),
+             mask=(r(B, 3, 64, 64) > 0.5).float())
+    d["c"] = 2 * r(B, 3) - 1  # shock force of the conditional (CVAE) fixtures
+    return d
 
 
 CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLD, "*vae*.pt")))
@@ -48,6 +50,9 @@ def test_oracle_reproduces_reference_step(case):
     from mmdyn_b200.pytorch.models.models import setup_model
     torch.manual_seed(g["weights_seed"])
     kw = dict(KW)
+    cd = g.get("cond_dim", 0)
+    if cd:
+        kw.update(condition_dim=cd, conditional=True)
     if "mvae" in g["model_name"]:
         kw["use_pose"] = g["use_pose"]
     model = setup_model(g["model_name"], cross_modal=g["input_type"] == "visuotactile", **kw)
@@ -59,6 +64,7 @@ def test_oracle_reproduces_reference_step(case):
     pkeys = [k for k, _ in model.named_parameters()]
     B, d = g["B"], batch(g["B"], g["data_seed"])
     mask = d["mask"] if g["mask_loss"] else None
+    cond = d["c"] if cd else None
     torch.manual_seed(g["noise_seed"])
     if "mvae" in g["model_name"]:
         passes = orc.MVAE_PASSES_POSE if g["use_pose"] else orc.MVAE_PASSES_NOPOSE
@@ -76,7 +82,7 @@ def test_oracle_reproduces_reference_step(case):
     if problem == "vae":
         params = [sd[k].requires_grad_(True) for k in pkeys]
         outputs, loss = orc.evaluate_vae(sd, b["x"], b["target"], g["kl_weight"], noises[0], mask,
-                                         input_type=g["input_type"])
+                                         input_type=g["input_type"], condition=cond)
         loss.backward()
         grads = [p.grad.detach().clone() for p in params]
         with torch.no_grad():
@@ -86,7 +92,7 @@ def test_oracle_reproduces_reference_step(case):
         loss = loss.detach()
     else:
         outputs, loss, grads = orc.train_step(sd, pkeys, problem, b, g["kl_weight"], 1000.0, noises, st, lr=1e-3,
-                                              loss_mask=mask)
+                                              loss_mask=mask, condition=cond)
     # identical op sequence on identical inputs: fp32 reduction-order noise only
     assert close(loss.item(), g["loss"], 2e-6), (loss.item(), g["loss"])
     assert torch.allclose(outputs["means"], g["means"], rtol=1e-4, atol=1e-6)

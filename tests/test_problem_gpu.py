@@ -60,6 +60,30 @@ def test_main_dyn_modeling_mvae_masked(tmp_path, monkeypatch):
     check_run(p, 92)
 
 
+def run_main_cond(tmp_path, monkeypatch, extra):
+    from mmdyn_b200.pytorch.main import main
+    monkeypatch.chdir(tmp_path)
+    return main(["--dataset-path", "synthetic:8:5:3", "--batchsize", "4", "--num-epochs", "2", "--annealing-epochs", "4",
+                 "--save-name", "t", "--conditional"] + extra)
+
+
+def test_main_conditional_mvae_pose_and_vae(tmp_path, monkeypatch):
+    """--conditional (exp 3: shock force as the CVAE condition, data[4]) through main.py; the step runs as a
+    CUDA graph with a static condition buffer."""
+    p = run_main_cond(tmp_path, monkeypatch, ["--problem-type", "seq_modeling", "--input-type", "visuotactile",
+                                              "--model-name", "cnn-mvae", "--use-pose"])
+    check_run(p, 106)
+    assert p._condition_dim == 3 and p._conditional
+    sd = p._model.state_dict()
+    assert tuple(sd["visual_encoder.linear_means.weight"].shape) == (256, 515)
+    assert tuple(sd["tactile_decoder.upsample.0.weight"].shape) == (6400, 259)
+    assert tuple(sd["pose_encoder.linear_means.weight"].shape) == (256, 512)  # the pose expert is un-conditional
+    assert getattr(p, "_graph_cache", None), "the conditional step did not go through the CUDA graph"
+    p = run_main_cond(tmp_path, monkeypatch, ["--problem-type", "dyn_modeling", "--input-type", "visual",
+                                              "--model-name", "cnn-vae"])
+    check_run(p, 46)
+
+
 def test_unsupported_paths_fail_loudly(tmp_path, monkeypatch):
     with pytest.raises(NotImplementedError):
         run_main(tmp_path, monkeypatch, ["--problem-type", "regression", "--model-name", "regressor"])
