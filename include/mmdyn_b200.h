@@ -277,6 +277,14 @@ int mmdyn_cond_add_f16(void* raw, const float* c, const float* W, const int32_t*
 int mmdyn_cond_wgrad_f16(const void* g, const float* c, float* dW, const int32_t* n_idx, int R, int N, int ldw,
                          int col0, int cd, float scale, void* stream);
 
+/* --- Regressor tail (models.py:56-62, 64-77) ---------------------------------
+ * out_net = Linear(512(+cd), 256) -> ReLU -> Linear(256, 256) -> ReLU -> Linear(256, out_dim): the first Linear
+ * runs on the tensor cores (mmdyn_igemm, fp32 out), the ReLU behind it here, the rest on mmdyn_linear_f32_*.
+ *   relu_f32     : y = max(x, 0)                      (n values, in place allowed)
+ *   act_grad_f32 : dx = dy * act'(y), act 1 = ReLU judged by its output y, 0 = identity */
+int mmdyn_relu_f32(const float* x, float* y, long long n, void* stream);
+int mmdyn_act_grad_f32(const float* y, const float* dy, float* dx, int M, int N, int ldy, int act, void* stream);
+
 /* --- device-side input pipeline --------------------------------------------
  * replaces transforms.Compose([Resize(input_size), ToTensor()]) per frame (utils/datasets.py:23-31,
  * 382-392) and the batch assembly of seq_collate_fn (:395-404) for uint8 frames kept in HBM.

@@ -225,7 +225,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_fmt, i
 // ---------------------------------------------------------------------------------------------
 // MUFU.EX2 + MUFU.RCP (approximate, ~2 ulp): the IEEE division costs ~10 extra instructions per element
 // and made the BatchNorm/Swish streaming kernels issue-bound instead of HBM-bound
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid with exactly two MUFU operations (ex2.approx.ftz + rcp.approx.ftz) and no range-check
+// code: __expf / __fdividef add an FSETP + scaling FMULs per element for denormal inputs and for
+// |divisor| > 2^126, which made the BatchNorm/Swish streaming kernels issue- and XU-bound
+// (ncu: XU pipe 50-66 %, issue 62-73 %).  Same limits: x -> -inf gives rcp(+inf) = 0, x -> +inf gives 1.
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x * sigmoid(x)] = s * (1 + x * (1 - s))
 __device__ __forceinline__ float swish_gradf_(float x) {

@@ -200,6 +200,18 @@ act_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy, float
   }
 }
 
+// ReLU in fp32 (Regressor.out_net behind the tensor-core Linear(512, 256), models.py:56-62)
+__global__ void __launch_bounds__(256) relu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x = fmaxf(v.x, 0.0f), v.y = fmaxf(v.y, 0.0f), v.z = fmaxf(v.z, 0.0f), v.w = fmaxf(v.w, 0.0f);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[n4 * 4 + threadIdx.x] = fmaxf(x[n4 * 4 + threadIdx.x], 0.0f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // CVAE conditioning (vae.py:231-237, 286-291): torch.cat((x, c), -1) in front of a Linear is the
 // Linear on x plus a rank-`cd` term  c . W[:, K0:K0+cd]^T  (cd = 3 shock-force components).  The big
@@ -372,6 +384,31 @@ extern "C" int mmdyn_cond_wgrad_f16(const void* g, const float* c, float* dW, co
   gy = (R + rpc - 1) / rpc;
   cond_wgrad_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(g), c, dW, n_idx, R, N,
                                                                ldw, col0, cd, scale, rpc);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+// y = max(x, 0) over n fp32 values (x == y allowed); x, y 16-byte aligned
+extern "C" int mmdyn_relu_f32(const float* x, float* y, long long n, void* stream) {
+  MMDYN_REQUIRE(x && y && n > 0, "relu_f32: bad arguments");
+  MMDYN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "relu_f32: pointers must be 16-byte aligned");
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  relu_f32_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(x, y, n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+// dx[M][N] = dy * act'(y)  (act 1: ReLU through its OUTPUT y; act 0: copy); y, dy at row pitch ldy, dx dense
+extern "C" int mmdyn_act_grad_f32(const float* y, const float* dy, float* dx, int M, int N, int ldy, int act,
+                                  void* stream) {
+  MMDYN_REQUIRE(y && dy && dx && M > 0 && N > 0 && ldy >= N && (act == 0 || act == 1), "act_grad_f32: bad arguments");
+  const long long n = static_cast<long long>(M) * N;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  act_grad_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(y, dy, dx, M, N, ldy, act);
   LAUNCHED();
   return MMDYN_OK;
 }

@@ -408,11 +408,15 @@ class _BN:
 # image encoder (vae.py:197-216, 224-242)
 # ---------------------------------------------------------------------------------------------
 class EncoderExec(_NetBase):
-    def __init__(self, arena, prefix, device, cond_dim=0):
+    def __init__(self, arena, prefix, device, cond_dim=0, head_names=("linear_means", "linear_log_var")):
         """cond_dim > 0: CVAE heads Linear(512 + cond_dim, 256) (vae.py:196, 231-237): the 512 feature
-        columns go through the tensor cores, the condition columns through mmdyn_linear_f32_acc."""
+        columns go through the tensor cores, the condition columns through mmdyn_linear_f32_acc.
+        head_names: the Linear(512 (+cd), 256) layers reading the trunk feature, concatenated along N
+        (the two posterior heads; Regressor: its first out_net layer, models.py:57)."""
         super().__init__(arena, prefix, device)
         self.cd = int(cond_dim)
+        self.head_names = tuple(head_names)
+        self.HN = 256 * len(self.head_names)
         self.c1 = self._pl(plan.conv1_plan("conv1", self.off("conv_net.0.weight")))
         self.c2 = self._pl(plan.conv_s2_plan("conv2", self.off("conv_net.2.weight"), 32, 64, 32))
         self.c3 = self._pl(plan.conv_s2_plan("conv3", self.off("conv_net.5.weight"), 64, 128, 16))
@@ -420,8 +424,8 @@ class EncoderExec(_NetBase):
         self.fc = self._pl(plan.linear_plan("fc", [self.off("fc_net.0.weight")], [self.off("fc_net.0.bias")],
                                             6400, [512], k_perm=plan.nhwc_perm(256, 5, 5)))
         self.heads = self._pl(plan.linear_plan(
-            "heads", [self.off("linear_means.weight"), self.off("linear_log_var.weight")],
-            [self.off("linear_means.bias"), self.off("linear_log_var.bias")], 512, [256, 256], ld=512 + self.cd))
+            "heads", [self.off(n + ".weight") for n in self.head_names], [self.off(n + ".bias") for n in self.head_names],
+            512, [256] * len(self.head_names), ld=512 + self.cd))
         self.bn2, self.bn3, self.bn4 = _BN(self, "conv_net.3", 64), _BN(self, "conv_net.6", 128), _BN(self, "conv_net.9", 256)
         self.c1_wg, c1_idx = plan.conv1_wgrad_plan(self.off("conv_net.0.weight"))
         self.c1_idx = torch.from_numpy(c1_idx).to(device)
@@ -455,15 +459,15 @@ class EncoderExec(_NetBase):
         _ig(self.fc, "fwd", act4, fc_raw, B, self.fc.bias, True)
         h = alloc(key + ".h", (nm, B, 512), F16)
         ops.swish_dropout_fwd(fc_raw, masks, h, B, 512)
-        heads = alloc(key + ".heads", (nm * B, LATENT_HEADS), F32)
+        heads = alloc(key + ".heads", (nm * B, self.HN), F32)
         _ig(self.heads, "fwd", h, heads, nm * B, self.heads.bias, True)
         if self.cd:
             if cond is None or tuple(cond.shape) != (B, self.cd):
                 raise ValueError(f"conditional encoder needs a condition of shape ({B}, {self.cd})")
             for j in range(nm):
-                for half, nm_ in enumerate(("linear_means", "linear_log_var")):
+                for half, nm_ in enumerate(self.head_names):
                     ops.linear_f32_acc(cond, self.pview(nm_ + ".weight")[512:], heads[j * B:(j + 1) * B, 256 * half:],
-                                       B, 256, self.cd, self.cd, 512 + self.cd, LATENT_HEADS)
+                                       B, 256, self.cd, self.cd, 512 + self.cd, self.HN)
             r["cond"] = cond
         r.update(raw1=raw1, act1=act1, raw2=raw2, act2=act2, raw3=raw3, act3=act3, raw4=raw4, act4=act4,
                  fc_raw=fc_raw, h=h, heads=heads)
@@ -475,18 +479,19 @@ class EncoderExec(_NetBase):
         Accumulates parameter gradients into the arena."""
         arena, B, nm = self.arena, r["B"], len(r["masks"])
         rows = nm * B
-        dh16 = alloc(key + ".dheads16", (rows, 512), F16)
-        ops.f32_to_f16(d_heads, dh16, rows * 512, in_scale)
-        db = alloc(key + ".db512", (512,), F32, zero="step")
-        ops.colsum_f32(d_heads, db, rows, 512, 512, unscale * in_scale)
+        HN = self.HN
+        dh16 = alloc(key + ".dheads16", (rows, HN), F16)
+        ops.f32_to_f16(d_heads, dh16, rows * HN, in_scale)
+        db = alloc(key + ".db512", (HN,), F32, zero="step")
+        ops.colsum_f32(d_heads, db, rows, HN, HN, unscale * in_scale)
         ops.unpack_add_f32(db, self.heads.bias_idx, arena.grad)
         _wgrad_into(self.heads, r["h"], dh16, rows, arena, alloc, key + ".dW_heads", unscale, gp)
         if self.cd:
             for j in range(nm):
-                for half, nm_ in enumerate(("linear_means", "linear_log_var")):
+                for half, nm_ in enumerate(self.head_names):
                     ops.linear_f32_wgrad(r["cond"], d_heads[j * B:(j + 1) * B, 256 * half:],
                                          self.pview(nm_ + ".weight", True)[512:], B, 256, self.cd, self.cd,
-                                         LATENT_HEADS, 512 + self.cd, unscale * in_scale)
+                                         HN, 512 + self.cd, unscale * in_scale)
         dH = alloc(key + ".dH", (rows, 512), F32)
         _ig(self.heads, "dgrad", dh16, dH, rows, None, True)
         dfc = alloc(key + ".dfc16", (B, 512), F16)
@@ -720,6 +725,55 @@ class PoseExec:
         return dz
 
 
+# ---------------------------------------------------------------------------------------------
+# pose regressor baseline (models.py:28-77)
+# ---------------------------------------------------------------------------------------------
+class RegressorExec:
+    """Regressor.forward: the image-encoder trunk (same conv_net / fc_net as the cnn Encoder) followed by
+    out_net = Linear(512 (+cd), 256) -> ReLU -> Linear(256, 256) -> ReLU -> Linear(256, out_dim).  The trunk
+    and out_net.0 run on the EncoderExec kernels (out_net.0 takes the place of the posterior heads,
+    condition columns included), the two small Linears behind it in fp32 on the pose-MLP kernels."""
+
+    def __init__(self, arena, device, cond_dim=0):
+        self.arena, self.device = arena, device
+        self.trunk = EncoderExec(arena, "", device, cond_dim, head_names=("out_net.0",))
+        self.out_dim = int(arena.view("out_net.4.bias").numel())
+
+    def p(self, name, grad=False):
+        return self.arena.view(name, self.arena.grad if grad else None)
+
+    def forward(self, x, mask, alloc, key, track=True, cond=None):
+        B = x.shape[0]
+        r = self.trunk.forward(x, [mask], alloc, key, track, cond)
+        a1 = alloc(key + ".a1", (B, 256), F32)
+        ops.relu_f32(r["heads"], a1)
+        a2 = alloc(key + ".a2", (B, 256), F32)
+        ops.linear_f32_fwd(a1, self.p("out_net.2.weight"), self.p("out_net.2.bias"), a2, B, 256, 256, 256, 256, 1)
+        out = alloc(key + ".out", (B, self.out_dim), F32)
+        ops.linear_f32_fwd(a2, self.p("out_net.4.weight"), self.p("out_net.4.bias"), out, B, self.out_dim, 256, 256,
+                           self.out_dim, 0)
+        r.update(a1=a1, a2=a2, out=out)
+        return r
+
+    def backward(self, r, d_out, alloc, key, unscale=1.0):
+        """d_out: (B, out_dim) fp32.  Parameter gradients accumulate into the arena."""
+        B, od = r["B"], self.out_dim
+        scr = alloc(key + ".scr", (B, 256), F32)
+        da2 = alloc(key + ".da2", (B, 256), F32)
+        ops.linear_f32_bwd(r["a2"], self.p("out_net.4.weight"), r["out"], d_out, scr, da2,
+                           self.p("out_net.4.weight", True), self.p("out_net.4.bias", True), B, od, 256, 256, od, 256,
+                           0, False, unscale)
+        da1 = alloc(key + ".da1", (B, 256), F32)
+        ops.linear_f32_bwd(r["a1"], self.p("out_net.2.weight"), r["a2"], da2, scr, da1,
+                           self.p("out_net.2.weight", True), self.p("out_net.2.bias", True), B, 256, 256, 256, 256, 256,
+                           1, False, unscale)
+        d_heads = alloc(key + ".d_heads", (B, 256), F32)
+        ops.act_grad_f32(r["a1"], da1, d_heads, B, 256, 256, 1)
+        # the fp16 trunk backward carries gradients multiplied by gs = B (like the ELBO step, whose loss is
+        # divided by B): a 'sum'-reduced MSE gradient is O(1) per sample already, so in_scale = 1
+        self.trunk.backward(r, d_heads, alloc, key, unscale, 1.0)
+
+
 def get_execs(module, device):
     """Build (once per module and device) the executors of every sub-network present."""
     arena = get_arena(module, device)
@@ -737,6 +791,10 @@ def get_execs(module, device):
                 ex["dec"][n] = DecoderExec(arena, n, dev, cd)
         if "pose_encoder" in names:
             ex["pose"] = PoseExec(arena, dev)
+        if "out_net" in names and "conv_net" in names:  # Regressor (models.py:28-77): the module IS the trunk
+            ex["reg"] = RegressorExec(arena, dev, int(getattr(module, "num_classes", 0) or 0)
+                                      if getattr(module, "conditional", False) else 0)
+            ex["enc"]["__regressor__"] = ex["reg"].trunk
         nets = list(ex["enc"].values()) + list(ex["dec"].values())
         ex["packer"] = ModelPacker(nets, dev)
         for net in nets:

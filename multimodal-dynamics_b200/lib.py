@@ -89,6 +89,8 @@ SIGNATURES = {
     "mmdyn_linear_f32_wgrad": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P], _I),
     "mmdyn_cond_add_f16": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "mmdyn_cond_wgrad_f16": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], _I),
+    "mmdyn_relu_f32": ([_P, _P, _LL, _P], _I),
+    "mmdyn_act_grad_f32": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     "mmdyn_resize_table_ints": ([_I, _I, _I, _I], _I),
     "mmdyn_resize_table": ([_I, _I, _I, _I, _P, _I], _I),
     "mmdyn_frames_u8_to_f32": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),

@@ -387,3 +387,13 @@ def cond_wgrad_f16(g, c, dW, n_idx, R, N, ldw, col0, cd, scale):
     with _Timed("cond_linear", None):
         check(_L().mmdyn_cond_wgrad_f16(_ptr(g), _ptr(c), _ptr(dW), _ptr(n_idx), R, N, ldw, col0, cd, scale, _stream()),
               "cond_wgrad_f16")
+
+
+def relu_f32(x, y):
+    with _Timed("relu_f32", None):
+        check(_L().mmdyn_relu_f32(_ptr(x), _ptr(y), x.numel(), _stream()), "relu_f32")
+
+
+def act_grad_f32(y, dy, dx, M, N, ldy, act):
+    with _Timed("act_grad_f32", None):
+        check(_L().mmdyn_act_grad_f32(_ptr(y), _ptr(dy), _ptr(dx), M, N, ldy, act, _stream()), "act_grad_f32")

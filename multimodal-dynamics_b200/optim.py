@@ -27,6 +27,25 @@ class _FlatOptimizer(torch.optim.Optimizer):
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=arena.flat.device)
         return arena
 
+    def state_dict(self):
+        """Flat-arena optimizer state (moment buffers + step count) for checkpoint resume."""
+        self._arena()
+        # the device-side counter is the truth: CUDA-graph replays advance it without touching self._step
+        return {"kind": type(self).__name__, "step": int(self._step_dev.item()), "bufs": [b.detach().cpu() for b in self._bufs],
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, state):
+        arena = self._arena()
+        if state.get("kind") != type(self).__name__ or len(state["bufs"]) != self._n_bufs \
+                or state["bufs"][0].numel() != arena.total:
+            raise ValueError("optimizer state does not match this optimizer / model")
+        for dst, src in zip(self._bufs, state["bufs"]):
+            dst.copy_(src)
+        self._step = int(state["step"])
+        self._step_dev.fill_(self._step)
+        for g, sg in zip(self.param_groups, state.get("param_groups", [])):
+            g.update(sg)
+
     def zero_grad(self, set_to_none=True):
         """Keeps p.grad as views of the gradient arena and clears it with one memset."""
         arena = self._arena()

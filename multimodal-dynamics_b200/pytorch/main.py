@@ -40,6 +40,9 @@ def build_parser():
     p.add_argument('--latent-size', type=int, default=256, help='Latent dimension (default: 256)')
     p.add_argument('--annealing-epochs', type=int, default=50, help='Number of epochs to anneal KL for (default: 50)')
     p.add_argument('--conditional', action='store_true', default=False, help='Conditional VAE: condition the image experts on the shock force (data[4])')
+    # not in the reference (it can only write checkpoints, problems.py:751-757): continue a run from one
+    p.add_argument('--resume', default=None, type=str,
+                   help='epoch_N.ckpt written by this code or by the reference: load the model, continue at epoch N+1')
     return p
 
 

@@ -55,6 +55,7 @@ class Problem:
         self._categorical_conditions = None
         self._seq_length = None
         self._engine = None
+        self._start_epoch = 0
         if self.parameters.get('no_cuda') or not torch.cuda.is_available():
             raise RuntimeError("mmdyn_b200 runs on a CUDA device (B200) only; --no-cuda / CPU execution is the "
                                "reference's own path")
@@ -66,6 +67,8 @@ class Problem:
         else:
             self.set_dir()
             self._set_problem()
+            if self.parameters.get('resume'):
+                self.load_checkpoint(self.parameters['resume'])
 
     # -- construction ---------------------------------------------------------------------------
     def _set_problem(self):
@@ -183,22 +186,51 @@ class Problem:
             self._log_test_info(inputs, outputs, targets, _f(validation_loss), epoch, perf_measure=perf_measure)
         return perf_measure
 
+    # -- checkpoints ---------------------------------------------------------------------------------
+    def save_checkpoint(self, loss, epoch):
+        """The reference's checkpoint, byte-compatible (problems.py:751-757: keys model / loss / epoch), plus
+        a side file `<ckpt>.optim` with the fused optimizer's moments so that a resumed run continues
+        the same trajectory (the reference saves no optimizer state and cannot resume)."""
+        path = self._checkpoint_dir + '/epoch_' + str(epoch) + '.ckpt'
+        torch.save({'model': self._model.state_dict(), 'loss': loss, 'epoch': epoch}, path)
+        if hasattr(self._optimizer, 'state_dict') and isinstance(self._optimizer, fused_optim._FlatOptimizer):
+            torch.save(self._optimizer.state_dict(), path + '.optim')
+        return path
+
+    def load_checkpoint(self, path):
+        """Resume: model weights + BatchNorm buffers from `path` (written here or by the reference),
+        best loss and epoch counter; optimizer moments from `<path>.optim` when present (otherwise the
+        optimizer restarts from zero moments, which is all a reference checkpoint allows)."""
+        state = torch.load(path, map_location='cpu', weights_only=False)
+        missing = {'model', 'loss', 'epoch'} - set(state)
+        if missing:
+            raise ValueError(f"{path} is not a mmdyn checkpoint: missing {sorted(missing)}")
+        self._model.load_state_dict(state['model'])
+        engine.get_arena(self._model).bump()  # the packed fp16 operand copies must be rebuilt
+        self._best_loss = _f(state['loss'])
+        self._start_epoch = int(state['epoch']) + 1
+        if os.path.exists(path + '.optim') and isinstance(self._optimizer, fused_optim._FlatOptimizer):
+            self._optimizer.load_state_dict(torch.load(path + '.optim', map_location='cpu', weights_only=False))
+        return state
+
     def train(self, save=True):
         from torch.utils.tensorboard import SummaryWriter
         perf_measure = 0
         self._writer = SummaryWriter(self._tensorboard_dir)
-        for epoch in range(self.parameters['num_epochs']):
+        first = self._start_epoch
+        for epoch in range(first, self.parameters['num_epochs']):
             self._anneal_KL(epoch)
             self._train_epoch(epoch)
             perf_measure = self._test_epoch(epoch)
             self._sample(n=50)
             for key in self._logger_dict:
-                self._writer.add_scalar(key, self._logger_dict[key][epoch], epoch)
+                self._writer.add_scalar(key, self._logger_dict[key][epoch - first], epoch)
             for key in self._logger_histogram:
                 self._writer.add_histogram(key, self._logger_histogram[key], global_step=epoch)
             self._write_images(epoch)
         hp = {k: v for k, v in self.parameters.items() if isinstance(v, (int, float, str, bool))}
-        self._writer.add_hparams(hp, {k: _f(v) for k, v in perf_measure.items()})
+        if isinstance(perf_measure, dict):  # no epoch ran (resumed at or past --num-epochs): nothing to report
+            self._writer.add_hparams(hp, {k: _f(v) for k, v in perf_measure.items()})
         if save:
             save_pkl(dict(self._logger_dict), os.path.join(self._log_dir, 'results.pkl'))
 
@@ -230,11 +262,77 @@ class Problem:
 
 
 class Regression(Problem):
-    """Pose-regression baseline (problems.py:263-359): not part of the accelerated path."""
+    """Baseline regressing the resting pose from the first frame (problems.py:263-359).
+    Eager step: trunk + out_net.0 on the tensor-core kernels, the rest of out_net and the MSE in fp32."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("--problem-type regression is outside the B200 hot path (SURVEY.md §8f); "
-                                  "use the reference for it")
+    def set_model(self):
+        self._set_condition_dim()
+        # the reference passes `condition_dim`, which its Regressor does not accept (TypeError as shipped,
+        # problems.py:272-277 vs models.py:30); the mirror's Regressor takes it as an alias of num_classes
+        self._model = setup_model(self.parameters['model_name'], condition_dim=self._condition_dim, out_dim=7,
+                                  conditional=self._conditional)
+        self._model.to(self._device)
+
+    def _set_condition_dim(self):
+        """problems.py:283-289: the shock-force width; the reference's fallback (`len(data[0][-1])`) only makes
+        sense for its pickled list datasets, here a dataset without a shock field gives 0."""
+        self._categorical_conditions = False
+        try:
+            self._condition_dim = len(self.train_dataset.data[0][0][4])
+        except Exception:
+            self._condition_dim = 0
+
+    def parse_input(self, data, target):
+        """problems.py:291-316: the image of the first frame of every sequence -> the resting pose."""
+        L, dev = self._seq_length, self._device
+        model_input = target_output = None
+        if not isinstance(data, list):
+            model_input, target_output = data.to(dev), target.to(dev)
+        elif len(data) == 1:
+            model_input, target_output = data[0].to(dev), target[0].to(dev)
+        elif self.parameters['input_type'] == 'visual':
+            model_input, target_output = data[0][::L].to(dev), target[2][::L].to(dev)
+        elif self.parameters['input_type'] == 'tactile':
+            model_input, target_output = data[1][::L].to(dev), target[2][::L].to(dev)
+        shock = data[4][::L].to(dev) if isinstance(data, list) and len(data) > 4 else None
+        return {'model_input': model_input, 'shock': shock}, target_output
+
+    def set_criterion(self):
+        self._criterion = losses.mse_sum  # nn.MSELoss(reduction='sum'), one kernel (sum + gradient)
+
+    def _evaluate_model(self, inputs, targets, **kwargs):
+        """problems.py:321-332."""
+        if self._conditional:
+            if inputs['shock'] is None:
+                raise ValueError("--conditional needs the shock force as the 5th data field (datasets.py: data[4])")
+            out = self._model(inputs['model_input'], inputs['shock'])
+        else:
+            out = self._model(inputs['model_input'])
+        loss = self._criterion(out.view(targets.size()), targets)
+        with torch.no_grad():
+            pose_measure = loss.detach() / targets.numel()  # F.mse_loss(reduction='mean') of the same tensors
+        return {'outputs': out, 'perf_measure': {'pose': pose_measure}}, loss
+
+    def _sample(self, n=50):
+        pass
+
+    def _log_train_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
+        self._logger_dict['Loss/train_epoch'].append(loss / len(self.train_loader))
+        if perf_measure:
+            for k, v in perf_measure.items():
+                self._logger_dict['Perf_measure_train/' + k].append(v / len(self.train_loader))
+
+    def _log_test_info(self, inputs, outputs, targets, loss, epoch, perf_measure=None):
+        self._logger_dict['Loss/validation_epoch'].append(loss / len(self.test_loader))
+        if perf_measure:
+            for k, v in perf_measure.items():
+                self._logger_dict['Perf_measure_validation/' + k].append(v / len(self.test_loader))
+        if loss < self._best_loss:
+            self.save_checkpoint(loss, epoch)
+            self._best_loss = loss
+
+    def _write_images(self, epoch, n_images=100):
+        pass
 
 
 class Reconstruction(Problem):
@@ -419,8 +517,7 @@ class Reconstruction(Problem):
     def _save_if_best(self, loss, epoch):
         """Best-validation checkpoint with the reference's keys (problems.py:580-586)."""
         if loss < self._best_loss:
-            state = {'model': self._model.state_dict(), 'loss': loss, 'epoch': epoch}
-            torch.save(state, self._checkpoint_dir + '/epoch_' + str(epoch) + '.ckpt')
+            self.save_checkpoint(loss, epoch)
             self._best_loss = loss
 
     def _write_images(self, epoch, n_images=120):

@@ -295,6 +295,50 @@ def evaluate_mvae(sd, x, targets, kl_weight, pose_multiplier, use_pose, noises, 
     return outputs, loss, per_pass
 
 
+def regressor_forward(sd, x, dropout_mask=None, c=None, track=True, acts=None):
+    """Regressor.forward (models.py:64-77): conv_net -> flatten -> fc_net (Linear, Swish, Dropout) ->
+    [cat condition] -> out_net (Linear ReLU Linear ReLU Linear).  The conv_net / fc_net stack is the cnn
+    Encoder's (models.py:38-55 == vae.py:198-214), restated once more here because the parameter names
+    carry no sub-module prefix."""
+    def rec(k, v):
+        if acts is not None:
+            acts[k] = v
+    h = swish(F.conv2d(x, sd["conv_net.0.weight"], stride=2, padding=1))
+    h = F.conv2d(h, sd["conv_net.2.weight"], stride=2, padding=1)
+    h = swish(_bn_train(h, sd, "conv_net.3", track))
+    h = F.conv2d(h, sd["conv_net.5.weight"], stride=2, padding=1)
+    h = swish(_bn_train(h, sd, "conv_net.6", track))
+    h = F.conv2d(h, sd["conv_net.8.weight"], stride=1, padding=0)
+    h = swish(_bn_train(h, sd, "conv_net.9", track))
+    rec("act4", h)
+    h = swish(F.linear(h.reshape(h.size(0), -1), sd["fc_net.0.weight"], sd["fc_net.0.bias"]))
+    if dropout_mask is not None:
+        h = h * dropout_mask
+    rec("fc", h)
+    h = _cat_condition(h, c)
+    h = F.relu(F.linear(h, sd["out_net.0.weight"], sd["out_net.0.bias"]))
+    rec("a1", h)
+    h = F.relu(F.linear(h, sd["out_net.2.weight"], sd["out_net.2.bias"]))
+    return F.linear(h, sd["out_net.4.weight"], sd["out_net.4.bias"])
+
+
+def evaluate_regression(sd, x, target, dropout_mask, condition=None, track=True, acts=None):
+    """Regression._evaluate_model (problems.py:321-332): MSE 'sum' loss, mean-MSE metric."""
+    out = regressor_forward(sd, x, dropout_mask, condition, track, acts)
+    loss = F.mse_loss(out.view(target.size()), target, reduction="sum")
+    with torch.no_grad():
+        m = F.mse_loss(out.view(target.size()), target, reduction="mean").item()
+    return {"outputs": out, "perf_measure": {"pose": m}}, loss
+
+
+def regression_parse_input(data, target, seq_length, input_type):
+    """Regression.parse_input (problems.py:291-316) on seq-collated lists."""
+    L = seq_length
+    k = 0 if input_type == "visual" else 1
+    shock = data[4][::L] if len(data) > 4 else None
+    return {"model_input": data[k][::L], "shock": shock}, target[2][::L]
+
+
 def evaluate_vae(sd, x, target, kl_weight, noise, loss_mask=None, track=True, acts=None, input_type="visual",
                  condition=None):
     """SeqModeling._evaluate_model, plain VAE / CVAE branch (problems.py:702-716)."""

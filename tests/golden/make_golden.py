@@ -116,6 +116,52 @@ def golden_case(problems, setup_model, name, model_name, input_type, use_pose, B
     print(name, "loss", g["loss"], "perf", g["perf_measure"])
 
 
+def golden_regression(problems, setup_model, name, B, cond_dim=0):
+    """Regression._evaluate_model + Adam on the reference's Regressor (models.py:28-77, problems.py:263-332).
+    The reference's own set_model cannot build it (it passes `condition_dim`, Regressor takes `num_classes`:
+    TypeError), so the model is built through setup_model with the keywords Regressor does accept."""
+    pr = object.__new__(problems.Regression)
+    pr.parameters = {"model_name": "regressor", "input_type": "visual"}
+    pr._conditional, pr._device, pr._seq_length = cond_dim > 0, torch.device("cpu"), 5
+    torch.manual_seed(0)
+    pr._model = setup_model("regressor", out_dim=7, conditional=cond_dim > 0, num_classes=cond_dim)  # num_classes=None fails even un-conditional: False * None (models.py:36)
+    pr._model.train()
+    pr.set_criterion()
+    d = batch(B, seed=1)
+    w0 = {n: summary(p) for n, p in pr._model.state_dict().items() if p.is_floating_point()}
+    opt = torch.optim.Adam(pr._model.parameters(), lr=1e-3)
+    opt.zero_grad()
+    torch.manual_seed(123)
+    outputs, loss = pr._evaluate_model({"model_input": d["v"], "shock": d["c"] if cond_dim else None}, d["tp"])
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in pr._model.named_parameters()}
+    opt.step()
+    # parse_input on a seq-collated batch (S sequences x L frames, small images)
+    S, L = 3, 5
+    g = torch.Generator().manual_seed(5)
+    n = S * L
+    data = [torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 7, generator=g),
+            torch.ones(n, 2), torch.rand(n, 3, generator=g)]
+    target = [torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 7, generator=g),
+              (torch.rand(n, 3, 4, 4, generator=g) > 0.5).float()]
+    parsed = {}
+    for it in ("visual", "tactile"):
+        pr.parameters["input_type"] = it
+        parsed[it] = pr.parse_input([t.clone() for t in data], [t.clone() for t in target])
+    out = {"case": name, "B": B, "cond_dim": cond_dim, "weights_seed": 0, "data_seed": 1, "noise_seed": 123,
+           "loss": loss.item(), "outputs": outputs["outputs"].detach().clone(),
+           "perf_measure": {k: float(v) for k, v in outputs["perf_measure"].items()},
+           "w0": w0, "grads": {n: summary(v) for n, v in grads.items()},
+           "params_after": {n: summary(p) for n, p in pr._model.named_parameters()},
+           "buffers_after": {n: b.detach().clone() for n, b in pr._model.named_buffers()
+                             if n.endswith("num_batches_tracked") or b.numel() <= 64},
+           "parse": {"L": L, "data": data, "target": target, "parsed": parsed},
+           "state_keys": list(pr._model.state_dict().keys()),
+           "torch": torch.__version__, "threads": torch.get_num_threads()}
+    torch.save(out, os.path.join(OUT, name + ".pt"))
+    print(name, "loss", out["loss"], "perf", out["perf_measure"])
+
+
 def golden_parse_input(problems):
     """Integer / index path: SeqModeling.parse_input and DynModeling.parse_input on a seq-collated
     batch of S sequences x L frames (small images: the indexing does not depend on H, W)."""
@@ -155,6 +201,10 @@ if __name__ == "__main__":
         golden_case(problems, setup_model, "cvae_visual_b4", "cnn-vae", "visual", False, 4, cond_dim=3)
         golden_case(problems, setup_model, "cmvae_pose_b3", "cnn-mvae", "visuotactile", True, 3, cond_dim=3)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "regression":  # only the Regressor fixtures
+        golden_regression(problems, setup_model, "regressor_b4", 4)
+        golden_regression(problems, setup_model, "regressor_cond_b4", 4, cond_dim=3)
+        sys.exit(0)
     golden_case(problems, setup_model, "vae_visual_b4", "cnn-vae", "visual", False, 4)
     golden_case(problems, setup_model, "vae_tactile_masked_b4", "cnn-vae", "tactile", False, 4, mask_loss=True)
     golden_case(problems, setup_model, "mvae_b4", "cnn-mvae", "visuotactile", False, 4)
@@ -162,5 +212,7 @@ if __name__ == "__main__":
     golden_case(problems, setup_model, "mvae_masked_b3", "cnn-mvae", "visuotactile", False, 3, mask_loss=True)
     golden_case(problems, setup_model, "cvae_visual_b4", "cnn-vae", "visual", False, 4, cond_dim=3)
     golden_case(problems, setup_model, "cmvae_pose_b3", "cnn-mvae", "visuotactile", True, 3, cond_dim=3)
+    golden_regression(problems, setup_model, "regressor_b4", 4)
+    golden_regression(problems, setup_model, "regressor_cond_b4", 4, cond_dim=3)
     golden_parse_input(problems)
     golden_anneal(problems)

@@ -498,3 +498,152 @@ def test_cmvae_pose_fused_step_matches_oracle():
     flat_o = torch.cat([sd_o[k].grad.reshape(-1) for k in pkeys])
     flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
     assert nrel(flat_d, flat_o) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# Regressor baseline (models.py:28-77, problems.py:321-332)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cd", [0, 3])
+def test_regressor_step_matches_oracle(cd):
+    from mmdyn_b200 import losses, noise, optim
+    from mmdyn_b200.pytorch.models.models import setup_model
+    B = 8
+    torch.manual_seed(3)
+    model = setup_model("regressor", condition_dim=cd, out_dim=7, conditional=cd > 0)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV)
+    assert tuple(sd["out_net.0.weight"].shape) == (256, 512 + cd)
+    d = batch(B, seed=12)
+    c = (2 * torch.rand(B, 3, generator=torch.Generator().manual_seed(5)) - 1) if cd else None
+    pkeys = [k for k, _ in model.named_parameters()]
+    mask, _, _ = orc.draw_pass_noise(B, True, False, generator=torch.Generator().manual_seed(11))
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    acts = {}
+    out_o, loss_o = orc.evaluate_regression(sd_o, d["v"], d["tp"], mask, c, acts=acts)
+    loss_o.backward()
+    model.noise = noise.HostNoise(torch.Generator().manual_seed(11))
+    opt = optim.FusedAdam(model, lr=1e-3)
+    opt.zero_grad()
+    out = model(d["v"].to(DEV), c.to(DEV)) if cd else model(d["v"].to(DEV))
+    loss = losses.mse_sum(out.view(B, 7), d["tp"].to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    # out = O(0.1) numbers behind a 12-layer fp16 trunk: norm-wise 2e-3; the loss is dominated by the targets
+    assert nrel(out, out_o["outputs"]) < 2e-3, nrel(out, out_o["outputs"])
+    assert abs(loss.item() - loss_o.item()) / loss_o.item() < 1e-3
+    gerr = {k: nrel(p.grad, sd_o[k].grad) for k, p in model.named_parameters()}
+    print("worst gradient errors:\n" + "\n".join(f"{k:40s} {v:.3e}" for k, v in sorted(gerr.items(), key=lambda kv: -kv[1])[:6]))
+    for k, v in gerr.items():
+        assert v < 2e-2, (k, v)  # ReLU units of out_net flip under the trunk's 1e-3 perturbation (cf. pose expert)
+    flat_o = torch.cat([sd_o[k].grad.reshape(-1) for k in pkeys])
+    flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    assert nrel(flat_d, flat_o) < 1e-2, nrel(flat_d, flat_o)
+    if cd:
+        e = nrel(dict(model.named_parameters())["out_net.0.weight"].grad[:, 512:], sd_o["out_net.0.weight"].grad[:, 512:])
+        assert e < 2e-2, e
+        with pytest.raises(ValueError):
+            model(d["v"].to(DEV))
+    # BatchNorm buffers follow the reference (one forward = one update)
+    sdd = model.state_dict()
+    for k in sd_o:
+        if k.endswith("num_batches_tracked"):
+            assert int(sdd[k]) == int(sd_o[k]) == 1, k
+        elif "running_" in k:
+            assert nrel(sdd[k], sd_o[k]) < 2e-3, k
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    opt.step()
+    torch.cuda.synchronize()
+    for k, p in model.named_parameters():
+        assert torch.isfinite(p).all() and (p - before[k]).abs().max().item() <= 1.0001e-3, k
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes through a size-independent property: replication invariance
+# ---------------------------------------------------------------------------------------------
+class _ReplayNoise:
+    """Test-only noise source handing out prescribed tensors in the engine's draw order."""
+
+    def __init__(self, noises, passes, reps):
+        self.q = []
+        for (mv, mt, eps), (hv, ht, hp) in zip(noises, passes):
+            self.q += ([("mask", mv)] if hv else []) + ([("mask", mt)] if ht else []) + [("eps", eps)]
+        self.reps = reps
+
+    def _next(self, kind, device, out):
+        k, t = self.q.pop(0)
+        assert k == kind
+        t = t.repeat(self.reps, 1).to(device)
+        if out is None:
+            return t
+        out.copy_(t)
+        return out
+
+    def dropout_mask(self, B, device, out=None):
+        return self._next("mask", device, out)
+
+    def normal(self, B, D, device, out=None):
+        return self._next("eps", device, out)
+
+
+@pytest.mark.parametrize("B", [1024, 4096])
+def test_full_size_step_equals_oracle_on_the_replicated_base_batch(B):
+    """The bench workload (cnn-mvae visuotactile + pose, 7 passes, per-GPU batch 1024; 4096 = the top of
+    configs[4]'s sweep) cannot be run by the CPU oracle in seconds, but a batch made of R copies of a
+    B0-row base batch (inputs, targets, dropout masks and eps all replicated) has the SAME BatchNorm
+    batch statistics (mean and biased variance), the same per-row activations, the same loss (sum / B)
+    and the same parameter gradients as the base batch.  So the full-size GPU step is checked against
+    the oracle run on B0 = 16 rows: every tile, group and row offset of the big launch is exercised and
+    any row-dependent indexing error breaks the equality."""
+    from mmdyn_b200 import engine
+    B0 = 16
+    R = B // B0
+    model, sd = make("cnn-mvae", True, seed=6)
+    d = batch(B0, seed=14)
+    klw, pm = 0.02, 1000.0
+    passes = orc.MVAE_PASSES_POSE
+    noises = oracle_noises(passes, B0, 31)
+    pkeys = [k for k, _ in model.named_parameters()]
+    x_o, t_o = [d["v"], d["t"], d["p"]], [d["tv"], d["tt"], d["tp"]]
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    out_o, loss_o, per_pass = orc.evaluate_mvae(sd_o, x_o, t_o, klw, pm, True, noises)
+    loss_o.backward()
+    rep = lambda t: t.repeat(R, *([1] * (t.dim() - 1))).to(DEV)
+    eng = engine.StepEngine(model, "mvae", use_pose=True, pose_multiplier=pm, noise_src=_ReplayNoise(noises, passes, R))
+    out_d, loss_d = eng.evaluate([rep(t) for t in x_o], [rep(t) for t in t_o], klw)
+    loss_d.backward()
+    torch.cuda.synchronize()
+    assert abs(loss_d.item() - loss_o.item()) / loss_o.item() < 1e-4, (loss_d.item(), loss_o.item())
+    for k, v in out_o["perf_measure"].items():
+        assert abs(float(out_d["perf_measure"][k]) - v) / abs(v) < 1e-3, k
+    mu_d, lv_d = eng.ws.bufs["mu"], eng.ws.bufs["lv"]          # (7, B, 256)
+    for i, pp in enumerate(per_pass):
+        assert nrel(mu_d[i][:B0], pp["mu"]) < 3e-3 and nrel(lv_d[i][:B0], pp["lv"]) < 3e-3, i
+    # every replica carries the same rows: posterior and reconstructions agree across the whole batch.
+    # Not bit for bit: the split-K fp32 atomics of the fc layer order their partial sums differently from
+    # tile to tile (1e-7), and behind that a few fp16 roundings of the decoder chain flip by one ulp.
+    for t in (mu_d, lv_d):
+        blocks = t.view(t.shape[0], R, B0, -1)
+        assert nrel(blocks[:, R - 1], blocks[:, 0]) < 1e-5 and nrel(blocks[:, R // 2], blocks[:, 0]) < 1e-5
+    for a, b in zip(out_d["recon_x"], out_o["recon_x"]):
+        a = a.reshape(R, B0, -1)
+        assert nrel(a[0], b.reshape(B0, -1)) < 3e-3
+        assert nrel(a[R - 1], a[0]) < 1e-3 and nrel(a[R // 3], a[0]) < 1e-3
+    gerr = {k: nrel(p.grad, sd_o[k].grad) for k, p in model.named_parameters()}
+    worst = sorted(gerr.items(), key=lambda kv: -kv[1])[:5]
+    print(f"B={B}: worst gradient errors vs the oracle on the base batch:\n" +
+          "\n".join(f"{k:50s} {v:.3e}" for k, v in worst))
+    for k, v in gerr.items():
+        assert v < 5e-2, (k, v)
+    flat_o = torch.cat([sd_o[k].grad.reshape(-1) for k in pkeys])
+    flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    assert nrel(flat_d, flat_o) < 2e-2, nrel(flat_d, flat_o)
+    # BatchNorm running statistics: the mean is replication invariant; the unbiased variance carries
+    # n/(n-1) with n = rows of the big batch instead of the base batch
+    sdd = model.state_dict()
+    for k in sd_o:
+        if k.endswith("running_mean") and "encoder" in k:
+            assert nrel(sdd[k], sd_o[k]) < 3e-3, k

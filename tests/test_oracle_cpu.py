@@ -157,3 +157,65 @@ def test_anneal_kl_matches_reference():
         pr.parameters = {"annealing_epochs": ae}
         pr._anneal_KL(e)
         assert pr._kl_weight == w == orc.anneal_kl(e, ae)
+
+
+# ---------------------------------------------------------------------------------------------
+# Regressor / --problem-type regression (models.py:28-77, problems.py:263-332)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["regressor_b4", "regressor_cond_b4"])
+def test_oracle_reproduces_reference_regression_step(case):
+    g = torch.load(os.path.join(GOLD, case + ".pt"), weights_only=False)
+    torch.set_num_threads(g["threads"])
+    from mmdyn_b200.pytorch.models.models import setup_model
+    cd = g["cond_dim"]
+    torch.manual_seed(g["weights_seed"])
+    # the keywords the reference's Regression.set_model passes (problems.py:272-277)
+    model = setup_model("regressor", condition_dim=cd, out_dim=7, conditional=cd > 0)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert list(sd.keys()) == g["state_keys"]
+    for k, s in g["w0"].items():  # bit-identical initialisation
+        m = summary(sd[k])
+        assert m["sum"] == s["sum"] and m["abs"] == s["abs"], k
+    pkeys = [k for k, _ in model.named_parameters()]
+    d = batch(g["B"], g["data_seed"])
+    torch.manual_seed(g["noise_seed"])
+    mask, _, _ = orc.draw_pass_noise(g["B"], True, False)  # the Dropout(0.1) mask behind fc_net
+    params = [sd[k].requires_grad_(True) for k in pkeys]
+    outputs, loss = orc.evaluate_regression(sd, d["v"], d["tp"], mask, d["c"] if cd else None)
+    loss.backward()
+    grads = [p.grad.detach().clone() for p in params]
+    st = {"step": 0, "m": [torch.zeros_like(p) for p in params], "v": [torch.zeros_like(p) for p in params]}
+    with torch.no_grad():
+        for p in params:
+            p.requires_grad_(False)
+        orc.adam_step(params, grads, st, lr=1e-3)
+    assert close(loss.item(), g["loss"], 2e-6), (loss.item(), g["loss"])
+    assert torch.allclose(outputs["outputs"].detach(), g["outputs"], rtol=1e-4, atol=1e-6)
+    assert close(outputs["perf_measure"]["pose"], g["perf_measure"]["pose"], 1e-5)
+    for k, gr in zip(pkeys, grads):
+        check_summary(gr, g["grads"][k], 2e-3, "grad " + k)
+    for k in pkeys:
+        check_summary(sd[k], g["params_after"][k], 1e-4, "param " + k)
+    for k, v in g["buffers_after"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert torch.allclose(sd[k], v, rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("it", ["visual", "tactile"])
+def test_regression_parse_input_is_bit_exact(it):
+    g = torch.load(os.path.join(GOLD, "regressor_cond_b4.pt"), weights_only=False)["parse"]
+    from mmdyn_b200.pytorch.problems import problems
+    pr = object.__new__(problems.Regression)
+    pr.parameters = {"input_type": it}
+    pr._seq_length, pr._device = g["L"], torch.device("cpu")
+    xi, ti = pr.parse_input([t.clone() for t in g["data"]], [t.clone() for t in g["target"]])
+    xo, to = orc.regression_parse_input(g["data"], g["target"], g["L"], it)
+    xg, tg = g["parsed"][it]
+    for a in (xi, xo):
+        assert torch.equal(a["model_input"], xg["model_input"]) and torch.equal(a["shock"], xg["shock"])
+    assert torch.equal(ti, tg) and torch.equal(to, tg)
+    # a batch without the shock field (exp 1 / 2 datasets): shock is None on every side
+    xi, _ = pr.parse_input([t.clone() for t in g["data"][:4]], [t.clone() for t in g["target"]])
+    assert xi["shock"] is None

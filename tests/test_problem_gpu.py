@@ -84,8 +84,60 @@ def test_main_conditional_mvae_pose_and_vae(tmp_path, monkeypatch):
     check_run(p, 46)
 
 
+def test_main_regression(tmp_path, monkeypatch):
+    """--problem-type regression --model-name regressor: first frame -> resting pose."""
+    p = run_main(tmp_path, monkeypatch, ["--problem-type", "regression", "--model-name", "regressor",
+                                         "--input-type", "tactile"])
+    ck = sorted(glob.glob(os.path.join(p.checkpoint_dir, "epoch_*.ckpt")))
+    state = torch.load(ck[-1], weights_only=False)
+    assert set(state) == {"model", "loss", "epoch"} and len(state["model"]) == 27
+    losses = p._logger_dict["Loss/train_epoch"]
+    assert len(losses) == 2 and all(float(l) == float(l) for l in losses)
+    assert len(p._logger_dict["Perf_measure_train/pose"]) == 2
+    vl = [float(v) for v in p._logger_dict["Loss/validation_epoch"]]
+    assert len(vl) == 2 and all(v == v and v < 1e4 for v in vl)
+    p = run_main_cond(tmp_path, monkeypatch, ["--problem-type", "regression", "--model-name", "regressor",
+                                              "--input-type", "visual"])
+    assert tuple(p._model.state_dict()["out_net.0.weight"].shape) == (256, 515)
+
+
+def test_resume_from_checkpoint(tmp_path, monkeypatch):
+    """--resume (not in the reference, which only writes checkpoints): weights, BatchNorm buffers, best loss,
+    epoch counter and the fused optimizer's moments / step count come back; training continues at epoch N+1."""
+    from mmdyn_b200.pytorch.main import main
+    p = run_main(tmp_path, monkeypatch, ["--problem-type", "seq_modeling", "--input-type", "visuotactile",
+                                         "--model-name", "cnn-mvae"])
+    ck = sorted(glob.glob(os.path.join(p.checkpoint_dir, "epoch_*.ckpt")))[-1]
+    state = torch.load(ck, weights_only=False)
+    assert os.path.exists(ck + ".optim")
+    ost = torch.load(ck + ".optim", weights_only=False)
+    steps_per_epoch = len(p.train_loader)
+    assert ost["kind"] == "FusedAdam" and ost["step"] == steps_per_epoch * (state["epoch"] + 1)
+    monkeypatch.chdir(tmp_path)
+    argv = ["--dataset-path", "synthetic:8:5", "--batchsize", "4", "--annealing-epochs", "4", "--save-name", "r",
+            "--problem-type", "seq_modeling", "--input-type", "visuotactile", "--model-name", "cnn-mvae", "--resume", ck]
+    from mmdyn_b200.pytorch.problems.problems import SeqModeling
+    from mmdyn_b200.pytorch.main import build_parser
+    q = SeqModeling(build_parser().parse_args(argv + ["--num-epochs", str(state["epoch"] + 2)]))
+    assert q._start_epoch == state["epoch"] + 1 and float(q._best_loss) == float(state["loss"])
+    for k, v in q._model.state_dict().items():
+        assert torch.equal(v.cpu(), state["model"][k].cpu()), k
+    assert int(q._optimizer._step_dev.item()) == ost["step"]
+    assert torch.equal(q._optimizer._bufs[0].cpu(), ost["bufs"][0])
+    q.train()
+    assert len(q._logger_dict["Loss/train_epoch"]) == 1  # exactly the one remaining epoch ran
+    assert q._logger_dict["KL_annealing/train_epoch"] == [(state["epoch"] + 2) / 4]
+    assert int(q._optimizer.state_dict()["step"]) == ost["step"] + steps_per_epoch
+    # a reference-format checkpoint without the side file resumes too (optimizer restarts)
+    os.remove(ck + ".optim")
+    r = SeqModeling(build_parser().parse_args(argv + ["--num-epochs", "1"]))
+    assert r._start_epoch == state["epoch"] + 1 and int(r._optimizer.state_dict()["step"]) == 0
+    with pytest.raises(ValueError):
+        bad = os.path.join(tmp_path, "bad.ckpt")
+        torch.save({"model": {}}, bad)
+        r.load_checkpoint(bad)
+
+
 def test_unsupported_paths_fail_loudly(tmp_path, monkeypatch):
-    with pytest.raises(NotImplementedError):
-        run_main(tmp_path, monkeypatch, ["--problem-type", "regression", "--model-name", "regressor"])
     with pytest.raises(RuntimeError, match="CUDA"):
         run_main(tmp_path, monkeypatch, ["--no-cuda"])
