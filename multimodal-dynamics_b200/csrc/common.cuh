@@ -242,6 +242,11 @@ __device__ __forceinline__ float swish_gradf_(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic transaction for 4 floats
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -330,9 +330,9 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else if (d.out_mode == 2) {
-          float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;
+          float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;  // 16-byte aligned (ldc % 4 == 0)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
+          for (int q = 0; q < 4; ++q) red_add_v4(o + 4 * q, f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else {
           // merged 2x2 sub-pixel phases -> fp32 NCHW planes; n = (ph*2 + pw)*3 + c
           float* o = reinterpret_cast<float*>(d.out) + out_off;
@@ -428,6 +428,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[BLOCK_N];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -603,24 +604,32 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
           }
         }
       }
+      // bias of this tile's BLOCK_N columns -> shared memory, once per tile and BEFORE the accumulator
+      // wait (16 dependent L2 round trips per tile inside the chunk loop made the K = 256 / 512 linear
+      // layers epilogue-bound: ncu long_scoreboard 6 warps per issue, tensor pipe 8.6 %)
+      if (d.bias != nullptr && t.split == 0) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) bias_s[i] = __ldg(d.bias + t.n_tile * BLOCK_N + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const int acc = tl & 1;
       mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS + (static_cast<uint32_t>(q4 * 32) << 16);
       const int n_base = t.n_tile * BLOCK_N;
       const bool add_bias = d.bias != nullptr && t.split == 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem_d + c0, v);
-        tmem_ld_wait();
-        if (out_off < 0) continue;
+      // one 16-column chunk of this thread's accumulator row -> global memory
+      auto emit = [&](const uint32_t (&v)[16], const int c0) {
+        if (out_off < 0) return;
         float f[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) f[q] = n_live > 0 ? __uint_as_float(v[q]) : 0.0f;
         if (add_bias) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) f[q] += __ldg(d.bias + n_base + c0 + q);
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(&bias_s[c0 + 4 * q]);  // same address in every lane
+            f[4 * q] += bq.x; f[4 * q + 1] += bq.y; f[4 * q + 2] += bq.z; f[4 * q + 3] += bq.w;
+          }
         }
         if (d.out_mode == 4) {
           // merged sub-pixel phases, NHWC fp16: this 16-column chunk belongs to one phase
@@ -642,9 +651,9 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else if (d.out_mode == 2) {
-          float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;
+          float* o = reinterpret_cast<float*>(d.out) + out_off + n_base + c0;  // 16-byte aligned (ldc % 4 == 0)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) atomicAdd(o + q, f[q]);
+          for (int q = 0; q < 4; ++q) red_add_v4(o + 4 * q, f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
         } else if (d.out_mode == 5) {
           if constexpr (BLOCK_N == 16) {
             const int plane = d.OH * d.OW;
@@ -709,6 +718,21 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
             for (int ph = 0; ph < 2; ++ph)
               *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
                   make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
+        }
+      };
+      // TMEM reads are software-pipelined: the load of chunk c+1 is in flight while chunk c is
+      // converted and stored (one tcgen05.ld round trip per 16 columns used to be fully exposed)
+      uint32_t va[16], vb[16];
+      tmem_ld_x16(tmem_d, va);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        tmem_ld_wait();
+        if (c0 + 16 < BLOCK_N) tmem_ld_x16(tmem_d + c0 + 16, vb);
+        emit(va, c0);
+        if (c0 + 16 < BLOCK_N) {
+          tmem_ld_wait();
+          if (c0 + 32 < BLOCK_N) tmem_ld_x16(tmem_d + c0 + 32, va);
+          emit(vb, c0 + 16);
         }
       }
       tc_fence_before();
@@ -1381,6 +1405,9 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
   MMDYN_REQUIRE(d->out_mode != 4 || (d->ldc % 16 == 0 && d->N == 4 * d->ldc && d->s_out == 2 && d->n_phases == 1),
                 "igemm: out_mode 4 needs N = 4*ldc, ldc %% 16 == 0, s_out = 2");
   MMDYN_REQUIRE(d->out_mode != 3 || (d->block_n == 16 && d->N == 16), "igemm: out_mode 3 needs N=16");
+  MMDYN_REQUIRE((d->out_mode != 1 && d->out_mode != 2) || d->ldc % 4 == 0,
+                "igemm: fp32 outputs (out_mode 1 / 2) are written as 16-byte vectors: ldc=%d must be a multiple of 4",
+                d->ldc);
   MMDYN_REQUIRE(d->row_mode == 0 || (d->row_mode == 1 && d->ksplit == 1 && d->Cin % 64 == 0),
                 "igemm: row_mode=%d (row_mode 1 needs ksplit 1 and Cin %% 64 == 0)", d->row_mode);
   MMDYN_REQUIRE(d->n_img > 0 && d->P > 0 && d->OXv > 0, "igemm: empty problem");

@@ -1234,9 +1234,13 @@ class GraphedTrainStep:
         eng = self.eng
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        # warm-up runs allocate every workspace outside the capture.  They must not train: no optimizer
+        # step (a graph is re-captured whenever the KL weight changes, i.e. every epoch of the annealing
+        # phase, and two stray Adam steps per capture would move the trajectory away from the reference's)
+        self.opt._arena()  # moment buffers + device step counter exist before the capture
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._body(True)
+                self._body(False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         eng.always_refresh = True
