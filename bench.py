@@ -362,6 +362,31 @@ def run_b200(args):
             with open(args.profile_out, "w") as f:
                 json.dump({"batch": B, "ms_per_step_events_sum": tot_ms, "kernels": table}, f, indent=1)
 
+    # ---- batch sweep (BASELINE.json configs[4]: batch 64-4096; 128 = the reference's --batchsize default) ----
+    sweep = None
+    if rank == 0 and world == 1 and use_graph and not args.no_sweep:
+        eng.set_concurrent(True)
+        sweep = []
+        for Bs in (64, 128, 256, 512, 1024, 2048, 4096):
+            if Bs == B:
+                sweep.append({"per_gpu_batch": Bs, "ms_per_step": ms_total / K, "samples_per_s": value})
+                continue
+            xb, tb = synth_batch(Bs, 99, device=dev)
+            g2 = engine.GraphedTrainStep(eng, opt, xb, tb, klw)
+            for _ in range(5):
+                g2.run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 30
+            e0.record()
+            for _ in range(n):
+                g2.run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            sweep.append({"per_gpu_batch": Bs, "ms_per_step": round(ms, 4), "samples_per_s": round(Bs / ms * 1e3, 1)})
+            del g2, xb, tb
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -382,7 +407,7 @@ def run_b200(args):
             "cuda_graph": bool(use_graph), "data_parallel_mode": dp_mode, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
             "step_tflops": value * FLOP_PER_SAMPLE / 1e12 / world,
             "step_frac_of_tensor_peak": value * FLOP_PER_SAMPLE / 1e12 / world / pk["tf_sust"],
-            "final_loss": final_loss, "top_kernels": table[:6],
+            "final_loss": final_loss, "top_kernels": table[:6], "batch_sweep": sweep,
         }
         print(json.dumps(out))
     if world > 1:
@@ -402,6 +427,7 @@ def main():
     ap.add_argument("--nccl-in-graph", action="store_true",
                     help="experimental: capture NCCL inside the step graph (hangs on torch 2.11 / NCCL 2.28.9)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the per-GPU batch sweep (64-4096, 30 graph replays each)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here (JSON)")
     args = ap.parse_args()
     if args.impl == "reference":
