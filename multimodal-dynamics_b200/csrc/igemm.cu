@@ -1373,6 +1373,16 @@ int igemm_init() {
     if (g_igemm_occ[i] * cols[i] > 512) g_igemm_occ[i] = 512 / cols[i];
     if (g_tma_occ[i] * cols[i] > 512) g_tma_occ[i] = 512 / cols[i];
   }
+  // experiment knob: cap the resident CTAs per SM of the persistent GEMM grids (leaves shared memory for
+  // co-resident CTAs of the HBM-bound BatchNorm kernels of the other modality's branch)
+  if (const char* cap = std::getenv("MMDYN_GEMM_OCC_CAP")) {
+    const int c = std::atoi(cap);
+    if (c >= 1)
+      for (int i = 0; i < 5; ++i) {
+        if (g_tma_occ[i] > c) g_tma_occ[i] = c;
+        if (g_igemm_occ[i] > c) g_igemm_occ[i] = c;
+      }
+  }
   return MMDYN_OK;
 }
 
