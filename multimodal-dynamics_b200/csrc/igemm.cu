@@ -301,7 +301,7 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
       for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
         uint32_t v[16];
         tmem_ld_x16(tmem_d + c0, v);
-        tmem_ld_wait();
+        tmem_ld_wait(v);
         if (out_off < 0) continue;
         float f[16];
 #pragma unroll
@@ -416,11 +416,25 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-template <int BLOCK_N, int A_MODE>
+// NCTA = 2 (A_MODE 0, BLOCK_N >= 128): CTA pairs.  The two CTAs of a cluster take the tiles 2q and 2q+1
+// (same weight tile: the launcher guarantees an even m-tile count), each loads its own 128 activation
+// rows and HALF of the weight tile, and the leader issues ONE tcgen05.mma.cta_group::2 (M = 256) per
+// K = 16 step.  Per SM and 64-wide k-block this halves the weight bytes TMA writes into and the tensor
+// core reads from shared memory: with cta_group::1 the 128 x 256 tile needs 183 B/clk/SM of
+// shared-memory bandwidth (TMA fill 48 KB + operand reads 48 KB per 524 MMA clocks) against the 128 B/clk
+// an SM has, which is what held the N >= 128 layers at 42-62 % tensor-pipe activity.
+template <int BLOCK_N, int A_MODE, int NCTA>
 __global__ void __launch_bounds__(TMA_THREADS)
 igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmW, const TileGeom g) {
   using C = Cfg<BLOCK_N>;
+  static_assert(NCTA == 1 || (A_MODE == 0 && BLOCK_N >= 128), "CTA pairs: A_MODE 0, BLOCK_N 128 / 256 only");
+  constexpr int B_LOAD_BYTES = C::B_STAGE_BYTES / NCTA;  // weight rows this CTA loads per k-block
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  // tiles of this CTA: first, stride (pairs walk tile pairs)
+  const int tile0 = NCTA == 2 ? 2 * (static_cast<int>(blockIdx.x) >> 1) + static_cast<int>(cta_rank)
+                              : static_cast<int>(blockIdx.x);
+  const int tile_step = NCTA == 2 ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
@@ -440,18 +454,24 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 128);
+      mbar_init(smem_u32(&tempty_bar[a]), 128 * NCTA);  // pairs: both CTAs' epilogues free the leader's MMA
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc2(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -470,7 +490,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
     // ======================= TMA producer =====================================================
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < g.total_tiles; tile += tile_step) {
         const TileCoord2 t = decode_tile2(d, g, tile);
         const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
         const int wx = t.x0 * d.s_in, wy = t.y0 * d.s_in;
@@ -478,8 +498,21 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
           if (!kb_live(t, kb)) continue;
           const int s = it % C::STAGES;
           mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
-          const uint32_t bar = smem_u32(&full_bar[s]);
           const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+          if constexpr (NCTA == 2) {
+            // every byte of the pair's stage is accounted on the LEADER's full barrier: the leader expects
+            // both CTAs' bytes, the peer's TMA completions may arrive first (transiently negative tx-count)
+            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2 * (A_STAGE_BYTES + B_LOAD_BYTES));
+            const int k = kb << 6;
+            const int tap = k / d.Cin, c0 = k - tap * d.Cin;
+            tma_load_4d_2cta(a_stage, &tmA, lbar, c0, wx + d.tap_dx[t.phase][tap], wy + d.tap_dy[t.phase][tap], t.img0);
+            tma_load_2d_2cta(a_stage + A_STAGE_BYTES, &tmW, lbar, kb << 6,
+                             t.phase * d.N + t.n_tile * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
+            ++it;
+            continue;
+          }
+          const uint32_t bar = smem_u32(&full_bar[s]);
           mbar_arrive_expect_tx(bar, A_STAGE_BYTES + C::B_STAGE_BYTES);
           if (A_MODE == 0) {
             const int k = kb << 6;
@@ -507,10 +540,10 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
     }
   } else if (warp == 1) {
     // ======================= MMA issuer ======================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 0, 0, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128 * NCTA, BLOCK_N, 0, 0, 0, 0);
       int it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++tl) {
         const TileCoord2 t = decode_tile2(d, g, tile);
         const int acc = tl & 1;
         mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
@@ -531,13 +564,16 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
             if (A_MODE == 0) adesc = make_smem_desc(a_base + 32 * kk, 16, 1024, LAYOUT_SW128);
             else if (A_MODE == 1) adesc = make_smem_desc(a_base + (kk >> 1) * 8192 + (kk & 1) * 32, 16, 512, LAYOUT_SW64);
             else adesc = make_smem_desc(a_base + kk * 4096, 2048, 128, 0);
-            umma_f16(tmem_d, adesc, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+            if (NCTA == 2) umma_f16_2cta(tmem_d, adesc, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+            else umma_f16(tmem_d, adesc, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
           }
           first = 0;
-          umma_commit(smem_u32(&empty_bar[s]));
+          if (NCTA == 2) umma_commit_2cta(smem_u32(&empty_bar[s]));  // frees the stage in both CTAs
+          else umma_commit(smem_u32(&empty_bar[s]));
           ++it;
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));
+        if (NCTA == 2) umma_commit_2cta(smem_u32(&tfull_bar[acc]));
+        else umma_commit(smem_u32(&tfull_bar[acc]));
       }
     }
   } else {
@@ -562,7 +598,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       bce_acc = 0.0f;
     };
     int tl = 0;
-    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++tl) {
       const TileCoord2 t = decode_tile2(d, g, tile);
       const int img = t.img0 + n_l, yv = t.y0 + y_l, xv = t.x0 + x_l;
       const bool valid = img < d.n_img;
@@ -726,25 +762,29 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       tmem_ld_x16(tmem_d, va);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        tmem_ld_wait();
+        tmem_ld_wait(va);  // ties va to the wait: no read of va may be scheduled before it
         if (c0 + 16 < BLOCK_N) tmem_ld_x16(tmem_d + c0 + 16, vb);
         emit(va, c0);
         if (c0 + 16 < BLOCK_N) {
-          tmem_ld_wait();
+          tmem_ld_wait(vb);
           if (c0 + 32 < BLOCK_N) tmem_ld_x16(tmem_d + c0 + 32, va);
           emit(vb, c0 + 16);
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&tempty_bar[acc]));  // accumulator stage free for tile tl + 2
+      // accumulator stage free for tile tl + 2 (pairs: the leader's MMA waits for both CTAs' epilogues)
+      if (NCTA == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      else mbar_arrive(smem_u32(&tempty_bar[acc]));
     }
     if (d.out_mode == 5) bce_flush();
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();  // the peer's shared memory / barriers / TMEM stay valid until both are done
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc2(tmem_base, 2 * C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
   }
 }
 
@@ -901,7 +941,7 @@ wgrad_kernel(const __grid_constant__ mmdyn_wgrad_desc d) {
     for (int c0 = 0; c0 < CN; c0 += 16) {
       uint32_t v[16];
       tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
-      tmem_ld_wait();
+      tmem_ld_wait(v);
 #pragma unroll
       for (int q = 0; q < 16; ++q)
         atomicAdd(o + static_cast<long long>(c0 + q) * d.ldw, d.scale * __uint_as_float(v[q]));
@@ -1053,7 +1093,7 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
     for (int c0 = 0; c0 < CN; c0 += 16) {
       uint32_t v[16];
       tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + c0, v);
-      tmem_ld_wait();
+      tmem_ld_wait(v);
 #pragma unroll
       for (int q = 0; q < 16; ++q)
         atomicAdd(o + static_cast<long long>(c0 + q) * d.ldw, d.scale * __uint_as_float(v[q]));
@@ -1146,7 +1186,7 @@ conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __h
   for (int c0 = 0; c0 < 32; c0 += 16) {
     uint32_t v[16];
     tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
-    tmem_ld_wait();
+    tmem_ld_wait(v);
     float f[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
@@ -1242,9 +1282,32 @@ int launch_igemm_tma(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CU
                      int occ, cudaStream_t st) {
   int grid = g_sm_count * occ;
   if (grid > g.total_tiles) grid = g.total_tiles;
-  igemm_tma_kernel<BLOCK_N, A_MODE><<<grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
+  igemm_tma_kernel<BLOCK_N, A_MODE, 1><<<grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+// CTA pairs (clusters of 2): tmW_half has a box of BLOCK_N / 2 weight rows; total_tiles is even
+template <int BLOCK_N>
+int launch_igemm_tma_pair(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW_half,
+                          const TileGeom& g, int occ, cudaStream_t st) {
+  int pairs = (g_sm_count / 2) * occ;
+  if (pairs > g.total_tiles / 2) pairs = g.total_tiles / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(TMA_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg<BLOCK_N>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMDYN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tma_kernel<BLOCK_N, 0, 2>, *d, tmA, tmW_half, g));
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return MMDYN_OK;
 }
 
@@ -1328,13 +1391,13 @@ int igemm_init() {
   OCC(4, igemm_kernel<256>, Cfg<256>::SMEM_BYTES);
 #undef OCC
 #define SET_TMA(I, BN)                                                                                        \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0>,      \
+  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0, 1>,      \
                                                                 TMA_THREADS, Cfg<BN>::SMEM_BYTES));          \
   if (g_tma_occ[I] < 1) g_tma_occ[I] = 1
   SET_TMA(0, 16);
@@ -1343,6 +1406,10 @@ int igemm_init() {
   SET_TMA(3, 128);
   SET_TMA(4, 256);
 #undef SET_TMA
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<128, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<128>::SMEM_BYTES));
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<256, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg<256>::SMEM_BYTES));
 #define SET_WG(CN)                                                                                            \
   MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<CN>::SMEM_BYTES));                                               \
@@ -1513,6 +1580,28 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     MMDYN_REQUIRE(d->out_mode != 5 || (g.bn == 1 && !g.pixel_major),
                   "igemm: out_mode 5 needs tiles that lie within one image (OXv=%d P=%d)", d->OXv, d->P);
     const int occ = g_tma_occ[occ_idx];
+    // CTA pairs (cta_group::2) for the wide layers: tiles 2q / 2q+1 must share their weight tile (even
+    // m-tile count) and, in pixel-major mode, their virtual pixel (same live taps)
+    // OPT-IN experiment (MMDYN_IGEMM_PAIRS=1): bit-identical to the single-CTA path on every layer, but not
+    // faster (the N >= 128 layers are bound by pipeline depth / operand latency, not by shared-memory
+    // bandwidth) and it can DEADLOCK when two pairs share a TPC next to single-CTA tcgen05 kernels of
+    // another stream (the paired TMEM allocation is not atomic across the two SMs) — see DESIGN.md §11.
+    static const bool no_pairs = getenv("MMDYN_IGEMM_PAIRS") == nullptr;
+    if (!no_pairs && a_mode == 0 && d->block_n >= 128 && (g.m_tiles % 2) == 0 &&
+        (!g.pixel_major || (g.img_blocks % 2) == 0) && g.total_tiles >= 2 &&
+        (d->out_mode == 0 || d->out_mode == 1 || d->out_mode == 2 || d->out_mode == 4)) {
+      CUtensorMap tmh;
+      const cuuint32_t hbox[2] = {64, static_cast<cuuint32_t>(d->block_n / 2)};
+      const CUresult hr = enc(&tmh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->W), gdim, gstr, hbox, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (hr != CUDA_SUCCESS) {
+        set_last_error("igemm: cuTensorMapEncodeTiled(W half) failed with CUresult %d", static_cast<int>(hr));
+        return MMDYN_ERR_CUDA;
+      }
+      return d->block_n == 128 ? launch_igemm_tma_pair<128>(d, tmA, tmh, g, occ, st)
+                               : launch_igemm_tma_pair<256>(d, tmA, tmh, g, occ, st);
+    }
     switch (d->block_n) {
       case 16: return dispatch_amode<16>(a_mode, d, tmA, tm, g, occ, st);
       case 32: return dispatch_amode<32>(a_mode, d, tmA, tm, g, occ, st);

@@ -627,7 +627,9 @@ def test_full_size_step_equals_oracle_on_the_replicated_base_batch(B):
     # tile to tile (1e-7), and behind that a few fp16 roundings of the decoder chain flip by one ulp.
     for t in (mu_d, lv_d):
         blocks = t.view(t.shape[0], R, B0, -1)
-        assert nrel(blocks[:, R - 1], blocks[:, 0]) < 1e-5 and nrel(blocks[:, R // 2], blocks[:, 0]) < 1e-5
+        # (the fp16 copy of the fc feature that feeds the heads flips a rounding here and there: measured
+        #  5e-6 .. 1.1e-5 norm-wise from run to run, bound 1e-4)
+        assert nrel(blocks[:, R - 1], blocks[:, 0]) < 1e-4 and nrel(blocks[:, R // 2], blocks[:, 0]) < 1e-4
     for a, b in zip(out_d["recon_x"], out_o["recon_x"]):
         a = a.reshape(R, B0, -1)
         assert nrel(a[0], b.reshape(B0, -1)) < 3e-3
