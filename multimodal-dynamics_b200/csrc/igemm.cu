@@ -657,6 +657,9 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       // one 16-column chunk of this thread's accumulator row -> global memory
       auto emit = [&](const uint32_t (&v)[16], const int c0) {
         if (out_off < 0) return;
+#ifdef MMDYN_EXP_NOSTORE  // timing experiment only: how much of the kernel are the fp16 epilogue stores?
+        if (d.out_mode == 0 || d.out_mode == 4) return;
+#endif
         float f[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) f[q] = n_live > 0 ? __uint_as_float(v[q]) : 0.0f;

@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmdyn_b200.so")
+# MMDYN_B200_LIB: load another build of the same ABI (kernel experiments); default = the in-tree library
+LIB_PATH = os.environ.get("MMDYN_B200_LIB") or os.path.join(_HERE, "libmmdyn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MAX_TAPS = 16
