@@ -157,6 +157,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) on stdout: keep stdout for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     pk = peaks()
@@ -233,22 +235,31 @@ def run_b200(args):
         opt.step()
         return l
 
-    loss_host = torch.zeros(1).pin_memory()
-    # e2e: the host->device copy of step i+1's pinned batch runs on a copy stream into one of two
-    # device staging sets while step i computes; the step then moves staging -> the graph's static
-    # inputs (device-to-device) and reads the loss back.  All of it is inside the timed region.
+    # e2e: every step's batch comes from pinned HOST memory and its loss goes back to the host, all inside
+    # the timed region.  Two sets of static device inputs (and, in graph mode, two captures of the same
+    # step reading one set each) alternate: the host->device copy of step i+1 lands directly in the set
+    # step i does not use, on a copy stream, while step i computes (no staging copy); the loss of step i
+    # is copied to a pinned slot asynchronously and read on the host while step i+1 runs.
     copy_stream = torch.cuda.Stream()
-    staging = [[torch.empty_like(a, device=dev) for a in host_batches[0][0] + host_batches[0][1]] for _ in range(2)]
+    gsteps = [gstep, None]
+    if gstep is not None:
+        gsteps[1] = engine.GraphedTrainStep(eng, opt, dev_batches[1][0], dev_batches[1][1], klw,
+                                            split_optimizer=world > 1, grad_sync=gstep.sync)
+        in_sets = [g_.x + g_.t for g_ in gsteps]
+    else:
+        in_sets = [[torch.empty_like(a, device=dev) for a in host_batches[0][0] + host_batches[0][1]] for _ in range(2)]
     staged_evt = [torch.cuda.Event(), torch.cuda.Event()]
     consumed_evt = [torch.cuda.Event(), torch.cuda.Event()]
-    e2e_state = {"primed": False}
+    loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"primed": False, "pending": None, "last": float("nan")}
 
     def stage(i):
         x, t = host_batches[i % 3]
         slot = i % 2
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed_evt[slot])
-            for dst, src in zip(staging[slot], x + t):
+            copy_stream.wait_event(consumed_evt[slot])  # the step that last read this set has finished
+            for dst, src in zip(in_sets[slot], x + t):
                 dst.copy_(src, non_blocking=True)
             staged_evt[slot].record(copy_stream)
 
@@ -262,25 +273,29 @@ def run_b200(args):
         stage(i + 1)  # prefetch the next batch while this step runs
         cur = torch.cuda.current_stream()
         cur.wait_event(staged_evt[slot])
-        xs, ts = staging[slot][:3], staging[slot][3:]
         if gstep is not None:
-            gstep.load(xs, ts)
-            consumed_evt[slot].record(cur)
-            gstep.run()
+            g_ = gsteps[slot]
+            g_.run()
             if world > 1 and not in_graph_sync:
                 sync_grads()
-                gstep.apply()
-            l = gstep.loss
+                g_.apply()
+            l = g_.loss
         else:
+            xs, ts = in_sets[slot][:3], in_sets[slot][3:]
             opt.zero_grad()
             _, l = eng.evaluate(xs, ts, klw, need_grad=True, autograd=False, want_outputs=False)
             eng.backward()
-            consumed_evt[slot].record(cur)
             sync_grads()
             opt.step()
-        loss_host.copy_(l.reshape(1), non_blocking=True)  # the step's result comes back to the host
-        cur.synchronize()
-        return float(loss_host[0])
+        consumed_evt[slot].record(cur)
+        loss_host[slot].copy_(l.reshape(1), non_blocking=True)  # the step's result goes back to the host ...
+        loss_evt[slot].record(cur)
+        if e2e_state["pending"] is not None:                     # ... and is read one step later, off the critical path
+            ps = e2e_state["pending"]
+            loss_evt[ps].synchronize()
+            e2e_state["last"] = float(loss_host[ps][0])
+        e2e_state["pending"] = slot
+        return e2e_state["last"]
 
     def timed(fn, n):
         if world > 1:
