@@ -649,3 +649,58 @@ def test_full_size_step_equals_oracle_on_the_replicated_base_batch(B):
     for k in sd_o:
         if k.endswith("running_mean") and "encoder" in k:
             assert nrel(sdd[k], sd_o[k]) < 3e-3, k
+
+
+@pytest.mark.parametrize("kind", ["vae_tactile", "mvae_masked"])
+def test_full_size_single_modality_and_masked_steps_equal_oracle_on_the_base_batch(kind):
+    """Replication invariance (see above) for the other two BASELINE.json workloads at full size:
+    configs[1] cnn-vae --input-type tactile (one pass, no prior expert) at batch 4096, and the
+    --mask-loss cnn-mvae step without the pose expert (3 passes, mask multiplies logits and targets,
+    problems.py:408-411, 445-447) at batch 2048."""
+    from mmdyn_b200 import engine
+    B0 = 16
+    klw = 0.02
+    if kind == "vae_tactile":
+        B, passes = 4096, [(True, False, False)]
+        model, sd = make("cnn-vae", seed=8)
+    else:
+        B, passes = 2048, orc.MVAE_PASSES_NOPOSE
+        model, sd = make("cnn-mvae", False, seed=8)
+    R = B // B0
+    d = batch(B0, seed=15)
+    gm = torch.Generator().manual_seed(3)
+    mask = (torch.rand(B0, 3, 64, 64, generator=gm) > 0.5).float()
+    noises = oracle_noises(passes, B0, 33)
+    pkeys = [k for k, _ in model.named_parameters()]
+    sd_o = copy.deepcopy(sd)
+    for k in pkeys:
+        sd_o[k].requires_grad_(True)
+    rep = lambda t: t.repeat(R, *([1] * (t.dim() - 1))).to(DEV)
+    if kind == "vae_tactile":
+        mk, _, eps = noises[0]
+        out_o, loss_o = orc.evaluate_vae(sd_o, d["t"], d["tt"], klw, (mk, eps), input_type="tactile")
+        eng = engine.StepEngine(model, "vae", noise_src=_ReplayNoise(noises, passes, R))
+        out_d, loss_d = eng.evaluate(rep(d["t"]), rep(d["tt"]), klw)
+        rec_d, rec_o = [out_d["recon_x"]], [out_o["recon_x"]]
+    else:
+        out_o, loss_o, _ = orc.evaluate_mvae(sd_o, [d["v"], d["t"]], [d["tv"], d["tt"]], klw, 1000.0, False, noises,
+                                             loss_mask=mask)
+        eng = engine.StepEngine(model, "mvae", noise_src=_ReplayNoise(noises, passes, R))
+        out_d, loss_d = eng.evaluate([rep(d["v"]), rep(d["t"])], [rep(d["tv"]), rep(d["tt"])], klw, loss_mask=rep(mask))
+        rec_d, rec_o = out_d["recon_x"], out_o["recon_x"]
+    loss_o.backward()
+    loss_d.backward()
+    torch.cuda.synchronize()
+    assert abs(loss_d.item() - loss_o.item()) / loss_o.item() < 1e-4, (loss_d.item(), loss_o.item())
+    assert nrel(out_d["means"][:B0], out_o["means"]) < 3e-3 and nrel(out_d["log_var"][:B0], out_o["log_var"]) < 3e-3
+    for a, b in zip(rec_d, rec_o):
+        a = a.reshape(R, B0, -1)
+        assert nrel(a[0], b.reshape(B0, -1)) < 3e-3
+        assert nrel(a[R - 1], a[0]) < 1e-3 and nrel(a[R // 3], a[0]) < 1e-3
+    gerr = {k: nrel(p.grad, sd_o[k].grad) for k, p in model.named_parameters()}
+    print(kind, "worst gradient errors:", sorted(gerr.items(), key=lambda kv: -kv[1])[:3])
+    for k, v in gerr.items():
+        assert v < 1e-2, (k, v)
+    flat_o = torch.cat([sd_o[k].grad.reshape(-1) for k in pkeys])
+    flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    assert nrel(flat_d, flat_o) < 3e-3, nrel(flat_d, flat_o)
