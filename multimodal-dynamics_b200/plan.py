@@ -17,10 +17,14 @@ fall outside the 5x5 map are skipped instead of multiplied by zeros.
 from dataclasses import dataclass, field
 from typing import List, Optional
 
+import os
+
 import numpy as np
 
 MAX_TAPS = 16
-MERGE_PHASES = True  # run the 4 sub-pixel phases of stride-2 (de)convs as one GEMM (see _merged_geom)
+# run the 4 sub-pixel phases of stride-2 (de)convs as one GEMM (see _merged_geom); MMDYN_MERGE_PHASES=0
+# keeps them as 4 phase GEMMs of 4 taps each (no zero-weight MMAs, 16 operand boxes instead of 9)
+MERGE_PHASES = os.environ.get("MMDYN_MERGE_PHASES", "1") != "0"
 
 
 @dataclass
