@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import lib as _lib
-from .lib import IgemmDesc, WgradDesc, MAX_GROUPS, MAX_PHASES, MAX_TAPS, check
+from .lib import IgemmDesc, WgradDesc, MAX_GROUPS, check
 
 
 def _ptr(t):

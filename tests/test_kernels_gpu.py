@@ -5,9 +5,7 @@ Tolerances: the tcgen05 kernels take fp16 operands (10-bit mantissa, TF32-equiva
 accumulate in fp32.  References are computed in fp64 from the *same fp16-rounded operands*, so
 the only differences are accumulation order and the output rounding: rel 1e-3 of the output
 scale for fp16 outputs, 1e-5 for fp32 outputs."""
-import math
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

@@ -1,7 +1,6 @@
 """Pins the oracle (oracle/mmdyn_oracle.py) to the golden fixtures generated from the live
 reference (tests/golden/make_golden.py), and the host-side index logic (parse_input, KL annealing)
 of the product mirror to the same fixtures, bit-exactly.  CPU only."""
-import copy
 import glob
 import os
 
