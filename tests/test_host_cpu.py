@@ -134,3 +134,71 @@ def test_gradsync_two_gloo_ranks():
     out = mgr.dict()
     mp.spawn(_ddp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_synthetic_dataset_with_shock_field_and_parse_input():
+    """`--dataset-path synthetic:N:L:3` (the stand-in for exp 3): 5th data field = one shock force per
+    sequence, `SeqModeling.parse_input` picks the first frame's (problems.py:634-673), `_set_condition_dim`
+    finds its width the way the reference does (problems.py:676-681)."""
+    from mmdyn_b200.pytorch.problems import problems
+    from mmdyn_b200.pytorch.utils.datasets import dataset_setup
+    d = dataset_setup("synthetic:6:4:3", "seq_modeling", batchsize=2, shuffle=False)
+    assert d["seq_length"] == 4 and len(d["train_dataset"].data[0][0][4]) == 3
+    data, target = next(iter(d["train_loader"]))
+    assert len(data) == 5 and tuple(data[4].shape) == (8, 3) and tuple(data[0].shape) == (8, 3, 64, 64)
+    assert torch.equal(data[4][0], data[4][3]) and not torch.equal(data[4][0], data[4][4])  # per sequence
+    pr = object.__new__(problems.SeqModeling)
+    pr.parameters = {"input_type": "visuotactile"}
+    pr._seq_length, pr._device = 4, torch.device("cpu")
+    pr.train_dataset = d["train_dataset"]
+    xi, ti = pr.parse_input(data, target)
+    assert tuple(xi["shock"].shape) == (2, 3) and torch.equal(xi["shock"], data[4][::4])
+    pr._set_condition_dim()
+    assert pr._condition_dim == 3 and pr._categorical_conditions is False
+    # without the field: no shock, condition_dim 0
+    d0 = dataset_setup("synthetic:6:4", "seq_modeling", batchsize=2, shuffle=False)
+    data0, target0 = next(iter(d0["train_loader"]))
+    xi0, _ = pr.parse_input(data0, target0)
+    assert len(data0) == 4 and xi0["shock"] is None
+    pr.train_dataset = d0["train_dataset"]
+    pr._set_condition_dim()
+    assert pr._condition_dim == 0
+
+
+def test_bench_clock_sampler_survives_without_a_gpu():
+    """bench.py's clock sampler must never take the bench down: without NVML / nvidia-smi it reports
+    'unavailable' instead of raising."""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.3)
+    s.stop_flag = True
+    s.join(timeout=10)
+    out = s.summary()
+    assert "sm_mhz" in out and "reasons" in out
+    cfg = bench.workload_config(type("A", (), {"gpus": 2})(), 1024)
+    assert cfg["global_batch"] == 2048 and cfg["parallelism"] == "dp2" and "workload" in cfg
+
+
+def test_plan_phase_merging_knob(monkeypatch):
+    """MMDYN_MERGE_PHASES=0 keeps the 4 sub-pixel phases of the stride-2 layers as separate 4-tap GEMMs;
+    both forms index the same weights (every arena element appears in both packings)."""
+    import importlib
+    from mmdyn_b200 import plan
+    merged = plan.deconv_s2_plan("deconv2", 1000, 128, 64, 8)
+    monkeypatch.setenv("MMDYN_MERGE_PHASES", "0")
+    plan0 = importlib.reload(plan)
+    try:
+        split = plan0.deconv_s2_plan("deconv2", 1000, 128, 64, 8)
+        assert merged.fwd.n_phases == 1 and merged.fwd.ntaps == 9 and merged.fwd.N == 4 * 64
+        assert split.fwd.n_phases == 4 and split.fwd.ntaps == 4 and split.fwd.N == 64
+        a = set(merged.idx_fwd[merged.idx_fwd >= 0].tolist())
+        b = set(split.idx_fwd[split.idx_fwd >= 0].tolist())
+        assert a == b and len(a) == 128 * 64 * 16
+    finally:
+        monkeypatch.delenv("MMDYN_MERGE_PHASES")
+        importlib.reload(plan)
