@@ -43,6 +43,24 @@ def shard_rows(n_rows, world, rank, seq_length=1):
     return start * seq_length, stop * seq_length
 
 
+def shard_batch(obj, world, rank, seq_length=1):
+    """Rows [shard_rows(...)] of every tensor in a parsed batch (tensor / list / tuple / dict, None kept).
+
+    Use it AFTER `parse_input` ran on the whole step batch: DynModeling.parse_input builds its targets
+    with a roll over dim 0 (problems.py:785-798), so the last row of a shard needs the first row of the
+    next shard (and the pose target of the very last row wraps around to row 0, a quirk of :798 that is
+    kept).  Parsing globally on the host and sharding the parsed rows gives every rank exactly the rows
+    of the single-process step; parsing each shard locally would change one target row per rank."""
+    if obj is None:
+        return None
+    if isinstance(obj, dict):
+        return {k: shard_batch(v, world, rank, seq_length) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(shard_batch(v, world, rank, seq_length) for v in obj)
+    a, b = shard_rows(obj.shape[0], world, rank, seq_length)
+    return obj[a:b]
+
+
 class GradSync:
     """Bucketed, overlapped all-reduce of a flat gradient tensor.  Works on any device / backend
     (the CPU + gloo combination is what the host-logic tests use)."""

@@ -202,3 +202,38 @@ def test_plan_phase_merging_knob(monkeypatch):
     finally:
         monkeypatch.delenv("MMDYN_MERGE_PHASES")
         importlib.reload(plan)
+
+
+def test_dyn_modeling_is_parsed_globally_then_sharded_by_whole_sequences():
+    """DynModeling.parse_input rolls the targets over dim 0 (problems.py:785-798), so a
+    shard's last row needs the next shard's first row (and the very last pose target wraps to row 0).
+    parallel.shard_batch slices the globally parsed batch; the shards concatenate back to the
+    single-process batch, whereas parsing each shard locally changes exactly one pose-target row per rank."""
+    from mmdyn_b200 import parallel
+    from mmdyn_b200.pytorch.problems import problems
+    S, L, world = 4, 5, 2
+    g = torch.Generator().manual_seed(3)
+    n = S * L
+    data = [torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 7, generator=g),
+            torch.ones(n, 2)]
+    target = [torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 3, 4, 4, generator=g), torch.rand(n, 7, generator=g),
+              (torch.rand(n, 3, 4, 4, generator=g) > 0.5).float()]
+    pr = object.__new__(problems.DynModeling)
+    pr.parameters = {"input_type": "visuotactile"}
+    pr._seq_length, pr._device = L, torch.device("cpu")
+    xi, ti = pr.parse_input([t.clone() for t in data], [t.clone() for t in target])
+    parts = [parallel.shard_batch((xi, ti), world, r, L) for r in range(world)]
+    for r, (xs, ts) in enumerate(parts):
+        a, b = parallel.shard_rows(n, world, r, L)
+        assert (a, b) == (r * 10, r * 10 + 10) and xs["model_input"][0].shape[0] == 10
+        assert torch.equal(xs["model_input"][1], xi["model_input"][1][a:b])
+        assert torch.equal(ts["target_object_pose"][0], ti["target_object_pose"][0][a:b])
+    cat = torch.cat([p[1]["target_object_pose"][0] for p in parts])
+    assert torch.equal(cat, ti["target_object_pose"][0])
+    # the alternative (each rank parses its own rows) differs in the last pose-target row of every shard
+    for r in range(world):
+        a, b = parallel.shard_rows(n, world, r, L)
+        _, tl = pr.parse_input([t[a:b].clone() for t in data], [t[a:b].clone() for t in target])
+        diff = (tl["target_object_pose"][0] != ti["target_object_pose"][0][a:b]).any(dim=1)
+        assert diff.nonzero().flatten().tolist() == [b - a - 1]
+        assert torch.equal(tl["target_output"][0], ti["target_output"][0][a:b])  # image targets stay local
