@@ -232,6 +232,17 @@ def mvae_elbo_loss(recons, targets, mu, lv, kl_weight, pose_multiplier, loss_mas
     return (err + kl_weight * kl_divergence(mu, lv)) / B
 
 
+def elbo_per_sample(recon_x, x, mu, lv, kl_weight, loss_mask=None):
+    """Reconstruction._elbo_loss with reduce=False (problems.py:408-417): element-wise BCE summed per
+    sample; the KL term is the batch TOTAL added to every sample (reference behaviour)."""
+    r = recon_x.view(x.size())
+    if loss_mask is not None:
+        bce = F.binary_cross_entropy_with_logits(r * loss_mask, x * loss_mask, reduction="none")
+    else:
+        bce = F.binary_cross_entropy_with_logits(r, x, reduction="none")
+    return bce.sum((1, 2, 3)) + kl_weight * kl_divergence(mu, lv)
+
+
 def mvae_elbo_per_sample(recons, targets, mu, lv, kl_weight, pose_multiplier, loss_mask=None):
     """Reconstruction._mvae_elbo_loss with reduce=False (problems.py:445-456): element-wise losses summed
     per sample; the KL term stays the batch TOTAL and is added to every sample (reference behaviour)."""

@@ -162,6 +162,36 @@ def golden_regression(problems, setup_model, name, B, cond_dim=0):
     print(name, "loss", out["loss"], "perf", out["perf_measure"])
 
 
+def golden_losses(problems):
+    """Reconstruction._elbo_loss / _mvae_elbo_loss called directly (problems.py:401-458) on seeded tensors:
+    the scalar training form (reduce=None), the per-sample scoring form (reduce=False) and the --mask-loss
+    variants.  No model involved; pins oracle.elbo_loss / mvae_elbo_loss / *_per_sample."""
+    import warnings
+    pr = object.__new__(problems.Reconstruction)
+    pr._kl_weight, pr._pose_multiplier = 0.3, 1000.0
+    g = torch.Generator().manual_seed(11)
+    B = 5
+    rv, rt = torch.randn(B, 3, 64, 64, generator=g), torch.randn(B, 3, 64, 64, generator=g)
+    tv, tt = torch.rand(B, 3, 64, 64, generator=g), torch.rand(B, 3, 64, 64, generator=g)
+    rp, tp = torch.rand(B, 7, generator=g), torch.rand(B, 7, generator=g)
+    mu, lv = torch.randn(B, 256, generator=g), 0.3 * torch.randn(B, 256, generator=g)
+    mask = (torch.rand(B, 3, 64, 64, generator=g) > 0.5).float()
+    out = {"seed": 11, "B": B, "kl_weight": 0.3, "pose_multiplier": 1000.0}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # the reference passes the deprecated `reduce=` argument
+        out["elbo"] = pr._elbo_loss(rv, tv, mu, lv)
+        out["elbo_masked"] = pr._elbo_loss(rv, tv, mu, lv, loss_mask=mask)
+        out["elbo_ps"] = pr._elbo_loss(rv, tv, mu, lv, reduce=False)
+        out["elbo_ps_masked"] = pr._elbo_loss(rv, tv, mu, lv, loss_mask=mask, reduce=False)
+        out["mvae"] = pr._mvae_elbo_loss([rv, rt, rp], [tv, tt, tp], mu, lv)
+        out["mvae_masked"] = pr._mvae_elbo_loss([rv, rt], [tv, tt], mu, lv, loss_mask=mask)
+        out["mvae_ps"] = pr._mvae_elbo_loss([rv, rt, rp], [tv, tt, tp], mu, lv, reduce=False)
+        out["mvae_ps_masked"] = pr._mvae_elbo_loss([rv, rt], [tv, tt], mu, lv, loss_mask=mask, reduce=False)
+    torch.save({k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in out.items()},
+               os.path.join(OUT, "losses.pt"))
+    print("loss fixtures written:", {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+
 def golden_parse_input(problems):
     """Integer / index path: SeqModeling.parse_input and DynModeling.parse_input on a seq-collated
     batch of S sequences x L frames (small images: the indexing does not depend on H, W)."""
@@ -201,6 +231,9 @@ if __name__ == "__main__":
         golden_case(problems, setup_model, "cvae_visual_b4", "cnn-vae", "visual", False, 4, cond_dim=3)
         golden_case(problems, setup_model, "cmvae_pose_b3", "cnn-mvae", "visuotactile", True, 3, cond_dim=3)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":
+        golden_losses(problems)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "regression":  # only the Regressor fixtures
         golden_regression(problems, setup_model, "regressor_b4", 4)
         golden_regression(problems, setup_model, "regressor_cond_b4", 4, cond_dim=3)
@@ -214,5 +247,6 @@ if __name__ == "__main__":
     golden_case(problems, setup_model, "cmvae_pose_b3", "cnn-mvae", "visuotactile", True, 3, cond_dim=3)
     golden_regression(problems, setup_model, "regressor_b4", 4)
     golden_regression(problems, setup_model, "regressor_cond_b4", 4, cond_dim=3)
+    golden_losses(problems)
     golden_parse_input(problems)
     golden_anneal(problems)

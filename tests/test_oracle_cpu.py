@@ -218,3 +218,30 @@ def test_regression_parse_input_is_bit_exact(it):
     # a batch without the shock field (exp 1 / 2 datasets): shock is None on every side
     xi, _ = pr.parse_input([t.clone() for t in g["data"][:4]], [t.clone() for t in g["target"]])
     assert xi["shock"] is None
+
+
+def test_oracle_loss_functions_match_reference_incl_per_sample_and_masked():
+    """oracle.elbo_loss / mvae_elbo_loss / *_per_sample against Reconstruction._elbo_loss / _mvae_elbo_loss
+    of the live reference (problems.py:401-458): scalar and reduce=False forms, with and without a mask."""
+    g = torch.load(os.path.join(GOLD, "losses.pt"), weights_only=False)
+    gen = torch.Generator().manual_seed(g["seed"])
+    B = g["B"]
+    rv, rt = torch.randn(B, 3, 64, 64, generator=gen), torch.randn(B, 3, 64, 64, generator=gen)
+    tv, tt = torch.rand(B, 3, 64, 64, generator=gen), torch.rand(B, 3, 64, 64, generator=gen)
+    rp, tp = torch.rand(B, 7, generator=gen), torch.rand(B, 7, generator=gen)
+    mu, lv = torch.randn(B, 256, generator=gen), 0.3 * torch.randn(B, 256, generator=gen)
+    mask = (torch.rand(B, 3, 64, 64, generator=gen) > 0.5).float()
+    klw, pm = g["kl_weight"], g["pose_multiplier"]
+    got = {
+        "elbo": orc.elbo_loss(rv, tv, mu, lv, klw),
+        "elbo_masked": orc.elbo_loss(rv, tv, mu, lv, klw, mask),
+        "elbo_ps": orc.elbo_per_sample(rv, tv, mu, lv, klw),
+        "elbo_ps_masked": orc.elbo_per_sample(rv, tv, mu, lv, klw, mask),
+        "mvae": orc.mvae_elbo_loss([rv, rt, rp], [tv, tt, tp], mu, lv, klw, pm),
+        "mvae_masked": orc.mvae_elbo_loss([rv, rt], [tv, tt], mu, lv, klw, pm, mask),
+        "mvae_ps": orc.mvae_elbo_per_sample([rv, rt, rp], [tv, tt, tp], mu, lv, klw, pm),
+        "mvae_ps_masked": orc.mvae_elbo_per_sample([rv, rt], [tv, tt], mu, lv, klw, pm, mask),
+    }
+    for k, v in got.items():
+        assert v.shape == g[k].shape, k
+        assert torch.allclose(v, g[k], rtol=2e-6, atol=0), (k, v, g[k])
