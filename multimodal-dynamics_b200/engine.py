@@ -1147,8 +1147,14 @@ class StepEngine:
         if st is None or st["token"] != token:
             raise RuntimeError("mmdyn_b200: backward() called for a step whose buffers were overwritten by a "
                                "later evaluate(); call loss.backward() before evaluating the next batch")
-        if os.environ.get("MMDYN_CHECK_GRAD_OUT") and grad_out is not None:
-            assert abs(float(grad_out) - 1.0) < 1e-6, "the fused backward assumes d(loss) = 1"
+        # autograd route only (loss.backward()): the hand-written backward is the gradient of `loss` itself,
+        # so an upstream gradient other than 1 (e.g. (2 * loss).backward()) must fail loudly instead of
+        # producing unscaled gradients.  One 4-byte read-back per eager step; the graph path never comes here.
+        if grad_out is not None and os.environ.get("MMDYN_NO_CHECK_GRAD_OUT") is None:
+            if abs(float(grad_out) - 1.0) > 1e-6:
+                raise RuntimeError("mmdyn_b200: the fused step's backward is d(loss)/d(params) for an upstream "
+                                   f"gradient of 1, got {float(grad_out)}; scale the learning rate or the "
+                                   "gradients (optimizer.grad_prescale) instead of the loss")
         arena, ex, ws, B, gs = st["arena"], st["ex"], self.ws, st["B"], st["gs"]
         arena.attach_grads()
         unscale = 1.0 / gs

@@ -704,3 +704,18 @@ def test_full_size_single_modality_and_masked_steps_equal_oracle_on_the_base_bat
     flat_o = torch.cat([sd_o[k].grad.reshape(-1) for k in pkeys])
     flat_d = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
     assert nrel(flat_d, flat_o) < 3e-3, nrel(flat_d, flat_o)
+
+
+def test_scaled_loss_backward_fails_loudly():
+    """The fused backward is the gradient of `loss` for an upstream gradient of 1: (2 * loss).backward() must
+    raise instead of silently producing unscaled gradients."""
+    from mmdyn_b200 import engine, noise
+    model, _ = make("cnn-vae", seed=1)
+    d = batch(4, seed=2)
+    eng = engine.StepEngine(model, "vae", noise_src=noise.HostNoise(torch.Generator().manual_seed(1)))
+    _, loss = eng.evaluate(d["v"].to(DEV), d["tv"].to(DEV), 0.02)
+    with pytest.raises(RuntimeError, match="upstream"):
+        (2.0 * loss).backward()
+    _, loss = eng.evaluate(d["v"].to(DEV), d["tv"].to(DEV), 0.02)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
