@@ -125,3 +125,25 @@ def test_heuristics():
     assert plan.choose_ksplit(lp.fwd, 128 * 200) == 1
     c2 = plan.conv_s2_plan("c2", 0, 32, 64, 32)
     assert plan.choose_row_splits(c2.wgrad, 128) >= 1
+
+
+def test_linear_plan_with_condition_columns_partitions_the_weight():
+    """CVAE (vae.py:196, 257): Linear(K + cd, N) weights keep the reference's shape; the tensor-core packing
+    indexes columns 0..K-1 at row pitch K + cd, the rank-cd fp32 kernels own the remaining columns.  Together
+    they touch every weight element exactly once."""
+    import numpy as np
+    from mmdyn_b200 import plan
+    K, N, cd, w_off, b_off = 512, 256, 3, 1000, 900000
+    lp = plan.linear_plan("heads", [w_off, w_off + N * (K + cd)], [b_off, b_off + N], K, [N, N], ld=K + cd)
+    idx = lp.idx_fwd
+    assert idx.shape == (2 * N, K) and lp.fwd.N == 2 * N and lp.fwd.K == K
+    rows = (idx - w_off) // (K + cd)
+    cols = (idx - w_off) % (K + cd)
+    assert (cols < K).all() and (rows == np.arange(2 * N)[:, None]).all()
+    packed = set(idx.reshape(-1).tolist())
+    cond = {w_off + n * (K + cd) + K + j for n in range(2 * N) for j in range(cd)}
+    assert not (packed & cond) and len(packed | cond) == 2 * N * (K + cd)
+    # the decoder's upsample Linear(256 + cd, 6400) with the NHWC output permutation
+    up = plan.linear_plan("up", [0], [10 ** 7], 256, [6400], n_perm=plan.nhwc_perm(256, 5, 5), ld=256 + cd)
+    assert up.idx_fwd.shape == (6400, 256) and (up.idx_fwd % (256 + cd) < 256).all()
+    assert sorted((up.idx_fwd[:, 0] // (256 + cd)).tolist()) == list(range(6400))  # a permutation of the rows
