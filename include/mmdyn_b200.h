@@ -315,6 +315,16 @@ int mmdyn_adam_flat_devstep(float* p, const float* g, float* m, float* v, long l
 /* SGD with momentum (problems.py:132-136): buf = mom*buf + (g + wd*p); p -= lr*buf */
 int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n, float lr, float momentum,
                    float weight_decay, int first_step, float gscale, void* stream);
+/* Guarded forms (what optimizer.step() of problems.py:155 runs here): a gradient entry that is inf / NaN
+ * (fp16 overflow in the backward, a poisoned input) leaves its parameter and moments untouched and ORs 1
+ * into *nonfinite_flag (device, may be NULL) — read on the host together with the loss, so a step never
+ * trains on a non-finite number silently. */
+int mmdyn_adam_flat_guarded(float* p, const float* g, float* m, float* v, long long n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay,
+                            const uint64_t* step_dev, float gscale, unsigned int* nonfinite_flag, void* stream);
+int mmdyn_sgd_flat_guarded(float* p, const float* g, float* buf, long long n, float lr, float momentum,
+                           float weight_decay, int first_step, float gscale, unsigned int* nonfinite_flag,
+                           void* stream);
 
 /* --- deterministic device RNG (Philox4x32-10) for eps / dropout masks --------------------------
  * replaces torch.randn (vae.py:58) and nn.Dropout's mask (vae.py:213) on the fast path */

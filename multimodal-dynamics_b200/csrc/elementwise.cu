@@ -1063,7 +1063,12 @@ logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, f
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
-            float bc1, float bc2_sqrt, float gscale, const uint64_t* __restrict__ step_dev) {
+            float bc1, float bc2_sqrt, float gscale, const uint64_t* __restrict__ step_dev,
+            unsigned int* __restrict__ nonfinite) {
+  // `nonfinite` (optional): a gradient entry that is inf / NaN (fp16 overflow somewhere in the backward,
+  // or a poisoned input) leaves its parameter and moments untouched and raises the sticky flag, which the
+  // host reads together with the loss — the step never trains on a non-finite number.
+  bool bad = false;
   if (step_dev) {  // bias corrections from the device-resident step counter
     const double t = static_cast<double>(*step_dev);
     bc1 = static_cast<float>(1.0 - pow(static_cast<double>(b1), t));
@@ -1084,6 +1089,10 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float gr = ga[q] * gscale;
+      if (!isfinite(gr)) {
+        bad = true;
+        continue;
+      }
       if (wd != 0.0f) gr = fmaf(wd, pa[q], gr);
       ma[q] = fmaf(b1, ma[q], (1.0f - b1) * gr);       // torch: m.lerp_(g, 1-b1)
       va[q] = fmaf(b2, va[q], (1.0f - b2) * gr * gr);  // v.mul_(b2).addcmul_(g, g, 1-b2)
@@ -1098,25 +1107,37 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long long i = (n4 << 2) + threadIdx.x;
     float gr = g[i] * gscale;
-    if (wd != 0.0f) gr = fmaf(wd, p[i], gr);
-    const float mm = fmaf(b1, m[i], (1.0f - b1) * gr);
-    const float vv = fmaf(b2, v[i], (1.0f - b2) * gr * gr);
-    m[i] = mm;
-    v[i] = vv;
-    p[i] -= step * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    if (!isfinite(gr)) {
+      bad = true;
+    } else {
+      if (wd != 0.0f) gr = fmaf(wd, p[i], gr);
+      const float mm = fmaf(b1, m[i], (1.0f - b1) * gr);
+      const float vv = fmaf(b2, v[i], (1.0f - b2) * gr * gr);
+      m[i] = mm;
+      v[i] = vv;
+      p[i] -= step * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    }
   }
+  if (bad && nonfinite) atomicOr(nonfinite, 1u);
 }
 
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
-           float lr, float momentum, float wd, int first_step, float gscale) {
+           float lr, float momentum, float wd, int first_step, float gscale, unsigned int* __restrict__ nonfinite) {
+  bool bad = false;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gr = fmaf(wd, p[i], g[i] * gscale);
+    const float g0 = g[i] * gscale;
+    if (!isfinite(g0)) {  // see adam_kernel: skip the entry, raise the flag
+      bad = true;
+      continue;
+    }
+    const float gr = fmaf(wd, p[i], g0);
     const float b = first_step ? gr : fmaf(momentum, buf[i], gr);
     buf[i] = b;
     p[i] -= lr * b;
   }
+  if (bad && nonfinite) atomicOr(nonfinite, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1579,7 +1600,21 @@ extern "C" int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, lon
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step_count);
   adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                         static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
-                                                        gscale, nullptr);
+                                                        gscale, nullptr, nullptr);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_adam_flat_guarded(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                       float beta1, float beta2, float eps, float weight_decay,
+                                       const uint64_t* step_dev, float gscale, unsigned int* nonfinite_flag,
+                                       void* stream) {
+  MMDYN_REQUIRE(p && g && m && v && n > 0 && step_dev, "adam_flat_devstep: bad arguments");
+  MMDYN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+                "adam_flat_devstep: arenas must be 16-byte aligned");
+  adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f,
+                                                        1.0f, gscale, step_dev, nonfinite_flag);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1587,20 +1622,20 @@ extern "C" int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, lon
 extern "C" int mmdyn_adam_flat_devstep(float* p, const float* g, float* m, float* v, long long n, float lr,
                                        float beta1, float beta2, float eps, float weight_decay,
                                        const uint64_t* step_dev, float gscale, void* stream) {
-  MMDYN_REQUIRE(p && g && m && v && n > 0 && step_dev, "adam_flat_devstep: bad arguments");
-  MMDYN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                  reinterpret_cast<uintptr_t>(v)) & 15) == 0,
-                "adam_flat_devstep: arenas must be 16-byte aligned");
-  adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f,
-                                                        1.0f, gscale, step_dev);
-  LAUNCHED();
-  return MMDYN_OK;
+  return mmdyn_adam_flat_guarded(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, gscale, nullptr, stream);
 }
 
 extern "C" int mmdyn_sgd_flat(float* p, const float* g, float* buf, long long n, float lr, float momentum,
                               float weight_decay, int first_step, float gscale, void* stream) {
+  return mmdyn_sgd_flat_guarded(p, g, buf, n, lr, momentum, weight_decay, first_step, gscale, nullptr, stream);
+}
+
+extern "C" int mmdyn_sgd_flat_guarded(float* p, const float* g, float* buf, long long n, float lr, float momentum,
+                                      float weight_decay, int first_step, float gscale, unsigned int* nonfinite_flag,
+                                      void* stream) {
   MMDYN_REQUIRE(p && g && buf && n > 0, "sgd_flat: bad arguments");
-  sgd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, first_step, gscale);
+  sgd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, first_step, gscale,
+                                                  nonfinite_flag);
   LAUNCHED();
   return MMDYN_OK;
 }

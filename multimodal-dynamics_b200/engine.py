@@ -45,13 +45,22 @@ class FreshAlloc:
 
 
 class Workspace:
-    """Persistent named buffers (fused step: stable addresses, CUDA-graph friendly)."""
+    """Persistent named buffers (fused step: stable addresses, CUDA-graph friendly).
+
+    A buffer is identified by (name, shape, dtype) and is NEVER replaced or freed once handed out: captured
+    CUDA graphs hold raw pointers into these buffers, and several graphs (one per input shape, see
+    Problem._graph_cache) as well as eager evaluations of other batch sizes share one Workspace.  A request
+    for a known name with a new shape therefore allocates a second buffer next to the first instead of
+    recycling it (the earlier graph keeps replaying into memory that is still its own).  `bufs[name]` is the
+    buffer most recently handed out under that name.  `trim()` drops everything — only legal when no
+    captured graph that used this workspace will be replayed again."""
 
     POOL_BYTES = 8 << 20
 
     def __init__(self, device):
         self.device = device
-        self.bufs = {}
+        self.bufs = {}       # name -> latest tensor
+        self._all = {}       # (name, shape, dtype) -> tensor
         self.pools = []      # fp32 chunks holding every zero="step" buffer: ONE memset per chunk and step
         self.pool_used = 0   # floats used in the last chunk
 
@@ -60,15 +69,17 @@ class Workspace:
         the step starts (BatchNorm sums, bias-gradient partials ...) — carved out of a pool that
         begin_step() clears with a single memset instead of one fill kernel per buffer."""
         shape = tuple(int(s) for s in shape)
-        t = self.bufs.get(key)
-        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+        full = (key, shape, dtype)
+        t = self._all.get(full)
+        if t is None:
             if zero == "step" and dtype == F32:
                 t = self._from_pool(shape)
             else:
                 t = torch.zeros(shape, dtype=dtype, device=self.device)
-            self.bufs[key] = t
+            self._all[full] = t
         elif zero is True:
             t.zero_()
+        self.bufs[key] = t
         return t
 
     def _from_pool(self, shape):
@@ -90,8 +101,16 @@ class Workspace:
         for p in self.pools:
             p.zero_()
 
+    def trim(self):
+        """Free every buffer (benchmark sweeps over many batch sizes).  The caller guarantees that no CUDA
+        graph captured on this workspace is replayed afterwards."""
+        self.bufs.clear()
+        self._all.clear()
+        self.pools = []
+        self.pool_used = 0
+
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+        return sum(t.numel() * t.element_size() for t in self._all.values())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -921,12 +940,14 @@ class StepEngine:
         return arena, ex
 
     def evaluate(self, x, targets, kl_weight, loss_mask=None, want_outputs=True, need_grad=None, autograd=True,
-                 condition=None):
+                 condition=None, track=True):
         """x / targets: tensor (vae) or list [visual, tactile(, pose)] (mvae), fp32, on the GPU.
         Returns (outputs, loss) like the reference; loss.backward() then fills the parameter
         gradients.  Under torch.no_grad() only the forward runs (Problem._test_epoch).
         need_grad / autograd=False: keep the backward state without an autograd node, for callers
-        that invoke backward() themselves (CUDA-graph capture of the whole step)."""
+        that invoke backward() themselves (CUDA-graph capture of the whole step).
+        track=False: BatchNorm running statistics / num_batches_tracked are left untouched (the warm-up
+        passes of a graph capture must not move model buffers)."""
         if self.kind == "vae":
             xs, ts = {"x": x}, {"x": targets}
         else:
@@ -988,7 +1009,7 @@ class StepEngine:
 
         def enc_branch(m):
             def fn():
-                enc_rec[m] = ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, True, cond)
+                enc_rec[m] = ex["enc"][self.mods[m][0]].forward(xs[m], masks[m], ws, "enc_" + m, track, cond)
             return fn
 
         def pose_enc():
@@ -1057,7 +1078,7 @@ class StepEngine:
                         lg = (jg, jg + 1)
                     fl = dict(target=ts[m], mask=loss_mask, dlogits=dl8[m], loss=scal, slots=slots, gscale=gs / B,
                               logit_groups=lg)
-                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True, fused_loss=fl, cond=cond)
+                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, track, fused_loss=fl, cond=cond)
                     return
 
                 def losses(g0, Gc, lg_rows):  # right after a group chunk's logits, while they are L2-resident
@@ -1069,7 +1090,7 @@ class StepEngine:
                                        dl8[m][g * B:(g + 1) * B] if need_grad else None, gs / B, B, 64, 64, 1)
                 dex.after_group = losses
                 try:
-                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, True, cond=cond)
+                    dec_rec[m] = dex.forward(zdec[m], G, B, ws, "dec_" + m, track, cond=cond)
                 finally:
                     dex.after_group = None
             return fn
@@ -1244,11 +1265,22 @@ class GraphedTrainStep:
         # step (a graph is re-captured whenever the KL weight changes, i.e. every epoch of the annealing
         # phase, and two stray Adam steps per capture would move the trajectory away from the reference's)
         self.opt._arena()  # moment buffers + device step counter exist before the capture
+        self.arena = get_arena(eng.model)
+        # ... and must not move model buffers either: BatchNorm running statistics stay untouched
+        # (track=False) and the device noise counter is put back, so that a run with N captures (one per
+        # annealing epoch) leaves the same state_dict / noise stream as a run with one
+        src = eng._noise()
+        ctr = getattr(src, "ctr", None)
+        ctr_saved = ctr.clone() if ctr is not None else None
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._body(False)
+                self._body(False, track=False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if ctr_saved is not None and getattr(src, "ctr", None) is not None:
+            src.ctr.copy_(ctr_saved)
+        elif ctr is None and getattr(src, "ctr", None) is not None:
+            src.ctr.zero_()  # the counter was created by the warm-up itself
         eng.always_refresh = True
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -1260,12 +1292,12 @@ class GraphedTrainStep:
                 self.opt.step()
         eng.always_refresh = False
 
-    def _body(self, with_opt):
+    def _body(self, with_opt, track=True):
         self.opt.zero_grad()
         if self.sync is not None:
             self.sync.begin()
         outputs, loss = self.eng.evaluate(self.x, self.t, self.klw, loss_mask=self.mask, need_grad=True, autograd=False,
-                                          condition=self.cond)
+                                          condition=self.cond, track=track)
         self.eng.backward()
         if self.sync is not None:
             self.sync.finish()
@@ -1291,7 +1323,13 @@ class GraphedTrainStep:
 
     def run(self):
         self.graph.replay()
+        if not self.split:
+            # the replayed optimizer rewrote the parameter arena behind Python's back: the fp16 operand
+            # copies packed at the START of this replay are one step old for any eager call that follows
+            # (Problem._test_epoch, _sample, the module-level API) -> invalidate the packer token
+            self.arena.bump()
         return self.outputs, self.loss
 
     def apply(self):
         self.graph_opt.replay()
+        self.arena.bump()

@@ -103,6 +103,8 @@ SIGNATURES = {
     "mmdyn_adam_flat": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P], _I),
     "mmdyn_adam_flat_devstep": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _F, _P], _I),
     "mmdyn_sgd_flat": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),
+    "mmdyn_adam_flat_guarded": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _F, _P, _P], _I),
+    "mmdyn_sgd_flat_guarded": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P, _P], _I),
     "mmdyn_fill_normal": ([_P, _LL, _U64, _U64, _P, _P], _I),
     "mmdyn_fill_dropout_mask": ([_P, _LL, _F, _U64, _U64, _P, _P], _I),
     "mmdyn_rng_advance": ([_P, _U64, _P], _I),

@@ -45,6 +45,16 @@ class DeviceNoise:
             self.ctr = torch.zeros(1, dtype=torch.int64, device=device)
         return self.ctr
 
+    def state_dict(self):
+        """Seed + Philox counter (checkpoint resume: the stream continues where it stopped)."""
+        return {"seed": self.seed, "counter": int(self.ctr.item()) if self.ctr is not None else 0}
+
+    @classmethod
+    def from_state_dict(cls, state, device):
+        src = cls(seed=int(state["seed"]), device=device)
+        src._counter(device).fill_(int(state["counter"]))
+        return src
+
     def dropout_mask(self, B, device, out=None):
         out = torch.empty(B, 512, device=device) if out is None else out
         ctr = self._counter(out.device)

@@ -314,16 +314,17 @@ def adam_flat(p, g, m, v, n, lr, b1, b2, eps, wd, step, gscale=1.0):
               "adam_flat")
 
 
-def adam_flat_devstep(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, gscale=1.0):
+def adam_flat_devstep(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, gscale=1.0, flag=None):
     with _Timed("adam_flat", lambda: (0.0, n * 28.0)):
-        check(_L().mmdyn_adam_flat_devstep(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, _ptr(step_dev),
-                                           gscale, _stream()), "adam_flat_devstep")
+        check(_L().mmdyn_adam_flat_guarded(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, b1, b2, eps, wd, _ptr(step_dev),
+                                           gscale, _ptr(flag) if flag is not None else None, _stream()),
+              "adam_flat_guarded")
 
 
-def sgd_flat(p, g, buf, n, lr, momentum, wd, first_step, gscale=1.0):
+def sgd_flat(p, g, buf, n, lr, momentum, wd, first_step, gscale=1.0, flag=None):
     with _Timed("sgd_flat", None):
-        check(_L().mmdyn_sgd_flat(_ptr(p), _ptr(g), _ptr(buf), n, lr, momentum, wd, int(first_step), gscale, _stream()),
-              "sgd_flat")
+        check(_L().mmdyn_sgd_flat_guarded(_ptr(p), _ptr(g), _ptr(buf), n, lr, momentum, wd, int(first_step), gscale,
+                                          _ptr(flag) if flag is not None else None, _stream()), "sgd_flat_guarded")
 
 
 def fill_normal(out, n, seed, offset, ctr=None):

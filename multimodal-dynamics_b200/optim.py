@@ -25,7 +25,29 @@ class _FlatOptimizer(torch.optim.Optimizer):
             self._step = 0
             # the step count also lives on the device so that a captured CUDA graph advances it
             self._step_dev = torch.zeros(1, dtype=torch.int64, device=arena.flat.device)
+            # sticky device-side flag: set by the update kernel when a gradient entry is inf / NaN
+            self._flag = torch.zeros(1, dtype=torch.int32, device=arena.flat.device)
         return arena
+
+    def nonfinite_flag(self):
+        """0-dim int32 device tensor: != 0 once any update since the last check_finite() met a non-finite
+        gradient entry (that entry was skipped).  Reading it is a host sync — do it where the loss is read."""
+        self._arena()
+        return self._flag[0]
+
+    def check_finite(self, loss=None):
+        """Raise FloatingPointError if a non-finite gradient entry was met since the last call (or if `loss`
+        is non-finite).  fp16 operands carry no overflow protection of their own: this is the
+        one per-step health signal, and it costs nothing until it is read."""
+        self._arena()
+        bad = int(self._flag.item()) != 0
+        if bad:
+            self._flag.zero_()
+        lv = float(loss) if loss is not None else 0.0
+        if bad or lv != lv or lv in (float("inf"), float("-inf")):
+            raise FloatingPointError(
+                "mmdyn_b200: non-finite " + ("gradient entries" if bad else "loss") + " in the training step "
+                "(fp16 overflow or a poisoned input); the affected parameter entries were NOT updated")
 
     def state_dict(self):
         """Flat-arena optimizer state (moment buffers + step count) for checkpoint resume."""
@@ -69,7 +91,7 @@ class FusedAdam(_FlatOptimizer):
         m, v = self._bufs
         ops.rng_advance(self._step_dev, 1)
         ops.adam_flat_devstep(arena.flat, arena.grad, m, v, arena.total, g["lr"], g["betas"][0], g["betas"][1],
-                              g["eps"], g["weight_decay"], self._step_dev, self.grad_prescale)
+                              g["eps"], g["weight_decay"], self._step_dev, self.grad_prescale, flag=self._flag)
         arena.bump()
 
 
@@ -88,5 +110,5 @@ class FusedSGD(_FlatOptimizer):
         self._step += 1
         # the momentum buffer starts at zero, so momentum*buf + g == g on step 1 (torch's first-step rule)
         ops.sgd_flat(arena.flat, arena.grad, self._bufs[0], arena.total, g["lr"], g["momentum"], g["weight_decay"],
-                     False, self.grad_prescale)
+                     False, self.grad_prescale, flag=self._flag)
         arena.bump()

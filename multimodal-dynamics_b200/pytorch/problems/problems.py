@@ -165,9 +165,15 @@ class Problem:
             train_loss += loss.detach()
             for k, v in outputs.get('perf_measure', {}).items():
                 perf_measure[k] = perf_measure[k] + v
-            if self._writer is not None and (batch_idx % 50 == 0 or batch_idx == n - 1):
-                self._writer.add_scalar('Loss/train_step', loss.item(), epoch * n + batch_idx)
-                progress_bar(batch_idx + 1, n, 'Loss %.3f' % loss.item())
+            if batch_idx % 50 == 0 or batch_idx == n - 1:
+                # the host reads the loss here anyway: read the optimizer's non-finite flag with it and fail
+                # loudly instead of training on inf / NaN (fp16 operands)
+                lv = loss.item()
+                if hasattr(self._optimizer, 'check_finite'):
+                    self._optimizer.check_finite(lv)
+                if self._writer is not None:
+                    self._writer.add_scalar('Loss/train_step', lv, epoch * n + batch_idx)
+                    progress_bar(batch_idx + 1, n, 'Loss %.3f' % lv)
         self._log_train_info(inputs, outputs, targets, _f(train_loss), epoch, perf_measure=perf_measure)
         return perf_measure
 
@@ -192,16 +198,24 @@ class Problem:
         a side file `<ckpt>.optim` with the fused optimizer's moments so that a resumed run continues
         the same trajectory (the reference saves no optimizer state and cannot resume)."""
         path = self._checkpoint_dir + '/epoch_' + str(epoch) + '.ckpt'
-        torch.save({'model': self._model.state_dict(), 'loss': loss, 'epoch': epoch}, path)
+        torch.save({'model': self._model.state_dict(), 'loss': float(loss), 'epoch': int(epoch)}, path)
         if hasattr(self._optimizer, 'state_dict') and isinstance(self._optimizer, fused_optim._FlatOptimizer):
-            torch.save(self._optimizer.state_dict(), path + '.optim')
+            side = self._optimizer.state_dict()
+            # device noise stream (dropout masks, eps) of the graphed step: seed + Philox counter, so that a
+            # resumed run draws the numbers the uninterrupted run would have drawn next
+            src = self._engine._noise() if self._engine is not None else None
+            if src is not None and hasattr(src, 'state_dict'):
+                side['noise'] = src.state_dict()
+            torch.save(side, path + '.optim')
         return path
 
     def load_checkpoint(self, path):
         """Resume: model weights + BatchNorm buffers from `path` (written here or by the reference),
         best loss and epoch counter; optimizer moments from `<path>.optim` when present (otherwise the
         optimizer restarts from zero moments, which is all a reference checkpoint allows)."""
-        state = torch.load(path, map_location='cpu', weights_only=False)
+        # weights_only: a checkpoint is tensors + a float + an int; never unpickle arbitrary objects from
+        # a user-supplied path (reference checkpoints, third-party files)
+        state = torch.load(path, map_location='cpu', weights_only=True)
         missing = {'model', 'loss', 'epoch'} - set(state)
         if missing:
             raise ValueError(f"{path} is not a mmdyn checkpoint: missing {sorted(missing)}")
@@ -210,7 +224,11 @@ class Problem:
         self._best_loss = _f(state['loss'])
         self._start_epoch = int(state['epoch']) + 1
         if os.path.exists(path + '.optim') and isinstance(self._optimizer, fused_optim._FlatOptimizer):
-            self._optimizer.load_state_dict(torch.load(path + '.optim', map_location='cpu', weights_only=False))
+            side = torch.load(path + '.optim', map_location='cpu', weights_only=True)
+            self._optimizer.load_state_dict(side)
+            if side.get('noise') is not None and hasattr(self, '_get_engine'):
+                from mmdyn_b200 import noise as _noise
+                self._get_engine().noise_src = _noise.DeviceNoise.from_state_dict(side['noise'], self._device)
         return state
 
     def train(self, save=True):
