@@ -237,3 +237,38 @@ def test_dyn_modeling_is_parsed_globally_then_sharded_by_whole_sequences():
         diff = (tl["target_object_pose"][0] != ti["target_object_pose"][0][a:b]).any(dim=1)
         assert diff.nonzero().flatten().tolist() == [b - a - 1]
         assert torch.equal(tl["target_output"][0], ti["target_output"][0][a:b])  # image targets stay local
+
+
+def test_workspace_never_recycles_a_buffer():
+    """Captured CUDA graphs keep raw pointers into Workspace buffers (advisor finding, round 1): a request for
+    a known name with another shape must allocate next to the old buffer, not replace it."""
+    from mmdyn_b200 import engine
+    ws = engine.Workspace(torch.device("cpu"))
+    a = ws("act", (8, 4), torch.float32)
+    s1 = ws("sums", (2, 3), torch.float32, zero="step")
+    b = ws("act", (4, 4), torch.float32)          # another batch size, same name
+    s2 = ws("sums", (1, 3), torch.float32, zero="step")
+    a2 = ws("act", (8, 4), torch.float32)
+    assert a2.data_ptr() == a.data_ptr() and b.data_ptr() != a.data_ptr()
+    assert ws("sums", (2, 3), torch.float32, zero="step").data_ptr() == s1.data_ptr() != s2.data_ptr()
+    assert ws.bufs["act"] is a2
+    s1.fill_(3.0)
+    s2.fill_(4.0)
+    ws.begin_step()                                # one memset clears every zero="step" buffer
+    assert float(s1.abs().sum()) == 0.0 and float(s2.abs().sum()) == 0.0
+    z = ws("z", (5,), torch.float32, zero=True)
+    z.fill_(1.0)
+    assert float(ws("z", (5,), torch.float32, zero=True).sum()) == 0.0
+    n = ws.nbytes()
+    ws.trim()
+    assert n > 0 and ws.nbytes() == 0 and not ws.bufs
+
+
+def test_device_noise_state_round_trip():
+    from mmdyn_b200 import noise
+    src = noise.DeviceNoise(seed=123)
+    assert src.state_dict() == {"seed": 123, "counter": 0}
+    src._counter("cpu").fill_(987654321012)
+    st = src.state_dict()
+    back = noise.DeviceNoise.from_state_dict(st, "cpu")
+    assert back.seed == 123 and int(back.ctr.item()) == 987654321012
