@@ -111,7 +111,8 @@ def test_mvae_fused_step_matches_oracle(use_pose):
     for k, v in errs.items():
         # chained activations compound the per-layer 1e-3 budget over depth (isolated layers are
         # held to 1e-3 in test_layers_in_isolation); the scalar loss averages the noise out
-        tol = 1e-4 if k == "loss" else 3e-3
+        # measured (r2 log, profiles/r2_parity_measured.txt): activations <= 1.28e-3, mu <= 1.37e-3, loss 6e-7
+        tol = 1e-5 if k == "loss" else 2e-3
         assert v < tol, (k, v, tol)
     # outputs dict: reference bindings (recon_x of the joint pass, posterior of the last pass)
     for a, b in zip(out_d["recon_x"], out_o["recon_x"]):
@@ -136,7 +137,9 @@ def test_mvae_fused_step_matches_oracle(use_pose):
     # With the pose expert the ReLU MLP decoder sits behind z: a 1e-3 perturbation of z (fp16 image
     # trunks) flips a few ReLU units of the 8-row batch and moves dz of that pass by ~2 % (measured:
     # the pose kernels themselves reproduce torch to 4e-7 on identical inputs), so the bound is 5e-2.
-    tol_t, tol_all = (5e-2, 2e-2) if use_pose else (1e-2, 3e-3)
+    # measured (r2): worst tensor 2.6e-3 without / 1.34e-2 with the pose expert; the pose figure is the ReLU-flip
+    # effect isolated row by row in tests/test_parity2_gpu.py::test_pose_gradient_error_is_explained_by_relu_flips
+    tol_t, tol_all = (4e-2, 2e-2) if use_pose else (6e-3, 3e-3)
     for k, v in gerr.items():
         assert v < tol_t, (k, v)
     flat_o = torch.cat([grads_o[k].reshape(-1) for k in pkeys])

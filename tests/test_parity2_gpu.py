@@ -158,14 +158,14 @@ def test_adam_trajectory_20_steps_b128_matches_oracle():
         _, l = eng.evaluate(x, t, (i + 1) / 50, want_outputs=False)
         l.backward()
         opt.step()
-        loss_d.append(float(l))
+        loss_d.append(float(l.detach()))
     opt.check_finite(loss_d[-1])
     errs = [abs(a - b) / abs(b) for a, b in zip(loss_d, loss_o)]
     print("Adam trajectory, B=128, loss per step (B200 | oracle | rel):")
     for i, (a, b, e) in enumerate(zip(loss_d, loss_o, errs)):
         print(f"  step {i:2d}  {a:12.4f}  {b:12.4f}  {e:.2e}")
     assert loss_o[-1] < 0.9 * loss_o[0], "the oracle trajectory itself must be learning"
-    assert max(errs) < 1e-3, max(errs)
+    assert max(errs) < 5e-4, max(errs)  # measured (r2): max 1.9e-4 at step 2, <= 5e-5 elsewhere
     # accumulated displacement: relative L2 distance of (theta_20 - theta_0) over the whole arena and per sub-network
     num = den = 0.0
     per = {}
@@ -179,7 +179,7 @@ def test_adam_trajectory_20_steps_b128_matches_oracle():
           ", ".join(f"{k} {(a / b) ** 0.5:.2e}" for k, (a, b) in per.items()))
     # step 1 of Adam is lr*sign(g): entries whose gradient sits below the fp16 noise floor start in a random
     # direction on either side; over 20 steps the moments average that out
-    assert (num / den) ** 0.5 < 0.10, (num / den) ** 0.5
+    assert (num / den) ** 0.5 < 0.06, (num / den) ** 0.5  # measured (r2): 3.0e-2 over the arena
 
 
 @pytest.mark.parametrize("use_pose", [False, True])
@@ -214,9 +214,11 @@ def test_sgd_one_step_b128_matches_oracle(use_pose):
     worst = sorted(derr.items(), key=lambda kv: -kv[1])[:6]
     print(f"SGD one step, B=128, pose={use_pose}: whole-arena delta rel {nrel(flat_d, flat_o):.3e}; worst tensors:\n" +
           "\n".join(f"  {k:50s} delta {v:.3e}  grad {gerr[k]:.3e}" for k, v in worst))
-    assert nrel(flat_d, flat_o) < 1e-2, nrel(flat_d, flat_o)
+    # measured (r2): whole arena 4.2e-4 / 4.5e-4; worst tensor 2.4e-3 without, 9.7e-3 with the pose expert (ReLU flips
+    # of the pose decoder behind z: test_pose_gradient_error_is_explained_by_relu_flips)
+    assert nrel(flat_d, flat_o) < 2e-3, nrel(flat_d, flat_o)
     for k, v in derr.items():
-        assert v < (5e-2 if use_pose else 1e-2), (k, v)
+        assert v < (2.5e-2 if use_pose else 5e-3), (k, v)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -355,19 +357,24 @@ def test_graph_survives_eager_steps_of_other_batch_sizes():
     x8, t8 = dev(8)
     g = engine.GraphedTrainStep(eng, opt, x8, t8, klw, split_optimizer=True)  # forward + backward only
     arena = engine.get_arena(model)
-    src.ctr.zero_()
-    g.run()
-    torch.cuda.synchronize()
-    loss_a, grad_a = float(g.loss), arena.grad.clone()
+    def replay():
+        src.ctr.zero_()  # same dropout masks / eps every time
+        g.run()
+        torch.cuda.synchronize()
+        return float(g.loss), arena.grad.clone()
+    loss_a, grad_a = replay()
+    loss_a2, grad_a2 = replay()
+    # run-to-run noise floor of one and the same graph: fp32 atomics (split-K, BatchNorm sums, weight gradients)
+    # land in a different order, and behind them a few fp16 roundings flip
+    e0 = nrel(grad_a2, grad_a)
     for n in (4, 16, 5):  # other shapes through the same engine / workspace, eagerly
         xs, ts = dev(n)
         _, l = eng.evaluate(xs, ts, klw, want_outputs=False)
         l.backward()
     torch.cuda.synchronize()
-    src.ctr.zero_()
-    g.run()
-    torch.cuda.synchronize()
-    loss_b, grad_b = float(g.loss), arena.grad.clone()
+    loss_b, grad_b = replay()
     e = nrel(grad_b, grad_a)
-    print(f"graph replay before / after eager steps of other sizes: loss {loss_a:.6f} / {loss_b:.6f}, grad rel {e:.2e}")
-    assert abs(loss_a - loss_b) <= 1e-6 * abs(loss_a) and e < 1e-5
+    print(f"graph replay before / after eager steps of other sizes: loss {loss_a:.6f} / {loss_b:.6f}, grad rel {e:.2e} "
+          f"(replay-to-replay noise floor {e0:.2e}, loss {abs(loss_a2 - loss_a) / abs(loss_a):.1e})")
+    assert abs(loss_a - loss_b) <= 2e-6 * abs(loss_a)
+    assert e < max(5 * e0, 1e-5), (e, e0)
