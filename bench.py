@@ -122,9 +122,21 @@ def synth_batch(B, seed, device=None, pin=False):
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference step on the host cores
+# reference arm / cpu baseline: the UNMODIFIED reference (baseline/_ref, copied from /root/reference by
+# __graft_entry__.build()) through its own SeqModeling._evaluate_model + torch.optim.Adam on the host cores;
+# the oracle port only if that copy is absent
 # ---------------------------------------------------------------------------------------------
+REF_SAMPLE_B = 128  # the reference's own default --batchsize (main.py:25) and its best CPU throughput
+
+
 def cpu_steps(sample_B, steps, warmup, threads):
+    """-> (seconds per step, kind, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    if ref_runner.available():
+        times, _, root = ref_runner.time_step(sample_B, steps, warmup, "cpu", threads)
+        where = "baseline/_ref" if root.endswith("_ref") else root
+        return times, "reference", f"the reference's own mmdyn.pytorch step (SeqModeling._evaluate_model + backward + torch.optim.Adam, {where})"
     from oracle import mmdyn_oracle as orc
     from mmdyn_b200.pytorch.models.models import setup_model
     torch.set_num_threads(threads)
@@ -141,7 +153,7 @@ def cpu_steps(sample_B, steps, warmup, threads):
         orc.train_step(sd, pkeys, "mvae+pose", {"x": x, "targets": t}, 1.0 / 50, 1000.0, noises, st)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times
+    return times, "port", "oracle port of the reference step (baseline/_ref absent)"
 
 
 def run_reference(args):
@@ -149,24 +161,88 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_B = min(args.batch, 128)
-    # ~0.4 s per 128-sample step on 16 cores: cap the timed steps so the arm ends within ~2 minutes
-    times = cpu_steps(sample_B, min(args.steps, 40), min(args.warmup, 2), threads)
+    sample_B = min(args.batch, REF_SAMPLE_B)
+    # ~0.4-1.3 s per 128-sample step: cap the timed steps so the arm ends within ~2 minutes
+    n_steps, n_warm = min(args.steps, 40), min(max(args.warmup, 1), 2)
+    times, kind, what = cpu_steps(sample_B, n_steps, n_warm, threads)
     tot = sum(times)
     v = sample_B * len(times) / tot
-    sample = f"{len(times)} steps x {sample_B} samples of the same 7-pass cnn-mvae+pose step (fp32, torch CPU ops)"
+    sample = (f"{len(times)} timed steps x {sample_B} samples (each step = a {sample_B}-sample SAMPLE of the per-GPU batch "
+              f"{args.batch} the B200 arm runs; CPU throughput is flat-to-falling in batch, BASELINE.md §2): {what}; fp32, {threads} threads")
+    cfg = workload_config(args, args.batch)
+    cfg["reference_sample_batch"] = sample_B
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.batch),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "warmup": n_warm, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def reference_cuda(B, dev, steps=8, warmup=3):
+    """Same-box comparator BASELINE.md §3 / SURVEY §0 name: the reference's own modules `.to('cuda')`, stock
+    PyTorch eager (cuDNN / cuBLAS), same step, same batch.  Informational (`extra.reference_cuda`)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    if not ref_runner.available():
+        return {"unavailable": "baseline/_ref absent"}
+    try:
+        times, lv, _ = ref_runner.time_step(B, steps, warmup, dev)
+        ms = 1e3 * sum(times) / len(times)
+        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": len(times),
+                "what": "unmodified reference modules .to('cuda'), stock PyTorch eager fp32 (TF32 off), 1 GPU, "
+                        "inputs resident, loss.item() per step as problems.py:156", "final_loss": lv}
+    except Exception as e:  # noqa: BLE001 - informational leg
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        torch.cuda.empty_cache()
+
+
+def synth_batch_u8(B, seed):
+    """The same batch in the dataset's native precision: 8-bit frames (the reference reads PNG renders and
+    divides by 255, datasets.py:23-31), HWC uint8, pinned; poses fp32.  Order as synth_batch: v, t, p, tv, tt, tp."""
+    g = torch.Generator().manual_seed(seed)
+    img = lambda: torch.randint(0, 256, (B, 64, 64, 3), generator=g, dtype=torch.uint8).pin_memory()
+    vec = lambda: torch.rand(B, 7, generator=g).pin_memory()
+    return [img(), img(), vec(), img(), img(), vec()]
+
+
+def dyn_shard(rank, world, S, L, seed):
+    """configs[3]: this rank's rows of a dyn_modeling step batch of world*S sequences x L frames, parsed as
+    DynModeling.parse_input parses the WHOLE batch (targets = roll(-1) over the frame axis, every
+    last-of-sequence image row <- the resting-state target, pose target = bare roll incl. the wrap-around of the
+    very last row to row 0, problems.py:765-803).  A shard's last row needs the next shard's first row, so the
+    rank builds its S sequences plus the first sequence of the next rank (cyclically) and parses those; the
+    rows of its own sequences are then exactly the rows of the global parse (tests/test_host_cpu.py)."""
+    def seq(i):
+        g = torch.Generator().manual_seed(seed * 1000003 + i)
+        r = lambda *s_: torch.rand(*s_, generator=g)
+        return r(L, 3, 64, 64), r(L, 3, 64, 64), r(L, 7), r(1, 3, 64, 64), r(1, 3, 64, 64)
+    ids = [rank * S + j for j in range(S)] + [((rank + 1) % world) * S]
+    parts = [seq(i) for i in ids]
+    vis, tac, pose = (torch.cat([p[k] for p in parts]) for k in range(3))
+    rest_v = torch.cat([p[3].expand(L, -1, -1, -1) for p in parts])
+    rest_t = torch.cat([p[4].expand(L, -1, -1, -1) for p in parts])
+
+    def shifted(x, rest):
+        t = torch.roll(x, -1, dims=0)
+        t[L - 1::L] = rest[L - 1::L]
+        return t
+    n = S * L
+    x = [vis[:n], tac[:n], pose[:n]]
+    t = [shifted(vis, rest_v)[:n], shifted(tac, rest_t)[:n], torch.roll(pose, -1, dims=0)[:n]]
+    return x, t
+
+
 def workload_config(args, B):
-    return {"workload": "cnn-mvae --input-type visuotactile --use-pose seq_modeling: 7 sub-sampled passes + backward + Adam "
-                        f"(BASELINE.json configs[2]/[4]), per-GPU batch {B}",
+    if getattr(args, "problem", "seq") == "dyn":
+        wl = ("cnn-mvae --input-type visuotactile --use-pose dyn_modeling with missing-modality sub-sampling: all S*L frames "
+              f"of {B // args.seq_len} sequences x {args.seq_len} frames per GPU, one-step targets by roll/fix-up, 7 passes + "
+              "backward + Adam (BASELINE.json configs[3]), sharded by whole sequences")
+    else:
+        wl = ("cnn-mvae --input-type visuotactile --use-pose seq_modeling: 7 sub-sampled passes + backward + Adam "
+              f"(BASELINE.json configs[2]/[4]), per-GPU batch {B}")
+    return {"workload": wl,
             "per_gpu_batch": B, "global_batch": B * args.gpus, "latent": 256, "image": "3x64x64 x2 + pose 7",
             "parallelism": f"dp{args.gpus}" if args.gpus > 1 else "single",
             "l2": "per-step working set (activations + inputs, ~5 MB/sample) exceeds the 126 MB L2"}
@@ -199,6 +275,9 @@ def run_b200(args):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+    dyn = args.problem == "dyn"
+    if dyn:
+        args.batch = args.sequences * args.seq_len  # rows entering the model per GPU and step
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     pk = peaks()
 
@@ -209,8 +288,18 @@ def run_b200(args):
     opt = optim.FusedAdam(model, lr=1e-3)
     opt.grad_prescale = 1.0 / world
     klw = 1.0 / 50
-    dev_batches = [synth_batch(B, 10 + 3 * rank + i, device=dev) for i in range(3)]
-    host_batches = [synth_batch(B, 10 + 3 * rank + i, pin=True) for i in range(3)]
+    if dyn:
+        dev_batches = []
+        for i in range(3):
+            xb, tb = dyn_shard(rank, world, args.sequences, args.seq_len, 10 + i)
+            dev_batches.append(([a.to(dev) for a in xb], [a.to(dev) for a in tb]))
+        del xb, tb
+    else:
+        dev_batches = [synth_batch(B, 10 + 3 * rank + i, device=dev) for i in range(3)]
+    # e2e feeds the step from pinned HOST memory in the dataset's native precision: uint8 frames (converted to
+    # the fp32 NCHW tensors the model reads by mmdyn_frames_u8_to_f32) + fp32 poses
+    host_batches = [synth_batch_u8(B, 10 + 3 * rank + i) for i in range(3)]
+    u8_table = ops.resize_table(64, 64, 64, 64).to(dev)
 
     arena = engine.get_arena(model, dev)
     from mmdyn_b200 import parallel
@@ -286,7 +375,8 @@ def run_b200(args):
                                             split_optimizer=world > 1, grad_sync=gstep.sync)
         in_sets = [g_.x + g_.t for g_ in gsteps]
     else:
-        in_sets = [[torch.empty_like(a, device=dev) for a in host_batches[0][0] + host_batches[0][1]] for _ in range(2)]
+        in_sets = [[torch.empty_like(a) for a in dev_batches[0][0] + dev_batches[0][1]] for _ in range(2)]
+    u8_sets = [[torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_batches[0]] for _ in range(2)]
     staged_evt = [torch.cuda.Event(), torch.cuda.Event()]
     consumed_evt = [torch.cuda.Event(), torch.cuda.Event()]
     loss_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
@@ -294,12 +384,15 @@ def run_b200(args):
     e2e_state = {"primed": False, "pending": None, "last": float("nan")}
 
     def stage(i):
-        x, t = host_batches[i % 3]
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed_evt[slot])  # the step that last read this set has finished
-            for dst, src in zip(in_sets[slot], x + t):
-                dst.copy_(src, non_blocking=True)
+            for dst, stg, src in zip(in_sets[slot], u8_sets[slot], host_batches[i % 3]):
+                stg.copy_(src, non_blocking=True)           # host -> device, uint8 frames / fp32 poses
+                if src.dtype == torch.uint8:
+                    ops.frames_u8_to_f32(stg, None, u8_table, dst)  # /255 -> fp32 NCHW, on the copy stream
+                else:
+                    dst.copy_(stg, non_blocking=True)
             staged_evt[slot].record(copy_stream)
 
     def step_e2e(i):
@@ -367,10 +460,18 @@ def run_b200(args):
 
     value = world * B * K / (ms_total / 1e3)
     e2e_v = world * B * K / (ms_e2e / 1e3)
-    h2d = sum(a.numel() * a.element_size() for a in host_batches[0][0] + host_batches[0][1])
+    h2d = sum(a.numel() * a.element_size() for a in host_batches[0])
+
+    # ---- sustained: the same resident step for >= 5 s (power-capped steady state, not a burst) ----
+    sustained = None
+    if not args.no_sustained:
+        n_s = max(K, int(5.5e3 / (ms_total / K)))
+        ms_s = timed(step_resident, n_s)
+        sustained = {"value": world * B * n_s / (ms_s / 1e3), "unit": UNIT, "steps": n_s, "seconds": ms_s / 1e3,
+                     "ms_per_step": ms_s / n_s}
 
     # ---- roofline pass: every launch of this library timed with CUDA events (eager, untimed run) ----
-    roof, table = None, []
+    roof, roof_hbm, table, families, tensor_all = None, None, [], [], None
     if rank == 0:
         eng.set_concurrent(False)  # serial branches: per-kernel events must not time-share the SMs
         eng.bucket_hook = None     # rank-0-only pass: no collectives
@@ -387,67 +488,87 @@ def run_b200(args):
                           "share": round(d["ms"] / tot_ms, 4),
                           "tflops": round(d["flops"] / d["ms"] / 1e9, 2) if d["flops"] else None,
                           "gbs": round(d["bytes"] / d["ms"] / 1e6, 1) if d["bytes"] else None})
-        top_tag, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-        # which roof binds the dominant kernel: time at the tensor peak vs time at the HBM peak for its
-        # ALGORITHMIC flops / bytes (e.g. the 3-channel logits layer is a GEMM but HBM-bound: 56 FLOP/B)
-        t_tensor = top["flops"] / (pk["tf_sust"] * 1e12)
-        t_hbm = top["bytes"] / (pk["hbm"] * 1e9)
-        common = {"kernel": top_tag, "traffic": None, "launch_ms": top["ms"] / top["count"],
-                  "launches": top["count"], "share_of_step": top["ms"] / tot_ms,
-                  "algorithmic_bytes_per_launch": top["bytes"] / top["count"],
-                  "algorithmic_flops_per_launch": top["flops"] / top["count"]}
-        if t_tensor > t_hbm:
-            ach = top["flops"] / (top["ms"] / 1e3) / 1e12
-            roof = dict(common, bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
-                        peak_source=pk["src"] + ", sustained bf16/fp16 GEMM")
-        else:
-            ach = top["bytes"] / (top["ms"] / 1e3) / 1e9
-            roof = dict(common, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
-                        peak_source=pk["src"])
-        try:  # DRAM traffic of the dominant kernel from the committed ncu capture (same batch only)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if tr.get("batch") == B and top_tag in tr:
-                roof["traffic"] = tr[top_tag]["traffic_bytes_largest_launch"]
-                roof["traffic_note"] = ("largest launch of this kernel, ncu --set full; algorithmic bytes of that launch: %d"
-                                        % tr[top_tag]["algorithmic_bytes_largest_launch"])
+        # The profile tags are per LAYER for the GEMMs ("deconv3.fwd") and per KERNEL for the streaming ops; the
+        # roofline is reported per kernel NAME, so the layer tags are pooled into the kernel that runs them.
+        fam = {}
+        for tag, d in prof.items():
+            name = ops.kernel_family(tag)
+            f = fam.setdefault(name, dict(count=0, ms=0.0, flops=0.0, bytes=0.0, tags=[]))
+            for k_ in ("count", "ms", "flops", "bytes"):
+                f[k_] += d[k_]
+            f["tags"].append(tag)
+        try:  # DRAM traffic per launch from the ncu --set full capture of THIS build (same batch only)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            tr = tr if tr.get("batch") == B else {}
         except Exception:
-            pass
+            tr = {}
+
+        def block(name, f):
+            t_tensor = f["flops"] / (pk["tf_sust"] * 1e12)
+            t_hbm = f["bytes"] / (pk["hbm"] * 1e9)
+            common = {"kernel": name, "layers": sorted(f["tags"]) if len(f["tags"]) > 1 else None,
+                      "traffic": (tr.get(name) or {}).get("dram_bytes_per_launch"),
+                      "traffic_source": (tr.get(name) or {}).get("source"),
+                      "launch_ms": f["ms"] / f["count"], "launches": f["count"], "share_of_step": f["ms"] / tot_ms,
+                      "algorithmic_bytes_per_launch": f["bytes"] / f["count"],
+                      "algorithmic_flops_per_launch": f["flops"] / f["count"]}
+            if t_tensor > t_hbm:
+                ach = f["flops"] / (f["ms"] / 1e3) / 1e12
+                return dict(common, bound="tensor", achieved=ach, peak=pk["tf_sust"], unit="TFLOP/s", frac=ach / pk["tf_sust"],
+                            peak_source=pk["src"] + ", sustained bf16/fp16 GEMM (kernel timed inside a long step)")
+            ach = f["bytes"] / (f["ms"] / 1e3) / 1e9
+            return dict(common, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                        peak_source=pk["src"])
+        ranked = sorted(fam.items(), key=lambda kv: -kv[1]["ms"])
+        blocks = [block(n_, f_) for n_, f_ in ranked if f_["flops"] or f_["bytes"]]
+        roof = blocks[0]                                                   # the dominant kernel of the step
+        roof_hbm = next((b_ for b_ in blocks if b_["bound"] == "hbm"), None)  # and the top HBM-bound one
+        families = [{"kernel": b_["kernel"], "bound": b_["bound"], "ms": round(b_["launch_ms"] * b_["launches"], 4),
+                     "share": round(b_["share_of_step"], 4), "frac": round(b_["frac"], 4)} for b_ in blocks[:8]]
+        # all tensor-core layers together (north_star's FLOP-weighted figure)
+        tc = [f_ for n_, f_ in fam.items() if n_.startswith(("igemm_tma", "wgrad_tma", "conv1_"))]
+        tc_ms, tc_fl = sum(f_["ms"] for f_ in tc), sum(f_["flops"] for f_ in tc)
+        tensor_all = {"ms": tc_ms, "tflops": tc_fl / tc_ms / 1e9, "frac_of_sustained_peak": tc_fl / tc_ms / 1e9 / pk["tf_sust"]} if tc_ms else None
         if args.profile_out:
             with open(args.profile_out, "w") as f:
-                json.dump({"batch": B, "ms_per_step_events_sum": tot_ms, "kernels": table}, f, indent=1)
+                json.dump({"batch": B, "ms_per_step_events_sum": tot_ms, "kernels": table, "families": families,
+                           "tensor_layers": tensor_all}, f, indent=1)
 
-    # ---- batch sweep (BASELINE.json configs[4]: batch 64-4096; 128 = the reference's --batchsize default) ----
+    # ---- config 5 grid (BASELINE.json configs[4]): GLOBAL batch 64..4096 on THIS run's N GPUs; 128 = --batchsize default ----
     sweep = None
-    if rank == 0 and world == 1 and use_graph and not args.no_sweep:
+    if use_graph and not args.no_sweep and not dyn:
         eng.set_concurrent(True)
         sweep = []
-        for Bs in (64, 128, 256, 512, 1024, 2048, 4096):
-            if Bs == B:
-                sweep.append({"per_gpu_batch": Bs, "ms_per_step": ms_total / K, "samples_per_s": value})
+        for Bg in (64, 128, 256, 512, 1024, 2048, 4096):
+            Bs = Bg // world
+            if Bs < 8:
                 continue
-            xb, tb = synth_batch(Bs, 99, device=dev)
-            g2 = engine.GraphedTrainStep(eng, opt, xb, tb, klw)
+            xb, tb = synth_batch(Bs, 99 + rank, device=dev)
+            g2 = engine.GraphedTrainStep(eng, opt, xb, tb, klw, split_optimizer=world > 1)
+
+            def one():
+                g2.run()
+                if world > 1:
+                    dist.all_reduce(arena.grad)
+                    g2.apply()
             for _ in range(5):
-                g2.run()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                one()
             n = 30
-            e0.record()
-            for _ in range(n):
-                g2.run()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / n
-            sweep.append({"per_gpu_batch": Bs, "ms_per_step": round(ms, 4), "samples_per_s": round(Bs / ms * 1e3, 1)})
+            ms = timed(lambda i: one(), n) / n
+            sweep.append({"global_batch": Bg, "per_gpu_batch": Bs, "n_gpus": world, "ms_per_step": round(ms, 4),
+                          "samples_per_s": round(Bg / ms * 1e3, 1)})
             del g2, xb, tb
 
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda and not dyn:
+        ref_cuda = reference_cuda(B, dev)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        sb = min(B, 128)
-        ts = cpu_steps(sb, 3, 1, threads)
-        cpu = {"value": sb * len(ts) / sum(ts), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{len(ts)} steps x {sb} samples of the same step (oracle, fp32 torch CPU ops)"}
+        sb = min(B, REF_SAMPLE_B)
+        ts, kind, what = cpu_steps(sb, 6, 1, threads)
+        cpu = {"value": sb * len(ts) / sum(ts), "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{len(ts)} steps x {sb} samples of the same step: {what}; fp32, {threads} threads"}
 
     if rank == 0:
         out = {
@@ -456,12 +577,17 @@ def run_b200(args):
             "dtype": "f16 operands (10-bit mantissa, TF32-equivalent) / f32 accumulate",
             "data": "synthetic", "config": workload_config(args, B),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / K},
+                    "ms_per_step": ms_e2e / K,
+                    "input_format": "pinned host uint8 HWC frames (the dataset's native 8-bit renders) + fp32 poses; "
+                                    "uint8 -> fp32 NCHW /255 on the device (mmdyn_frames_u8_to_f32) inside the timed region"},
             "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
-            "cuda_graph": bool(use_graph), "data_parallel_mode": dp_mode, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "cuda_graph": bool(use_graph), "data_parallel_mode": dp_mode, "clocks": sampler.summary(), "roofline": roof, "roofline_hbm": roof_hbm,
+            "cpu_baseline": cpu,
+            "extra": {"sustained": sustained, "reference_cuda": ref_cuda, "grid": sweep, "kernel_families": families,
+                      "tensor_layers_all": tensor_all},
             "step_tflops": value * FLOP_PER_SAMPLE / 1e12 / world,
             "step_frac_of_tensor_peak": value * FLOP_PER_SAMPLE / 1e12 / world / pk["tf_sust"],
-            "final_loss": final_loss, "top_kernels": table[:6], "batch_sweep": sweep,
+            "final_loss": final_loss, "top_kernels": table[:6],
         }
         print(json.dumps(out))
     if world > 1:
@@ -481,6 +607,12 @@ def main():
     ap.add_argument("--nccl-in-graph", action="store_true",
                     help="experimental: capture NCCL inside the step graph (hangs on torch 2.11 / NCCL 2.28.9)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip extra.reference_cuda (stock eager reference on this GPU)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip extra.sustained (>= 5 s of the resident step)")
+    ap.add_argument("--problem", default="seq", choices=["seq", "dyn"],
+                    help="seq: BASELINE configs[2] (default); dyn: configs[3], dyn_modeling over --sequences x --seq-len frames per GPU")
+    ap.add_argument("--sequences", type=int, default=128, help="dyn: sequences per GPU and step (--batchsize default 128)")
+    ap.add_argument("--seq-len", type=int, default=50, help="dyn: frames per sequence (50 in exp 1/2)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the per-GPU batch sweep (64-4096, 30 graph replays each)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event table here (JSON)")
     args = ap.parse_args()

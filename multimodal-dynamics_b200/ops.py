@@ -59,6 +59,25 @@ def stop_profile():
     return out
 
 
+_FAMILY = {"adam_flat": "adam_kernel", "sgd_flat": "sgd_kernel", "bn_stats": "bn_stats_bulk_kernel",
+           "bn_swish_fwd": "bn_swish_fwd_bulk_kernel", "bn_swish_bwd_reduce": "bn_swish_bwd_reduce_bulk_kernel",
+           "bn_bwd_apply": "bn_bwd_apply_bulk_kernel", "linear_f32_fwd": "sgemm_kernel (pose MLP forward)",
+           "linear_f32_bwd": "sgemm_kernel (pose MLP backward)", "conv1_fwd": "conv1_fwd_kernel",
+           "conv1.wgrad": "wgrad_kernel<32> (conv1, Cin = 3 -> 8-channel pixels)"}
+
+
+def kernel_family(tag):
+    """Kernel NAME a profile tag runs in: the GEMM launches are tagged per layer ("deconv3.fwd") and pooled here
+    into the kernel template that executes them; the streaming kernels are tagged by their own name."""
+    if tag in _FAMILY:
+        return _FAMILY[tag]
+    if tag.endswith(".fwd") or tag.endswith(".dgrad"):
+        return "igemm_tma_kernel<*> (conv / deconv / linear forward + dgrad)"
+    if tag.endswith(".wgrad"):
+        return "wgrad_tma_kernel<*> (weight gradients)"
+    return tag + "_kernel"
+
+
 class _Timed:
     __slots__ = ("tag", "alg", "e0")
 

@@ -272,3 +272,28 @@ def test_device_noise_state_round_trip():
     st = src.state_dict()
     back = noise.DeviceNoise.from_state_dict(st, "cpu")
     assert back.seed == 123 and int(back.ctr.item()) == 987654321012
+
+
+def test_bench_dyn_shards_equal_the_global_parse():
+    """bench.py --problem dyn builds every rank's rows locally (its sequences + the next rank's first one); the
+    result must be the rows DynModeling.parse_input gives on the WHOLE step batch, incl. the wrap-around row."""
+    import bench
+    from oracle import mmdyn_oracle as orc
+    world, S, L = 3, 2, 4
+    shards = [bench.dyn_shard(r, world, S, L, seed=5) for r in range(world)]
+    # global batch from the same per-sequence generator
+    def seq(i):
+        g = torch.Generator().manual_seed(5 * 1000003 + i)
+        r = lambda *s_: torch.rand(*s_, generator=g)
+        return r(L, 3, 64, 64), r(L, 3, 64, 64), r(L, 7), r(1, 3, 64, 64), r(1, 3, 64, 64)
+    parts = [seq(i) for i in range(world * S)]
+    data = [torch.cat([p[k] for p in parts]) for k in range(3)] + [torch.ones(world * S * L, 2)]
+    target = [torch.cat([p[3].expand(L, -1, -1, -1) for p in parts]), torch.cat([p[4].expand(L, -1, -1, -1) for p in parts]),
+              data[2].clone(), torch.ones(world * S * L, 3, 64, 64)]
+    inp, tgt = orc.dyn_parse_input(data, target, L, "visuotactile")
+    n = S * L
+    for r, (x, t) in enumerate(shards):
+        sl = slice(r * n, (r + 1) * n)
+        assert torch.equal(x[0], inp["model_input"][0][sl]) and torch.equal(x[2], inp["input_object_pose"][0][sl])
+        assert torch.equal(t[0], tgt["target_output"][0][sl]) and torch.equal(t[1], tgt["target_output"][1][sl])
+        assert torch.equal(t[2], tgt["target_object_pose"][0][sl]), r  # bare roll; last rank wraps to row 0
