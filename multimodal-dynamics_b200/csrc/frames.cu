@@ -151,6 +151,43 @@ frames_u8_to_f32_kernel(const uint8_t* __restrict__ src, const long long* __rest
   }
 }
 
+// Same-size frames (the renders are already at the model's resolution, e.g. the uint8 host batches of
+// bench.py's e2e leg): Pillow's resize is the identity there, so the kernel is ToTensor alone — HWC uint8 ->
+// planar fp32 / 255.  Pure HBM byte work (3 B read + 12 B written per pixel): one CTA stages 1024 pixels
+// with 16-byte loads and writes three 4 KB plane segments with 16-byte stores.
+constexpr int TT_PIX = 1024;
+__global__ void __launch_bounds__(256)
+frames_u8_to_tensor_kernel(const uint8_t* __restrict__ src, const long long* __restrict__ index,
+                           float* __restrict__ dst, int hw, int chunks_per_frame) {
+  __shared__ __align__(16) uint8_t px[TT_PIX * 3];
+  const int fi = blockIdx.x / chunks_per_frame, ch = blockIdx.x - fi * chunks_per_frame;
+  const long long frame = index ? index[fi] : fi;
+  const int p0 = ch * TT_PIX, np = min(TT_PIX, hw - p0);
+  const uint8_t* g = src + (frame * hw + p0) * 3;
+  if (np == TT_PIX && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    for (int i = threadIdx.x; i < TT_PIX * 3 / 16; i += 256)
+      reinterpret_cast<uint4*>(px)[i] = __ldg(reinterpret_cast<const uint4*>(g) + i);
+  } else {
+    for (int i = threadIdx.x; i < np * 3; i += 256) px[i] = __ldg(g + i);
+  }
+  __syncthreads();
+  float* o = dst + static_cast<long long>(fi) * 3 * hw + p0;
+  for (int j = threadIdx.x; j < 3 * (TT_PIX / 4); j += 256) {
+    const int c = j / (TT_PIX / 4), q = (j - c * (TT_PIX / 4)) * 4;
+    if (q + 3 < np && ((hw | p0) & 3) == 0) {
+      float4 v;
+      v.x = __fdiv_rn(static_cast<float>(px[(q + 0) * 3 + c]), 255.0f);
+      v.y = __fdiv_rn(static_cast<float>(px[(q + 1) * 3 + c]), 255.0f);
+      v.z = __fdiv_rn(static_cast<float>(px[(q + 2) * 3 + c]), 255.0f);
+      v.w = __fdiv_rn(static_cast<float>(px[(q + 3) * 3 + c]), 255.0f);
+      *reinterpret_cast<float4*>(o + static_cast<long long>(c) * hw + q) = v;
+    } else {
+      for (int e = q; e < min(q + 4, np); ++e)
+        o[static_cast<long long>(c) * hw + e] = __fdiv_rn(static_cast<float>(px[e * 3 + c]), 255.0f);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace mmdyn
 
@@ -184,6 +221,14 @@ extern "C" int mmdyn_frames_u8_to_f32(const void* frames_u8, const long long* in
   MMDYN_REQUIRE(frames_u8 && table_dev && out_nchw && n > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0,
                 "frames_u8_to_f32: bad arguments");
   MMDYN_REQUIRE(n <= 65535, "frames_u8_to_f32: at most 65535 frames per call (n=%d)", n);
+  if (in_h == out_h && in_w == out_w) {  // no resampling: ToTensor only
+    const int hw = in_h * in_w, chunks = (hw + TT_PIX - 1) / TT_PIX;
+    frames_u8_to_tensor_kernel<<<n * chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(frames_u8), index, out_nchw, hw, chunks);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    MMDYN_CHECK_CUDA(cudaGetLastError());
+    return MMDYN_OK;
+  }
   const int ksy = axis_ksize(in_h, out_h);
   const int row_pitch = (in_w * 3 + 15) & ~15;
   const size_t smem = static_cast<size_t>(ksy) * (row_pitch + out_w * 3);

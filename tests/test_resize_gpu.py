@@ -29,7 +29,8 @@ def test_kernel_matches_reference_goldens(case):
     assert np.array_equal(out, GOLD[name].astype(np.float32) / np.float32(255.0))
 
 
-@pytest.mark.parametrize("sizes", [(256, 256, 64, 64), (97, 131, 64, 64), (33, 40, 64, 64), (480, 640, 64, 64)])
+@pytest.mark.parametrize("sizes", [(256, 256, 64, 64), (97, 131, 64, 64), (33, 40, 64, 64), (480, 640, 64, 64),
+                                   (64, 64, 64, 64), (30, 17, 30, 17)])  # same size: the ToTensor-only kernel
 def test_kernel_matches_oracle_with_gather(sizes):
     h, w, oh, ow = sizes
     rs = np.random.RandomState(h * 1000 + w)
