@@ -99,6 +99,16 @@ typedef struct mmdyn_igemm_desc {
   int32_t bce_rows_per_group;
   int32_t bce_slot[MMDYN_MAX_GROUPS]; /* < 0: group carries no loss (its gradient rows are left untouched) */
   int32_t logit_row_lo, logit_row_hi;
+  /* patch_mode != 0 (merged 3x3-tap layers only: s_in = 1, the 9 taps dy,dx in {-1,0,1} row-major first,
+   * out_mode 3 / 4 / 5, OXv = IW in {8,16,32}): shared-memory patch reuse — one activation box per filter
+   * column serves its three row taps, and with out_mode 4 only the structurally non-zero (tap, sub-pixel
+   * phase) weight blocks are fetched and multiplied (vae.py:271-277 forward; dgrad of vae.py:200-203). */
+  int32_t patch_mode;
+  /* out_mode 4 + patch_mode: optional BatchNorm statistics of the raw output fused into the epilogue —
+   * bn_sums[group][ldc][2] += {sum x, sum x^2} of the fp16-rounded outputs, group = image / bn_rows_per_group
+   * (replaces mmdyn_bn_stats for this layer's output; caller zeroes bn_sums). */
+  int32_t bn_rows_per_group;
+  float* bn_sums;
 } mmdyn_igemm_desc;
 int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream);
 

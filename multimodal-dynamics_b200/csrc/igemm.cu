@@ -791,6 +791,433 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// igemm, shared-memory PATCH reuse for the merged 3x3-tap layers (the 4 sub-pixel phases of a k4/s2/p1
+// transposed conv, or of the dgrad of a k4/s2/p1 conv, as one GEMM over the 3x3 neighbourhood of the
+// low-resolution grid: deconv2/3/4 forward, conv2/3 dgrad).  These layers were bound by the L2 -> shared
+// memory operand feed: every input pixel was fetched once per tap (9 boxes per 128-row tile), and 20 of the
+// 36 (tap, phase) weight blocks are structurally zero.  Here
+//   * ONE activation box per filter COLUMN dx and 64-channel block — (bh + 2) image rows x bw pixels x bn
+//     images, zero-filled halo — serves the three taps dy = -1, 0, +1: tile row r = (y * bn + img) * bw + x, so
+//     a shift by one image row is a shift by bn * bw rows of the box = a whole number of 8-row swizzle atoms,
+//     i.e. just another start address of the UMMA descriptor.  9 boxes -> 3 x (bh + 2) / bh box equivalents;
+//   * the weight operand is fetched and multiplied per LIVE quarter of the N dimension only (quarter = one
+//     sub-pixel phase): corner taps feed 1 phase, edge taps 2, the centre tap 4 -> 16 instead of 36 blocks, and
+//     the MMAs run with N = 1, 2 or 4 quarters into the matching TMEM column range.  The centre tap goes first
+//     so that its accumulate = 0 MMA initialises every column.
+//   warp 0 TMA producer (ring of activation patches; the live weight blocks stay resident), warp 1 MMA issuer,
+//   EG groups of 4 epilogue warps: group e drains the tiles whose accumulator stage is e (EG = 2), so the epilogue
+//   (fp16 stores + BatchNorm statistics) has two tile times per tile
+// CIN_MODE 0: Cin % 64 == 0 (128-byte rows, 128B swizzle); 1: Cin == 32 (64-byte rows, 64B swizzle).
+// ---------------------------------------------------------------------------------------------
+// Tap schedule of the patch kernel, fixed at compile time so that the MMA issuer is straight-line code (one
+// descriptor add per operand and MMA; table look-ups in the issue loop made it issue-bound: ncu source view,
+// 27 uniform-datapath instructions incl. 3 dependent constant loads per UTCHMMA).  Order: filter column
+// dx = 0, -1, +1; inside a column dy = 0, -1, +1 — the centre tap first (its accumulate = 0 MMA initialises every
+// column).  NQ4 (out_mode 4): quarter q = ph*2 + pw of the N dimension is one sub-pixel phase of a k4/s2/p1
+// transposed conv; phase parity 0 reads input offsets {0, -1}, parity 1 reads {+1, 0} along that axis, so a tap
+// (dy, dx) feeds the quarters listed here.  blk = index of the run's first weight block in the resident region
+// (live blocks are stored back to back in schedule order).
+struct TapSched {
+  int dy, dx, nruns, q0[2], len[2], blk[2];
+};
+__host__ __device__ constexpr TapSched tap_sched(bool nq4, int ti) {
+  if (nq4) {
+    switch (ti) {
+      case 0: return {0, 0, 1, {0, 0}, {4, 0}, {0, 0}};
+      case 1: return {-1, 0, 1, {0, 0}, {2, 0}, {4, 0}};
+      case 2: return {1, 0, 1, {2, 0}, {2, 0}, {6, 0}};
+      case 3: return {0, -1, 2, {0, 2}, {1, 1}, {8, 9}};
+      case 4: return {-1, -1, 1, {0, 0}, {1, 0}, {10, 0}};
+      case 5: return {1, -1, 1, {2, 0}, {1, 0}, {11, 0}};
+      case 6: return {0, 1, 2, {1, 3}, {1, 1}, {12, 13}};
+      case 7: return {-1, 1, 1, {1, 0}, {1, 0}, {14, 0}};
+      default: return {1, 1, 1, {3, 0}, {1, 0}, {15, 0}};
+    }
+  }
+  switch (ti) {
+    case 0: return {0, 0, 1, {0, 0}, {1, 0}, {0, 0}};
+    case 1: return {-1, 0, 1, {0, 0}, {1, 0}, {1, 0}};
+    case 2: return {1, 0, 1, {0, 0}, {1, 0}, {2, 0}};
+    case 3: return {0, -1, 1, {0, 0}, {1, 0}, {3, 0}};
+    case 4: return {-1, -1, 1, {0, 0}, {1, 0}, {4, 0}};
+    case 5: return {1, -1, 1, {0, 0}, {1, 0}, {5, 0}};
+    case 6: return {0, 1, 1, {0, 0}, {1, 0}, {6, 0}};
+    case 7: return {-1, 1, 1, {0, 0}, {1, 0}, {7, 0}};
+    default: return {1, 1, 1, {0, 0}, {1, 0}, {8, 0}};
+  }
+}
+
+struct PatchGeom {
+  int lbw, lbn, bh, bn;     // box: bw = 1 << lbw pixels wide (= IW), bh rows, bn = 1 << lbn images
+  int tiles_y, img_blocks, total_tiles;
+  int a_rows;               // (bh + 2) * bn * bw rows per activation box
+  int nq;                   // live-quarter granularity: 4 (out_mode 4: one quarter per sub-pixel phase) or 1
+  int w_bytes_cb;           // bytes of the live weight blocks of one 64-channel block (all 9 taps)
+  int8_t tap_k[9];          // [dxi * 3 + dyi] -> tap index in the K order of the packed weights
+  int8_t tap_dyv[9];        // dy of that tap (-1, 0, 1)
+  int8_t tap_dxv[9];
+  int8_t nruns[9];          // contiguous runs of live quarters (<= 2)
+  int8_t run_q0[9][2], run_len[9][2];
+  int32_t run_off[9][2];    // byte offset of the run's first weight block inside the resident weight region
+  uint8_t qmask[9];
+};
+
+template <int BLOCK_N, int CIN_MODE, int SA, int W_KB>
+struct PatchCfg {
+  static constexpr int RB = CIN_MODE == 0 ? 128 : 64;          // bytes per operand row (one pixel, one k-block)
+  static constexpr int KK = RB / 32;                            // K = 16 MMAs per k-block
+  static constexpr int A_SLOT = CIN_MODE == 0 ? 20 * 1024 : 12 * 1024;  // 160 rows x 128 B / 192 rows x 64 B
+  static constexpr int W_BYTES = W_KB * 1024;                   // resident live weight blocks
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int SMEM_BYTES = SA * A_SLOT + W_BYTES + 1024;
+};
+
+template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
+igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ PatchGeom g) {
+  using C = PatchCfg<BLOCK_N, CIN_MODE, SA, W_KB>;
+  constexpr int RB = C::RB;
+  constexpr uint32_t LAYOUT = CIN_MODE == 0 ? LAYOUT_SW128 : LAYOUT_SW64;
+  constexpr int NQ_MAX = 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base, a_ring = smem_base + C::W_BYTES;
+  __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full;
+  __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float stat_all[EG][2 * 64];  // per epilogue group: BatchNorm partial sums {sum x, sum x^2} per channel
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+    mbar_init(smem_u32(&w_full), 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 128); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  for (int i = threadIdx.x; i < EG * 128; i += blockDim.x) (&stat_all[0][0])[i] = 0.0f;
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int CB = CIN_MODE == 0 ? (d.Cin >> 6) : 1;
+  const int bw = 1 << g.lbw;
+  const int NQ = BLOCK_N / g.nq;                        // columns per quarter
+  const uint32_t dy_shift = static_cast<uint32_t>(g.bn * bw * RB);  // one image row of the box, in bytes
+
+  if (warp == 0) {
+    // ======================= TMA producer =====================================================
+    if (elect_one()) {
+      // the live weight blocks of the whole layer stay resident in shared memory: fetched once per CTA
+      {
+        const uint32_t wbar = smem_u32(&w_full);
+        mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(CB * g.w_bytes_cb));
+        for (int cb = 0; cb < CB; ++cb)
+          for (int ti = 0; ti < 9; ++ti) {
+            const int k = g.tap_k[ti] * d.Cin + (cb << 6);
+            uint32_t dst = w_base + cb * g.w_bytes_cb + g.run_off[ti][0];
+            const uint32_t mask = g.qmask[ti];
+#pragma unroll
+            for (int q = 0; q < NQ_MAX; ++q)
+              if (mask & (1u << q)) {
+                tma_load_2d(dst, &tmW, wbar, k, q * NQ);
+                dst += NQ * RB;
+              }
+          }
+      }
+      int ia = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int iblk = tile / g.tiles_y;
+        const int img0 = iblk * g.bn, y0 = (tile - iblk * g.tiles_y) * g.bh;
+        for (int dxi = 0; dxi < 3; ++dxi) {
+          const int dx = g.tap_dxv[dxi * 3];
+          for (int cb = 0; cb < CB; ++cb) {
+            const int sa = ia % SA;
+            mbar_wait(smem_u32(&a_empty[sa]), ((ia / SA) & 1) ^ 1);
+            const uint32_t abar = smem_u32(&a_full[sa]);
+            mbar_arrive_expect_tx(abar, static_cast<uint32_t>(g.a_rows * RB));
+            tma_load_4d(a_ring + sa * C::A_SLOT, &tmA, abar, cb << 6, dx, img0, y0 - 1);  // dims (c, x, img, y)
+            ++ia;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer ======================================================
+    // one ELECTED thread (elect.sync: the compiler then knows the region is single-threaded and emits plain
+    // uniform-datapath code, no ELECT / BRA.U.ANY waterfall around every UTCHMMA); schedule fully unrolled
+    if (elect_one()) {
+      constexpr bool NQ4 = BLOCK_N >= 64;
+      constexpr int NQC = NQ4 ? BLOCK_N / 4 : BLOCK_N;   // columns (= weight rows) per quarter
+      // descriptor = DESC_HI | (address >> 4): LBO 16 B (unused with swizzled K-major), SBO = 8 rows, version 1
+      constexpr uint64_t DESC_HI = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>((8 * RB) >> 4) << 32) |
+                                   (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(LAYOUT) << 61);
+      mbar_wait(smem_u32(&w_full), 0);
+      const uint32_t sh0 = 0, sh1 = dy_shift >> 4, sh2 = (2 * dy_shift) >> 4;  // dy = -1, 0, +1 in 16-byte units
+      int ia = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS;
+#pragma unroll
+        for (int dxi = 0; dxi < 3; ++dxi) {
+          for (int cb = 0; cb < CB; ++cb) {
+            const int sa = ia % SA;
+            mbar_wait(smem_u32(&a_full[sa]), (ia / SA) & 1);
+            tc_fence_after();
+            const uint32_t a16 = (a_ring + sa * C::A_SLOT) >> 4;
+            const uint32_t w16 = (w_base + cb * g.w_bytes_cb) >> 4;
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const TapSched ts = tap_sched(NQ4, dxi * 3 + dyi);
+              const uint32_t a_tap = a16 + (ts.dy < 0 ? sh0 : (ts.dy == 0 ? sh1 : sh2));
+#pragma unroll
+              for (int kk = 0; kk < C::KK; ++kk) {
+                const uint64_t adesc = DESC_HI | static_cast<uint64_t>(a_tap + 2 * kk);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  if (r < ts.nruns) {
+                    const uint64_t bdesc = DESC_HI | static_cast<uint64_t>(w16 + ((ts.blk[r] * NQC * RB + 32 * kk) >> 4));
+                    const uint32_t accumulate = (dxi == 0 && dyi == 0 && kk == 0) ? (cb == 0 ? 0u : 1u) : 1u;
+                    umma_f16(tmem_d + ts.q0[r] * NQC, adesc, bdesc, make_idesc_f16(128, ts.len[r] * NQC, 0, 0, 0, 0),
+                             accumulate);
+                  }
+                }
+              }
+            }
+            umma_commit(smem_u32(&a_empty[sa]));
+            ++ia;
+          }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
+      }
+    }
+  } else {
+    // ======================= epilogue: TMEM -> registers -> global ============================
+    const int q4 = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;  // tile row owned by this thread: r = (y * bn + img) * bw + x
+    const int eg = EG == 1 ? 0 : (warp - 2) >> 2;  // epilogue group: tiles tl = eg, eg + EG, ...
+    const int et = (threadIdx.x - 64) & 127;       // thread index inside the group
+    float* stat_s = stat_all[eg];
+    const int x_l = r & (bw - 1);
+    const int n_l = (r >> g.lbw) & (g.bn - 1);
+    const int y_l = r >> (g.lbw + g.lbn);
+    float bce_acc = 0.0f;
+    int bce_cur = -1;
+    auto bce_flush = [&]() {
+      const float v = warp_sum(bce_acc);
+      if (lane == 0 && bce_cur >= 0) atomicAdd(d.bce_loss + bce_cur, v);
+      bce_acc = 0.0f;
+    };
+    // BatchNorm statistics of the raw output (out_mode 4 with bn_sums): the CTA's partial sums live in shared
+    // memory and are flushed to bn_sums[group] when the group changes (tiles are walked in image order)
+    const bool want_stats = d.out_mode == 4 && d.bn_sums != nullptr;
+    int stat_grp = -1;
+    auto stat_flush = [&]() {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+      const int i = et;
+      if (stat_grp >= 0 && i < 2 * d.ldc) {
+        const float v = stat_s[i];
+        if (v != 0.0f) atomicAdd(d.bn_sums + (static_cast<long long>(stat_grp) * d.ldc + (i >> 1)) * 2 + (i & 1), v);
+        stat_s[i] = 0.0f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+    };
+    for (int tile = blockIdx.x + eg * gridDim.x, tl = eg; tile < g.total_tiles; tile += EG * gridDim.x, tl += EG) {
+      const int iblk = tile / g.tiles_y;
+      const int img = iblk * g.bn + n_l, yv = (tile - iblk * g.tiles_y) * g.bh + y_l, xv = x_l;
+      const bool valid = img < d.n_img;
+      int out_off;
+      if (d.out_mode == 3 || d.out_mode == 5) out_off = valid ? ((img * 3 * d.OH) + 2 * yv) * d.OW + 2 * xv : -1;
+      else out_off = valid ? ((img * d.OH + 2 * yv) * d.OW + 2 * xv) * d.ldc : -1;
+      if (want_stats) {
+        // all images of a tile belong to one group (checked by the launcher: rows_per_group % bn == 0)
+        const int grp = (iblk * g.bn) / d.bn_rows_per_group;
+        if (grp != stat_grp) {
+          stat_flush();
+          stat_grp = grp;
+        }
+      }
+      float2 bce_t[6], bce_m[6];
+      int bce_slot_now = -1;
+      if constexpr (BLOCK_N == 16) {
+        if (d.out_mode == 5 && valid) {
+          const int grp = img / d.bce_rows_per_group;
+          bce_slot_now = d.bce_slot[grp];
+          if (bce_slot_now >= 0) {
+            const int plane = d.OH * d.OW;
+            const int toff = (((img - grp * d.bce_rows_per_group) * 3) * d.OH + 2 * yv) * d.OW + 2 * xv;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int ph = 0; ph < 2; ++ph) {
+                bce_t[c * 2 + ph] = __ldg(reinterpret_cast<const float2*>(d.bce_target + toff + c * plane + ph * d.OW));
+                bce_m[c * 2 + ph] = d.bce_mask ? __ldg(reinterpret_cast<const float2*>(d.bce_mask + toff + c * plane +
+                                                                                       ph * d.OW))
+                                               : make_float2(1.0f, 1.0f);
+              }
+          }
+        }
+      }
+      const int acc = tl & 1;
+      mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS + (static_cast<uint32_t>(q4 * 32) << 16);
+      if constexpr (BLOCK_N == 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_d, v);
+        tmem_ld_wait(v);
+        if (out_off >= 0) {
+          float f[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
+          const int plane = d.OH * d.OW;
+          if (d.out_mode == 3 || (img >= d.logit_row_lo && img < d.logit_row_hi)) {
+            float* o = reinterpret_cast<float*>(d.out) + out_off;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int ph = 0; ph < 2; ++ph)
+                *reinterpret_cast<float2*>(o + c * plane + ph * d.OW) =
+                    make_float2(f[(ph * 2 + 0) * 3 + c], f[(ph * 2 + 1) * 3 + c]);
+          }
+          const int slot = bce_slot_now;
+          if (d.out_mode == 5 && slot >= 0) {
+            if (slot != bce_cur) {
+              bce_flush();
+              bce_cur = slot;
+            }
+            float gq[4][4];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int ph = 0; ph < 2; ++ph) {
+                const float2 tv = bce_t[c * 2 + ph], mv = bce_m[c * 2 + ph];
+                const float ts[2] = {tv.x, tv.y}, ms[2] = {mv.x, mv.y};
+#pragma unroll
+                for (int pw = 0; pw < 2; ++pw) {
+                  const float m = ms[pw], x = f[(ph * 2 + pw) * 3 + c] * m, tt = ts[pw] * m;
+                  const float e = __expf(-fabsf(x));
+                  const float rr = __fdividef(1.0f, 1.0f + e);
+                  bce_acc += fmaxf(x, 0.0f) - x * tt + __logf(1.0f + e);
+                  const float sig = x >= 0.0f ? rr : e * rr;
+                  gq[ph * 2 + pw][c] = d.bce_gscale * (sig - tt) * m;
+                }
+              }
+            if (d.bce_dlogits) {
+              __half* go = reinterpret_cast<__half*>(d.bce_dlogits);
+#pragma unroll
+              for (int ph = 0; ph < 2; ++ph) {
+                const long long pix =
+                    (static_cast<long long>(img) * (d.OH + 2) + 2 * yv + ph + 1) * (d.OW + 2) + 2 * xv + 1;
+                uint4* o4 = reinterpret_cast<uint4*>(go + pix * 8);
+#pragma unroll
+                for (int pw = 0; pw < 2; ++pw) {
+                  const float* q = gq[ph * 2 + pw];
+                  o4[pw] = make_uint4(pack_h2(q[0], q[1]), pack_h2(q[2], 0.0f), 0u, 0u);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // out_mode 4: n = phase * ldc + c.  Walk 16-channel chunks; inside a chunk the 4 phases, so that the
+        // BatchNorm partial sums of a channel chunk are reduced across the warp once per 4 phases.
+        const int Cc = d.ldc;
+        for (int c0 = 0; c0 < Cc; c0 += 16) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) s1[q] = s2[q] = 0.0f;
+          // one 16-channel chunk of sub-pixel phase ph: convert, store 32 bytes, accumulate the statistics
+          auto emit = [&](const uint32_t (&v)[16], const int ph) {
+            if (out_off < 0) return;
+            float f[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
+            __half* o = reinterpret_cast<__half*>(d.out) + out_off + ((ph >> 1) * d.OW + (ph & 1)) * Cc + c0;
+            const uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+            const uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
+                                        pack_h2(f[14], f[15]));
+            reinterpret_cast<uint4*>(o)[0] = u0;
+            reinterpret_cast<uint4*>(o)[1] = u1;
+            if (want_stats) {
+              // statistics of the values the BatchNorm kernels will read: the fp16-ROUNDED outputs
+              const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&uu[q]));
+                s1[2 * q] += a.x;
+                s2[2 * q] = fmaf(a.x, a.x, s2[2 * q]);
+                s1[2 * q + 1] += a.y;
+                s2[2 * q + 1] = fmaf(a.y, a.y, s2[2 * q + 1]);
+              }
+            }
+          };
+          uint32_t va[16], vb[16];
+          tmem_ld_x16(tmem_d + c0, va);
+          tmem_ld_wait(va);
+          tmem_ld_x16(tmem_d + Cc + c0, vb);
+          emit(va, 0);
+          tmem_ld_wait(vb);
+          tmem_ld_x16(tmem_d + 2 * Cc + c0, va);
+          emit(vb, 1);
+          tmem_ld_wait(va);
+          tmem_ld_x16(tmem_d + 3 * Cc + c0, vb);
+          emit(va, 2);
+          tmem_ld_wait(vb);
+          emit(vb, 3);
+          if (want_stats) {
+            // 32 values (16 sums, 16 sums of squares) over the warp's 32 rows: butterfly reduce-scatter, 31 shuffles;
+            // lane l ends with the total of value l (l < 16: sum of channel c0 + l; l >= 16: squares of c0 + l - 16)
+            float w[32];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              w[q] = s1[q];
+              w[16 + q] = s2[q];
+            }
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+              const int off = 16 >> st, cnt = 16 >> st;
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < cnt; ++j) {
+                const float mine = upper ? w[j + cnt] : w[j];
+                const float send = upper ? w[j] : w[j + cnt];
+                w[j] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            atomicAdd(&stat_s[(c0 + (lane & 15)) * 2 + (lane >> 4)], w[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[acc]));
+    }
+    if (d.out_mode == 5) bce_flush();
+    if (want_stats) stat_flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // wgrad: dW[n][k] += scale * sum_rows Nat[row][n] * G_gather[row][k]
 //   D tile = [128 k-columns (M)] x [CN channels (N)], reduction over rows in steps of 64.
@@ -1345,6 +1772,144 @@ int ilog2(int v) {
   return l;
 }
 
+template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG>
+int launch_patch(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW, const PatchGeom& g,
+                 cudaStream_t st) {
+  using C = PatchCfg<BLOCK_N, CIN_MODE, SA, W_KB>;
+  MMDYN_REQUIRE((d->Cin >= 64 ? d->Cin / 64 : 1) * g.w_bytes_cb <= C::W_BYTES,
+                "igemm patch_mode: %d bytes of live weights do not fit the resident region (%d)",
+                (d->Cin >= 64 ? d->Cin / 64 : 1) * g.w_bytes_cb, C::W_BYTES);
+  static bool configured = false;
+  if (!configured) {
+    MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  int occ = (228 * 1024) / (C::SMEM_BYTES + 1024 + 1024);
+  if (occ * 2 * C::TMEM_COLS > 512) occ = 512 / (2 * C::TMEM_COLS);
+  if (occ > 6) occ = 6;
+  if (occ < 1) occ = 1;
+  int grid = g_sm_count * occ;
+  if (grid > g.total_tiles) grid = g.total_tiles;
+  igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG><<<grid, 64 + 128 * EG, C::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
+// patch_mode launch: geometry checks, the two tensor maps (activations with dims (c, x, img, y); weights with a
+// box of one N-quarter), the tap schedule (centre tap first) and the live-quarter runs of every tap
+int igemm_patch(const mmdyn_igemm_desc* d, cudaStream_t st) {
+  const int IW = d->IW, IH = d->IH;
+  MMDYN_REQUIRE(d->s_in == 1 && d->n_phases == 1 && d->ksplit == 1 && d->row_mode == 0 && d->ntaps >= 9 &&
+                    d->OXv == IW && d->P == IH * IW && (IW == 8 || IW == 16 || IW == 32) && d->N == d->block_n &&
+                    (d->out_mode == 3 || d->out_mode == 4 || d->out_mode == 5) && d->bias == nullptr &&
+                    d->a_row_stride == 0 && d->a_img_stride == 0 && d->a_pix_stride == d->Cin,
+                "igemm patch_mode: unsupported geometry (s_in=%d ntaps=%d OXv=%d IW=%d IH=%d N=%d out_mode=%d)", d->s_in,
+                d->ntaps, d->OXv, IW, IH, d->N, d->out_mode);
+  for (int t = 0; t < 9; ++t)
+    MMDYN_REQUIRE(d->tap_dy[0][t] == t / 3 - 1 && d->tap_dx[0][t] == t % 3 - 1,
+                  "igemm patch_mode: taps 0..8 must be the 3x3 neighbourhood in row-major order");
+  const int cin_mode = (d->Cin % 64 == 0) ? 0 : (d->Cin == 32 ? 1 : -1);
+  MMDYN_REQUIRE(cin_mode >= 0, "igemm patch_mode: Cin=%d (multiple of 64, or 32)", d->Cin);
+  PatchGeom g = {};
+  const int bw = IW;
+  g.bh = 128 / bw < IH ? 128 / bw : IH;
+  g.bn = 128 / (bw * g.bh);
+  MMDYN_REQUIRE(g.bn >= 1 && bw * g.bh * g.bn == 128 && IH % g.bh == 0 && (g.bn & (g.bn - 1)) == 0,
+                "igemm patch_mode: tile %d x %d x %d", bw, g.bh, g.bn);
+  g.lbw = ilog2(bw);
+  g.lbn = ilog2(g.bn);
+  g.tiles_y = IH / g.bh;
+  g.img_blocks = (d->n_img + g.bn - 1) / g.bn;
+  g.total_tiles = g.img_blocks * g.tiles_y;
+  g.a_rows = (g.bh + 2) * g.bn * bw;
+  const int rb = cin_mode == 0 ? 128 : 64;
+  MMDYN_REQUIRE(g.a_rows * rb <= (cin_mode == 0 ? 20 * 1024 : 12 * 1024), "igemm patch_mode: activation box of %d rows", g.a_rows);
+  g.nq = d->out_mode == 4 ? 4 : 1;
+  MMDYN_REQUIRE(d->out_mode != 4 || (d->N == 4 * d->ldc && d->ldc % 16 == 0 && d->N >= 64),
+                "igemm patch_mode: out_mode 4 needs N = 4*ldc >= 64");
+  MMDYN_REQUIRE(d->out_mode == 4 || d->N == 16, "igemm patch_mode: out_mode 3 / 5 need N = 16");
+  if (d->bn_sums) {
+    MMDYN_REQUIRE(d->out_mode == 4 && d->ldc <= 64 && d->bn_rows_per_group > 0 && d->bn_rows_per_group % g.bn == 0,
+                  "igemm patch_mode: bn_sums needs out_mode 4, <= 64 channels and rows_per_group %% %d == 0", g.bn);
+  }
+  if (d->out_mode == 5) {
+    MMDYN_REQUIRE(d->bce_target && d->bce_loss && d->bce_rows_per_group > 0 &&
+                      d->n_img <= MMDYN_MAX_GROUPS * d->bce_rows_per_group && g.bn == 1,
+                  "igemm patch_mode: out_mode 5 arguments");
+  }
+  // tap schedule (tap_sched: shared with the kernel's unrolled MMA loop)
+  const int nq_bytes = (d->N / g.nq) * rb;  // one weight block: N / nq rows of one k-block
+  int w_off = 0;
+  for (int ti = 0; ti < 9; ++ti) {
+    const TapSched ts = tap_sched(g.nq == 4, ti);
+    g.tap_k[ti] = static_cast<int8_t>((ts.dy + 1) * 3 + (ts.dx + 1));
+    g.tap_dyv[ti] = static_cast<int8_t>(ts.dy);
+    g.tap_dxv[ti] = static_cast<int8_t>(ts.dx);
+    g.nruns[ti] = static_cast<int8_t>(ts.nruns);
+    unsigned mask = 0;
+    for (int r = 0; r < ts.nruns; ++r) {
+      g.run_q0[ti][r] = static_cast<int8_t>(ts.q0[r]);
+      g.run_len[ti][r] = static_cast<int8_t>(ts.len[r]);
+      g.run_off[ti][r] = ts.blk[r] * nq_bytes;
+      for (int q = 0; q < ts.len[r]; ++q) mask |= 1u << (ts.q0[r] + q);
+      w_off += ts.len[r] * nq_bytes;
+    }
+    g.qmask[ti] = static_cast<uint8_t>(mask);
+  }
+  g.w_bytes_cb = w_off;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_last_error("igemm: cuTensorMapEncodeTiled driver entry point not available");
+    return MMDYN_ERR_CUDA;
+  }
+  CUtensorMap tmA, tmW;
+  {
+    const cuuint64_t dim[4] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(IW),
+                               static_cast<cuuint64_t>(d->n_img), static_cast<cuuint64_t>(IH)};
+    const cuuint64_t pix_b = static_cast<cuuint64_t>(d->Cin) * 2;
+    const cuuint64_t str[3] = {pix_b, pix_b * IW * IH, pix_b * IW};  // x, image, y
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(cin_mode == 0 ? 64 : 32), static_cast<cuuint32_t>(bw),
+                               static_cast<cuuint32_t>(g.bn), static_cast<cuuint32_t>(g.bh + 2)};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), dim, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           cin_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("igemm patch_mode: cuTensorMapEncodeTiled(A) failed with CUresult %d", static_cast<int>(r));
+      return MMDYN_ERR_CUDA;
+    }
+  }
+  {
+    const int ktot = d->ntaps * d->Cin;
+    const cuuint64_t dim[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(d->N)};
+    const cuuint64_t str[1] = {static_cast<cuuint64_t>(ktot) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(cin_mode == 0 ? 64 : 32), static_cast<cuuint32_t>(d->N / g.nq)};
+    const cuuint32_t es[2] = {1, 1};
+    const CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->W), dim, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           cin_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("igemm patch_mode: cuTensorMapEncodeTiled(W) failed with CUresult %d", static_cast<int>(r));
+      return MMDYN_ERR_CUDA;
+    }
+  }
+  if (cin_mode == 1) {
+    MMDYN_REQUIRE(d->N == 16, "igemm patch_mode: Cin = 32 is the logits layer (N = 16)");
+    return launch_patch<16, 1, 4, 9, 1>(d, tmA, tmW, g, st);   // 9 KB of weights, 4 x 12 KB patches: 3-4 CTAs per SM
+  }
+  switch (d->N) {
+    case 64: return launch_patch<64, 0, 6, 64, 2>(d, tmA, tmW, g, st);
+    case 128: return launch_patch<128, 0, 7, 64, 2>(d, tmA, tmW, g, st);  // 64 KB of weights + 7 x 20 KB patches, 1 CTA per SM
+    default: break;
+  }
+  set_last_error("igemm patch_mode: N=%d unsupported", d->N);
+  return MMDYN_ERR_ARG;
+}
+
 template <int BLOCK_N>
 int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, int m_tiles, int n_tiles, int total_tiles,
                  int occ, cudaStream_t st) {
@@ -1502,6 +2067,7 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
   MMDYN_REQUIRE(d->a_row_stride % 8 == 0 && d->a_img_stride % 8 == 0 && d->a_row_stride >= 0 && d->a_img_stride >= 0,
                 "igemm: a_row_stride / a_img_stride must be non-negative multiples of 8 elements");
 
+  if (d->patch_mode) return igemm_patch(d, static_cast<cudaStream_t>(stream));
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_last_error("igemm: cuTensorMapEncodeTiled driver entry point not available");

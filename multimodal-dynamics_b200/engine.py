@@ -336,12 +336,15 @@ class _NetBase:
         self.packer.refresh(self.arena)
 
 
-def _ig(pl, which, A, out, n_img, bias=None, f32_out=False, bce=None):
-    """One implicit-GEMM launch of layer `pl` ('fwd' or 'dgrad'); fp32 outputs may split K."""
+def _ig(pl, which, A, out, n_img, bias=None, f32_out=False, bce=None, stats=None):
+    """One implicit-GEMM launch of layer `pl` ('fwd' or 'dgrad'); fp32 outputs may split K.
+    stats = (sums, images per group): BatchNorm statistics of the output in the epilogue (patch kernel)."""
     geom, W = (pl.lp.fwd, pl.Wf) if which == "fwd" else (pl.lp.dgrad, pl.Wd)
     kw = dict(tag=f"{pl.lp.name}.{which}", macs_per_img=pl.lp.extra.get("macs"))
     if bce is not None:
         kw["bce"] = bce
+    if stats is not None:
+        kw["stats"] = stats
     ks = plan.choose_ksplit(geom, n_img) if f32_out else 1
     if ks > 1:
         out.zero_()
@@ -396,11 +399,13 @@ class _BN:
         return (alloc(key + ".sums", (G, C, 2), F32, zero="step"), alloc(key + ".ab", (G, C, 2), F32),
                 alloc(key + ".mi", (G, C, 2), F32))
 
-    def run_fwd(self, raw, act, Gc, rows, st, g0, track, repeat=1):
-        """Groups g0 .. g0+Gc-1: `raw` / `act` hold exactly these groups' rows, `st` = alloc_fwd(...) of all groups."""
+    def run_fwd(self, raw, act, Gc, rows, st, g0, track, repeat=1, have_stats=False):
+        """Groups g0 .. g0+Gc-1: `raw` / `act` hold exactly these groups' rows, `st` = alloc_fwd(...) of all groups.
+        have_stats: `sums` was already filled by the epilogue of the GEMM that produced `raw`."""
         net, C = self.net, self.C
         sums, ab, mi = (t[g0:g0 + Gc] for t in st)
-        ops.bn_stats(raw, sums, Gc, rows, C)
+        if not have_stats:
+            ops.bn_stats(raw, sums, Gc, rows, C)
         rm = net.buf(self.name + ".running_mean") if track else None
         rv = net.buf(self.name + ".running_var") if track else None
         nbt = net.buf(self.name + ".num_batches_tracked") if track else None
@@ -602,10 +607,14 @@ class DecoderExec(_NetBase):
             ops.bn_swish_fwd(raw0[sl], None, act0[sl], 1, n * 25, 256)
             _ig(self.d1, "fwd", act0[sl], raw1[sl], n)
             self.bn1.run_fwd(raw1[sl], act1[sl], Gc, B * 64, s1, g0, track)
-            _ig(self.d2, "fwd", act1[sl], raw2[sl], n)
-            self.bn2.run_fwd(raw2[sl], act2[sl], Gc, B * 256, s2, g0, track)
-            _ig(self.d3, "fwd", act2[sl], raw3[sl], n)
-            self.bn3.run_fwd(raw3[sl], act3[sl], Gc, B * 1024, s3, g0, track)
+            # BatchNorm statistics of raw2 / raw3 come out of the producing GEMM's epilogue (patch kernel);
+            # a tile of the 8x8 layer holds two images, which must belong to one group
+            f2 = bool(self.fuse_stats and self.d2.lp.fwd.patch and B % 2 == 0)
+            f3 = bool(self.fuse_stats and self.d3.lp.fwd.patch)
+            _ig(self.d2, "fwd", act1[sl], raw2[sl], n, stats=(s2[0][g0:g0 + Gc], B) if f2 else None)
+            self.bn2.run_fwd(raw2[sl], act2[sl], Gc, B * 256, s2, g0, track, have_stats=f2)
+            _ig(self.d3, "fwd", act2[sl], raw3[sl], n, stats=(s3[0][g0:g0 + Gc], B) if f3 else None)
+            self.bn3.run_fwd(raw3[sl], act3[sl], Gc, B * 1024, s3, g0, track, have_stats=f3)
             if fused_loss is not None:
                 fl = fused_loss
                 lo, hi = fl["logit_groups"]
@@ -624,6 +633,7 @@ class DecoderExec(_NetBase):
         return r
 
     after_group = None  # optional callback(g0, Gc, logits_rows) run right after a group chunk's logits (fused losses)
+    fuse_stats = os.environ.get("MMDYN_NO_FUSED_STATS") is None  # BatchNorm sums in the deconv2/3 epilogues
 
     def backward(self, r, dl8, alloc, key, unscale, gp=None):
         """dl8: (G*B, 66, 66, 8) fp16 logit gradients with a one-pixel ZERO border (3 channels used, times grad_scale).

@@ -35,6 +35,7 @@ class IgemmDesc(C.Structure):
         ("bce_target", C.c_void_p), ("bce_mask", C.c_void_p), ("bce_dlogits", C.c_void_p), ("bce_loss", C.c_void_p),
         ("bce_gscale", C.c_float), ("bce_rows_per_group", C.c_int32), ("bce_slot", C.c_int32 * MAX_GROUPS),
         ("logit_row_lo", C.c_int32), ("logit_row_hi", C.c_int32),
+        ("patch_mode", C.c_int32), ("bn_rows_per_group", C.c_int32), ("bn_sums", C.c_void_p),
     ]
 
 

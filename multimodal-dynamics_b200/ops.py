@@ -101,7 +101,7 @@ def _esz(t):
 
 
 def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None, a_pix_stride=None, tag="igemm",
-          macs_per_img=None, bce=None):
+          macs_per_img=None, bce=None, stats=None):
     """bce (out_mode 5, the logits layer with its loss fused): dict(target, mask, dlogits, loss, gscale,
     rows_per_group, slots=[loss index per group or -1], logit_rows=(lo, hi))."""
     d = IgemmDesc()
@@ -120,6 +120,10 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     d.OH, d.OW, d.s_out = geom.OH, geom.OW, geom.s_out
     d.ldc = geom.ldc if ldc is None else ldc
     d.a_row_stride, d.a_img_stride = geom.a_row_stride, geom.a_img_stride
+    d.patch_mode = int(getattr(geom, "patch", 0))
+    if stats is not None:  # (sums [G][C][2] fp32 zeroed, images per group): BatchNorm statistics in the epilogue
+        assert d.patch_mode and d.out_mode == 4
+        d.bn_sums, d.bn_rows_per_group = stats[0].data_ptr(), int(stats[1])
     if bce is not None:
         d.out_mode = 5
         d.bce_target, d.bce_mask = bce["target"].data_ptr(), _ptr(bce.get("mask"))

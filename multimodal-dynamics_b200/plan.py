@@ -25,6 +25,9 @@ MAX_TAPS = 16
 # run the 4 sub-pixel phases of stride-2 (de)convs as one GEMM (see _merged_geom); MMDYN_MERGE_PHASES=0
 # keeps them as 4 phase GEMMs of 4 taps each (no zero-weight MMAs, 16 operand boxes instead of 9)
 MERGE_PHASES = os.environ.get("MMDYN_MERGE_PHASES", "1") != "0"
+# merged 3x3-tap layers on the patch-reuse kernel (one activation box per filter column, live weight blocks
+# only); MMDYN_NO_PATCH=1 keeps them on the generic one-box-per-tap kernel (A/B measurements)
+USE_PATCH = os.environ.get("MMDYN_NO_PATCH") is None
 
 
 @dataclass
@@ -49,6 +52,7 @@ class GemmGeom:
     a_pix_stride: Optional[int] = None
     a_row_stride: int = 0     # 0 = dense; see include/mmdyn_b200.h (overlapping-window operands)
     a_img_stride: int = 0
+    patch: int = 0            # 1: merged 3x3-tap layer -> shared-memory patch reuse kernel (mmdyn_igemm patch_mode)
 
     @property
     def ntaps(self):
@@ -162,7 +166,9 @@ def _merged_geom(Hv, Cg, Cn_out, widx_fn):
     rows instead of 16 — these layers are operand-feed bound, the extra (zero-weight) MACs are free."""
     geom = GemmGeom(P=Hv * Hv, OXv=Hv, IH=Hv, IW=Hv, Cin=Cg, s_in=1, tap_dy=[[t[0] for t in TAPS3]],
                     tap_dx=[[t[1] for t in TAPS3]], N=4 * Cn_out, OH=2 * Hv, OW=2 * Hv, s_out=2, off_y=[0],
-                    off_x=[0], ldc=Cn_out, out_mode=4)
+                    off_x=[0], ldc=Cn_out, out_mode=4,
+                    patch=int(USE_PATCH and Hv in (8, 16, 32) and (Cg % 64 == 0) and 4 * Cn_out in (64, 128)
+                              and 16 * Cn_out * 128 * (Cg // 64) <= 64 * 1024))  # live weight blocks stay resident
     idx = np.full((4 * Cn_out, 9 * Cg), -1, np.int32)
     for ph in (0, 1):
         for pw in (0, 1):
@@ -290,7 +296,7 @@ def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
     kof = {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}}  # phase parity -> {input offset: kernel index}
     fwd = GemmGeom(P=H * H, OXv=H, IH=H, IW=H, Cin=Cin, s_in=1, tap_dy=[[t[0] for t in taps]],
                    tap_dx=[[t[1] for t in taps]], N=16, OH=Ho, OW=Ho, s_out=2, off_y=[0], off_x=[0],
-                   ldc=0, out_mode=3)
+                   ldc=0, out_mode=3, patch=int(USE_PATCH and H == 32 and Cin == 32))
     idx_fwd = np.full((16, len(taps) * Cin), -1, np.int32)
     for ph in (0, 1):
         for pw in (0, 1):
