@@ -416,25 +416,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-// NCTA = 2 (A_MODE 0, BLOCK_N >= 128): CTA pairs.  The two CTAs of a cluster take the tiles 2q and 2q+1
-// (same weight tile: the launcher guarantees an even m-tile count), each loads its own 128 activation
-// rows and HALF of the weight tile, and the leader issues ONE tcgen05.mma.cta_group::2 (M = 256) per
-// K = 16 step.  Per SM and 64-wide k-block this halves the weight bytes TMA writes into and the tensor
-// core reads from shared memory: with cta_group::1 the 128 x 256 tile needs 183 B/clk/SM of
-// shared-memory bandwidth (TMA fill 48 KB + operand reads 48 KB per 524 MMA clocks) against the 128 B/clk
-// an SM has, which is what held the N >= 128 layers at 42-62 % tensor-pipe activity.
-template <int BLOCK_N, int A_MODE, int NCTA>
+// The per-k-block loops are kept free of integer divisions and table walks: the producer tracks (tap, channel
+// block) incrementally, and for pixel-major tiles all three roles derive ONE live-tap bit mask per tile (a tap
+// whose input pixel falls outside the image is skipped, not multiplied by zeros) — evaluating that test with
+// its divisions per k-block in both the producer and the MMA issuer cost as much as a live k-block's MMAs on
+// the 5x5 <-> 8x8 layers (ncu source view, round 2).  Producer and MMA issuer run under elect.sync.
+template <int BLOCK_N, int A_MODE>
 __global__ void __launch_bounds__(TMA_THREADS)
 igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmW, const TileGeom g) {
   using C = Cfg<BLOCK_N>;
-  static_assert(NCTA == 1 || (A_MODE == 0 && BLOCK_N >= 128), "CTA pairs: A_MODE 0, BLOCK_N 128 / 256 only");
-  constexpr int B_LOAD_BYTES = C::B_STAGE_BYTES / NCTA;  // weight rows this CTA loads per k-block
-  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
-  // tiles of this CTA: first, stride (pairs walk tile pairs)
-  const int tile0 = NCTA == 2 ? 2 * (static_cast<int>(blockIdx.x) >> 1) + static_cast<int>(cta_rank)
-                              : static_cast<int>(blockIdx.x);
-  const int tile_step = NCTA == 2 ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x);
+  const int tile0 = static_cast<int>(blockIdx.x);
+  const int tile_step = static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
@@ -454,126 +447,130 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 128 * NCTA);  // pairs: both CTAs' epilogues free the leader's MMA
+      mbar_init(smem_u32(&tempty_bar[a]), 128);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1) {
-    if (NCTA == 2) {
-      tmem_alloc2(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
-      tmem_relinquish2();
-    } else {
-      tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
-      tmem_relinquish();
-    }
+    tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
   const int kb_total = (d.ntaps * d.Cin) >> 6;
   const int kb_per = (kb_total + d.ksplit - 1) / d.ksplit;
-  // pixel-major tiles share the virtual pixel: a k-block whose tap(s) fall outside the image is skipped
-  auto kb_live = [&](const TileCoord2& t, int kb) -> bool {
-    if (!g.pixel_major || A_MODE != 0) return true;
-    const int tap = (kb << 6) / d.Cin;
-    const int iy = t.y0 * d.s_in + d.tap_dy[t.phase][tap];
-    const int ix = t.x0 * d.s_in + d.tap_dx[t.phase][tap];
-    return (unsigned)iy < (unsigned)d.IH && (unsigned)ix < (unsigned)d.IW;
+  const int CB = A_MODE == 0 ? (d.Cin >> 6) : 1;  // 64-channel blocks per tap (A_MODE 0)
+  // (linear layers are pixel-major tiles with one tap that is always live, and may split K across CTAs)
+  const bool skip_taps = g.pixel_major && A_MODE == 0 && d.ksplit == 1 && d.ntaps > 1;
+  // pixel-major tiles share the virtual pixel: bit t = tap t reads a pixel inside the image
+  auto live_taps = [&](const TileCoord2& t) -> uint32_t {
+    if (!skip_taps) return 0xFFFFFFFFu;
+    uint32_t m = 0;
+    const int by = t.y0 * d.s_in, bx = t.x0 * d.s_in;
+    for (int tap = 0; tap < d.ntaps; ++tap) {
+      const int iy = by + d.tap_dy[t.phase][tap], ix = bx + d.tap_dx[t.phase][tap];
+      if ((unsigned)iy < (unsigned)d.IH && (unsigned)ix < (unsigned)d.IW) m |= 1u << tap;
+    }
+    return m;
+  };
+  // k-blocks of a tile that are actually loaded and multiplied (row_mode 1 implies ksplit 1)
+  auto live_kbs = [&](const TileCoord2& t) -> int {
+    if (skip_taps) return __popc(live_taps(t)) * CB;
+    const int kb_begin = t.split * kb_per;
+    return min(kb_total, kb_begin + kb_per) - kb_begin;
   };
 
   if (warp == 0) {
     // ======================= TMA producer =====================================================
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int tile = tile0; tile < g.total_tiles; tile += tile_step) {
         const TileCoord2 t = decode_tile2(d, g, tile);
         const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
         const int wx = t.x0 * d.s_in, wy = t.y0 * d.s_in;
+        const uint32_t mask = live_taps(t);
+        const int w_row = t.phase * d.N + t.n_tile * BLOCK_N;
+        int tap = A_MODE == 0 ? kb_begin / CB : 0, cb = A_MODE == 0 ? kb_begin - tap * CB : 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (!kb_live(t, kb)) continue;
+          bool live = true;
+          int tdx = 0, tdy = 0, c0 = 0;
+          if (A_MODE == 0) {
+            live = (mask >> tap) & 1u;
+            tdx = d.tap_dx[t.phase][tap];
+            tdy = d.tap_dy[t.phase][tap];
+            c0 = cb << 6;
+            if (++cb == CB) {
+              cb = 0;
+              ++tap;
+            }
+          }
+          if (!live) continue;
           const int s = it % C::STAGES;
           mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
           const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
-          if constexpr (NCTA == 2) {
-            // every byte of the pair's stage is accounted on the LEADER's full barrier: the leader expects
-            // both CTAs' bytes, the peer's TMA completions may arrive first (transiently negative tx-count)
-            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[s]), 0);
-            if (cta_rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2 * (A_STAGE_BYTES + B_LOAD_BYTES));
-            const int k = kb << 6;
-            const int tap = k / d.Cin, c0 = k - tap * d.Cin;
-            tma_load_4d_2cta(a_stage, &tmA, lbar, c0, wx + d.tap_dx[t.phase][tap], wy + d.tap_dy[t.phase][tap], t.img0);
-            tma_load_2d_2cta(a_stage + A_STAGE_BYTES, &tmW, lbar, kb << 6,
-                             t.phase * d.N + t.n_tile * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
-            ++it;
-            continue;
-          }
           const uint32_t bar = smem_u32(&full_bar[s]);
           mbar_arrive_expect_tx(bar, A_STAGE_BYTES + C::B_STAGE_BYTES);
           if (A_MODE == 0) {
-            const int k = kb << 6;
-            const int tap = k / d.Cin, c0 = k - tap * d.Cin;
-            tma_load_4d(a_stage, &tmA, bar, c0, wx + d.tap_dx[t.phase][tap], wy + d.tap_dy[t.phase][tap], t.img0);
+            tma_load_4d(a_stage, &tmA, bar, c0, wx + tdx, wy + tdy, t.img0);
           } else if (A_MODE == 1) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-              const int tap = 2 * kb + b;
-              tma_load_4d(a_stage + b * 8192, &tmA, bar, 0, wx + d.tap_dx[t.phase][tap],
-                          wy + d.tap_dy[t.phase][tap], t.img0);
+              const int tp = 2 * kb + b;
+              tma_load_4d(a_stage + b * 8192, &tmA, bar, 0, wx + d.tap_dx[t.phase][tp], wy + d.tap_dy[t.phase][tp], t.img0);
             }
           } else {
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
-              const int tap = 8 * kb + b;
-              tma_load_4d(a_stage + b * 2048, &tmA, bar, 0, wx + d.tap_dx[t.phase][tap],
-                          wy + d.tap_dy[t.phase][tap], t.img0);
+              const int tp = 8 * kb + b;
+              tma_load_4d(a_stage + b * 2048, &tmA, bar, 0, wx + d.tap_dx[t.phase][tp], wy + d.tap_dy[t.phase][tp], t.img0);
             }
           }
-          tma_load_2d(a_stage + A_STAGE_BYTES, &tmW, bar, kb << 6, t.phase * d.N + t.n_tile * BLOCK_N);
+          tma_load_2d(a_stage + A_STAGE_BYTES, &tmW, bar, kb << 6, w_row);
           ++it;
         }
       }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer ======================================================
-    if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128 * NCTA, BLOCK_N, 0, 0, 0, 0);
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 0, 0, 0, 0);
+      // descriptor = HI | (address >> 4); B: 128B swizzle, 8-row atoms of 1024 B
+      constexpr uint64_t B_HI = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(LAYOUT_SW128) << 61);
+      constexpr uint64_t A_HI = A_MODE == 0 ? B_HI
+                                : A_MODE == 1 ? ((static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(512 >> 4) << 32) |
+                                                 (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(LAYOUT_SW64) << 61))
+                                              : ((static_cast<uint64_t>(2048 >> 4) << 16) | (static_cast<uint64_t>(128 >> 4) << 32) |
+                                                 (static_cast<uint64_t>(1) << 46));
       int it = 0, tl = 0;
       for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++tl) {
         const TileCoord2 t = decode_tile2(d, g, tile);
+        const int n_kb = live_kbs(t);
         const int acc = tl & 1;
         mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS;
-        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
-        int first = 1;
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (!kb_live(t, kb)) continue;
+        for (int i = 0; i < n_kb; ++i) {
           const int s = it % C::STAGES;
           mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
           tc_fence_after();
-          const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
-          const uint64_t bdesc = make_smem_desc(a_base + A_STAGE_BYTES, 16, 1024, LAYOUT_SW128);
+          const uint32_t a16 = (smem_base + s * C::STAGE_BYTES) >> 4;
+          const uint32_t b16 = a16 + (A_STAGE_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16) per 64-wide k-block
-            uint64_t adesc;
-            if (A_MODE == 0) adesc = make_smem_desc(a_base + 32 * kk, 16, 1024, LAYOUT_SW128);
-            else if (A_MODE == 1) adesc = make_smem_desc(a_base + (kk >> 1) * 8192 + (kk & 1) * 32, 16, 512, LAYOUT_SW64);
-            else adesc = make_smem_desc(a_base + kk * 4096, 2048, 128, 0);
-            if (NCTA == 2) umma_f16_2cta(tmem_d, adesc, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
-            else umma_f16(tmem_d, adesc, bdesc + 2 * kk, idesc, (first && kk == 0) ? 0u : 1u);
+            const uint32_t a_off = A_MODE == 0 ? 2 * kk : (A_MODE == 1 ? (kk >> 1) * (8192 >> 4) + (kk & 1) * 2 : kk * (4096 >> 4));
+            umma_f16(tmem_d, A_HI | static_cast<uint64_t>(a16 + a_off), B_HI | static_cast<uint64_t>(b16 + 2 * kk), idesc,
+                     (i | kk) ? 1u : 0u);
           }
-          first = 0;
-          if (NCTA == 2) umma_commit_2cta(smem_u32(&empty_bar[s]));  // frees the stage in both CTAs
-          else umma_commit(smem_u32(&empty_bar[s]));
+          umma_commit(smem_u32(&empty_bar[s]));
           ++it;
         }
-        if (NCTA == 2) umma_commit_2cta(smem_u32(&tfull_bar[acc]));
-        else umma_commit(smem_u32(&tfull_bar[acc]));
+        umma_commit(smem_u32(&tfull_bar[acc]));
       }
     }
   } else {
@@ -609,13 +606,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
         const int oy = yv * d.s_out + d.off_y[t.phase], ox = xv * d.s_out + d.off_x[t.phase];
         out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
       }
-      int n_live = 0;
-      {
-        const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
-        if (!g.pixel_major || A_MODE != 0) n_live = kb_end - kb_begin;
-        else
-          for (int kb = kb_begin; kb < kb_end; ++kb) n_live += kb_live(t, kb) ? 1 : 0;
-      }
+      const int n_live = live_kbs(t);
       // out_mode 5: the targets (and mask) of this thread's 2x2x3 output pixels depend on the tile
       // coordinates only, so they are requested BEFORE waiting for the accumulator: their latency
       // hides behind the tile's MMAs instead of serialising the epilogue
@@ -775,19 +766,15 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
         }
       }
       tc_fence_before();
-      // accumulator stage free for tile tl + 2 (pairs: the leader's MMA waits for both CTAs' epilogues)
-      if (NCTA == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
-      else mbar_arrive(smem_u32(&tempty_bar[acc]));
+      mbar_arrive(smem_u32(&tempty_bar[acc]));  // accumulator stage free for tile tl + 2
     }
     if (d.out_mode == 5) bce_flush();
   }
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all();  // the peer's shared memory / barriers / TMEM stay valid until both are done
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (NCTA == 2) tmem_dealloc2(tmem_base, 2 * C::TMEM_COLS);
-    else tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
+    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
   }
 }
 
@@ -875,7 +862,7 @@ struct PatchCfg {
 };
 
 template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG>
-__global__ void __launch_bounds__(64 + 128 * EG, 1)
+__global__ void __launch_bounds__(64 + 128 * EG, BLOCK_N == 16 ? 2 : 1)
 igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ PatchGeom g) {
   using C = PatchCfg<BLOCK_N, CIN_MODE, SA, W_KB>;
@@ -1440,22 +1427,61 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
   constexpr int NAT_BYTES = 64 * CN * 2;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
+      // operand-box coordinates that do not depend on the step: taps / channel offsets of this CTA's k-columns
+      int tdx[16], tdy[16], tc0[2];
+#pragma unroll
+      for (int b = 0; b < 16; ++b) tdx[b] = tdy[b] = 0;
+      if (G_MODE == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int k = kcol0 + b * 64;
+          const int tap = k / d.Cg;
+          tc0[b] = k - tap * d.Cg;
+          tdx[b] = d.tap_dx[tap];
+          tdy[b] = d.tap_dy[tap];
+        }
+      } else if (G_MODE == 1) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          tdx[b] = d.tap_dx[(kcol0 >> 5) + b];
+          tdy[b] = d.tap_dy[(kcol0 >> 5) + b];
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          tdx[b] = d.tap_dx[(kcol0 >> 3) + b];
+          tdy[b] = d.tap_dy[(kcol0 >> 3) + b];
+        }
+      }
+      // step -> (outer, inner) without a division per step: pixel-major (pixel, image block), else (image block, row tile)
+      const int inner_n = g.pixel_major ? g.img_blocks : g.tiles_y;
+      int outer = step_begin / inner_n, inner = step_begin - outer * inner_n;
+      int py = 0, px = 0;
+      if (g.pixel_major) {
+        py = outer / d.OXv;
+        px = outer - py * d.OXv;
+      }
       for (int it = 0; it < n_steps; ++it) {
         const int s = it % C::STAGES;
         mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
-        const int step = step_begin + it;
         int img0, y0, x0;
         if (g.pixel_major) {
-          const int pix = step / g.img_blocks;
-          img0 = (step - pix * g.img_blocks) * 64;
-          y0 = pix / d.OXv;
-          x0 = pix - y0 * d.OXv;
+          img0 = inner * 64;
+          y0 = py;
+          x0 = px;
         } else {
-          const int ib = step / g.tiles_y;
-          img0 = ib * g.bn;
-          y0 = (step - ib * g.tiles_y) << g.lbh;
+          img0 = outer * g.bn;
+          y0 = inner << g.lbh;
           x0 = 0;
+        }
+        if (++inner == inner_n) {
+          inner = 0;
+          ++outer;
+          if (g.pixel_major && ++px == d.OXv) {
+            px = 0;
+            ++py;
+          }
         }
         const uint32_t bar = smem_u32(&full_bar[s]);
         const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
@@ -1464,23 +1490,13 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
         const int wx = x0 * d.s_in, wy = y0 * d.s_in;
         if (G_MODE == 0) {
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int k = kcol0 + b * 64;
-            const int tap = k / d.Cg, c0 = k - tap * d.Cg;
-            tma_load_4d(a_stage + b * 8192, &tmG, bar, c0, wx + d.tap_dx[tap], wy + d.tap_dy[tap], img0);
-          }
+          for (int b = 0; b < 2; ++b) tma_load_4d(a_stage + b * 8192, &tmG, bar, tc0[b], wx + tdx[b], wy + tdy[b], img0);
         } else if (G_MODE == 1) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int tap = (kcol0 >> 5) + b;
-            tma_load_4d(a_stage + b * 4096, &tmG, bar, 0, wx + d.tap_dx[tap], wy + d.tap_dy[tap], img0);
-          }
+          for (int b = 0; b < 4; ++b) tma_load_4d(a_stage + b * 4096, &tmG, bar, 0, wx + tdx[b], wy + tdy[b], img0);
         } else {
 #pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            const int tap = (kcol0 >> 3) + b;
-            tma_load_4d(a_stage + b * 1024, &tmG, bar, 0, wx + d.tap_dx[tap], wy + d.tap_dy[tap], img0);
-          }
+          for (int b = 0; b < 16; ++b) tma_load_4d(a_stage + b * 1024, &tmG, bar, 0, wx + tdx[b], wy + tdy[b], img0);
         }
         if (CN >= 64) {
 #pragma unroll
@@ -1491,7 +1507,7 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(128, CN, 0, 0, 1, 1);
       constexpr uint32_t b_layout = CN >= 64 ? LAYOUT_SW128 : (CN == 32 ? LAYOUT_SW64 : LAYOUT_SW32);
       constexpr uint32_t b_sbo = CN >= 64 ? 1024 : (CN == 32 ? 512 : 256);  // 8 reduction rows of the tile
@@ -1712,32 +1728,9 @@ int launch_igemm_tma(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CU
                      int occ, cudaStream_t st) {
   int grid = g_sm_count * occ;
   if (grid > g.total_tiles) grid = g.total_tiles;
-  igemm_tma_kernel<BLOCK_N, A_MODE, 1><<<grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
+  igemm_tma_kernel<BLOCK_N, A_MODE><<<grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
-  return MMDYN_OK;
-}
-
-// CTA pairs (clusters of 2): tmW_half has a box of BLOCK_N / 2 weight rows; total_tiles is even
-template <int BLOCK_N>
-int launch_igemm_tma_pair(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW_half,
-                          const TileGeom& g, int occ, cudaStream_t st) {
-  int pairs = (g_sm_count / 2) * occ;
-  if (pairs > g.total_tiles / 2) pairs = g.total_tiles / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.blockDim = dim3(TMA_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = Cfg<BLOCK_N>::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  MMDYN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, igemm_tma_kernel<BLOCK_N, 0, 2>, *d, tmA, tmW_half, g));
-  g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return MMDYN_OK;
 }
 
@@ -1899,7 +1892,7 @@ int igemm_patch(const mmdyn_igemm_desc* d, cudaStream_t st) {
   }
   if (cin_mode == 1) {
     MMDYN_REQUIRE(d->N == 16, "igemm patch_mode: Cin = 32 is the logits layer (N = 16)");
-    return launch_patch<16, 1, 4, 9, 1>(d, tmA, tmW, g, st);   // 9 KB of weights, 4 x 12 KB patches: 3-4 CTAs per SM
+    return launch_patch<16, 1, 6, 9, 2>(d, tmA, tmW, g, st);   // 9 KB of weights, 6 x 12 KB patches, 2 CTAs per SM x 8 epilogue warps
   }
   switch (d->N) {
     case 64: return launch_patch<64, 0, 6, 64, 2>(d, tmA, tmW, g, st);
@@ -1959,13 +1952,13 @@ int igemm_init() {
   OCC(4, igemm_kernel<256>, Cfg<256>::SMEM_BYTES);
 #undef OCC
 #define SET_TMA(I, BN)                                                                                        \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0, 1>,      \
+  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0>,      \
                                                                 TMA_THREADS, Cfg<BN>::SMEM_BYTES));          \
   if (g_tma_occ[I] < 1) g_tma_occ[I] = 1
   SET_TMA(0, 16);
@@ -1974,10 +1967,6 @@ int igemm_init() {
   SET_TMA(3, 128);
   SET_TMA(4, 256);
 #undef SET_TMA
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<128, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<128>::SMEM_BYTES));
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<256, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<256>::SMEM_BYTES));
 #define SET_WG(CN)                                                                                            \
   MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<CN>::SMEM_BYTES));                                               \
@@ -2149,28 +2138,6 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     MMDYN_REQUIRE(d->out_mode != 5 || (g.bn == 1 && !g.pixel_major),
                   "igemm: out_mode 5 needs tiles that lie within one image (OXv=%d P=%d)", d->OXv, d->P);
     const int occ = g_tma_occ[occ_idx];
-    // CTA pairs (cta_group::2) for the wide layers: tiles 2q / 2q+1 must share their weight tile (even
-    // m-tile count) and, in pixel-major mode, their virtual pixel (same live taps)
-    // OPT-IN experiment (MMDYN_IGEMM_PAIRS=1): bit-identical to the single-CTA path on every layer, but not
-    // faster (the N >= 128 layers are bound by pipeline depth / operand latency, not by shared-memory
-    // bandwidth) and it can DEADLOCK when two pairs share a TPC next to single-CTA tcgen05 kernels of
-    // another stream (the paired TMEM allocation is not atomic across the two SMs) — see DESIGN.md §11.
-    static const bool no_pairs = getenv("MMDYN_IGEMM_PAIRS") == nullptr;
-    if (!no_pairs && a_mode == 0 && d->block_n >= 128 && (g.m_tiles % 2) == 0 &&
-        (!g.pixel_major || (g.img_blocks % 2) == 0) && g.total_tiles >= 2 &&
-        (d->out_mode == 0 || d->out_mode == 1 || d->out_mode == 2 || d->out_mode == 4)) {
-      CUtensorMap tmh;
-      const cuuint32_t hbox[2] = {64, static_cast<cuuint32_t>(d->block_n / 2)};
-      const CUresult hr = enc(&tmh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d->W), gdim, gstr, hbox, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (hr != CUDA_SUCCESS) {
-        set_last_error("igemm: cuTensorMapEncodeTiled(W half) failed with CUresult %d", static_cast<int>(hr));
-        return MMDYN_ERR_CUDA;
-      }
-      return d->block_n == 128 ? launch_igemm_tma_pair<128>(d, tmA, tmh, g, occ, st)
-                               : launch_igemm_tma_pair<256>(d, tmA, tmh, g, occ, st);
-    }
     switch (d->block_n) {
       case 16: return dispatch_amode<16>(a_mode, d, tmA, tm, g, occ, st);
       case 32: return dispatch_amode<32>(a_mode, d, tmA, tm, g, occ, st);

@@ -29,7 +29,7 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 
-def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, stats_c=0):
+def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, stats_c=0, bce=False):
     geom = lp.fwd if which == "fwd" else lp.dgrad
     idx = lp.idx_fwd if which == "fwd" else lp.idx_dgrad
     A = torch.randn(n_img, *in_shape, device=DEV).half()
@@ -40,6 +40,11 @@ def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, st
     if stats_c and getattr(geom, "patch", 0):
         sums = torch.zeros(4, stats_c, 2, device=DEV)
         kw["stats"] = (sums, n_img // 4)
+    if bce:  # the logits layer as the step runs it: BCE loss + logit gradient fused into the epilogue, 4 groups
+        B = n_img // 4
+        kw["bce"] = dict(target=torch.rand(B, 3, 64, 64, device=DEV), mask=None, loss=torch.zeros(64, device=DEV), gscale=1.0,
+                         dlogits=torch.zeros(n_img, 66, 66, 8, device=DEV, dtype=torch.float16), rows_per_group=B,
+                         slots=[8, 9, 10, 11], logit_rows=(0, B))
     ms = timeit(lambda: ops.igemm(geom, A, W, out, n_img, **kw))
     rows = n_img * geom.P * geom.n_phases
     tiles = (rows + 127) // 128 * (geom.N // geom.block_n)
@@ -51,6 +56,7 @@ def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, st
 
 CASES = {
     "deconv4.fwd": lambda R: run("deconv4.fwd", plan.deconv_out_plan("d4", 0), "fwd", R, (32, 32, 32), (3, 64, 64), torch.float32),
+    "deconv4.fwd.bce": lambda R: run("deconv4.fwd.bce", plan.deconv_out_plan("d4", 0), "fwd", R, (32, 32, 32), (3, 64, 64), torch.float32, bce=True),
     "deconv3.fwd": lambda R: run("deconv3.fwd", plan.deconv_s2_plan("d3", 0, 64, 32, 16), "fwd", R, (16, 16, 64), (32, 32, 32), stats_c=32),
     "deconv3.fwd.nostats": lambda R: run("deconv3.fwd.nost", plan.deconv_s2_plan("d3", 0, 64, 32, 16), "fwd", R, (16, 16, 64), (32, 32, 32)),
     "deconv2.fwd": lambda R: run("deconv2.fwd", plan.deconv_s2_plan("d2", 0, 128, 64, 8), "fwd", R, (8, 8, 128), (16, 16, 64), stats_c=64),
