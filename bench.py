@@ -262,6 +262,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # captured NCCL collectives: the watchdog's event queries must not run into the capture
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         # NCCL prints its version banner on stdout when the first communicator comes up: point fd 1 at
         # stderr while that happens, so that stdout carries the JSON line and nothing else
         sys.stdout.flush()
@@ -328,15 +330,16 @@ def run_b200(args):
     gstep = None
     dp_mode = "single" if world == 1 else ("eager: bucketed all-reduce overlapped with backward" if args.no_graph else "")
     if use_graph:
-        if world > 1 and args.nccl_in_graph:
-            # experimental: capture the bucketed NCCL all-reduces inside the step graph.  On this stack
-            # (torch 2.11 / NCCL 2.28.9) the capture HANGS (measured in round 1, 2 GPUs), so the
-            # default for data parallelism is the split scheme below.
+        if world > 1 and not args.dp_split:
+            # data parallel as north_star states it, inside the step's CUDA graph: the gradient arena is cut
+            # into one bucket per sub-network, each bucket's NCCL all-reduce is launched from the backward on a
+            # side stream as soon as that sub-network's gradients are final (decoders first) and overlaps the
+            # encoder backward; the fused Adam (grad_prescale = 1/N) closes the graph.  One graph launch per step.
             try:
                 sync_in_graph = parallel.attach(eng, opt, arena, overlap=True)
                 gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw,
                                                 grad_sync=sync_in_graph)
-                dp_mode = "one graph: bucketed all-reduce captured, overlapped with backward"
+                dp_mode = "one CUDA graph: bucketed NCCL all-reduce captured, overlapped with backward, fused Adam"
             except Exception as e:  # noqa: BLE001 - fall back to the split-graph scheme below
                 if rank == 0:
                     print(f"[bench] NCCL capture failed ({type(e).__name__}: {e}); using split graphs", file=sys.stderr)
@@ -372,7 +375,7 @@ def run_b200(args):
     gsteps = [gstep, None]
     if gstep is not None:
         gsteps[1] = engine.GraphedTrainStep(eng, opt, dev_batches[1][0], dev_batches[1][1], klw,
-                                            split_optimizer=world > 1, grad_sync=gstep.sync)
+                                            split_optimizer=world > 1 and not in_graph_sync, grad_sync=gstep.sync)
         in_sets = [g_.x + g_.t for g_ in gsteps]
     else:
         in_sets = [[torch.empty_like(a) for a in dev_batches[0][0] + dev_batches[0][1]] for _ in range(2)]
@@ -474,7 +477,7 @@ def run_b200(args):
     roof, roof_hbm, table, families, tensor_all = None, None, [], [], None
     if rank == 0:
         eng.set_concurrent(False)  # serial branches: per-kernel events must not time-share the SMs
-        eng.bucket_hook = None     # rank-0-only pass: no collectives
+        saved_hook, eng.bucket_hook = eng.bucket_hook, None  # rank-0-only pass: no collectives
         for _ in range(2):
             ops.start_profile()
             opt.zero_grad()
@@ -482,6 +485,7 @@ def run_b200(args):
             eng.backward()
             opt.step()
             prof = ops.stop_profile()
+        eng.bucket_hook = saved_hook
         tot_ms = sum(d["ms"] for d in prof.values())
         for tag, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
             table.append({"kernel": tag, "launches": d["count"], "ms": round(d["ms"], 4),
@@ -544,11 +548,12 @@ def run_b200(args):
             if Bs < 8:
                 continue
             xb, tb = synth_batch(Bs, 99 + rank, device=dev)
-            g2 = engine.GraphedTrainStep(eng, opt, xb, tb, klw, split_optimizer=world > 1)
+            g2 = engine.GraphedTrainStep(eng, opt, xb, tb, klw, split_optimizer=world > 1 and not in_graph_sync,
+                                         grad_sync=gstep.sync if in_graph_sync else None)
 
             def one():
                 g2.run()
-                if world > 1:
+                if world > 1 and not in_graph_sync:
                     dist.all_reduce(arena.grad)
                     g2.apply()
             for _ in range(5):
@@ -604,8 +609,9 @@ def main():
                     help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--nccl-in-graph", action="store_true",
-                    help="experimental: capture NCCL inside the step graph (hangs on torch 2.11 / NCCL 2.28.9)")
+    ap.add_argument("--dp-split", action="store_true",
+                    help="data parallel as backward graph + flat all-reduce + optimizer graph instead of one graph with "
+                         "the bucketed all-reduces captured inside")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip extra.reference_cuda (stock eager reference on this GPU)")
     ap.add_argument("--no-sustained", action="store_true", help="skip extra.sustained (>= 5 s of the resident step)")

@@ -167,33 +167,52 @@ def dyn_case(use_pose, dev, rank, world):
 
 def graph_case(dev, rank, world):
     """The CUDA-graph step, data parallel: every available exchange scheme gives the eager path's summed
-    gradients and leaves bit-identical replicas."""
+    gradients and leaves bit-identical replicas.  (No pose expert here: its ReLU units flip under the
+    replay-to-replay fp32-atomics noise and would blur the comparison, see tests/test_parity2_gpu.py.)"""
     from mmdyn_b200 import engine, noise, optim, parallel
     klw, Bl = 0.02, 8
-    model, sd = make(True, 13, dev)
+    model, sd = make(False, 13, dev)
     d = global_batch(Bl * world, 21)
     a, b = parallel.shard_rows(Bl * world, world, rank)
-    x = [d["v"][a:b].to(dev), d["t"][a:b].to(dev), d["p"][a:b].to(dev)]
-    t = [d["tv"][a:b].to(dev), d["tt"][a:b].to(dev), d["tp"][a:b].to(dev)]
+    x = [d["v"][a:b].to(dev), d["t"][a:b].to(dev)]
+    t = [d["tv"][a:b].to(dev), d["tt"][a:b].to(dev)]
     src = noise.DeviceNoise(seed=900 + rank)
-    eng = engine.StepEngine(model, "mvae", use_pose=True, noise_src=src)
+    eng = engine.StepEngine(model, "mvae", use_pose=False, noise_src=src)
     opt = optim.FusedAdam(model, lr=1e-3)
     arena = engine.get_arena(model, dev)
     opt.grad_prescale = 1.0 / world
-    # reference: eager step, flat all-reduce
-    src._counter(dev).zero_()
+    w0 = arena.flat.clone()
+
+    def reset():  # same weights, fresh optimizer moments, same noise stream for every scheme
+        arena.flat.copy_(w0)
+        arena.bump()
+        for buf in opt._bufs or ():
+            buf.zero_()
+        if opt._bufs is not None:
+            opt._step_dev.zero_()
+        src._counter(dev).zero_()
+
+    # reference: eager step, flat all-reduce, one Adam step
+    opt._arena()
+    reset()
     opt.zero_grad()
     _, l0 = eng.evaluate(x, t, klw, need_grad=True, autograd=False, want_outputs=False)
     eng.backward()
     dist.all_reduce(arena.grad)
     torch.cuda.synchronize()
     g_ref, l_ref = arena.grad.clone(), float(l0)
+    opt.step()
+    torch.cuda.synchronize()
+    w_ref = arena.flat.clone()
     schemes = ["split"]
     if os.environ.get("MMDYN_TEST_NCCL_IN_GRAPH") == "1":
         schemes.append("nccl_in_graph")
     if hasattr(parallel, "PeerExchange") and os.environ.get("MMDYN_TEST_NO_PEER") is None:
         schemes.append("peer")
     for scheme in schemes:
+        reset()
+        torch.cuda.synchronize()
+        dist.barrier()
         if scheme == "split":
             g = engine.GraphedTrainStep(eng, opt, x, t, klw, split_optimizer=True)
         elif scheme == "nccl_in_graph":
@@ -201,20 +220,25 @@ def graph_case(dev, rank, world):
             g = engine.GraphedTrainStep(eng, opt, x, t, klw, split_optimizer=True, grad_sync=sync)
         else:
             px = parallel.PeerExchange(arena, opt)
-            g = engine.GraphedTrainStep(eng, opt, x, t, klw, split_optimizer=True, peer_exchange=px)
-        src.ctr.zero_()
+            g = engine.GraphedTrainStep(eng, opt, x, t, klw, peer_exchange=px)
+        reset()
         g.run()
         if scheme == "split":
             dist.all_reduce(arena.grad)
         torch.cuda.synchronize()
-        e = nrel(arena.grad, g_ref) if scheme != "peer" else g.peer_exchange.check_against(g_ref)
         el = abs(float(g.loss) - l_ref) / abs(l_ref)
-        log(f"[dp] graph step, scheme {scheme}: loss rel {el:.1e}, summed gradients vs eager rel {e:.2e}")
-        # not bit-equal: fp32 atomics reorder from launch to launch and a few fp16 roundings / pose-MLP ReLU units
-        # flip behind them (replay-to-replay noise floor of one graph: tests/test_parity2_gpu.py); measured 7.7e-5
-        assert el < 2e-6 and e < 2e-3, (scheme, el, e)
-        g.apply()
+        if scheme != "peer":
+            e = nrel(arena.grad, g_ref)
+            log(f"[dp] graph step, scheme {scheme}: loss rel {el:.1e}, summed gradients vs eager rel {e:.2e}")
+            # not bit-equal: fp32 atomics reorder from launch to launch and a few fp16 roundings flip behind them
+            assert el < 2e-6 and e < 1e-3, (scheme, el, e)
+            g.apply()
         torch.cuda.synchronize()
+        ew = nrel(arena.flat - w0, w_ref - w0)
+        log(f"[dp] graph step, scheme {scheme}: Adam displacement vs eager rel {ew:.2e} (loss rel {el:.1e})")
+        # step 1 of Adam is lr * sign(g) wherever |g| >> eps: entries whose tiny gradient changes sign under the
+        # replay noise move by 2 lr, the rest agree exactly
+        assert el < 2e-6 and ew < 5e-2, (scheme, el, ew)
         check_replicas_identical(model, f"graph {scheme}")
         eng.bucket_hook = None
         del g
