@@ -595,9 +595,15 @@ def run_b200(args):
             "final_loss": final_loss, "top_kernels": table[:6],
         }
         print(json.dumps(out))
+        sys.stdout.flush()
     if world > 1:
+        # CUDA graphs that captured NCCL kernels are still alive here; tearing the communicator down under them
+        # can hang (measured: the JSON line was out, destroy_process_group never returned).  Drain, meet, leave.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
