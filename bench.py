@@ -329,12 +329,26 @@ def run_b200(args):
     use_graph = not args.no_graph
     gstep = None
     dp_mode = "single" if world == 1 else ("eager: bucketed all-reduce overlapped with backward" if args.no_graph else "")
+    px = None
     if use_graph:
-        if world > 1 and not args.dp_split:
-            # data parallel as north_star states it, inside the step's CUDA graph: the gradient arena is cut
-            # into one bucket per sub-network, each bucket's NCCL all-reduce is launched from the backward on a
-            # side stream as soon as that sub-network's gradients are final (decoders first) and overlaps the
-            # encoder backward; the fused Adam (grad_prescale = 1/N) closes the graph.  One graph launch per step.
+        if world > 1 and args.dp == "peer":
+            # data parallel as ONE CUDA graph with no NCCL call in it: the graph ends with the fused
+            # reduce-scatter + Adam + all-gather kernel over NVLink peer memory (csrc/peer.cu): rank r sums the r-th
+            # shard of all ranks' gradient arenas with peer loads, updates it, and stores the new parameters into
+            # every replica; cross-GPU flags inside the kernel replace the host-side collective
+            try:
+                px = parallel.PeerExchange(arena, opt)
+                gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw, peer_exchange=px)
+                dp_mode = ("one CUDA graph: fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory "
+                           "(CUDA IPC mapped arenas, in-kernel flags, no NCCL on the step path)")
+            except Exception as e:  # noqa: BLE001 - e.g. no peer access: fall back to NCCL
+                if rank == 0:
+                    print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+                px, gstep = None, None
+        if world > 1 and gstep is None and args.dp != "split":
+            # the gradient arena is cut into one bucket per sub-network, each bucket's NCCL all-reduce is launched
+            # from the backward on a side stream as soon as that sub-network's gradients are final (decoders first)
+            # and overlaps the encoder backward; the fused Adam (grad_prescale = 1/N) closes the graph
             try:
                 sync_in_graph = parallel.attach(eng, opt, arena, overlap=True)
                 gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw,
@@ -349,7 +363,7 @@ def run_b200(args):
             gstep = engine.GraphedTrainStep(eng, opt, dev_batches[0][0], dev_batches[0][1], klw, split_optimizer=world > 1)
             if world > 1:
                 dp_mode = "backward graph + flat all-reduce + optimizer graph"
-    in_graph_sync = gstep is not None and gstep.sync is not None
+    in_graph_sync = gstep is not None and (gstep.sync is not None or px is not None)  # the graph holds the exchange
 
     def step_resident(i):
         x, t = dev_batches[i % 3]
@@ -375,7 +389,8 @@ def run_b200(args):
     gsteps = [gstep, None]
     if gstep is not None:
         gsteps[1] = engine.GraphedTrainStep(eng, opt, dev_batches[1][0], dev_batches[1][1], klw,
-                                            split_optimizer=world > 1 and not in_graph_sync, grad_sync=gstep.sync)
+                                            split_optimizer=world > 1 and not in_graph_sync, grad_sync=gstep.sync,
+                                            peer_exchange=px)
         in_sets = [g_.x + g_.t for g_ in gsteps]
     else:
         in_sets = [[torch.empty_like(a) for a in dev_batches[0][0] + dev_batches[0][1]] for _ in range(2)]
@@ -549,7 +564,7 @@ def run_b200(args):
                 continue
             xb, tb = synth_batch(Bs, 99 + rank, device=dev)
             g2 = engine.GraphedTrainStep(eng, opt, xb, tb, klw, split_optimizer=world > 1 and not in_graph_sync,
-                                         grad_sync=gstep.sync if in_graph_sync else None)
+                                         grad_sync=gstep.sync if in_graph_sync else None, peer_exchange=px)
 
             def one():
                 g2.run()
@@ -615,9 +630,10 @@ def main():
                     help="per-GPU batch (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--dp-split", action="store_true",
-                    help="data parallel as backward graph + flat all-reduce + optimizer graph instead of one graph with "
-                         "the bucketed all-reduces captured inside")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl", "split"],
+                    help="data-parallel exchange of the graphed step: peer = fused reduce-scatter + Adam + all-gather kernel "
+                         "over NVLink peer memory (default); nccl = bucketed NCCL all-reduces captured in the graph, "
+                         "overlapped with backward; split = backward graph + flat all-reduce + optimizer graph")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip extra.reference_cuda (stock eager reference on this GPU)")
     ap.add_argument("--no-sustained", action="store_true", help="skip extra.sustained (>= 5 s of the resident step)")

@@ -336,6 +336,28 @@ int mmdyn_sgd_flat_guarded(float* p, const float* g, float* buf, long long n, fl
                            float weight_decay, int first_step, float gscale, unsigned int* nonfinite_flag,
                            void* stream);
 
+/* --- data-parallel exchange fused with the optimizer over NVLink peer memory -------------------------
+ * (north_star: gradients of the sharded batch are combined across the GPUs of one box; the step it completes is
+ * problems.py:150-155.)  One process per GPU; every rank maps the other ranks' gradient arena, parameter arena and
+ * flag block (CUDA IPC) and passes the N pointers of each (own rank included) as HOST arrays.
+ *   mmdyn_enable_peer_access : cudaDeviceEnablePeerAccess from the current device to `peer_device` (idempotent)
+ *   mmdyn_peer_rs_adam_ag    : reduce-scatter + Adam + all-gather in one kernel.  Rank r sums the gradients of its
+ *       contiguous shard of the n-float arena over all ranks (peer loads), applies the mmdyn_adam_flat_guarded update
+ *       with its local moments, and stores the new parameters into every rank's arena (peer stores).  flag_ptrs[p]:
+ *       2*world zero-initialised uint32 of rank p (ready / done epochs); epoch_dev: device counter, incremented by
+ *       the caller before every launch on every rank; block_counter: one zeroed uint32.  The kernel returns on a
+ *       rank only after all peers finished reading its gradients and writing its parameters. */
+/*   mmdyn_ipc_export / mmdyn_ipc_import : CUDA IPC handle (64 bytes) of the allocation containing ptr + the
+ *       offset of ptr inside it; import maps it into the CURRENT device address space with peer access enabled
+ *       (the mapping stays for the life of the process) and returns the peer pointer. */
+int mmdyn_enable_peer_access(int peer_device);
+int mmdyn_ipc_export(const void* ptr, void* handle_out /* 64 bytes */, long long* offset_out);
+int mmdyn_ipc_import(const void* handle /* 64 bytes */, long long offset, void** ptr_out);
+int mmdyn_peer_rs_adam_ag(float* const* grad_ptrs, float* const* param_ptrs, unsigned int* const* flag_ptrs, float* m,
+                          float* v, long long n, int rank, int world, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, const uint64_t* step_dev, const uint64_t* epoch_dev, float gscale,
+                          unsigned int* nonfinite_flag, unsigned int* block_counter, void* stream);
+
 /* --- deterministic device RNG (Philox4x32-10) for eps / dropout masks --------------------------
  * replaces torch.randn (vae.py:58) and nn.Dropout's mask (vae.py:213) on the fast path */
 /* the Philox counter of element block i is (*ctr_dev if ctr_dev else 0) + offset + i; keeping the

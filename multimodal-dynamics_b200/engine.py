@@ -1252,14 +1252,18 @@ class GraphedTrainStep:
     gradient arena and then calls `apply()`, a second graph holding the optimizer update."""
 
     def __init__(self, step_engine, optimizer, example_x, example_t, kl_weight, loss_mask=None, split_optimizer=False,
-                 warmup=2, grad_sync=None, condition=None):
+                 warmup=2, grad_sync=None, condition=None, peer_exchange=None):
         """grad_sync: a parallel.GradSync whose bucketed NCCL all-reduces are captured INSIDE the graph
         (launched from the backward on a side stream, overlapping the encoder backward); the
         alternative for data parallelism is split_optimizer=True (backward graph, eager all-reduce,
-        optimizer graph)."""
+        optimizer graph).
+        peer_exchange: a parallel.PeerExchange — the graph ends with the fused reduce-scatter + Adam + all-gather
+        kernel over NVLink peer memory instead of optimizer.step(): the whole data-parallel step is one graph with
+        no NCCL call in it."""
         self.eng, self.opt, self.klw = step_engine, optimizer, float(kl_weight)
-        self.split = split_optimizer
-        self.sync = grad_sync
+        self.split = split_optimizer and peer_exchange is None
+        self.sync = grad_sync if peer_exchange is None else None
+        self.peer_exchange = peer_exchange
         lst = isinstance(example_x, (list, tuple))
         self.x = [t.clone() for t in example_x] if lst else example_x.clone()
         self.t = [t.clone() for t in example_t] if lst else example_t.clone()
@@ -1312,7 +1316,10 @@ class GraphedTrainStep:
         if self.sync is not None:
             self.sync.finish()
         if with_opt:
-            self.opt.step()
+            if self.peer_exchange is not None:
+                self.peer_exchange.step()
+            else:
+                self.opt.step()
         return outputs, loss
 
     def load(self, x, t, non_blocking=True, mask=None, condition=None):

@@ -106,6 +106,11 @@ SIGNATURES = {
     "mmdyn_sgd_flat": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),
     "mmdyn_adam_flat_guarded": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _F, _P, _P], _I),
     "mmdyn_sgd_flat_guarded": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P, _P], _I),
+    "mmdyn_enable_peer_access": ([_I], _I),
+    "mmdyn_ipc_export": ([_P, _P, C.POINTER(_LL)], _I),
+    "mmdyn_ipc_import": ([_P, _LL, C.POINTER(_P)], _I),
+    "mmdyn_peer_rs_adam_ag": ([C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, _LL, _I, _I, _F, _F, _F, _F, _F, _P, _P,
+                               _F, _P, _P, _P], _I),
     "mmdyn_fill_normal": ([_P, _LL, _U64, _U64, _P, _P], _I),
     "mmdyn_fill_dropout_mask": ([_P, _LL, _F, _U64, _U64, _P, _P], _I),
     "mmdyn_rng_advance": ([_P, _U64, _P], _I),

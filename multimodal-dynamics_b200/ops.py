@@ -421,3 +421,33 @@ def relu_f32(x, y):
 def act_grad_f32(y, dy, dx, M, N, ldy, act):
     with _Timed("act_grad_f32", None):
         check(_L().mmdyn_act_grad_f32(_ptr(y), _ptr(dy), _ptr(dx), M, N, ldy, act, _stream()), "act_grad_f32")
+
+
+def ipc_export(t):
+    """(64-byte CUDA IPC handle, byte offset) of a device tensor's memory — picklable, for the other ranks."""
+    h = C.create_string_buffer(64)
+    off = C.c_longlong(0)
+    check(_L().mmdyn_ipc_export(_ptr(t), h, C.byref(off)), "ipc_export")
+    return bytes(h.raw), int(off.value)
+
+
+def ipc_import(handle, offset):
+    """Raw device pointer (int) of a peer rank's exported memory, mapped for kernels of the CURRENT device."""
+    p = C.c_void_p(0)
+    check(_L().mmdyn_ipc_import(C.create_string_buffer(handle, 64), int(offset), C.byref(p)), "ipc_import")
+    return int(p.value)
+
+
+def enable_peer_access(peer_device):
+    check(_L().mmdyn_enable_peer_access(int(peer_device)), "enable_peer_access")
+
+
+def peer_rs_adam_ag(grad_ptrs, param_ptrs, flag_ptrs, m, v, n, rank, world, lr, b1, b2, eps, wd, step_dev, epoch_dev,
+                    gscale, flag, counter):
+    """Fused reduce-scatter + Adam + all-gather over peer memory (csrc/peer.cu).  *_ptrs: python lists of the N ranks'
+    raw device pointers (peer-mapped; own rank included).  Algorithmic bytes: own shard 28 B/param + peer traffic."""
+    arr = lambda ps: (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in ps])
+    with _Timed("peer_rs_adam_ag", lambda: (0.0, n * 4.0 * (2.0 * (world - 1) / world) + n * 28.0 / world)):
+        check(_L().mmdyn_peer_rs_adam_ag(arr(grad_ptrs), arr(param_ptrs), arr(flag_ptrs), _ptr(m), _ptr(v), n, rank, world,
+                                         lr, b1, b2, eps, wd, _ptr(step_dev), _ptr(epoch_dev), gscale, _ptr(flag),
+                                         _ptr(counter), _stream()), "peer_rs_adam_ag")

@@ -105,6 +105,64 @@ class GradSync:
         self.pending = []
 
 
+class PeerExchange:
+    """Gradient exchange fused with the optimizer over NVLink peer memory: reduce-scatter + Adam + all-gather as ONE
+    kernel (csrc/peer.cu) instead of an NCCL all-reduce followed by N identical Adam updates.  Rank r owns the r-th
+    shard of the flat arena: it sums that shard's gradients over all ranks with peer loads, updates it with its local
+    moments, and stores the new parameters into every replica.  No host synchronisation and no NCCL call on the step
+    path (the kernel carries its own cross-GPU flags), so the whole data-parallel step is one CUDA graph.
+
+    Set-up (once): every rank exports its gradient arena, parameter arena and a flag block as CUDA IPC handles
+    (mmdyn_ipc_export), the handles travel through `torch.distributed` (object all-gather), every rank maps
+    its peers' buffers and enables peer access.  One node only (NVLink / NVSwitch)."""
+
+    def __init__(self, arena, optimizer, group=None):
+        from . import ops
+        if not isinstance(optimizer, __import__("mmdyn_b200.optim", fromlist=["FusedAdam"]).FusedAdam):
+            raise TypeError("PeerExchange fuses the exchange with FusedAdam")
+        self.arena, self.opt, self.group = arena, optimizer, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise ValueError("PeerExchange: at most 8 ranks (one NVSwitch box)")
+        dev = arena.flat.device
+        optimizer._arena()  # moment arenas + device step counter
+        self.flags = torch.zeros(2 * self.world, dtype=torch.int32, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        mine = [arena.grad, arena.flat, self.flags]
+        ptrs = [[None] * self.world for _ in mine]
+        for k, t in enumerate(mine):
+            ptrs[k][self.rank] = t.data_ptr()
+        if self.world > 1:
+            torch.cuda.synchronize(dev)
+            with torch.cuda.device(dev):
+                exported = [ops.ipc_export(t) for t in mine]
+                everyone = [None] * self.world
+                dist.all_gather_object(everyone, exported, group=group)
+                for p, theirs in enumerate(everyone):
+                    if p != self.rank:
+                        for k, (handle, off) in enumerate(theirs):
+                            ptrs[k][p] = ops.ipc_import(handle, off)  # mapped for THIS device, peer access enabled
+            dist.barrier(group=group)  # everybody has mapped everybody before the first kernel may signal
+        self.grad_ptrs, self.param_ptrs, self.flag_ptrs = ptrs
+        optimizer.grad_prescale = 1.0 / self.world
+
+    def step(self):
+        """The optimizer step of problems.py:155 for all replicas at once (call it where optimizer.step() would be)."""
+        from . import ops
+        opt, arena = self.opt, self.arena
+        g = opt.param_groups[0]
+        opt._step += 1
+        ops.rng_advance(opt._step_dev, 1)
+        ops.rng_advance(self.epoch, 1)
+        m, v = opt._bufs
+        ops.peer_rs_adam_ag(self.grad_ptrs, self.param_ptrs, self.flag_ptrs, m, v, arena.total, self.rank, self.world,
+                            g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], opt._step_dev, self.epoch,
+                            opt.grad_prescale, opt._flag, self.counter)
+        arena.bump()
+
+
 def attach(step_engine, optimizer, arena, group=None, overlap=True):
     """Wire a StepEngine + fused optimizer for data parallel training; returns the GradSync.
     Usage per step: sync.begin(); loss.backward() (fires bucket hooks); sync.finish(); optimizer.step()."""

@@ -233,6 +233,15 @@ def graph_case(dev, rank, world):
             # not bit-equal: fp32 atomics reorder from launch to launch and a few fp16 roundings flip behind them
             assert el < 2e-6 and e < 1e-3, (scheme, el, e)
             g.apply()
+        else:
+            # the fused exchange leaves the local gradients untouched: rebuild what it must have computed from them
+            gsum = arena.grad.clone()
+            dist.all_reduce(gsum)
+            gavg = gsum / world
+            want = w0 - 1e-3 * (0.1 * gavg / 0.1) / ((0.001 * gavg * gavg).sqrt() / (0.001 ** 0.5) + 1e-8)  # Adam, step 1
+            e = (arena.flat - want).abs().max().item()
+            log(f"[dp] graph step, scheme peer: parameters vs Adam(all-reduced local gradients): max abs diff {e:.2e}")
+            assert e < 2e-6, e
         torch.cuda.synchronize()
         ew = nrel(arena.flat - w0, w_ref - w0)
         log(f"[dp] graph step, scheme {scheme}: Adam displacement vs eager rel {ew:.2e} (loss rel {el:.1e})")
