@@ -287,6 +287,19 @@ int mmdyn_cond_add_f16(void* raw, const float* c, const float* W, const int32_t*
 int mmdyn_cond_wgrad_f16(const void* g, const float* c, float* dW, const int32_t* n_idx, int R, int N, int ldw,
                          int col0, int cd, float scale, void* stream);
 
+/* --- pose MLP on the tensor cores at fp32 accuracy (vae.py:14-19, 118-123, 219-222, 282-283) -----------------
+ * The 512-wide Linear layers of the pose expert run on mmdyn_igemm / mmdyn_wgrad with every fp32 operand split into
+ * two fp16 terms (x = hi + lo) and the three significant products hi*hi + lo*hi + hi*lo concatenated along the
+ * contraction dimension: out[m] = [hi | lo | hi] (mode 0, activations) or [hi | hi | lo] (mode 1: gradients; weights
+ * are packed like mode 1 / mode 0 by mmdyn_pack_f16 with index bit 30 marking a low part).  fp32 accumulation in TMEM
+ * keeps the result within ~1e-6 of the fp32 product (north_star: 1e-5 for the fp32 parts).
+ *   x [M][N] fp32 -> out [M][3N] fp16; relu != 0: x := max(x, 0); mask_y: x := x * (mask_y > 0) (ReLU backward by its
+ *   output); x_out (nullable, may alias x): the fp32 value after relu / mask; colsum0 / colsum1 (nullable): column
+ *   sums * colsum_scale of that value accumulated into colsum0[n] for n < n_split and colsum1[n - n_split] beyond
+ *   (bias gradients of one or two concatenated Linear layers). */
+int mmdyn_split_f16(const float* x, const float* mask_y, float* x_out, void* out, int M, int N, int mode, int relu,
+                    float* colsum0, float* colsum1, int n_split, float colsum_scale, void* stream);
+
 /* --- Regressor tail (models.py:56-62, 64-77) ---------------------------------
  * out_net = Linear(512(+cd), 256) -> ReLU -> Linear(256, 256) -> ReLU -> Linear(256, out_dim): the first Linear
  * runs on the tensor cores (mmdyn_igemm, fp32 out), the ReLU behind it here, the rest on mmdyn_linear_f32_*.

@@ -991,7 +991,56 @@ pack_f16_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, 
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int32_t j = idx[i];
-    dst[i] = __float2half_rn(j < 0 ? 0.0f : src[j]);
+    if (j < 0) {
+      dst[i] = __float2half_rn(0.0f);
+    } else if (j & (1 << 30)) {
+      // low part of the two-term fp16 split of an fp32 weight (pose MLP on the tensor cores, mmdyn_split_f16)
+      const float w = src[j & ((1 << 30) - 1)];
+      dst[i] = __float2half_rn(w - __half2float(__float2half_rn(w)));
+    } else {
+      dst[i] = __float2half_rn(src[j]);
+    }
+  }
+}
+
+// Two-term fp16 split of an fp32 matrix for fp32-accurate products on the fp16 tensor cores:
+//   x = hi + lo (+ O(2^-22 |x|)),  hi = fp16(x),  lo = fp16(x - hi)
+//   x . w  ~=  hi_x hi_w + lo_x hi_w + hi_x lo_w     (three fp16 products, fp32 accumulation; lo_x lo_w ~ 2^-22 dropped)
+// which one GEMM computes when the three terms are concatenated along the contraction dimension:
+//   mode 0 ("activation" side)  out[m] = [hi | lo | hi]      mode 1 ("other" side)  out[m] = [hi | hi | lo]
+// (weights are packed the same way by mmdyn_pack_f16, index bit 30 = low part).  Optional on the way:
+//   relu      x := max(x, 0)                       (forward: bias was added by the producing GEMM)
+//   mask_y    x := x * (mask_y > 0)                (backward through a ReLU, judged by its output)
+//   x_out     the fp32 value after relu / mask     (may alias x)
+//   colsum0/1 column sums (times colsum_scale) of the fp32 value: columns < n_split into colsum0, the rest into
+//             colsum1 (bias gradients of one or two concatenated Linear layers), accumulated with atomics
+// thread = column (coalesced along the row), CTA = a slab of rows.
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, const float* __restrict__ mask_y, float* __restrict__ x_out,
+                 __half* __restrict__ out, int M, int N, int mode, int relu, float* __restrict__ colsum0,
+                 float* __restrict__ colsum1, int n_split, float colsum_scale, int rows_per_cta) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  const int p_lo = mode == 0 ? 1 : 2;  // segment that holds the low part
+  float acc = 0.0f;
+  for (int r = r0; r < r1; ++r) {
+    const long long i = static_cast<long long>(r) * N + n;
+    float v = x[i];
+    if (relu) v = fmaxf(v, 0.0f);
+    if (mask_y && !(mask_y[i] > 0.0f)) v = 0.0f;
+    if (x_out) x_out[i] = v;
+    acc += v;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    __half* o = out + static_cast<long long>(r) * 3 * N + n;
+    o[0] = hi;
+    o[N] = p_lo == 1 ? lo : hi;
+    o[2 * N] = p_lo == 2 ? lo : hi;
+  }
+  if (colsum0) {
+    if (n < n_split) atomicAdd(colsum0 + n, colsum_scale * acc);
+    else if (colsum1) atomicAdd(colsum1 + (n - n_split), colsum_scale * acc);
   }
 }
 
@@ -1539,6 +1588,23 @@ extern "C" int mmdyn_colsum_f16(const void* x, float* out, int M, int N, int ld,
 extern "C" int mmdyn_pack_f16(const float* src, const int32_t* idx, void* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && idx && dst && n > 0, "pack_f16: bad arguments");
   pack_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, reinterpret_cast<__half*>(dst), n);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_split_f16(const float* x, const float* mask_y, float* x_out, void* out, int M, int N, int mode,
+                               int relu, float* colsum0, float* colsum1, int n_split, float colsum_scale, void* stream) {
+  MMDYN_REQUIRE(x && out && M > 0 && N > 0 && (mode == 0 || mode == 1), "split_f16: bad arguments");
+  MMDYN_REQUIRE(!colsum1 || (colsum0 && n_split > 0 && n_split < N), "split_f16: colsum1 needs colsum0 and 0 < n_split < N");
+  const int gx = (N + 255) / 256;
+  int row_ctas = (148 * 4) / gx;
+  if (row_ctas < 1) row_ctas = 1;
+  int rpc = (M + row_ctas - 1) / row_ctas;
+  if (rpc < 8) rpc = 8;
+  const int gy = (M + rpc - 1) / rpc;
+  split_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(x, mask_y, x_out, reinterpret_cast<__half*>(out), M, N, mode, relu,
+                                                         colsum0, colsum1, colsum0 && !colsum1 ? N : n_split, colsum_scale,
+                                                         rpc);
   LAUNCHED();
   return MMDYN_OK;
 }

@@ -683,16 +683,130 @@ def _group_chunk(G, B):
 
 
 # ---------------------------------------------------------------------------------------------
-# pose MLP expert, fp32 (vae.py:118-123, 219-222, 282-283)
+# pose MLP expert (vae.py:118-123, 219-222, 282-283)
 # ---------------------------------------------------------------------------------------------
-class PoseExec:
+class PoseExec(_NetBase):
+    """Pose expert Linear(7,512)-ReLU-Linear(512,512)-{Linear(512,256)}x2 and Linear(256,512)-ReLU-Linear(512,512)-
+    ReLU-Linear(512,7).  The four 256/512-wide layers (99 % of its FLOPs) run on the tensor cores at fp32 accuracy
+    through the two-term fp16 split (plan.linear_split_plan, mmdyn_split_f16): forward, dgrad and wgrad are the
+    tcgen05 kernels of the image layers with the contraction tripled; the 7-wide edge layers stay on the fp32 SIMT
+    kernels (mmdyn_linear_f32_*).  MMDYN_POSE_F32=1 keeps every layer on the SIMT kernels (A/B, debugging)."""
+
     def __init__(self, arena, device):
-        self.arena, self.device = arena, device
+        super().__init__(arena, "", device)
+        self.tc = os.environ.get("MMDYN_POSE_F32") is None
+        o = self.arena.offset
+        if self.tc:
+            self.e2 = self._pl(plan.linear_split_plan("pose.fc2", [o["pose_encoder.fc_net.2.weight"]],
+                                                      [o["pose_encoder.fc_net.2.bias"]], 512, [512]))
+            self.eh = self._pl(plan.linear_split_plan(
+                "pose.heads", [o["pose_encoder.linear_means.weight"], o["pose_encoder.linear_log_var.weight"]],
+                [o["pose_encoder.linear_means.bias"], o["pose_encoder.linear_log_var.bias"]], 512, [256, 256]))
+            self.d0 = self._pl(plan.linear_split_plan("pose.dec0", [o["pose_decoder.deconv_net.0.weight"]],
+                                                      [o["pose_decoder.deconv_net.0.bias"]], 256, [512]))
+            self.d2 = self._pl(plan.linear_split_plan("pose.dec2", [o["pose_decoder.deconv_net.2.weight"]],
+                                                      [o["pose_decoder.deconv_net.2.bias"]], 512, [512]))
 
     def p(self, name, grad=False):
         return self.arena.view(name, self.arena.grad if grad else None)
 
+    # -- split-GEMM building blocks ------------------------------------------------------------
+    def _fwd(self, pl, xs, out, M):
+        """out[M][N] fp32 = x W^T + b from the split rows xs [M][3K]."""
+        _ig(pl, "fwd", xs, out, M, pl.bias, True)
+
+    def _bwd(self, pl, xs, ds, dx, M, unscale, names):
+        """dW (+=, straight into the gradient arena, torch layout) and dx [M][K] fp32 from the split rows
+        xs [M][3K] (mode 0) and ds [M][3N] (mode 1)."""
+        col = 0
+        for wg, nm, n_i in zip(pl.lp.extra["wgrads"], names, pl.lp.extra["Ns"]):
+            ops.wgrad(wg, xs, ds[:, col:] if col else ds, self.p(nm + ".weight", True).view(n_i, pl.lp.extra["K"]), 3 * M,
+                      scale=unscale, row_splits=plan.choose_row_splits(wg, 3 * M), tag=f"{pl.lp.name}.wgrad",
+                      macs_per_img=pl.lp.extra["K"] * n_i)
+            col += n_i
+        if dx is not None:
+            _ig(pl, "dgrad", ds, dx, M, None, True)
+
+    # -- encoder -----------------------------------------------------------------------------------
     def enc_forward(self, pose, alloc, key):
+        if not self.tc:
+            return self._enc_forward_f32(pose, alloc, key)
+        self.refresh()
+        B = pose.shape[0]
+        h1 = alloc(key + ".h1", (B, 512), F32)
+        ops.linear_f32_fwd(pose, self.p("pose_encoder.fc_net.0.weight"), self.p("pose_encoder.fc_net.0.bias"), h1,
+                           B, 512, 7, 7, 512, 1)
+        h1s = alloc(key + ".h1s", (B, 1536), F16)
+        ops.split_f16(h1, h1s, B, 512, 0)
+        h2 = alloc(key + ".h2", (B, 512), F32)
+        self._fwd(self.e2, h1s, h2, B)
+        h2s = alloc(key + ".h2s", (B, 1536), F16)
+        ops.split_f16(h2, h2s, B, 512, 0)
+        heads = alloc(key + ".heads", (B, LATENT_HEADS), F32)
+        self._fwd(self.eh, h2s, heads, B)
+        return {"pose": pose, "h1": h1, "h1s": h1s, "h2": h2, "h2s": h2s, "heads": heads, "B": B}
+
+    def enc_backward(self, r, d_heads, alloc, key, unscale):
+        if not self.tc:
+            return self._enc_backward_f32(r, d_heads, alloc, key, unscale)
+        B = r["B"]
+        dhs = alloc(key + ".dhs", (B, 1536), F16)
+        ops.split_f16(d_heads, dhs, B, 512, 1, colsum0=self.p("pose_encoder.linear_means.bias", True),
+                      colsum1=self.p("pose_encoder.linear_log_var.bias", True), n_split=256, colsum_scale=unscale)
+        dh2 = alloc(key + ".dh2", (B, 512), F32)
+        self._bwd(self.eh, r["h2s"], dhs, dh2, B, unscale, ("pose_encoder.linear_means", "pose_encoder.linear_log_var"))
+        d2s = alloc(key + ".d2s", (B, 1536), F16)  # fc_net.2 carries no activation (vae.py:17)
+        ops.split_f16(dh2, d2s, B, 512, 1, colsum0=self.p("pose_encoder.fc_net.2.bias", True), colsum_scale=unscale)
+        dh1 = alloc(key + ".dh1", (B, 512), F32)
+        self._bwd(self.e2, r["h1s"], d2s, dh1, B, unscale, ("pose_encoder.fc_net.2",))
+        scr = alloc(key + ".scr", (B, 512), F32)
+        ops.linear_f32_bwd(r["pose"], self.p("pose_encoder.fc_net.0.weight"), r["h1"], dh1, scr, None,
+                           self.p("pose_encoder.fc_net.0.weight", True), self.p("pose_encoder.fc_net.0.bias", True),
+                           B, 512, 7, 7, 512, 7, 1, False, unscale)
+
+    # -- decoder -----------------------------------------------------------------------------------
+    def dec_forward(self, z, alloc, key):
+        if not self.tc:
+            return self._dec_forward_f32(z, alloc, key)
+        self.refresh()
+        R = z.shape[0]
+        zs = alloc(key + ".zs", (R, 768), F16)
+        ops.split_f16(z, zs, R, 256, 0)
+        a1 = alloc(key + ".a1", (R, 512), F32)
+        self._fwd(self.d0, zs, a1, R)
+        a1s = alloc(key + ".a1s", (R, 1536), F16)
+        ops.split_f16(a1, a1s, R, 512, 0, relu=True, x_out=a1)   # a1 := relu(a1), in place
+        a2 = alloc(key + ".a2", (R, 512), F32)
+        self._fwd(self.d2, a1s, a2, R)
+        ops.relu_f32(a2, a2)
+        rec = alloc(key + ".rec", (R, 7), F32)
+        ops.linear_f32_fwd(a2, self.p("pose_decoder.deconv_net.4.weight"), self.p("pose_decoder.deconv_net.4.bias"),
+                           rec, R, 7, 512, 512, 7, 0)
+        return {"z": z, "zs": zs, "a1": a1, "a1s": a1s, "a2": a2, "rec": rec, "R": R}
+
+    def dec_backward(self, r, d_rec, alloc, key, unscale):
+        if not self.tc:
+            return self._dec_backward_f32(r, d_rec, alloc, key, unscale)
+        R = r["R"]
+        scr = alloc(key + ".scr", (R, 512), F32)
+        da2 = alloc(key + ".da2", (R, 512), F32)
+        ops.linear_f32_bwd(r["a2"], self.p("pose_decoder.deconv_net.4.weight"), r["rec"], d_rec, scr, da2,
+                           self.p("pose_decoder.deconv_net.4.weight", True),
+                           self.p("pose_decoder.deconv_net.4.bias", True), R, 7, 512, 512, 7, 512, 0, False, unscale)
+        d2s = alloc(key + ".d2s", (R, 1536), F16)
+        ops.split_f16(da2, d2s, R, 512, 1, mask_y=r["a2"], colsum0=self.p("pose_decoder.deconv_net.2.bias", True),
+                      colsum_scale=unscale)
+        da1 = alloc(key + ".da1", (R, 512), F32)
+        self._bwd(self.d2, r["a1s"], d2s, da1, R, unscale, ("pose_decoder.deconv_net.2",))
+        d1s = alloc(key + ".d1s", (R, 1536), F16)
+        ops.split_f16(da1, d1s, R, 512, 1, mask_y=r["a1"], colsum0=self.p("pose_decoder.deconv_net.0.bias", True),
+                      colsum_scale=unscale)
+        dz = alloc(key + ".dz", (R, 256), F32)
+        self._bwd(self.d0, r["zs"], d1s, dz, R, unscale, ("pose_decoder.deconv_net.0",))
+        return dz
+
+    # -- all-SIMT fp32 path (MMDYN_POSE_F32=1) ---------------------------------------------------
+    def _enc_forward_f32(self, pose, alloc, key):
         B = pose.shape[0]
         h1 = alloc(key + ".h1", (B, 512), F32)
         ops.linear_f32_fwd(pose, self.p("pose_encoder.fc_net.0.weight"), self.p("pose_encoder.fc_net.0.bias"), h1,
@@ -707,7 +821,7 @@ class PoseExec:
                            self.p("pose_encoder.linear_log_var.bias"), heads[:, 256:], B, 256, 512, 512, 512, 0)
         return {"pose": pose, "h1": h1, "h2": h2, "heads": heads, "B": B}
 
-    def enc_backward(self, r, d_heads, alloc, key, unscale):
+    def _enc_backward_f32(self, r, d_heads, alloc, key, unscale):
         B = r["B"]
         scr = alloc(key + ".scr", (B, 512), F32)
         dh2 = alloc(key + ".dh2", (B, 512), F32)
@@ -723,7 +837,7 @@ class PoseExec:
                            self.p("pose_encoder.fc_net.0.weight", True), self.p("pose_encoder.fc_net.0.bias", True),
                            B, 512, 7, 7, 512, 7, 1, False, unscale)
 
-    def dec_forward(self, z, alloc, key):
+    def _dec_forward_f32(self, z, alloc, key):
         R = z.shape[0]
         a1 = alloc(key + ".a1", (R, 512), F32)
         ops.linear_f32_fwd(z, self.p("pose_decoder.deconv_net.0.weight"), self.p("pose_decoder.deconv_net.0.bias"),
@@ -736,7 +850,7 @@ class PoseExec:
                            rec, R, 7, 512, 512, 7, 0)
         return {"z": z, "a1": a1, "a2": a2, "rec": rec, "R": R}
 
-    def dec_backward(self, r, d_rec, alloc, key, unscale):
+    def _dec_backward_f32(self, r, d_rec, alloc, key, unscale):
         R = r["R"]
         scr = alloc(key + ".scr", (R, 512), F32)
         da2 = alloc(key + ".da2", (R, 512), F32)
@@ -825,8 +939,9 @@ def get_execs(module, device):
                                       if getattr(module, "conditional", False) else 0)
             ex["enc"]["__regressor__"] = ex["reg"].trunk
         nets = list(ex["enc"].values()) + list(ex["dec"].values())
-        ex["packer"] = ModelPacker(nets, dev)
-        for net in nets:
+        packed = nets + ([ex["pose"]] if ex["pose"] is not None else [])  # the pose expert's split weights are packed too
+        ex["packer"] = ModelPacker(packed, dev)
+        for net in packed:
             net.packer = ex["packer"]
         ex["gradpack"] = {net.prefix: GradPack(net, dev) for net in nets}
         module.__dict__["_mmdyn_execs"] = ex

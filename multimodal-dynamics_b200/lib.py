@@ -86,6 +86,7 @@ SIGNATURES = {
     "mmdyn_colsum_f32": ([_P, _P, _I, _I, _I, _F, _P], _I),
     "mmdyn_colsum_f16": ([_P, _P, _I, _I, _I, _F, _P], _I),
     "mmdyn_pack_f16": ([_P, _P, _P, _LL, _P], _I),
+    "mmdyn_split_f16": ([_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _F, _P], _I),
     "mmdyn_gather_f32": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_linear_f32_acc": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "mmdyn_linear_f32_wgrad": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P], _I),

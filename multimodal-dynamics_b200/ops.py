@@ -438,6 +438,14 @@ def ipc_import(handle, offset):
     return int(p.value)
 
 
+def split_f16(x, out, M, N, mode, relu=False, mask_y=None, x_out=None, colsum0=None, colsum1=None, n_split=0,
+              colsum_scale=1.0):
+    """fp32 [M][N] -> fp16 [M][3N] two-term split ([hi|lo|hi] mode 0, [hi|hi|lo] mode 1), see include/mmdyn_b200.h."""
+    with _Timed("split_f16", None):
+        check(_L().mmdyn_split_f16(_ptr(x), _ptr(mask_y), _ptr(x_out), _ptr(out), M, N, mode, int(relu), _ptr(colsum0),
+                                   _ptr(colsum1), n_split, colsum_scale, _stream()), "split_f16")
+
+
 def enable_peer_access(peer_device):
     check(_L().mmdyn_enable_peer_access(int(peer_device)), "enable_peer_access")
 

@@ -347,6 +347,35 @@ def linear_plan(name, w_offs, b_offs, K, Ns, k_perm=None, n_perm=None, ld=None):
     return LayerPlan(name, "linear", fwd, idx_fwd, dg, idx_dg, wg, idx_fwd, bias_idx=bias_idx, extra={"macs": K * N})
 
 
+LO_BIT = 1 << 30  # pack index flag: low part of the two-term fp16 split of that weight (mmdyn_pack_f16)
+
+
+def linear_split_plan(name, w_offs, b_offs, K, Ns):
+    """nn.Linear(K, N_i) layers of the fp32 pose expert (vae.py:14-19, 118-123) on the fp16 tensor cores at fp32
+    accuracy: every operand is split x = hi + lo and the GEMMs run over the contraction dimension tripled,
+    activations as [hi | lo | hi], weights / gradients as [hi | hi | lo], so that one fp32-accumulating GEMM sums
+    hi*hi + lo*hi + hi*lo (mmdyn_split_f16).  Forward: rows [M][3K] x packed W [N][3K]; dgrad: rows [M][3N] x
+    packed W^T [K][3N] (the gradient rows are mode 1, so W^T is packed [hi | lo | hi]); wgrad: the split rows seen as
+    [3M][K] and [3M][N] matrices pair up segment by segment, dW lands in the torch layout [N][K] directly."""
+    N = int(sum(Ns))
+    rows, bias = [], []
+    for w_off, b_off, n_i in zip(w_offs, b_offs, Ns):
+        rows.append(w_off + np.arange(n_i)[:, None] * K + np.arange(K)[None, :])
+        bias.append(b_off + np.arange(n_i))
+    w = np.concatenate(rows, 0).astype(np.int64)                    # [N][K] arena indices
+    idx_fwd = np.concatenate([w, w, w | LO_BIT], 1).astype(np.int32)          # [N][3K]   hi | hi | lo
+    wt = np.ascontiguousarray(w.T)                                   # [K][N]
+    idx_dg = np.concatenate([wt, wt | LO_BIT, wt], 1).astype(np.int32)        # [K][3N]   hi | lo | hi
+    fwd = GemmGeom(P=1, OXv=1, IH=1, IW=1, Cin=3 * K, s_in=1, tap_dy=[[0]], tap_dx=[[0]], N=N, OH=1, OW=1,
+                   s_out=1, off_y=[0], off_x=[0], ldc=N)
+    dg = GemmGeom(P=1, OXv=1, IH=1, IW=1, Cin=3 * N, s_in=1, tap_dy=[[0]], tap_dx=[[0]], N=K, OH=1, OW=1,
+                  s_out=1, off_y=[0], off_x=[0], ldc=K)
+    wgs = [WgradGeom(P=1, OXv=1, IH=1, IW=1, Cg=K, s_in=1, tap_dy=[0], tap_dx=[0], Cn=int(n_i), nat_stride=N) for n_i in Ns]
+    return LayerPlan(name, "linear_split", fwd, idx_fwd, dg, idx_dg, None, None,
+                     bias_idx=np.concatenate(bias, 0).astype(np.int32),
+                     extra={"macs": 3 * K * N, "wgrads": wgs, "w_offs": list(w_offs), "Ns": [int(n) for n in Ns], "K": K})
+
+
 def conv1_plan(name, w_off):
     """nn.Conv2d(3, 32, 4, 2, 1, bias=False) on the fp32 NCHW input (vae.py:198): packed [32][64],
     k = ci*16 + kh*4 + kw (the torch layout), 48 used."""

@@ -239,9 +239,14 @@ def graph_case(dev, rank, world):
             dist.all_reduce(gsum)
             gavg = gsum / world
             want = w0 - 1e-3 * (0.1 * gavg / 0.1) / ((0.001 * gavg * gavg).sqrt() / (0.001 ** 0.5) + 1e-8)  # Adam, step 1
-            e = (arena.flat - want).abs().max().item()
-            log(f"[dp] graph step, scheme peer: parameters vs Adam(all-reduced local gradients): max abs diff {e:.2e}")
-            assert e < 2e-6, e
+            # entries with |g| ~ eps = 1e-8 amplify the summation-order difference between NCCL's all-reduce and the
+            # kernel's rank-order sum (step 1 of Adam is lr * g / (|g| + eps)): judge the well-conditioned entries
+            sel = gavg.abs() > 1e-5
+            e = (arena.flat - want)[sel].abs().max().item()
+            e_all = (arena.flat - want).abs().max().item()
+            log(f"[dp] graph step, scheme peer: parameters vs Adam(all-reduced local gradients): max abs diff {e:.2e} "
+                f"over the {int(sel.sum())} entries with |g| > 1e-5 ({e_all:.2e} over all, lr = 1e-3)")
+            assert e < 2e-6 and e_all < 1.01e-3, (e, e_all)
         torch.cuda.synchronize()
         ew = nrel(arena.flat - w0, w_ref - w0)
         log(f"[dp] graph step, scheme {scheme}: Adam displacement vs eager rel {ew:.2e} (loss rel {el:.1e})")

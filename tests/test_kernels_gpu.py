@@ -544,3 +544,80 @@ def test_philox_rng_statistics():
     keep = (mk > 0).float().mean().item()
     assert abs(keep - 0.9) < 2e-3
     assert torch.all((mk == 0) | ((mk - 1 / 0.9).abs() < 1e-6))
+
+
+@pytest.mark.parametrize("B", [8, 100, 1024])
+def test_pose_expert_on_tensor_cores_matches_fp64(B):
+    """Pose MLP encoder / decoder (vae.py:118-123, 219-222, 282-283) through engine.PoseExec: the 256/512-wide Linear
+    layers run on the fp16 tensor cores with the two-term split (mmdyn_split_f16 + mmdyn_igemm / mmdyn_wgrad), the
+    7-wide edge layers on the fp32 SIMT kernels.  north_star tolerance for the fp32 parts: 1e-5."""
+    from mmdyn_b200 import engine
+    from mmdyn_b200.pytorch.models.models import setup_model
+    torch.manual_seed(5)
+    model = setup_model("cnn-mvae", cross_modal=True, condition_dim=0, input_dim=4096, architecture="cnn",
+                        conditional=False, categorical_conditions=False, latent_size=256, use_pose=True)
+    sd = {k: v.clone().double() for k, v in model.state_dict().items() if k.startswith("pose_")}
+    model.to(DEV)
+    arena, ex = engine.get_execs(model, torch.device(DEV))
+    pex = ex["pose"]
+    assert pex.tc, "the tensor-core pose path is the default"
+    alloc = engine.Workspace(torch.device(DEV))
+    arena.attach_grads()
+    arena.grad.zero_()
+    # (seed chosen so that no first-layer pre-activation lands within fp32 round-off of zero: with seed B = 1024 one of
+    #  the 524,288 units sits at +1.2e-8 in fp64 and at 0 in fp32, and that single ReLU flip alone moves dW of the
+    #  7 -> 512 layer by 1e-2 in the max-norm used here — tools/pose_debug.py)
+    g = torch.Generator().manual_seed(B + 7)
+    pose, z = torch.rand(B, 7, generator=g), torch.randn(B, 256, generator=g)
+    d_heads, d_rec = torch.randn(B, 512, generator=g), 100.0 * torch.randn(B, 7, generator=g)
+    # ---- fp64 reference ----
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    h1 = F.relu(F.linear(pose.double(), P["pose_encoder.fc_net.0.weight"], P["pose_encoder.fc_net.0.bias"]))
+    h2 = F.linear(h1, P["pose_encoder.fc_net.2.weight"], P["pose_encoder.fc_net.2.bias"])
+    heads = torch.cat([F.linear(h2, P["pose_encoder.linear_means.weight"], P["pose_encoder.linear_means.bias"]),
+                       F.linear(h2, P["pose_encoder.linear_log_var.weight"], P["pose_encoder.linear_log_var.bias"])], 1)
+    zr = z.double().requires_grad_(True)
+    a1 = F.relu(F.linear(zr, P["pose_decoder.deconv_net.0.weight"], P["pose_decoder.deconv_net.0.bias"]))
+    a2 = F.relu(F.linear(a1, P["pose_decoder.deconv_net.2.weight"], P["pose_decoder.deconv_net.2.bias"]))
+    rec = F.linear(a2, P["pose_decoder.deconv_net.4.weight"], P["pose_decoder.deconv_net.4.bias"])
+    for t_ in (h1, h2, a1, a2):
+        t_.retain_grad()
+    ((heads * d_heads.double()).sum() + (rec * d_rec.double()).sum()).backward()
+    # ---- B200 path ----
+    r_e = pex.enc_forward(pose.to(DEV), alloc, "penc")
+    r_d = pex.dec_forward(z.to(DEV), alloc, "pdec")
+    pex.enc_backward(r_e, d_heads.to(DEV), alloc, "penc", 0.5)
+    dz = pex.dec_backward(r_d, d_rec.to(DEV), alloc, "pdec", 0.5)
+    torch.cuda.synchronize()
+    errs = {"heads": rel_err(r_e["heads"], heads), "rec": rel_err(r_d["rec"], rec), "dz": rel_err(dz, zr.grad),
+            "dh2": rel_err(alloc.bufs["penc.dh2"], h2.grad), "dh1": rel_err(alloc.bufs["penc.dh1"], h1.grad),
+            "da2": rel_err(alloc.bufs["pdec.da2"], a2.grad), "da1": rel_err(alloc.bufs["pdec.da1"], a1.grad)}
+    named = dict(model.named_parameters())
+    for k in P:
+        errs[k] = rel_err(named[k].grad, 0.5 * P[k].grad)
+    print(f"pose expert on tensor cores, B={B}: " + ", ".join(f"{k.replace('pose_', '')} {v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < 1e-5, (k, v)
+
+
+@pytest.mark.parametrize("M", [1000, 1024, 2048])
+def test_linear_f32_first_pose_layer_without_dx(M):
+    """Linear(7, 512) + ReLU backward exactly as the pose encoder calls it (dx = None)."""
+    ops = _ops()
+    torch.manual_seed(3)
+    N, K = 512, 7
+    x, w, b = torch.rand(M, K), torch.randn(N, K) * 0.3, torch.randn(N) * 0.1
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    y = F.relu(F.linear(xr, wr, br))
+    dy = torch.randn(M, N)
+    y.backward(dy.double())
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    yd = torch.empty(M, N, device=DEV)
+    ops.linear_f32_fwd(xd, wd, bd, yd, M, N, K, K, N, 1)
+    dya = torch.empty(M, N, device=DEV)
+    dW, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    ops.linear_f32_bwd(xd, wd, yd, dy.to(DEV), dya, None, dW, db, M, N, K, K, N, K, 1, False, 0.5)
+    torch.cuda.synchronize()
+    e = (rel_err(yd, y), rel_err(dW, 0.5 * wr.grad), rel_err(db, 0.5 * br.grad))
+    print(f"linear_f32 (M={M}, 512 <- 7, relu, dx=None): y {e[0]:.1e} dW {e[1]:.1e} db {e[2]:.1e}")
+    assert max(e) < 1e-5, e
