@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 namespace mmdyn {
 extern std::atomic<long long> g_launch_count;
@@ -12,6 +13,11 @@ int igemm_init();
 int elementwise_init();
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+  static const bool on = std::getenv("MMDYN_NO_PDL") == nullptr;
+  return on;
+}
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;

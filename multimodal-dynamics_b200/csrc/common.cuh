@@ -39,6 +39,44 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_sync():
+//   griddepcontrol.wait               block until the preceding grid of the stream has completed and its memory is
+//                                     visible (a no-op for a launch without programmatic predecessor), then
+//   griddepcontrol.launch_dependents  allow the NEXT grid of the stream to be scheduled as SMs free up: its CTAs run
+//                                     their prologue (barrier init, TMEM allocation, descriptor prefetch) and park
+//                                     at their own griddepcontrol.wait while this grid drains.
+// At small batch the step is ~200 kernels of 5-10 us each on three concurrent branches: the launch + prologue
+// latency of kernel k+1 hides behind the tail of kernel k (also inside captured CUDA graphs).  MMDYN_NO_PDL=1 turns
+// the launch attribute off (A/B); the device-side instructions are then no-ops.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+bool pdl_enabled();  // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define MMDYN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)::mmdyn::launch_pdl(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), stream, __VA_ARGS__)
+
+// ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -50,6 +50,7 @@ constexpr int RED_THREADS = 256;
 __global__ void __launch_bounds__(RED_THREADS)
 bn_stats_kernel(const __half* __restrict__ x, float* __restrict__ sums, int rows_per_group, int C,
                 int rows_per_chunk) {
+  pdl_sync();
   extern __shared__ float red[];  // [row_lanes][C][2]
   const int vpr = C >> 3;
   const int row_lanes = RED_THREADS / vpr;
@@ -90,6 +91,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
                                    float* __restrict__ mean_invstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int G, int n, int C, float eps,
                                    float momentum, int stat_repeat, long long* __restrict__ num_batches_tracked) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches_tracked) *num_batches_tracked += static_cast<long long>(G) * stat_repeat;
   if (c >= C) return;
@@ -123,6 +125,7 @@ constexpr int EW_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 bn_swish_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
                     long long n_vec, int rows_per_group, int C) {
+  pdl_sync();
   const int vpr = C >> 3;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < n_vec;
@@ -164,6 +167,7 @@ bn_swish_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ ab, 
 __global__ void __launch_bounds__(RED_THREADS)
 bn_swish_fwd_rows_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
                          int rows_per_group, int C, int rows_per_chunk) {
+  pdl_sync();
   const int vpr = C >> 3;
   const int row_lanes = RED_THREADS / vpr;
   const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;
@@ -202,6 +206,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
                            const float* __restrict__ mean_invstd, const __half* __restrict__ dY,
                            float* __restrict__ sums2, int rows_per_group, int C, int rows_per_chunk) {
+  pdl_sync();
   extern __shared__ float red[];
   const int vpr = C >> 3;
   const int row_lanes = RED_THREADS / vpr;
@@ -260,6 +265,7 @@ bn_swish_bwd_reduce_kernel(const __half* __restrict__ x, const float* __restrict
 // plain Swish backward in place: dX = dY * swish'(x)
 __global__ void __launch_bounds__(256)
 swish_bwd_kernel(const __half* __restrict__ x, __half* __restrict__ dY, long long n_vec) {
+  pdl_sync();
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n_vec;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     float fx[8], fd[8];
@@ -277,6 +283,7 @@ swish_bwd_kernel(const __half* __restrict__ x, __half* __restrict__ dY, long lon
 __global__ void bn_bwd_coef_kernel(const float* __restrict__ ab, const float* __restrict__ mean_invstd,
                                    const float* __restrict__ sums2, float* __restrict__ coef, int GC,
                                    float inv_n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= GC) return;
   const float a = ab[2 * i], mean = mean_invstd[2 * i], invstd = mean_invstd[2 * i + 1];
@@ -290,6 +297,7 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ ab, const float* __
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_kernel(const __half* __restrict__ x, const float* __restrict__ coef, __half* __restrict__ dU,
                     int rows_per_group, int C, int rows_per_chunk) {
+  pdl_sync();
   const int vpr = C >> 3;
   const int row_lanes = RED_THREADS / vpr;
   const int vec = threadIdx.x % vpr, rl = threadIdx.x / vpr;
@@ -415,6 +423,7 @@ template <int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_stats_bulk_kernel(const __half* __restrict__ x, float* __restrict__ sums, int rows_per_group, int C,
                      int rows_per_chunk) {
+  pdl_sync();
   BS_PROLOGUE(1, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
   BS_START(STAGES);
@@ -460,6 +469,7 @@ template <int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_swish_fwd_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ ab, __half* __restrict__ y,
                          int rows_per_group, int C, int rows_per_chunk, BnFinalizeArgs fin) {
+  pdl_sync();
   BS_PROLOGUE(1, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
   BS_START(STAGES);
@@ -540,6 +550,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 bn_swish_bwd_reduce_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ ab,
                                 const float* __restrict__ mean_invstd, const __half* __restrict__ dY,
                                 float* __restrict__ sums2, int rows_per_group, int C, int rows_per_chunk) {
+  pdl_sync();
   BS_PROLOGUE(2, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
   st.src[1] = reinterpret_cast<const uint8_t*>(dY + base);
@@ -596,6 +607,7 @@ template <int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ coef, __half* __restrict__ dU,
                          int rows_per_group, int C, int rows_per_chunk, BnBwdFinalArgs fin) {
+  pdl_sync();
   BS_PROLOGUE(2, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
   st.src[1] = reinterpret_cast<const uint8_t*>(dU + base);
@@ -663,6 +675,7 @@ bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums2, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int G, int C, float unscale) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s1 = 0.0f, s2 = 0.0f;
@@ -684,6 +697,7 @@ struct MaskPtrs {
 __global__ void __launch_bounds__(256)
 swish_dropout_fwd_kernel(const float* __restrict__ raw, MaskPtrs masks, __half* __restrict__ h,
                          int n_masks, long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float s = swishf_(raw[i]);
@@ -697,6 +711,7 @@ swish_dropout_fwd_kernel(const float* __restrict__ raw, MaskPtrs masks, __half* 
 __global__ void __launch_bounds__(256)
 swish_dropout_bwd_kernel(const float* __restrict__ raw, MaskPtrs masks, const float* __restrict__ dH,
                          __half* __restrict__ dRaw, int n_masks, long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float acc = 0.0f;
@@ -725,6 +740,7 @@ __global__ void __launch_bounds__(256)
 poe_fwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
                float* __restrict__ mu_o, float* __restrict__ lv_o, float* __restrict__ z_o,
                __half* __restrict__ zh_o, __half* __restrict__ zh2_o, float* __restrict__ kl_sum, int B, int D) {
+  pdl_sync();
   const long long n = static_cast<long long>(B) * D;
   float kl = 0.0f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -775,6 +791,7 @@ __global__ void __launch_bounds__(256)
 poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
                const float* __restrict__ dmu_in, const float* __restrict__ dlv_in, float kl_coef, int ld_out,
                int accumulate, int B, int D) {
+  pdl_sync();
   const long long n = static_cast<long long>(B) * D;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -851,6 +868,7 @@ __global__ void __launch_bounds__(256)
 bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                   const float* __restrict__ mask, float* __restrict__ loss_sum,
                   __half* __restrict__ dlogits, float gscale, long long n_pix, int HW, int W, int pad) {
+  pdl_sync();
   float acc = 0.0f;
   const long long n_quad = n_pix >> 2;  // W is a multiple of 4 (checked by the launcher)
   const int H = HW / W, Wp = W + 2 * pad, Hp = H + 2 * pad;
@@ -899,6 +917,7 @@ __global__ void __launch_bounds__(256)
 bce_flat_kernel(const float* __restrict__ logits, const float* __restrict__ target, const float* __restrict__ mask,
                 float* __restrict__ loss_sum, float* __restrict__ per_sample_sum, float* __restrict__ dlogits,
                 float gscale, int per_sample) {
+  pdl_sync();
   const long long base = static_cast<long long>(blockIdx.y) * per_sample;
   float acc = 0.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
@@ -917,6 +936,7 @@ bce_flat_kernel(const float* __restrict__ logits, const float* __restrict__ targ
 
 __global__ void mse_rows_kernel(const float* __restrict__ recon, const float* __restrict__ target,
                                 float* __restrict__ row_sum, float mult, int n, int d) {
+  pdl_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   float acc = 0.0f;
@@ -930,6 +950,7 @@ __global__ void mse_rows_kernel(const float* __restrict__ recon, const float* __
 __global__ void __launch_bounds__(256)
 mse_kernel(const float* __restrict__ recon, const float* __restrict__ target, float* __restrict__ loss_sum,
            float* __restrict__ drecon, float mult, float gscale, long long n) {
+  pdl_sync();
   float acc = 0.0f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -947,6 +968,7 @@ mse_kernel(const float* __restrict__ recon, const float* __restrict__ target, fl
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, int ld, float scale,
               int rows_per_cta) {
+  pdl_sync();
   // thread -> column (coalesced across the row), loop over the CTA's rows
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -960,6 +982,7 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const __half* __restrict__ x, float* __restrict__ out, int M, int N, int ld, float scale,
                   int rows_per_cta) {
+  pdl_sync();
   __shared__ float red[8][256 + 1];
   const int vl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * 32 + vl) * 8;
@@ -988,6 +1011,7 @@ colsum_f16_kernel(const __half* __restrict__ x, float* __restrict__ out, int M, 
 __global__ void __launch_bounds__(256)
 pack_f16_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, __half* __restrict__ dst,
                 long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int32_t j = idx[i];
@@ -1019,6 +1043,7 @@ __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ x, const float* __restrict__ mask_y, float* __restrict__ x_out,
                  __half* __restrict__ out, int M, int N, int mode, int relu, float* __restrict__ colsum0,
                  float* __restrict__ colsum1, int n_split, float colsum_scale, int rows_per_cta) {
+  pdl_sync();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -1047,6 +1072,7 @@ split_f16_kernel(const float* __restrict__ x, const float* __restrict__ mask_y, 
 __global__ void __launch_bounds__(256)
 gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
                   long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int32_t j = idx[i];
@@ -1057,6 +1083,7 @@ gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx
 __global__ void __launch_bounds__(256)
 unpack_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
                   long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int32_t j = idx[i];
@@ -1069,6 +1096,7 @@ unpack_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx
 __global__ void __launch_bounds__(256)
 gather_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ inv, float* __restrict__ dst,
                   long long n) {
+  pdl_sync();
   for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int32_t i = __ldg(inv + k);
@@ -1078,6 +1106,7 @@ gather_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ inv
 
 __global__ void __launch_bounds__(256)
 f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n, float scale) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dst[i] = __float2half_rn(scale * src[i]);
@@ -1085,6 +1114,7 @@ f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long 
 
 __global__ void __launch_bounds__(256)
 scale_f32_kernel(float* __restrict__ x, long long n, float s) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     x[i] *= s;
@@ -1093,6 +1123,7 @@ scale_f32_kernel(float* __restrict__ x, long long n, float s) {
 __global__ void __launch_bounds__(256)
 logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, float scale, long long n_pix,
                        int HW, int W, int pad) {
+  pdl_sync();
   const int H = HW / W, Wp = W + 2 * pad, Hp = H + 2 * pad;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pix;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1114,6 +1145,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
             float bc1, float bc2_sqrt, float gscale, const uint64_t* __restrict__ step_dev,
             unsigned int* __restrict__ nonfinite) {
+  pdl_sync();
   // `nonfinite` (optional): a gradient entry that is inf / NaN (fp16 overflow somewhere in the backward,
   // or a poisoned input) leaves its parameter and moments untouched and raises the sticky flag, which the
   // host reads together with the loss — the step never trains on a non-finite number.
@@ -1173,6 +1205,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
            float lr, float momentum, float wd, int first_step, float gscale, unsigned int* __restrict__ nonfinite) {
+  pdl_sync();
   bool bad = false;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1211,6 +1244,7 @@ __device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
 __global__ void __launch_bounds__(256)
 fill_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset,
                    const uint64_t* __restrict__ ctr) {
+  pdl_sync();
   if (ctr) offset += *ctr;
   const long long n4 = (n + 3) >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
@@ -1233,6 +1267,7 @@ fill_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t
 __global__ void __launch_bounds__(256)
 fill_dropout_kernel(float* __restrict__ out, long long n, float p_drop, float keep_scale, uint64_t seed,
                     uint64_t offset, const uint64_t* __restrict__ ctr) {
+  pdl_sync();
   if (ctr) offset += *ctr;
   const long long n4 = (n + 3) >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
@@ -1247,7 +1282,8 @@ fill_dropout_kernel(float* __restrict__ out, long long n, float p_drop, float ke
   }
 }
 
-__global__ void rng_advance_kernel(uint64_t* ctr, uint64_t inc) { *ctr += inc; }
+__global__ void rng_advance_kernel(uint64_t* ctr, uint64_t inc) {
+  pdl_sync(); *ctr += inc; }
 
 inline int grid_for(long long n, int threads = 256, int max_blocks = 148 * 8) {
   long long b = (n + threads - 1) / threads;
@@ -1313,14 +1349,14 @@ extern "C" int mmdyn_bn_stats(const void* x, float* sums, int G, int rows_per_gr
   int rpc;
   if (use_bulk() && bulk_ok(C)) {
     const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
-    bn_stats_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES, ST(stream)>>>(
+    MMDYN_LAUNCH((bn_stats_bulk_kernel<BS_STAGES_1IN>), dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES, ST(stream), 
         reinterpret_cast<const __half*>(x), sums, rows_per_group, C, rpc);
     LAUNCHED();
     return MMDYN_OK;
   }
   const int chunks = chunking(rows_per_group, G, C, &rpc);
   const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
-  bn_stats_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
+  MMDYN_LAUNCH((bn_stats_kernel), dim3(chunks, G), RED_THREADS, smem, ST(stream), 
       reinterpret_cast<const __half*>(x), sums, rows_per_group, C, rpc);
   LAUNCHED();
   return MMDYN_OK;
@@ -1331,7 +1367,7 @@ extern "C" int mmdyn_bn_finalize(const float* sums, const float* gamma, const fl
                                  int rows_per_group, int C, float eps, float momentum, int stat_repeat,
                                  long long* num_batches_tracked, void* stream) {
   MMDYN_REQUIRE(sums && gamma && beta && ab && mean_invstd && G > 0 && C > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, gamma, beta, ab, mean_invstd, running_mean,
+  MMDYN_LAUNCH((bn_finalize_kernel), (C + 127) / 128, 128, 0, ST(stream), sums, gamma, beta, ab, mean_invstd, running_mean,
                                                                running_var, G, rows_per_group, C, eps, momentum,
                                                                stat_repeat, num_batches_tracked);
   LAUNCHED();
@@ -1346,8 +1382,8 @@ extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G
     int rpc;
     const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
     BnFinalizeArgs fin = {};
-    bn_swish_fwd_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
-                                              ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
+    MMDYN_LAUNCH((bn_swish_fwd_bulk_kernel<BS_STAGES_1IN>), dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
+                                              ST(stream), reinterpret_cast<const __half*>(x), ab,
                                                             reinterpret_cast<__half*>(y), rows_per_group, C, rpc, fin);
     LAUNCHED();
     return MMDYN_OK;
@@ -1355,12 +1391,12 @@ extern "C" int mmdyn_bn_swish_fwd(const void* x, const float* ab, void* y, int G
   if (ab && bn_c_ok(C)) {
     int rpc;
     const int chunks = chunking(rows_per_group, G, C, &rpc);
-    bn_swish_fwd_rows_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
+    MMDYN_LAUNCH((bn_swish_fwd_rows_kernel), dim3(chunks, G), RED_THREADS, 0, ST(stream), 
         reinterpret_cast<const __half*>(x), ab, reinterpret_cast<__half*>(y), rows_per_group, C, rpc);
     LAUNCHED();
     return MMDYN_OK;
   }
-  bn_swish_fwd_kernel<<<grid_for(n_vec / EW_UNROLL + 1), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), ab,
+  MMDYN_LAUNCH((bn_swish_fwd_kernel), grid_for(n_vec / EW_UNROLL + 1), 256, 0, ST(stream), reinterpret_cast<const __half*>(x), ab,
                                                                reinterpret_cast<__half*>(y), n_vec,
                                                                rows_per_group, C);
   LAUNCHED();
@@ -1378,8 +1414,8 @@ extern "C" int mmdyn_bn_finalize_swish_fwd(const void* x, const float* sums, con
     const int chunks = bulk_chunking(rows_per_group, G, C, 3, &rpc);
     BnFinalizeArgs fin = {sums, gamma, beta, ab, mean_invstd, running_mean, running_var, num_batches_tracked,
                           eps, momentum, stat_repeat};
-    bn_swish_fwd_bulk_kernel<BS_STAGES_1IN><<<dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
-                                              ST(stream)>>>(reinterpret_cast<const __half*>(x), nullptr,
+    MMDYN_LAUNCH((bn_swish_fwd_bulk_kernel<BS_STAGES_1IN>), dim3(chunks, G), RED_THREADS, BS_STAGES_1IN * BS_STAGE_BYTES,
+                                              ST(stream), reinterpret_cast<const __half*>(x), nullptr,
                                                             reinterpret_cast<__half*>(y), rows_per_group, C, rpc, fin);
     LAUNCHED();
     return MMDYN_OK;
@@ -1395,7 +1431,7 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
   MMDYN_REQUIRE(x && dY && G > 0 && rows_per_group > 0 && C % 8 == 0, "bn_swish_bwd_reduce: bad arguments");
   if (!ab) {
     const long long n_vec = static_cast<long long>(G) * rows_per_group * (C >> 3);
-    swish_bwd_kernel<<<grid_for(n_vec), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x),
+    MMDYN_LAUNCH((swish_bwd_kernel), grid_for(n_vec), 256, 0, ST(stream), reinterpret_cast<const __half*>(x),
                                                               reinterpret_cast<__half*>(dY), n_vec);
     LAUNCHED();
     return MMDYN_OK;
@@ -1404,8 +1440,7 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
   int rpc;
   if (use_bulk() && bulk_ok(C)) {
     const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
-    bn_swish_bwd_reduce_bulk_kernel<BS_STAGES_2IN>
-        <<<dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream)>>>(
+    MMDYN_LAUNCH((bn_swish_bwd_reduce_bulk_kernel<BS_STAGES_2IN>), dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream), 
             reinterpret_cast<const __half*>(x), ab, mean_invstd, reinterpret_cast<const __half*>(dY), sums2,
             rows_per_group, C, rpc);
     LAUNCHED();
@@ -1413,7 +1448,7 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
   }
   const int chunks = chunking(rows_per_group, G, C, &rpc);
   const size_t smem = static_cast<size_t>(RED_THREADS / (C >> 3)) * C * 2 * sizeof(float);
-  bn_swish_bwd_reduce_kernel<<<dim3(chunks, G), RED_THREADS, smem, ST(stream)>>>(
+  MMDYN_LAUNCH((bn_swish_bwd_reduce_kernel), dim3(chunks, G), RED_THREADS, smem, ST(stream), 
       reinterpret_cast<const __half*>(x), ab, mean_invstd, reinterpret_cast<const __half*>(dY), sums2,
       rows_per_group, C, rpc);
   LAUNCHED();
@@ -1431,21 +1466,20 @@ extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* m
     const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
     BnBwdFinalArgs fin = {ab, mean_invstd, sums2, dgamma, dbeta, 1.0f / static_cast<float>(rows_per_group),
                           grad_unscale};
-    bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>
-        <<<dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream)>>>(
+    MMDYN_LAUNCH((bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>), dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream), 
             reinterpret_cast<const __half*>(x), nullptr, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc, fin);
     LAUNCHED();
     return MMDYN_OK;
   }
-  bn_bwd_coef_kernel<<<(G * C + 127) / 128, 128, 0, ST(stream)>>>(ab, mean_invstd, sums2, coef_scratch, G * C,
+  MMDYN_LAUNCH((bn_bwd_coef_kernel), (G * C + 127) / 128, 128, 0, ST(stream), ab, mean_invstd, sums2, coef_scratch, G * C,
                                                                    1.0f / static_cast<float>(rows_per_group));
   LAUNCHED();
   const int chunks = chunking(rows_per_group, G, C, &rpc);
-  bn_bwd_apply_kernel<<<dim3(chunks, G), RED_THREADS, 0, ST(stream)>>>(
+  MMDYN_LAUNCH((bn_bwd_apply_kernel), dim3(chunks, G), RED_THREADS, 0, ST(stream), 
       reinterpret_cast<const __half*>(x), coef_scratch, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc);
   LAUNCHED();
   if (dgamma && dbeta) {
-    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums2, dgamma, dbeta, G, C, grad_unscale);
+    MMDYN_LAUNCH((bn_param_grad_kernel), (C + 127) / 128, 128, 0, ST(stream), sums2, dgamma, dbeta, G, C, grad_unscale);
     LAUNCHED();
   }
   return MMDYN_OK;
@@ -1457,7 +1491,7 @@ extern "C" int mmdyn_swish_dropout_fwd(const float* raw, const float* const* mas
   MaskPtrs mp;
   for (int i = 0; i < 8; ++i) mp.p[i] = (masks && i < n_masks) ? masks[i] : nullptr;
   const long long n = static_cast<long long>(B) * C;
-  swish_dropout_fwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(raw, mp, reinterpret_cast<__half*>(h), n_masks, n);
+  MMDYN_LAUNCH((swish_dropout_fwd_kernel), grid_for(n), 256, 0, ST(stream), raw, mp, reinterpret_cast<__half*>(h), n_masks, n);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1468,7 +1502,7 @@ extern "C" int mmdyn_swish_dropout_bwd(const float* raw, const float* const* mas
   MaskPtrs mp;
   for (int i = 0; i < 8; ++i) mp.p[i] = (masks && i < n_masks) ? masks[i] : nullptr;
   const long long n = static_cast<long long>(B) * C;
-  swish_dropout_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(raw, mp, dH, reinterpret_cast<__half*>(dRaw),
+  MMDYN_LAUNCH((swish_dropout_bwd_kernel), grid_for(n), 256, 0, ST(stream), raw, mp, dH, reinterpret_cast<__half*>(dRaw),
                                                                 n_masks, n);
   LAUNCHED();
   return MMDYN_OK;
@@ -1486,7 +1520,7 @@ extern "C" int mmdyn_poe_fwd(const float* const* mu_e, const float* const* lv_e,
     ex.lv[e] = lv_e[e];
   }
   const long long n = static_cast<long long>(B) * D;
-  poe_fwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(ex, n_experts, use_prior, ld, eps, mu, lv, z,
+  MMDYN_LAUNCH((poe_fwd_kernel), grid_for(n), 256, 0, ST(stream), ex, n_experts, use_prior, ld, eps, mu, lv, z,
                                                       reinterpret_cast<__half*>(zh), reinterpret_cast<__half*>(zh2),
                                                       kl_sum, B, D);
   LAUNCHED();
@@ -1510,7 +1544,7 @@ extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e,
   }
   for (int q = 0; q < 3; ++q) ex.dz[q] = dz ? dz[q] : nullptr;
   const long long n = static_cast<long long>(B) * D;
-  poe_bwd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(ex, n_experts, use_prior, ld, eps, dmu_in, dlv_in, kl_coef,
+  MMDYN_LAUNCH((poe_bwd_kernel), grid_for(n), 256, 0, ST(stream), ex, n_experts, use_prior, ld, eps, dmu_in, dlv_in, kl_coef,
                                                       ld_out, accumulate, B, D);
   LAUNCHED();
   return MMDYN_OK;
@@ -1522,7 +1556,7 @@ extern "C" int mmdyn_bce_logits(const float* logits, const float* target, const 
                 "bce_logits: bad arguments (n=%d H=%d W=%d pad=%d; W must be a multiple of 4)", n, H, W, pad);
   const int HW = H * W;
   const long long n_pix = static_cast<long long>(n) * HW;
-  bce_logits_kernel<<<grid_for(n_pix >> 2), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum,
+  MMDYN_LAUNCH((bce_logits_kernel), grid_for(n_pix >> 2), 256, 0, ST(stream), logits, target, mask, loss_sum,
                                                              reinterpret_cast<__half*>(dlogits_nhwc8), gscale,
                                                              n_pix, HW, W, pad);
   LAUNCHED();
@@ -1537,7 +1571,7 @@ extern "C" int mmdyn_bce_logits_flat(const float* logits, const float* target, c
   const int max_chunks = (per_sample + 1023) / 1024;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
-  bce_flat_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(logits, target, mask, loss_sum, per_sample_sum, dlogits,
+  MMDYN_LAUNCH((bce_flat_kernel), dim3(chunks, n), 256, 0, ST(stream), logits, target, mask, loss_sum, per_sample_sum, dlogits,
                                                            gscale, per_sample);
   LAUNCHED();
   return MMDYN_OK;
@@ -1546,7 +1580,7 @@ extern "C" int mmdyn_bce_logits_flat(const float* logits, const float* target, c
 extern "C" int mmdyn_mse_rows(const float* recon, const float* target, float* row_sum, float mult, int n, int d,
                               void* stream) {
   MMDYN_REQUIRE(recon && target && row_sum && n > 0 && d > 0, "mse_rows: bad arguments");
-  mse_rows_kernel<<<(n + 127) / 128, 128, 0, ST(stream)>>>(recon, target, row_sum, mult, n, d);
+  MMDYN_LAUNCH((mse_rows_kernel), (n + 127) / 128, 128, 0, ST(stream), recon, target, row_sum, mult, n, d);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1554,7 +1588,7 @@ extern "C" int mmdyn_mse_rows(const float* recon, const float* target, float* ro
 extern "C" int mmdyn_mse(const float* recon, const float* target, float* loss_sum, float* drecon, float mult,
                          float gscale, int n, void* stream) {
   MMDYN_REQUIRE(recon && target && loss_sum && n > 0, "mse: bad arguments");
-  mse_kernel<<<grid_for(n, 256, 64), 256, 0, ST(stream)>>>(recon, target, loss_sum, drecon, mult, gscale, n);
+  MMDYN_LAUNCH((mse_kernel), grid_for(n, 256, 64), 256, 0, ST(stream), recon, target, loss_sum, drecon, mult, gscale, n);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1566,7 +1600,7 @@ extern "C" int mmdyn_colsum_f32(const float* x, float* out, int M, int N, int ld
   int rpc = (M + row_ctas - 1) / row_ctas;
   if (rpc < 16) rpc = 16;
   const int gy = (M + rpc - 1) / rpc;
-  colsum_kernel<<<dim3((N + 255) / 256, gy), 256, 0, ST(stream)>>>(x, out, M, N, ld, scale, rpc);
+  MMDYN_LAUNCH((colsum_kernel), dim3((N + 255) / 256, gy), 256, 0, ST(stream), x, out, M, N, ld, scale, rpc);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1579,7 +1613,7 @@ extern "C" int mmdyn_colsum_f16(const void* x, float* out, int M, int N, int ld,
   int rpc = (M + row_ctas - 1) / row_ctas;
   if (rpc < 32) rpc = 32;
   const int gy = (M + rpc - 1) / rpc;
-  colsum_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(x), out, M, N, ld, scale,
+  MMDYN_LAUNCH((colsum_f16_kernel), dim3(gx, gy), 256, 0, ST(stream), reinterpret_cast<const __half*>(x), out, M, N, ld, scale,
                                                           rpc);
   LAUNCHED();
   return MMDYN_OK;
@@ -1587,7 +1621,7 @@ extern "C" int mmdyn_colsum_f16(const void* x, float* out, int M, int N, int ld,
 
 extern "C" int mmdyn_pack_f16(const float* src, const int32_t* idx, void* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && idx && dst && n > 0, "pack_f16: bad arguments");
-  pack_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, reinterpret_cast<__half*>(dst), n);
+  MMDYN_LAUNCH((pack_f16_kernel), grid_for(n), 256, 0, ST(stream), src, idx, reinterpret_cast<__half*>(dst), n);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1602,7 +1636,7 @@ extern "C" int mmdyn_split_f16(const float* x, const float* mask_y, float* x_out
   int rpc = (M + row_ctas - 1) / row_ctas;
   if (rpc < 8) rpc = 8;
   const int gy = (M + rpc - 1) / rpc;
-  split_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(x, mask_y, x_out, reinterpret_cast<__half*>(out), M, N, mode, relu,
+  MMDYN_LAUNCH((split_f16_kernel), dim3(gx, gy), 256, 0, ST(stream), x, mask_y, x_out, reinterpret_cast<__half*>(out), M, N, mode, relu,
                                                          colsum0, colsum1, colsum0 && !colsum1 ? N : n_split, colsum_scale,
                                                          rpc);
   LAUNCHED();
@@ -1611,35 +1645,35 @@ extern "C" int mmdyn_split_f16(const float* x, const float* mask_y, float* x_out
 
 extern "C" int mmdyn_gather_f32(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && idx && dst && n > 0, "gather_f32: bad arguments");
-  gather_f32_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  MMDYN_LAUNCH((gather_f32_kernel), grid_for(n), 256, 0, ST(stream), src, idx, dst, n);
   LAUNCHED();
   return MMDYN_OK;
 }
 
 extern "C" int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && idx && dst && n > 0, "unpack_add: bad arguments");
-  unpack_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, idx, dst, n);
+  MMDYN_LAUNCH((unpack_add_kernel), grid_for(n), 256, 0, ST(stream), src, idx, dst, n);
   LAUNCHED();
   return MMDYN_OK;
 }
 
 extern "C" int mmdyn_gather_add_f32(const float* src, const int32_t* inv, float* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && inv && dst && n > 0, "gather_add: bad arguments");
-  gather_add_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, inv, dst, n);
+  MMDYN_LAUNCH((gather_add_kernel), grid_for(n), 256, 0, ST(stream), src, inv, dst, n);
   LAUNCHED();
   return MMDYN_OK;
 }
 
 extern "C" int mmdyn_f32_to_f16(const float* src, void* dst, long long n, float scale, void* stream) {
   MMDYN_REQUIRE(src && dst && n > 0, "f32_to_f16: bad arguments");
-  f32_to_f16_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(src, reinterpret_cast<__half*>(dst), n, scale);
+  MMDYN_LAUNCH((f32_to_f16_kernel), grid_for(n), 256, 0, ST(stream), src, reinterpret_cast<__half*>(dst), n, scale);
   LAUNCHED();
   return MMDYN_OK;
 }
 
 extern "C" int mmdyn_scale_f32(float* x, long long n, float s, void* stream) {
   MMDYN_REQUIRE(x && n > 0, "scale_f32: bad arguments");
-  scale_f32_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(x, n, s);
+  MMDYN_LAUNCH((scale_f32_kernel), grid_for(n), 256, 0, ST(stream), x, n, s);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1649,7 +1683,7 @@ extern "C" int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8,
   MMDYN_REQUIRE(dlogits_nchw && out_nhwc8 && n > 0 && H > 0 && W > 0 && pad >= 0, "logit_grad_pack: bad arguments");
   const int HW = H * W;
   const long long n_pix = static_cast<long long>(n) * HW;
-  logit_grad_pack_kernel<<<grid_for(n_pix), 256, 0, ST(stream)>>>(dlogits_nchw, reinterpret_cast<__half*>(out_nhwc8),
+  MMDYN_LAUNCH((logit_grad_pack_kernel), grid_for(n_pix), 256, 0, ST(stream), dlogits_nchw, reinterpret_cast<__half*>(out_nhwc8),
                                                                   scale, n_pix, HW, W, pad);
   LAUNCHED();
   return MMDYN_OK;
@@ -1664,7 +1698,7 @@ extern "C" int mmdyn_adam_flat(float* p, const float* g, float* m, float* v, lon
                 "adam_flat: arenas must be 16-byte aligned");
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step_count);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step_count);
-  adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+  MMDYN_LAUNCH((adam_kernel), grid_for(n >> 2), 256, 0, ST(stream), p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                         static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
                                                         gscale, nullptr, nullptr);
   LAUNCHED();
@@ -1679,7 +1713,7 @@ extern "C" int mmdyn_adam_flat_guarded(float* p, const float* g, float* m, float
   MMDYN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                 "adam_flat_devstep: arenas must be 16-byte aligned");
-  adam_kernel<<<grid_for(n >> 2), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f,
+  MMDYN_LAUNCH((adam_kernel), grid_for(n >> 2), 256, 0, ST(stream), p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.0f,
                                                         1.0f, gscale, step_dev, nonfinite_flag);
   LAUNCHED();
   return MMDYN_OK;
@@ -1700,7 +1734,7 @@ extern "C" int mmdyn_sgd_flat_guarded(float* p, const float* g, float* buf, long
                                       float weight_decay, int first_step, float gscale, unsigned int* nonfinite_flag,
                                       void* stream) {
   MMDYN_REQUIRE(p && g && buf && n > 0, "sgd_flat: bad arguments");
-  sgd_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, first_step, gscale,
+  MMDYN_LAUNCH((sgd_kernel), grid_for(n), 256, 0, ST(stream), p, g, buf, n, lr, momentum, weight_decay, first_step, gscale,
                                                   nonfinite_flag);
   LAUNCHED();
   return MMDYN_OK;
@@ -1708,7 +1742,7 @@ extern "C" int mmdyn_sgd_flat_guarded(float* p, const float* g, float* buf, long
 
 extern "C" int mmdyn_rng_advance(uint64_t* ctr_dev, uint64_t inc, void* stream) {
   MMDYN_REQUIRE(ctr_dev, "rng_advance: null counter");
-  rng_advance_kernel<<<1, 1, 0, ST(stream)>>>(ctr_dev, inc);
+  MMDYN_LAUNCH((rng_advance_kernel), 1, 1, 0, ST(stream), ctr_dev, inc);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1716,7 +1750,7 @@ extern "C" int mmdyn_rng_advance(uint64_t* ctr_dev, uint64_t inc, void* stream) 
 extern "C" int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_t offset, const uint64_t* ctr_dev,
                                  void* stream) {
   MMDYN_REQUIRE(out && n > 0, "fill_normal: bad arguments");
-  fill_normal_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, seed, offset, ctr_dev);
+  MMDYN_LAUNCH((fill_normal_kernel), grid_for((n + 3) >> 2), 256, 0, ST(stream), out, n, seed, offset, ctr_dev);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1724,7 +1758,7 @@ extern "C" int mmdyn_fill_normal(float* out, long long n, uint64_t seed, uint64_
 extern "C" int mmdyn_fill_dropout_mask(float* out, long long n, float p_drop, uint64_t seed, uint64_t offset,
                                        const uint64_t* ctr_dev, void* stream) {
   MMDYN_REQUIRE(out && n > 0 && p_drop >= 0.0f && p_drop < 1.0f, "fill_dropout_mask: bad arguments");
-  fill_dropout_kernel<<<grid_for((n + 3) >> 2), 256, 0, ST(stream)>>>(out, n, p_drop, 1.0f / (1.0f - p_drop), seed,
+  MMDYN_LAUNCH((fill_dropout_kernel), grid_for((n + 3) >> 2), 256, 0, ST(stream), out, n, p_drop, 1.0f / (1.0f - p_drop), seed,
                                                                       offset, ctr_dev);
   LAUNCHED();
   return MMDYN_OK;

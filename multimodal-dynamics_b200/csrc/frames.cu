@@ -82,6 +82,7 @@ __device__ __forceinline__ int clip8(int v) {
 __global__ void __launch_bounds__(256)
 frames_u8_to_f32_kernel(const uint8_t* __restrict__ src, const long long* __restrict__ index,
                         const int32_t* __restrict__ table, float* __restrict__ dst, long long frame_stride) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t fr_smem[];
   const int ksx = table[0], ksy = table[1], in_h = table[2], in_w = table[3], out_h = table[4], out_w = table[5];
   const int32_t* bx = table + TABLE_HEADER;
@@ -159,6 +160,7 @@ constexpr int TT_PIX = 1024;
 __global__ void __launch_bounds__(256)
 frames_u8_to_tensor_kernel(const uint8_t* __restrict__ src, const long long* __restrict__ index,
                            float* __restrict__ dst, int hw, int chunks_per_frame) {
+  pdl_sync();
   __shared__ __align__(16) uint8_t px[TT_PIX * 3];
   const int fi = blockIdx.x / chunks_per_frame, ch = blockIdx.x - fi * chunks_per_frame;
   const long long frame = index ? index[fi] : fi;
@@ -223,7 +225,7 @@ extern "C" int mmdyn_frames_u8_to_f32(const void* frames_u8, const long long* in
   MMDYN_REQUIRE(n <= 65535, "frames_u8_to_f32: at most 65535 frames per call (n=%d)", n);
   if (in_h == out_h && in_w == out_w) {  // no resampling: ToTensor only
     const int hw = in_h * in_w, chunks = (hw + TT_PIX - 1) / TT_PIX;
-    frames_u8_to_tensor_kernel<<<n * chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    MMDYN_LAUNCH((frames_u8_to_tensor_kernel), n * chunks, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const uint8_t*>(frames_u8), index, out_nchw, hw, chunks);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     MMDYN_CHECK_CUDA(cudaGetLastError());
@@ -239,7 +241,7 @@ extern "C" int mmdyn_frames_u8_to_f32(const void* frames_u8, const long long* in
                                           static_cast<int>(smem)));
     configured = smem;
   }
-  frames_u8_to_f32_kernel<<<dim3(out_h, n), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  MMDYN_LAUNCH((frames_u8_to_f32_kernel), dim3(out_h, n), 256, smem, static_cast<cudaStream_t>(stream), 
       static_cast<const uint8_t*>(frames_u8), index, table_dev, out_nchw,
       static_cast<long long>(in_h) * in_w * 3);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

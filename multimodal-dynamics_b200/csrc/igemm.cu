@@ -127,6 +127,7 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();  // the prologue above touched no global memory: it overlaps the previous grid's tail
 
   const int kb_total = (d.ntaps * d.Cin) >> 6;
   const int kb_per = (kb_total + d.ksplit - 1) / d.ksplit;
@@ -461,6 +462,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();  // the prologue above touched no global memory: it overlaps the previous grid's tail
 
   const int kb_total = (d.ntaps * d.Cin) >> 6;
   const int kb_per = (kb_total + d.ksplit - 1) / d.ksplit;
@@ -897,6 +899,7 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();  // the prologue above touched no global memory: it overlaps the previous grid's tail
 
   const int CB = CIN_MODE == 0 ? (d.Cin >> 6) : 1;
   const int bw = 1 << g.lbw;
@@ -1244,6 +1247,7 @@ wgrad_kernel(const __grid_constant__ mmdyn_wgrad_desc d) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();  // the prologue above touched no global memory: it overlaps the previous grid's tail
 
   const int M = d.n_img * d.P;
   const int steps_total = (M + STEP_ROWS - 1) / STEP_ROWS;
@@ -1419,6 +1423,7 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();  // the prologue above touched no global memory: it overlaps the previous grid's tail
 
   const int steps_per = (g.total_steps + d.row_splits - 1) / d.row_splits;
   const int step_begin = blockIdx.x * steps_per;
@@ -1561,6 +1566,7 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
 __global__ void __launch_bounds__(128)
 conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __half* __restrict__ out,
                  int n_img) {
+  pdl_sync();
   __shared__ __align__(1024) uint8_t a_tile[TILE_M * 128];
   __shared__ __align__(1024) uint8_t b_tile[32 * 128];
   __shared__ __align__(8) uint64_t accum_bar;
@@ -1655,6 +1661,7 @@ conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __h
 __global__ void __launch_bounds__(256)
 conv1_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dRaw, float* __restrict__ dW,
                    int n_img, float scale, int pix_per_cta) {
+  pdl_sync();
   constexpr int PIX = 64;
   __shared__ float patch[PIX][49];
   __shared__ float dy[PIX][33];
@@ -1728,7 +1735,7 @@ int launch_igemm_tma(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CU
                      int occ, cudaStream_t st) {
   int grid = g_sm_count * occ;
   if (grid > g.total_tiles) grid = g.total_tiles;
-  igemm_tma_kernel<BLOCK_N, A_MODE><<<grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
+  MMDYN_LAUNCH((igemm_tma_kernel<BLOCK_N, A_MODE>), grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st, *d, tmA, tmW, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -1745,7 +1752,7 @@ int dispatch_amode(int a_mode, const mmdyn_igemm_desc* d, const CUtensorMap& tmA
 template <int CN, int G_MODE>
 int launch_wgrad_tma(const mmdyn_wgrad_desc* d, const CUtensorMap& tmG, const CUtensorMap& tmN,
                      const WgradGeomDev& g, dim3 grid, cudaStream_t st) {
-  wgrad_tma_kernel<CN, G_MODE><<<grid, TMA_THREADS, Cfg<CN>::SMEM_BYTES, st>>>(*d, tmG, tmN, g);
+  MMDYN_LAUNCH((wgrad_tma_kernel<CN, G_MODE>), grid, TMA_THREADS, Cfg<CN>::SMEM_BYTES, st, *d, tmG, tmN, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -1784,7 +1791,7 @@ int launch_patch(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtens
   if (occ < 1) occ = 1;
   int grid = g_sm_count * occ;
   if (grid > g.total_tiles) grid = g.total_tiles;
-  igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG><<<grid, 64 + 128 * EG, C::SMEM_BYTES, st>>>(*d, tmA, tmW, g);
+  MMDYN_LAUNCH((igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG>), grid, 64 + 128 * EG, C::SMEM_BYTES, st, *d, tmA, tmW, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -1908,7 +1915,7 @@ int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, int m_tiles, 
                  int occ, cudaStream_t st) {
   int grid = g_sm_count * occ;
   if (grid > total_tiles) grid = total_tiles;
-  igemm_kernel<BLOCK_N><<<grid, IGEMM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st>>>(*d, tm, m_tiles, n_tiles,
+  MMDYN_LAUNCH((igemm_kernel<BLOCK_N>), grid, IGEMM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st, *d, tm, m_tiles, n_tiles,
                                                                                  total_tiles);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
@@ -1917,7 +1924,7 @@ int launch_igemm(const mmdyn_igemm_desc* d, const CUtensorMap& tm, int m_tiles, 
 
 template <int CN>
 int launch_wgrad(const mmdyn_wgrad_desc* d, dim3 grid, cudaStream_t st) {
-  wgrad_kernel<CN><<<grid, CTA_THREADS, Cfg<CN>::SMEM_BYTES, st>>>(*d);
+  MMDYN_LAUNCH((wgrad_kernel<CN>), grid, CTA_THREADS, Cfg<CN>::SMEM_BYTES, st, *d);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -2292,7 +2299,7 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
 
 extern "C" int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, int n_img, void* stream) {
   MMDYN_REQUIRE(x_nchw && Wp && out && n_img > 0, "conv1_fwd: bad arguments");
-  conv1_fwd_kernel<<<n_img * 8, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  MMDYN_LAUNCH((conv1_fwd_kernel), n_img * 8, 128, 0, static_cast<cudaStream_t>(stream), 
       x_nchw, reinterpret_cast<const __half*>(Wp), reinterpret_cast<__half*>(out), n_img);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
@@ -2306,7 +2313,7 @@ extern "C" int mmdyn_conv1_wgrad(const float* x_nchw, const void* dRaw, float* d
   long long per = (total + row_splits - 1) / row_splits;
   per = (per + 63) / 64 * 64;
   const int grid = static_cast<int>((total + per - 1) / per);
-  conv1_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MMDYN_LAUNCH((conv1_wgrad_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       x_nchw, reinterpret_cast<const __half*>(dRaw), dW, n_img, scale, static_cast<int>(per));
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());

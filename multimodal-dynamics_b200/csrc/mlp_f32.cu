@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
              const float* __restrict__ bias, int M, int N, int K, int lda, int ldb, int ldc, int act,
              int atomic_add, float scale, int k_per_split) {
+  pdl_sync();
   constexpr int TM = BM / 16;          // rows per thread
   constexpr int A_V4 = BM * BK / 4 / 256;  // float4 loads of A per thread and k-tile
   constexpr int B_V4 = BN * BK / 4 / 256;
@@ -180,10 +181,10 @@ void launch_sgemm(const float* A, const float* B, float* C, const float* bias, i
                   int ldc, int act, int atomic_add, float scale, int k_per_split, int splits, cudaStream_t st) {
   const int nb = (N + BN - 1) / BN;
   if (static_cast<long long>((M + 127) / 128) * nb * splits >= 148) {
-    sgemm_kernel<128, TA, TB><<<dim3(nb, (M + 127) / 128, splits), 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc,
+    MMDYN_LAUNCH((sgemm_kernel<128, TA, TB>), dim3(nb, (M + 127) / 128, splits), 256, 0, st, A, B, C, bias, M, N, K, lda, ldb, ldc,
                                                                                    act, atomic_add, scale, k_per_split);
   } else {
-    sgemm_kernel<64, TA, TB><<<dim3(nb, (M + 63) / 64, splits), 256, 0, st>>>(A, B, C, bias, M, N, K, lda, ldb, ldc,
+    MMDYN_LAUNCH((sgemm_kernel<64, TA, TB>), dim3(nb, (M + 63) / 64, splits), 256, 0, st, A, B, C, bias, M, N, K, lda, ldb, ldc,
                                                                                  act, atomic_add, scale, k_per_split);
   }
 }
@@ -191,6 +192,7 @@ void launch_sgemm(const float* A, const float* B, float* C, const float* bias, i
 __global__ void __launch_bounds__(256)
 act_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ out, int M,
                 int N, int ldy, int act) {
+  pdl_sync();
   const long long n = static_cast<long long>(M) * N;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -202,6 +204,7 @@ act_grad_kernel(const float* __restrict__ y, const float* __restrict__ dy, float
 
 // ReLU in fp32 (Regressor.out_net behind the tensor-core Linear(512, 256), models.py:56-62)
 __global__ void __launch_bounds__(256) relu_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_sync();
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -224,6 +227,7 @@ constexpr int MAX_COND = 8;
 __global__ void __launch_bounds__(256)
 cond_add_f16_kernel(__half* __restrict__ raw, const float* __restrict__ c, const float* __restrict__ W,
                     const int32_t* __restrict__ n_idx, int R, int N, int ldw, int col0, int cd) {
+  pdl_sync();
   const int nv = N >> 3;
   const long long total = static_cast<long long>(R) * nv;
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total;
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(256)
 cond_wgrad_f16_kernel(const __half* __restrict__ g, const float* __restrict__ c, float* __restrict__ dW,
                       const int32_t* __restrict__ n_idx, int R, int N, int ldw, int col0, int cd, float scale,
                       int rows_per_cta) {
+  pdl_sync();
   const int n = blockIdx.x * 256 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
   __shared__ float cs[64][MAX_COND];
@@ -311,7 +316,7 @@ extern "C" int mmdyn_linear_f32_bwd(const float* x, const float* W, const float*
     const long long n = static_cast<long long>(M) * N;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    act_grad_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(y, dy, dy_act, M, N, ldy, act);
+    MMDYN_LAUNCH((act_grad_kernel), static_cast<int>(blocks), 256, 0, ST(stream), y, dy, dy_act, M, N, ldy, act);
     LAUNCHED();
   }
   if (dx) {  // dx[M][K] = dy_act[M][N] * W[N][K]
@@ -367,7 +372,7 @@ extern "C" int mmdyn_cond_add_f16(void* raw, const float* c, const float* W, con
   const long long total = static_cast<long long>(R) * (N >> 3);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  cond_add_f16_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(reinterpret_cast<__half*>(raw), c, W, n_idx,
+  MMDYN_LAUNCH((cond_add_f16_kernel), static_cast<int>(blocks), 256, 0, ST(stream), reinterpret_cast<__half*>(raw), c, W, n_idx,
                                                                          R, N, ldw, col0, cd);
   LAUNCHED();
   return MMDYN_OK;
@@ -382,7 +387,7 @@ extern "C" int mmdyn_cond_wgrad_f16(const void* g, const float* c, float* dW, co
   int rpc = (R + gy - 1) / gy;
   rpc = (rpc + 63) / 64 * 64;
   gy = (R + rpc - 1) / rpc;
-  cond_wgrad_f16_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(reinterpret_cast<const __half*>(g), c, dW, n_idx, R, N,
+  MMDYN_LAUNCH((cond_wgrad_f16_kernel), dim3(gx, gy), 256, 0, ST(stream), reinterpret_cast<const __half*>(g), c, dW, n_idx, R, N,
                                                                ldw, col0, cd, scale, rpc);
   LAUNCHED();
   return MMDYN_OK;
@@ -396,7 +401,7 @@ extern "C" int mmdyn_relu_f32(const float* x, float* y, long long n, void* strea
   long long blocks = ((n >> 2) + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  relu_f32_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(x, y, n);
+  MMDYN_LAUNCH((relu_f32_kernel), static_cast<int>(blocks), 256, 0, ST(stream), x, y, n);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -408,7 +413,7 @@ extern "C" int mmdyn_act_grad_f32(const float* y, const float* dy, float* dx, in
   const long long n = static_cast<long long>(M) * N;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  act_grad_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(y, dy, dx, M, N, ldy, act);
+  MMDYN_LAUNCH((act_grad_kernel), static_cast<int>(blocks), 256, 0, ST(stream), y, dy, dx, M, N, ldy, act);
   LAUNCHED();
   return MMDYN_OK;
 }

@@ -55,6 +55,7 @@ peer_rs_adam_ag_kernel(const __grid_constant__ PeerArgs pa, float* __restrict__ 
                        int rank, int world, float lr, float b1, float b2, float eps, float wd,
                        const uint64_t* __restrict__ step_dev, const uint64_t* __restrict__ epoch_dev, float gscale,
                        unsigned int* __restrict__ nonfinite, unsigned int* __restrict__ block_counter) {
+  pdl_sync();
   const unsigned int epoch = static_cast<unsigned int>(*epoch_dev);
   // ---- my gradients are final (stream order): tell every peer, then wait for theirs ----
   if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -212,7 +213,7 @@ extern "C" int mmdyn_peer_rs_adam_ag(float* const* grad_ptrs, float* const* para
   long long blocks = (per + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  peer_rs_adam_ag_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MMDYN_LAUNCH((peer_rs_adam_ag_kernel), static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
       pa, m, v, n4, rank, world, lr, beta1, beta2, eps, weight_decay, step_dev, epoch_dev, gscale, nonfinite_flag,
       block_counter);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
