@@ -207,6 +207,33 @@ int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e, int n_expe
                   int ld, const float* eps, const float* const* dz, const float* dmu_in,
                   const float* dlv_in, float kl_coef, float* const* dmu_e, float* const* dlv_e,
                   int ld_out, int accumulate, int B, int D, void* stream);
+/* All sub-sampled passes of a step (problems.py:478-529: 3, or 7 with --use-pose) in ONE launch each way: pass k
+ * reads / writes the pointers of passes[k] (same meaning as the arguments of mmdyn_poe_fwd / mmdyn_poe_bwd).  In the
+ * backward several passes may accumulate into the same expert-gradient rows (the pose expert serves 4 passes):
+ * accumulation is atomic there. */
+#define MMDYN_MAX_POE_PASSES 8
+typedef struct mmdyn_poe_pass {
+  const float* mu_e[4];
+  const float* lv_e[4];
+  int32_t n_experts;
+  const float* eps;
+  /* forward outputs */
+  float* mu;
+  float* lv;
+  float* z;
+  void* zh;
+  void* zh2;
+  float* kl_sum;
+  /* backward */
+  const float* dz[3];
+  const float* dmu_in;
+  const float* dlv_in;
+  float* dmu_e[4];
+  float* dlv_e[4];
+} mmdyn_poe_pass;
+int mmdyn_poe_fwd_multi(const mmdyn_poe_pass* passes, int n_passes, int use_prior, int ld, int B, int D, void* stream);
+int mmdyn_poe_bwd_multi(const mmdyn_poe_pass* passes, int n_passes, int use_prior, int ld, float kl_coef, int ld_out,
+                        int accumulate, int B, int D, void* stream);
 
 /* --- reconstruction losses (problems.py:409-413, 431-449, 499-503, 535) -----------------------
  * BCE-with-logits, reduction 'sum' into loss_sum[0]; dlogits (fp16 NHWC, 8 channels per pixel,

@@ -736,11 +736,10 @@ struct ExpertPtrs {
 };
 constexpr float POE_EPS = 1e-8f;
 
-__global__ void __launch_bounds__(256)
-poe_fwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
-               float* __restrict__ mu_o, float* __restrict__ lv_o, float* __restrict__ z_o,
-               __half* __restrict__ zh_o, __half* __restrict__ zh2_o, float* __restrict__ kl_sum, int B, int D) {
-  pdl_sync();
+__device__ __forceinline__ void poe_fwd_body(const ExpertPtrs& ex, int n_experts, int use_prior, int ld,
+                                             const float* __restrict__ eps, float* __restrict__ mu_o,
+                                             float* __restrict__ lv_o, float* __restrict__ z_o, __half* __restrict__ zh_o,
+                                             __half* __restrict__ zh2_o, float* __restrict__ kl_sum, int B, int D) {
   const long long n = static_cast<long long>(B) * D;
   float kl = 0.0f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -788,10 +787,52 @@ poe_fwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
 }
 
 __global__ void __launch_bounds__(256)
-poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
-               const float* __restrict__ dmu_in, const float* __restrict__ dlv_in, float kl_coef, int ld_out,
-               int accumulate, int B, int D) {
+poe_fwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
+               float* __restrict__ mu_o, float* __restrict__ lv_o, float* __restrict__ z_o,
+               __half* __restrict__ zh_o, __half* __restrict__ zh2_o, float* __restrict__ kl_sum, int B, int D) {
   pdl_sync();
+  poe_fwd_body(ex, n_experts, use_prior, ld, eps, mu_o, lv_o, z_o, zh_o, zh2_o, kl_sum, B, D);
+}
+
+// All sub-sampled passes of the step in ONE launch (blockIdx.y = pass): 7 launches of a few microseconds each sit on
+// the critical path between the encoders and the decoders otherwise.
+struct PoePassDev {
+  ExpertPtrs ex;
+  int n_experts;
+  const float* eps;
+  float* mu_o;
+  float* lv_o;
+  float* z_o;
+  __half* zh_o;
+  __half* zh2_o;
+  float* kl_sum;
+  const float* dmu_in;
+  const float* dlv_in;
+};
+struct PoePassesDev {
+  PoePassDev p[MMDYN_MAX_POE_PASSES];
+};
+
+__global__ void __launch_bounds__(256)
+poe_fwd_multi_kernel(const __grid_constant__ PoePassesDev ps, int use_prior, int ld, int B, int D) {
+  pdl_sync();
+  const PoePassDev& q = ps.p[blockIdx.y];
+  poe_fwd_body(q.ex, q.n_experts, use_prior, ld, q.eps, q.mu_o, q.lv_o, q.z_o, q.zh_o, q.zh2_o, q.kl_sum, B, D);
+}
+
+// ATOMIC: several passes may accumulate into the same expert gradient rows concurrently (multi-pass launch)
+template <bool ATOMIC>
+__device__ __forceinline__ void poe_store(float* p, float v, int accumulate) {
+  if (!accumulate) *p = v;
+  else if (ATOMIC) atomicAdd(p, v);
+  else *p += v;
+}
+
+template <bool ATOMIC>
+__device__ __forceinline__ void poe_bwd_body(const ExpertPtrs& ex, int n_experts, int use_prior, int ld,
+                                             const float* __restrict__ eps, const float* __restrict__ dmu_in,
+                                             const float* __restrict__ dlv_in, float kl_coef, int ld_out, int accumulate,
+                                             int B, int D) {
   const long long n = static_cast<long long>(B) * D;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -807,13 +848,8 @@ poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
       const float dmu = g + kl_coef * mu + (dmu_in ? dmu_in[i] : 0.0f);
       const float dlv = 0.5f * g * eps[i] * expf(0.5f * lv) + 0.5f * kl_coef * (expf(lv) - 1.0f) +
                         (dlv_in ? dlv_in[i] : 0.0f);
-      if (accumulate) {
-        ex.dmu[0][oi] += dmu;
-        ex.dlv[0][oi] += dlv;
-      } else {
-        ex.dmu[0][oi] = dmu;
-        ex.dlv[0][oi] = dlv;
-      }
+      poe_store<ATOMIC>(ex.dmu[0] + oi, dmu, accumulate);
+      poe_store<ATOMIC>(ex.dlv[0] + oi, dlv, accumulate);
       continue;
     }
     float st = 0.0f, sm = 0.0f, t_e[MAX_EXPERTS], elv[MAX_EXPERTS];
@@ -837,15 +873,27 @@ poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float*
       const float dmu_e = dsm * t_e[e];
       const float dt = fmaf(dsm, ex.mu[e][ei], dst);
       const float dlv_e = -dt * t_e[e] * t_e[e] * elv[e];
-      if (accumulate) {
-        ex.dmu[e][oi] += dmu_e;
-        ex.dlv[e][oi] += dlv_e;
-      } else {
-        ex.dmu[e][oi] = dmu_e;
-        ex.dlv[e][oi] = dlv_e;
-      }
+      poe_store<ATOMIC>(ex.dmu[e] + oi, dmu_e, accumulate);
+      poe_store<ATOMIC>(ex.dlv[e] + oi, dlv_e, accumulate);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+poe_bwd_kernel(ExpertPtrs ex, int n_experts, int use_prior, int ld, const float* __restrict__ eps,
+               const float* __restrict__ dmu_in, const float* __restrict__ dlv_in, float kl_coef, int ld_out,
+               int accumulate, int B, int D) {
+  pdl_sync();
+  poe_bwd_body<false>(ex, n_experts, use_prior, ld, eps, dmu_in, dlv_in, kl_coef, ld_out, accumulate, B, D);
+}
+
+__global__ void __launch_bounds__(256)
+poe_bwd_multi_kernel(const __grid_constant__ PoePassesDev ps, int use_prior, int ld, float kl_coef, int ld_out,
+                     int accumulate, int B, int D) {
+  pdl_sync();
+  const PoePassDev& q = ps.p[blockIdx.y];
+  if (q.n_experts == 0) return;
+  poe_bwd_body<true>(q.ex, q.n_experts, use_prior, ld, q.eps, q.dmu_in, q.dlv_in, kl_coef, ld_out, accumulate, B, D);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1546,6 +1594,77 @@ extern "C" int mmdyn_poe_bwd(const float* const* mu_e, const float* const* lv_e,
   const long long n = static_cast<long long>(B) * D;
   MMDYN_LAUNCH((poe_bwd_kernel), grid_for(n), 256, 0, ST(stream), ex, n_experts, use_prior, ld, eps, dmu_in, dlv_in, kl_coef,
                                                       ld_out, accumulate, B, D);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+static int fill_poe_passes(const mmdyn_poe_pass* passes, int n_passes, bool bwd, PoePassesDev* out, const char* what) {
+  MMDYN_REQUIRE(passes && n_passes >= 1 && n_passes <= MMDYN_MAX_POE_PASSES, "%s: n_passes=%d (1..%d)", what, n_passes,
+                MMDYN_MAX_POE_PASSES);
+  for (int k = 0; k < n_passes; ++k) {
+    const mmdyn_poe_pass& a = passes[k];
+    PoePassDev& q = out->p[k];
+    q = {};
+    MMDYN_REQUIRE(a.n_experts >= 0 && a.n_experts <= MAX_EXPERTS && a.eps, "%s: pass %d: n_experts=%d / eps", what, k,
+                  a.n_experts);
+    q.n_experts = a.n_experts;
+    q.eps = a.eps;
+    for (int e = 0; e < a.n_experts; ++e) {
+      MMDYN_REQUIRE(a.mu_e[e] && a.lv_e[e], "%s: pass %d: null expert %d", what, k, e);
+      q.ex.mu[e] = a.mu_e[e];
+      q.ex.lv[e] = a.lv_e[e];
+      if (bwd) {
+        MMDYN_REQUIRE(a.dmu_e[e] && a.dlv_e[e], "%s: pass %d: null expert gradient %d", what, k, e);
+        q.ex.dmu[e] = a.dmu_e[e];
+        q.ex.dlv[e] = a.dlv_e[e];
+      }
+    }
+    if (bwd) {
+      for (int j = 0; j < 3; ++j) q.ex.dz[j] = a.dz[j];
+      q.dmu_in = a.dmu_in;
+      q.dlv_in = a.dlv_in;
+    } else {
+      MMDYN_REQUIRE(a.mu && a.lv && a.z && a.kl_sum, "%s: pass %d: null output", what, k);
+      q.mu_o = a.mu;
+      q.lv_o = a.lv;
+      q.z_o = a.z;
+      q.zh_o = reinterpret_cast<__half*>(a.zh);
+      q.zh2_o = reinterpret_cast<__half*>(a.zh2);
+      q.kl_sum = a.kl_sum;
+    }
+  }
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_poe_fwd_multi(const mmdyn_poe_pass* passes, int n_passes, int use_prior, int ld, int B, int D,
+                                   void* stream) {
+  MMDYN_REQUIRE(B > 0 && D > 0, "poe_fwd_multi: empty problem");
+  PoePassesDev ps = {};
+  const int rc = fill_poe_passes(passes, n_passes, false, &ps, "poe_fwd_multi");
+  if (rc != MMDYN_OK) return rc;
+  for (int k = 0; k < n_passes; ++k)
+    MMDYN_REQUIRE(passes[k].n_experts > 0 || use_prior, "poe_fwd_multi: pass %d has no expert and no prior", k);
+  const long long n = static_cast<long long>(B) * D;
+  int gx = static_cast<int>((n + 255) / 256);
+  const int cap = (148 * 8 + n_passes - 1) / n_passes;
+  if (gx > cap) gx = cap;
+  MMDYN_LAUNCH((poe_fwd_multi_kernel), dim3(gx, n_passes), 256, 0, ST(stream), ps, use_prior, ld, B, D);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
+extern "C" int mmdyn_poe_bwd_multi(const mmdyn_poe_pass* passes, int n_passes, int use_prior, int ld, float kl_coef,
+                                   int ld_out, int accumulate, int B, int D, void* stream) {
+  MMDYN_REQUIRE(B > 0 && D > 0, "poe_bwd_multi: empty problem");
+  PoePassesDev ps = {};
+  const int rc = fill_poe_passes(passes, n_passes, true, &ps, "poe_bwd_multi");
+  if (rc != MMDYN_OK) return rc;
+  const long long n = static_cast<long long>(B) * D;
+  int gx = static_cast<int>((n + 255) / 256);
+  const int cap = (148 * 8 + n_passes - 1) / n_passes;
+  if (gx > cap) gx = cap;
+  MMDYN_LAUNCH((poe_bwd_multi_kernel), dim3(gx, n_passes), 256, 0, ST(stream), ps, use_prior, ld, kl_coef, ld_out,
+               accumulate, B, D);
   LAUNCHED();
   return MMDYN_OK;
 }

@@ -1159,6 +1159,7 @@ class StepEngine:
                 out.append(pose_rec["heads"])
             return out
 
+        fwd_passes = []
         for i, p in enumerate(self.passes):
             hs = experts(i)
             zh = []
@@ -1167,9 +1168,11 @@ class StepEngine:
                     g = dec_groups[m].index(i)
                     zh.append(zdec[m][g * B:(g + 1) * B])
             zf = zpose[pose_passes.index(i) * B:(pose_passes.index(i) + 1) * B] if "p" in p else zscr
-            ops.poe_fwd([h[:, :D] for h in hs], [h[:, D:] for h in hs], self.use_prior, 2 * D, eps[i], mu_all[i],
-                        lv_all[i], zf, zh[0] if len(zh) > 0 else None, zh[1] if len(zh) > 1 else None,
-                        scal[i:i + 1], B, D)
+            fwd_passes.append(dict(mu_e=[h[:, :D] for h in hs], lv_e=[h[:, D:] for h in hs], eps=eps[i], mu=mu_all[i],
+                                   lv=lv_all[i], z=zf, zh=zh[0] if len(zh) > 0 else None,
+                                   zh2=zh[1] if len(zh) > 1 else None, kl_sum=scal[i:i + 1]))
+        # every sub-sampled pass in one launch (z_scratch is shared by the passes without a pose decoder: nobody reads it)
+        ops.poe_fwd_multi(fwd_passes, self.use_prior, 2 * D, B, D)
 
         # decoders, group-batched, + losses (and logit gradients when training): one branch per modality
         slot, nslot = {}, 8
@@ -1325,6 +1328,7 @@ class StepEngine:
         dzp = dzp_box.get("dz")
         dh = {m: ws("dheads_" + m, (len(st["enc_passes"][m]) * B, 512), F32, zero=True) for m in img_mods}
         dhp = ws("dheads_p", (B, 512), F32, zero=True) if self.use_pose else None
+        bwd_passes = []
         for i, p in enumerate(self.passes):
             hs = st["experts"](i)
             outs, dzs = [], []
@@ -1338,8 +1342,10 @@ class StepEngine:
                 outs.append(dhp)
                 g = st["pose_passes"].index(i)
                 dzs.append(dzp[g * B:(g + 1) * B])
-            ops.poe_bwd([h[:, :D] for h in hs], [h[:, D:] for h in hs], self.use_prior, 2 * D, st["eps"][i], dzs,
-                        st["klw"] * gs / B, [o[:, :D] for o in outs], [o[:, D:] for o in outs], 2 * D, True, B, D)
+            bwd_passes.append(dict(mu_e=[h[:, :D] for h in hs], lv_e=[h[:, D:] for h in hs], eps=st["eps"][i], dz=dzs,
+                                   dmu_e=[o[:, :D] for o in outs], dlv_e=[o[:, D:] for o in outs]))
+        # one launch for all passes; the pose expert's gradient rows are shared by its 4 passes (atomic accumulation)
+        ops.poe_bwd_multi(bwd_passes, self.use_prior, 2 * D, st["klw"] * gs / B, 2 * D, True, B, D)
         def enc_bwd(m):
             def fn():
                 gp = gps[self.mods[m][0]]

@@ -50,6 +50,13 @@ class WgradDesc(C.Structure):
     ]
 
 
+class PoePass(C.Structure):
+    _fields_ = [("mu_e", C.c_void_p * 4), ("lv_e", C.c_void_p * 4), ("n_experts", C.c_int32), ("eps", C.c_void_p),
+                ("mu", C.c_void_p), ("lv", C.c_void_p), ("z", C.c_void_p), ("zh", C.c_void_p), ("zh2", C.c_void_p),
+                ("kl_sum", C.c_void_p), ("dz", C.c_void_p * 3), ("dmu_in", C.c_void_p), ("dlv_in", C.c_void_p),
+                ("dmu_e", C.c_void_p * 4), ("dlv_e", C.c_void_p * 4)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _F = C.c_float
@@ -77,6 +84,8 @@ SIGNATURES = {
     "mmdyn_poe_fwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),
     "mmdyn_poe_bwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, C.POINTER(_P), _P, _P, _F, C.POINTER(_P), C.POINTER(_P),
                        _I, _I, _I, _I, _P], _I),
+    "mmdyn_poe_fwd_multi": ([C.POINTER(PoePass), _I, _I, _I, _I, _I, _P], _I),
+    "mmdyn_poe_bwd_multi": ([C.POINTER(PoePass), _I, _I, _I, _F, _I, _I, _I, _I, _P], _I),
     "mmdyn_bce_logits": ([_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P], _I),
     "mmdyn_mse": ([_P, _P, _P, _P, _F, _F, _I, _P], _I),
     "mmdyn_bce_logits_flat": ([_P, _P, _P, _P, _P, _P, _F, _I, _I, _P], _I),

@@ -249,6 +249,38 @@ def poe_bwd(mu_e, lv_e, use_prior, ld, eps, dzs, kl_coef, dmu_e, dlv_e, ld_out, 
                                  int(accumulate), B, D, _stream()), "poe_bwd")
 
 
+def _poe_passes(passes):
+    from .lib import PoePass
+    arr = (PoePass * len(passes))()
+    dp = lambda t: t.data_ptr() if t is not None else None
+    for k, a in enumerate(passes):
+        q = arr[k]
+        q.n_experts = len(a["mu_e"])
+        for e in range(q.n_experts):
+            q.mu_e[e], q.lv_e[e] = a["mu_e"][e].data_ptr(), a["lv_e"][e].data_ptr()
+            if "dmu_e" in a:
+                q.dmu_e[e], q.dlv_e[e] = a["dmu_e"][e].data_ptr(), a["dlv_e"][e].data_ptr()
+        q.eps = a["eps"].data_ptr()
+        for f in ("mu", "lv", "z", "zh", "zh2", "kl_sum", "dmu_in", "dlv_in"):
+            setattr(q, f, dp(a.get(f)))
+        for j, t in enumerate(a.get("dz", [])[:3]):
+            q.dz[j] = dp(t)
+    return arr
+
+
+def poe_fwd_multi(passes, use_prior, ld, B, D):
+    """passes: list of dict(mu_e, lv_e, eps, mu, lv, z, zh, zh2, kl_sum) — every pass of the step in one launch."""
+    with _Timed("poe_fwd", None):
+        check(_L().mmdyn_poe_fwd_multi(_poe_passes(passes), len(passes), int(use_prior), ld, B, D, _stream()), "poe_fwd_multi")
+
+
+def poe_bwd_multi(passes, use_prior, ld, kl_coef, ld_out, accumulate, B, D):
+    """passes: list of dict(mu_e, lv_e, eps, dz, dmu_e, dlv_e[, dmu_in, dlv_in]) — one launch for all passes."""
+    with _Timed("poe_bwd", None):
+        check(_L().mmdyn_poe_bwd_multi(_poe_passes(passes), len(passes), int(use_prior), ld, kl_coef, ld_out,
+                                       int(accumulate), B, D, _stream()), "poe_bwd_multi")
+
+
 def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, H, W, pad=0):
     """pad: border (pixels) of the NHWC8 gradient images, see include/mmdyn_b200.h"""
     with _Timed("bce_logits", lambda: (0.0, n * H * W * (3 * 8.0 + (16.0 if dlogits is not None else 0.0)))):

@@ -54,6 +54,19 @@ def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, st
           f"TFLOPs={2 * macs / ms / 1e9:7.1f} algGB/s={abytes / ms / 1e6:7.0f} patch={getattr(geom, 'patch', 0)}", flush=True)
 
 
+def run_wgrad(name, lp, n_img, g_shape, nat_shape, wg=None):
+    wg = wg or lp.wgrad
+    G = torch.randn(n_img, *g_shape, device=DEV).half()
+    Nat = torch.randn(n_img, *nat_shape, device=DEV).half()
+    dW = torch.zeros(wg.Cn, wg.K, device=DEV)
+    rs = plan.choose_row_splits(wg, n_img)
+    ms = timeit(lambda: ops.wgrad(wg, G, Nat, dW, n_img, scale=1.0, row_splits=rs))
+    macs = lp.extra["macs"] * n_img
+    abytes = G.numel() * 2 + Nat.numel() * 2
+    print(f"{name:16s} n={n_img:6d} ms={ms:7.3f} row_splits={rs:4d} K={wg.K:5d} Cn={wg.Cn:4d} TFLOPs={2 * macs / ms / 1e9:7.1f} "
+          f"algGB/s={abytes / ms / 1e6:7.0f}", flush=True)
+
+
 CASES = {
     "deconv4.fwd": lambda R: run("deconv4.fwd", plan.deconv_out_plan("d4", 0), "fwd", R, (32, 32, 32), (3, 64, 64), torch.float32),
     "deconv4.fwd.bce": lambda R: run("deconv4.fwd.bce", plan.deconv_out_plan("d4", 0), "fwd", R, (32, 32, 32), (3, 64, 64), torch.float32, bce=True),
@@ -67,6 +80,14 @@ CASES = {
     "conv2.dgrad": lambda R: run("conv2.dgrad", plan.conv_s2_plan("c2", 0, 32, 64, 32), "dgrad", R // 4, (16, 16, 64), (32, 32, 32)),
     "conv3.dgrad": lambda R: run("conv3.dgrad", plan.conv_s2_plan("c3", 0, 64, 128, 16), "dgrad", R // 4, (8, 8, 128), (16, 16, 64)),
     "deconv3.dgrad": lambda R: run("deconv3.dgrad", plan.deconv_s2_plan("d3", 0, 64, 32, 16), "dgrad", R, (32, 32, 32), (16, 16, 64)),
+    "deconv1.wgrad": lambda R: run_wgrad("deconv1.wgrad", plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), R, (8, 8, 128), (5, 5, 256)),
+    "deconv2.wgrad": lambda R: run_wgrad("deconv2.wgrad", plan.deconv_s2_plan("d2", 0, 128, 64, 8), R, (16, 16, 64), (8, 8, 128)),
+    "deconv3.wgrad": lambda R: run_wgrad("deconv3.wgrad", plan.deconv_s2_plan("d3", 0, 64, 32, 16), R, (32, 32, 32), (16, 16, 64)),
+    "deconv4.wgrad": lambda R: run_wgrad("deconv4.wgrad", plan.deconv_out_plan("d4", 0), R, (66, 66, 8), (32, 32, 32)),
+    "conv2.wgrad": lambda R: run_wgrad("conv2.wgrad", plan.conv_s2_plan("c2", 0, 32, 64, 32), R // 4, (32, 32, 32), (16, 16, 64)),
+    "conv3.wgrad": lambda R: run_wgrad("conv3.wgrad", plan.conv_s2_plan("c3", 0, 64, 128, 16), R // 4, (16, 16, 64), (8, 8, 128)),
+    "conv4.wgrad": lambda R: run_wgrad("conv4.wgrad", plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), R // 4, (8, 8, 128), (5, 5, 256)),
+    "deconv4.dgrad": lambda R: run("deconv4.dgrad", plan.deconv_out_plan("d4", 0), "dgrad", R, (66, 66, 8), (32, 32, 32)),
     "deconv2.dgrad": lambda R: run("deconv2.dgrad", plan.deconv_s2_plan("d2", 0, 128, 64, 8), "dgrad", R, (16, 16, 64), (8, 8, 128)),
 }
 
