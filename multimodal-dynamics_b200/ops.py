@@ -66,11 +66,16 @@ _FAMILY = {"adam_flat": "adam_kernel", "sgd_flat": "sgd_kernel", "bn_stats": "bn
            "conv1.wgrad": "wgrad_kernel<32> (conv1, Cin = 3 -> 8-channel pixels)"}
 
 
+_PATCH_TAGS = set()  # layer tags that run on igemm_patch_kernel (filled by igemm() as launches happen)
+
+
 def kernel_family(tag):
     """Kernel NAME a profile tag runs in: the GEMM launches are tagged per layer ("deconv3.fwd") and pooled here
     into the kernel template that executes them; the streaming kernels are tagged by their own name."""
     if tag in _FAMILY:
         return _FAMILY[tag]
+    if tag in _PATCH_TAGS:
+        return "igemm_patch_kernel<*> (merged 3x3-tap layers: deconv3/4 forward, conv2 dgrad)"
     if tag.endswith(".fwd") or tag.endswith(".dgrad"):
         return "igemm_tma_kernel<*> (conv / deconv / linear forward + dgrad)"
     if tag.endswith(".wgrad"):
@@ -121,6 +126,8 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     d.ldc = geom.ldc if ldc is None else ldc
     d.a_row_stride, d.a_img_stride = geom.a_row_stride, geom.a_img_stride
     d.patch_mode = int(getattr(geom, "patch", 0))
+    if d.patch_mode:
+        _PATCH_TAGS.add(tag)
     if stats is not None:  # (sums [G][C][2] fp32 zeroed, images per group): BatchNorm statistics in the epilogue
         assert d.patch_mode and d.out_mode == 4
         d.bn_sums, d.bn_rows_per_group = stats[0].data_ptr(), int(stats[1])
