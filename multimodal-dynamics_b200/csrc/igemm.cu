@@ -1,19 +1,22 @@
 // Implicit-GEMM convolution / transposed convolution / linear kernels for sm_100a.
 //
-//   igemm_kernel  : out[row, n] = sum_k A_gather[row, k] * W[n, k]        (fwd + dgrad form)
-//   wgrad_kernel  : dW[n, k]   += sum_row Nat[row, n] * G_gather[row, k]  (weight gradients)
-//   conv1_*       : the Cin = 3 first encoder layer on the fp32 NCHW input
+//   igemm_tma_kernel   : out[row, n] = sum_k A_gather[row, k] * W[n, k]        (forward + dgrad form), both operands by TMA:
+//                        weights as 2-D boxes, activations as one 4-D box (channel, x, y, image) per filter tap
+//   igemm_patch_kernel : the merged 3x3-tap layers (4 sub-pixel phases of a stride-2 transposed conv as one GEMM): one
+//                        activation box per filter column serves three taps, live weight blocks resident in shared memory,
+//                        compile-time MMA schedule, BatchNorm statistics / BCE loss in the epilogue
+//   wgrad_tma_kernel   : dW[n, k] += sum_row Nat[row, n] * G_gather[row, k]    (weight gradients), both operands MN-major
+//   conv1_*            : the Cin = 3 first encoder layer on the fp32 NCHW input
+//   igemm_kernel / wgrad_kernel : cp.async (LDGSTS) gather variants for geometries TMA handles badly (8-channel pixels)
 //
 // Mapping to the hardware (B200):
-//   * accumulators live in TMEM (tcgen05.alloc, 128 lanes x BLOCK_N fp32 columns);
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N, K = 16)
-//     on UMMA shared-memory descriptors (128B swizzle; K-major for igemm, MN-major for wgrad);
-//   * the weight operand arrives by TMA (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier tx);
-//   * the gathered activation operand is an im2col gather done with 16-byte cp.async (LDGSTS,
-//     zero fill for padding) straight into the swizzled UMMA layout by four producer warps,
-//     published to the async proxy with fence.proxy.async + mbarrier arrive;
-//   * a STAGES-deep smem ring decouples {gather, TMA} from the MMA issuer; tcgen05.commit frees
-//     ring slots and finally signals the epilogue, which reads TMEM with tcgen05.ld.
+//   * accumulators live in TMEM (tcgen05.alloc, 128 lanes x BLOCK_N fp32 columns, double-buffered);
+//   * one ELECTED thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 16..256, K = 16) on UMMA shared-memory
+//     descriptors (128B / 64B swizzle or plain core matrices; K-major for igemm, MN-major for wgrad);
+//   * operands arrive by TMA (cp.async.bulk.tensor.{2d,4d}, mbarrier transaction counts), hardware zero fill for padding;
+//   * shared-memory rings decouple the TMA producer from the MMA issuer; tcgen05.commit frees ring slots and signals the
+//     epilogue warps, which read TMEM with tcgen05.ld and write global memory;
+//   * every kernel is launched with programmatic stream serialisation (pdl_sync, common.cuh).
 //
 // Reference semantics: nn.Conv2d / nn.ConvTranspose2d / nn.Linear in
 // mmdyn/pytorch/models/vae.py:198-216, 263-277 and their autograd (problems.py:153).
