@@ -425,8 +425,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
 // whose input pixel falls outside the image is skipped, not multiplied by zeros) — evaluating that test with
 // its divisions per k-block in both the producer and the MMA issuer cost as much as a live k-block's MMAs on
 // the 5x5 <-> 8x8 layers (ncu source view, round 2).  Producer and MMA issuer run under elect.sync.
-template <int BLOCK_N, int A_MODE>
-__global__ void __launch_bounds__(TMA_THREADS)
+// EG epilogue groups of 4 warps: group e drains the tiles whose accumulator stage is e.  EG = 2 for BLOCK_N = 256 (one CTA
+// per SM: its 4 epilogue warps were busy 80 % of the kernel on deconv2.fwd, profiles/r2_stalls_igemm_tma_256_deconv2fwd.txt).
+template <int BLOCK_N, int A_MODE, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG)
 igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmW, const TileGeom g) {
   using C = Cfg<BLOCK_N>;
@@ -439,7 +441,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[BLOCK_N];
+  __shared__ __align__(16) float bias_all[EG][BLOCK_N];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -582,6 +584,9 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
     // ======================= epilogue: TMEM -> registers -> global ============================
     const int q4 = warp & 3;       // TMEM lane quarter this warp may access
     const int r = q4 * 32 + lane;  // tile row owned by this thread
+    const int eg = EG == 1 ? 0 : (warp - 2) >> 2;  // epilogue group: tiles tl = eg, eg + EG, ...
+    const int et = (threadIdx.x - 64) & 127;       // thread index inside the group
+    float* bias_s = bias_all[eg];
     int x_l, y_l, n_l;
     if (g.pixel_major) {
       x_l = 0; y_l = 0; n_l = r;
@@ -599,8 +604,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       if (lane == 0 && bce_cur >= 0) atomicAdd(d.bce_loss + bce_cur, v);
       bce_acc = 0.0f;
     };
-    int tl = 0;
-    for (int tile = tile0; tile < g.total_tiles; tile += tile_step, ++tl) {
+    for (int tile = tile0 + eg * tile_step, tl = eg; tile < g.total_tiles; tile += EG * tile_step, tl += EG) {
       const TileCoord2 t = decode_tile2(d, g, tile);
       const int img = t.img0 + n_l, yv = t.y0 + y_l, xv = t.x0 + x_l;
       const bool valid = img < d.n_img;
@@ -640,9 +644,9 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       // wait (16 dependent L2 round trips per tile inside the chunk loop made the K = 256 / 512 linear
       // layers epilogue-bound: ncu long_scoreboard 6 warps per issue, tensor pipe 8.6 %)
       if (d.bias != nullptr && t.split == 0) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
-        for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) bias_s[i] = __ldg(d.bias + t.n_tile * BLOCK_N + i);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");  // previous tile's readers are done
+        for (int i = et; i < BLOCK_N; i += 128) bias_s[i] = __ldg(d.bias + t.n_tile * BLOCK_N + i);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
       }
       const int acc = tl & 1;
       mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
@@ -1738,7 +1742,8 @@ int launch_igemm_tma(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CU
                      int occ, cudaStream_t st) {
   int grid = g_sm_count * occ;
   if (grid > g.total_tiles) grid = g.total_tiles;
-  MMDYN_LAUNCH((igemm_tma_kernel<BLOCK_N, A_MODE>), grid, TMA_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, st, *d, tmA, tmW, g);
+  constexpr int EG = BLOCK_N == 256 ? 2 : 1;
+  MMDYN_LAUNCH((igemm_tma_kernel<BLOCK_N, A_MODE, EG>), grid, 64 + 128 * EG, Cfg<BLOCK_N>::SMEM_BYTES, st, *d, tmA, tmW, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -1962,13 +1967,13 @@ int igemm_init() {
   OCC(4, igemm_kernel<256>, Cfg<256>::SMEM_BYTES);
 #undef OCC
 #define SET_TMA(I, BN)                                                                                        \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 0, (BN == 256 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 1, (BN == 256 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<BN, 2, (BN == 256 ? 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<BN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0>,      \
+  MMDYN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_tma_occ[I], igemm_tma_kernel<BN, 0, (BN == 256 ? 2 : 1)>,      \
                                                                 TMA_THREADS, Cfg<BN>::SMEM_BYTES));          \
   if (g_tma_occ[I] < 1) g_tma_occ[I] = 1
   SET_TMA(0, 16);
