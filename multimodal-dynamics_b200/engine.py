@@ -1009,6 +1009,7 @@ class StepEngine:
         # small batch a single branch cannot fill 148 SMs; in a captured graph these become
         # parallel branches
         self.concurrent = os.environ.get("MMDYN_SERIAL_BRANCHES") is None
+        self.stagger = int(os.environ.get("MMDYN_STAGGER", "0"))  # offset between the image branches, in GEMM launches
         self._side = {}
 
     # -- helpers ------------------------------------------------------------------------------
@@ -1045,13 +1046,20 @@ class StepEngine:
         ev = torch.cuda.Event()
         ev.record(cur)
         used = []
+        prev_evt = None
         for k, fn in branches.items():
             st = self._side.get(k)
             if st is None:
                 st = self._side[k] = torch.cuda.Stream()
             st.wait_event(ev)
+            if prev_evt is not None:
+                st.wait_event(prev_evt)  # start this branch behind the previous branch's first GEMM(s): see ops.arm_stagger
             with torch.cuda.stream(st):
+                evt = torch.cuda.Event() if self.stagger > 0 else None
+                ops.arm_stagger(evt, self.stagger)
                 fn()
+                ops.arm_stagger(None, 0)
+            prev_evt = evt
             used.append(st)
         if main_fn is not None:
             main_fn()

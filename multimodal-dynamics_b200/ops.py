@@ -105,6 +105,26 @@ def _esz(t):
     return t.element_size()
 
 
+# Branch staggering (engine.StepEngine._fork): the visual and tactile branches run the same kernel sequence, so without an
+# offset their tensor-bound GEMMs (and their HBM-bound BatchNorm passes) hit the machine at the same time.  The first branch
+# records an event after its k-th GEMM launch; the next branch starts behind that event.
+_stagger = None  # [event, launches to go]
+
+
+def arm_stagger(event, after):
+    global _stagger
+    _stagger = [event, int(after)] if event is not None else None
+
+
+def _stagger_tick():
+    global _stagger
+    if _stagger is not None:
+        _stagger[1] -= 1
+        if _stagger[1] <= 0:
+            _stagger[0].record()
+            _stagger = None
+
+
 def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None, a_pix_stride=None, tag="igemm",
           macs_per_img=None, bce=None, stats=None):
     """bce (out_mode 5, the logits layer with its loss fused): dict(target, mask, dlogits, loss, gscale,
@@ -149,6 +169,7 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
         return 2.0 * macs, float(nbytes)
     with _Timed(tag, alg):
         check(_L().mmdyn_igemm(C.byref(d), _stream()), "mmdyn_igemm")
+    _stagger_tick()
 
 
 def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride=None, g_pix_stride=None,
