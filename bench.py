@@ -555,6 +555,8 @@ def run_b200(args):
 
     # ---- config 5 grid (BASELINE.json configs[4]): GLOBAL batch 64..4096 on THIS run's N GPUs; 128 = --batchsize default ----
     sweep = None
+    if world > 1:
+        dist.barrier()  # rank 0 ran the roofline pass alone: meet before the ranks replay exchange kernels again
     if use_graph and not args.no_sweep and not dyn:
         eng.set_concurrent(True)
         sweep = []

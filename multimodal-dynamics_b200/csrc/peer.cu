@@ -40,7 +40,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void wait_flag(const unsigned int* p, unsigned int epoch) {
   const long long t0 = clock64();
   while (static_cast<int>(ld_acquire_sys(p) - epoch) < 0) {
-    if (clock64() - t0 > 20000000000LL) __trap();
+    if (clock64() - t0 > 120000000000LL) __trap();  // ~60 s: ranks may be a graph capture or a profiling pass apart
   }
 }
 
