@@ -845,6 +845,24 @@ __host__ __device__ constexpr TapSched tap_sched(bool nq4, int ti) {
   }
 }
 
+// Phase-split variant (PS): layers whose live weight blocks do not fit in shared memory (deconv2.fwd, conv3.dgrad: 256 KB)
+// give each CTA ONE output-row parity ph (CTA index parity) and the two sub-pixel phases (ph, pw = 0 / 1) that go with it:
+// half of the live blocks (8 per 64-channel block), 6 taps per filter-column patch — dy = 0 and dy = -1 (ph = 0) or +1
+// (ph = 1); dx = 0 feeds both pw quarters, dx = -1 only pw = 0, dx = +1 only pw = 1.
+struct TapSchedPS {
+  int dx, dy_kind, nruns, q0, len, blk;  // dy_kind 0: dy = 0; 1: dy = ph ? +1 : -1
+};
+__host__ __device__ constexpr TapSchedPS tap_sched_ps(int ti) {
+  switch (ti) {
+    case 0: return {0, 0, 1, 0, 2, 0};
+    case 1: return {0, 1, 1, 0, 2, 2};
+    case 2: return {-1, 0, 1, 0, 1, 4};
+    case 3: return {-1, 1, 1, 0, 1, 5};
+    case 4: return {1, 0, 1, 1, 1, 6};
+    default: return {1, 1, 1, 1, 1, 7};
+  }
+}
+
 struct PatchGeom {
   int lbw, lbn, bh, bn;     // box: bw = 1 << lbw pixels wide (= IW), bh rows, bn = 1 << lbn images
   int tiles_y, img_blocks, total_tiles;
@@ -870,7 +888,7 @@ struct PatchCfg {
   static constexpr int SMEM_BYTES = SA * A_SLOT + W_BYTES + 1024;
 };
 
-template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG>
+template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG, bool PS>
 __global__ void __launch_bounds__(64 + 128 * EG, BLOCK_N == 16 ? 2 : 1)
 igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ PatchGeom g) {
@@ -910,14 +928,30 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
 
   const int CB = CIN_MODE == 0 ? (d.Cin >> 6) : 1;
   const int bw = 1 << g.lbw;
-  const int NQ = BLOCK_N / g.nq;                        // columns per quarter
+  const int NQ = PS ? BLOCK_N / 2 : BLOCK_N / g.nq;    // columns per quarter
   const uint32_t dy_shift = static_cast<uint32_t>(g.bn * bw * RB);  // one image row of the box, in bytes
+  // PS: this CTA's output-row parity; CTAs 2c and 2c + 1 walk the same tiles c, c + gridDim/2, ...
+  const int ph = PS ? static_cast<int>(blockIdx.x & 1) : 0;
+  const int tile_first = PS ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_stride = PS ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ======================= TMA producer =====================================================
     if (elect_one()) {
       // the live weight blocks of the whole layer stay resident in shared memory: fetched once per CTA
-      {
+      if constexpr (PS) {
+        const uint32_t wbar = smem_u32(&w_full);
+        mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(CB * 8 * NQ * RB));
+        for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+          for (int ti = 0; ti < 6; ++ti) {
+            const TapSchedPS ts = tap_sched_ps(ti);
+            const int dy = ts.dy_kind == 0 ? 0 : (ph ? 1 : -1);
+            const int k = ((dy + 1) * 3 + (ts.dx + 1)) * d.Cin + (cb << 6);
+            for (int q = 0; q < ts.len; ++q)
+              tma_load_2d(w_base + (cb * 8 + ts.blk + q) * NQ * RB, &tmW, wbar, k, (ph * 2 + ts.q0 + q) * NQ);
+          }
+      } else {
         const uint32_t wbar = smem_u32(&w_full);
         mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(CB * g.w_bytes_cb));
         for (int cb = 0; cb < CB; ++cb)
@@ -934,11 +968,11 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
           }
       }
       int ia = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < g.total_tiles; tile += tile_stride) {
         const int iblk = tile / g.tiles_y;
         const int img0 = iblk * g.bn, y0 = (tile - iblk * g.tiles_y) * g.bh;
         for (int dxi = 0; dxi < 3; ++dxi) {
-          const int dx = g.tap_dxv[dxi * 3];
+          const int dx = dxi == 0 ? 0 : (dxi == 1 ? -1 : 1);
           for (int cb = 0; cb < CB; ++cb) {
             const int sa = ia % SA;
             mbar_wait(smem_u32(&a_empty[sa]), ((ia / SA) & 1) ^ 1);
@@ -956,14 +990,14 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
     // uniform-datapath code, no ELECT / BRA.U.ANY waterfall around every UTCHMMA); schedule fully unrolled
     if (elect_one()) {
       constexpr bool NQ4 = BLOCK_N >= 64;
-      constexpr int NQC = NQ4 ? BLOCK_N / 4 : BLOCK_N;   // columns (= weight rows) per quarter
+      constexpr int NQC = PS ? BLOCK_N / 2 : (NQ4 ? BLOCK_N / 4 : BLOCK_N);   // columns (= weight rows) per quarter
       // descriptor = DESC_HI | (address >> 4): LBO 16 B (unused with swizzled K-major), SBO = 8 rows, version 1
       constexpr uint64_t DESC_HI = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>((8 * RB) >> 4) << 32) |
                                    (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(LAYOUT) << 61);
       mbar_wait(smem_u32(&w_full), 0);
       const uint32_t sh0 = 0, sh1 = dy_shift >> 4, sh2 = (2 * dy_shift) >> 4;  // dy = -1, 0, +1 in 16-byte units
       int ia = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = tile_first; tile < g.total_tiles; tile += tile_stride, ++tl) {
         const int acc = tl & 1;
         mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
@@ -975,6 +1009,24 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
             mbar_wait(smem_u32(&a_full[sa]), (ia / SA) & 1);
             tc_fence_after();
             const uint32_t a16 = (a_ring + sa * C::A_SLOT) >> 4;
+            if constexpr (PS) {
+              const uint32_t w16 = (w_base + cb * 8 * NQC * RB) >> 4;
+#pragma unroll
+              for (int dyi = 0; dyi < 2; ++dyi) {
+                const TapSchedPS ts = tap_sched_ps(dxi * 2 + dyi);
+                const uint32_t a_tap = a16 + (ts.dy_kind == 0 ? sh1 : (ph ? sh2 : sh0));
+#pragma unroll
+                for (int kk = 0; kk < C::KK; ++kk) {
+                  const uint64_t adesc = DESC_HI | static_cast<uint64_t>(a_tap + 2 * kk);
+                  const uint64_t bdesc = DESC_HI | static_cast<uint64_t>(w16 + ((ts.blk * NQC * RB + 32 * kk) >> 4));
+                  const uint32_t accumulate = (dxi == 0 && dyi == 0 && kk == 0) ? (cb == 0 ? 0u : 1u) : 1u;
+                  umma_f16(tmem_d + ts.q0 * NQC, adesc, bdesc, make_idesc_f16(128, ts.len * NQC, 0, 0, 0, 0), accumulate);
+                }
+              }
+              umma_commit(smem_u32(&a_empty[sa]));
+              ++ia;
+              continue;
+            }
             const uint32_t w16 = (w_base + cb * g.w_bytes_cb) >> 4;
 #pragma unroll
             for (int dyi = 0; dyi < 3; ++dyi) {
@@ -1034,7 +1086,7 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
     };
-    for (int tile = blockIdx.x + eg * gridDim.x, tl = eg; tile < g.total_tiles; tile += EG * gridDim.x, tl += EG) {
+    for (int tile = tile_first + eg * tile_stride, tl = eg; tile < g.total_tiles; tile += EG * tile_stride, tl += EG) {
       const int iblk = tile / g.tiles_y;
       const int img = iblk * g.bn + n_l, yv = (tile - iblk * g.tiles_y) * g.bh + y_l, xv = x_l;
       const bool valid = img < d.n_img;
@@ -1168,15 +1220,21 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
           tmem_ld_x16(tmem_d + c0, va);
           tmem_ld_wait(va);
           tmem_ld_x16(tmem_d + Cc + c0, vb);
-          emit(va, 0);
-          tmem_ld_wait(vb);
-          tmem_ld_x16(tmem_d + 2 * Cc + c0, va);
-          emit(vb, 1);
-          tmem_ld_wait(va);
-          tmem_ld_x16(tmem_d + 3 * Cc + c0, vb);
-          emit(va, 2);
-          tmem_ld_wait(vb);
-          emit(vb, 3);
+          if constexpr (PS) {  // this CTA holds the phases (ph, 0) and (ph, 1)
+            emit(va, ph * 2);
+            tmem_ld_wait(vb);
+            emit(vb, ph * 2 + 1);
+          } else {
+            emit(va, 0);
+            tmem_ld_wait(vb);
+            tmem_ld_x16(tmem_d + 2 * Cc + c0, va);
+            emit(vb, 1);
+            tmem_ld_wait(va);
+            tmem_ld_x16(tmem_d + 3 * Cc + c0, vb);
+            emit(va, 2);
+            tmem_ld_wait(vb);
+            emit(vb, 3);
+          }
           if (want_stats) {
             // 32 values (16 sums, 16 sums of squares) over the warp's 32 rows: butterfly reduce-scatter, 31 shuffles;
             // lane l ends with the total of value l (l < 16: sum of channel c0 + l; l >= 16: squares of c0 + l - 16)
@@ -1780,16 +1838,16 @@ int ilog2(int v) {
   return l;
 }
 
-template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG>
+template <int BLOCK_N, int CIN_MODE, int SA, int W_KB, int EG, bool PS = false>
 int launch_patch(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW, const PatchGeom& g,
                  cudaStream_t st) {
   using C = PatchCfg<BLOCK_N, CIN_MODE, SA, W_KB>;
-  MMDYN_REQUIRE((d->Cin >= 64 ? d->Cin / 64 : 1) * g.w_bytes_cb <= C::W_BYTES,
-                "igemm patch_mode: %d bytes of live weights do not fit the resident region (%d)",
-                (d->Cin >= 64 ? d->Cin / 64 : 1) * g.w_bytes_cb, C::W_BYTES);
+  const int w_need = (d->Cin >= 64 ? d->Cin / 64 : 1) * (PS ? 8 * (BLOCK_N / 2) * C::RB : g.w_bytes_cb);
+  MMDYN_REQUIRE(w_need <= C::W_BYTES, "igemm patch_mode: %d bytes of live weights do not fit the resident region (%d)",
+                w_need, C::W_BYTES);
   static bool configured = false;
   if (!configured) {
-    MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG>,
+    MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG, PS>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
@@ -1798,8 +1856,13 @@ int launch_patch(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtens
   if (occ > 6) occ = 6;
   if (occ < 1) occ = 1;
   int grid = g_sm_count * occ;
-  if (grid > g.total_tiles) grid = g.total_tiles;
-  MMDYN_LAUNCH((igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG>), grid, 64 + 128 * EG, C::SMEM_BYTES, st, *d, tmA, tmW, g);
+  if (PS) {  // two CTAs (output-row parities) per tile
+    grid &= ~1;
+    if (grid > 2 * g.total_tiles) grid = 2 * g.total_tiles;
+  } else if (grid > g.total_tiles) {
+    grid = g.total_tiles;
+  }
+  MMDYN_LAUNCH((igemm_patch_kernel<BLOCK_N, CIN_MODE, SA, W_KB, EG, PS>), grid, 64 + 128 * EG, C::SMEM_BYTES, st, *d, tmA, tmW, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -1835,6 +1898,7 @@ int igemm_patch(const mmdyn_igemm_desc* d, cudaStream_t st) {
   const int rb = cin_mode == 0 ? 128 : 64;
   MMDYN_REQUIRE(g.a_rows * rb <= (cin_mode == 0 ? 20 * 1024 : 12 * 1024), "igemm patch_mode: activation box of %d rows", g.a_rows);
   g.nq = d->out_mode == 4 ? 4 : 1;
+  MMDYN_REQUIRE(d->N != 256 || (d->Cin == 128 && d->out_mode == 4), "igemm patch_mode: N = 256 is the phase-split layer (Cin = 128)");
   MMDYN_REQUIRE(d->out_mode != 4 || (d->N == 4 * d->ldc && d->ldc % 16 == 0 && d->N >= 64),
                 "igemm patch_mode: out_mode 4 needs N = 4*ldc >= 64");
   MMDYN_REQUIRE(d->out_mode == 4 || d->N == 16, "igemm patch_mode: out_mode 3 / 5 need N = 16");
@@ -1912,6 +1976,8 @@ int igemm_patch(const mmdyn_igemm_desc* d, cudaStream_t st) {
   switch (d->N) {
     case 64: return launch_patch<64, 0, 6, 64, 2>(d, tmA, tmW, g, st);
     case 128: return launch_patch<128, 0, 7, 64, 2>(d, tmA, tmW, g, st);  // 64 KB of weights + 7 x 20 KB patches, 1 CTA per SM
+    case 256:  // phase-split: each CTA owns one output-row parity = 128 columns, 128 KB of weights + 4 x 20 KB patches
+      return launch_patch<128, 0, 4, 128, 2, true>(d, tmA, tmW, g, st);
     default: break;
   }
   set_last_error("igemm patch_mode: N=%d unsupported", d->N);

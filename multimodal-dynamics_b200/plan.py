@@ -28,6 +28,7 @@ MERGE_PHASES = os.environ.get("MMDYN_MERGE_PHASES", "1") != "0"
 # merged 3x3-tap layers on the patch-reuse kernel (one activation box per filter column, live weight blocks
 # only); MMDYN_NO_PATCH=1 keeps them on the generic one-box-per-tap kernel (A/B measurements)
 USE_PATCH = os.environ.get("MMDYN_NO_PATCH") is None
+PATCH_SPLIT = os.environ.get("MMDYN_NO_PATCH_SPLIT") is None  # deconv2.fwd / conv3.dgrad on the phase-split patch kernel
 
 
 @dataclass
@@ -167,8 +168,9 @@ def _merged_geom(Hv, Cg, Cn_out, widx_fn):
     geom = GemmGeom(P=Hv * Hv, OXv=Hv, IH=Hv, IW=Hv, Cin=Cg, s_in=1, tap_dy=[[t[0] for t in TAPS3]],
                     tap_dx=[[t[1] for t in TAPS3]], N=4 * Cn_out, OH=2 * Hv, OW=2 * Hv, s_out=2, off_y=[0],
                     off_x=[0], ldc=Cn_out, out_mode=4,
-                    patch=int(USE_PATCH and Hv in (8, 16, 32) and (Cg % 64 == 0) and 4 * Cn_out in (64, 128)
-                              and 16 * Cn_out * 128 * (Cg // 64) <= 64 * 1024))  # live weight blocks stay resident
+                    patch=int(USE_PATCH and Hv in (8, 16, 32) and (Cg % 64 == 0) and
+                              ((4 * Cn_out in (64, 128) and 16 * Cn_out * 128 * (Cg // 64) <= 64 * 1024)  # live blocks resident
+                               or (PATCH_SPLIT and 4 * Cn_out == 256 and Cg == 128))))  # phase-split: half of them per CTA
     idx = np.full((4 * Cn_out, 9 * Cg), -1, np.int32)
     for ph in (0, 1):
         for pw in (0, 1):
