@@ -87,7 +87,7 @@ typedef struct mmdyn_igemm_desc {
   /* out_mode 5 only — the logits layer with the reconstruction loss fused into its epilogue
    * (vae.py:277 + problems.py:409-413, 431-449): per output pixel BCE-with-logits against
    * bce_target (and bce_mask), summed into bce_loss[bce_slot[group]], gradient
-   * gscale*(sigmoid(x*m) - t*m)*m written as fp16 NHWC8 with a one-pixel border (see mmdyn_bce_logits,
+   * gscale*(sigmoid(x*m) - t*m)*m written as fp16 NHWC4 with a one-pixel border (see mmdyn_bce_logits,
    * pad = 1).  group = image / bce_rows_per_group; every group is compared with the same
    * bce_rows_per_group target images.  The fp32 NCHW logits themselves are only stored for images
    * in [logit_row_lo, logit_row_hi). */
@@ -109,6 +109,9 @@ typedef struct mmdyn_igemm_desc {
    * (replaces mmdyn_bn_stats for this layer's output; caller zeroes bn_sums). */
   int32_t bn_rows_per_group;
   float* bn_sums;
+  int32_t s_in_x;       /* input stride along x when it differs from s_in (0 = s_in): the 4-channel logit
+                           gradient is addressed in 16-byte pixel PAIRS along x (TMA strides are multiples of
+                           16 bytes), so its window tap advances 1 pair per virtual pixel but 2 rows per row  */
 } mmdyn_igemm_desc;
 int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream);
 
@@ -123,7 +126,8 @@ typedef struct mmdyn_wgrad_desc {
   float* dW;            /* fp32 [Cn][ntaps*Cg], accumulated with atomics (caller zeroes)       */
   int32_t n_img, P, OXv, IH, IW;
   int32_t g_pix_stride; /* elements between consecutive pixels of G                            */
-  int32_t Cg;           /* channels per tap of G (multiple of 8), ntaps*Cg multiple of 128     */
+  int32_t Cg;           /* channels per tap of G (multiple of 8), ntaps*Cg multiple of 128
+                           (or Cg = 16, ntaps = 4: 64 columns)                                 */
   int32_t s_in, ntaps;
   int8_t tap_dy[MMDYN_MAX_TAPS];
   int8_t tap_dx[MMDYN_MAX_TAPS];
@@ -134,6 +138,7 @@ typedef struct mmdyn_wgrad_desc {
   float scale;
   int32_t g_row_stride; /* elements between rows / images of G; 0 = dense.  Same overlapping-   */
   int32_t g_img_stride; /* window convention as mmdyn_igemm_desc (TMA path only)                */
+  int32_t s_in_x;       /* as mmdyn_igemm_desc.s_in_x                                           */
 } mmdyn_wgrad_desc;
 int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream);
 
@@ -236,13 +241,13 @@ int mmdyn_poe_bwd_multi(const mmdyn_poe_pass* passes, int n_passes, int use_prio
                         int accumulate, int B, int D, void* stream);
 
 /* --- reconstruction losses (problems.py:409-413, 431-449, 499-503, 535) -----------------------
- * BCE-with-logits, reduction 'sum' into loss_sum[0]; dlogits (fp16 NHWC, 8 channels per pixel,
+ * BCE-with-logits, reduction 'sum' into loss_sum[0]; dlogits (fp16 NHWC, 4 channels per pixel,
  * 3 used) = gscale*(sigmoid(x) - t)*m.  mask (optional, NCHW fp32) multiplies logits and targets
  * as the reference does.  logits/target: NCHW fp32 (n,3,H,W).  pad > 0: dlogits images are
  * (H+2*pad) x (W+2*pad) with a border that is never written (the caller zeroes it once): the
  * layout the decoder backward reads as overlapping 4-pixel windows (mmdyn_igemm_desc.a_row_stride). */
 int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
-                     void* dlogits_nhwc8, float gscale, int n, int H, int W, int pad, void* stream);
+                     void* dlogits_nhwc4, float gscale, int n, int H, int W, int pad, void* stream);
 /* Same loss for callers outside the fused step (Reconstruction._elbo_loss / _mvae_elbo_loss called
  * on their own, problems.py:401-458, and the per-sample scoring path reduce=False, :415-417, :451-456):
  * logits / target / mask are flat fp32 [n][per_sample] in any (identical) layout; loss_sum[0] += total,
@@ -290,10 +295,11 @@ int mmdyn_gather_add_f32(const float* src, const int32_t* inv, float* dst, long 
 int mmdyn_f32_to_f16(const float* src, void* dst, long long n, float scale, void* stream);
 /* x *= s in place */
 int mmdyn_scale_f32(float* x, long long n, float s, void* stream);
-/* fp32 NCHW (n,3,H,W) logit gradients -> fp16 NHWC8 (3 used) times scale: the layout the decoder
- * backward reads (used when the loss is computed outside the library, e.g. by torch autograd) */
-int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int H, int W,
-                          int pad, void* stream);
+/* fp32 NCHW (n,3,H,W) logit gradients -> fp16 NHWC with cp = 4 or 8 channels per pixel (3 used) times
+ * scale: cp = 4 is the layout the decoder backward reads (used when the loss is computed outside the
+ * library, e.g. by torch autograd) */
+int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc, float scale, int n, int H, int W,
+                          int pad, int cp, void* stream);
 
 /* --- CVAE conditioning (vae.py:231-237, 286-291) ---------------------------
  * torch.cat((x, c), -1) followed by Linear(K0 + cd, N) = Linear on x (tensor cores, weight columns

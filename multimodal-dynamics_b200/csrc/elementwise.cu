@@ -41,6 +41,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 constexpr int RED_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
@@ -911,7 +916,7 @@ __device__ __forceinline__ float block_sum_256(float v) {
 }
 
 // one thread per 4 consecutive pixels: float4 loads from each of the 3 planes (coalesced), four
-// 16-byte NHWC8 gradient stores
+// 8-byte NHWC4 gradient stores (32 contiguous bytes)
 __global__ void __launch_bounds__(256)
 bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                   const float* __restrict__ mask, float* __restrict__ loss_sum,
@@ -925,11 +930,9 @@ bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ ta
     const long long p = q << 2;
     const long long img = p / HW;
     const int hw = static_cast<int>(p - img * HW);
-    float g[4][8];
+    float g[4][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) g[k][c] = 0.0f;
+    for (int k = 0; k < 4; ++k) g[k][3] = 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const long long idx = (img * 3 + c) * HW + hw;
@@ -953,7 +956,8 @@ bce_logits_kernel(const float* __restrict__ logits, const float* __restrict__ ta
       const int y = hw / W, x = hw - y * W;
       const long long o = (img * Hp + y + pad) * Wp + x + pad;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(dlogits)[o + k] = pack8(g[k]);
+      for (int k = 0; k < 4; ++k)
+        reinterpret_cast<uint2*>(dlogits)[o + k] = make_uint2(pack_h2(g[k][0], g[k][1]), pack_h2(g[k][2], 0.0f));
     }
   }
   const float t = block_sum_256(acc);
@@ -1170,7 +1174,7 @@ scale_f32_kernel(float* __restrict__ x, long long n, float s) {
 
 __global__ void __launch_bounds__(256)
 logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, float scale, long long n_pix,
-                       int HW, int W, int pad) {
+                       int HW, int W, int pad, int cp) {
   pdl_sync();
   const int H = HW / W, Wp = W + 2 * pad, Hp = H + 2 * pad;
   for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < n_pix;
@@ -1181,7 +1185,9 @@ logit_grad_pack_kernel(const float* __restrict__ dl, __half* __restrict__ out, f
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c] = scale * dl[(img * 3 + c) * HW + hw];
     const int y = hw / W, x = hw - y * W;
-    reinterpret_cast<uint4*>(out)[(img * Hp + y + pad) * Wp + x + pad] = pack8(g);
+    const long long o = (img * Hp + y + pad) * Wp + x + pad;
+    if (cp == 8) reinterpret_cast<uint4*>(out)[o] = pack8(g);
+    else reinterpret_cast<uint2*>(out)[o] = make_uint2(pack_h2(g[0], g[1]), pack_h2(g[2], 0.0f));
   }
 }
 
@@ -1670,13 +1676,13 @@ extern "C" int mmdyn_poe_bwd_multi(const mmdyn_poe_pass* passes, int n_passes, i
 }
 
 extern "C" int mmdyn_bce_logits(const float* logits, const float* target, const float* mask, float* loss_sum,
-                                void* dlogits_nhwc8, float gscale, int n, int H, int W, int pad, void* stream) {
+                                void* dlogits_nhwc4, float gscale, int n, int H, int W, int pad, void* stream) {
   MMDYN_REQUIRE(logits && target && loss_sum && n > 0 && H > 0 && W > 0 && W % 4 == 0 && pad >= 0,
                 "bce_logits: bad arguments (n=%d H=%d W=%d pad=%d; W must be a multiple of 4)", n, H, W, pad);
   const int HW = H * W;
   const long long n_pix = static_cast<long long>(n) * HW;
   MMDYN_LAUNCH((bce_logits_kernel), grid_for(n_pix >> 2), 256, 0, ST(stream), logits, target, mask, loss_sum,
-                                                             reinterpret_cast<__half*>(dlogits_nhwc8), gscale,
+                                                             reinterpret_cast<__half*>(dlogits_nhwc4), gscale,
                                                              n_pix, HW, W, pad);
   LAUNCHED();
   return MMDYN_OK;
@@ -1797,13 +1803,14 @@ extern "C" int mmdyn_scale_f32(float* x, long long n, float s, void* stream) {
   return MMDYN_OK;
 }
 
-extern "C" int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc8, float scale, int n, int H, int W,
-                                     int pad, void* stream) {
-  MMDYN_REQUIRE(dlogits_nchw && out_nhwc8 && n > 0 && H > 0 && W > 0 && pad >= 0, "logit_grad_pack: bad arguments");
+extern "C" int mmdyn_logit_grad_pack(const float* dlogits_nchw, void* out_nhwc, float scale, int n, int H, int W,
+                                     int pad, int cp, void* stream) {
+  MMDYN_REQUIRE(dlogits_nchw && out_nhwc && n > 0 && H > 0 && W > 0 && pad >= 0 && (cp == 4 || cp == 8),
+                "logit_grad_pack: bad arguments (cp=%d must be 4 or 8)", cp);
   const int HW = H * W;
   const long long n_pix = static_cast<long long>(n) * HW;
-  MMDYN_LAUNCH((logit_grad_pack_kernel), grid_for(n_pix), 256, 0, ST(stream), dlogits_nchw, reinterpret_cast<__half*>(out_nhwc8),
-                                                                  scale, n_pix, HW, W, pad);
+  MMDYN_LAUNCH((logit_grad_pack_kernel), grid_for(n_pix), 256, 0, ST(stream), dlogits_nchw, reinterpret_cast<__half*>(out_nhwc),
+                                                                  scale, n_pix, HW, W, pad, cp);
   LAUNCHED();
   return MMDYN_OK;
 }

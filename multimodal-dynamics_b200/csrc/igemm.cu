@@ -371,7 +371,12 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
 // A tile is 128 GEMM rows = a box of bw x bh virtual pixels x bn images (bw*bh*bn = 128), or, for
 // the 5x5 / single-pixel layers, one virtual pixel x 128 images ("pixel-major").
 // A_MODE: 0 = Cin % 64 == 0 (one 128B-swizzled box per k-block), 1 = Cin == 32 (two 64B-swizzled
-// boxes = two taps), 2 = Cin == 8 (eight un-swizzled 16-byte boxes = eight taps).
+// boxes = two taps), 2 = Cin == 8 (eight un-swizzled 16-byte boxes = eight taps), 3 = Cin == 16: the 4-channel
+// logit gradient read through 4-pixel (32-byte) windows that advance 16 bytes per output pixel.  The windows
+// are never materialised: per row tap the raw padded image rows are fetched twice as 512-byte runs (pairs
+// 0..31 and pairs 1..32 of each of the tile's 4 rows), and an un-swizzled K-major descriptor whose two 16-byte
+// K chunks point into the two copies (LBO = 2 KB) with 8-row groups 128 bytes apart reads window x as pairs
+// x, x + 1 — 32 TMA row requests of 512 bytes per tile instead of 512 requests of 32 bytes.
 // ---------------------------------------------------------------------------------------------
 constexpr int TMA_THREADS = 192;
 
@@ -499,7 +504,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       for (int tile = tile0; tile < g.total_tiles; tile += tile_step) {
         const TileCoord2 t = decode_tile2(d, g, tile);
         const int kb_begin = t.split * kb_per, kb_end = min(kb_total, kb_begin + kb_per);
-        const int wx = t.x0 * d.s_in, wy = t.y0 * d.s_in;
+        const int wx = t.x0 * (d.s_in_x ? d.s_in_x : d.s_in), wy = t.y0 * d.s_in;
         const uint32_t mask = live_taps(t);
         const int w_row = t.phase * d.N + t.n_tile * BLOCK_N;
         int tap = A_MODE == 0 ? kb_begin / CB : 0, cb = A_MODE == 0 ? kb_begin - tap * CB : 0;
@@ -530,6 +535,10 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
               const int tp = 2 * kb + b;
               tma_load_4d(a_stage + b * 8192, &tmA, bar, 0, wx + d.tap_dx[t.phase][tp], wy + d.tap_dy[t.phase][tp], t.img0);
             }
+          } else if (A_MODE == 3) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b)  // (row tap b / 2, copy b % 2 shifted by one pixel pair = 8 elements)
+              tma_load_4d(a_stage + b * 2048, &tmA, bar, (b & 1) * 8, 0, wy + d.tap_dy[t.phase][4 * kb + (b >> 1)], t.img0);
           } else {
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
@@ -570,7 +579,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
           const uint32_t b16 = a16 + (A_STAGE_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // 4 x (K = 16) per 64-wide k-block
-            const uint32_t a_off = A_MODE == 0 ? 2 * kk : (A_MODE == 1 ? (kk >> 1) * (8192 >> 4) + (kk & 1) * 2 : kk * (4096 >> 4));
+            const uint32_t a_off = A_MODE == 0 ? 2 * kk : (A_MODE == 1 ? (kk >> 1) * (8192 >> 4) + (kk & 1) * 2 : kk * (4096 >> 4));  // modes 2, 3: 4 KB per K = 16
             umma_f16(tmem_d, A_HI | static_cast<uint64_t>(a16 + a_off), B_HI | static_cast<uint64_t>(b16 + 2 * kk), idesc,
                      (i | kk) ? 1u : 0u);
           }
@@ -737,11 +746,11 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
                 for (int ph = 0; ph < 2; ++ph) {
                   const long long pix =
                       (static_cast<long long>(img) * (d.OH + 2) + 2 * yv + ph + 1) * (d.OW + 2) + 2 * xv + 1;
-                  uint4* o4 = reinterpret_cast<uint4*>(go + pix * 8);
+                  uint2* o2 = reinterpret_cast<uint2*>(go + pix * 4);  // NHWC4: 8 bytes per pixel
 #pragma unroll
                   for (int pw = 0; pw < 2; ++pw) {
                     const float* q = gq[ph * 2 + pw];
-                    o4[pw] = make_uint4(pack_h2(q[0], q[1]), pack_h2(q[2], 0.0f), 0u, 0u);
+                    o2[pw] = make_uint2(pack_h2(q[0], q[1]), pack_h2(q[2], 0.0f));
                   }
                 }
               }
@@ -1173,11 +1182,11 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
               for (int ph = 0; ph < 2; ++ph) {
                 const long long pix =
                     (static_cast<long long>(img) * (d.OH + 2) + 2 * yv + ph + 1) * (d.OW + 2) + 2 * xv + 1;
-                uint4* o4 = reinterpret_cast<uint4*>(go + pix * 8);
+                uint2* o2 = reinterpret_cast<uint2*>(go + pix * 4);  // NHWC4: 8 bytes per pixel
 #pragma unroll
                 for (int pw = 0; pw < 2; ++pw) {
                   const float* q = gq[ph * 2 + pw];
-                  o4[pw] = make_uint4(pack_h2(q[0], q[1]), pack_h2(q[2], 0.0f), 0u, 0u);
+                  o2[pw] = make_uint2(pack_h2(q[0], q[1]), pack_h2(q[2], 0.0f));
                 }
               }
             }
@@ -1446,7 +1455,11 @@ wgrad_kernel(const __grid_constant__ mmdyn_wgrad_desc d) {
 // rows (bw x bh virtual pixels x bn images, or one pixel x 64 images); they land in shared memory
 // as rows-of-channels, which IS the MN-major UMMA layout, so nothing is transposed or touched by
 // the LSU.  G_MODE: 0 = Cg % 64 == 0 (2 boxes of 64 k-columns, 128B swizzle), 1 = Cg == 32 (4 taps,
-// 64B swizzle), 2 = Cg == 8 (16 taps, un-swizzled 16-byte rows).
+// 64B swizzle), 2 = Cg == 8 (16 taps, un-swizzled 16-byte rows), 3 = Cg == 16 with ntaps * Cg = 64: the 4-channel
+// logit gradient (or the padded 4-channel input image) through 4-pixel windows — per row tap the raw rows are
+// fetched twice as 512-byte runs (pixel pairs 0..31 and 1..32), which land as the two 16-byte column chunks of
+// that tap in G_MODE 2's layout: 16 TMA row requests per step instead of 256.  The upper 64 accumulator rows
+// multiply whatever the stage held before and are never read.
 //   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (fp32 atomics into dW)
 // ---------------------------------------------------------------------------------------------
 struct WgradGeomDev {
@@ -1517,6 +1530,12 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
           tdx[b] = d.tap_dx[(kcol0 >> 5) + b];
           tdy[b] = d.tap_dy[(kcol0 >> 5) + b];
         }
+      } else if (G_MODE == 3) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          tdx[b] = d.tap_dx[b];
+          tdy[b] = d.tap_dy[b];
+        }
       } else {
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
@@ -1556,9 +1575,12 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
         const uint32_t bar = smem_u32(&full_bar[s]);
         const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
         const uint32_t b_stage = a_stage + A_STAGE_BYTES;
-        mbar_arrive_expect_tx(bar, A_STAGE_BYTES + NAT_BYTES);
-        const int wx = x0 * d.s_in, wy = y0 * d.s_in;
-        if (G_MODE == 0) {
+        mbar_arrive_expect_tx(bar, (G_MODE == 3 ? 8 * 1024 : A_STAGE_BYTES) + NAT_BYTES);
+        const int wx = x0 * (d.s_in_x ? d.s_in_x : d.s_in), wy = y0 * d.s_in;
+        if (G_MODE == 3) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) tma_load_4d(a_stage + b * 1024, &tmG, bar, (b & 1) * 8, 0, wy + tdy[b >> 1], img0);
+        } else if (G_MODE == 0) {
 #pragma unroll
           for (int b = 0; b < 2; ++b) tma_load_4d(a_stage + b * 8192, &tmG, bar, tc0[b], wx + tdx[b], wy + tdy[b], img0);
         } else if (G_MODE == 1) {
@@ -1605,8 +1627,9 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
     mbar_wait(smem_u32(&accum_bar), 0);
     tc_fence_after();
     float* o = d.dW + static_cast<long long>(n0) * d.ldw + kcol0 + q4 * 32 + lane;
+    const int c_end = (G_MODE == 3 && q4 >= 2) ? 0 : CN;  // G_MODE 3: 64 live k-columns
 #pragma unroll 1
-    for (int c0 = 0; c0 < CN; c0 += 16) {
+    for (int c0 = 0; c0 < c_end; c0 += 16) {
       uint32_t v[16];
       tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + c0, v);
       tmem_ld_wait(v);
@@ -1812,6 +1835,10 @@ int dispatch_amode(int a_mode, const mmdyn_igemm_desc* d, const CUtensorMap& tmA
                    const TileGeom& g, int occ, cudaStream_t st) {
   if (a_mode == 0) return launch_igemm_tma<BLOCK_N, 0>(d, tmA, tmW, g, occ, st);
   if (a_mode == 1) return launch_igemm_tma<BLOCK_N, 1>(d, tmA, tmW, g, occ, st);
+  if (a_mode == 3) {
+    if constexpr (BLOCK_N == 32) return launch_igemm_tma<32, 3>(d, tmA, tmW, g, occ, st);
+    MMDYN_REQUIRE(false, "igemm: Cin = 16 is built for N = 32 only (N=%d)", d->N);
+  }
   return launch_igemm_tma<BLOCK_N, 2>(d, tmA, tmW, g, occ, st);
 }
 
@@ -1829,6 +1856,10 @@ int dispatch_gmode(int g_mode, const mmdyn_wgrad_desc* d, const CUtensorMap& tmG
                    const WgradGeomDev& g, dim3 grid, cudaStream_t st) {
   if (g_mode == 0) return launch_wgrad_tma<CN, 0>(d, tmG, tmN, g, grid, st);
   if (g_mode == 1) return launch_wgrad_tma<CN, 1>(d, tmG, tmN, g, grid, st);
+  if (g_mode == 3) {
+    if constexpr (CN == 32) return launch_wgrad_tma<32, 3>(d, tmG, tmN, g, grid, st);
+    MMDYN_REQUIRE(false, "wgrad: Cg = 16 is built for Cn = 32 only (Cn=%d)", d->Cn);
+  }
   return launch_wgrad_tma<CN, 2>(d, tmG, tmN, g, grid, st);
 }
 
@@ -2048,6 +2079,8 @@ int igemm_init() {
   SET_TMA(3, 128);
   SET_TMA(4, 256);
 #undef SET_TMA
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<32, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM_BYTES));
+  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM_BYTES));
 #define SET_WG(CN)                                                                                            \
   MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         Cfg<CN>::SMEM_BYTES));                                               \
@@ -2161,9 +2194,10 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
   const int occ_idx = d->block_n == 16 ? 0 : d->block_n == 32 ? 1 : d->block_n == 64 ? 2 : d->block_n == 128 ? 3 : 4;
 
   // ---- TMA-fed path: tile = box of bw x bh virtual pixels x bn images, or pixel-major -------------
-  const int a_mode = (d->Cin % 64 == 0) ? 0 : (d->Cin == 32 ? 1 : (d->Cin == 8 ? 2 : -1));
+  const int a_mode = (d->Cin % 64 == 0) ? 0 : (d->Cin == 32 ? 1 : (d->Cin == 8 ? 2 : (d->Cin == 16 ? 3 : -1)));
   static const bool legacy = getenv("MMDYN_IGEMM_LEGACY") != nullptr;
-  if (a_mode >= 0 && !legacy && (a_mode != 1 || d->ntaps % 2 == 0) && (a_mode != 2 || d->ntaps % 8 == 0)) {
+  if (a_mode >= 0 && !legacy && (a_mode != 1 || d->ntaps % 2 == 0) && (a_mode != 2 || d->ntaps % 8 == 0) &&
+      (a_mode != 3 || d->ntaps % 4 == 0)) {
     TileGeom g = {};
     const int OYv = d->P / d->OXv;
     const int bw = d->OXv;
@@ -2194,8 +2228,9 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     g.total_tiles = static_cast<int>(total_ll);
 
     CUtensorMap tmA;
-    const int kc = a_mode == 0 ? 64 : (a_mode == 1 ? 32 : 8);
+    const int kc = a_mode == 0 ? 64 : (a_mode == 1 ? 32 : (a_mode == 3 ? 16 : 8));
     const int es = g.pixel_major ? 1 : d->s_in;
+    const int esx = g.pixel_major ? 1 : (d->s_in_x ? d->s_in_x : d->s_in);
     const cuuint64_t adim[4] = {static_cast<cuuint64_t>(d->Cin), static_cast<cuuint64_t>(d->IW),
                                 static_cast<cuuint64_t>(d->IH), static_cast<cuuint64_t>(d->n_img)};
     const cuuint64_t pix_b = static_cast<cuuint64_t>(d->a_pix_stride) * 2;
@@ -2203,14 +2238,30 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     const cuuint64_t img_b = d->a_img_stride ? static_cast<cuuint64_t>(d->a_img_stride) * 2 : row_b * d->IH;
     const cuuint64_t astr[3] = {pix_b, row_b, img_b};
     const cuuint32_t abox[4] = {static_cast<cuuint32_t>(kc),
-                                static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * es),
+                                static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * esx),
                                 static_cast<cuuint32_t>(g.pixel_major ? 1 : bh * es), static_cast<cuuint32_t>(bn)};
-    const cuuint32_t aes[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
+    const cuuint32_t aes[4] = {1, static_cast<cuuint32_t>(esx), static_cast<cuuint32_t>(es), 1};
     const CUtensorMapSwizzle asw = a_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                : (a_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
-    const CUresult ar = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), adim, astr, abox, aes,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, asw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult ar;
+    if (a_mode == 3) {
+      // raw rows: (elements of a padded row, 1, rows, images); box = 256 elements x bh rows (see the kernel header)
+      MMDYN_REQUIRE(!g.pixel_major && bw == 32 && bh == 4 && bn == 1 && d->a_pix_stride == 8 && esx == 1 &&
+                        d->a_row_stride >= (d->IW + 1) * 8 && d->a_row_stride >= 264,
+                    "igemm: Cin = 16 is the 4-pixel window form (OXv = 32, pixel pairs of 8 elements, s_in_x = 1)");
+      for (int t_ = 0; t_ < d->ntaps; ++t_) MMDYN_REQUIRE(d->tap_dx[0][t_] == 0, "igemm: Cin = 16 takes row taps only");
+      const cuuint64_t rdim[4] = {static_cast<cuuint64_t>(d->a_row_stride), 1, static_cast<cuuint64_t>(d->IH),
+                                  static_cast<cuuint64_t>(d->n_img)};
+      const cuuint64_t rstr[3] = {row_b, row_b, img_b};
+      const cuuint32_t rbox[4] = {256, 1, static_cast<cuuint32_t>(bh * es), 1};
+      const cuuint32_t res[4] = {1, 1, static_cast<cuuint32_t>(es), 1};
+      ar = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), rdim, rstr, rbox, res,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      ar = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->A), adim, astr, abox, aes,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, asw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (ar != CUDA_SUCCESS) {
       set_last_error("igemm: cuTensorMapEncodeTiled(A) failed with CUresult %d (Cin=%d IW=%d IH=%d box=%u,%u,%u,%u es=%d)",
                      static_cast<int>(ar), d->Cin, d->IW, d->IH, abox[0], abox[1], abox[2], abox[3], es);
@@ -2257,8 +2308,8 @@ extern "C" int mmdyn_debug_occ(int which, int idx) {
 
 extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
   MMDYN_REQUIRE(d && d->G && d->Nat && d->dW, "wgrad: null pointer");
-  MMDYN_REQUIRE(d->Cg > 0 && d->Cg % 8 == 0 && (d->ntaps * d->Cg) % 128 == 0,
-                "wgrad: Cg=%d ntaps=%d (ntaps*Cg must be a multiple of 128)", d->Cg, d->ntaps);
+  MMDYN_REQUIRE(d->Cg > 0 && d->Cg % 8 == 0 && ((d->ntaps * d->Cg) % 128 == 0 || (d->Cg == 16 && d->ntaps == 4)),
+                "wgrad: Cg=%d ntaps=%d (ntaps*Cg must be a multiple of 128, or the 4 x 16 window form)", d->Cg, d->ntaps);
   MMDYN_REQUIRE(d->ntaps >= 1 && d->ntaps <= MMDYN_MAX_TAPS, "wgrad: ntaps=%d", d->ntaps);
   const int cn_tile = d->Cn >= 256 ? 256 : d->Cn;
   MMDYN_REQUIRE(cn_tile == 16 || cn_tile == 32 || cn_tile == 64 || cn_tile == 128 || cn_tile == 256,
@@ -2273,14 +2324,18 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
   const bool custom_strides = d->g_row_stride != 0 || d->g_img_stride != 0 || d->g_pix_stride < d->Cg;
   MMDYN_REQUIRE(d->g_row_stride % 8 == 0 && d->g_img_stride % 8 == 0 && d->g_row_stride >= 0 && d->g_img_stride >= 0,
                 "wgrad: g_row_stride / g_img_stride must be non-negative multiples of 8 elements");
-  dim3 grid(d->row_splits, (d->ntaps * d->Cg) / 128, d->Cn / cn_tile);
+  dim3 grid(d->row_splits, (d->ntaps * d->Cg + 127) / 128, d->Cn / cn_tile);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // ---- TMA-fed path ---------------------------------------------------------------------------------
   // Cg == 8 (16-byte pixels: logit gradients, repacked input) stays on the cp.async gather: sixteen
   // 1 KB boxes of 16-byte rows per step are slower through TMA than 16-byte LDGSTS (measured)
   static const bool g8_tma = getenv("MMDYN_WGRAD_G8_TMA") != nullptr;
-  const int g_mode = (d->Cg % 64 == 0) ? 0 : (d->Cg == 32 ? 1 : ((d->Cg == 8 && g8_tma) ? 2 : -1));
+  const int g_mode = (d->Cg % 64 == 0) ? 0
+                     : d->Cg == 32     ? 1
+                     : (d->Cg == 16 && d->ntaps == 4) ? 3
+                     : (d->Cg == 8 && g8_tma)         ? 2
+                                                      : -1;
   static const bool legacy = getenv("MMDYN_WGRAD_LEGACY") != nullptr;
   EncodeTiledFn enc = get_encode_fn();
   if (g_mode >= 0 && !legacy && enc) {
@@ -2310,7 +2365,8 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
     if (static_cast<long long>(grid.x) > steps) grid.x = static_cast<unsigned>(steps);
 
     const int es = g.pixel_major ? 1 : d->s_in;
-    const int kc = g_mode == 0 ? 64 : (g_mode == 1 ? 32 : 8);
+    const int esx = g.pixel_major ? 1 : (d->s_in_x ? d->s_in_x : d->s_in);
+    const int kc = g_mode == 0 ? 64 : (g_mode == 1 ? 32 : (g_mode == 3 ? 16 : 8));
     CUtensorMap tmG, tmN;
     {
       const cuuint64_t dim[4] = {static_cast<cuuint64_t>(d->Cg), static_cast<cuuint64_t>(d->IW),
@@ -2319,14 +2375,30 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
       const cuuint64_t rb = d->g_row_stride ? static_cast<cuuint64_t>(d->g_row_stride) * 2 : pb * d->IW;
       const cuuint64_t ib = d->g_img_stride ? static_cast<cuuint64_t>(d->g_img_stride) * 2 : rb * d->IH;
       const cuuint64_t str[3] = {pb, rb, ib};
-      const cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * es),
+      const cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(g.pixel_major ? 1 : bw * esx),
                                  static_cast<cuuint32_t>(g.pixel_major ? 1 : bh * es), static_cast<cuuint32_t>(bn)};
-      const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es), 1};
+      const cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(esx), static_cast<cuuint32_t>(es), 1};
       const CUtensorMapSwizzle sw = g_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                 : (g_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
-      const CUresult r = enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->G), dim, str, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r;
+      if (g_mode == 3) {
+        // raw rows: (elements of a padded row, 1, rows, images); box = 256 elements x bh rows (see the kernel header)
+        MMDYN_REQUIRE(!g.pixel_major && bw == 32 && bh == 2 && bn == 1 && d->g_pix_stride == 8 && esx == 1 &&
+                          d->g_row_stride >= (d->IW + 1) * 8 && d->g_row_stride >= 264,
+                      "wgrad: Cg = 16 is the 4-pixel window form (OXv = 32, pixel pairs of 8 elements, s_in_x = 1)");
+        for (int t_ = 0; t_ < d->ntaps; ++t_) MMDYN_REQUIRE(d->tap_dx[t_] == 0, "wgrad: Cg = 16 takes row taps only");
+        const cuuint64_t rdim[4] = {static_cast<cuuint64_t>(d->g_row_stride), 1, static_cast<cuuint64_t>(d->IH),
+                                    static_cast<cuuint64_t>(d->n_img)};
+        const cuuint64_t rstr[3] = {rb, rb, ib};
+        const cuuint32_t rbox[4] = {256, 1, static_cast<cuuint32_t>(bh * es), 1};
+        const cuuint32_t res[4] = {1, 1, static_cast<cuuint32_t>(es), 1};
+        r = enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->G), rdim, rstr, rbox, res,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      } else {
+        r = enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->G), dim, str, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
       if (r != CUDA_SUCCESS) {
         set_last_error("wgrad: cuTensorMapEncodeTiled(G) failed with CUresult %d", static_cast<int>(r));
         return MMDYN_ERR_CUDA;

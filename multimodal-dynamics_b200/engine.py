@@ -537,10 +537,11 @@ class EncoderExec(_NetBase):
         d1 = alloc(key + ".d1", (B, 32, 32, 32), F16)
         _ig(self.c2, "dgrad", d2, d1, B)
         ops.bn_swish_bwd_reduce(r["raw1"], None, None, d1, None, 1, B * 1024, 32)
-        # conv1 weight gradient on the tensor cores: x -> NHWC fp16 with 8 channels per pixel
-        x8 = alloc(key + ".x8", (B, 64, 64, 8), F16)
-        ops.logit_grad_pack(r["x"], x8, 1.0, B, 64, 64)
-        dW1 = gp.view("conv1") if gp is not None else alloc(key + ".dW_c1", (32, 128), F32, zero=True)
+        # conv1 weight gradient on the tensor cores: x -> NHWC fp16 with 4 channels per pixel and a zero border
+        # (written once: the workspace hands out zeroed buffers and the packer never touches the border)
+        x8 = alloc(key + ".x4p", (B, 66, 66, plan.LOGIT_CP), F16, zero=not isinstance(alloc, Workspace))
+        ops.logit_grad_pack(r["x"], x8, 1.0, B, 64, 64, 1, cp=plan.LOGIT_CP)
+        dW1 = gp.view("conv1") if gp is not None else alloc(key + ".dW_c1", tuple(self.c1_idx.shape), F32, zero=True)
         with _on_side(gp):
             ops.wgrad(self.c1_wg, x8, d1, dW1, B, scale=unscale, row_splits=plan.choose_row_splits(self.c1_wg, B),
                       tag="conv1.wgrad", macs_per_img=1024 * 32 * 48)
@@ -569,7 +570,7 @@ class DecoderExec(_NetBase):
     def forward(self, zh, G, B, alloc, key, track=True, fused_loss=None, cond=None):
         """zh: (G*B, 256) fp16 latent rows, group-major.  Returns record with fp32 NCHW logits.
 
-        fused_loss: dict(target (B,3,64,64), mask|None, dlogits (G*B,66,66,8)|None, loss (fp32 vector),
+        fused_loss: dict(target (B,3,64,64), mask|None, dlogits (G*B,66,66,4)|None, loss (fp32 vector),
         slots [loss index per group or -1], gscale, logit_groups (g_lo, g_hi)): the BCE reconstruction
         loss and its logit gradient are computed in the epilogue of the logits layer (problems.py:409-413,
         431-449); logits are then only written for the groups in logit_groups.
@@ -636,7 +637,7 @@ class DecoderExec(_NetBase):
     fuse_stats = os.environ.get("MMDYN_NO_FUSED_STATS") is None  # BatchNorm sums in the deconv2/3 epilogues
 
     def backward(self, r, dl8, alloc, key, unscale, gp=None):
-        """dl8: (G*B, 66, 66, 8) fp16 logit gradients with a one-pixel ZERO border (3 channels used, times grad_scale).
+        """dl8: (G*B, 66, 66, plan.LOGIT_CP = 4) fp16 logit gradients with a one-pixel ZERO border (3 channels used, times grad_scale).
         Returns dz (G*B, 256) fp32 (times grad_scale)."""
         arena, G, B = self.arena, r["G"], r["B"]
         R = G * B
@@ -1199,7 +1200,7 @@ class StepEngine:
                 dex = ex["dec"][self.mods[m][1]]
                 # one-pixel zero border (zeroed at allocation, never written): deconv4's backward reads
                 # the 4 x-taps of a pixel as one 64-byte window (plan.deconv_out_plan)
-                dl8[m] = ws("dl8_" + m, (G * B, 66, 66, 8), F16, zero=self.exact) if need_grad else None
+                dl8[m] = ws("dl8_" + m, (G * B, 66, 66, plan.LOGIT_CP), F16, zero=self.exact) if need_grad else None
 
                 slots = [slot[(m, i)] if i in enc_passes[m] else -1 for i in dec_groups[m]]
                 if self.fuse_bce:

@@ -36,6 +36,7 @@ class IgemmDesc(C.Structure):
         ("bce_gscale", C.c_float), ("bce_rows_per_group", C.c_int32), ("bce_slot", C.c_int32 * MAX_GROUPS),
         ("logit_row_lo", C.c_int32), ("logit_row_hi", C.c_int32),
         ("patch_mode", C.c_int32), ("bn_rows_per_group", C.c_int32), ("bn_sums", C.c_void_p),
+        ("s_in_x", C.c_int32),
     ]
 
 
@@ -46,7 +47,7 @@ class WgradDesc(C.Structure):
         ("g_pix_stride", C.c_int32), ("Cg", C.c_int32), ("s_in", C.c_int32), ("ntaps", C.c_int32),
         ("tap_dy", C.c_int8 * MAX_TAPS), ("tap_dx", C.c_int8 * MAX_TAPS),
         ("Cn", C.c_int32), ("nat_stride", C.c_int32), ("ldw", C.c_int32), ("row_splits", C.c_int32),
-        ("scale", C.c_float), ("g_row_stride", C.c_int32), ("g_img_stride", C.c_int32),
+        ("scale", C.c_float), ("g_row_stride", C.c_int32), ("g_img_stride", C.c_int32), ("s_in_x", C.c_int32),
     ]
 
 
@@ -110,7 +111,7 @@ SIGNATURES = {
     "mmdyn_gather_add_f32": ([_P, _P, _P, _LL, _P], _I),
     "mmdyn_f32_to_f16": ([_P, _P, _LL, _F, _P], _I),
     "mmdyn_scale_f32": ([_P, _LL, _F, _P], _I),
-    "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _I, _I, _P], _I),
+    "mmdyn_logit_grad_pack": ([_P, _P, _F, _I, _I, _I, _I, _I, _P], _I),
     "mmdyn_adam_flat": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _F, _P], _I),
     "mmdyn_adam_flat_devstep": ([_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P, _F, _P], _I),
     "mmdyn_sgd_flat": ([_P, _P, _P, _LL, _F, _F, _F, _I, _F, _P], _I),

@@ -145,6 +145,7 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     d.OH, d.OW, d.s_out = geom.OH, geom.OW, geom.s_out
     d.ldc = geom.ldc if ldc is None else ldc
     d.a_row_stride, d.a_img_stride = geom.a_row_stride, geom.a_img_stride
+    d.s_in_x = int(getattr(geom, "s_in_x", 0))
     d.patch_mode = int(getattr(geom, "patch", 0))
     if d.patch_mode:
         _PATCH_TAGS.add(tag)
@@ -186,6 +187,7 @@ def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride
     d.ldw = geom.K if ldw is None else ldw
     d.row_splits, d.scale = row_splits, scale
     d.g_row_stride, d.g_img_stride = geom.g_row_stride, geom.g_img_stride
+    d.s_in_x = int(getattr(geom, "s_in_x", 0))
 
     def alg():
         macs = (macs_per_img if macs_per_img is not None else geom.P * geom.Cn * geom.K) * n_img
@@ -310,8 +312,8 @@ def poe_bwd_multi(passes, use_prior, ld, kl_coef, ld_out, accumulate, B, D):
 
 
 def bce_logits(logits, target, mask, loss_sum, dlogits, gscale, n, H, W, pad=0):
-    """pad: border (pixels) of the NHWC8 gradient images, see include/mmdyn_b200.h"""
-    with _Timed("bce_logits", lambda: (0.0, n * H * W * (3 * 8.0 + (16.0 if dlogits is not None else 0.0)))):
+    """pad: border (pixels) of the NHWC4 gradient images, see include/mmdyn_b200.h"""
+    with _Timed("bce_logits", lambda: (0.0, n * H * W * (3 * 8.0 + (8.0 if dlogits is not None else 0.0)))):
         check(_L().mmdyn_bce_logits(_ptr(logits), _ptr(target), _ptr(mask), _ptr(loss_sum), _ptr(dlogits), gscale, n,
                                     H, W, pad, _stream()), "bce_logits")
 
@@ -386,9 +388,11 @@ def scale_f32(x, n, s):
         check(_L().mmdyn_scale_f32(_ptr(x), n, s, _stream()), "scale_f32")
 
 
-def logit_grad_pack(dl, out, scale, n, H, W, pad=0):
+def logit_grad_pack(dl, out, scale, n, H, W, pad=0, cp=8):
+    """cp: channels per pixel of `out` (3 used): 4 = the layout of the logit gradients (plan.LOGIT_CP), 8 = the repacked input
+    image of the first conv's weight gradient"""
     with _Timed("logit_grad_pack", None):
-        check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, H, W, pad, _stream()), "logit_grad_pack")
+        check(_L().mmdyn_logit_grad_pack(_ptr(dl), _ptr(out), scale, n, H, W, pad, cp, _stream()), "logit_grad_pack")
 
 
 def adam_flat(p, g, m, v, n, lr, b1, b2, eps, wd, step, gscale=1.0):

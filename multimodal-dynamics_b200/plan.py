@@ -28,6 +28,7 @@ MERGE_PHASES = os.environ.get("MMDYN_MERGE_PHASES", "1") != "0"
 # merged 3x3-tap layers on the patch-reuse kernel (one activation box per filter column, live weight blocks
 # only); MMDYN_NO_PATCH=1 keeps them on the generic one-box-per-tap kernel (A/B measurements)
 USE_PATCH = os.environ.get("MMDYN_NO_PATCH") is None
+LOGIT_CP = 4  # channels per pixel of the stored logit gradients (3 used): fp16 NHWC4 with a one-pixel zero border
 PATCH_SPLIT = os.environ.get("MMDYN_NO_PATCH_SPLIT") is None  # deconv2.fwd / conv3.dgrad on the phase-split patch kernel
 
 
@@ -53,6 +54,7 @@ class GemmGeom:
     a_pix_stride: Optional[int] = None
     a_row_stride: int = 0     # 0 = dense; see include/mmdyn_b200.h (overlapping-window operands)
     a_img_stride: int = 0
+    s_in_x: int = 0           # input stride along x when it differs from s_in (0 = s_in)
     patch: int = 0            # 1: merged 3x3-tap layer -> shared-memory patch reuse kernel (mmdyn_igemm patch_mode)
 
     @property
@@ -94,6 +96,7 @@ class WgradGeom:
     nat_stride: Optional[int] = None
     g_row_stride: int = 0
     g_img_stride: int = 0
+    s_in_x: int = 0
 
     @property
     def ntaps(self):
@@ -108,7 +111,7 @@ class WgradGeom:
             self.g_pix_stride = self.Cg
         if self.nat_stride is None:
             self.nat_stride = self.Cn
-        assert self.K % 128 == 0, (self.ntaps, self.Cg)
+        assert self.K % 128 == 0 or (self.Cg == 16 and self.ntaps == 4), (self.ntaps, self.Cg)
 
 
 @dataclass
@@ -286,10 +289,10 @@ def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
 
     Forward: the 4 sub-pixel phases are merged into the N dimension (n = (ph*2+pw)*3 + co, 12 of
     16 used) over the union of their taps (3x3 + one zero-weight dummy tap so K = 10*32 = 320);
-    the epilogue writes fp32 NCHW planes.  Backward works on dlogits stored NHWC with 8 channels
-    per pixel (3 used)."""
+    the epilogue writes fp32 NCHW planes.  Backward works on dlogits stored NHWC with LOGIT_CP = 4
+    channels per pixel (3 used)."""
     Ho = 2 * H
-    CP = 8  # padded gradient channels
+    CP = LOGIT_CP  # padded gradient channels
 
     def widx(ci, co, kh, kw):
         return w_off + ((ci * Cout + co) * 4 + kh) * 4 + kw
@@ -307,22 +310,24 @@ def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):
                 for t_, (a, b) in enumerate(taps[:9]):
                     if a in kof[ph] and b in kof[pw]:
                         idx_fwd[n, t_ * Cin:(t_ + 1) * Cin] = widx(np.arange(Cin), co, kof[ph][a], kof[pw][b])
-    # Backward operand = dlogits, NHWC with CP = 8 channels per pixel, stored with a one-pixel zero
-    # border: [img][Ho+2][Ho+2][8].  The 4 x-taps of an output pixel (padded columns 2x .. 2x+3) are
-    # 64 contiguous bytes, so they are read as ONE tap of a "window pixel" with 4*CP = 32 channels whose
-    # pitch is a single physical pixel (a_pix_stride = 8 < Cin = 32): 4 operand boxes of 64-byte rows per
-    # tile instead of 16 boxes of 16-byte rows, and no out-of-image taps.  K order (kh, kw, c) is unchanged.
-    Hp = Ho + 2  # window pixel xw covers padded columns xw .. xw+3, so there are Hp - 3 = Ho - 1 of them per row
+    # Backward operand = dlogits, NHWC with CP = 4 channels per pixel (8 bytes: 1.33x the 3 algorithmic
+    # channels), stored with a one-pixel zero border: [img][Ho+2][Ho+2][4].  The 4 x-taps of an output
+    # pixel (padded columns 2x .. 2x+3) are 32 contiguous bytes, so they are read as ONE tap of a "window
+    # pixel" with 4*CP = 16 channels.  TMA strides are multiples of 16 bytes, so the x dimension counts
+    # pixel PAIRS (a_pix_stride = 2*CP = 8 elements < Cin = 16): window x covers pairs x, x+1 and advances one
+    # pair per output pixel (s_in_x = 1) while rows advance two per output row (s_in = 2).  4 operand boxes
+    # of 32-byte rows (K = 64, one k-block) per tile, and no out-of-image taps.  K order (kh, kw, c).
+    Hp = Ho + 2
     wdy, wdx = [0, 1, 2, 3], [0, 0, 0, 0]
-    dg = GemmGeom(P=H * H, OXv=H, IH=Hp, IW=Ho - 1, Cin=4 * CP, s_in=2, tap_dy=[wdy], tap_dx=[wdx], N=Cin,
-                  OH=H, OW=H, s_out=1, off_y=[0], off_x=[0], ldc=Cin, a_pix_stride=CP, a_row_stride=Hp * CP,
+    dg = GemmGeom(P=H * H, OXv=H, IH=Hp, IW=H, Cin=4 * CP, s_in=2, s_in_x=1, tap_dy=[wdy], tap_dx=[wdx], N=Cin,
+                  OH=H, OW=H, s_out=1, off_y=[0], off_x=[0], ldc=Cin, a_pix_stride=2 * CP, a_row_stride=Hp * CP,
                   a_img_stride=Hp * Hp * CP)
     idx_dg = np.full((Cin, 16 * CP), -1, np.int32)
     for t_ in range(16):
         for co in range(Cout):
             idx_dg[:, t_ * CP + co] = widx(np.arange(Cin), co, t_ // 4, t_ % 4)
-    wg = WgradGeom(P=H * H, OXv=H, IH=Hp, IW=Ho - 1, Cg=4 * CP, s_in=2, tap_dy=wdy, tap_dx=wdx, Cn=Cin,
-                   g_pix_stride=CP, g_row_stride=Hp * CP, g_img_stride=Hp * Hp * CP)
+    wg = WgradGeom(P=H * H, OXv=H, IH=Hp, IW=H, Cg=4 * CP, s_in=2, s_in_x=1, tap_dy=wdy, tap_dx=wdx, Cn=Cin,
+                   g_pix_stride=2 * CP, g_row_stride=Hp * CP, g_img_stride=Hp * Hp * CP)
     return LayerPlan(name, "deconv_out", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
 
 
@@ -388,14 +393,16 @@ def conv1_plan(name, w_off):
 
 def conv1_wgrad_plan(w_off):
     """Weight gradient of the first conv through the generic tensor-core wgrad kernel: the fp32 NCHW
-    input is repacked once per backward into NHWC fp16 with 8 channels per pixel (3 used), so
-    dW[co][t*8 + c] = sum_pix dRaw[pix][co] * x8[gather(pix, t)][c] with the 16 taps of k4/s2/p1."""
-    dy, dx = _conv_taps(4, 1)
-    wg = WgradGeom(P=32 * 32, OXv=32, IH=64, IW=64, Cg=8, s_in=2, tap_dy=dy, tap_dx=dx, Cn=32)
-    idx = np.full((32, 16 * 8), -1, np.int32)
+    input is repacked once per backward into NHWC fp16 with LOGIT_CP = 4 channels per pixel (3 used) and a
+    one-pixel zero border, so dW[co][(kh*4 + kw)*4 + c] = sum_pix dRaw[pix][co] * xp[2*oy + kh][2*ox + kw][c]:
+    the same 4-pixel-window operand as the logits layer's weight gradient (deconv_out_plan), K = 64."""
+    CP, Hp = LOGIT_CP, 66
+    wg = WgradGeom(P=32 * 32, OXv=32, IH=Hp, IW=32, Cg=4 * CP, s_in=2, s_in_x=1, tap_dy=[0, 1, 2, 3],
+                   tap_dx=[0, 0, 0, 0], Cn=32, g_pix_stride=2 * CP, g_row_stride=Hp * CP, g_img_stride=Hp * Hp * CP)
+    idx = np.full((32, 16 * CP), -1, np.int32)
     for t_ in range(16):
         for c in range(3):
-            idx[:, t_ * 8 + c] = w_off + (np.arange(32) * 3 + c) * 16 + t_
+            idx[:, t_ * CP + c] = w_off + (np.arange(32) * 3 + c) * 16 + t_
     return wg, idx
 
 
@@ -419,7 +426,7 @@ def choose_ksplit(geom: GemmGeom, n_img: int, sm_count: int = 148):
 
 def choose_row_splits(geom: WgradGeom, n_img: int, sm_count: int = 148):
     cn_tile = min(geom.Cn, 256)
-    base = (geom.K // 128) * (geom.Cn // cn_tile)
+    base = ((geom.K + 127) // 128) * (geom.Cn // cn_tile)
     steps = (n_img * geom.P + 63) // 64
     want = (2 * sm_count + base - 1) // base
     return int(max(1, min(steps, want)))

@@ -16,7 +16,7 @@ reference features outside this path and raise NotImplementedError.
 import torch
 import torch.nn as nn
 
-from mmdyn_b200 import engine, noise, ops
+from mmdyn_b200 import engine, noise, ops, plan
 from mmdyn_b200.pytorch import config
 
 F16, F32 = torch.float16, torch.float32
@@ -143,8 +143,8 @@ class _DecoderFn(torch.autograd.Function):
         ex.arena.attach_grads()
         B = rec["B"]
         gs = float(B)
-        dl8 = torch.zeros(B, 66, 66, 8, dtype=F16, device=dlogits.device)  # zero border: engine.DecoderExec.backward
-        ops.logit_grad_pack(dlogits.contiguous().float(), dl8, gs, B, 64, 64, 1)
+        dl8 = torch.zeros(B, 66, 66, plan.LOGIT_CP, dtype=F16, device=dlogits.device)  # zero border: engine.DecoderExec.backward
+        ops.logit_grad_pack(dlogits.contiguous().float(), dl8, gs, B, 64, 64, 1, cp=plan.LOGIT_CP)
         dz = ex.backward(rec, dl8, engine.FreshAlloc(dlogits.device), "dec", 1.0 / gs)
         ops.scale_f32(dz, dz.numel(), 1.0 / gs)
         return dz, None, None, None, None

@@ -43,7 +43,7 @@ def igemm(geom, A, Wp, n_img, bias=None):
                 acc = np.zeros((n_img, g.N))
                 for t in range(g.ntaps):
                     iy = yv * g.s_in + g.tap_dy[ph][t]
-                    ix = xv * g.s_in + g.tap_dx[ph][t]
+                    ix = xv * (g.s_in_x or g.s_in) + g.tap_dx[ph][t]
                     if 0 <= iy < g.IH and 0 <= ix < g.IW:
                         acc += A[:, iy, ix, :g.Cin] @ W[:, t * g.Cin:(t + 1) * g.Cin].T
                 if bias is not None:
@@ -78,7 +78,7 @@ def wgrad(geom, G, Nat, n_img):
             nat = Nat[:, yv * g.OXv + xv, :g.Cn]
             for t in range(g.ntaps):
                 iy = yv * g.s_in + g.tap_dy[t]
-                ix = xv * g.s_in + g.tap_dx[t]
+                ix = xv * (g.s_in_x or g.s_in) + g.tap_dx[t]
                 if 0 <= iy < g.IH and 0 <= ix < g.IW:
                     dW[:, t * g.Cg:(t + 1) * g.Cg] += nat.T @ G[:, iy, ix, :g.Cg]
     return dW

@@ -152,7 +152,7 @@ def test_deconv4_out():
     torch.manual_seed(7)
     w = torch.randn(32, 3, 4, 4) * 0.1
     x = torch.randn(3, 32, 32, 32)
-    check_conv_layer(plan.deconv_out_plan("d4", 0, 32, 3, 32), w, x, 2, 1, True, grad_pad=8, border=1)
+    check_conv_layer(plan.deconv_out_plan("d4", 0, 32, 3, 32), w, x, 2, 1, True, grad_pad=plan.LOGIT_CP, border=1)
 
 
 @pytest.mark.parametrize("use_mask", [False, True])
@@ -178,7 +178,7 @@ def test_deconv4_fused_bce_epilogue(use_mask):
     (loss_ref[0] + loss_ref[2]).backward(retain_graph=True)
     dy_ref = torch.autograd.grad(loss_ref[0] + loss_ref[2], y, retain_graph=True)[0]
     logits = torch.full((6, 3, 64, 64), -77.0, device=DEV)
-    dl = torch.full((6, 66, 66, 8), 7.0, dtype=torch.float16, device=DEV)
+    dl = torch.full((6, 66, 66, plan.LOGIT_CP), 7.0, dtype=torch.float16, device=DEV)
     loss = torch.zeros(4, device=DEV)
     bce = dict(target=t.to(DEV), mask=m.to(DEV) if use_mask else None, dlogits=dl, loss=loss, gscale=2.0,
                rows_per_group=2, slots=[0, -1, 2], logit_rows=(2, 4))
@@ -426,7 +426,7 @@ def test_bce_logits_and_mse(use_mask):
     loss.backward()
     for pad in (0, 1):
         ls = torch.zeros(1, device=DEV)
-        dl = torch.full((n, 64 + 2 * pad, 64 + 2 * pad, 8), 7.0, dtype=torch.float16, device=DEV)
+        dl = torch.full((n, 64 + 2 * pad, 64 + 2 * pad, plan.LOGIT_CP), 7.0, dtype=torch.float16, device=DEV)
         ops.bce_logits(x.to(DEV), t.to(DEV), m.to(DEV) if use_mask else None, ls, dl, 2.0, n, 64, 64, pad)
         torch.cuda.synchronize()
         assert abs(ls.item() - loss.item()) / loss.item() < 1e-5
@@ -439,10 +439,15 @@ def test_bce_logits_and_mse(use_mask):
             assert (bord == 7.0).all()
         # the same gradient through the stand-alone packer (loss computed outside the library)
         dl2 = torch.full_like(dl, 7.0)
-        ops.logit_grad_pack(xr.grad.float().to(DEV), dl2, 2.0, n, 64, 64, pad)
+        ops.logit_grad_pack(xr.grad.float().to(DEV), dl2, 2.0, n, 64, 64, pad, cp=plan.LOGIT_CP)
         torch.cuda.synchronize()
         assert rel_err(dl2[:, pad:pad + 64, pad:pad + 64, :3].permute(0, 3, 1, 2), 2.0 * xr.grad) < 1e-3
         assert (dl2[:, :pad] == 7.0).all() and (dl2[:, :, :pad] == 7.0).all()
+        dl3 = torch.full((n, 64 + 2 * pad, 64 + 2 * pad, 8), 7.0, dtype=torch.float16, device=DEV)  # 8-channel form
+        ops.logit_grad_pack(xr.grad.float().to(DEV), dl3, 2.0, n, 64, 64, pad, cp=8)
+        torch.cuda.synchronize()
+        assert rel_err(dl3[:, pad:pad + 64, pad:pad + 64, :3].permute(0, 3, 1, 2), 2.0 * xr.grad) < 1e-3
+        assert dl3[:, pad:pad + 64, pad:pad + 64, 3:].abs().max().item() == 0
     # pose MSE * multiplier
     r, tt = torch.randn(n, 7), torch.rand(n, 7)
     rr = r.double().requires_grad_(True)

@@ -89,7 +89,22 @@ def test_deconv_out():
     w = torch.randn(32, 3, 4, 4)
     x = torch.randn(2, 32, 8, 8)
     y = F.conv_transpose2d(x, w, stride=2, padding=1)
-    check_layer(plan.deconv_out_plan("d4", 0, 32, 3, 8), w, x, y, torch.randn_like(y), 2, 1, True, cin_pad=8, border=1)
+    check_layer(plan.deconv_out_plan("d4", 0, 32, 3, 8), w, x, y, torch.randn_like(y), 2, 1, True, cin_pad=plan.LOGIT_CP, border=1)
+
+
+def test_conv1_wgrad_window_form():
+    """vae.py:198 Conv2d(3, 32, 4, 2, 1): the weight gradient read through 4-pixel windows of the padded NHWC4 input"""
+    w = torch.randn(32, 3, 4, 4).requires_grad_(True)
+    x = torch.randn(2, 3, 64, 64)
+    y = F.conv2d(x, w, stride=2, padding=1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wg, idx = plan.conv1_wgrad_plan(0)
+    xp = np.zeros((2, 66, 66, plan.LOGIT_CP))
+    xp[:, 1:65, 1:65, :3] = nhwc(x)
+    dWp = emul.wgrad(wg, xp, nhwc(dy).reshape(2, -1, 32), 2)
+    dW = emul.unpack_add(dWp, idx, w.numel())
+    np.testing.assert_allclose(dW, w.grad.reshape(-1).numpy(), atol=1e-8)
 
 
 def test_linear_permuted_and_concat():

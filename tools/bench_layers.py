@@ -43,7 +43,7 @@ def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, st
     if bce:  # the logits layer as the step runs it: BCE loss + logit gradient fused into the epilogue, 4 groups
         B = n_img // 4
         kw["bce"] = dict(target=torch.rand(B, 3, 64, 64, device=DEV), mask=None, loss=torch.zeros(64, device=DEV), gscale=1.0,
-                         dlogits=torch.zeros(n_img, 66, 66, 8, device=DEV, dtype=torch.float16), rows_per_group=B,
+                         dlogits=torch.zeros(n_img, 66, 66, 4, device=DEV, dtype=torch.float16), rows_per_group=B,
                          slots=[8, 9, 10, 11], logit_rows=(0, B))
     ms = timeit(lambda: ops.igemm(geom, A, W, out, n_img, **kw))
     rows = n_img * geom.P * geom.n_phases
@@ -83,11 +83,11 @@ CASES = {
     "deconv1.wgrad": lambda R: run_wgrad("deconv1.wgrad", plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), R, (8, 8, 128), (5, 5, 256)),
     "deconv2.wgrad": lambda R: run_wgrad("deconv2.wgrad", plan.deconv_s2_plan("d2", 0, 128, 64, 8), R, (16, 16, 64), (8, 8, 128)),
     "deconv3.wgrad": lambda R: run_wgrad("deconv3.wgrad", plan.deconv_s2_plan("d3", 0, 64, 32, 16), R, (32, 32, 32), (16, 16, 64)),
-    "deconv4.wgrad": lambda R: run_wgrad("deconv4.wgrad", plan.deconv_out_plan("d4", 0), R, (66, 66, 8), (32, 32, 32)),
+    "deconv4.wgrad": lambda R: run_wgrad("deconv4.wgrad", plan.deconv_out_plan("d4", 0), R, (66, 66, 4), (32, 32, 32)),
     "conv2.wgrad": lambda R: run_wgrad("conv2.wgrad", plan.conv_s2_plan("c2", 0, 32, 64, 32), R // 4, (32, 32, 32), (16, 16, 64)),
     "conv3.wgrad": lambda R: run_wgrad("conv3.wgrad", plan.conv_s2_plan("c3", 0, 64, 128, 16), R // 4, (16, 16, 64), (8, 8, 128)),
     "conv4.wgrad": lambda R: run_wgrad("conv4.wgrad", plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), R // 4, (8, 8, 128), (5, 5, 256)),
-    "deconv4.dgrad": lambda R: run("deconv4.dgrad", plan.deconv_out_plan("d4", 0), "dgrad", R, (66, 66, 8), (32, 32, 32)),
+    "deconv4.dgrad": lambda R: run("deconv4.dgrad", plan.deconv_out_plan("d4", 0), "dgrad", R, (66, 66, 4), (32, 32, 32)),
     "deconv2.dgrad": lambda R: run("deconv2.dgrad", plan.deconv_s2_plan("d2", 0, 128, 64, 8), "dgrad", R, (16, 16, 64), (8, 8, 128)),
 }
 
