@@ -58,6 +58,20 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 32 contiguous bytes of one thread: ONE 256-bit store (STG.256, sm_100) when the address allows it — a full 32-byte
+// sector per request instead of two half-sector writes (the epilogue stores of the N <= 128 layers were the
+// longest stage of their tiles, profiles/r2b_patch_ablation.md)
+__device__ __forceinline__ void st_global_32B(void* p, const uint4& u0, const uint4& u1) {
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(u0.x), "r"(u0.y), "r"(u0.z),
+                 "r"(u0.w), "r"(u1.x), "r"(u1.y), "r"(u1.z), "r"(u1.w)
+                 : "memory");
+  } else {
+    reinterpret_cast<uint4*>(p)[0] = u0;
+    reinterpret_cast<uint4*>(p)[1] = u1;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // igemm: forward / dgrad form — persistent, warp-specialised
 //   warps 0-3  A producers (im2col gather, cp.async)      warp 4  MMA issuer (+ TMEM owner)
@@ -318,17 +332,14 @@ igemm_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__
           // merged sub-pixel phases, NHWC fp16: this 16-column chunk belongs to one phase
           const int n = n_base + c0, phs = n / d.ldc, co0 = n - phs * d.ldc;
           __half* o = reinterpret_cast<__half*>(d.out) + out_off + ((phs >> 1) * d.OW + (phs & 1)) * d.ldc + co0;
-          reinterpret_cast<uint4*>(o)[0] =
-              make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
-          reinterpret_cast<uint4*>(o)[1] = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]),
-                                                      pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+          st_global_32B(o, make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])),
+                        make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15])));
         } else if (d.out_mode == 0) {
           __half* o = reinterpret_cast<__half*>(d.out) + out_off + n_base + c0;
           uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
           uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
                                 pack_h2(f[14], f[15]));
-          reinterpret_cast<uint4*>(o)[0] = u0;
-          reinterpret_cast<uint4*>(o)[1] = u1;
+          st_global_32B(o, u0, u1);
         } else if (d.out_mode == 1) {
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + out_off + n_base + c0);
 #pragma unroll
@@ -683,17 +694,14 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
           // merged sub-pixel phases, NHWC fp16: this 16-column chunk belongs to one phase
           const int n = n_base + c0, phs = n / d.ldc, co0 = n - phs * d.ldc;
           __half* o = reinterpret_cast<__half*>(d.out) + out_off + ((phs >> 1) * d.OW + (phs & 1)) * d.ldc + co0;
-          reinterpret_cast<uint4*>(o)[0] =
-              make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
-          reinterpret_cast<uint4*>(o)[1] = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]),
-                                                      pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+          st_global_32B(o, make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])),
+                        make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15])));
         } else if (d.out_mode == 0) {
           __half* o = reinterpret_cast<__half*>(d.out) + out_off + n_base + c0;
           uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
           uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
                                 pack_h2(f[14], f[15]));
-          reinterpret_cast<uint4*>(o)[0] = u0;
-          reinterpret_cast<uint4*>(o)[1] = u1;
+          st_global_32B(o, u0, u1);
         } else if (d.out_mode == 1) {
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + out_off + n_base + c0);
 #pragma unroll
@@ -885,7 +893,14 @@ struct PatchGeom {
   int8_t run_q0[9][2], run_len[9][2];
   int32_t run_off[9][2];    // byte offset of the run's first weight block inside the resident weight region
   uint8_t qmask[9];
+  int dbg;                  // ablation switches, honoured only by builds with -DMMDYN_PATCH_DBG (env MMDYN_PATCH_DBG):
+                            // 1 = epilogue body skipped, 2 = no MMAs, 4 = no activation loads, 8 = no global stores
 };
+#ifdef MMDYN_PATCH_DBG
+#define PATCH_DBG(g, bit) (((g).dbg & (bit)) != 0)
+#else
+#define PATCH_DBG(g, bit) false
+#endif
 
 template <int BLOCK_N, int CIN_MODE, int SA, int W_KB>
 struct PatchCfg {
@@ -909,7 +924,8 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base, a_ring = smem_base + C::W_BYTES;
   __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full;
-  __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
+  constexpr int NACC = EG < 2 ? 2 : EG;  // accumulator stages in TMEM: epilogue group e drains stage e
+  __shared__ __align__(8) uint64_t tfull_bar[NACC], tempty_bar[NACC];
   __shared__ uint32_t tmem_base_s;
   __shared__ float stat_all[EG][2 * 64];  // per epilogue group: BatchNorm partial sums {sum x, sum x^2} per channel
 
@@ -919,14 +935,14 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
     mbar_init(smem_u32(&w_full), 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 128); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 128); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
   for (int i = threadIdx.x; i < EG * 128; i += blockDim.x) (&stat_all[0][0])[i] = 0.0f;
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_s), 2 * C::TMEM_COLS);
+    tmem_alloc(smem_u32(&tmem_base_s), NACC * C::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -986,8 +1002,12 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
             const int sa = ia % SA;
             mbar_wait(smem_u32(&a_empty[sa]), ((ia / SA) & 1) ^ 1);
             const uint32_t abar = smem_u32(&a_full[sa]);
-            mbar_arrive_expect_tx(abar, static_cast<uint32_t>(g.a_rows * RB));
-            tma_load_4d(a_ring + sa * C::A_SLOT, &tmA, abar, cb << 6, dx, img0, y0 - 1);  // dims (c, x, img, y)
+            if (PATCH_DBG(g, 4)) {
+              mbar_arrive(abar);
+            } else {
+              mbar_arrive_expect_tx(abar, static_cast<uint32_t>(g.a_rows * RB));
+              tma_load_4d(a_ring + sa * C::A_SLOT, &tmA, abar, cb << 6, dx, img0, y0 - 1);  // dims (c, x, img, y)
+            }
             ++ia;
           }
         }
@@ -1007,8 +1027,8 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
       const uint32_t sh0 = 0, sh1 = dy_shift >> 4, sh2 = (2 * dy_shift) >> 4;  // dy = -1, 0, +1 in 16-byte units
       int ia = 0, tl = 0;
       for (int tile = tile_first; tile < g.total_tiles; tile += tile_stride, ++tl) {
-        const int acc = tl & 1;
-        mbar_wait(smem_u32(&tempty_bar[acc]), ((tl >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        const int acc = tl % NACC;
+        mbar_wait(smem_u32(&tempty_bar[acc]), ((tl / NACC) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS;
 #pragma unroll
@@ -1039,8 +1059,7 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
             const uint32_t w16 = (w_base + cb * g.w_bytes_cb) >> 4;
 #pragma unroll
             for (int dyi = 0; dyi < 3; ++dyi) {
-              constexpr int dummy = 0;
-              (void)dummy;
+              if (PATCH_DBG(g, 2)) break;
               const TapSched ts = tap_sched(NQ4, dxi * 3 + dyi);
               const uint32_t a_tap = a16 + (ts.dy < 0 ? sh0 : (ts.dy == 0 ? sh1 : sh2));
 #pragma unroll
@@ -1131,11 +1150,13 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
           }
         }
       }
-      const int acc = tl & 1;
-      mbar_wait(smem_u32(&tfull_bar[acc]), (tl >> 1) & 1);
+      const int acc = tl % NACC;
+      mbar_wait(smem_u32(&tfull_bar[acc]), (tl / NACC) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * C::TMEM_COLS + (static_cast<uint32_t>(q4 * 32) << 16);
-      if constexpr (BLOCK_N == 16) {
+      if (PATCH_DBG(g, 1)) out_off = -2;
+      if (out_off == -2) {
+      } else if constexpr (BLOCK_N == 16) {
         uint32_t v[16];
         tmem_ld_x16(tmem_d, v);
         tmem_ld_wait(v);
@@ -1210,8 +1231,9 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
             const uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
             const uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
                                         pack_h2(f[14], f[15]));
-            reinterpret_cast<uint4*>(o)[0] = u0;
-            reinterpret_cast<uint4*>(o)[1] = u1;
+            if (!PATCH_DBG(g, 8)) {
+              st_global_32B(o, u0, u1);
+            }
             if (want_stats) {
               // statistics of the values the BatchNorm kernels will read: the fp16-ROUNDED outputs
               const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -1278,7 +1300,7 @@ igemm_patch_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * C::TMEM_COLS);
+    tmem_dealloc(tmem_base, NACC * C::TMEM_COLS);
   }
 }
 
@@ -1883,7 +1905,8 @@ int launch_patch(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtens
     configured = true;
   }
   int occ = (228 * 1024) / (C::SMEM_BYTES + 1024 + 1024);
-  if (occ * 2 * C::TMEM_COLS > 512) occ = 512 / (2 * C::TMEM_COLS);
+  constexpr int NACC = EG < 2 ? 2 : EG;
+  if (occ * NACC * C::TMEM_COLS > 512) occ = 512 / (NACC * C::TMEM_COLS);
   if (occ > 6) occ = 6;
   if (occ < 1) occ = 1;
   int grid = g_sm_count * occ;
@@ -1898,6 +1921,11 @@ int launch_patch(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtens
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
 }
+
+// epilogue groups (= TMEM accumulator stages) of the one-CTA-per-SM patch variants: a tile's accumulator is handed
+// MMA -> epilogue -> MMA through two mbarrier round trips, so its stage is busy for (round trips + epilogue time);
+// with 4 stages / 4 groups of 4 warps that latency is spread over 4 tiles in flight instead of 2
+constexpr int PEG = 4;
 
 // patch_mode launch: geometry checks, the two tensor maps (activations with dims (c, x, img, y); weights with a
 // box of one N-quarter), the tap schedule (centre tap first) and the live-quarter runs of every tap
@@ -1915,6 +1943,8 @@ int igemm_patch(const mmdyn_igemm_desc* d, cudaStream_t st) {
   const int cin_mode = (d->Cin % 64 == 0) ? 0 : (d->Cin == 32 ? 1 : -1);
   MMDYN_REQUIRE(cin_mode >= 0, "igemm patch_mode: Cin=%d (multiple of 64, or 32)", d->Cin);
   PatchGeom g = {};
+  static const int dbg = getenv("MMDYN_PATCH_DBG") ? atoi(getenv("MMDYN_PATCH_DBG")) : 0;
+  g.dbg = dbg;
   const int bw = IW;
   g.bh = 128 / bw < IH ? 128 / bw : IH;
   g.bn = 128 / (bw * g.bh);
@@ -2005,10 +2035,10 @@ int igemm_patch(const mmdyn_igemm_desc* d, cudaStream_t st) {
     return launch_patch<16, 1, 6, 9, 2>(d, tmA, tmW, g, st);   // 9 KB of weights, 6 x 12 KB patches, 2 CTAs per SM x 8 epilogue warps
   }
   switch (d->N) {
-    case 64: return launch_patch<64, 0, 6, 64, 2>(d, tmA, tmW, g, st);
-    case 128: return launch_patch<128, 0, 7, 64, 2>(d, tmA, tmW, g, st);  // 64 KB of weights + 7 x 20 KB patches, 1 CTA per SM
+    case 64: return launch_patch<64, 0, 6, 64, PEG>(d, tmA, tmW, g, st);
+    case 128: return launch_patch<128, 0, 7, 64, PEG>(d, tmA, tmW, g, st);  // 64 KB of weights + 7 x 20 KB patches, 1 CTA per SM
     case 256:  // phase-split: each CTA owns one output-row parity = 128 columns, 128 KB of weights + 4 x 20 KB patches
-      return launch_patch<128, 0, 4, 128, 2, true>(d, tmA, tmW, g, st);
+      return launch_patch<128, 0, 4, 128, PEG, true>(d, tmA, tmW, g, st);
     default: break;
   }
   set_last_error("igemm patch_mode: N=%d unsupported", d->N);
