@@ -104,9 +104,11 @@ typedef struct mmdyn_igemm_desc {
    * column serves its three row taps, and with out_mode 4 only the structurally non-zero (tap, sub-pixel
    * phase) weight blocks are fetched and multiplied (vae.py:271-277 forward; dgrad of vae.py:200-203). */
   int32_t patch_mode;
-  /* out_mode 4 + patch_mode: optional BatchNorm statistics of the raw output fused into the epilogue —
-   * bn_sums[group][ldc][2] += {sum x, sum x^2} of the fp16-rounded outputs, group = image / bn_rows_per_group
-   * (replaces mmdyn_bn_stats for this layer's output; caller zeroes bn_sums). */
+  /* optional BatchNorm statistics of the raw output fused into the epilogue (out_mode 4 + patch_mode: channels =
+   * ldc <= 64; out_mode 0 without patch_mode: channels = N in [64, 256], one phase, no K split) —
+   * bn_sums[group][channels][2] += {sum x, sum x^2} of the fp16-rounded outputs, group = image / bn_rows_per_group,
+   * which must be a multiple of the images per tile (replaces mmdyn_bn_stats for this layer's output; caller
+   * zeroes bn_sums). */
   int32_t bn_rows_per_group;
   float* bn_sums;
   int32_t s_in_x;       /* input stride along x when it differs from s_in (0 = s_in): the 4-channel logit

@@ -458,6 +458,12 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_all[EG][BLOCK_N];
+  // BatchNorm statistics of the fp16 outputs (out_mode 0 + bn_sums, the conv / 5x5 -> 8x8 deconv layers): per epilogue
+  // group {sum x, sum x^2} per channel, flushed to bn_sums[group] with one atomic per value, CTA and group
+  constexpr bool STATS = (A_MODE == 0 || A_MODE == 1) && BLOCK_N >= 64;
+  __shared__ float stat_all[STATS ? EG : 1][STATS ? 2 * BLOCK_N : 2];
+  if constexpr (STATS)
+    for (int i = threadIdx.x; i < EG * 2 * BLOCK_N; i += blockDim.x) (&stat_all[0][0])[i] = 0.0f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -617,6 +623,19 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
     }
     // out_mode 5: BCE partial sum of this thread for loss slot bce_cur; a tile lies within one image
     // (checked by the launcher), so slot changes are warp-uniform and rare (<= groups per CTA)
+    const bool want_stats = STATS && d.out_mode == 0 && d.bn_sums != nullptr;
+    float* stat_s = stat_all[STATS ? eg : 0];
+    int stat_grp = -1;
+    auto stat_flush = [&]() {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+      for (int i = et; i < 2 * BLOCK_N; i += 128) {
+        const float v = stat_s[i];
+        if (stat_grp >= 0 && v != 0.0f)
+          atomicAdd(d.bn_sums + (static_cast<long long>(stat_grp) * d.N + (i >> 1)) * 2 + (i & 1), v);
+        stat_s[i] = 0.0f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+    };
     float bce_acc = 0.0f;
     int bce_cur = -1;
     auto bce_flush = [&]() {
@@ -636,6 +655,14 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
         out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
       }
       const int n_live = live_kbs(t);
+      if (want_stats) {
+        // all images of a tile belong to one group (checked by the launcher)
+        const int grp = t.img0 / d.bn_rows_per_group;
+        if (grp != stat_grp) {
+          stat_flush();
+          stat_grp = grp;
+        }
+      }
       // out_mode 5: the targets (and mask) of this thread's 2x2x3 output pixels depend on the tile
       // coordinates only, so they are requested BEFORE waiting for the accumulator: their latency
       // hides behind the tile's MMAs instead of serialising the epilogue
@@ -676,6 +703,43 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       const bool add_bias = d.bias != nullptr && t.split == 0;
       // one 16-column chunk of this thread's accumulator row -> global memory
       auto emit = [&](const uint32_t (&v)[16], const int c0) {
+        if constexpr (STATS) {
+          if (want_stats) {
+            // fp16 row chunk + its statistics: every lane takes part in the reduction, rows past the last image add zeros
+            float f[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] = (n_live > 0 && out_off >= 0) ? __uint_as_float(v[q]) : 0.0f;
+            const uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+            const uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]),
+                                        pack_h2(f[14], f[15]));
+            if (out_off >= 0) st_global_32B(reinterpret_cast<__half*>(d.out) + out_off + n_base + c0, u0, u1);
+            // statistics of the values the BatchNorm kernels will read: the fp16-ROUNDED outputs.  32 values (16 sums,
+            // 16 sums of squares) over the warp's 32 rows: butterfly reduce-scatter, 31 shuffles
+            const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+            float w[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&uu[q]));
+              w[2 * q] = a.x;
+              w[2 * q + 1] = a.y;
+              w[16 + 2 * q] = a.x * a.x;
+              w[16 + 2 * q + 1] = a.y * a.y;
+            }
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+              const int off = 16 >> st, cnt = 16 >> st;
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int j = 0; j < cnt; ++j) {
+                const float mine = upper ? w[j + cnt] : w[j];
+                const float send = upper ? w[j] : w[j + cnt];
+                w[j] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            atomicAdd(&stat_s[(c0 + (lane & 15)) * 2 + (lane >> 4)], w[0]);
+            return;
+          }
+        }
         if (out_off < 0) return;
 #ifdef MMDYN_EXP_NOSTORE  // timing experiment only: how much of the kernel are the fp16 epilogue stores?
         if (d.out_mode == 0 || d.out_mode == 4) return;
@@ -795,6 +859,7 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
       mbar_arrive(smem_u32(&tempty_bar[acc]));  // accumulator stage free for tile tl + 2
     }
     if (d.out_mode == 5) bce_flush();
+    if (want_stats) stat_flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -1488,11 +1553,25 @@ struct WgradGeomDev {
   int lbw, lbh, bn, pixel_major, tiles_y, img_blocks, total_steps;
 };
 
-template <int CN, int G_MODE>
+// NB = 128-column blocks of dW per CTA.  These kernels run at the L2 -> SM throughput cap (~43 B/clk/SM: every
+// 64-row step moves NB * 16 KB of gathered gradient + CN * 128 B of the natural operand for NB * 128 * CN * 64
+// MACs), so NB = 2 shares each natural-operand stage between two accumulators: 25 % fewer L2 bytes per MAC at
+// CN = 128.  Stage count: what fits two CTAs per SM (>= 2), TMEM = NB * CN columns.
+template <int CN, int NB>
+struct WCfg {
+  static constexpr int STAGE_BYTES = NB * A_STAGE_BYTES + CN * 128;
+  static constexpr int TMEM_COLS = NB * CN < 32 ? 32 : NB * CN;
+  static constexpr int FIT = (TMEM_COLS > 256 ? 200 * 1024 : 110 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = FIT < 2 ? 2 : (FIT > 4 ? 4 : FIT);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+template <int CN, int G_MODE, int NB>
 __global__ void __launch_bounds__(TMA_THREADS)
 wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_constant__ CUtensorMap tmG,
                  const __grid_constant__ CUtensorMap tmN, const WgradGeomDev g) {
-  using C = Cfg<CN>;
+  using C = WCfg<CN, NB>;
+  static_assert(NB == 1 || G_MODE == 0 || G_MODE == 1, "two column blocks per CTA: G_MODE 0 / 1 only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
@@ -1502,8 +1581,9 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kcol0 = blockIdx.y * 128;
+  const int kcol0 = blockIdx.y * (128 * NB);
   const int n0 = blockIdx.z * CN;
+  constexpr int G_BYTES = NB * A_STAGE_BYTES;  // gathered operand of one stage; the natural operand follows it
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -1534,12 +1614,12 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
   if (warp == 0) {
     if (elect_one()) {
       // operand-box coordinates that do not depend on the step: taps / channel offsets of this CTA's k-columns
-      int tdx[16], tdy[16], tc0[2];
+      int tdx[16], tdy[16], tc0[2 * NB];
 #pragma unroll
       for (int b = 0; b < 16; ++b) tdx[b] = tdy[b] = 0;
       if (G_MODE == 0) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 2 * NB; ++b) {
           const int k = kcol0 + b * 64;
           const int tap = k / d.Cg;
           tc0[b] = k - tap * d.Cg;
@@ -1548,7 +1628,7 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
         }
       } else if (G_MODE == 1) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 4 * NB; ++b) {
           tdx[b] = d.tap_dx[(kcol0 >> 5) + b];
           tdy[b] = d.tap_dy[(kcol0 >> 5) + b];
         }
@@ -1596,18 +1676,18 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
         }
         const uint32_t bar = smem_u32(&full_bar[s]);
         const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
-        const uint32_t b_stage = a_stage + A_STAGE_BYTES;
-        mbar_arrive_expect_tx(bar, (G_MODE == 3 ? 8 * 1024 : A_STAGE_BYTES) + NAT_BYTES);
+        const uint32_t b_stage = a_stage + G_BYTES;
+        mbar_arrive_expect_tx(bar, (G_MODE == 3 ? 8 * 1024 : G_BYTES) + NAT_BYTES);
         const int wx = x0 * (d.s_in_x ? d.s_in_x : d.s_in), wy = y0 * d.s_in;
         if (G_MODE == 3) {
 #pragma unroll
           for (int b = 0; b < 8; ++b) tma_load_4d(a_stage + b * 1024, &tmG, bar, (b & 1) * 8, 0, wy + tdy[b >> 1], img0);
         } else if (G_MODE == 0) {
 #pragma unroll
-          for (int b = 0; b < 2; ++b) tma_load_4d(a_stage + b * 8192, &tmG, bar, tc0[b], wx + tdx[b], wy + tdy[b], img0);
+          for (int b = 0; b < 2 * NB; ++b) tma_load_4d(a_stage + b * 8192, &tmG, bar, tc0[b], wx + tdx[b], wy + tdy[b], img0);
         } else if (G_MODE == 1) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) tma_load_4d(a_stage + b * 4096, &tmG, bar, 0, wx + tdx[b], wy + tdy[b], img0);
+          for (int b = 0; b < 4 * NB; ++b) tma_load_4d(a_stage + b * 4096, &tmG, bar, 0, wx + tdx[b], wy + tdy[b], img0);
         } else {
 #pragma unroll
           for (int b = 0; b < 16; ++b) tma_load_4d(a_stage + b * 1024, &tmG, bar, 0, wx + tdx[b], wy + tdy[b], img0);
@@ -1630,15 +1710,19 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
         mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
         tc_fence_after();
         const uint32_t a_base = smem_base + s * C::STAGE_BYTES;
-        const uint32_t b_base = a_base + A_STAGE_BYTES;
+        const uint32_t b_base = a_base + G_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {  // 16 reduction rows per MMA
-          uint64_t adesc;
-          if (G_MODE == 0) adesc = make_smem_desc(a_base + kk * 2048, 8192, 1024, LAYOUT_SW128);
-          else if (G_MODE == 1) adesc = make_smem_desc(a_base + kk * 1024, 4096, 512, LAYOUT_SW64);
-          else adesc = make_smem_desc(a_base + kk * 256, 128, 1024, 0);
           const uint64_t bdesc = make_smem_desc(b_base + kk * 2 * b_sbo, 8192, b_sbo, b_layout);
-          umma_f16(tmem_base, adesc, bdesc, idesc, (it | kk) != 0);
+#pragma unroll
+          for (int h = 0; h < NB; ++h) {  // column blocks: same natural-operand slice, own accumulator
+            const uint32_t a_h = a_base + h * A_STAGE_BYTES;
+            uint64_t adesc;
+            if (G_MODE == 0) adesc = make_smem_desc(a_h + kk * 2048, 8192, 1024, LAYOUT_SW128);
+            else if (G_MODE == 1) adesc = make_smem_desc(a_h + kk * 1024, 4096, 512, LAYOUT_SW64);
+            else adesc = make_smem_desc(a_h + kk * 256, 128, 1024, 0);
+            umma_f16(tmem_base + h * CN, adesc, bdesc, idesc, (it | kk) != 0);
+          }
         }
         umma_commit(smem_u32(&empty_bar[s]));
       }
@@ -1648,16 +1732,19 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
     const int q4 = warp & 3;
     mbar_wait(smem_u32(&accum_bar), 0);
     tc_fence_after();
-    float* o = d.dW + static_cast<long long>(n0) * d.ldw + kcol0 + q4 * 32 + lane;
     const int c_end = (G_MODE == 3 && q4 >= 2) ? 0 : CN;  // G_MODE 3: 64 live k-columns
 #pragma unroll 1
-    for (int c0 = 0; c0 < c_end; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + c0, v);
-      tmem_ld_wait(v);
+    for (int h = 0; h < NB; ++h) {
+      float* o = d.dW + static_cast<long long>(n0) * d.ldw + kcol0 + h * 128 + q4 * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < c_end; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + h * CN + c0, v);
+        tmem_ld_wait(v);
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        atomicAdd(o + static_cast<long long>(c0 + q) * d.ldw, d.scale * __uint_as_float(v[q]));
+        for (int q = 0; q < 16; ++q)
+          atomicAdd(o + static_cast<long long>(c0 + q) * d.ldw, d.scale * __uint_as_float(v[q]));
+      }
     }
   }
   tc_fence_before();
@@ -1752,10 +1839,8 @@ conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __h
     float f[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
-    reinterpret_cast<uint4*>(o + c0)[0] = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]),
-                                                     pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
-    reinterpret_cast<uint4*>(o + c0)[1] = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]),
-                                                     pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+    st_global_32B(o + c0, make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])),
+                  make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15])));
   }
   tc_fence_before();
   __syncthreads();
@@ -1864,10 +1949,23 @@ int dispatch_amode(int a_mode, const mmdyn_igemm_desc* d, const CUtensorMap& tmA
   return launch_igemm_tma<BLOCK_N, 2>(d, tmA, tmW, g, occ, st);
 }
 
-template <int CN, int G_MODE>
+template <int CN, int G_MODE, int NB>
 int launch_wgrad_tma(const mmdyn_wgrad_desc* d, const CUtensorMap& tmG, const CUtensorMap& tmN,
                      const WgradGeomDev& g, dim3 grid, cudaStream_t st) {
-  MMDYN_LAUNCH((wgrad_tma_kernel<CN, G_MODE>), grid, TMA_THREADS, Cfg<CN>::SMEM_BYTES, st, *d, tmG, tmN, g);
+  static bool configured = false;
+  if (!configured) {
+    MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, G_MODE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          WCfg<CN, NB>::SMEM_BYTES));
+    configured = true;
+  }
+  if (NB == 2) {  // half as many column blocks: split the reduction twice as finely to keep the CTA count
+    grid.y /= 2;
+    grid.x = static_cast<unsigned>(std::min<long long>(2LL * grid.x, g.total_steps));
+  }
+  mmdyn_wgrad_desc dd = *d;
+  dd.row_splits = static_cast<int>(grid.x);
+  constexpr int smem_bytes = WCfg<CN, NB>::SMEM_BYTES;
+  MMDYN_LAUNCH((wgrad_tma_kernel<CN, G_MODE, NB>), grid, TMA_THREADS, smem_bytes, st, dd, tmG, tmN, g);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;
@@ -1876,13 +1974,17 @@ int launch_wgrad_tma(const mmdyn_wgrad_desc* d, const CUtensorMap& tmG, const CU
 template <int CN>
 int dispatch_gmode(int g_mode, const mmdyn_wgrad_desc* d, const CUtensorMap& tmG, const CUtensorMap& tmN,
                    const WgradGeomDev& g, dim3 grid, cudaStream_t st) {
-  if (g_mode == 0) return launch_wgrad_tma<CN, 0>(d, tmG, tmN, g, grid, st);
-  if (g_mode == 1) return launch_wgrad_tma<CN, 1>(d, tmG, tmN, g, grid, st);
+  static const bool nb1 = getenv("MMDYN_WGRAD_NB1") != nullptr;
+  // measured (tools/bench_layers.py): +10 % on the 5x5 <-> 8x8 layer at 4096 rows, neutral at Cn = 64, a loss when a CTA
+  // has only ~10 reduction steps to amortise the second accumulator's epilogue
+  const bool two = !nb1 && (d->ntaps * d->Cg) % 256 == 0 && CN >= 128 && g.total_steps >= 48LL * grid.x;
+  if (g_mode == 0) return two ? launch_wgrad_tma<CN, 0, 2>(d, tmG, tmN, g, grid, st) : launch_wgrad_tma<CN, 0, 1>(d, tmG, tmN, g, grid, st);
+  if (g_mode == 1) return two ? launch_wgrad_tma<CN, 1, 2>(d, tmG, tmN, g, grid, st) : launch_wgrad_tma<CN, 1, 1>(d, tmG, tmN, g, grid, st);
   if (g_mode == 3) {
-    if constexpr (CN == 32) return launch_wgrad_tma<32, 3>(d, tmG, tmN, g, grid, st);
+    if constexpr (CN == 32) return launch_wgrad_tma<32, 3, 1>(d, tmG, tmN, g, grid, st);
     MMDYN_REQUIRE(false, "wgrad: Cg = 16 is built for Cn = 32 only (Cn=%d)", d->Cn);
   }
-  return launch_wgrad_tma<CN, 2>(d, tmG, tmN, g, grid, st);
+  return launch_wgrad_tma<CN, 2, 1>(d, tmG, tmN, g, grid, st);
 }
 
 int ilog2(int v) {
@@ -2110,20 +2212,6 @@ int igemm_init() {
   SET_TMA(4, 256);
 #undef SET_TMA
   MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_tma_kernel<32, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM_BYTES));
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM_BYTES));
-#define SET_WG(CN)                                                                                            \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        Cfg<CN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        Cfg<CN>::SMEM_BYTES));                                               \
-  MMDYN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<CN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        Cfg<CN>::SMEM_BYTES))
-  SET_WG(16);
-  SET_WG(32);
-  SET_WG(64);
-  SET_WG(128);
-  SET_WG(256);
-#undef SET_WG
   // cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports these kernels (it returned <= 1 for every
   // variant on B200 although ncu shows a shared-memory limit of 2-3 CTAs), so the persistent grids
   // are sized from the resources directly: 228 KB shared memory per SM, 1 KB reserved per CTA.
@@ -2299,6 +2387,12 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
     }
     MMDYN_REQUIRE(d->out_mode != 5 || (g.bn == 1 && !g.pixel_major),
                   "igemm: out_mode 5 needs tiles that lie within one image (OXv=%d P=%d)", d->OXv, d->P);
+    if (d->bn_sums) {
+      MMDYN_REQUIRE(d->out_mode == 0 && (a_mode == 0 || a_mode == 1) && d->block_n >= 64 && n_tiles == 1 && d->ksplit == 1 &&
+                        d->n_phases == 1 && d->bn_rows_per_group > 0 && d->bn_rows_per_group % bn == 0,
+                    "igemm: bn_sums needs out_mode 0, Cin %% 64 == 0 or 32, 64 <= N <= 256, one phase, no K split and "
+                    "rows_per_group %% %d == 0 (images per tile)", bn);
+    }
     const int occ = g_tma_occ[occ_idx];
     switch (d->block_n) {
       case 16: return dispatch_amode<16>(a_mode, d, tmA, tm, g, occ, st);
@@ -2311,6 +2405,7 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
 
   // ---- cp.async gather path (any dense geometry) -------------------------------------------------
   MMDYN_REQUIRE(d->out_mode != 5, "igemm: out_mode 5 needs the TMA path");
+  MMDYN_REQUIRE(d->bn_sums == nullptr, "igemm: bn_sums needs the TMA path");
   MMDYN_REQUIRE(!custom_strides, "igemm: a_row_stride / a_img_stride / overlapping windows need the TMA path "
                 "(Cin=%d ntaps=%d)", d->Cin, d->ntaps);
   long long m_tiles_ll;

@@ -383,6 +383,9 @@ def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale, gp=None):
         ops.unpack_add_f32(dWp, pl.idx_wgrad, arena.grad)
 
 
+FUSE_STATS = os.environ.get("MMDYN_NO_FUSED_STATS") is None  # BatchNorm sums from the producing GEMM's epilogue
+
+
 class _BN:
     """Grouped training-mode BatchNorm2d + Swish around a raw conv output."""
 
@@ -467,18 +470,19 @@ class EncoderExec(_NetBase):
         ops.conv1_fwd(x, self.c1.Wf, raw1, B)
         act1 = alloc(key + ".act1", (B, 32, 32, 32), F16)
         ops.bn_swish_fwd(raw1, None, act1, 1, B * 1024, 32)
-        raw2 = alloc(key + ".raw2", (B, 16, 16, 64), F16)
-        _ig(self.c2, "fwd", act1, raw2, B)
-        act2 = alloc(key + ".act2", (B, 16, 16, 64), F16)
-        r["bn2"] = self.bn2.forward(raw2, act2, 1, B * 256, alloc, key + ".bn2", track, nm)
-        raw3 = alloc(key + ".raw3", (B, 8, 8, 128), F16)
-        _ig(self.c3, "fwd", act2, raw3, B)
-        act3 = alloc(key + ".act3", (B, 8, 8, 128), F16)
-        r["bn3"] = self.bn3.forward(raw3, act3, 1, B * 64, alloc, key + ".bn3", track, nm)
-        raw4 = alloc(key + ".raw4", (B, 5, 5, 256), F16)
-        _ig(self.c4, "fwd", act3, raw4, B)
-        act4 = alloc(key + ".act4", (B, 5, 5, 256), F16)
-        r["bn4"] = self.bn4.forward(raw4, act4, 1, B * 25, alloc, key + ".bn4", track, nm)
+        def conv_bn(pl, bn, a_in, shape, rows, name):
+            # conv -> BatchNorm + Swish; the batch statistics come out of the GEMM epilogue when the batch is a whole
+            # number of tiles (else mmdyn_bn_stats reads the raw output once more)
+            raw, act = alloc(key + ".raw" + name, shape, F16), alloc(key + ".act" + name, shape, F16)
+            st = bn.alloc_fwd(1, alloc, key + ".bn" + name)
+            fused = bool(FUSE_STATS and B % plan.tile_images(pl.lp.fwd) == 0)
+            _ig(pl, "fwd", a_in, raw, B, stats=(st[0], B) if fused else None)
+            bn.run_fwd(raw, act, 1, rows, st, 0, track, nm, have_stats=fused)
+            return raw, act, (st[1], st[2])
+
+        raw2, act2, r["bn2"] = conv_bn(self.c2, self.bn2, act1, (B, 16, 16, 64), B * 256, "2")
+        raw3, act3, r["bn3"] = conv_bn(self.c3, self.bn3, act2, (B, 8, 8, 128), B * 64, "3")
+        raw4, act4, r["bn4"] = conv_bn(self.c4, self.bn4, act3, (B, 5, 5, 256), B * 25, "4")
         fc_raw = alloc(key + ".fc_raw", (B, 512), F32)
         _ig(self.fc, "fwd", act4, fc_raw, B, self.fc.bias, True)
         h = alloc(key + ".h", (nm, B, 512), F16)
@@ -606,8 +610,9 @@ class DecoderExec(_NetBase):
                 ops.cond_add_f16(raw0[sl], cond_rep[sl], self.pview("upsample.0.weight"), self.up_rows, n, 6400,
                                  256 + self.cd, 256, self.cd)
             ops.bn_swish_fwd(raw0[sl], None, act0[sl], 1, n * 25, 256)
-            _ig(self.d1, "fwd", act0[sl], raw1[sl], n)
-            self.bn1.run_fwd(raw1[sl], act1[sl], Gc, B * 64, s1, g0, track)
+            f1 = bool(self.fuse_stats and B % plan.tile_images(self.d1.lp.fwd) == 0)
+            _ig(self.d1, "fwd", act0[sl], raw1[sl], n, stats=(s1[0][g0:g0 + Gc], B) if f1 else None)
+            self.bn1.run_fwd(raw1[sl], act1[sl], Gc, B * 64, s1, g0, track, have_stats=f1)
             # BatchNorm statistics of raw2 / raw3 come out of the producing GEMM's epilogue (patch kernel);
             # a tile of the 8x8 layer holds two images, which must belong to one group
             f2 = bool(self.fuse_stats and self.d2.lp.fwd.patch and B % 2 == 0)
@@ -634,7 +639,7 @@ class DecoderExec(_NetBase):
         return r
 
     after_group = None  # optional callback(g0, Gc, logits_rows) run right after a group chunk's logits (fused losses)
-    fuse_stats = os.environ.get("MMDYN_NO_FUSED_STATS") is None  # BatchNorm sums in the deconv2/3 epilogues
+    fuse_stats = FUSE_STATS  # BatchNorm sums in the deconv1/2/3 epilogues
 
     def backward(self, r, dl8, alloc, key, unscale, gp=None):
         """dl8: (G*B, 66, 66, plan.LOGIT_CP = 4) fp16 logit gradients with a one-pixel ZERO border (3 channels used, times grad_scale).

@@ -150,7 +150,7 @@ def igemm(geom, A, Wp, out, n_img, bias=None, ksplit=1, out_mode=None, ldc=None,
     if d.patch_mode:
         _PATCH_TAGS.add(tag)
     if stats is not None:  # (sums [G][C][2] fp32 zeroed, images per group): BatchNorm statistics in the epilogue
-        assert d.patch_mode and d.out_mode == 4
+        assert (d.patch_mode and d.out_mode == 4) or (not d.patch_mode and d.out_mode == 0)
         d.bn_sums, d.bn_rows_per_group = stats[0].data_ptr(), int(stats[1])
     if bce is not None:
         d.out_mode = 5

@@ -412,6 +412,18 @@ def nhwc_perm(C, H, W):
     return (c * (H * W) + hw).reshape(-1)
 
 
+def tile_images(geom: GemmGeom) -> int:
+    """Images per 128-row tile of mmdyn_igemm's TMA path (same rule as the launcher, csrc/igemm.cu): a box of
+    OXv x bh pixels x bn images, or one pixel x 128 images.  Fused BatchNorm statistics need whole tiles per group."""
+    OYv, bw = geom.P // geom.OXv, geom.OXv
+    if geom.row_mode != 0 or geom.P <= 1 or bw > 128 or 128 % bw:
+        return 128
+    bh = min(128 // bw, OYv)
+    if OYv % bh or bh & (bh - 1) or 128 % (bw * bh):
+        return 128
+    return 128 // (bw * bh)
+
+
 def choose_ksplit(geom: GemmGeom, n_img: int, sm_count: int = 148):
     """Split K across CTAs when the output grid alone cannot fill the machine."""
     if geom.row_mode == 1:
