@@ -871,6 +871,265 @@ igemm_tma_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------
+// igemm, TWO 128-row tiles per weight stage (Cin % 64 == 0, fp16 row output, one N tile, no bias / K split).
+// The N >= 128 conv layers run at the L2 -> SM throughput cap (LTS ~ 6.3 KB/clk for the chip = 43 B/clk/SM: every
+// 64-wide k-block of a 128 x N tile moves 16 KB of activations + N * 128 B of weights through it; deconv1.fwd
+// moves 1.64 GB in 0.115 ms = 14 TB/s), not at the tensor pipe.  Here a CTA owns the tile PAIR (2p, 2p + 1) — same
+// virtual pixel or box row, neighbouring image blocks — and each weight k-block is fetched ONCE for both:
+// (2 * 16 KB + N * 128 B) per 2 * 128 * N * 64 MACs, 25 % (N = 128) / 33 % (N = 256) fewer L2 bytes per MAC.
+//   warp 0 TMA producer, warp 1 MMA issuer (8 MMAs per k-block: 4 per tile, one B descriptor),
+//   epilogue group e (4 warps) drains tile e of the pair.  TMEM: NACC stages x 2 tiles x N columns.
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct Cfg2 {
+  static constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + BLOCK_N * 128;
+  static constexpr int STAGES = BLOCK_N == 256 ? 3 : 4;
+  static constexpr int NACC = BLOCK_N == 256 ? 1 : 2;
+  static constexpr int TMEM_COLS = NACC * 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+};
+
+template <int BLOCK_N, int A_MODE>
+__global__ void __launch_bounds__(320)
+igemm_pair_kernel(const __grid_constant__ mmdyn_igemm_desc d, const __grid_constant__ CUtensorMap tmA,
+                  const __grid_constant__ CUtensorMap tmW, const TileGeom g) {
+  using C = Cfg2<BLOCK_N>;
+  constexpr int NACC = C::NACC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[NACC];
+  __shared__ __align__(8) uint64_t tempty_bar[NACC];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float stat_all[2][2 * BLOCK_N];
+  for (int i = threadIdx.x; i < 4 * BLOCK_N; i += blockDim.x) (&stat_all[0][0])[i] = 0.0f;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 256);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  pdl_sync();
+
+  const int n_pairs = g.total_tiles >> 1;
+  const int CB = A_MODE == 0 ? (d.Cin >> 6) : 1;
+  const bool skip_taps = A_MODE == 0 && g.pixel_major && d.ntaps > 1;
+  // both tiles of a pair share the virtual pixel (pixel-major) or have no out-of-image skipping (box tiles)
+  auto live_taps = [&](const TileCoord2& t) -> uint32_t {
+    if (!skip_taps) return (d.ntaps >= 32) ? 0xFFFFFFFFu : ((1u << d.ntaps) - 1u);
+    uint32_t m = 0;
+    const int by = t.y0 * d.s_in, bx = t.x0 * d.s_in;
+    for (int tap = 0; tap < d.ntaps; ++tap) {
+      const int iy = by + d.tap_dy[0][tap], ix = bx + d.tap_dx[0][tap];
+      if ((unsigned)iy < (unsigned)d.IH && (unsigned)ix < (unsigned)d.IW) m |= 1u << tap;
+    }
+    return m;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const TileCoord2 t0 = decode_tile2(d, g, 2 * p), t1 = decode_tile2(d, g, 2 * p + 1);
+        const uint32_t mask = live_taps(t0);
+        const int wx0 = t0.x0 * d.s_in, wy0 = t0.y0 * d.s_in, wx1 = t1.x0 * d.s_in, wy1 = t1.y0 * d.s_in;
+        if constexpr (A_MODE == 1) {  // Cin = 32: two taps (two 64B-swizzled boxes) per k-block and tile, box tiles only
+          for (int kb = 0; kb < (d.ntaps >> 1); ++kb) {
+            const int s = it % C::STAGES;
+            mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+            const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int tdx = d.tap_dx[0][2 * kb + b], tdy = d.tap_dy[0][2 * kb + b];
+              tma_load_4d(a_stage + b * 8192, &tmA, bar, 0, wx0 + tdx, wy0 + tdy, t0.img0);
+              tma_load_4d(a_stage + A_STAGE_BYTES + b * 8192, &tmA, bar, 0, wx1 + tdx, wy1 + tdy, t1.img0);
+            }
+            tma_load_2d(a_stage + 2 * A_STAGE_BYTES, &tmW, bar, kb << 6, 0);
+            ++it;
+          }
+          continue;
+        }
+        int kb = 0;
+        for (int tap = 0; tap < d.ntaps; ++tap) {
+          if (!((mask >> tap) & 1u)) {
+            kb += CB;
+            continue;
+          }
+          const int tdx = d.tap_dx[0][tap], tdy = d.tap_dy[0][tap];
+          for (int cb = 0; cb < CB; ++cb, ++kb) {
+            const int s = it % C::STAGES;
+            mbar_wait(smem_u32(&empty_bar[s]), ((it / C::STAGES) & 1) ^ 1);
+            const uint32_t a_stage = smem_base + s * C::STAGE_BYTES;
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            mbar_arrive_expect_tx(bar, C::STAGE_BYTES);
+            tma_load_4d(a_stage, &tmA, bar, cb << 6, wx0 + tdx, wy0 + tdy, t0.img0);
+            tma_load_4d(a_stage + A_STAGE_BYTES, &tmA, bar, cb << 6, wx1 + tdx, wy1 + tdy, t1.img0);
+            tma_load_2d(a_stage + 2 * A_STAGE_BYTES, &tmW, bar, kb << 6, 0);
+            ++it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BLOCK_N, 0, 0, 0, 0);
+      constexpr uint64_t HI = (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                              (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(LAYOUT_SW128) << 61);
+      constexpr uint64_t A_HI = A_MODE == 0 ? HI
+                                            : ((static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>(512 >> 4) << 32) |
+                                               (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(LAYOUT_SW64) << 61));
+      int it = 0, tl = 0;
+      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++tl) {
+        const TileCoord2 t0 = decode_tile2(d, g, 2 * p);
+        const int n_kb = A_MODE == 0 ? __popc(live_taps(t0)) * CB : (d.ntaps >> 1);
+        const int acc = tl % NACC;
+        mbar_wait(smem_u32(&tempty_bar[acc]), ((tl / NACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 2 * BLOCK_N;
+        for (int i = 0; i < n_kb; ++i) {
+          const int s = it % C::STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (it / C::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a16 = (smem_base + s * C::STAGE_BYTES) >> 4;
+          const uint32_t b16 = a16 + ((2 * A_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = HI | static_cast<uint64_t>(b16 + 2 * kk);
+            const uint32_t a_off = A_MODE == 0 ? 2 * kk : (kk >> 1) * (8192 >> 4) + (kk & 1) * 2;
+            umma_f16(tmem_d, A_HI | static_cast<uint64_t>(a16 + a_off), bdesc, idesc, (i | kk) ? 1u : 0u);
+            umma_f16(tmem_d + BLOCK_N, A_HI | static_cast<uint64_t>(a16 + (A_STAGE_BYTES >> 4) + a_off), bdesc, idesc,
+                     (i | kk) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          ++it;
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int eg = (warp - 2) >> 2;             // epilogue group = tile of the pair
+    const int et = (threadIdx.x - 64) & 127;
+    int x_l, y_l, n_l;
+    if (g.pixel_major) {
+      x_l = 0; y_l = 0; n_l = r;
+    } else {
+      x_l = r & ((1 << g.lbw) - 1);
+      y_l = (r >> g.lbw) & ((1 << g.lbh) - 1);
+      n_l = r >> (g.lbw + g.lbh);
+    }
+    const bool want_stats = d.bn_sums != nullptr;
+    float* stat_s = stat_all[eg];
+    int stat_grp = -1;
+    auto stat_flush = [&]() {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+      for (int i = et; i < 2 * BLOCK_N; i += 128) {
+        const float v = stat_s[i];
+        if (stat_grp >= 0 && v != 0.0f)
+          atomicAdd(d.bn_sums + (static_cast<long long>(stat_grp) * d.N + (i >> 1)) * 2 + (i & 1), v);
+        stat_s[i] = 0.0f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+    };
+    int tl = 0;
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++tl) {
+      const TileCoord2 t = decode_tile2(d, g, 2 * p + eg);
+      const int img = t.img0 + n_l, yv = t.y0 + y_l, xv = t.x0 + x_l;
+      const bool valid = img < d.n_img;
+      const int oy = yv * d.s_out + d.off_y[0], ox = xv * d.s_out + d.off_x[0];
+      const int out_off = valid ? ((img * d.OH + oy) * d.OW + ox) * d.ldc : -1;
+      const bool has_k = live_taps(t) != 0u;
+      if (want_stats) {
+        const int grp = t.img0 / d.bn_rows_per_group;
+        if (grp != stat_grp) {
+          stat_flush();
+          stat_grp = grp;
+        }
+      }
+      const int acc = tl % NACC;
+      mbar_wait(smem_u32(&tfull_bar[acc]), (tl / NACC) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (acc * 2 + eg) * BLOCK_N + (static_cast<uint32_t>(q4 * 32) << 16);
+      auto emit = [&](const uint32_t (&v)[16], const int c0) {
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) f[q] = (has_k && out_off >= 0) ? __uint_as_float(v[q]) : 0.0f;
+        const uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+        const uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+        if (out_off >= 0) st_global_32B(reinterpret_cast<__half*>(d.out) + out_off + c0, u0, u1);
+        if (want_stats) {
+          // statistics of the fp16-ROUNDED outputs over the warp's 32 rows: butterfly reduce-scatter, 31 shuffles
+          const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          float w[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&uu[q]));
+            w[2 * q] = a.x;
+            w[2 * q + 1] = a.y;
+            w[16 + 2 * q] = a.x * a.x;
+            w[16 + 2 * q + 1] = a.y * a.y;
+          }
+#pragma unroll
+          for (int st = 0; st < 5; ++st) {
+            const int off = 16 >> st, cnt = 16 >> st;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < cnt; ++j) {
+              const float mine = upper ? w[j + cnt] : w[j];
+              const float send = upper ? w[j] : w[j + cnt];
+              w[j] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          atomicAdd(&stat_s[(c0 + (lane & 15)) * 2 + (lane >> 4)], w[0]);
+        }
+      };
+      uint32_t va[16], vb[16];
+      tmem_ld_x16(tmem_d, va);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        tmem_ld_wait(va);
+        tmem_ld_x16(tmem_d + c0 + 16, vb);
+        emit(va, c0);
+        tmem_ld_wait(vb);
+        if (c0 + 32 < BLOCK_N) tmem_ld_x16(tmem_d + c0 + 32, va);
+        emit(vb, c0 + 16);
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[acc]));
+    }
+    if (want_stats) stat_flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // igemm, shared-memory PATCH reuse for the merged 3x3-tap layers (the 4 sub-pixel phases of a k4/s2/p1
 // transposed conv, or of the dgrad of a k4/s2/p1 conv, as one GEMM over the 3x3 neighbourhood of the
 // low-resolution grid: deconv2/3/4 forward, conv2/3 dgrad).  These layers were bound by the L2 -> shared
@@ -1937,6 +2196,24 @@ int launch_igemm_tma(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CU
   return MMDYN_OK;
 }
 
+template <int BLOCK_N, int A_MODE>
+int launch_igemm_pair(const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW, const TileGeom& g,
+                      cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    MMDYN_CHECK_CUDA(cudaFuncSetAttribute(igemm_pair_kernel<BLOCK_N, A_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg2<BLOCK_N>::SMEM_BYTES));
+    configured = true;
+  }
+  int grid = g_sm_count;
+  if (grid > g.total_tiles / 2) grid = g.total_tiles / 2;
+  constexpr int smem_bytes = Cfg2<BLOCK_N>::SMEM_BYTES;
+  MMDYN_LAUNCH((igemm_pair_kernel<BLOCK_N, A_MODE>), grid, 320, smem_bytes, st, *d, tmA, tmW, g);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  MMDYN_CHECK_CUDA(cudaGetLastError());
+  return MMDYN_OK;
+}
+
 template <int BLOCK_N>
 int dispatch_amode(int a_mode, const mmdyn_igemm_desc* d, const CUtensorMap& tmA, const CUtensorMap& tmW,
                    const TileGeom& g, int occ, cudaStream_t st) {
@@ -2392,6 +2669,17 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
                         d->n_phases == 1 && d->bn_rows_per_group > 0 && d->bn_rows_per_group % bn == 0,
                     "igemm: bn_sums needs out_mode 0, Cin %% 64 == 0 or 32, 64 <= N <= 256, one phase, no K split and "
                     "rows_per_group %% %d == 0 (images per tile)", bn);
+    }
+    // tile pairs sharing each weight stage (igemm_pair_kernel): the L2-bound conv layers with enough work per SM
+    static const int pair_mode = getenv("MMDYN_IGEMM_PAIR") ? atoi(getenv("MMDYN_IGEMM_PAIR")) : 1;
+    if (pair_mode && d->out_mode == 0 && d->bias == nullptr && d->ksplit == 1 && n_tiles == 1 && d->n_phases == 1 &&
+        (g.total_tiles & 1) == 0 && (!g.pixel_major || (g.img_blocks & 1) == 0) &&
+        (pair_mode == 2 || g.total_tiles >= 4 * g_sm_count) && d->ntaps <= 32) {
+      if (a_mode == 0 && d->block_n == 128) return launch_igemm_pair<128, 0>(d, tmA, tm, g, st);
+      if (a_mode == 0 && d->block_n == 256) return launch_igemm_pair<256, 0>(d, tmA, tm, g, st);
+      if (a_mode == 0 && d->block_n == 64 && pair_mode >= 2) return launch_igemm_pair<64, 0>(d, tmA, tm, g, st);
+      if (a_mode == 1 && d->block_n == 64 && !g.pixel_major && (pair_mode >= 2 || pair_mode == 1))
+        return launch_igemm_pair<64, 1>(d, tmA, tm, g, st);
     }
     const int occ = g_tma_occ[occ_idx];
     switch (d->block_n) {

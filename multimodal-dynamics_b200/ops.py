@@ -75,9 +75,9 @@ def kernel_family(tag):
     if tag in _FAMILY:
         return _FAMILY[tag]
     if tag in _PATCH_TAGS:
-        return "igemm_patch_kernel<*> (merged 3x3-tap layers: deconv3/4 forward, conv2 dgrad)"
+        return "igemm_patch_kernel<*> (merged 3x3-tap layers: deconv2/3/4 forward, conv2/3 dgrad)"
     if tag.endswith(".fwd") or tag.endswith(".dgrad"):
-        return "igemm_tma_kernel<*> (conv / deconv / linear forward + dgrad)"
+        return "igemm_tma_kernel<*> + igemm_pair_kernel<*> (conv / deconv / linear forward + dgrad)"
     if tag.endswith(".wgrad"):
         return "wgrad_tma_kernel<*> (weight gradients)"
     return tag + "_kernel"

@@ -126,6 +126,19 @@ def test_conv4_k4s1p0(n):
     check_conv_layer(plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), w, x, 1, 0, False)
 
 
+def test_pair_kernel_sizes():
+    """Enough tiles for igemm_pair_kernel (two 128-row tiles per weight stage, csrc/igemm.cu): the 5x5 -> 8x8 deconv
+    forward (N = 128) and data gradient (N = 256) with pixel-major tile pairs, and a Cin = 32 stride-2 conv (N = 64,
+    two 64B-swizzled tap boxes per k-block) with box tile pairs."""
+    torch.manual_seed(41)
+    w = torch.randn(256, 128, 4, 4) * 0.03
+    x = torch.randn(3072, 256, 5, 5)
+    check_conv_layer(plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), w, x, 1, 0, True)
+    w = torch.randn(64, 32, 4, 4) * 0.05
+    x = torch.randn(320, 32, 32, 32)
+    check_conv_layer(plan.conv_s2_plan("c2", 0, 32, 64, 32), w, x, 2, 1, False)
+
+
 @pytest.mark.parametrize("n", [7, 130])
 def test_deconv1_k4s1p0(n):
     torch.manual_seed(4)

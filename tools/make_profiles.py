@@ -20,7 +20,8 @@ def run(args, out):
 def family(name):
     name = name.replace("void ", "").replace("mmdyn::<unnamed>::", "").replace("unnamed>::", "")
     m = re.match(r"([A-Za-z0-9_]+)", name)
-    return m.group(1) if m else name
+    fam = m.group(1) if m else name
+    return "igemm_tma_kernel" if fam == "igemm_pair_kernel" else fam  # one family in bench.py (ops.kernel_family)
 
 
 def traffic(raw_csv, T):
@@ -58,14 +59,14 @@ def main(T):
     fam = {}
     for what in ("gemm", "bn"):
         fam.update(traffic(os.path.join(G, f"{T}_{what}_raw.csv"), T))
-    names = {"igemm_tma_kernel": "igemm_tma_kernel<*> (conv / deconv / linear forward + dgrad)",
-             "igemm_patch_kernel": "igemm_patch_kernel<*> (merged 3x3-tap layers: deconv3/4 forward, conv2 dgrad)",
+    names = {"igemm_tma_kernel": "igemm_tma_kernel<*> + igemm_pair_kernel<*> (conv / deconv / linear forward + dgrad)",
+             "igemm_patch_kernel": "igemm_patch_kernel<*> (merged 3x3-tap layers: deconv2/3/4 forward, conv2/3 dgrad)",
              "wgrad_tma_kernel": "wgrad_tma_kernel<*> (weight gradients)"}
     for k, v in fam.items():
         v["source"] = tr["source"]
         tr[names.get(k, k)] = v
     json.dump(tr, open(os.path.join(P, "r2_traffic.json"), "w"), indent=1)
-    for rep, name in ((f"{T}_src_deconv2fwd", "r2_stalls_igemm_tma_256_deconv2fwd.txt"), (f"{T}_src_deconv3fwd", "r2_stalls_igemm_patch_128_deconv3fwd.txt")):
+    for rep, name in ((f"{T}_src_deconv1fwd", "r2_stalls_igemm_pair_128_deconv1fwd.txt"), (f"{T}_src_deconv3fwd", "r2_stalls_igemm_patch_128_deconv3fwd.txt")):
         if os.path.exists(os.path.join(G, rep + ".ncu-rep")):
             run([sys.executable, "tools/ncu_regions.py", f"gpurun_out/{rep}.ncu-rep", "80"], os.path.join(P, name))
     for src, dst in ((f"{T}_bench.json", "r2_bench_default.json"), (f"{T}_bench_ref.json", "r2_bench_reference_arm.json"),
