@@ -2255,8 +2255,12 @@ int dispatch_gmode(int g_mode, const mmdyn_wgrad_desc* d, const CUtensorMap& tmG
   // measured (tools/bench_layers.py): +10 % on the 5x5 <-> 8x8 layer at 4096 rows, neutral at Cn = 64, a loss when a CTA
   // has only ~10 reduction steps to amortise the second accumulator's epilogue
   const bool two = !nb1 && (d->ntaps * d->Cg) % 256 == 0 && CN >= 128 && g.total_steps >= 48LL * grid.x;
-  if (g_mode == 0) return two ? launch_wgrad_tma<CN, 0, 2>(d, tmG, tmN, g, grid, st) : launch_wgrad_tma<CN, 0, 1>(d, tmG, tmN, g, grid, st);
-  if (g_mode == 1) return two ? launch_wgrad_tma<CN, 1, 2>(d, tmG, tmN, g, grid, st) : launch_wgrad_tma<CN, 1, 1>(d, tmG, tmN, g, grid, st);
+  if constexpr (CN >= 128) {
+    if (two && g_mode == 0) return launch_wgrad_tma<CN, 0, 2>(d, tmG, tmN, g, grid, st);
+    if (two && g_mode == 1) return launch_wgrad_tma<CN, 1, 2>(d, tmG, tmN, g, grid, st);
+  }
+  if (g_mode == 0) return launch_wgrad_tma<CN, 0, 1>(d, tmG, tmN, g, grid, st);
+  if (g_mode == 1) return launch_wgrad_tma<CN, 1, 1>(d, tmG, tmN, g, grid, st);
   if (g_mode == 3) {
     if constexpr (CN == 32) return launch_wgrad_tma<32, 3, 1>(d, tmG, tmN, g, grid, st);
     MMDYN_REQUIRE(false, "wgrad: Cg = 16 is built for Cn = 32 only (Cn=%d)", d->Cn);

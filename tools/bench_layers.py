@@ -89,6 +89,8 @@ CASES = {
     "conv4.wgrad": lambda R: run_wgrad("conv4.wgrad", plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), R // 4, (8, 8, 128), (5, 5, 256)),
     "deconv4.dgrad": lambda R: run("deconv4.dgrad", plan.deconv_out_plan("d4", 0), "dgrad", R, (66, 66, 4), (32, 32, 32)),
     "deconv2.dgrad": lambda R: run("deconv2.dgrad", plan.deconv_s2_plan("d2", 0, 128, 64, 8), "dgrad", R, (16, 16, 64), (8, 8, 128)),
+    "deconv1.dgrad": lambda R: run("deconv1.dgrad", plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), "dgrad", R, (8, 8, 128), (5, 5, 256)),
+    "conv4.dgrad": lambda R: run("conv4.dgrad", plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), "dgrad", R // 4, (5, 5, 256), (8, 8, 128)),
 }
 
 if __name__ == "__main__":
