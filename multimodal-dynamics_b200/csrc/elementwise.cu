@@ -1060,23 +1060,33 @@ colsum_f16_kernel(const __half* __restrict__ x, float* __restrict__ out, int M, 
   }
 }
 
+__device__ __forceinline__ __half pack_f16_one(const float* __restrict__ src, int32_t j) {
+  if (j < 0) return __float2half_rn(0.0f);
+  if (j & (1 << 30)) {
+    // low part of the two-term fp16 split of an fp32 weight (pose MLP on the tensor cores, mmdyn_split_f16)
+    const float w = __ldg(src + (j & ((1 << 30) - 1)));
+    return __float2half_rn(w - __half2float(__float2half_rn(w)));
+  }
+  return __float2half_rn(__ldg(src + j));
+}
+
+// 8 packed elements per thread: two 16-byte index loads, 8 gathers from the (L2-resident) fp32 arena, one 16-byte store
 __global__ void __launch_bounds__(256)
 pack_f16_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, __half* __restrict__ dst,
                 long long n) {
   pdl_sync();
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int32_t j = idx[i];
-    if (j < 0) {
-      dst[i] = __float2half_rn(0.0f);
-    } else if (j & (1 << 30)) {
-      // low part of the two-term fp16 split of an fp32 weight (pose MLP on the tensor cores, mmdyn_split_f16)
-      const float w = src[j & ((1 << 30) - 1)];
-      dst[i] = __float2half_rn(w - __half2float(__float2half_rn(w)));
-    } else {
-      dst[i] = __float2half_rn(src[j]);
-    }
+  const long long n8 = n >> 3;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n8;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int4 j0 = __ldg(reinterpret_cast<const int4*>(idx) + 2 * v), j1 = __ldg(reinterpret_cast<const int4*>(idx) + 2 * v + 1);
+    const int32_t j[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h[q] = pack_f16_one(src, j[q]);
+    reinterpret_cast<uint4*>(dst)[v] = *reinterpret_cast<const uint4*>(h);
   }
+  if (blockIdx.x == 0)
+    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = pack_f16_one(src, idx[i]);
 }
 
 // Two-term fp16 split of an fp32 matrix for fp32-accurate products on the fp16 tensor cores:
@@ -1149,7 +1159,20 @@ __global__ void __launch_bounds__(256)
 gather_add_kernel(const float* __restrict__ src, const int32_t* __restrict__ inv, float* __restrict__ dst,
                   long long n) {
   pdl_sync();
-  for (long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+  // 4 arena elements per thread when inv / dst are 16-byte aligned (they are slices of 16-byte-aligned arena entries)
+  const bool vec = ((reinterpret_cast<uintptr_t>(inv) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const long long n4 = vec ? (n >> 2) : 0;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n4;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int4 i = __ldg(reinterpret_cast<const int4*>(inv) + v);
+    float4 d = reinterpret_cast<float4*>(dst)[v];
+    if (i.x >= 0) d.x += __ldg(src + i.x);
+    if (i.y >= 0) d.y += __ldg(src + i.y);
+    if (i.z >= 0) d.z += __ldg(src + i.z);
+    if (i.w >= 0) d.w += __ldg(src + i.w);
+    reinterpret_cast<float4*>(dst)[v] = d;
+  }
+  for (long long k = (n4 << 2) + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
        k += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int32_t i = __ldg(inv + k);
     if (i >= 0) dst[k] += __ldg(src + i);
@@ -1746,7 +1769,9 @@ extern "C" int mmdyn_colsum_f16(const void* x, float* out, int M, int N, int ld,
 
 extern "C" int mmdyn_pack_f16(const float* src, const int32_t* idx, void* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && idx && dst && n > 0, "pack_f16: bad arguments");
-  MMDYN_LAUNCH((pack_f16_kernel), grid_for(n), 256, 0, ST(stream), src, idx, reinterpret_cast<__half*>(dst), n);
+  MMDYN_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                "pack_f16: idx and dst must be 16-byte aligned");
+  MMDYN_LAUNCH((pack_f16_kernel), grid_for((n >> 3) + 1), 256, 0, ST(stream), src, idx, reinterpret_cast<__half*>(dst), n);
   LAUNCHED();
   return MMDYN_OK;
 }
@@ -1784,7 +1809,7 @@ extern "C" int mmdyn_unpack_add_f32(const float* src, const int32_t* idx, float*
 
 extern "C" int mmdyn_gather_add_f32(const float* src, const int32_t* inv, float* dst, long long n, void* stream) {
   MMDYN_REQUIRE(src && inv && dst && n > 0, "gather_add: bad arguments");
-  MMDYN_LAUNCH((gather_add_kernel), grid_for(n), 256, 0, ST(stream), src, inv, dst, n);
+  MMDYN_LAUNCH((gather_add_kernel), grid_for((n >> 2) + 1), 256, 0, ST(stream), src, inv, dst, n);
   LAUNCHED();
   return MMDYN_OK;
 }
