@@ -2,12 +2,13 @@
 //
 //   igemm_tma_kernel   : out[row, n] = sum_k A_gather[row, k] * W[n, k]        (forward + dgrad form), both operands by TMA:
 //                        weights as 2-D boxes, activations as one 4-D box (channel, x, y, image) per filter tap
+//   igemm_pair_kernel  : the same contraction with two 128-row tiles per weight stage (the layers bound by L2 -> SM bytes)
 //   igemm_patch_kernel : the merged 3x3-tap layers (4 sub-pixel phases of a stride-2 transposed conv as one GEMM): one
 //                        activation box per filter column serves three taps, live weight blocks resident in shared memory,
 //                        compile-time MMA schedule, BatchNorm statistics / BCE loss in the epilogue
 //   wgrad_tma_kernel   : dW[n, k] += sum_row Nat[row, n] * G_gather[row, k]    (weight gradients), both operands MN-major
 //   conv1_*            : the Cin = 3 first encoder layer on the fp32 NCHW input
-//   igemm_kernel / wgrad_kernel : cp.async (LDGSTS) gather variants for geometries TMA handles badly (8-channel pixels)
+//   igemm_kernel / wgrad_kernel : cp.async (LDGSTS) gather variants, the fallback for geometries without a TMA mode
 //
 // Mapping to the hardware (B200):
 //   * accumulators live in TMEM (tcgen05.alloc, 128 lanes x BLOCK_N fp32 columns, double-buffered);
@@ -15,7 +16,8 @@
 //     descriptors (128B / 64B swizzle or plain core matrices; K-major for igemm, MN-major for wgrad);
 //   * operands arrive by TMA (cp.async.bulk.tensor.{2d,4d}, mbarrier transaction counts), hardware zero fill for padding;
 //   * shared-memory rings decouple the TMA producer from the MMA issuer; tcgen05.commit frees ring slots and signals the
-//     epilogue warps, which read TMEM with tcgen05.ld and write global memory;
+//     epilogue warps, which read TMEM with tcgen05.ld and write global memory (256-bit stores for fp16 rows) and can
+//     reduce the BatchNorm statistics of what they store;
 //   * every kernel is launched with programmatic stream serialisation (pdl_sync, common.cuh).
 //
 // Reference semantics: nn.Conv2d / nn.ConvTranspose2d / nn.Linear in
