@@ -148,7 +148,8 @@ int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream);
  * replaces vae.py:198 forward and its weight gradient (the input needs no gradient).
  * W is the fp16 packed [32][64] matrix (K order (ci,kh,kw), 48 used).  out: fp16 NHWC (B,32,32,32).
  */
-int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, int n_img, void* stream);
+/* act_out (nullable): Swish of the fp16 output, same layout (vae.py:199) — saves the stand-alone activation pass */
+int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, void* act_out, int n_img, void* stream);
 int mmdyn_conv1_wgrad(const float* x_nchw, const void* dRaw, float* dW /*[32][48]*/, int n_img,
                       float scale, int row_splits, void* stream);
 

@@ -2023,7 +2023,7 @@ wgrad_tma_kernel(const __grid_constant__ mmdyn_wgrad_desc d, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __half* __restrict__ out,
-                 int n_img) {
+                 __half* __restrict__ act, int n_img) {
   pdl_sync();
   __shared__ __align__(1024) uint8_t a_tile[TILE_M * 128];
   __shared__ __align__(1024) uint8_t b_tile[32 * 128];
@@ -2100,8 +2100,20 @@ conv1_fwd_kernel(const float* __restrict__ x, const __half* __restrict__ Wp, __h
     float f[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[q]);
-    st_global_32B(o + c0, make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])),
-                  make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15])));
+    const uint4 u0 = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+    const uint4 u1 = make_uint4(pack_h2(f[8], f[9]), pack_h2(f[10], f[11]), pack_h2(f[12], f[13]), pack_h2(f[14], f[15]));
+    st_global_32B(o + c0, u0, u1);
+    if (act != nullptr) {
+      // Swish of the fp16-ROUNDED conv output (what the stand-alone mmdyn_bn_swish_fwd pass would read back): vae.py:199
+      const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      uint32_t a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&uu[q]));
+        a[q] = pack_h2(swishf_(v.x), swishf_(v.y));
+      }
+      st_global_32B(act + (o - out) + c0, make_uint4(a[0], a[1], a[2], a[3]), make_uint4(a[4], a[5], a[6], a[7]));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -2862,10 +2874,10 @@ extern "C" int mmdyn_wgrad(const mmdyn_wgrad_desc* d, void* stream) {
   }
 }
 
-extern "C" int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, int n_img, void* stream) {
+extern "C" int mmdyn_conv1_fwd(const float* x_nchw, const void* Wp, void* out, void* act_out, int n_img, void* stream) {
   MMDYN_REQUIRE(x_nchw && Wp && out && n_img > 0, "conv1_fwd: bad arguments");
   MMDYN_LAUNCH((conv1_fwd_kernel), n_img * 8, 128, 0, static_cast<cudaStream_t>(stream), 
-      x_nchw, reinterpret_cast<const __half*>(Wp), reinterpret_cast<__half*>(out), n_img);
+      x_nchw, reinterpret_cast<const __half*>(Wp), reinterpret_cast<__half*>(out), reinterpret_cast<__half*>(act_out), n_img);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   MMDYN_CHECK_CUDA(cudaGetLastError());
   return MMDYN_OK;

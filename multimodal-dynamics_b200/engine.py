@@ -467,9 +467,8 @@ class EncoderExec(_NetBase):
         B, nm = x.shape[0], len(masks)
         r = {"x": x, "B": B, "masks": masks}
         raw1 = alloc(key + ".raw1", (B, 32, 32, 32), F16)
-        ops.conv1_fwd(x, self.c1.Wf, raw1, B)
         act1 = alloc(key + ".act1", (B, 32, 32, 32), F16)
-        ops.bn_swish_fwd(raw1, None, act1, 1, B * 1024, 32)
+        ops.conv1_fwd(x, self.c1.Wf, raw1, B, act=act1)  # raw output + its Swish in one pass
         def conv_bn(pl, bn, a_in, shape, rows, name):
             # conv -> BatchNorm + Swish; the batch statistics come out of the GEMM epilogue when the batch is a whole
             # number of tiles (else mmdyn_bn_stats reads the raw output once more)

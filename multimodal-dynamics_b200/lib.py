@@ -72,7 +72,7 @@ SIGNATURES = {
     "mmdyn_init": ([_I], _I),
     "mmdyn_igemm": ([C.POINTER(IgemmDesc), _P], _I),
     "mmdyn_wgrad": ([C.POINTER(WgradDesc), _P], _I),
-    "mmdyn_conv1_fwd": ([_P, _P, _P, _I, _P], _I),
+    "mmdyn_conv1_fwd": ([_P, _P, _P, _P, _I, _P], _I),
     "mmdyn_conv1_wgrad": ([_P, _P, _P, _I, _F, _I, _P], _I),
     "mmdyn_bn_stats": ([_P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P], _I),

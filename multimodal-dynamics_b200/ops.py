@@ -198,9 +198,11 @@ def wgrad(geom, G, Nat, dW, n_img, scale=1.0, row_splits=1, ldw=None, nat_stride
         check(_L().mmdyn_wgrad(C.byref(d), _stream()), "mmdyn_wgrad")
 
 
-def conv1_fwd(x, Wp, out, n_img):
-    with _Timed("conv1_fwd", lambda: (2.0 * n_img * 1024 * 32 * 48, n_img * (3 * 64 * 64 * 4 + 1024 * 32 * 2.0))):
-        check(_L().mmdyn_conv1_fwd(_ptr(x), _ptr(Wp), _ptr(out), n_img, _stream()), "conv1_fwd")
+def conv1_fwd(x, Wp, out, n_img, act=None):
+    """act: optional second output, Swish(out) (the layer's activation, vae.py:199)"""
+    with _Timed("conv1_fwd", lambda: (2.0 * n_img * 1024 * 32 * 48,
+                                      n_img * (3 * 64 * 64 * 4 + 1024 * 32 * (4.0 if act is not None else 2.0)))):
+        check(_L().mmdyn_conv1_fwd(_ptr(x), _ptr(Wp), _ptr(out), _ptr(act), n_img, _stream()), "conv1_fwd")
 
 
 def conv1_wgrad(x, dRaw, dW, n_img, scale, row_splits):

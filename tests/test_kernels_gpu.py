@@ -269,12 +269,20 @@ def test_conv1_fwd_and_wgrad():
     x = torch.rand(n, 3, 64, 64)
     lp = plan.conv1_plan("c1", 0)
     out = torch.zeros(n, 32, 32, 32, dtype=torch.float16, device=DEV)
-    ops.conv1_fwd(x.to(DEV), packed(w, lp.idx_fwd), out, n)
+    act = torch.zeros_like(out)
+    ops.conv1_fwd(x.to(DEV), packed(w, lp.idx_fwd), out, n, act=act)
     torch.cuda.synchronize()
     xr = r16(x)
     wr = r16(w).requires_grad_(True)
     y = F.conv2d(xr, wr, stride=2, padding=1)
     assert rel_err(out.permute(0, 3, 1, 2), y) < 1e-3
+    # fused activation = Swish of the fp16 output, bit-identical to the stand-alone pass over it (vae.py:199)
+    act2 = torch.zeros_like(out)
+    ops.bn_swish_fwd(out, None, act2, 1, n * 1024, 32)
+    torch.cuda.synchronize()
+    assert torch.equal(act, act2)
+    o64 = out.double()
+    assert rel_err(act, o64 * torch.sigmoid(o64)) < 1e-3
     dy = torch.randn_like(y).half().double()
     y.backward(dy)
     dW = torch.zeros(32 * 48, dtype=torch.float32, device=DEV)
