@@ -297,3 +297,37 @@ def test_bench_dyn_shards_equal_the_global_parse():
         assert torch.equal(x[0], inp["model_input"][0][sl]) and torch.equal(x[2], inp["input_object_pose"][0][sl])
         assert torch.equal(t[0], tgt["target_output"][0][sl]) and torch.equal(t[1], tgt["target_output"][1][sl])
         assert torch.equal(t[2], tgt["target_object_pose"][0][sl]), r  # bare roll; last rank wraps to row 0
+
+
+def test_packer_stages_follow_the_order_a_step_needs_them():
+    """engine.ModelPacker lays the fp16 weight copies out in three contiguous stages — forward copies of the encoder-side
+    networks, forward copies of the decoders, data-gradient copies — so that a staged refresh can pack the later stages on
+    a side stream.  Views must tile the arena without overlap, 16-byte aligned."""
+    from types import SimpleNamespace
+    from mmdyn_b200 import engine, plan
+
+    def layer(nf, nd, name):
+        mk = lambda n: torch.arange(n, dtype=torch.int32).view(8, -1) if n else None
+        return SimpleNamespace(idx_fwd=mk(nf), idx_dgrad=mk(nd), bias_idx=None, lp=SimpleNamespace(name=name),
+                               Wf=None, Wd=None, bias=None)
+
+    enc = SimpleNamespace(layers=[layer(64, 128, "e0"), layer(256, 0, "e1")])
+    dec = object.__new__(engine.DecoderExec)
+    dec.layers = [layer(512, 1024, "d0")]
+    pose = SimpleNamespace(layers=[layer(192, 192, "p0")])
+    pk = engine.ModelPacker([enc, dec, pose], torch.device("cpu"))
+    s0, s1 = 64 + 256 + 192, 64 + 256 + 192 + 512
+    assert pk.stage_off == [0, s0, s1, s1 + 128 + 1024 + 192]
+    assert pk.idx.numel() == pk.W.numel() == pk.stage_off[-1]
+    spans = sorted((o, o + sh[0] * sh[1], attr, pl.lp.name) for pl, attr, o, sh in pk.slots)
+    assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] == pk.stage_off[-1]
+    assert all(o % 8 == 0 for o, *_ in spans)
+    for o, e, attr, name in spans:
+        stage = 2 if attr == "Wd" else (1 if name == "d0" else 0)
+        assert pk.stage_off[stage] <= o and e <= pk.stage_off[stage + 1], (name, attr)
+    assert dec.layers[0].Wf.shape == (8, 64) and dec.layers[0].Wf.data_ptr() == pk.W[s0:].data_ptr()
+    # images per GEMM tile (fused BatchNorm statistics need whole tiles per group): same rule as the launcher
+    assert plan.tile_images(plan.conv_s2_plan("c2", 0, 32, 64, 32).fwd) == 1      # 16 x 8 pixels of one image
+    assert plan.tile_images(plan.conv_s2_plan("c3", 0, 64, 128, 16).fwd) == 2     # 8 x 8 pixels x 2 images
+    assert plan.tile_images(plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8).fwd) == 128  # one pixel x 128 images
+    assert plan.tile_images(plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5).fwd) == 128
