@@ -187,6 +187,13 @@ int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const float* mean_
 int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
                        void* dU, float* dgamma, float* dbeta, float* coef_scratch, int G,
                        int rows_per_group, int C, float grad_unscale, void* stream);
+/* the same pass with dX written to a second buffer instead of over dU: rows are image rows of 2^row_w_log2 pixels, stored
+ * with one extra pixel on each side, [rows / 2^w][2^w + 2][C] (the caller zeroes the buffer once; the border is never
+ * written) — the layout in which the k4/s2 data and weight gradients of the producing layer read their 4 x-taps as two
+ * 128-byte pixel pairs (plan.deconv_s2_plan, mmdyn_igemm_desc.s_in_x) */
+int mmdyn_bn_bwd_apply_padded(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
+                              const void* dU, void* dX_padded, int row_w_log2, float* dgamma, float* dbeta,
+                              int G, int rows_per_group, int C, float grad_unscale, void* stream);
 
 /* --- fc tail: bias + Swish + Dropout mask (vae.py:210-214) ------------------------------------
  * raw [B][C] fp32 (igemm output incl. bias); for each of n_masks masks (fp32, values 0 or 1/(1-p),

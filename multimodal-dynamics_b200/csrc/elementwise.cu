@@ -611,7 +611,8 @@ bn_swish_bwd_reduce_bulk_kernel(const __half* __restrict__ x, const float* __res
 template <int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__ coef, __half* __restrict__ dU,
-                         int rows_per_group, int C, int rows_per_chunk, BnBwdFinalArgs fin) {
+                         int rows_per_group, int C, int rows_per_chunk, BnBwdFinalArgs fin,
+                         __half* __restrict__ out_pad, int lw) {
   pdl_sync();
   BS_PROLOGUE(2, STAGES);
   st.src[0] = reinterpret_cast<const uint8_t*>(x + base);
@@ -658,6 +659,9 @@ bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__
     const uint8_t* sx = bs_smem + (s * 2) * BS_STAGE_BYTES + vec * 16;
     const uint8_t* sd = sx + BS_STAGE_BYTES;
     __half* out = dU + base + static_cast<long long>(it) * rps * C + vec * 8;  // in place: rows of this stage only
+    // out_pad: dX goes to a second buffer whose image rows of 2^lw pixels carry one extra (zero, never written) pixel on
+    // each side — the layout the stride-2 data / weight gradient kernels read as 128-byte pixel pairs (plan.deconv_s2_plan)
+    const long long row0 = static_cast<long long>(g) * rows_per_group + r_begin + static_cast<long long>(it) * rps;
 #pragma unroll
     for (int k = 0; k < BS_ROWS_PER_THREAD; ++k) {
       const int row = rl + k * row_lanes;
@@ -670,7 +674,12 @@ bn_bwd_apply_bulk_kernel(const __half* __restrict__ x, const float* __restrict__
           const float du = fd[i] * swish_gradf_(fmaf(ka[i], fx[i], ks[i]));
           fd[i] = fmaf(ka[i], du, fmaf(kb[i], fx[i], kc[i]));
         }
-        *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = pack8(fd);
+        if (out_pad != nullptr) {
+          const long long R = row0 + row;
+          *reinterpret_cast<uint4*>(out_pad + (R + ((R >> lw) << 1) + 1) * C + vec * 8) = pack8(fd);
+        } else {
+          *reinterpret_cast<uint4*>(out + static_cast<long long>(row) * C) = pack8(fd);
+        }
       }
     }
     __syncthreads();
@@ -1532,6 +1541,23 @@ extern "C" int mmdyn_bn_swish_bwd_reduce(const void* x, const float* ab, const f
   return MMDYN_OK;
 }
 
+extern "C" int mmdyn_bn_bwd_apply_padded(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
+                                         const void* dU, void* dX_padded, int row_w_log2, float* dgamma, float* dbeta,
+                                         int G, int rows_per_group, int C, float grad_unscale, void* stream) {
+  MMDYN_REQUIRE(x && ab && mean_invstd && sums2 && dU && dX_padded && G > 0 && C % 8 == 0 && row_w_log2 >= 1 &&
+                    row_w_log2 <= 12 && rows_per_group % (1 << row_w_log2) == 0,
+                "bn_bwd_apply_padded: bad arguments (rows_per_group must be whole image rows of 2^row_w_log2 pixels)");
+  MMDYN_REQUIRE(bulk_ok(C), "bn_bwd_apply_padded: C=%d unsupported", C);
+  int rpc;
+  const int chunks = bulk_chunking(rows_per_group, G, C, 2, &rpc);
+  BnBwdFinalArgs fin = {ab, mean_invstd, sums2, dgamma, dbeta, 1.0f / static_cast<float>(rows_per_group), grad_unscale};
+  MMDYN_LAUNCH((bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>), dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream),
+          reinterpret_cast<const __half*>(x), nullptr, const_cast<__half*>(reinterpret_cast<const __half*>(dU)), rows_per_group, C, rpc,
+          fin, reinterpret_cast<__half*>(dX_padded), row_w_log2);
+  LAUNCHED();
+  return MMDYN_OK;
+}
+
 extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* mean_invstd, const float* sums2,
                                   void* dU, float* dgamma, float* dbeta, float* coef_scratch, int G,
                                   int rows_per_group, int C, float grad_unscale, void* stream) {
@@ -1544,7 +1570,8 @@ extern "C" int mmdyn_bn_bwd_apply(const void* x, const float* ab, const float* m
     BnBwdFinalArgs fin = {ab, mean_invstd, sums2, dgamma, dbeta, 1.0f / static_cast<float>(rows_per_group),
                           grad_unscale};
     MMDYN_LAUNCH((bn_bwd_apply_bulk_kernel<BS_STAGES_2IN>), dim3(chunks, G), RED_THREADS, 2 * BS_STAGES_2IN * BS_STAGE_BYTES, ST(stream), 
-            reinterpret_cast<const __half*>(x), nullptr, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc, fin);
+            reinterpret_cast<const __half*>(x), nullptr, reinterpret_cast<__half*>(dU), rows_per_group, C, rpc, fin,
+            static_cast<__half*>(nullptr), 0);
     LAUNCHED();
     return MMDYN_OK;
   }

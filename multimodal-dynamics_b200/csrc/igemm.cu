@@ -2695,7 +2695,7 @@ extern "C" int mmdyn_igemm(const mmdyn_igemm_desc* d, void* stream) {
         (pair_mode == 2 || g.total_tiles >= 4 * g_sm_count) && d->ntaps <= 32) {
       if (a_mode == 0 && d->block_n == 128) return launch_igemm_pair<128, 0>(d, tmA, tm, g, st);
       if (a_mode == 0 && d->block_n == 256) return launch_igemm_pair<256, 0>(d, tmA, tm, g, st);
-      if (a_mode == 0 && d->block_n == 64 && pair_mode >= 2) return launch_igemm_pair<64, 0>(d, tmA, tm, g, st);
+      if (a_mode == 0 && d->block_n == 64) return launch_igemm_pair<64, 0>(d, tmA, tm, g, st);
       if (a_mode == 1 && d->block_n == 64 && !g.pixel_major && (pair_mode >= 2 || pair_mode == 1))
         return launch_igemm_pair<64, 1>(d, tmA, tm, g, st);
     }

@@ -421,6 +421,7 @@ def _wgrad_into(pl, G, Nat, n_img, arena, alloc, key, scale, gp=None):
 
 
 FUSE_STATS = os.environ.get("MMDYN_NO_FUSED_STATS") is None  # BatchNorm sums from the producing GEMM's epilogue
+PAIR_GRADS = os.environ.get("MMDYN_NO_PAIR_GRADS") is None  # deconv3's gradient stored with an x border, read as pixel pairs
 STAGED_PACK = os.environ.get("MMDYN_NO_STAGED_PACK") is None  # weight packing in three stages, two of them off the critical path
 
 
@@ -460,10 +461,16 @@ class _BN:
     def alloc_bwd(self, G, alloc, key):
         return alloc(key + ".sums2", (G, self.C, 2), F32, zero="step"), alloc(key + ".coef", (G, self.C, 4), F32)
 
-    def run_bwd(self, raw, ab, mi, dAct, Gc, rows, st, g0, unscale):
+    def run_bwd(self, raw, ab, mi, dAct, Gc, rows, st, g0, unscale, padded=None):
+        """padded = (buffer [rows / 2^w][2^w + 2][C] with zero borders, w): dRaw goes there instead of over dAct"""
         net, C = self.net, self.C
         sums2, coef = st[0][g0:g0 + Gc], st[1][g0:g0 + Gc]
         ops.bn_swish_bwd_reduce(raw, ab[g0:g0 + Gc], mi[g0:g0 + Gc], dAct, sums2, Gc, rows, C)
+        if padded is not None:
+            ops.bn_bwd_apply_padded(raw, ab[g0:g0 + Gc], mi[g0:g0 + Gc], sums2, dAct, padded[0], padded[1],
+                                    net.pview(self.name + ".weight", True), net.pview(self.name + ".bias", True), Gc, rows, C,
+                                    unscale)
+            return padded[0]
         ops.bn_bwd_apply(raw, ab[g0:g0 + Gc], mi[g0:g0 + Gc], sums2, dAct, net.pview(self.name + ".weight", True),
                          net.pview(self.name + ".bias", True), coef, Gc, rows, C, unscale)
         return dAct  # now dRaw
@@ -604,7 +611,11 @@ class DecoderExec(_NetBase):
         self.up_rows = torch.from_numpy(np.ascontiguousarray(plan.nhwc_perm(256, 5, 5)).astype(np.int32)).to(device)
         self.d1 = self._pl(plan.deconv_k4s1p0_plan("deconv1", self.off("hallucinate.0.weight"), 256, 128, 5))
         self.d2 = self._pl(plan.deconv_s2_plan("deconv2", self.off("hallucinate.3.weight"), 128, 64, 8))
-        self.d3 = self._pl(plan.deconv_s2_plan("deconv3", self.off("hallucinate.6.weight"), 64, 32, 16))
+        lp3 = plan.deconv_s2_plan("deconv3", self.off("hallucinate.6.weight"), 64, 32, 16)
+        self.pair_grads = bool(PAIR_GRADS and "pair_dgrad" in lp3.extra)
+        if self.pair_grads:  # the backward reads deconv3's output gradient as 128-byte pixel pairs (same packed weights)
+            lp3.dgrad, lp3.wgrad = lp3.extra["pair_dgrad"], lp3.extra["pair_wgrad"]
+        self.d3 = self._pl(lp3)
         self.d4 = self._pl(plan.deconv_out_plan("deconv4", self.off("hallucinate.9.weight"), 32, 3, 32))
         self.bn1, self.bn2, self.bn3 = _BN(self, "hallucinate.1", 128), _BN(self, "hallucinate.4", 64), _BN(self, "hallucinate.7", 32)
 
@@ -684,6 +695,9 @@ class DecoderExec(_NetBase):
         arena, G, B = self.arena, r["G"], r["B"]
         R = G * B
         g3 = alloc(key + ".g3", (R, 32, 32, 32), F16)
+        # deconv3's output gradient as 128-byte pixel pairs: image rows with one zero pixel on each side (zeroed once: the
+        # workspace hands out zeroed buffers, the BatchNorm backward writes the 32 inner pixels only)
+        g3p = alloc(key + ".g3p", (R, 32, 34, 32), F16, zero=not isinstance(alloc, Workspace)) if self.pair_grads else None
         g2 = alloc(key + ".g2", (R, 16, 16, 64), F16)
         g1 = alloc(key + ".g1", (R, 8, 8, 128), F16)
         g0_ = alloc(key + ".g0", (R, 5, 5, 256), F16)
@@ -693,9 +707,10 @@ class DecoderExec(_NetBase):
             sl, n = slice(g0 * B, (g0 + Gc) * B), Gc * B
             _wgrad_into(self.d4, dl8[sl], r["act3"][sl], n, arena, alloc, key + ".dW_d4", unscale, gp)
             _ig(self.d4, "dgrad", dl8[sl], g3[sl], n)
-            self.bn3.run_bwd(r["raw3"][sl], r["bn3"][0], r["bn3"][1], g3[sl], Gc, B * 1024, b3, g0, unscale)
-            _wgrad_into(self.d3, g3[sl], r["act2"][sl], n, arena, alloc, key + ".dW_d3", unscale, gp)
-            _ig(self.d3, "dgrad", g3[sl], g2[sl], n)
+            d3g = self.bn3.run_bwd(r["raw3"][sl], r["bn3"][0], r["bn3"][1], g3[sl], Gc, B * 1024, b3, g0, unscale,
+                                   padded=(g3p[sl], 5) if self.pair_grads else None)
+            _wgrad_into(self.d3, d3g, r["act2"][sl], n, arena, alloc, key + ".dW_d3", unscale, gp)
+            _ig(self.d3, "dgrad", d3g, g2[sl], n)
             self.bn2.run_bwd(r["raw2"][sl], r["bn2"][0], r["bn2"][1], g2[sl], Gc, B * 256, b2, g0, unscale)
             _wgrad_into(self.d2, g2[sl], r["act1"][sl], n, arena, alloc, key + ".dW_d2", unscale, gp)
             _ig(self.d2, "dgrad", g2[sl], g1[sl], n)

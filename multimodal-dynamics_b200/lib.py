@@ -80,6 +80,7 @@ SIGNATURES = {
     "mmdyn_bn_swish_fwd": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_swish_bwd_reduce": ([_P, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_bn_bwd_apply": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P], _I),
+    "mmdyn_bn_bwd_apply_padded": ([_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _F, _P], _I),
     "mmdyn_swish_dropout_fwd": ([_P, C.POINTER(_P), _P, _I, _I, _I, _P], _I),
     "mmdyn_swish_dropout_bwd": ([_P, C.POINTER(_P), _P, _P, _I, _I, _I, _P], _I),
     "mmdyn_poe_fwd": ([C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P], _I),

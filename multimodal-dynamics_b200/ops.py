@@ -250,6 +250,14 @@ def bn_bwd_apply(x, ab, mean_invstd, sums2, dU, dgamma, dbeta, coef, G, rows, Cc
                                       _ptr(dbeta), _ptr(coef), G, rows, Cch, unscale, _stream()), "bn_bwd_apply")
 
 
+def bn_bwd_apply_padded(x, ab, mean_invstd, sums2, dU, dX_padded, row_w_log2, dgamma, dbeta, G, rows, Cch, unscale):
+    """dX into [rows / 2^w][2^w + 2][C] (one zero pixel on each side of every image row) instead of over dU"""
+    with _Timed("bn_bwd_apply", lambda: (0.0, G * rows * Cch * 6.0)):
+        check(_L().mmdyn_bn_bwd_apply_padded(_ptr(x), _ptr(ab), _ptr(mean_invstd), _ptr(sums2), _ptr(dU), _ptr(dX_padded),
+                                             row_w_log2, _ptr(dgamma), _ptr(dbeta), G, rows, Cch, unscale, _stream()),
+              "bn_bwd_apply_padded")
+
+
 def swish_dropout_fwd(raw, masks, h, B, Cch):
     n = len(masks)
     with _Timed("swish_dropout_fwd", None):

@@ -281,7 +281,22 @@ def deconv_s2_plan(name, w_off, Cin, Cout, H):
     ci_, t_, co_ = np.meshgrid(np.arange(Cin), np.arange(16), np.arange(Cout), indexing="ij")
     idx_dg = widx(ci_, co_, t_ // 4, t_ % 4).reshape(Cin, 16 * Cout).astype(np.int32)
     wg = WgradGeom(P=H * H, OXv=H, IH=Ho, IW=Ho, Cg=Cout, s_in=2, tap_dy=dy, tap_dx=dx, Cn=Cin)
-    return LayerPlan(name, "deconv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra={"macs": H * H * Cout * Cin * 16})
+    extra = {"macs": H * H * Cout * Cin * 16}
+    if Cout == 32 and H >= 16 and (H & (H - 1)) == 0:
+        # 32-channel gradient (64-byte pixels): the same contraction over 128-byte pixel PAIRS.  With the gradient stored
+        # with one extra pixel on each side of every image row ([img][Ho][Ho + 2][32], mmdyn_bn_bwd_apply_padded) the four
+        # x-taps kw = 0..3 of output pixel x are padded pixels 2x .. 2x + 3 = pairs x and x + 1: 8 taps (kh, pair) of 64
+        # "channels" instead of 16 taps of 32 — half the TMA row requests for the same bytes, and the K order (kh, kw, c)
+        # of the packed weights is unchanged.  Rows above / below the image come from the TMA zero fill as before.
+        pdy = [kh - 1 for kh in range(4) for _ in range(2)]
+        pdx = [p for _ in range(4) for p in range(2)]
+        row, img = (Ho + 2) * Cout, Ho * (Ho + 2) * Cout
+        extra["pair_dgrad"] = GemmGeom(P=H * H, OXv=H, IH=Ho, IW=H + 1, Cin=2 * Cout, s_in=2, s_in_x=1, tap_dy=[pdy],
+                                       tap_dx=[pdx], N=Cin, OH=H, OW=H, s_out=1, off_y=[0], off_x=[0], ldc=Cin,
+                                       a_pix_stride=2 * Cout, a_row_stride=row, a_img_stride=img)
+        extra["pair_wgrad"] = WgradGeom(P=H * H, OXv=H, IH=Ho, IW=H + 1, Cg=2 * Cout, s_in=2, s_in_x=1, tap_dy=pdy,
+                                        tap_dx=pdx, Cn=Cin, g_pix_stride=2 * Cout, g_row_stride=row, g_img_stride=img)
+    return LayerPlan(name, "deconv_s2", fwd, idx_fwd, dg, idx_dg, wg, idx_dg, extra=extra)
 
 
 def deconv_out_plan(name, w_off, Cin=32, Cout=3, H=32):

@@ -126,6 +126,53 @@ def test_conv4_k4s1p0(n):
     check_conv_layer(plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), w, x, 1, 0, False)
 
 
+@pytest.mark.parametrize("n", [3, 320])
+def test_deconv3_pixel_pair_gradients(n):
+    """deconv3's data / weight gradients over 128-byte pixel pairs of the x-padded gradient (plan.deconv_s2_plan
+    extra["pair_*"], mmdyn_bn_bwd_apply_padded's layout); n = 320 selects the tile-pair kernel"""
+    ops = _ops()
+    torch.manual_seed(43)
+    Cin, Cout, H = 64, 32, 16
+    w = torch.randn(Cin, Cout, 4, 4) * 0.05
+    x = torch.randn(n, Cin, H, H)
+    lp = plan.deconv_s2_plan("d3", 0, Cin, Cout, H)
+    xr, wr, y, dy = conv_case(lp, w, x, 2, 1, True, n)
+    gpad = F.pad(dy.float(), (1, 1))                                   # one zero pixel on each side of every image row
+    dA = nhwc16(gpad)
+    assert tuple(dA.shape) == (n, 2 * H, 2 * H + 2, Cout)
+    dx = run_fwd(lp.extra["pair_dgrad"], lp.idx_dgrad, w, dA, n)
+    assert rel_err(dx.permute(0, 3, 1, 2), xr.grad) < 1e-3
+    wg = lp.extra["pair_wgrad"]
+    dWp = torch.zeros(wg.Cn, wg.K, dtype=torch.float32, device=DEV)
+    ops.wgrad(wg, dA, nhwc16(x), dWp, n, scale=0.5, row_splits=plan.choose_row_splits(wg, n))
+    dW = torch.zeros(w.numel(), dtype=torch.float32, device=DEV)
+    ops.unpack_add_f32(dWp, torch.from_numpy(lp.idx_wgrad).to(DEV), dW)
+    torch.cuda.synchronize()
+    assert rel_err(dW, 0.5 * wr.grad.reshape(-1)) < 2e-5
+
+
+def test_bn_bwd_apply_padded_matches_in_place():
+    ops = _ops()
+    torch.manual_seed(44)
+    G, n, C, W = 2, 3, 32, 32
+    rows = n * W * W
+    x = torch.randn(G * rows, C, device=DEV).half()
+    dy = torch.randn(G * rows, C, device=DEV).half()
+    ab = torch.randn(G, C, 2, device=DEV)
+    mi = torch.rand(G, C, 2, device=DEV) + 0.5
+    sums2 = torch.randn(G, C, 2, device=DEV) * 10
+    coef = torch.zeros(G, C, 4, device=DEV)
+    dg1, db1, dg2, db2 = (torch.zeros(C, device=DEV) for _ in range(4))
+    ref = dy.clone()
+    ops.bn_bwd_apply(x, ab, mi, sums2, ref, dg1, db1, coef, G, rows, C, 0.25)
+    out = torch.full((G * n * W, W + 2, C), 7.0, dtype=torch.float16, device=DEV)
+    ops.bn_bwd_apply_padded(x, ab, mi, sums2, dy, out, 5, dg2, db2, G, rows, C, 0.25)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, 1:-1].reshape(-1, C), ref)               # bit-identical values, shifted by one pixel
+    assert (out[:, 0] == 7.0).all() and (out[:, -1] == 7.0).all()      # the border is never written
+    assert torch.equal(dg1, dg2) and torch.equal(db1, db2)
+
+
 def test_pair_kernel_sizes():
     """Enough tiles for igemm_pair_kernel (two 128-row tiles per weight stage, csrc/igemm.cu): the 5x5 -> 8x8 deconv
     forward (N = 128) and data gradient (N = 256) with pixel-major tile pairs, and a Cin = 32 stride-2 conv (N = 64,

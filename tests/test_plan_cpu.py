@@ -85,6 +85,25 @@ def test_deconv_s2(Cin, Cout, H):
     check_layer(plan.deconv_s2_plan("d", 0, Cin, Cout, H), w, x, y, torch.randn_like(y), 2, 1, True)
 
 
+def test_deconv_s2_pixel_pair_gradients():
+    """deconv3's backward over 128-byte pixel pairs of the x-padded gradient: same packed weights, same results"""
+    Cin, Cout, H = 64, 32, 16
+    w = torch.randn(Cin, Cout, 4, 4).requires_grad_(True)
+    x = torch.randn(2, Cin, H, H).requires_grad_(True)
+    y = F.conv_transpose2d(x, w, stride=2, padding=1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    lp = plan.deconv_s2_plan("d3", 0, Cin, Cout, H)
+    flat = w.detach().double().reshape(-1).numpy()
+    g = np.zeros((2, 2 * H, 2 * H + 2, Cout))
+    g[:, :, 1:-1] = nhwc(dy)
+    dx = emul.igemm(lp.extra["pair_dgrad"], g, emul.pack(flat, lp.idx_dgrad), 2)
+    np.testing.assert_allclose(dx, nhwc(x.grad), atol=1e-9)
+    dWp = emul.wgrad(lp.extra["pair_wgrad"], g, nhwc(x.detach()).reshape(2, -1, Cin), 2)
+    dW = emul.unpack_add(dWp, lp.idx_wgrad, flat.size)
+    np.testing.assert_allclose(dW, w.grad.reshape(-1).numpy(), atol=1e-8)
+
+
 def test_deconv_out():
     w = torch.randn(32, 3, 4, 4)
     x = torch.randn(2, 32, 8, 8)

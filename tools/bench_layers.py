@@ -29,8 +29,8 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 
-def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, stats_c=0, bce=False):
-    geom = lp.fwd if which == "fwd" else lp.dgrad
+def run(name, lp, which, n_img, in_shape, out_shape, out_dtype=torch.float16, stats_c=0, bce=False, geom=None):
+    geom = geom or (lp.fwd if which == "fwd" else lp.dgrad)
     idx = lp.idx_fwd if which == "fwd" else lp.idx_dgrad
     A = torch.randn(n_img, *in_shape, device=DEV).half()
     W = (torch.randn(idx.shape, device=DEV) * 0.05).half()
@@ -89,6 +89,10 @@ CASES = {
     "conv4.wgrad": lambda R: run_wgrad("conv4.wgrad", plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), R // 4, (8, 8, 128), (5, 5, 256)),
     "deconv4.dgrad": lambda R: run("deconv4.dgrad", plan.deconv_out_plan("d4", 0), "dgrad", R, (66, 66, 4), (32, 32, 32)),
     "deconv2.dgrad": lambda R: run("deconv2.dgrad", plan.deconv_s2_plan("d2", 0, 128, 64, 8), "dgrad", R, (16, 16, 64), (8, 8, 128)),
+    "deconv3.dgrad.pairs": lambda R: run("deconv3.dgrad.pr", plan.deconv_s2_plan("d3", 0, 64, 32, 16), "dgrad", R, (32, 34, 32), (16, 16, 64),
+                                         geom=plan.deconv_s2_plan("d3", 0, 64, 32, 16).extra["pair_dgrad"]),
+    "deconv3.wgrad.pairs": lambda R: run_wgrad("deconv3.wgrad.pr", plan.deconv_s2_plan("d3", 0, 64, 32, 16), R, (32, 34, 32), (16, 16, 64),
+                                               wg=plan.deconv_s2_plan("d3", 0, 64, 32, 16).extra["pair_wgrad"]),
     "deconv1.dgrad": lambda R: run("deconv1.dgrad", plan.deconv_k4s1p0_plan("d1", 0, 256, 128, 5), "dgrad", R, (8, 8, 128), (5, 5, 256)),
     "conv4.dgrad": lambda R: run("conv4.dgrad", plan.conv_k4s1p0_plan("c4", 0, 128, 256, 8), "dgrad", R // 4, (5, 5, 256), (8, 8, 128)),
 }
